@@ -1,0 +1,157 @@
+/*
+ * openimpala_b200.h -- C-ABI of the B200-native TortuosityHypre path.
+ *
+ * The reference (kramergroup/openImpala) has no FFI table for this path: the
+ * seam is the C++ class surface OpenImpala::TortuosityHypre /
+ * OpenImpala::VolumeFraction plus the two Fortran bind(c) kernels.  Every entry
+ * point below names the reference interface it replaces (file:line relative to
+ * the reference tree).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - fields are dense boxes, x fastest, z slowest (AMReX/Fortran order,
+ *     src/io/TiffReader.cpp:130-134, src/io/RawReader.cpp:310-313);
+ *   - one handle = one (image, phase, direction) solve, like one
+ *     TortuosityHypre object (src/props/TortuosityHypre.H:68-80);
+ *   - a handle owns one z-slab [z_begin, z_begin+nz_local) of the global box;
+ *     with n_ranks == 1 the slab is the whole box;
+ *   - every function returns OI_OK (0) or a negative oi_status; text of the
+ *     last failure on the calling thread: oi_last_error();
+ *   - not thread-safe per handle; no exceptions cross the boundary;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with OI_ERR_CUDA.
+ */
+#ifndef OPENIMPALA_B200_H
+#define OPENIMPALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OI_B200_VERSION 100
+
+typedef enum oi_status {
+    OI_OK = 0,
+    OI_ERR_INVALID = -1,   /* bad argument / call order          */
+    OI_ERR_CUDA = -2,      /* CUDA runtime failure or no device  */
+    OI_ERR_NCCL = -3,      /* NCCL failure / library not found   */
+    OI_ERR_NOMEM = -4
+} oi_status;
+
+/* OpenImpala::Direction, src/props/Tortuosity.H:9-13 */
+typedef enum oi_direction { OI_DIR_X = 0, OI_DIR_Y = 1, OI_DIR_Z = 2 } oi_direction;
+
+/* Preconditioner selection (the reference hard-wires FlexGMRES + SMG,
+ * src/props/TortuosityHypre.cpp:664-678; every SolverType maps to PCG here). */
+typedef enum oi_precond { OI_PRECOND_MG = 0, OI_PRECOND_JACOBI = 1 } oi_precond;
+
+typedef struct oi_params {
+    int32_t nx, ny, nz;        /* global box, cells (Geometry::Domain)            */
+    int32_t z_begin, nz_local; /* this rank's z-slab                              */
+    int32_t direction;         /* oi_direction                                    */
+    int32_t phase_id;          /* m_phase, TortuosityHypre.cpp:115                */
+    double  vlo, vhi;          /* Dirichlet values, TortuosityHypre.cpp:118       */
+    double  dx[3];             /* Geometry::CellSize (1,1,1 in both drivers)      */
+    double  eps;               /* hypre.eps,  default 1e-9  (TortuosityHypre.cpp:142) */
+    int32_t maxiter;           /* hypre.maxiter, default 200 (TortuosityHypre.cpp:143) */
+    int32_t verbose;
+    int32_t device;            /* CUDA device ordinal, -1 = current               */
+    int32_t precond;           /* oi_precond                                      */
+    int32_t mg_degree;         /* smoother polynomial degree per leg, 0 = default */
+    int32_t stencil_variant;   /* 0 = z-plane staged (default), 1 = simple gather  */
+    int32_t flux_polish;       /* 1: keep iterating (<= maxiter) until the flux
+                                  imbalance is 10x inside the reference's 1e-6
+                                  gate (TortuosityHypre.cpp:794-803); 0: stop on
+                                  the residual rule alone                          */
+    int32_t rank, n_ranks;     /* z-slab decomposition                             */
+    const void* nccl_unique_id;/* 128-byte ncclUniqueId when n_ranks > 1, else NULL */
+} oi_params;
+
+typedef struct oi_solve_info {
+    int32_t iterations;        /* getSolverIterations(), TortuosityHypre.H:116     */
+    int32_t converged;         /* getSolverConverged(),  TortuosityHypre.H:114     */
+    double  rel_residual;      /* getFinalRelativeResidualNorm(), :115             */
+    double  b_norm;            /* ||b||_2 of the un-eliminated rhs (stop rule)     */
+    double  solve_ms;          /* device time of the Krylov loop                   */
+    double  setup_ms;          /* coarse-operator build                            */
+} oi_solve_info;
+
+typedef struct oi_solver oi_solver; /* opaque */
+
+int         oi_version(void);
+const char* oi_last_error(void);
+int         oi_device_count(int* count);
+void        oi_default_params(oi_params* p);
+
+/* ---- VolumeFraction::value, src/props/VolumeFraction.cpp:22-66 ---------- */
+/* Count cells == phase in a host field (copied to the device, counted there).
+ * total_count is n (Sum of tile numPts, VolumeFraction.cpp:48). */
+int oi_count_phase_i32(const int32_t* host_field, int64_t n, int32_t phase,
+                       int64_t* phase_count, int64_t* total_count);
+int oi_count_phase_u8(const uint8_t* host_field, int64_t n, int32_t phase,
+                      int64_t* phase_count, int64_t* total_count);
+
+/* ---- TortuosityHypre ctor, src/props/TortuosityHypre.cpp:100-191 -------- */
+int oi_create(oi_solver** out, const oi_params* p);
+int oi_destroy(oi_solver* h);
+
+/* Phase field of the local slab (m_mf_phase deep copy, TortuosityHypre.cpp:132).
+ * Host buffers hold nx*ny*nz_local values; the *_device variant takes a device
+ * pointer to uint8 values already resident in HBM. */
+int oi_set_phase_i32(oi_solver* h, const int32_t* host_phase);
+int oi_set_phase_u8(oi_solver* h, const uint8_t* host_phase);
+int oi_set_phase_device_u8(oi_solver* h, const void* device_phase);
+
+/* Global counts over the resident phase field (VolumeFraction.cpp:22-66). */
+int oi_volume_fraction(oi_solver* h, int64_t* phase_count, int64_t* total_count);
+
+/* tortuosity_remspot, src/props/Tortuosity_filcc.F90:88-177 (optional filter,
+ * tortuosity.remspot_passes, TortuosityHypre.cpp:248-292). */
+int oi_remspot(oi_solver* h, int32_t passes);
+
+/* generateActivityMask + parallelFloodFill, TortuosityHypre.cpp:394-558 /
+ * :297-389, then setupMatrixEquation / tortuosity_fillmtx
+ * (TortuosityHypre.cpp:562-649, TortuosityHypreFill.F90:44-314) in matrix-free
+ * form: per-cell connectivity byte, rhs norm and initial guess.
+ * n_active = global sum(mask) (TortuosityHypre.cpp:549). */
+int oi_build_mask(oi_solver* h, int64_t* n_active);
+
+/* solve(), TortuosityHypre.cpp:654-756 */
+int oi_solve(oi_solver* h, oi_solve_info* info);
+
+/* global_fluxes(), TortuosityHypre.cpp:1000-1134 (already x face area). */
+int oi_fluxes(oi_solver* h, double* flux_in, double* flux_out,
+              int64_t* n_active_in, int64_t* n_active_out);
+
+/* checkMatrixProperties(), TortuosityHypre.cpp:896-982: device-side check of the
+ * same invariants on the matrix-free rows.  ok = 1 when all pass (global). */
+int oi_check_matrix_properties(oi_solver* h, int32_t* ok);
+
+/* ---- read-backs / test hooks (local slab, nx*ny*nz_local values) -------- */
+int oi_get_mask_u8(oi_solver* h, uint8_t* host_mask);      /* m_mf_active_mask  */
+int oi_get_solution(oi_solver* h, double* host_x);          /* HYPRE m_x         */
+int oi_set_solution(oi_solver* h, const double* host_x);
+int oi_get_initial_guess(oi_solver* h, double* host_x0);    /* xinit, F90:233-262 */
+int oi_get_rhs(oi_solver* h, double* host_rhs);             /* rhs,   F90:115-225 */
+/* a[7*m+s], slot order C,-x,+x,-y,+y,-z,+z (TortuosityHypreFill.F90:20-26):
+ * the rows tortuosity_fillmtx would have produced, rebuilt from the
+ * connectivity bytes. */
+int oi_get_matrix_rows(oi_solver* h, double* host_a7);
+/* y = A_elim * x on the active interior unknowns (0 elsewhere). */
+int oi_apply_operator(oi_solver* h, const double* host_x, double* host_y);
+/* z = M^-1 r : one application of the preconditioner (test hook). */
+int oi_apply_precond(oi_solver* h, const double* host_r, double* host_z);
+/* Average device time (ms) of one launch of a named kernel over `reps`
+ * launches on the resident problem, CUDA events on the solver stream.
+ * name: "apply" | "smooth" | "residual_restrict" | "axpy2_dot" | "xpby" | "dot"
+ *       | "count_phase" */
+int oi_time_kernel(oi_solver* h, const char* name, int32_t reps, double* avg_ms,
+                   int64_t* cells);
+/* Number of kernels this handle has launched since creation. */
+int oi_launch_count(oi_solver* h, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENIMPALA_B200_H */

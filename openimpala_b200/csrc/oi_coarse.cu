@@ -1,0 +1,223 @@
+// Coarse-level kernels of the geometric V-cycle (levels >= 1).
+//
+// Coarse operators are aggregation-Galerkin: a coarse cell is a (fx x fy x fz)
+// block of finer cells, the coupling across a coarse face is the sum of the
+// finer couplings crossing it, the diagonal is the sum of outward couplings plus
+// the children's Dirichlet sink terms.  Each level is scaled by `scale`
+// (0.5 = the over-correction that turns piecewise-constant aggregation into the
+// rediscretised cell-centred operator).  This replaces HYPRE SMG/PFMG's coarse
+// operator build (reference call site src/props/TortuosityHypre.cpp:671-681).
+#include "oi_kernels.h"
+
+namespace oi {
+
+namespace {
+
+__device__ __forceinline__ double diag0(uint8_t f, const Grid& g) {
+    return g.cx * (double)__popc(f & 0x03u) + g.cy * (double)__popc(f & 0x0cu) +
+           g.cz * (double)__popc(f & 0x30u);
+}
+
+// level 1 from connectivity bytes
+__global__ void __launch_bounds__(256)
+build_from_flags_kernel(Grid g, const uint8_t* __restrict__ flags, CoarseLevel c, int fx, int fy,
+                        int fz, double scale) {
+    const long long nc = (long long)c.nz * c.plane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += stride) {
+        const int ci = (int)(I % c.nx);
+        const int cj = (int)((I / c.nx) % c.ny);
+        const int ck = (int)(I / c.plane);
+        const int i0 = ci * fx, j0 = cj * fy, k0 = ck * fz;
+        const int i1 = min(i0 + fx, g.nx), j1 = min(j0 + fy, g.ny), k1 = min(k0 + fz, g.nz);
+        double sx = 0.0, sy = 0.0, sz = 0.0, sd = 0.0, internal = 0.0;
+        for (int k = k0; k < k1; ++k)
+            for (int j = j0; j < j1; ++j)
+                for (int i = i0; i < i1; ++i) {
+                    const long long idx = (long long)k * g.plane + (long long)j * g.nx + i;
+                    const uint8_t f = flags[idx];
+                    if (!(f & F_UNK)) continue;
+                    sd += diag0(f, g);
+                    // +x, +y, +z couplings to UNKNOWN neighbours (Dirichlet
+                    // neighbours stay in the diagonal as sink terms)
+                    if ((f & F_XP) && (flags[idx + 1] & F_UNK)) {
+                        if (i + 1 < i1) internal += g.cx; else sx += g.cx;
+                    }
+                    if ((f & F_YP) && (flags[idx + g.nx] & F_UNK)) {
+                        if (j + 1 < j1) internal += g.cy; else sy += g.cy;
+                    }
+                    if ((f & F_ZP) && (flags[idx + g.plane] & F_UNK)) {
+                        if (k + 1 < k1) internal += g.cz; else sz += g.cz;
+                    }
+                }
+        c.cxp[I] = (float)(scale * sx);
+        c.cyp[I] = (float)(scale * sy);
+        c.czp[I] = (float)(scale * sz);
+        c.dg[I] = (float)(scale * (sd - 2.0 * internal));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scale) {
+    const long long nc = (long long)c.nz * c.plane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int fx = f.fx, fy = f.fy, fz = f.fz;
+    for (long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += stride) {
+        const int ci = (int)(I % c.nx);
+        const int cj = (int)((I / c.nx) % c.ny);
+        const int ck = (int)(I / c.plane);
+        const int i0 = ci * fx, j0 = cj * fy, k0 = ck * fz;
+        const int i1 = min(i0 + fx, f.nx), j1 = min(j0 + fy, f.ny), k1 = min(k0 + fz, f.nz);
+        double sx = 0.0, sy = 0.0, sz = 0.0, sd = 0.0, internal = 0.0;
+        for (int k = k0; k < k1; ++k)
+            for (int j = j0; j < j1; ++j)
+                for (int i = i0; i < i1; ++i) {
+                    const long long idx = (long long)k * f.plane + (long long)j * f.nx + i;
+                    sd += (double)f.dg[idx];
+                    const double ax = (double)f.cxp[idx], ay = (double)f.cyp[idx], az = (double)f.czp[idx];
+                    if (i + 1 < i1) internal += ax; else sx += ax;
+                    if (j + 1 < j1) internal += ay; else sy += ay;
+                    if (k + 1 < k1) internal += az; else sz += az;
+                }
+        c.cxp[I] = (float)(scale * sx);
+        c.cyp[I] = (float)(scale * sy);
+        c.czp[I] = (float)(scale * sz);
+        c.dg[I] = (float)(scale * (sd - 2.0 * internal));
+    }
+}
+
+struct ProlongRef {
+    const double* ec;
+    int cnx, cny, fx, fy, fz;
+};
+
+template <bool ADDC>
+__device__ __forceinline__ double cval(const CoarseLevel& L, const double* __restrict__ x,
+                                       long long idx, int i, int j, int k, const ProlongRef& pr) {
+    double v = x[idx];
+    if (ADDC) {
+        if (L.dg[idx] > 0.f) {
+            const int ci = (pr.fx == 2) ? (i >> 1) : i;
+            const int cj = (pr.fy == 2) ? (j >> 1) : j;
+            const int ck = (pr.fz == 2) ? ((k + 2) >> 1) - 1 : k;
+            v += pr.ec[((long long)ck * pr.cny + cj) * pr.cnx + ci];
+        }
+    }
+    return v;
+}
+
+// MODE 1: out = x' + w (b - A x')/dg ; MODE 2: out = b - A x'
+template <int MODE, bool ADDC>
+__global__ void __launch_bounds__(256)
+coarse_stencil_kernel(CoarseLevel L, const double* __restrict__ x, const double* __restrict__ b,
+                      double* __restrict__ out, double w, ProlongRef pr) {
+    const long long n = (long long)L.nz * L.plane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const float d = L.dg[idx];
+        double o = 0.0;
+        if (d > 0.f) {
+            const int i = (int)(idx % L.nx);
+            const int j = (int)((idx / L.nx) % L.ny);
+            const int k = (int)(idx / L.plane);
+            const double c = cval<ADDC>(L, x, idx, i, j, k, pr);
+            double acc = (double)d * c;
+            // couplings are zero across domain faces, so guarded loads suffice
+            const float cxp = L.cxp[idx], cyp = L.cyp[idx], czp = L.czp[idx];
+            if (cxp != 0.f) acc -= (double)cxp * cval<ADDC>(L, x, idx + 1, i + 1, j, k, pr);
+            if (cyp != 0.f) acc -= (double)cyp * cval<ADDC>(L, x, idx + L.nx, i, j + 1, k, pr);
+            if (czp != 0.f) acc -= (double)czp * cval<ADDC>(L, x, idx + L.plane, i, j, k + 1, pr);
+            if (i > 0) {
+                const float cm = L.cxp[idx - 1];
+                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - 1, i - 1, j, k, pr);
+            }
+            if (j > 0) {
+                const float cm = L.cyp[idx - L.nx];
+                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - L.nx, i, j - 1, k, pr);
+            }
+            {   // k-1 may be the ghost plane (coefficients exchanged at setup)
+                const float cm = L.czp[idx - L.plane];
+                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - L.plane, i, j, k - 1, pr);
+            }
+            if (MODE == 1) o = c + w * (b[idx] - acc) / (double)d;
+            else           o = b[idx] - acc;
+        }
+        out[idx] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+coarse_jacobi_first_kernel(CoarseLevel L, const double* __restrict__ b, double* __restrict__ out,
+                           double w) {
+    const long long n = (long long)L.nz * L.plane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const float d = L.dg[idx];
+        out[idx] = (d > 0.f) ? w * b[idx] / (double)d : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+coarse_restrict_kernel(CoarseLevel f, const double* __restrict__ res, CoarseLevel c,
+                       double* __restrict__ bc) {
+    const long long nc = (long long)c.nz * c.plane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += stride) {
+        const int ci = (int)(I % c.nx);
+        const int cj = (int)((I / c.nx) % c.ny);
+        const int ck = (int)(I / c.plane);
+        const int i0 = ci * f.fx, j0 = cj * f.fy, k0 = ck * f.fz;
+        const int i1 = min(i0 + f.fx, f.nx), j1 = min(j0 + f.fy, f.ny), k1 = min(k0 + f.fz, f.nz);
+        double s = 0.0;
+        for (int k = k0; k < k1; ++k)
+            for (int j = j0; j < j1; ++j)
+                for (int i = i0; i < i1; ++i)
+                    s += res[(long long)k * f.plane + (long long)j * f.nx + i];
+        bc[I] = s;
+    }
+}
+
+inline int blocks_for(long long n) {
+    long long b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int, int, const CoarseLevel& c,
+                             int fx, int fy, int fz, double scale, cudaStream_t st) {
+    build_from_flags_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(g, flags, c, fx, fy, fz, scale);
+}
+
+void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double scale, cudaStream_t st) {
+    build_from_coarse_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, c, scale);
+}
+
+void coarse_jacobi_first(const CoarseLevel& L, const double* b, double* out, double w, cudaStream_t st) {
+    coarse_jacobi_first_kernel<<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, b, out, w);
+}
+
+void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, double* out, double w,
+                   const CoarseLevel* next, const double* ec, cudaStream_t st) {
+    const int nb = blocks_for((long long)L.nz * L.plane);
+    if (next) {
+        ProlongRef pr{ec, next->nx, next->ny, L.fx, L.fy, L.fz};
+        coarse_stencil_kernel<1, true><<<nb, 256, 0, st>>>(L, x, b, out, w, pr);
+    } else {
+        ProlongRef pr{nullptr, 0, 0, 1, 1, 1};
+        coarse_stencil_kernel<1, false><<<nb, 256, 0, st>>>(L, x, b, out, w, pr);
+    }
+}
+
+void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out, cudaStream_t st) {
+    ProlongRef pr{nullptr, 0, 0, 1, 1, 1};
+    coarse_stencil_kernel<2, false><<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, x, b, out, 0.0, pr);
+}
+
+void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc, cudaStream_t st) {
+    coarse_restrict_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, res, c, bc);
+}
+
+}  // namespace oi

@@ -1,0 +1,92 @@
+// Shared device helpers for the openimpala_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oi {
+
+// ---- connectivity byte (one per cell; replaces the 7 stored fp64 coefficients
+// of tortuosity_fillmtx, reference src/props/TortuosityHypreFill.F90:96-228) ----
+// bits 0..5: this cell is an unknown AND the -x,+x,-y,+y,-z,+z neighbour is an
+//            active cell of the same phase (coefficient -c_d, diag += c_d;
+//            F90:126-166).  Neighbours may be Dirichlet cells.
+// bit 6    : unknown  = active, not on a Dirichlet plane (eliminated system row)
+// bit 7    : active cell on the inlet/outlet plane (identity row, b = vlo/vhi;
+//            F90:192-228)
+enum : uint8_t {
+    F_XM = 1u << 0, F_XP = 1u << 1, F_YM = 1u << 2, F_YP = 1u << 3,
+    F_ZM = 1u << 4, F_ZP = 1u << 5, F_UNK = 1u << 6, F_DIR = 1u << 7,
+    F_FACES = 0x3f
+};
+
+// Problem geometry of one level-0 slab, passed by value to kernels.
+struct Grid {
+    int nx, ny, nz;        // local box (nz = local planes)
+    int nzg;               // global nz
+    int z0;                // global index of local plane 0
+    long long plane;       // nx*ny
+    double cx, cy, cz;     // 1/dx^2, 1/dy^2, 1/dz^2  (TortuosityHypre.cpp:580-582)
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic grid reduction of NV doubles per thread.
+//   partials : [gridDim_total][NV] scratch,  counter : zeroed uint (self-resetting)
+//   out      : [NV] result, written by the last block in fixed block order.
+// Every thread of the block must call this (contains __syncthreads).
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials,
+                                            unsigned int* counter, double* out) {
+    __shared__ double s_part[32][NV];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = warp_sum(v[q]);
+        if (lane == 0) s_part[warp][q] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            double s = (lane < nwarps) ? s_part[lane][q] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) partials[(size_t)bid * NV + q] = s;
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        unsigned int ticket = atomicAdd(counter, 1u);
+        s_last = (ticket == nblocks - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                double s = 0.0;
+                for (unsigned int b = lane; b < nblocks; b += 32)
+                    s += __ldcg(&partials[(size_t)b * NV + q]);
+                s = warp_sum(s);
+                if (lane == 0) out[q] = s;
+            }
+            if (lane == 0) *counter = 0u;
+        }
+    }
+}
+
+}  // namespace oi

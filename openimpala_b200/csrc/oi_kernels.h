@@ -1,0 +1,131 @@
+// Internal launcher interface between the solver driver and the .cu kernels.
+#pragma once
+#include "oi_common.cuh"
+
+namespace oi {
+
+// ---------------------------------------------------------------- level 0
+struct L0Args {
+    Grid g;
+    const uint8_t* flags;      // connectivity bytes, ghost planes at k=-1, k=nz
+    const double* u;           // input field (ghost planes)
+    const double* b;           // rhs (SMOOTH / RESTRICT)
+    double* out;               // output field, or coarse rhs for RESTRICT
+    double w;                  // Jacobi weight (SMOOTH) or scale (APPLY)
+    const double* ec;          // coarse correction (ADDC) or nullptr
+    int cnx, cny;              // coarse dims (ADDC / RESTRICT)
+    int fx, fy, fz;            // coarsening factors to level 1
+    double* red_partials;      // reduction scratch (DOT)
+    unsigned int* red_counter;
+    double* red_out;
+    int n_sm;
+};
+
+long long l0_max_blocks(const Grid& g, int n_sm);
+void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st);
+void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st);
+void l0_residual_restrict(const L0Args& a, cudaStream_t st);
+void l0_residual(const L0Args& a, cudaStream_t st);
+void l0_jacobi_first(const L0Args& a, cudaStream_t st);
+
+// ---------------------------------------------------------------- coarse levels
+// 7-point operator with stored face couplings (Galerkin sums of fine faces):
+//   (A x)_I = dg_I x_I - cxp_I x_{I+ex} - cxp_{I-ex} x_{I-ex} - ... (y, z)
+struct CoarseLevel {
+    int nx, ny, nz;            // local dims (nz local planes)
+    int z0;                    // global index of local plane 0 at this level
+    int nzg;                   // global planes at this level
+    long long plane;
+    int fx, fy, fz;            // coarsening factors from this level to the next
+    float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
+    float* dg;                 // diagonal (0 = empty aggregate)
+    double *x, *b, *t;         // solution, rhs, scratch (ghost planes)
+};
+
+void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int dir_axis, int n_dir_global,
+                             const CoarseLevel& c, int fx, int fy, int fz, double scale,
+                             cudaStream_t st);
+void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double scale,
+                              cudaStream_t st);
+void coarse_jacobi_first(const CoarseLevel& L, const double* b, double* out, double w, cudaStream_t st);
+// out = x (+P ec) + w (b - A x') / dg
+void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, double* out, double w,
+                   const CoarseLevel* next /*add P*next->x when non-null*/, const double* ec,
+                   cudaStream_t st);
+void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out,
+                     cudaStream_t st);
+void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc,
+                     cudaStream_t st);
+
+// ---------------------------------------------------------------- vector ops (K4)
+// x += a p ; r -= a q ; out[0] = r.r      with a = num[0]/den[0] read on device
+void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
+                   const double* num, const double* den, double* partials, unsigned int* counter,
+                   double* out, int n_sm, cudaStream_t st);
+// p = z + (num/den) p
+void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
+              int n_sm, cudaStream_t st);
+// out[0] = a.b
+void vec_dot(long long n, const double* a, const double* b, double* partials,
+             unsigned int* counter, double* out, int n_sm, cudaStream_t st);
+void vec_copy(long long n, double* dst, const double* src, int n_sm, cudaStream_t st);
+// z = r / diag on unknowns (Jacobi preconditioner), out[0] = r.z
+void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, double* z,
+                           double* partials, unsigned int* counter, double* out, int n_sm,
+                           cudaStream_t st);
+int vec_max_blocks(int n_sm);
+
+// ---------------------------------------------------------------- mask / setup (K1, K2, K7, K8)
+void count_phase_u8(const uint8_t* f, long long n, int phase, unsigned long long* out, int n_sm,
+                    cudaStream_t st);
+void count_phase_i32(const int32_t* f, long long n, int phase, unsigned long long* out, int n_sm,
+                     cudaStream_t st);
+void phase_i32_to_u8(const int32_t* in, uint8_t* is_phase, long long n, int phase, int n_sm,
+                     cudaStream_t st);
+void phase_u8_to_isphase(const uint8_t* in, uint8_t* is_phase, long long n, int phase, int n_sm,
+                         cudaStream_t st);
+
+// connected components of {is_phase}: labels = min linear index of the component
+void ccl_label(const uint8_t* is_phase /*ghost planes*/, int* labels, int nx, int ny, int nz,
+               int n_sm, cudaStream_t st);
+// reach[root] |= 1 (touches inlet plane) | 2 (touches outlet plane); planes given
+// in local coordinates, -1 = not on this slab
+void ccl_mark_planes(const uint8_t* is_phase, const int* labels, unsigned int* reach, int nx,
+                     int ny, int nz, int dir, int lo_local, int hi_local, int n_sm,
+                     cudaStream_t st);
+// cross-slab propagation: for cells of local plane k (0 or nz-1) whose neighbour
+// across the slab boundary is phase, OR the neighbour's reach bits into the
+// local root; sets *changed when any bit was added.
+void ccl_export_plane(const uint8_t* is_phase, const int* labels, const unsigned int* reach,
+                      uint8_t* plane_bits, int nx, int ny, int k, int n_sm, cudaStream_t st);
+void ccl_import_plane(const uint8_t* is_phase, const int* labels, unsigned int* reach,
+                      const uint8_t* nbr_bits, int nx, int ny, int k, int* changed, int n_sm,
+                      cudaStream_t st);
+// mask = phase && reach[label]==3 ; writes active u8 (with ghost planes untouched)
+void build_active(const uint8_t* is_phase, const int* labels, const unsigned int* reach,
+                  uint8_t* active, int nx, int ny, int nz, unsigned long long* n_active, int n_sm,
+                  cudaStream_t st);
+// connectivity bytes from the active mask (ghost planes of `active` must be valid)
+// counts[0] = active cells on the inlet plane, counts[1] = on the outlet plane
+void build_flags(const Grid& g, const uint8_t* active, uint8_t* flags, int dir,
+                 unsigned long long* counts, cudaStream_t st);
+// x0 (F90:233-262).  mirror_quirk = 1 reproduces the reference's xinit exactly
+// (cells with diagonal == 1 keep 0, F90:233); 0 = plain ramp with exact
+// Dirichlet values, which is what the solver starts from.
+void fill_initial_guess(const Grid& g, const uint8_t* flags, double* x, int dir, int n_dir_global,
+                        double vlo, double vhi, int mirror_quirk, cudaStream_t st);
+// isolated-voxel filter, one Jacobi-ordered pass (see DESIGN.md on ordering)
+void remspot_pass(const uint8_t* in, uint8_t* out, int nx, int ny, int nz, int z0, int nzg,
+                  cudaStream_t st);
+// boundary fluxes (TortuosityHypre.cpp:1052-1105): out[0]=sum_in, out[1]=sum_out
+void flux_planes(const Grid& g, const uint8_t* flags, const double* x, int dir, int n_dir_global,
+                 double* partials, unsigned int* counter, double* out, cudaStream_t st);
+// matrix rows / rhs as tortuosity_fillmtx would have produced them
+void export_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
+                 int n_dir_global, double vlo, double vhi, double* a7, double* rhs,
+                 cudaStream_t st);
+// device-side checkMatrixProperties; bad[0] incremented per violation
+void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
+                int n_dir_global, unsigned long long* bad, cudaStream_t st);
+
+}  // namespace oi

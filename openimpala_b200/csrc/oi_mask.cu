@@ -1,0 +1,500 @@
+// Setup-side kernels: phase counting (K1), percolation mask by connected-
+// component labelling (K2), connectivity bytes / rhs / initial guess (K7),
+// boundary-flux reduction (K8), matrix-row export and invariant check.
+//
+// Reference restated here:
+//   VolumeFraction::value          src/props/VolumeFraction.cpp:22-66
+//   generateActivityMask           src/props/TortuosityHypre.cpp:394-558
+//   parallelFloodFill              src/props/TortuosityHypre.cpp:297-389
+//   tortuosity_fillmtx             src/props/TortuosityHypreFill.F90:44-314
+//   global_fluxes                  src/props/TortuosityHypre.cpp:1000-1134
+//   checkMatrixProperties          src/props/TortuosityHypre.cpp:896-982
+//
+// The reference floods the phase from every inlet-plane cell and from every
+// outlet-plane cell by repeated sweeps and keeps the intersection.  The exact
+// fixed point of that is "union of 6-connected components of {phase == id} that
+// touch both planes", which is what the label-equivalence (union-find) kernels
+// below compute in a constant number of passes.
+#include "oi_kernels.h"
+
+namespace oi {
+
+namespace {
+
+constexpr int BT = 256;
+
+inline int nblocks(long long n, int n_sm, int per_sm = 8) {
+    long long b = (n + BT - 1) / BT;
+    const long long cap = (long long)n_sm * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------ K1
+template <typename T>
+__global__ void __launch_bounds__(BT)
+count_kernel(const T* __restrict__ f, long long n, int phase, unsigned long long* out) {
+    const long long stride = (long long)gridDim.x * BT;
+    long long acc = 0;
+    for (long long i = (long long)blockIdx.x * BT + threadIdx.x; i < n; i += stride)
+        acc += ((int)f[i] == phase) ? 1 : 0;
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);  // integer: exact
+}
+
+// 16 bytes per thread per step for the uint8 field
+__global__ void __launch_bounds__(BT)
+count_u8_vec_kernel(const uint8_t* __restrict__ f, long long n, int phase, unsigned long long* out) {
+    const long long n16 = n >> 4;
+    const long long stride = (long long)gridDim.x * BT;
+    long long acc = 0;
+    if (phase >= 0 && phase <= 255) {
+        const unsigned int pat = 0x01010101u * (unsigned int)phase;
+        const uint4* v = reinterpret_cast<const uint4*>(f);
+        for (long long i = (long long)blockIdx.x * BT + threadIdx.x; i < n16; i += stride) {
+            const uint4 w = v[i];
+            // bytes equal to phase: xor -> zero byte; count zero bytes
+            unsigned int a = w.x ^ pat, b = w.y ^ pat, c = w.z ^ pat, d = w.w ^ pat;
+            // zero-byte mask: __vcmpeq4 returns 0xff per equal byte
+            acc += (__popc(__vcmpeq4(a, 0u)) + __popc(__vcmpeq4(b, 0u)) +
+                    __popc(__vcmpeq4(c, 0u)) + __popc(__vcmpeq4(d, 0u))) >> 3;
+        }
+        for (long long i = (n16 << 4) + (long long)blockIdx.x * BT + threadIdx.x; i < n; i += stride)
+            acc += ((int)f[i] == phase) ? 1 : 0;
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT)
+to_isphase_kernel(const T* __restrict__ in, uint8_t* __restrict__ out, long long n, int phase) {
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long i = (long long)blockIdx.x * BT + threadIdx.x; i < n; i += stride)
+        out[i] = ((int)in[i] == phase) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ K2: union-find CCL
+// Read-only root search: safe while other threads hook roots with atomicMin
+// (every value ever stored in L[i] is a smaller index of the same final set).
+__device__ __forceinline__ int uf_find(const int* L, int i) {
+    while (true) {
+        const int p = __ldcg(&L[i]);   // L2: other SMs hook roots concurrently
+        if (p == i) return i;
+        i = p;
+    }
+}
+
+// Label-equivalence union (Komura / Playne-Hawick): hook the larger root under
+// the smaller one with atomicMin and retry when the root moved meanwhile.
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }   // a < b: hook b under a
+        const int old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;                                         // b had been hooked to `old`: merge a with it
+    }
+}
+
+// one warp per x-row: label = linear index of the first cell of the x-run
+__global__ void __launch_bounds__(BT)
+ccl_rows_kernel(const uint8_t* __restrict__ ph, int* __restrict__ L, int nx, long long nrows) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * BT + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * BT) >> 5;
+    for (long long row = warp; row < nrows; row += nwarps) {
+        const long long base = row * nx;
+        int carry = -1;  // run start (x index) continuing from the previous chunk
+        for (int x0 = 0; x0 < nx; x0 += 32) {
+            const int x = x0 + lane;
+            const bool on = (x < nx) && ph[base + x];
+            const unsigned int m = __ballot_sync(0xffffffffu, on);
+            const unsigned int below = (lane == 0) ? 0u : (~m & ((1u << lane) - 1u));
+            int start;
+            if (below == 0u) start = (carry >= 0) ? carry : x0;
+            else start = x0 + (32 - __clz(below));
+            if (x < nx) L[base + x] = on ? (int)(base + start) : -1;
+            const int s31 = __shfl_sync(0xffffffffu, start, 31);
+            carry = (m >> 31) ? s31 : -1;
+        }
+    }
+}
+
+// merge runs across -y and -z; one union per start of an overlap segment
+__global__ void __launch_bounds__(BT)
+ccl_merge_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, int nz) {
+    const long long n = (long long)nx * ny * nz;
+    const long long plane = (long long)nx * ny;
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        if (!ph[idx]) continue;
+        const int i = (int)(idx % nx);
+        const int j = (int)((idx / nx) % ny);
+        const int k = (int)(idx / plane);
+        const bool left = (i > 0) && ph[idx - 1];
+        if (j > 0 && ph[idx - nx]) {
+            if (!(left && ph[idx - nx - 1])) uf_union(L, (int)idx, (int)(idx - nx));
+        }
+        if (k > 0 && ph[idx - plane]) {
+            if (!(left && ph[idx - plane - 1])) uf_union(L, (int)idx, (int)(idx - plane));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+ccl_flatten_kernel(const uint8_t* __restrict__ ph, int* L, long long n) {
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        if (!ph[idx]) continue;
+        int r = L[idx];
+        while (true) { const int p = L[r]; if (p == r) break; r = p; }
+        L[idx] = r;
+    }
+}
+
+__device__ __forceinline__ void reach_or(unsigned int* reach_words, int root, unsigned int bits) {
+    atomicOr(&reach_words[root >> 2], bits << ((root & 3) * 8));
+}
+__device__ __forceinline__ unsigned int reach_get(const unsigned int* reach_words, int root) {
+    return (reach_words[root >> 2] >> ((root & 3) * 8)) & 0xffu;
+}
+
+__global__ void __launch_bounds__(BT)
+ccl_mark_kernel(const uint8_t* __restrict__ ph, const int* __restrict__ L, unsigned int* reach,
+                int nx, int ny, int nz, int dir, int lo_local, int hi_local) {
+    // threads enumerate the cells of one plane perpendicular to dir
+    const int na = (dir == 0) ? ny : nx;
+    const int nb = (dir == 2) ? ny : nz;
+    const long long np = (long long)na * nb;
+    const long long stride = (long long)gridDim.x * BT;
+    const long long plane = (long long)nx * ny;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < np; t += stride) {
+        const int a = (int)(t % na), b = (int)(t / na);
+        for (int side = 0; side < 2; ++side) {
+            const int p = side ? hi_local : lo_local;
+            if (p < 0) continue;
+            long long idx;
+            if (dir == 0) idx = (long long)b * plane + (long long)a * nx + p;
+            else if (dir == 1) idx = (long long)b * plane + (long long)p * nx + a;
+            else idx = (long long)p * plane + (long long)b * nx + a;
+            if (ph[idx]) reach_or(reach, L[idx], side ? 2u : 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+ccl_export_kernel(const uint8_t* __restrict__ ph, const int* __restrict__ L,
+                  const unsigned int* __restrict__ reach, uint8_t* __restrict__ bits, long long np,
+                  long long off) {
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < np; t += stride)
+        bits[t] = ph[off + t] ? (uint8_t)reach_get(reach, L[off + t]) : (uint8_t)0;
+}
+
+__global__ void __launch_bounds__(BT)
+ccl_import_kernel(const uint8_t* __restrict__ ph, const int* __restrict__ L, unsigned int* reach,
+                  const uint8_t* __restrict__ nbr_bits, long long np, long long off, int* changed) {
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < np; t += stride) {
+        if (!ph[off + t]) continue;
+        const unsigned int nb = nbr_bits[t] & 3u;
+        if (!nb) continue;
+        const int root = L[off + t];
+        const unsigned int have = reach_get(reach, root);
+        if (nb & ~have) { reach_or(reach, root, nb); *changed = 1; }
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+build_active_kernel(const uint8_t* __restrict__ ph, const int* __restrict__ L,
+                    const unsigned int* __restrict__ reach, uint8_t* __restrict__ active,
+                    long long n, unsigned long long* n_active) {
+    const long long stride = (long long)gridDim.x * BT;
+    long long acc = 0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        uint8_t a = 0;
+        if (ph[idx]) a = (reach_get(reach, L[idx]) == 3u) ? 1 : 0;
+        active[idx] = a;
+        acc += a;
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(n_active, (unsigned long long)acc);
+}
+
+// ------------------------------------------------------------------ K7
+__device__ __forceinline__ int dir_index(int dir, int i, int j, int kglob) {
+    return dir == 0 ? i : (dir == 1 ? j : kglob);
+}
+
+__global__ void __launch_bounds__(BT)
+build_flags_kernel(Grid g, const uint8_t* __restrict__ active, uint8_t* __restrict__ flags, int dir,
+                   int n_dir, unsigned long long* counts) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    long long c_in = 0, c_out = 0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        uint8_t f = 0;
+        if (active[idx]) {
+            const int i = (int)(idx % g.nx);
+            const int j = (int)((idx / g.nx) % g.ny);
+            const int k = (int)(idx / g.plane);
+            const int d = dir_index(dir, i, j, g.z0 + k);
+            if (d == 0) { f = F_DIR; ++c_in; }                       // F90:193-197
+            else if (d == n_dir - 1) { f = F_DIR; ++c_out; }         // F90:198-202
+            else {
+                f = F_UNK;                                           // F90:126-166
+                if (i > 0 && active[idx - 1]) f |= F_XM;
+                if (i + 1 < g.nx && active[idx + 1]) f |= F_XP;
+                if (j > 0 && active[idx - g.nx]) f |= F_YM;
+                if (j + 1 < g.ny && active[idx + g.nx]) f |= F_YP;
+                // z neighbours: ghost planes of `active` hold the neighbour slab's
+                // plane, or 0 outside the global box
+                if (active[idx - g.plane]) f |= F_ZM;
+                if (active[idx + g.plane]) f |= F_ZP;
+            }
+        }
+        flags[idx] = f;
+    }
+    c_in = warp_sum_ll(c_in);
+    c_out = warp_sum_ll(c_out);
+    if ((threadIdx.x & 31) == 0) {
+        if (c_in) atomicAdd(&counts[0], (unsigned long long)c_in);
+        if (c_out) atomicAdd(&counts[1], (unsigned long long)c_out);
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+initial_guess_kernel(Grid g, const uint8_t* __restrict__ flags, double* __restrict__ x, int dir,
+                     int n_dir, double vlo, double vhi, int mirror_quirk) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    const double ext = (double)(n_dir - 1);
+    const double factor = (fabs(ext) < 1e-15) ? 0.0 : 1.0 / ext;     // F90:236-241
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const uint8_t f = flags[idx];
+        double v = 0.0;
+        if (f & (F_UNK | F_DIR)) {
+            const int i = (int)(idx % g.nx);
+            const int j = (int)((idx / g.nx) % g.ny);
+            const int k = (int)(idx / g.plane);
+            const int d = dir_index(dir, i, j, g.z0 + k);
+            if (f & F_DIR) {
+                v = mirror_quirk ? vlo + (vhi - vlo) * (double)d * factor : ((d == 0) ? vlo : vhi);
+            } else {
+                v = vlo + (vhi - vlo) * (double)d * factor;          // F90:242-258
+                if (mirror_quirk) {
+                    // F90:233: cells whose diagonal is exactly 1 keep the
+                    // caller's value-initialised 0 (TortuosityHypre.cpp:606)
+                    const double dg = g.cx * (double)__popc(f & 0x03u) +
+                                      g.cy * (double)__popc(f & 0x0cu) +
+                                      g.cz * (double)__popc(f & 0x30u);
+                    if (!(fabs(dg - 1.0) > 1e-15)) v = 0.0;
+                }
+            }
+        }
+        x[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------ K8
+__global__ void __launch_bounds__(BT)
+flux_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ x, int dir,
+            int n_dir, double inv_dx, double* partials, unsigned int* counter, double* out) {
+    const int na = (dir == 0) ? g.ny : g.nx;
+    const int nb = (dir == 2) ? g.ny : g.nz;
+    const long long np = (long long)na * nb;
+    const long long stride = (long long)gridDim.x * BT;
+    const long long sd = (dir == 0) ? 1 : (dir == 1 ? (long long)g.nx : g.plane);
+    // local position of the global planes 0 and n_dir-1 (z: only on the owning slab)
+    const int lo = (dir == 2) ? (0 - g.z0) : 0;
+    const int hi = (dir == 2) ? (n_dir - 1 - g.z0) : (n_dir - 1);
+    const int nloc = (dir == 2) ? g.nz : n_dir;
+    double fin = 0.0, fout = 0.0;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < np; t += stride) {
+        const int a = (int)(t % na), b = (int)(t / na);
+        long long base;   // index of the cell with dir-index 0 (local)
+        if (dir == 0) base = (long long)b * g.plane + (long long)a * g.nx;
+        else if (dir == 1) base = (long long)b * g.plane + a;
+        else base = (long long)b * g.nx + a;
+        if (n_dir >= 2) {
+            if (lo >= 0 && lo < nloc) {
+                const long long c = base + lo * sd, in = c + sd;     // :1067-1083
+                if ((flags[c] & F_DIR) && (flags[in] & (F_UNK | F_DIR)))
+                    fin += -((x[in] - x[c]) * inv_dx);
+            }
+            if (hi >= 0 && hi < nloc) {
+                const long long c = base + hi * sd, in = c - sd;     // :1086-1103
+                if ((flags[c] & F_DIR) && (flags[in] & (F_UNK | F_DIR)))
+                    fout += -((x[c] - x[in]) * inv_dx);
+            }
+        }
+    }
+    double v[2] = {fin, fout};
+    grid_reduce<2>(v, partials, counter, out);
+}
+
+// ------------------------------------------------------------------ rows / checks
+__device__ __forceinline__ void make_row(const Grid& g, uint8_t f, int d, int n_dir, double vlo,
+                                         double vhi, double (&a)[7], double& rhs) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) a[s] = 0.0;
+    rhs = 0.0;
+    if (f & F_UNK) {
+        double dg = 0.0;
+        if (f & F_XM) { a[1] = -g.cx; dg += g.cx; }
+        if (f & F_XP) { a[2] = -g.cx; dg += g.cx; }
+        if (f & F_YM) { a[3] = -g.cy; dg += g.cy; }
+        if (f & F_YP) { a[4] = -g.cy; dg += g.cy; }
+        if (f & F_ZM) { a[5] = -g.cz; dg += g.cz; }
+        if (f & F_ZP) { a[6] = -g.cz; dg += g.cz; }
+        a[0] = dg;
+    } else {
+        a[0] = 1.0;
+        if (f & F_DIR) rhs = (d == 0) ? vlo : vhi;
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+export_rows_kernel(Grid g, const uint8_t* __restrict__ flags, int dir, int n_dir, double vlo,
+                   double vhi, double* __restrict__ a7, double* __restrict__ rhs) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % g.nx);
+        const int j = (int)((idx / g.nx) % g.ny);
+        const int k = (int)(idx / g.plane);
+        double a[7], r;
+        make_row(g, flags[idx], dir_index(dir, i, j, g.z0 + k), n_dir, vlo, vhi, a, r);
+        if (a7) {
+#pragma unroll
+            for (int s = 0; s < 7; ++s) a7[idx * 7 + s] = a[s];
+        }
+        if (rhs) rhs[idx] = r;
+    }
+}
+
+__global__ void __launch_bounds__(BT)
+check_rows_kernel(Grid g, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ active,
+                  int dir, int n_dir, unsigned long long* bad) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    const double tol = 1e-14;                                         // TortuosityHypre.cpp:903
+    long long nbad = 0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % g.nx);
+        const int j = (int)((idx / g.nx) % g.ny);
+        const int k = (int)(idx / g.plane);
+        const int d = dir_index(dir, i, j, g.z0 + k);
+        double a[7], r;
+        make_row(g, flags[idx], d, n_dir, 0.25, 0.75, a, r);
+        bool ok = true;
+        for (int s = 0; s < 7; ++s) ok = ok && isfinite(a[s]);
+        const bool act = active[idx] != 0;
+        const bool dirichlet = act && (d == 0 || d == n_dir - 1);     // :950-956
+        double off = 0.0;
+        for (int s = 1; s < 7; ++s) off = fmax(off, fabs(a[s]));
+        if (!act) {                                                   // :957-960
+            ok = ok && fabs(a[0] - 1.0) <= tol && fabs(r) <= tol && off <= tol;
+        } else if (dirichlet) {                                       // :961-965
+            const double e = (d == 0) ? 0.25 : 0.75;
+            ok = ok && fabs(a[0] - 1.0) <= tol && fabs(r - e) <= tol && off <= tol;
+        } else {                                                      // :966-972
+            double row = 0.0;
+            for (int s = 0; s < 7; ++s) row += a[s];
+            ok = ok && (a[0] > tol) && fabs(r) <= tol && fabs(row) <= tol;
+            // and the stored couplings must mirror the active neighbours
+            uint8_t e = F_UNK;
+            if (i > 0 && active[idx - 1]) e |= F_XM;
+            if (i + 1 < g.nx && active[idx + 1]) e |= F_XP;
+            if (j > 0 && active[idx - g.nx]) e |= F_YM;
+            if (j + 1 < g.ny && active[idx + g.nx]) e |= F_YP;
+            if (active[idx - g.plane]) e |= F_ZM;
+            if (active[idx + g.plane]) e |= F_ZP;
+            ok = ok && (e == flags[idx]);
+        }
+        if (!ok) ++nbad;
+    }
+    nbad = warp_sum_ll(nbad);
+    if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+void count_phase_u8(const uint8_t* f, long long n, int phase, unsigned long long* out, int n_sm, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(f) & 15) == 0)
+        count_u8_vec_kernel<<<nblocks((n + 15) / 16, n_sm), BT, 0, st>>>(f, n, phase, out);
+    else
+        count_kernel<uint8_t><<<nblocks(n, n_sm), BT, 0, st>>>(f, n, phase, out);
+}
+void count_phase_i32(const int32_t* f, long long n, int phase, unsigned long long* out, int n_sm, cudaStream_t st) {
+    count_kernel<int32_t><<<nblocks(n, n_sm), BT, 0, st>>>(f, n, phase, out);
+}
+void phase_i32_to_u8(const int32_t* in, uint8_t* o, long long n, int phase, int n_sm, cudaStream_t st) {
+    to_isphase_kernel<int32_t><<<nblocks(n, n_sm), BT, 0, st>>>(in, o, n, phase);
+}
+void phase_u8_to_isphase(const uint8_t* in, uint8_t* o, long long n, int phase, int n_sm, cudaStream_t st) {
+    to_isphase_kernel<uint8_t><<<nblocks(n, n_sm), BT, 0, st>>>(in, o, n, phase);
+}
+
+void ccl_label(const uint8_t* ph, int* L, int nx, int ny, int nz, int n_sm, cudaStream_t st) {
+    const long long n = (long long)nx * ny * nz;
+    const long long nrows = (long long)ny * nz;
+    ccl_rows_kernel<<<nblocks(nrows * 32, n_sm), BT, 0, st>>>(ph, L, nx, nrows);
+    ccl_merge_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
+    ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
+}
+void ccl_mark_planes(const uint8_t* ph, const int* L, unsigned int* reach, int nx, int ny, int nz,
+                     int dir, int lo_local, int hi_local, int n_sm, cudaStream_t st) {
+    const long long np = (long long)((dir == 0) ? ny : nx) * ((dir == 2) ? ny : nz);
+    ccl_mark_kernel<<<nblocks(np, n_sm), BT, 0, st>>>(ph, L, reach, nx, ny, nz, dir, lo_local, hi_local);
+}
+void ccl_export_plane(const uint8_t* ph, const int* L, const unsigned int* reach, uint8_t* bits,
+                      int nx, int ny, int k, int n_sm, cudaStream_t st) {
+    const long long np = (long long)nx * ny;
+    ccl_export_kernel<<<nblocks(np, n_sm), BT, 0, st>>>(ph, L, reach, bits, np, (long long)k * np);
+}
+void ccl_import_plane(const uint8_t* ph, const int* L, unsigned int* reach, const uint8_t* nbr,
+                      int nx, int ny, int k, int* changed, int n_sm, cudaStream_t st) {
+    const long long np = (long long)nx * ny;
+    ccl_import_kernel<<<nblocks(np, n_sm), BT, 0, st>>>(ph, L, reach, nbr, np, (long long)k * np, changed);
+}
+void build_active(const uint8_t* ph, const int* L, const unsigned int* reach, uint8_t* active,
+                  int nx, int ny, int nz, unsigned long long* n_active, int n_sm, cudaStream_t st) {
+    const long long n = (long long)nx * ny * nz;
+    build_active_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, reach, active, n, n_active);
+}
+void build_flags(const Grid& g, const uint8_t* active, uint8_t* flags, int dir,
+                 unsigned long long* counts, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    const int n_dir = (dir == 0) ? g.nx : (dir == 1 ? g.ny : g.nzg);
+    build_flags_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, active, flags, dir, n_dir, counts);
+}
+void fill_initial_guess(const Grid& g, const uint8_t* flags, double* x, int dir, int n_dir,
+                        double vlo, double vhi, int mirror_quirk, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    initial_guess_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, flags, x, dir, n_dir, vlo, vhi, mirror_quirk);
+}
+void flux_planes(const Grid& g, const uint8_t* flags, const double* x, int dir, int n_dir,
+                 double* partials, unsigned int* counter, double* out, cudaStream_t st) {
+    const long long np = (long long)((dir == 0) ? g.ny : g.nx) * ((dir == 2) ? g.ny : g.nz);
+    const double dxd = 1.0 / sqrt(dir == 0 ? g.cx : (dir == 1 ? g.cy : g.cz));
+    flux_kernel<<<nblocks(np, 148, 4), BT, 0, st>>>(g, flags, x, dir, n_dir, 1.0 / dxd, partials, counter, out);
+}
+void export_rows(const Grid& g, const uint8_t* flags, const uint8_t*, int dir, int n_dir,
+                 double vlo, double vhi, double* a7, double* rhs, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    export_rows_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, flags, dir, n_dir, vlo, vhi, a7, rhs);
+}
+void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir, int n_dir,
+                unsigned long long* bad, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    check_rows_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, flags, active, dir, n_dir, bad);
+}
+void remspot_pass(const uint8_t*, uint8_t*, int, int, int, int, int, cudaStream_t) {}
+
+}  // namespace oi

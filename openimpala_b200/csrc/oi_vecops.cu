@@ -1,0 +1,132 @@
+// Krylov vector kernels (K4): fused AXPY pairs + dot products with warp-shuffle
+// and block reductions, deterministic last-block finish.  These replace HYPRE's
+// struct axpy / inner-product calls inside the Krylov loop (reference call site
+// src/props/TortuosityHypre.cpp:681-683).  Scalars (alpha, beta) are read from
+// device memory so the loop needs no host round trip to form them.
+#include "oi_kernels.h"
+
+namespace oi {
+
+namespace {
+constexpr int VT = 256;
+
+__global__ void __launch_bounds__(VT)
+axpy2_dot_kernel(long long n, double* __restrict__ x, double* __restrict__ r,
+                 const double* __restrict__ p, const double* __restrict__ q,
+                 const double* __restrict__ num, const double* __restrict__ den,
+                 double* partials, unsigned int* counter, double* out) {
+    const double a = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT * 2;
+    double acc = 0.0;
+    // two doubles per thread per step (16-byte vector access when aligned)
+    const long long n2 = n & ~1LL;
+    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
+        double2 xv = *reinterpret_cast<double2*>(x + i);
+        double2 rv = *reinterpret_cast<double2*>(r + i);
+        const double2 pv = *reinterpret_cast<const double2*>(p + i);
+        const double2 qv = *reinterpret_cast<const double2*>(q + i);
+        xv.x += a * pv.x; xv.y += a * pv.y;
+        rv.x -= a * qv.x; rv.y -= a * qv.y;
+        *reinterpret_cast<double2*>(x + i) = xv;
+        *reinterpret_cast<double2*>(r + i) = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
+        const long long i = n2;
+        x[i] += a * p[i];
+        const double rv = r[i] - a * q[i];
+        r[i] = rv;
+        acc += rv * rv;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(VT)
+xpby_kernel(long long n, double* __restrict__ p, const double* __restrict__ z,
+            const double* __restrict__ num, const double* __restrict__ den) {
+    const double bta = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT * 2;
+    const long long n2 = n & ~1LL;
+    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
+        double2 pv = *reinterpret_cast<double2*>(p + i);
+        const double2 zv = *reinterpret_cast<const double2*>(z + i);
+        pv.x = zv.x + bta * pv.x; pv.y = zv.y + bta * pv.y;
+        *reinterpret_cast<double2*>(p + i) = pv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = z[n2] + bta * p[n2];
+}
+
+__global__ void __launch_bounds__(VT)
+dot_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b,
+           double* partials, unsigned int* counter, double* out) {
+    const long long stride = (long long)gridDim.x * VT;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride) acc += a[i] * b[i];
+    double v[1] = {acc};
+    grid_reduce<1>(v, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(VT)
+copy_kernel(long long n, double* __restrict__ d, const double* __restrict__ s) {
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(VT)
+jacobi_precond_dot_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ r,
+                          double* __restrict__ z, long long n, double* partials,
+                          unsigned int* counter, double* out) {
+    const long long stride = (long long)gridDim.x * VT;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride) {
+        const uint8_t f = flags[i];
+        double zv = 0.0;
+        if (f & F_UNK) {
+            const double d = g.cx * (double)__popc(f & 0x03u) + g.cy * (double)__popc(f & 0x0cu) +
+                             g.cz * (double)__popc(f & 0x30u);
+            const double rv = r[i];
+            zv = rv / d;
+            acc += rv * zv;
+        }
+        z[i] = zv;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, partials, counter, out);
+}
+
+inline int nblocks(long long work_items, int n_sm) {
+    long long b = (work_items + VT - 1) / VT;
+    const long long cap = (long long)n_sm * 8;     // 8 x 256 threads resident per SM
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+}  // namespace
+
+int vec_max_blocks(int n_sm) { return n_sm * 8; }
+
+void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
+                   const double* num, const double* den, double* partials, unsigned int* counter,
+                   double* out, int n_sm, cudaStream_t st) {
+    axpy2_dot_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, x, r, p, q, num, den, partials, counter, out);
+}
+void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
+              int n_sm, cudaStream_t st) {
+    xpby_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, p, z, num, den);
+}
+void vec_dot(long long n, const double* a, const double* b, double* partials, unsigned int* counter,
+             double* out, int n_sm, cudaStream_t st) {
+    dot_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(n, a, b, partials, counter, out);
+}
+void vec_copy(long long n, double* dst, const double* src, int n_sm, cudaStream_t st) {
+    copy_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);
+}
+void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, double* z,
+                           double* partials, unsigned int* counter, double* out, int n_sm,
+                           cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    jacobi_precond_dot_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(g, flags, r, z, n, partials, counter, out);
+}
+
+}  // namespace oi

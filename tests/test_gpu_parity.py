@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the
+oracle (oracle/oi_numpy.py) on the same inputs.  Integer work bit-exact, fp64
+within the tolerance written beside each assert (north_star: tau within 1e-6
+relative of the converged reference solve).
+
+Modelled on the reference's own drivers: src/props/tTortuosity.cpp (construct,
+checkMatrixProperties, value() finite), src/props/tVolumeFraction.cpp (counts ==
+independent loop) plus the analytic cases of SURVEY 8c.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TAU_RTOL = 1e-6   # north_star tolerance on D_eff / tau
+
+
+def _blobs(shape, seed, porosity=0.5, sigma=1.5):
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    f = ndimage.gaussian_filter(rng.standard_normal(shape), sigma)
+    return (f > np.quantile(f, 1.0 - porosity)).astype(np.int32)
+
+
+@pytest.fixture(scope="module")
+def capi(built_lib):
+    from openimpala_b200 import capi as c
+    assert c.device_count() >= 1, "no CUDA device: the product path has no CPU fallback"
+    return c
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("dtype", [np.uint8, np.int32])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4097, 1_000_003])
+def test_count_phase_bit_exact(capi, dtype, n):
+    rng = np.random.default_rng(n + 7)
+    f = rng.integers(0, 3, size=n).astype(dtype)
+    for phase in (0, 1, 2, 5):
+        pc, tc = capi.count_phase(f, phase)
+        assert pc == int(np.count_nonzero(f == phase))
+        assert tc == n
+
+
+def test_volume_fraction_sample(capi, sample_phase):
+    from openimpala_b200.tortuosity import VolumeFraction
+    # integer facts of SURVEY 8c-3
+    assert VolumeFraction(sample_phase, 1).value() == (398309, 1000000)
+    assert VolumeFraction(sample_phase, 0).value() == (601691, 1000000)
+    assert VolumeFraction(sample_phase.astype(np.uint8), 1).value() == (398309, 1000000)
+    vf0 = VolumeFraction(sample_phase, 0).value_vf()
+    vf1 = VolumeFraction(sample_phase, 1).value_vf()
+    assert abs(vf0 + vf1 - 1.0) < 1e-15          # tVolumeFraction.cpp: VF0 + VF1 ~ 1
+
+
+# ------------------------------------------------------------------ K2 / K7: mask + rows
+CASES = [((13, 17, 20), 3, 0.55), ((24, 9, 31), 4, 0.5), ((8, 8, 8), 5, 0.7), ((33, 66, 5), 6, 0.6),
+         ((40, 40, 40), 7, 0.45), ((7, 130, 70), 8, 0.5)]
+
+
+@pytest.mark.parametrize("shape,seed,por", CASES)
+@pytest.mark.parametrize("direction", [0, 1, 2])
+def test_mask_rows_and_operator(capi, shape, seed, por, direction):
+    from oracle import oi_numpy as o
+    ph = _blobs(shape, seed, por)
+    for phase_id in (1, 0):
+        mask = o.activity_mask(ph, phase_id, direction)
+        with capi.Solver(shape, direction, phase_id, vlo=-1.0, vhi=1.0) as s:
+            s.set_phase(ph)
+            assert s.volume_fraction() == o.volume_fraction_counts(ph, phase_id)
+            n_active = s.build_mask()
+            assert n_active == int(mask.sum())                       # bit-exact count
+            if n_active == 0:
+                continue
+            assert np.array_equal(s.mask().astype(bool), mask)       # bit-exact mask
+            a, rhs, x0 = o.fill_matrix(ph, mask, phase_id, direction, -1.0, 1.0)
+            assert np.array_equal(s.matrix_rows().reshape(-1, 7), a)  # coefficients are exact
+            assert np.array_equal(s.rhs().ravel(), rhs)
+            np.testing.assert_allclose(s.initial_guess().ravel(), x0, rtol=0, atol=1e-15)
+            assert s.check_matrix_properties()
+            assert o.check_matrix_properties(s.matrix_rows(), s.rhs(), mask, direction, -1.0, 1.0, shape)
+            # K3: y = A_elim x against the assembled matrix
+            A = o.assemble_csr(a, shape)
+            Auu, bu, unk, xf = o.eliminate_dirichlet(A, rhs, x0, shape, mask, direction)
+            rng = np.random.default_rng(seed)
+            x = np.where(unk, rng.standard_normal(unk.size), 0.0)
+            y_ref = np.zeros(unk.size)
+            y_ref[unk] = Auu @ x[unk]
+            y = s.apply_operator(x.reshape(shape)).ravel()
+            np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("shape,seed,por", CASES[:5])
+def test_tau_matches_oracle(capi, shape, seed, por, variant):
+    from oracle import oi_numpy as o
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = _blobs(shape, seed, por)
+    for direction in (0, 1, 2):
+        ref = o.tortuosity(ph, 1, direction, -1.0, 1.0, eps=1e-13)
+        t = TortuosityHypre(None, None, None, ph, ref.active_vf, 1, Direction(direction),
+                            SolverType.FlexGMRES, "", -1.0, 1.0, stencil_variant=variant)
+        assert t.checkMatrixProperties()
+        tau = t.value()
+        assert t.getActiveVolumeFraction() == ref.active_vf
+        if math.isnan(ref.tau):
+            assert math.isnan(tau)
+            continue
+        assert t.getSolverConverged()
+        assert t.getFinalRelativeResidualNorm() <= 1e-9
+        assert abs(tau - ref.tau) <= TAU_RTOL * abs(ref.tau), (tau, ref.tau)
+        np.testing.assert_allclose(t.getFluxIn(), ref.flux_in, rtol=TAU_RTOL)
+        np.testing.assert_allclose(t.getFluxOut(), ref.flux_out, rtol=TAU_RTOL)
+        t.close()
+
+
+def test_jacobi_pcg_matches_mg(capi):
+    from openimpala_b200 import capi as c
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = _blobs((20, 24, 28), 11, 0.55)
+    taus = []
+    for pre in (c.OI_PRECOND_MG, c.OI_PRECOND_JACOBI):
+        from openimpala_b200.tortuosity import ParmParse
+        ParmParse.table = {"hypre.maxiter": 2000}
+        try:
+            t = TortuosityHypre(None, None, None, ph, 0.5, 1, Direction.X, SolverType.PCG, "", 0.0, 1.0,
+                                precond=pre)
+            taus.append(t.value())
+            assert t.getSolverConverged()
+        finally:
+            ParmParse.table = {}
+    assert abs(taus[0] - taus[1]) <= TAU_RTOL * abs(taus[0])
+
+
+# ------------------------------------------------------------------ analytic known answers
+@pytest.mark.parametrize("n", [8, 16, 33])
+@pytest.mark.parametrize("direction", [0, 1, 2])
+def test_uniform_block(capi, n, direction):
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = np.ones((n, n, n), dtype=np.int32)
+    t = TortuosityHypre(None, None, None, ph, 1.0, 1, Direction(direction), SolverType.FlexGMRES, "")
+    assert t.getActiveVolumeFraction() == 1.0
+    assert abs(t.value() - (n - 1) / n) <= 1e-12
+    assert t.getSolverConverged()
+
+
+def test_half_slab_and_blocked(capi):
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    n = 8
+    ph = np.zeros((n, n, n), dtype=np.int32)
+    ph[:, : n // 2, :] = 1                    # phase occupies y < n/2
+    t = TortuosityHypre(None, None, None, ph, 0.5, 1, Direction.X, SolverType.FlexGMRES, "")
+    assert t.getActiveVolumeFraction() == 0.5
+    assert abs(t.value() - (n - 1) / n) <= 1e-12
+    t = TortuosityHypre(None, None, None, ph, 0.5, 1, Direction.Y, SolverType.FlexGMRES, "")
+    assert t.getActiveVolumeFraction() == 0.0           # no outlet seeds -> empty mask
+    assert math.isnan(t.value())
+    assert t.checkMatrixProperties()
+
+
+def test_equal_potentials_gives_inf(capi):
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = np.ones((6, 6, 6), dtype=np.int32)
+    t = TortuosityHypre(None, None, None, ph, 1.0, 1, Direction.Z, SolverType.FlexGMRES, "", 0.5, 0.5)
+    assert math.isinf(t.value())               # avg flux ~ 0 -> +Inf (TortuosityHypre.cpp:846-851)
+
+
+def test_anisotropic_cell_size(capi):
+    from oracle import oi_numpy as o
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = _blobs((18, 20, 22), 21, 0.6)
+    dx = (0.5, 1.0, 2.0)
+    for d in (0, 2):
+        ref = o.tortuosity(ph, 1, d, 0.0, 1.0, eps=1e-13, dx=dx)
+        t = TortuosityHypre({"dx": dx}, None, None, ph, 0.6, 1, Direction(d), SolverType.FlexGMRES, "")
+        assert abs(t.value() - ref.tau) <= TAU_RTOL * abs(ref.tau)
+
+
+# ------------------------------------------------------------------ the reference's sample image
+def test_sample_image_golden(capi, sample_phase):
+    """BASELINE configs[0]/[1]: tau in X/Y/Z for both phases + VF; golden values
+    from tests/golden/make_golden.py (oracle at eps 1e-12)."""
+    import hashlib
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    gold = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    for case in gold["cases"]:
+        t = TortuosityHypre(None, None, None, sample_phase, 0.4, case["phase"], Direction(case["direction"]),
+                            SolverType.FlexGMRES, "", gold["vlo"], gold["vhi"])
+        assert t._n_active == case["n_active"]
+        assert hashlib.sha256(t.active_mask().tobytes()).hexdigest() == case["mask_sha256"]
+        assert t.checkMatrixProperties()
+        tau = t.value()                        # default eps 1e-9, maxiter 200
+        assert t.getSolverConverged() and t.getSolverIterations() <= 200
+        assert abs(tau - case["tau"]) <= TAU_RTOL * case["tau"], (case, tau)
+        fi, fo, ni, no = t.solver.fluxes()
+        assert (ni, no) == (case["n_in"], case["n_out"])
+        t.close()
+
+
+def test_preconditioner_is_symmetric(capi):
+    """PCG needs M = M^T: <M a, b> == <a, M b> on random vectors."""
+    ph = _blobs((24, 28, 32), 31, 0.6)
+    with capi.Solver(ph.shape, 2, 1) as s:
+        s.set_phase(ph)
+        s.build_mask()
+        unk = (s.matrix_rows()[..., 0] != 1.0) | (s.matrix_rows()[..., 1:] != 0).any(axis=-1)
+        rng = np.random.default_rng(5)
+        a = np.where(unk, rng.standard_normal(ph.shape), 0.0)
+        b = np.where(unk, rng.standard_normal(ph.shape), 0.0)
+        ma, mb = s.apply_precond(a), s.apply_precond(b)
+        lhs, rhs = float((ma * b).sum()), float((a * mb).sum())
+        assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+        assert float((ma * a).sum()) > 0.0
