@@ -46,6 +46,8 @@ typedef enum oi_direction { OI_DIR_X = 0, OI_DIR_Y = 1, OI_DIR_Z = 2 } oi_direct
  * src/props/TortuosityHypre.cpp:664-678; every SolverType maps to PCG here). */
 typedef enum oi_precond { OI_PRECOND_MG = 0, OI_PRECOND_JACOBI = 1 } oi_precond;
 
+struct oi_comm;
+
 typedef struct oi_params {
     int32_t nx, ny, nz;        /* global box, cells (Geometry::Domain)            */
     int32_t z_begin, nz_local; /* this rank's z-slab                              */
@@ -64,8 +66,8 @@ typedef struct oi_params {
                                   imbalance is 10x inside the reference's 1e-6
                                   gate (TortuosityHypre.cpp:794-803); 0: stop on
                                   the residual rule alone                          */
-    int32_t rank, n_ranks;     /* z-slab decomposition                             */
-    const void* nccl_unique_id;/* 128-byte ncclUniqueId when n_ranks > 1, else NULL */
+    struct oi_comm* comm;      /* z-slab communicator (oi_comm_create) or NULL for
+                                  a single slab; must outlive the handle            */
 } oi_params;
 
 typedef struct oi_solve_info {
@@ -78,11 +80,22 @@ typedef struct oi_solve_info {
 } oi_solve_info;
 
 typedef struct oi_solver oi_solver; /* opaque */
+typedef struct oi_comm oi_comm;     /* opaque */
 
 int         oi_version(void);
 const char* oi_last_error(void);
 int         oi_device_count(int* count);
 void        oi_default_params(oi_params* p);
+
+/* ---- z-slab communicator --------------------------------------------------
+ * Stands in for MPI_COMM_WORLD of the reference (TortuosityHypre.cpp:211,
+ * 463-484; AMReX FillBoundary / ParallelDescriptor::Reduce*): one process per
+ * GPU, rank r owns slab r, halo planes and scalar reductions go over NCCL.
+ * id128 is a 128-byte ncclUniqueId made by oi_comm_unique_id on one rank and
+ * distributed by the host program (torch.distributed, MPI_Bcast, a file ...). */
+int oi_comm_unique_id(void* id128_out);
+int oi_comm_create(oi_comm** out, int32_t rank, int32_t n_ranks, const void* id128, int32_t device);
+int oi_comm_destroy(oi_comm* c);
 
 /* ---- VolumeFraction::value, src/props/VolumeFraction.cpp:22-66 ---------- */
 /* Count cells == phase in a host field (copied to the device, counted there).
@@ -148,6 +161,11 @@ int oi_apply_precond(oi_solver* h, const double* host_r, double* host_z);
  *       | "count_phase" */
 int oi_time_kernel(oi_solver* h, const char* name, int32_t reps, double* avg_ms,
                    int64_t* cells);
+/* CUDA-event stopwatch on the solver's own stream (the stream every kernel of
+ * this handle is launched on): record slot 0..7, then elapsed ms between two
+ * recorded slots (synchronises on the later one). */
+int oi_timer_record(oi_solver* h, int32_t slot);
+int oi_timer_elapsed_ms(oi_solver* h, int32_t slot_begin, int32_t slot_end, double* ms);
 /* Number of kernels this handle has launched since creation. */
 int oi_launch_count(oi_solver* h, int64_t* launches);
 

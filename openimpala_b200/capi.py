@@ -36,8 +36,7 @@ class oi_params(C.Structure):
         ("maxiter", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32),
         ("precond", C.c_int32), ("mg_degree", C.c_int32), ("stencil_variant", C.c_int32),
         ("flux_polish", C.c_int32),
-        ("rank", C.c_int32), ("n_ranks", C.c_int32),
-        ("nccl_unique_id", C.c_void_p),
+        ("comm", C.c_void_p),
     ]
 
 
@@ -56,6 +55,9 @@ _SIGS = {
     "oi_last_error": (C.c_char_p, []),
     "oi_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "oi_default_params": (None, [C.POINTER(oi_params)]),
+    "oi_comm_unique_id": (C.c_int, [_P]),
+    "oi_comm_create": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P, C.c_int32]),
+    "oi_comm_destroy": (C.c_int, [_P]),
     "oi_count_phase_i32": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_count_phase_u8": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_create": (C.c_int, [C.POINTER(_P), C.POINTER(oi_params)]),
@@ -79,6 +81,8 @@ _SIGS = {
     "oi_apply_operator": (C.c_int, [_P, _P, _P]),
     "oi_apply_precond": (C.c_int, [_P, _P, _P]),
     "oi_time_kernel": (C.c_int, [_P, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "oi_timer_record": (C.c_int, [_P, C.c_int32]),
+    "oi_timer_elapsed_ms": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "oi_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -131,14 +135,62 @@ def count_phase(field: np.ndarray, phase: int):
     return pc.value, tc.value
 
 
+def comm_unique_id() -> bytes:
+    """128-byte ncclUniqueId (call on one rank, hand the bytes to the others)."""
+    buf = C.create_string_buffer(128)
+    _check(load().oi_comm_unique_id(C.cast(buf, _P)))
+    return buf.raw
+
+
+class Comm:
+    """z-slab communicator: rank r owns slab r (stands in for MPI_COMM_WORLD)."""
+
+    def __init__(self, rank: int, n_ranks: int, unique_id: bytes, device: int = -1):
+        self._lib = load()
+        self._h = _P(None)
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(self._lib.oi_comm_create(C.byref(self._h), self.rank, self.n_ranks, C.cast(buf, _P), device))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            self._lib.oi_comm_destroy(self._h)
+            self._h = _P(None)
+
+
+def slab_partition(nz: int, n_ranks: int, align: int = 0):
+    """Contiguous z-slabs [(z_begin, nz_local)] whose boundaries are multiples of
+    `align` planes (so 2x2x2 multigrid aggregates never straddle ranks).
+    align = 0 picks the largest power of two <= nz // n_ranks, capped at 64."""
+    if n_ranks <= 1:
+        return [(0, nz)]
+    if align <= 0:
+        align = 1
+        while align * 2 <= max(1, nz // n_ranks) and align < 64:
+            align *= 2
+    blocks = nz // align
+    if blocks < n_ranks:
+        raise ValueError(f"nz={nz} too small for {n_ranks} slabs aligned to {align}")
+    out, z = [], 0
+    for r in range(n_ranks):
+        nb = blocks // n_ranks + (1 if r < blocks % n_ranks else 0)
+        n = nb * align if r < n_ranks - 1 else nz - z
+        out.append((z, n))
+        z += n
+    return out
+
+
 class Solver:
     """Thin RAII wrapper of one oi_solver handle (one image / phase / direction)."""
 
     def __init__(self, shape, direction: int, phase_id: int = 1, vlo: float = 0.0, vhi: float = 1.0,
                  eps: float = 1e-9, maxiter: int = 200, dx=(1.0, 1.0, 1.0), precond: int = OI_PRECOND_MG,
                  mg_degree: int = 0, stencil_variant: int = 0, flux_polish: int = 1, device: int = -1,
-                 z_begin: int = 0, nz_local: int = 0, rank: int = 0, n_ranks: int = 1,
-                 nccl_unique_id: bytes | None = None, verbose: int = 0):
+                 z_begin: int = 0, nz_local: int = 0, comm: "Comm | None" = None, verbose: int = 0):
         self._lib = load()
         self._h = _P(None)
         nz, ny, nx = (int(s) for s in shape)
@@ -151,12 +203,10 @@ class Solver:
         p.eps, p.maxiter, p.verbose, p.device = float(eps), int(maxiter), int(verbose), int(device)
         p.precond, p.mg_degree, p.stencil_variant = int(precond), int(mg_degree), int(stencil_variant)
         p.flux_polish = int(flux_polish)
-        p.rank, p.n_ranks = int(rank), int(n_ranks)
-        self._id_buf = None
-        if nccl_unique_id is not None:
-            self._id_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
-            p.nccl_unique_id = C.cast(self._id_buf, C.c_void_p)
+        self._comm = comm                       # keep the communicator alive
+        p.comm = comm.handle if comm is not None else None
         self.params = p
+        self.global_shape = (nz, ny, nx)
         self.local_shape = (p.nz_local, ny, nx)
         _check(self._lib.oi_create(C.byref(self._h), C.byref(p)))
 
@@ -263,6 +313,14 @@ class Solver:
         ms, cells = C.c_double(0), C.c_int64(0)
         _check(self._lib.oi_time_kernel(self._h, name.encode(), reps, C.byref(ms), C.byref(cells)))
         return ms.value, cells.value
+
+    def timer_record(self, slot: int):
+        _check(self._lib.oi_timer_record(self._h, slot))
+
+    def timer_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0)
+        _check(self._lib.oi_timer_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
 
     def launch_count(self) -> int:
         n = C.c_int64(0)

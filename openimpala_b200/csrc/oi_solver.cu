@@ -47,6 +47,7 @@ struct OiError : std::runtime_error {
 // ------------------------------------------------------------------ NCCL (lazy)
 struct NcclApi {
     void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -72,6 +73,7 @@ NcclApi& nccl_api() {
         if (!p) throw OiError(OI_ERR_NCCL, std::string("libnccl lacks ") + s);
         return p;
     };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
@@ -122,8 +124,14 @@ struct HostLevel {
 
 }  // namespace
 
+struct oi_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1, device = 0;
+};
+
 struct oi_solver {
     oi_params prm{};
+    int rank = 0, n_ranks = 1;
     int device = 0, n_sm = 148;
     cudaStream_t st = nullptr;
     oi::Grid g{};
@@ -156,6 +164,7 @@ struct oi_solver {
     oi_solve_info info{};
     long long launches = 0;
     double setup_ms = 0.0;
+    cudaEvent_t timer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -182,10 +191,10 @@ ncclDataType_t nccl_bytes_type() { return ncclUint8; }
 
 void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long long nz) {
     // send plane 0 down / plane nz-1 up; receive into plane -1 / plane nz
-    if (S->prm.n_ranks <= 1) return;
+    if (S->n_ranks <= 1) return;
     NcclApi& N = nccl_api();
     char* p0 = static_cast<char*>(plane0);
-    const int rk = S->prm.rank, nr = S->prm.n_ranks;
+    const int rk = S->rank, nr = S->n_ranks;
     NCCL_CHECK(N.GroupStart());
     if (rk > 0) {
         NCCL_CHECK(N.Send(p0, plane_bytes, ncclUint8, rk - 1, S->comm, S->st));
@@ -206,15 +215,15 @@ inline void haloL(oi_solver* S, const CoarseLevel& L, double* v) {
 }
 
 void allreduce_sum_f64(oi_solver* S, double* d, int n) {
-    if (S->prm.n_ranks <= 1) return;
+    if (S->n_ranks <= 1) return;
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclFloat64, ncclSum, S->comm, S->st));
 }
 void allreduce_sum_u64(oi_solver* S, unsigned long long* d, int n) {
-    if (S->prm.n_ranks <= 1) return;
+    if (S->n_ranks <= 1) return;
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclUint64, ncclSum, S->comm, S->st));
 }
 void allreduce_max_i32(oi_solver* S, int* d, int n) {
-    if (S->prm.n_ranks <= 1) return;
+    if (S->n_ranks <= 1) return;
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclInt32, ncclMax, S->comm, S->st));
 }
 
@@ -257,7 +266,7 @@ void free_vectors(oi_solver* S) {
 void build_hierarchy(oi_solver* S) {
     free_levels(S);
     if (S->prm.precond != OI_PRECOND_MG) { S->hierarchy_built = true; return; }
-    const int nr = S->prm.n_ranks, rk = S->prm.rank;
+    const int nr = S->n_ranks, rk = S->rank;
     // per-rank slab table at the current level
     std::vector<int> z0 = S->all_z0, nz = S->all_nz;
     int nx = S->g.nx, ny = S->g.ny, nzg = S->g.nzg;
@@ -557,12 +566,12 @@ void build_mask(oi_solver* S) {
     oi::ccl_mark_planes(S->d_isphase, d_labels, d_reach, g.nx, g.ny, g.nz, dir, lo_local, hi_local,
                         S->n_sm, S->st); S->launches++;
 
-    if (S->prm.n_ranks > 1) {
+    if (S->n_ranks > 1) {
         // propagate the inlet/outlet reach bits across slab boundaries to a fixed point
         NcclApi& N = nccl_api();
         const size_t pb = (size_t)g.plane;
         CUDA_CHECK(cudaMalloc(&d_bits, 4 * pb));
-        const int rk = S->prm.rank, nr = S->prm.n_ranks;
+        const int rk = S->rank, nr = S->n_ranks;
         for (int round = 0; round < 4 * nr + 1024; ++round) {
             CUDA_CHECK(cudaMemsetAsync(S->d_changed, 0, sizeof(int), S->st));
             CUDA_CHECK(cudaMemsetAsync(d_bits + 2 * pb, 0, 2 * pb, S->st));
@@ -744,8 +753,45 @@ void oi_default_params(oi_params* p) {
     p->mg_degree = 0;
     p->stencil_variant = 0;
     p->flux_polish = 1;
-    p->rank = 0; p->n_ranks = 1;
-    p->nccl_unique_id = nullptr;
+    p->comm = nullptr;
+}
+
+int oi_comm_unique_id(void* id128_out) {
+    return guarded([&] {
+        OI_REQUIRE(id128_out, "null argument");
+        ncclUniqueId id;
+        NCCL_CHECK(nccl_api().GetUniqueId(&id));
+        static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+        std::memcpy(id128_out, &id, sizeof(id));
+    });
+}
+
+int oi_comm_create(oi_comm** out, int32_t rank, int32_t n_ranks, const void* id128, int32_t device) {
+    return guarded([&] {
+        OI_REQUIRE(out && id128, "null argument");
+        *out = nullptr;
+        OI_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
+        int ndev = 0;
+        require_gpu(&ndev);
+        std::unique_ptr<oi_comm> c(new oi_comm());
+        c->rank = rank; c->n_ranks = n_ranks;
+        if (device >= 0) { OI_REQUIRE(device < ndev, "device ordinal out of range"); c->device = device; }
+        else CUDA_CHECK(cudaGetDevice(&c->device));
+        CUDA_CHECK(cudaSetDevice(c->device));
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        NCCL_CHECK(nccl_api().CommInitRank(&c->comm, n_ranks, id, rank));
+        *out = c.release();
+    });
+}
+
+int oi_comm_destroy(oi_comm* c) {
+    if (!c) return OI_OK;
+    return guarded([&] {
+        cudaSetDevice(c->device);
+        if (c->comm) nccl_api().CommDestroy(c->comm);
+        delete c;
+    });
 }
 
 int oi_count_phase_i32(const int32_t* f, int64_t n, int32_t phase, int64_t* pc, int64_t* tc) {
@@ -764,9 +810,10 @@ int oi_create(oi_solver** out, const oi_params* p) {
         OI_REQUIRE(p->eps > 0.0, "Solver tolerance (eps) must be positive");          // TortuosityHypre.cpp:159
         OI_REQUIRE(p->maxiter > 0, "Solver max iterations must be positive");         // :160
         OI_REQUIRE(p->dx[0] > 0 && p->dx[1] > 0 && p->dx[2] > 0, "cell size must be positive");
-        OI_REQUIRE(p->n_ranks >= 1 && p->rank >= 0 && p->rank < p->n_ranks, "bad rank / n_ranks");
+        const int n_ranks = p->comm ? p->comm->n_ranks : 1;
+        const int rank = p->comm ? p->comm->rank : 0;
         int nzl = p->nz_local, z0 = p->z_begin;
-        if (p->n_ranks == 1 && nzl <= 0) { nzl = p->nz; z0 = 0; }
+        if (n_ranks == 1 && nzl <= 0) { nzl = p->nz; z0 = 0; }
         OI_REQUIRE(nzl > 0 && z0 >= 0 && z0 + nzl <= p->nz, "bad z-slab");
         OI_REQUIRE((long long)p->nx * p->ny * (nzl + 2) < 2147483647LL,
                    "slab exceeds 2^31 cells; use more z-slabs");
@@ -775,8 +822,12 @@ int oi_create(oi_solver** out, const oi_params* p) {
         std::unique_ptr<oi_solver> S(new oi_solver());
         S->prm = *p;
         S->prm.nz_local = nzl; S->prm.z_begin = z0;
-        S->prm.nccl_unique_id = nullptr;
-        if (p->device >= 0) {
+        S->rank = rank; S->n_ranks = n_ranks;
+        if (p->comm) {
+            S->comm = p->comm->comm;
+            S->device = p->comm->device;
+            OI_REQUIRE(p->device < 0 || p->device == p->comm->device, "device differs from the communicator's");
+        } else if (p->device >= 0) {
             OI_REQUIRE(p->device < ndev, "device ordinal out of range");
             S->device = p->device;
         } else {
@@ -809,26 +860,22 @@ int oi_create(oi_solver** out, const oi_params* p) {
         CUDA_CHECK(cudaMemset(S->d_ull, 0, 8 * sizeof(unsigned long long)));
         CUDA_CHECK(cudaMalloc(&S->d_changed, sizeof(int)));
         CUDA_CHECK(cudaMallocHost(&S->h_pinned, 16 * sizeof(double)));
-        S->all_z0.assign(p->n_ranks, 0);
-        S->all_nz.assign(p->n_ranks, 0);
+        S->all_z0.assign(n_ranks, 0);
+        S->all_nz.assign(n_ranks, 0);
         S->all_z0[0] = z0; S->all_nz[0] = nzl;
-        if (p->n_ranks > 1) {
-            OI_REQUIRE(p->nccl_unique_id != nullptr, "n_ranks > 1 needs nccl_unique_id");
+        if (n_ranks > 1) {
             NcclApi& N = nccl_api();
-            ncclUniqueId id;
-            std::memcpy(&id, p->nccl_unique_id, sizeof(id));
-            NCCL_CHECK(N.CommInitRank(&S->comm, p->n_ranks, id, p->rank));
             int* d_tab = nullptr;
-            CUDA_CHECK(cudaMalloc(&d_tab, (size_t)(2 * p->n_ranks + 2) * sizeof(int)));
+            CUDA_CHECK(cudaMalloc(&d_tab, (size_t)(2 * n_ranks + 2) * sizeof(int)));
             int mine[2] = {z0, nzl};
             CUDA_CHECK(cudaMemcpyAsync(d_tab, mine, sizeof(mine), cudaMemcpyHostToDevice, S->st));
             NCCL_CHECK(N.AllGather(d_tab, d_tab + 2, 2, ncclInt32, S->comm, S->st));
-            std::vector<int> tab(2 * p->n_ranks);
+            std::vector<int> tab(2 * n_ranks);
             CUDA_CHECK(cudaMemcpyAsync(tab.data(), d_tab + 2, tab.size() * sizeof(int), cudaMemcpyDeviceToHost, S->st));
             CUDA_CHECK(cudaStreamSynchronize(S->st));
             cudaFree(d_tab);
             int expect = 0;
-            for (int r = 0; r < p->n_ranks; ++r) {
+            for (int r = 0; r < n_ranks; ++r) {
                 S->all_z0[r] = tab[2 * r]; S->all_nz[r] = tab[2 * r + 1];
                 OI_REQUIRE(S->all_z0[r] == expect, "z-slabs must tile [0,nz) in rank order");
                 expect += S->all_nz[r];
@@ -854,7 +901,7 @@ int oi_destroy(oi_solver* S) {
         if (S->d_ull) cudaFree(S->d_ull);
         if (S->d_changed) cudaFree(S->d_changed);
         if (S->h_pinned) cudaFreeHost(S->h_pinned);
-        if (S->comm) nccl_api().CommDestroy(S->comm);
+        for (auto& e : S->timer) if (e) cudaEventDestroy(e);
         if (S->st) cudaStreamDestroy(S->st);
         delete S;
     });
@@ -879,7 +926,7 @@ int oi_volume_fraction(oi_solver* S, int64_t* pc, int64_t* tc) {
         OI_REQUIRE(S->phase_count_local >= 0, "oi_volume_fraction: call oi_set_phase_* first");
         ensure_device(S);
         unsigned long long h = (unsigned long long)S->phase_count_local;
-        if (S->prm.n_ranks > 1) {
+        if (S->n_ranks > 1) {
             CUDA_CHECK(cudaMemcpyAsync(S->d_ull + 5, &h, sizeof(h), cudaMemcpyHostToDevice, S->st));
             allreduce_sum_u64(S, S->d_ull + 5, 1);
             CUDA_CHECK(cudaMemcpyAsync(&h, S->d_ull + 5, sizeof(h), cudaMemcpyDeviceToHost, S->st));
@@ -1081,6 +1128,26 @@ int oi_time_kernel(oi_solver* S, const char* name, int32_t reps, double* avg_ms,
         S->solved = false;
         if (avg_ms) *avg_ms = (double)ms / reps;
         if (cells) *cells = n;
+    });
+}
+
+int oi_timer_record(oi_solver* S, int32_t slot) {
+    return guarded([&] {
+        OI_REQUIRE(S && slot >= 0 && slot < 8, "bad timer slot");
+        ensure_device(S);
+        if (!S->timer[slot]) CUDA_CHECK(cudaEventCreate(&S->timer[slot]));
+        CUDA_CHECK(cudaEventRecord(S->timer[slot], S->st));
+    });
+}
+
+int oi_timer_elapsed_ms(oi_solver* S, int32_t a, int32_t b, double* ms) {
+    return guarded([&] {
+        OI_REQUIRE(S && ms && a >= 0 && a < 8 && b >= 0 && b < 8 && S->timer[a] && S->timer[b], "bad timer slot");
+        ensure_device(S);
+        CUDA_CHECK(cudaEventSynchronize(S->timer[b]));
+        float f = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&f, S->timer[a], S->timer[b]));
+        *ms = (double)f;
     });
 }
 

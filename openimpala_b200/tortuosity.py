@@ -146,13 +146,15 @@ class TortuosityHypre:
         self._active_vf = 0.0
         self.last_info = None
 
-        self._solver = capi.Solver(self._phase_field.shape, int(self._dir), self._phase, self._vlo,
+        # multi-GPU: mf_phase_input is this rank's z-slab, `global_shape` the whole box
+        shape = b200.pop("global_shape", None) or self._phase_field.shape
+        self._solver = capi.Solver(shape, int(self._dir), self._phase, self._vlo,
                                    self._vhi, eps=self._eps, maxiter=self._maxiter, dx=self._dx,
                                    verbose=self._verbose, **b200)
         self._solver.set_phase(self._phase_field)
         self._solver.remspot(ParmParse.query("tortuosity.remspot_passes", 0))     # :248-292
         n_active = self._solver.build_mask()                                       # :394-558
-        total = self._phase_field.size
+        total = int(np.prod(self._solver.global_shape))   # Geometry::Domain().numPts()
         self._n_active = n_active
         self._active_vf = (n_active / total) if total > 0 else 0.0                  # :552-553
         if self._active_vf <= _EPS:                                                 # :170-178
@@ -194,7 +196,7 @@ class TortuosityHypre:
                 self._first_call = False
                 return self._value
             self._flux_in, self._flux_out, _, _ = self._solver.fluxes()             # :790
-            nz, ny, nx = self._phase_field.shape
+            nz, ny, nx = self._solver.global_shape
             ext = (nx * self._dx[0], ny * self._dx[1], nz * self._dx[2])            # ProbLength
             d = int(self._dir)
             length = ext[d]
