@@ -61,7 +61,8 @@ typedef struct oi_params {
     int32_t device;            /* CUDA device ordinal, -1 = current               */
     int32_t precond;           /* oi_precond                                      */
     int32_t mg_degree;         /* smoother polynomial degree per leg, 0 = default */
-    int32_t stencil_variant;   /* 0 = z-plane staged (default), 1 = simple gather  */
+    int32_t stencil_variant;   /* 0 = z-plane ring in shared memory (cp.async, default),
+                                  2 = register z-march, 1 = simple gather            */
     int32_t flux_polish;       /* 1: keep iterating (<= maxiter) until the flux
                                   imbalance is 10x inside the reference's 1e-6
                                   gate (TortuosityHypre.cpp:794-803); 0: stop on

@@ -24,7 +24,7 @@ struct L0Args {
 long long l0_max_blocks(const Grid& g, int n_sm);
 void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st);
 void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st);
-void l0_residual_restrict(const L0Args& a, cudaStream_t st);
+void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st);
 void l0_residual(const L0Args& a, cudaStream_t st);
 void l0_jacobi_first(const L0Args& a, cudaStream_t st);
 

@@ -146,6 +146,8 @@ struct oi_solver {
     long long phase_count_local = -1;
     long long n_active = -1, n_in = 0, n_out = 0;
     bool mask_built = false, hierarchy_built = false, solved = false;
+    bool levels_allocated = false, vectors_allocated = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // Krylov vectors
     Field<double> x, r, p, q, z;
     // scalars / reductions
@@ -256,6 +258,7 @@ void free_levels(oi_solver* S) {
     }
     S->levels.clear();
     S->hierarchy_built = false;
+    S->levels_allocated = false;
 }
 
 void free_vectors(oi_solver* S) {
@@ -263,11 +266,11 @@ void free_vectors(oi_solver* S) {
 }
 
 // ------------------------------------------------------------------ hierarchy
-void build_hierarchy(oi_solver* S) {
-    free_levels(S);
-    if (S->prm.precond != OI_PRECOND_MG) { S->hierarchy_built = true; return; }
+void allocate_hierarchy(oi_solver* S) {
+    // Level shapes depend only on the box and the slab table, so the arrays are
+    // allocated once per handle and reused by every rebuild.
+    if (S->levels_allocated) return;
     const int nr = S->n_ranks, rk = S->rank;
-    // per-rank slab table at the current level
     std::vector<int> z0 = S->all_z0, nz = S->all_nz;
     int nx = S->g.nx, ny = S->g.ny, nzg = S->g.nzg;
     L0Info f0{1, 1, 1};
@@ -299,11 +302,17 @@ void build_hierarchy(oi_solver* S) {
         h.L.x = h.x.p; h.L.b = h.b.p; h.L.t = h.t.p;
     }
     S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
-    // operators
+    S->levels_allocated = true;
+}
+
+void build_hierarchy(oi_solver* S) {
+    if (S->prm.precond != OI_PRECOND_MG) { S->hierarchy_built = true; return; }
+    allocate_hierarchy(S);
+    std::vector<HostLevel>& lv = S->levels;
     for (size_t l = 0; l < lv.size(); ++l) {
         if (l == 0) {
             oi::coarse_build_from_flags(S->g, S->flags.p, S->prm.direction, S->n_dir, lv[0].L,
-                                        f0.fx, f0.fy, f0.fz, S->mg_scale, S->st);
+                                        S->fx0, S->fy0, S->fz0, S->mg_scale, S->st);
         } else {
             oi::coarse_build_from_coarse(lv[l - 1].L, lv[l].L, S->mg_scale, S->st);
         }
@@ -313,7 +322,6 @@ void build_hierarchy(oi_solver* S) {
         halo_exchange_bytes(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
         halo_exchange_bytes(S, lv[l].dg.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
     }
-    CUDA_CHECK(cudaStreamSynchronize(S->st));
     S->hierarchy_built = true;
 }
 
@@ -383,8 +391,8 @@ void apply_precond(oi_solver* S, double* dot_out) {
         {
             L0Args a = l0args(S, cur, S->r.p, h1.L.b, 0.0, nullptr);
             a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
-            if (variant == 0) {
-                oi::l0_residual_restrict(a, S->st); S->launches++;
+            if (variant != 1) {
+                oi::l0_residual_restrict(a, variant, S->st); S->launches++;
             } else {
                 // unfused cross-check path: residual to scratch, gather-restrict
                 a.out = oth;
@@ -457,8 +465,8 @@ void run_solve(oi_solver* S) {
     info.b_norm = bnorm;
     if (S->n_active <= 0) { info.converged = 0; return; }
 
-    cudaEvent_t e0, e1, e2;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
+    for (auto& e : S->ev) if (!e) CUDA_CHECK(cudaEventCreate(&e));
+    cudaEvent_t e0 = S->ev[0], e1 = S->ev[1], e2 = S->ev[2];
     CUDA_CHECK(cudaEventRecord(e0, S->st));
     if (!S->hierarchy_built) build_hierarchy(S);
     CUDA_CHECK(cudaEventRecord(e1, S->st));
@@ -527,7 +535,6 @@ void run_solve(oi_solver* S) {
     float ms01 = 0, ms12 = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms01, e0, e1));
     CUDA_CHECK(cudaEventElapsedTime(&ms12, e1, e2));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     info.setup_ms = ms01;
     info.solve_ms = ms12;
     info.iterations = it;
@@ -545,15 +552,20 @@ void build_mask(oi_solver* S) {
     const Grid& g = S->g;
     const long long n = S->n_local;
     const int dir = S->prm.direction;
-    free_levels(S);
-    free_vectors(S);
+    S->hierarchy_built = false;
     S->solved = false;
-    int* d_labels = nullptr;
-    unsigned int* d_reach = nullptr;
-    uint8_t* d_bits = nullptr;   // 4 planes: send lo, send hi, recv lo, recv hi
-    CUDA_CHECK(cudaMalloc(&d_labels, (size_t)n * sizeof(int)));
+    // Krylov vectors are allocated once per handle; while the mask is being built
+    // they are dead, so the labelling scratch aliases them (no cudaMalloc/cudaFree
+    // in the steady-state step): labels -> p, reach bytes -> q, plane bits -> z.
+    if (!S->vectors_allocated) {
+        S->x.alloc(g.plane, g.nz); S->r.alloc(g.plane, g.nz); S->p.alloc(g.plane, g.nz);
+        S->q.alloc(g.plane, g.nz); S->z.alloc(g.plane, g.nz);
+        S->vectors_allocated = true;
+    }
+    int* d_labels = reinterpret_cast<int*>(S->p.p);
+    unsigned int* d_reach = reinterpret_cast<unsigned int*>(S->q.p);
+    uint8_t* d_bits = reinterpret_cast<uint8_t*>(S->z.p);   // 4 planes: send lo, send hi, recv lo, recv hi
     const size_t reach_words = (size_t)(n + 3) / 4 + 1;
-    CUDA_CHECK(cudaMalloc(&d_reach, reach_words * sizeof(unsigned int)));
     CUDA_CHECK(cudaMemsetAsync(d_reach, 0, reach_words * sizeof(unsigned int), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
 
@@ -570,7 +582,6 @@ void build_mask(oi_solver* S) {
         // propagate the inlet/outlet reach bits across slab boundaries to a fixed point
         NcclApi& N = nccl_api();
         const size_t pb = (size_t)g.plane;
-        CUDA_CHECK(cudaMalloc(&d_bits, 4 * pb));
         const int rk = S->rank, nr = S->n_ranks;
         for (int round = 0; round < 4 * nr + 1024; ++round) {
             CUDA_CHECK(cudaMemsetAsync(S->d_changed, 0, sizeof(int), S->st));
@@ -612,16 +623,20 @@ void build_mask(oi_solver* S) {
     S->n_active = (long long)h[0];
     S->n_in = (long long)h[1];
     S->n_out = (long long)h[2];
-    cudaFree(d_labels); cudaFree(d_reach);
-    if (d_bits) cudaFree(d_bits);
+    // the scratch aliases held integers: restore the vectors' invariant (zero
+    // everywhere, ghost planes included) before they are used as fp64 fields
+    CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->z.base, 0, S->z.count * sizeof(double), S->st));
 
-    // Krylov vectors + initial guess (skipped when nothing percolates, like the
-    // reference's early return TortuosityHypre.cpp:170-178)
+    // initial guess (skipped when nothing percolates, like the reference's early
+    // return TortuosityHypre.cpp:170-178)
     if (S->n_active > 0) {
-        S->x.alloc(g.plane, g.nz); S->r.alloc(g.plane, g.nz); S->p.alloc(g.plane, g.nz);
-        S->q.alloc(g.plane, g.nz); S->z.alloc(g.plane, g.nz);
         oi::fill_initial_guess(g, S->flags.p, S->x.p, dir, S->n_dir, S->prm.vlo, S->prm.vhi, 0, S->st);
         S->launches++;
+        CUDA_CHECK(cudaStreamSynchronize(S->st));
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(S->x.base, 0, S->x.count * sizeof(double), S->st));
         CUDA_CHECK(cudaStreamSynchronize(S->st));
     }
     S->mask_built = true;
@@ -902,6 +917,7 @@ int oi_destroy(oi_solver* S) {
         if (S->d_changed) cudaFree(S->d_changed);
         if (S->h_pinned) cudaFreeHost(S->h_pinned);
         for (auto& e : S->timer) if (e) cudaEventDestroy(e);
+        for (auto& e : S->ev) if (e) cudaEventDestroy(e);
         if (S->st) cudaStreamDestroy(S->st);
         delete S;
     });
@@ -1099,7 +1115,7 @@ int oi_time_kernel(oi_solver* S, const char* name, int32_t reps, double* avg_ms,
                 OI_REQUIRE(!S->levels.empty(), "no coarse level");
                 L0Args a = l0args(S, S->z.p, S->r.p, S->levels[0].L.b, 0.0, nullptr);
                 a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
-                oi::l0_residual_restrict(a, S->st);
+                oi::l0_residual_restrict(a, variant == 1 ? 0 : variant, S->st);
             } else if (k == "axpy2_dot") {
                 oi::vec_axpy2_dot(n, S->z.p, S->q.p, S->p.p, S->r.p, S->d_scal + 10, S->d_scal + 11,
                                   S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);

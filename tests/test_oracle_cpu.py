@@ -1,0 +1,170 @@
+"""CPU-side tests (run without a GPU): the oracle against the reference's own
+fixtures / invariants and the committed golden vectors, the two restatements
+(numpy and C) against each other, and the analytic known answers."""
+import hashlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SAMPLE_TIFF
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import oi_numpy
+    return oi_numpy
+
+
+@pytest.fixture(scope="module")
+def oc():
+    from oracle import oi_c
+    oi_c.load()
+    return oi_c
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+
+
+def _blobs(shape, seed, porosity=0.5, sigma=1.5):
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    f = ndimage.gaussian_filter(rng.standard_normal(shape), sigma)
+    return (f > np.quantile(f, 1.0 - porosity)).astype(np.int32)
+
+
+# ---- reader facts pinned by the reference's tTiffReader (src/io/tTiffReader.cpp:98-219)
+def test_sample_tiff_reader_facts(o, gold):
+    assert hashlib.md5(open(SAMPLE_TIFF, "rb").read()).hexdigest() == gold["md5"]
+    raw = o.read_tiff_raw(SAMPLE_TIFF)
+    assert raw.shape == (100, 100, 100)                  # width/height/depth 100
+    bo, ifds = o._read_ifds(open(SAMPLE_TIFF, "rb").read())
+    assert ifds[0].get(258, (1,))[0] == 1                # BitsPerSample 1
+    assert ifds[0].get(339, (1,))[0] == 1                # SampleFormat UINT
+    assert ifds[0].get(277, (1,))[0] == 1                # SamplesPerPixel 1
+    ph = o.threshold(raw, 0.5)
+    assert ph.min() == 0 and ph.max() == 1               # thresholded min/max
+
+
+def test_sample_tiff_matches_pillow(o):
+    Image = pytest.importorskip("PIL.Image")
+    im = Image.open(SAMPLE_TIFF)
+    frames = []
+    for k in range(im.n_frames):
+        im.seek(k)
+        frames.append(np.array(im.convert("L")) > 0)
+    assert np.array_equal(np.stack(frames), o.read_tiff_raw(SAMPLE_TIFF) > 0.5)
+
+
+# ---- VolumeFraction (tVolumeFraction.cpp: counts == independent loop; VF0+VF1 == 1)
+def test_volume_fraction_sample(o, oc, sample_phase, gold):
+    for pid in (0, 1):
+        pc, tc = o.volume_fraction_counts(sample_phase, pid)
+        assert pc == gold["phase_count"][str(pid)] and tc == 1_000_000
+        assert oc.count_phase(sample_phase, pid) == pc
+    assert gold["phase_count"]["1"] == 398309 and gold["phase_count"]["0"] == 601691
+
+
+# ---- percolation mask
+def test_mask_sample_golden(o, oc, sample_phase, gold):
+    for case in gold["cases"]:
+        m = o.activity_mask(sample_phase, case["phase"], case["direction"])
+        assert int(m.sum()) == case["n_active"]
+        assert hashlib.sha256(m.astype("u1").tobytes()).hexdigest() == case["mask_sha256"]
+    # the reference's literal capped sweep reaches the same fixed point on the sample
+    mc, n = oc.activity_mask(sample_phase, 1, 0, capped=True)
+    assert n == 397743 and np.array_equal(mc.astype(bool), o.activity_mask(sample_phase, 1, 0))
+
+
+@pytest.mark.parametrize("shape,seed", [((9, 11, 13), 1), ((16, 16, 16), 2), ((5, 30, 7), 3)])
+def test_mask_three_ways(o, oc, shape, seed):
+    ph = _blobs(shape, seed, 0.55)
+    for d in range(3):
+        for pid in (0, 1):
+            a = o.activity_mask(ph, pid, d)
+            b, _ = o.activity_mask_flood(ph, pid, d)
+            c, n = oc.activity_mask(ph, pid, d)
+            assert np.array_equal(a, b) and np.array_equal(a, c.astype(bool)) and n == int(a.sum())
+
+
+# ---- tortuosity_fillmtx + the reference's own invariants (checkMatrixProperties)
+@pytest.mark.parametrize("shape,seed", [((9, 11, 13), 1), ((16, 16, 16), 2), ((12, 7, 20), 4)])
+def test_fillmtx_numpy_vs_c_and_invariants(o, oc, shape, seed):
+    ph = _blobs(shape, seed, 0.6)
+    for d in range(3):
+        mask = o.activity_mask(ph, 1, d)
+        a, rhs, x0 = o.fill_matrix(ph, mask, 1, d, -1.0, 1.0, dx=(1.0, 0.5, 2.0))
+        a2, rhs2, x02 = oc.fill_matrix(ph, mask, 1, d, -1.0, 1.0, dx=(1.0, 0.5, 2.0))
+        assert np.array_equal(a, a2) and np.array_equal(rhs, rhs2)
+        np.testing.assert_allclose(x0, x02, rtol=0, atol=1e-15)
+        assert o.check_matrix_properties(a, rhs, mask, d, -1.0, 1.0, shape)
+
+
+def test_sample_matrix_invariants(o, sample_phase):
+    # tTortuosity.inputs: phase 0, direction X
+    mask = o.activity_mask(sample_phase, 0, 0)
+    a, rhs, _ = o.fill_matrix(sample_phase, mask, 0, 0, 0.0, 1.0)
+    assert o.check_matrix_properties(a, rhs, mask, 0, 0.0, 1.0, sample_phase.shape)
+
+
+# ---- analytic known answers
+@pytest.mark.parametrize("n", [8, 16])
+def test_uniform_block(o, oc, n):
+    ph = np.ones((n, n, n), dtype=np.int32)
+    for d in range(3):
+        assert abs(o.tortuosity(ph, 1, d).tau - (n - 1) / n) < 1e-12
+        assert abs(oc.tortuosity(ph, 1, d)["tau"] - (n - 1) / n) < 1e-12
+
+
+def test_half_slab_and_blocked(o, oc):
+    n = 8
+    ph = np.zeros((n, n, n), dtype=np.int32)
+    ph[:, : n // 2, :] = 1
+    r = o.tortuosity(ph, 1, 0)
+    assert r.active_vf == 0.5 and abs(r.tau - (n - 1) / n) < 1e-12
+    r = o.tortuosity(ph, 1, 1)
+    assert r.active_vf == 0.0 and math.isnan(r.tau)
+    c = oc.tortuosity(ph, 1, 1)
+    assert c["n_active"] == 0 and math.isnan(c["tau"])
+
+
+def test_tau_edge_conventions(o):
+    shape = (4, 4, 4)
+    assert math.isnan(o.tau_from_fluxes(-1.0, -1.0, 0.0, shape, 0, 0.0, 1.0)[0])          # active_vf 0
+    assert math.isnan(o.tau_from_fluxes(-1.0, -1.1, 0.5, shape, 0, 0.0, 1.0)[0])          # not conserved
+    assert math.isinf(o.tau_from_fluxes(0.0, 0.0, 0.5, shape, 0, 0.0, 1.0)[0])            # zero flux
+    assert math.isnan(o.tau_from_fluxes(-1.0, -1.0, 0.5, shape, 0, 0.0, 1.0, converged=False)[0])
+
+
+# ---- solve: C restatement against the golden (scipy) values on the sample image
+@pytest.mark.parametrize("idx", [3])          # phase 1, direction X (BASELINE configs[0])
+def test_sample_tau_c_oracle_vs_golden(oc, sample_phase, gold, idx):
+    case = gold["cases"][idx]
+    r = oc.tortuosity(sample_phase, case["phase"], case["direction"], gold["vlo"], gold["vhi"], eps=1e-10)
+    assert r["n_active"] == case["n_active"]
+    assert abs(r["tau"] - case["tau"]) <= 1e-7 * case["tau"]
+    assert abs(case["tau"] - 3.1330740847) < 1e-9
+
+
+@pytest.mark.parametrize("shape,seed", [((14, 15, 16), 5), ((20, 10, 12), 6)])
+def test_tau_numpy_vs_c(o, oc, shape, seed):
+    ph = _blobs(shape, seed, 0.6)
+    for d in range(3):
+        r = o.tortuosity(ph, 1, d, -1.0, 1.0, eps=1e-12)
+        c = oc.tortuosity(ph, 1, d, -1.0, 1.0, eps=1e-12)
+        assert c["n_active"] == r.n_active
+        if math.isnan(r.tau):
+            assert math.isnan(c["tau"])
+        else:
+            assert abs(c["tau"] - r.tau) <= 1e-9 * abs(r.tau)
+
+
+def test_vlo_vhi_independence(oc):
+    ph = _blobs((12, 12, 12), 9, 0.65)
+    a = oc.tortuosity(ph, 1, 0, -1.0, 1.0, eps=1e-12)["tau"]
+    b = oc.tortuosity(ph, 1, 0, 0.0, 1.0, eps=1e-12)["tau"]
+    assert abs(a - b) <= 1e-9 * abs(a)
