@@ -22,6 +22,12 @@ struct L0Args {
 };
 
 long long l0_max_blocks(const Grid& g, int n_sm);
+int pick_zchunk(const Grid& g, int n_sm);
+// shared-memory ring kernels (oi_level0_ring.cu): mode 0 APPLY, 1 SMOOTH, 2 RESTRICT
+bool ring_supported(const L0Args& a, int mode);
+void ring_launch(const L0Args& a, int mode, bool dot, cudaStream_t st);
+// z += P*ec on unknown cells (prolongation + correction)
+void l0_prolong_add(const L0Args& a, cudaStream_t st);
 void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st);
 void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st);
 void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st);

@@ -197,165 +197,6 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
     }
 }
 
-// ---------------------------------------------------------------------------
-// Ring variant (default): same tiling, but plane k+RING_P+1 of the input field is
-// already on its way into a shared-memory ring (cp.async, LDGSTS) while plane k
-// is computed, so each CTA keeps RING_P+1 planes (x 5.3 KB) of loads in flight
-// instead of one register per thread.  The z-march kernel above is bound by
-// memory latency (one outstanding 8-byte load per thread); the ring removes
-// that limit without spending registers.  flags / rhs are private to a thread
-// and ride in small register queues of the same depth.
-constexpr int RING_P = 4;               // planes in flight beyond k+1
-constexpr int RING_R = RING_P + 2;      // ring stages: planes k-1 .. k+RING_P
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;       // src-size 0: destination is zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int MODE, bool DOT>
-__global__ void __launch_bounds__(NTHREADS)
-l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ u,
-               const double* __restrict__ b, double* __restrict__ out, double w, CoarseRef cr,
-               int zchunk, double* red_partials, unsigned int* red_counter, double* red_out) {
-    __shared__ double ring[RING_R][TY + 2][TX + 2];
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int tx = (warp & 3) * 16 + (lane & 15);
-    const int ty = (warp >> 2) * 2 + (lane >> 4);
-    const int i = blockIdx.x * TX + tx;
-    const int j = blockIdx.y * TY + ty;
-    const bool inb = (i < g.nx) && (j < g.ny);
-    const int k0 = blockIdx.z * zchunk;
-    const int k1 = min(k0 + zchunk, g.nz);
-
-    const bool hx_l = (tx == 0), hx_r = (tx == TX - 1);
-    const bool hy_t = (ty == 0), hy_b = (ty == TY - 1);
-    const int hi_x = hx_l ? i - 1 : i + 1;
-    const int hj_y = hy_t ? j - 1 : j + 1;
-    const bool hx_ok = (hx_l || hx_r) && (j < g.ny) && hi_x >= 0 && hi_x < g.nx;
-    const bool hy_ok = (hy_t || hy_b) && (i < g.nx) && hj_y >= 0 && hj_y < g.ny;
-    const long long col = inb ? (long long)j * g.nx + i : 0;
-    const long long colhx = hx_ok ? (long long)j * g.nx + hi_x : 0;
-    const long long colhy = hy_ok ? (long long)hj_y * g.nx + i : 0;
-    const int hx_col = hx_l ? 0 : TX + 1;
-    const int hy_row = hy_t ? 0 : TY + 1;
-
-    // copies of plane kk (k0-1 <= kk <= k1) into ring stage `st`
-    auto issue = [&](int kk, int st) {
-        const double* pl = u + (long long)kk * g.plane;
-        cp_async8(&ring[st][ty + 1][tx + 1], pl + col, inb);
-        if (hx_l || hx_r) cp_async8(&ring[st][ty + 1][hx_col], pl + colhx, hx_ok);
-        if (hy_t || hy_b) cp_async8(&ring[st][hy_row][tx + 1], pl + colhy, hy_ok);
-    };
-
-    // prologue: planes k0-1 .. k0+RING_P, one commit group per plane (empty
-    // groups keep the count uniform at the end of the chunk)
-#pragma unroll
-    for (int s = 0; s < RING_R; ++s) {
-        const int kk = k0 - 1 + s;
-        if (kk <= k1) issue(kk, s);
-        cp_async_commit();
-    }
-    uint8_t fq[RING_P];
-    double bq[RING_P];
-#pragma unroll
-    for (int s = 0; s < RING_P; ++s) {
-        fq[s] = 0; bq[s] = 0.0;
-        const int kk = k0 + s;
-        if (inb && kk < k1) {
-            fq[s] = flags[(long long)kk * g.plane + col];
-            if (MODE != 0) bq[s] = b[(long long)kk * g.plane + col];
-        }
-    }
-
-    double dot_acc = 0.0, zpair = 0.0;
-    int sc = 1;                              // ring stage of plane k
-
-    for (int k = k0; k < k1; ++k) {
-        cp_async_wait<RING_P - 1>();         // this thread's copies of planes <= k+1 landed
-        __syncthreads();                     // ... and everybody else's
-
-        const int sm = (sc == 0) ? RING_R - 1 : sc - 1;
-        const int sp = (sc == RING_R - 1) ? 0 : sc + 1;
-        const uint8_t f_c = fq[0];
-        const double b_c = bq[0];
-#pragma unroll
-        for (int s = 0; s + 1 < RING_P; ++s) { fq[s] = fq[s + 1]; bq[s] = bq[s + 1]; }
-        {
-            const int kk = k + RING_P;
-            uint8_t fn = 0; double bn = 0.0;
-            if (inb && kk < k1) {
-                fn = flags[(long long)kk * g.plane + col];
-                if (MODE != 0) bn = b[(long long)kk * g.plane + col];
-            }
-            fq[RING_P - 1] = fn; bq[RING_P - 1] = bn;
-        }
-
-        double res = 0.0;
-        if (inb) {
-            double o = 0.0;
-            if (f_c & F_UNK) {
-                const double c = ring[sc][ty + 1][tx + 1];
-                const double xm = ring[sc][ty + 1][tx], xp = ring[sc][ty + 1][tx + 2];
-                const double ym = ring[sc][ty][tx + 1], yp = ring[sc][ty + 2][tx + 1];
-                const double zm = ring[sm][ty + 1][tx + 1], zp = ring[sp][ty + 1][tx + 1];
-                const double au = stencil_au(f_c, g, c, xm, xp, ym, yp, zm, zp);
-                if (MODE == 0) {
-                    o = w * au;
-                    if (DOT) dot_acc += c * o;
-                } else if (MODE == 1) {
-                    o = c + w * (b_c - au) / diag_of(f_c, g);
-                    if (DOT) dot_acc += b_c * o;
-                } else {
-                    res = b_c - au;
-                }
-            }
-            if (MODE != 2) out[(long long)k * g.plane + col] = o;
-        }
-        if (MODE == 2) {
-            double s = res;
-            if (cr.fx == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (cr.fy == 2) s += __shfl_xor_sync(0xffffffffu, s, 16);
-            const int kg = g.z0 + k;
-            bool flush = true;
-            if (cr.fz == 2) {
-                if ((kg & 1) == 0) { zpair = s; flush = (k + 1 == k1); }
-                else { s += zpair; zpair = 0.0; }
-            }
-            const bool writer = inb && ((cr.fx == 1) || ((i & 1) == 0)) &&
-                                ((cr.fy == 1) || ((j & 1) == 0));
-            if (flush && writer) {
-                const int ci = (cr.fx == 2) ? (i >> 1) : i;
-                const int cj = (cr.fy == 2) ? (j >> 1) : j;
-                const int ck = (cr.fz == 2) ? ((kg >> 1) - (cr.z0 >> 1)) : k;
-                out[((long long)ck * cr.cny + cj) * cr.cnx + ci] = s;
-            }
-        }
-
-        // refill the stage that held plane k-1 with plane k+RING_P+1.  Nobody reads
-        // that stage's halo cells any more, and its centre cells only through
-        // their own thread, so no second barrier is needed.
-        {
-            const int kk = k + RING_P + 1;
-            if (kk <= k1) issue(kk, sm);
-            cp_async_commit();
-        }
-        sc = sp;
-    }
-    cp_async_wait<0>();
-
-    if (DOT) {
-        double v[1] = {dot_acc};
-        grid_reduce<1>(v, red_partials, red_counter, red_out);
-    }
-}
-
 // Simple gather variant (one thread per cell, neighbours straight from
 // global/L1/L2).  Kept as an independent cross-check of the staged kernel.
 template <int MODE, bool ADDC, bool DOT>
@@ -411,7 +252,7 @@ l0_jacobi_first_kernel(Grid g, const uint8_t* __restrict__ flags, const double* 
 }
 
 // ---------------------------------------------------------------- launchers
-static int pick_zchunk(const Grid& g, int n_sm) {
+int pick_zchunk(const Grid& g, int n_sm) {
     const long long tiles = (long long)((g.nx + TX - 1) / TX) * ((g.ny + TY - 1) / TY);
     const long long target = (long long)n_sm * 6;  // ~2 waves at 3 CTAs/SM
     long long chunks = (target + tiles - 1) / tiles;
@@ -432,15 +273,6 @@ static void launch_zmarch(const L0Args& a, cudaStream_t st) {
         a.g, a.flags, a.u, a.b, a.out, a.w, cr, zc, a.red_partials, a.red_counter, a.red_out);
 }
 
-template <int MODE, bool DOT>
-static void launch_ring(const L0Args& a, cudaStream_t st) {
-    CoarseRef cr{a.ec, a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
-    const int zc = pick_zchunk(a.g, a.n_sm);
-    dim3 grid((a.g.nx + TX - 1) / TX, (a.g.ny + TY - 1) / TY, (a.g.nz + zc - 1) / zc);
-    l0_ring_kernel<MODE, DOT><<<grid, NTHREADS, 0, st>>>(
-        a.g, a.flags, a.u, a.b, a.out, a.w, cr, zc, a.red_partials, a.red_counter, a.red_out);
-}
-
 template <int MODE, bool ADDC, bool DOT>
 static void launch_gather(const L0Args& a, cudaStream_t st) {
     CoarseRef cr{a.ec, a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
@@ -458,9 +290,9 @@ long long l0_max_blocks(const Grid& g, int n_sm) {
 
 // variant: 0 = shared-memory ring (cp.async), 2 = register z-march, 1 = gather
 void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {
-    if (variant == 0) {
-        if (dot) launch_ring<0, true>(a, st); else launch_ring<0, false>(a, st);
-    } else if (variant == 2) {
+    if (variant == 0 && ring_supported(a, 0)) {
+        ring_launch(a, 0, dot, st);
+    } else if (variant == 0 || variant == 2) {
         if (dot) launch_zmarch<0, false, true>(a, st); else launch_zmarch<0, false, false>(a, st);
     } else {
         if (dot) launch_gather<0, false, true>(a, st); else launch_gather<0, false, false>(a, st);
@@ -468,8 +300,8 @@ void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {
 }
 
 void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st) {
-    if (variant == 0 && !addc) {
-        if (dot) launch_ring<1, true>(a, st); else launch_ring<1, false>(a, st);
+    if (variant == 0 && !addc && ring_supported(a, 1)) {
+        ring_launch(a, 1, dot, st);
     } else if (variant == 0 || variant == 2) {
         if (addc) { if (dot) launch_zmarch<1, true, true>(a, st); else launch_zmarch<1, true, false>(a, st); }
         else      { if (dot) launch_zmarch<1, false, true>(a, st); else launch_zmarch<1, false, false>(a, st); }
@@ -480,7 +312,7 @@ void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t s
 }
 
 void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st) {   // out = coarse rhs
-    if (variant == 0) launch_ring<2, false>(a, st);
+    if (variant == 0 && ring_supported(a, 2)) ring_launch(a, 2, false, st);
     else launch_zmarch<2, false, false>(a, st);
 }
 

@@ -406,11 +406,21 @@ void apply_precond(oi_solver* S, double* dot_out) {
         coarse_cycle(S, 0);
         haloL(S, h1.L, h1.L.x);
         for (int s = 0; s < deg; ++s) {
-            if (s > 0) halo0(S, cur);
             const bool dot = (s == deg - 1) && dot_out;
             L0Args a = l0args(S, cur, S->r.p, oth, w[deg - 1 - s], dot_out);
             a.ec = h1.L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
-            oi::l0_smooth(a, s == 0, dot, variant, S->st); S->launches++;
+            bool addc = (s == 0);
+            if (addc && variant == 0 && oi::ring_supported(a, 1)) {
+                // ring kernels take the field as is: apply the correction first
+                L0Args pa = a;
+                pa.out = cur;
+                oi::l0_prolong_add(pa, S->st); S->launches++;
+                addc = false;
+                halo0(S, cur);
+            } else if (s > 0) {
+                halo0(S, cur);
+            }
+            oi::l0_smooth(a, addc, dot, variant, S->st); S->launches++;
             std::swap(cur, oth);
         }
     } else if (deg == 1 && dot_out) {
