@@ -86,63 +86,64 @@ build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scale) {
     }
 }
 
-struct ProlongRef {
-    const double* ec;
-    int cnx, cny, fx, fy, fz;
-};
-
-template <bool ADDC>
-__device__ __forceinline__ double cval(const CoarseLevel& L, const double* __restrict__ x,
-                                       long long idx, int i, int j, int k, const ProlongRef& pr) {
-    double v = x[idx];
-    if (ADDC) {
-        if (L.dg[idx] > 0.f) {
-            const int ci = (pr.fx == 2) ? (i >> 1) : i;
-            const int cj = (pr.fy == 2) ? (j >> 1) : j;
-            const int ck = (pr.fz == 2) ? ((k + 2) >> 1) - 1 : k;
-            v += pr.ec[((long long)ck * pr.cny + cj) * pr.cnx + ci];
-        }
-    }
-    return v;
-}
-
-// MODE 1: out = x' + w (b - A x')/dg ; MODE 2: out = b - A x'
-template <int MODE, bool ADDC>
+// MODE 1: out = x + w (b - A x)/dg ; MODE 2: out = b - A x
+// 64 x 4 cells per CTA in (x, y), blockIdx.z strides over planes (32-bit index math only).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 coarse_stencil_kernel(CoarseLevel L, const double* __restrict__ x, const double* __restrict__ b,
-                      double* __restrict__ out, double w, ProlongRef pr) {
-    const long long n = (long long)L.nz * L.plane;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+                      double* __restrict__ out, double w) {
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= L.nx || j >= L.ny) return;
+    const long long col = (long long)j * L.nx + i;
+    for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
+        const long long idx = (long long)k * L.plane + col;
         const float d = L.dg[idx];
         double o = 0.0;
         if (d > 0.f) {
-            const int i = (int)(idx % L.nx);
-            const int j = (int)((idx / L.nx) % L.ny);
-            const int k = (int)(idx / L.plane);
-            const double c = cval<ADDC>(L, x, idx, i, j, k, pr);
+            const double c = x[idx];
             double acc = (double)d * c;
             // couplings are zero across domain faces, so guarded loads suffice
             const float cxp = L.cxp[idx], cyp = L.cyp[idx], czp = L.czp[idx];
-            if (cxp != 0.f) acc -= (double)cxp * cval<ADDC>(L, x, idx + 1, i + 1, j, k, pr);
-            if (cyp != 0.f) acc -= (double)cyp * cval<ADDC>(L, x, idx + L.nx, i, j + 1, k, pr);
-            if (czp != 0.f) acc -= (double)czp * cval<ADDC>(L, x, idx + L.plane, i, j, k + 1, pr);
+            if (cxp != 0.f) acc -= (double)cxp * x[idx + 1];
+            if (cyp != 0.f) acc -= (double)cyp * x[idx + L.nx];
+            if (czp != 0.f) acc -= (double)czp * x[idx + L.plane];
             if (i > 0) {
                 const float cm = L.cxp[idx - 1];
-                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - 1, i - 1, j, k, pr);
+                if (cm != 0.f) acc -= (double)cm * x[idx - 1];
             }
             if (j > 0) {
                 const float cm = L.cyp[idx - L.nx];
-                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - L.nx, i, j - 1, k, pr);
+                if (cm != 0.f) acc -= (double)cm * x[idx - L.nx];
             }
             {   // k-1 may be the ghost plane (coefficients exchanged at setup)
                 const float cm = L.czp[idx - L.plane];
-                if (cm != 0.f) acc -= (double)cm * cval<ADDC>(L, x, idx - L.plane, i, j, k - 1, pr);
+                if (cm != 0.f) acc -= (double)cm * x[idx - L.plane];
             }
             if (MODE == 1) o = c + w * (b[idx] - acc) / (double)d;
             else           o = b[idx] - acc;
         }
         out[idx] = o;
+    }
+}
+
+// x += P * ec on non-empty cells (prolongation + correction between coarse levels)
+__global__ void __launch_bounds__(256)
+coarse_prolong_add_kernel(CoarseLevel L, double* __restrict__ x, const double* __restrict__ ec,
+                          int cnx, int cny) {
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= L.nx || j >= L.ny) return;
+    const int ci = (L.fx == 2) ? (i >> 1) : i, cj = (L.fy == 2) ? (j >> 1) : j;
+    const long long col = (long long)j * L.nx + i;
+    const long long ccol = (long long)cj * cnx + ci;
+    const long long cplane = (long long)cnx * cny;
+    for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
+        const long long idx = (long long)k * L.plane + col;
+        if (L.dg[idx] > 0.f) {
+            const int ck = (L.fz == 2) ? (k >> 1) : k;
+            x[idx] += ec[(long long)ck * cplane + ccol];
+        }
     }
 }
 
@@ -199,21 +200,23 @@ void coarse_jacobi_first(const CoarseLevel& L, const double* b, double* out, dou
     coarse_jacobi_first_kernel<<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, b, out, w);
 }
 
+static dim3 grid3(const CoarseLevel& L) {
+    int gz = L.nz < 128 ? L.nz : 128;
+    return dim3((L.nx + 63) / 64, (L.ny + 3) / 4, gz > 0 ? gz : 1);
+}
+
 void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, double* out, double w,
-                   const CoarseLevel* next, const double* ec, cudaStream_t st) {
-    const int nb = blocks_for((long long)L.nz * L.plane);
-    if (next) {
-        ProlongRef pr{ec, next->nx, next->ny, L.fx, L.fy, L.fz};
-        coarse_stencil_kernel<1, true><<<nb, 256, 0, st>>>(L, x, b, out, w, pr);
-    } else {
-        ProlongRef pr{nullptr, 0, 0, 1, 1, 1};
-        coarse_stencil_kernel<1, false><<<nb, 256, 0, st>>>(L, x, b, out, w, pr);
-    }
+                   const CoarseLevel*, const double*, cudaStream_t st) {
+    coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, w);
+}
+
+void coarse_prolong_add(const CoarseLevel& L, double* x, const CoarseLevel& next, const double* ec,
+                        cudaStream_t st) {
+    coarse_prolong_add_kernel<<<grid3(L), 256, 0, st>>>(L, x, ec, next.nx, next.ny);
 }
 
 void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out, cudaStream_t st) {
-    ProlongRef pr{nullptr, 0, 0, 1, 1, 1};
-    coarse_stencil_kernel<2, false><<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, x, b, out, 0.0, pr);
+    coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, 0.0);
 }
 
 void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc, cudaStream_t st) {

@@ -60,6 +60,9 @@ void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, doubl
                    cudaStream_t st);
 void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out,
                      cudaStream_t st);
+// x += P * ec  (ec lives on level `next`)
+void coarse_prolong_add(const CoarseLevel& L, double* x, const CoarseLevel& next, const double* ec,
+                        cudaStream_t st);
 void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc,
                      cudaStream_t st);
 

@@ -346,10 +346,10 @@ void coarse_cycle(oi_solver* S, size_t l) {
         oi::coarse_residual(L, cur, L.b, oth, S->st); S->launches++;
         oi::coarse_restrict(L, oth, hn.L, hn.L.b, S->st); S->launches++;
         coarse_cycle(S, l + 1);
-        haloL(S, hn.L, hn.L.x);
+        oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
         for (int s = 0; s < deg; ++s) {
-            if (s > 0) haloL(S, L, cur);
-            oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], s == 0 ? &hn.L : nullptr, hn.L.x, S->st);
+            haloL(S, L, cur);
+            oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], nullptr, nullptr, S->st);
             S->launches++;
             std::swap(cur, oth);
         }

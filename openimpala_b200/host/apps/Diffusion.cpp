@@ -1,0 +1,216 @@
+// `Diffusion <inputs> [key=value ...]` -- the reference's application driver
+// (src/props/Diffusion.cpp) for calculation_method = flow_through: same inputs
+// keys and defaults (:200-223, :605-611), same readers by file extension
+// (:262-300), same results.txt (:709-732).  The homogenisation / REV branches
+// (:317-589) are outside the scope of this build and abort with a message.
+#include <algorithm>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <AMReX.H>
+#include <AMReX_ParmParse.H>
+#include <AMReX_Print.H>
+
+#include "../io/HDF5Reader.H"
+#include "../io/RawReader.H"
+#include "../io/TiffReader.H"
+#include "../props/TortuosityHypre.H"
+#include "../props/VolumeFraction.H"
+
+namespace {
+
+OpenImpala::TortuosityHypre::SolverType stringToSolverType(const std::string& solver_str) {
+    std::string s = solver_str;
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    using ST = OpenImpala::TortuosityHypre::SolverType;
+    if (s == "jacobi") return ST::Jacobi;
+    if (s == "gmres") return ST::GMRES;
+    if (s == "flexgmres") return ST::FlexGMRES;
+    if (s == "pcg") return ST::PCG;
+    if (s == "bicgstab") return ST::BiCGSTAB;
+    if (s == "smg") return ST::SMG;
+    if (s == "pfmg") return ST::PFMG;
+    amrex::Abort("Invalid solver string: '" + solver_str + "'.");
+    return ST::GMRES;
+}
+
+template <class Reader>
+void loadThresholded(Reader& reader, int box_size, double threshold, amrex::Box& domain, amrex::BoxArray& ba,
+                     amrex::DistributionMapping& dm, amrex::iMultiFab& mf_phase) {
+    domain = reader.box();
+    ba.define(domain);
+    ba.maxSize(box_size);
+    dm.define(ba);
+    mf_phase.define(ba, dm, 1, 1);
+    amrex::iMultiFab tmp(ba, dm, 1, 0);
+    reader.threshold(threshold, 1, 0, tmp);      // > threshold -> 1, else 0 (reference :259-271)
+    amrex::Copy(mf_phase, tmp, 0, 0, 1, 0);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    amrex::Initialize(argc, argv);
+    {
+        const amrex::Real t_start = amrex::second();
+        std::string filename, data_path = "./data/", results_path = "./results_diffusion/";
+        std::string hdf5_dataset = "image", solver_str = "FlexGMRES", method = "homogenization";
+        std::string output_filename = "results.txt";
+        amrex::Real threshold_val = 0.5;
+        int phase_id = 1, box_size = 32, verbose = 1, write_plotfile = 0;
+        int raw_w = 0, raw_h = 0, raw_d = 0;
+        std::string raw_type = "UINT8";
+        {
+            amrex::ParmParse pp;
+            pp.get("filename", filename);
+            pp.query("data_path", data_path);
+            pp.query("results_path", results_path);
+            pp.query("hdf5_dataset", hdf5_dataset);
+            pp.query("threshold_val", threshold_val);
+            pp.query("phase_id", phase_id);
+            pp.query("solver_type", solver_str);
+            pp.query("box_size", box_size);
+            pp.query("verbose", verbose);
+            pp.query("write_plotfile", write_plotfile);
+            pp.query("calculation_method", method);
+            pp.query("output_filename", output_filename);
+            // .raw needs its shape from the inputs (RawReader contract); keys of tRawReader.inputs
+            pp.query("width", raw_w); pp.query("height", raw_h); pp.query("depth", raw_d);
+            pp.query("datatype", raw_type);
+        }
+        std::filesystem::path results_dir(results_path);
+        if (!std::filesystem::exists(results_dir)) {
+            std::filesystem::create_directories(results_dir);
+            if (verbose >= 1) amrex::Print() << "Created results directory: " << results_dir.string() << std::endl;
+        }
+        const std::filesystem::path input = std::filesystem::path(data_path) / filename;
+
+        amrex::Geometry geom_full;
+        amrex::BoxArray ba;
+        amrex::DistributionMapping dm;
+        amrex::iMultiFab mf_phase;
+        amrex::Box domain;
+        try {
+            if (verbose >= 1) amrex::Print() << "Reading full domain data from: " << input.string() << std::endl;
+            if (!input.has_extension()) throw std::runtime_error("File has no extension: " + input.string());
+            std::string ext = input.extension().string();
+            std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
+            if (ext == ".tif" || ext == ".tiff") {
+                OpenImpala::TiffReader reader(input.string());
+                if (!reader.isRead()) throw std::runtime_error("TiffReader failed to read metadata.");
+                loadThresholded(reader, box_size, threshold_val, domain, ba, dm, mf_phase);
+            } else if (ext == ".h5" || ext == ".hdf5") {
+                OpenImpala::HDF5Reader reader(input.string(), hdf5_dataset);
+                if (!reader.isRead()) throw std::runtime_error("HDF5Reader failed to read metadata.");
+                loadThresholded(reader, box_size, threshold_val, domain, ba, dm, mf_phase);
+            } else if (ext == ".raw") {
+                static const std::map<std::string, OpenImpala::RawDataType> types = {
+                    {"UINT8", OpenImpala::RawDataType::UINT8}, {"INT8", OpenImpala::RawDataType::INT8},
+                    {"INT16_LE", OpenImpala::RawDataType::INT16_LE}, {"INT16_BE", OpenImpala::RawDataType::INT16_BE},
+                    {"UINT16_LE", OpenImpala::RawDataType::UINT16_LE}, {"UINT16_BE", OpenImpala::RawDataType::UINT16_BE},
+                    {"INT32_LE", OpenImpala::RawDataType::INT32_LE}, {"INT32_BE", OpenImpala::RawDataType::INT32_BE},
+                    {"UINT32_LE", OpenImpala::RawDataType::UINT32_LE}, {"UINT32_BE", OpenImpala::RawDataType::UINT32_BE},
+                    {"FLOAT32_LE", OpenImpala::RawDataType::FLOAT32_LE}, {"FLOAT32_BE", OpenImpala::RawDataType::FLOAT32_BE},
+                    {"FLOAT64_LE", OpenImpala::RawDataType::FLOAT64_LE}, {"FLOAT64_BE", OpenImpala::RawDataType::FLOAT64_BE}};
+                auto it = types.find(raw_type);
+                if (it == types.end()) throw std::runtime_error("Unknown raw datatype: " + raw_type);
+                OpenImpala::RawReader reader(input.string(), raw_w, raw_h, raw_d, it->second);
+                loadThresholded(reader, box_size, threshold_val, domain, ba, dm, mf_phase);
+            } else {
+                throw std::runtime_error("Unsupported file extension for full domain load: " + ext);
+            }
+            amrex::RealBox rb({AMREX_D_DECL(0.0, 0.0, 0.0)},
+                              {AMREX_D_DECL(amrex::Real(domain.length(0)), amrex::Real(domain.length(1)),
+                                            amrex::Real(domain.length(2)))});
+            amrex::Array<int, AMREX_SPACEDIM> periodic = {AMREX_D_DECL(1, 1, 1)};   // reference :306-309
+            geom_full.define(domain, &rb, 0, periodic.data());
+            mf_phase.FillBoundary(geom_full.periodicity());
+        } catch (const std::exception& e) {
+            amrex::Print() << "Error loading full domain data: " << e.what() << std::endl;
+            amrex::Abort("Full domain data loading failed.");
+        }
+
+        if (method != "flow_through")
+            amrex::Abort("calculation_method = '" + method + "' is outside this build; set calculation_method = flow_through "
+                         "(homogenisation / REV study: see DESIGN.md, out of scope).");
+
+        if (verbose >= 1) amrex::Print() << "\n--- Full Domain Calculation: Tortuosity via Flow-Through ---\n";
+        amrex::Real vlo = -1.0, vhi = 1.0;                                            // reference :605-611
+        amrex::ParmParse pp_tort("tortuosity");
+        pp_tort.query("vlo", vlo);
+        pp_tort.query("vhi", vhi);
+
+        if (verbose > 0) amrex::Print() << "Calculating Volume Fraction for Phase ID: " << phase_id << "\n";
+        OpenImpala::VolumeFraction vf_calc(mf_phase, phase_id);
+        long long phase_voxels = 0, total_voxels = 0;
+        vf_calc.value(phase_voxels, total_voxels, false);
+        const amrex::Real volume_fraction = total_voxels > 0 ? (amrex::Real)phase_voxels / (amrex::Real)total_voxels : 0.0;
+        amrex::Print() << "  Volume Fraction = " << std::fixed << std::setprecision(8) << volume_fraction << "\n";
+
+        std::map<std::string, amrex::Real> results;
+        std::string direction_str;
+        amrex::ParmParse pp;
+        pp.get("direction", direction_str);
+        {   // unquoted `direction = X Y Z` arrives as several values
+            std::vector<std::string> all;
+            if (pp.queryarr("direction", all) && all.size() > 1) {
+                direction_str.clear();
+                for (const auto& s : all) direction_str += s + " ";
+            }
+        }
+        std::string upper = direction_str;
+        std::transform(upper.begin(), upper.end(), upper.begin(), ::toupper);
+        std::vector<OpenImpala::Direction> dirs;
+        if (upper.find("ALL") != std::string::npos) {
+            dirs = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
+        } else {
+            std::stringstream ss(upper);
+            std::string one;
+            while (ss >> one) {
+                if (one == "X") dirs.push_back(OpenImpala::Direction::X);
+                else if (one == "Y") dirs.push_back(OpenImpala::Direction::Y);
+                else if (one == "Z") dirs.push_back(OpenImpala::Direction::Z);
+            }
+        }
+        if (dirs.empty()) amrex::Warning("No valid directions specified in 'direction' input. Skipping tortuosity calculation.");
+
+        for (const auto dir : dirs) {
+            const std::string dc = dir == OpenImpala::Direction::X ? "X" : dir == OpenImpala::Direction::Y ? "Y" : "Z";
+            if (verbose >= 1) amrex::Print() << "\n--- Solving for Tortuosity in Direction: " << dc << " ---\n";
+            amrex::Geometry geom_tort;                 // same box, NON-periodic (reference :671-677)
+            {
+                amrex::RealBox rb = geom_full.ProbDomain();
+                amrex::Array<int, AMREX_SPACEDIM> np = {AMREX_D_DECL(0, 0, 0)};
+                geom_tort.define(geom_full.Domain(), &rb, 0, np.data());
+            }
+            OpenImpala::TortuosityHypre solver(geom_tort, ba, dm, mf_phase, volume_fraction, phase_id, dir,
+                                               stringToSolverType(solver_str), results_path, vlo, vhi, verbose,
+                                               write_plotfile != 0);
+            const amrex::Real tau = solver.value();
+            results["Tortuosity_" + dc] = tau;
+            amrex::Print() << "  >>> Calculated Tortuosity (" << dc << "): " << std::fixed << std::setprecision(8) << tau << " <<<\n";
+        }
+
+        const std::filesystem::path out_path = results_dir / output_filename;
+        amrex::Print() << "\nWriting final results to: " << out_path << "\n";
+        std::ofstream out(out_path);
+        if (out.is_open()) {
+            out << "# Tortuosity Calculation Results (Flow-Through Method)\n";
+            out << "# Input File: " << filename << "\n";
+            out << "# Analysis Phase ID: " << phase_id << "\n";
+            out << "# -----------------------------\n";
+            out << "VolumeFraction: " << std::fixed << std::setprecision(9) << volume_fraction << "\n";
+            for (const auto& kv : results) out << kv.first << ": " << std::fixed << std::setprecision(9) << kv.second << "\n";
+        } else {
+            amrex::Warning("Could not open output file for writing: " + out_path.string());
+        }
+        amrex::Print() << std::endl << "Total run time (seconds) = " << (amrex::second() - t_start) << std::endl;
+    }
+    amrex::Finalize();
+    return 0;
+}

@@ -1,0 +1,89 @@
+// Reader + VolumeFraction checks in the mould of src/io/tTiffReader.cpp,
+// tRawReader.cpp, tHDF5Reader.cpp and src/props/tVolumeFraction.cpp:
+//   mode = tiff | raw | hdf5 ; prints dims, sample metadata, thresholded min/max
+//   and the phase counts, compares the GPU count with a direct host loop.
+#include <iomanip>
+#include <string>
+
+#include <AMReX.H>
+#include <AMReX_ParmParse.H>
+#include <AMReX_Print.H>
+
+#include "../io/HDF5Reader.H"
+#include "../io/RawReader.H"
+#include "../io/TiffReader.H"
+#include "../props/VolumeFraction.H"
+
+int main(int argc, char* argv[]) {
+    amrex::Initialize(argc, argv);
+    bool passed = true;
+    auto fail = [&](const std::string& why) { passed = false; amrex::Print() << "TEST FAILED: " << why << "\n"; };
+    {
+        std::string mode = "tiff", file, dataset = "image", datatype = "UINT8";
+        int width = 0, height = 0, depth = 0, box_size = 32, use_gpu_count = 1;
+        amrex::Real threshold = 0.5;
+        amrex::ParmParse pp;
+        pp.query("mode", mode);
+        if (!pp.query("tifffile", file) && !pp.query("rawfile", file) && !pp.query("hdf5file", file)) pp.get("filename", file);
+        pp.query("hdf5dataset", dataset);
+        pp.query("datatype", datatype);
+        pp.query("width", width); pp.query("height", height); pp.query("depth", depth);
+        pp.query("threshold", threshold); pp.query("threshold_val", threshold);
+        pp.query("box_size", box_size);
+        pp.query("gpu_count", use_gpu_count);
+
+        amrex::Box domain;
+        amrex::BoxArray ba;
+        amrex::DistributionMapping dm;
+        amrex::iMultiFab mf;
+        auto prepare = [&](const amrex::Box& b) {
+            domain = b; ba.define(b); ba.maxSize(box_size); dm.define(ba); mf.define(ba, dm, 1, 0);
+        };
+        try {
+            if (mode == "tiff") {
+                OpenImpala::TiffReader r(file);
+                amrex::Print() << "BitsPerSample: " << r.bitsPerSample() << " SampleFormat: " << r.sampleFormat()
+                               << " SamplesPerPixel: " << r.samplesPerPixel() << "\n";
+                prepare(r.box());
+                r.threshold(threshold, 1, 0, mf);
+            } else if (mode == "raw") {
+                OpenImpala::RawDataType t = OpenImpala::RawDataType::UINT8;
+                if (datatype == "INT16_LE") t = OpenImpala::RawDataType::INT16_LE;
+                else if (datatype == "UINT16_LE") t = OpenImpala::RawDataType::UINT16_LE;
+                else if (datatype == "UINT16_BE") t = OpenImpala::RawDataType::UINT16_BE;
+                else if (datatype == "FLOAT32_LE") t = OpenImpala::RawDataType::FLOAT32_LE;
+                else if (datatype != "UINT8") fail("datatype not handled by this driver: " + datatype);
+                OpenImpala::RawReader r(file, width, height, depth, t);
+                prepare(r.box());
+                r.threshold(threshold, 1, 0, mf);
+            } else if (mode == "hdf5") {
+                OpenImpala::HDF5Reader r(file, dataset);
+                prepare(r.box());
+                r.threshold(threshold, 1, 0, mf);
+            } else {
+                fail("unknown mode " + mode);
+            }
+        } catch (const std::exception& e) {
+            fail(e.what());
+        }
+        if (passed) {
+            amrex::Print() << "Dims: " << domain.length(0) << " " << domain.length(1) << " " << domain.length(2) << "\n";
+            amrex::Print() << "ThresholdMinMax: " << mf.min(0) << " " << mf.max(0) << "\n";
+            long long direct1 = mf.sum(0), total = domain.numPts();
+            amrex::Print() << "DirectCount1: " << direct1 << " Total: " << total << "\n";
+            if (use_gpu_count) {
+                for (int phase = 0; phase <= 1; ++phase) {
+                    OpenImpala::VolumeFraction vf(mf, phase);
+                    long long pc = 0, tc = 0;
+                    vf.value(pc, tc);
+                    amrex::Print() << "VolumeFractionCount" << phase << ": " << pc << " of " << tc << "\n";
+                    const long long expect = phase == 1 ? direct1 : total - direct1;
+                    if (pc != expect || tc != total) fail("VolumeFraction count differs from the direct loop");
+                }
+            }
+        }
+        amrex::Print() << (passed ? "TEST PASSED\n" : "TEST FAILED\n");
+    }
+    amrex::Finalize();
+    return passed ? 0 : 1;
+}

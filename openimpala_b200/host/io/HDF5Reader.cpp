@@ -1,0 +1,275 @@
+// Minimal HDF5 (file format spec 1.x objects) reader; semantics of the
+// reference reader: dims (Z,Y,X) -> box (X,Y,Z) (src/io/HDF5Reader.cpp:136-153),
+// native-type dispatch u8/i8/u16/i16/u32/i32/u64/i64/f32/f64 (:359-383),
+// threshold rule double(v) > t ? a : b (:321-326).
+#include "HDF5Reader.H"
+
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <vector>
+
+#include <AMReX_Utility.H>
+
+namespace OpenImpala {
+namespace {
+
+class H5File {
+public:
+    explicit H5File(const std::string& path) : in(path, std::ios::binary) {
+        if (!in) throw std::runtime_error("cannot open HDF5 file: " + path);
+        static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+        uint64_t base = 0;
+        bool found = false;
+        for (int t = 0; t < 8 && !found; ++t) {          // superblock at 0, 512, 1024, ...
+            unsigned char b[8];
+            if (!readAt(base, b, 8)) break;
+            if (std::memcmp(b, sig, 8) == 0) found = true; else base = base ? base * 2 : 512;
+        }
+        if (!found) throw std::runtime_error("not an HDF5 file: " + path);
+        unsigned char h[24];
+        readAt(base + 8, h, 24);
+        const int version = h[0];
+        if (version > 1)
+            throw std::runtime_error("HDF5 superblock version " + std::to_string(version) +
+                                     " (latest-format file) needs libhdf5, which this build does not have");
+        so = h[5]; sl = h[6];
+        uint64_t p = base + 8 + 8 + 2 + 2 + 4 + (version == 1 ? 4 : 0);
+        base_addr = rd(p, so); p += 4 * (uint64_t)so;      // base, free-space, eof, driver
+        // root group symbol table entry
+        p += so;                                            // link name offset
+        root_header = rd(p, so);
+    }
+    uint64_t rootHeader() const { return root_header; }
+    int sizeOffsets() const { return so; }
+    int sizeLengths() const { return sl; }
+    bool readAt(uint64_t off, void* dst, size_t n) {
+        in.clear();
+        in.seekg((std::streamoff)off);
+        in.read(reinterpret_cast<char*>(dst), (std::streamsize)n);
+        return (size_t)in.gcount() == n;
+    }
+    uint64_t rd(uint64_t off, int n) {
+        unsigned char b[8] = {0};
+        if (!readAt(off, b, (size_t)n)) throw std::runtime_error("HDF5: read past end of file");
+        uint64_t v = 0;
+        for (int q = 0; q < n; ++q) v |= (uint64_t)b[q] << (8 * q);
+        return v;
+    }
+    struct Message { int type; std::vector<unsigned char> data; };
+    // all messages of a version-1 object header, following continuation blocks
+    std::vector<Message> messages(uint64_t addr) {
+        addr += base_addr;
+        unsigned char h[16];
+        if (!readAt(addr, h, 16)) throw std::runtime_error("HDF5: bad object header address");
+        if (h[0] != 1) throw std::runtime_error("HDF5: object header version " + std::to_string((int)h[0]) + " not supported without libhdf5");
+        const int nmsg = h[2] | (h[3] << 8);
+        const uint32_t hsize = h[8] | (h[9] << 8) | (h[10] << 16) | ((uint32_t)h[11] << 24);
+        std::vector<Message> out;
+        std::vector<std::pair<uint64_t, uint64_t>> blocks{{addr + 16, hsize}};
+        for (size_t bi = 0; bi < blocks.size() && (int)out.size() < nmsg; ++bi) {
+            uint64_t p = blocks[bi].first;
+            const uint64_t end = p + blocks[bi].second;
+            while (p + 8 <= end && (int)out.size() < nmsg) {
+                unsigned char mh[8];
+                if (!readAt(p, mh, 8)) break;
+                Message m;
+                m.type = mh[0] | (mh[1] << 8);
+                const size_t sz = mh[2] | (mh[3] << 8);
+                m.data.resize(sz);
+                if (sz && !readAt(p + 8, m.data.data(), sz)) break;
+                p += 8 + sz;
+                if (m.type == 0x0010 && sz >= (size_t)(so + sl)) {          // continuation
+                    uint64_t o = 0, l = 0;
+                    for (int q = 0; q < so; ++q) o |= (uint64_t)m.data[q] << (8 * q);
+                    for (int q = 0; q < sl; ++q) l |= (uint64_t)m.data[so + q] << (8 * q);
+                    blocks.emplace_back(o + base_addr, l);
+                }
+                out.push_back(std::move(m));
+            }
+        }
+        return out;
+    }
+    // object header address of `name` inside the old-style group whose header is at `group`
+    uint64_t lookup(uint64_t group, const std::string& name) {
+        uint64_t btree = 0, heap = 0;
+        bool have = false;
+        for (const Message& m : messages(group))
+            if (m.type == 0x0011 && m.data.size() >= (size_t)(2 * so)) {
+                for (int q = 0; q < so; ++q) btree |= (uint64_t)m.data[q] << (8 * q);
+                for (int q = 0; q < so; ++q) heap |= (uint64_t)m.data[so + q] << (8 * q);
+                have = true;
+            }
+        if (!have) throw std::runtime_error("HDF5: group without a symbol table (new-style groups need libhdf5)");
+        heap += base_addr;
+        char sig[4];
+        readAt(heap, sig, 4);
+        if (std::memcmp(sig, "HEAP", 4) != 0) throw std::runtime_error("HDF5: bad local heap");
+        const uint64_t heap_data = rd(heap + 8 + 2 * (uint64_t)sl, so) + base_addr;
+        return walk(btree + base_addr, heap_data, name);
+    }
+    uint64_t baseAddr() const { return base_addr; }
+private:
+    uint64_t walk(uint64_t node, uint64_t heap_data, const std::string& name) {
+        char sig[4];
+        readAt(node, sig, 4);
+        if (std::memcmp(sig, "TREE", 4) == 0) {
+            unsigned char h[4];
+            readAt(node + 4, h, 4);
+            const int level = h[1], used = h[2] | (h[3] << 8);
+            uint64_t p = node + 8 + 2 * (uint64_t)so;
+            for (int e = 0; e < used; ++e) {
+                p += sl;                                    // key e
+                const uint64_t child = rd(p, so) + base_addr;
+                p += so;
+                const uint64_t r = walk(child, heap_data, name);
+                if (r != UINT64_MAX) return r;
+                (void)level;
+            }
+            return UINT64_MAX;
+        }
+        if (std::memcmp(sig, "SNOD", 4) == 0) {
+            unsigned char h[4];
+            readAt(node + 4, h, 4);
+            const int nsym = h[2] | (h[3] << 8);
+            uint64_t p = node + 8;
+            for (int s = 0; s < nsym; ++s) {
+                const uint64_t name_off = rd(p, so), hdr = rd(p + so, so);
+                std::string nm;
+                for (uint64_t q = heap_data + name_off;; ++q) {
+                    char ch = 0;
+                    if (!readAt(q, &ch, 1) || ch == 0) break;
+                    nm += ch;
+                }
+                if (nm == name) return hdr;
+                p += 2 * (uint64_t)so + 4 + 4 + 16;
+            }
+            return UINT64_MAX;
+        }
+        throw std::runtime_error("HDF5: unexpected node signature in group B-tree");
+    }
+    std::ifstream in;
+    int so = 8, sl = 8;
+    uint64_t base_addr = 0, root_header = 0;
+};
+
+}  // namespace
+
+HDF5Reader::HDF5Reader() = default;
+
+HDF5Reader::HDF5Reader(const std::string& filename, const std::string& hdf5dataset) {
+    if (!readFile(filename, hdf5dataset))
+        throw std::runtime_error("HDF5Reader: failed to read metadata of " + filename + ":" + hdf5dataset);
+}
+
+bool HDF5Reader::readFile(const std::string& filename, const std::string& hdf5dataset) {
+    m_filename = filename; m_hdf5dataset = hdf5dataset; m_is_read = false;
+    return readMetadataInternal();
+}
+
+bool HDF5Reader::readMetadataInternal() {
+    try {
+        H5File f(m_filename);
+        uint64_t obj = f.rootHeader();
+        std::stringstream path(m_hdf5dataset);
+        std::string part;
+        while (std::getline(path, part, '/')) {
+            if (part.empty()) continue;
+            obj = f.lookup(obj, part);
+            if (obj == UINT64_MAX) throw std::runtime_error("dataset '" + m_hdf5dataset + "' not found");
+        }
+        const int so = f.sizeOffsets(), sl = f.sizeLengths();
+        bool have_space = false, have_type = false, have_layout = false;
+        for (const auto& m : f.messages(obj)) {
+            const unsigned char* d = m.data.data();
+            if (m.type == 0x0001 && m.data.size() >= 8) {                 // dataspace
+                const int version = d[0], rank = d[1];
+                if (rank != 3) throw std::runtime_error("dataset rank " + std::to_string(rank) + " != 3");
+                const size_t off = version == 1 ? 8 : 4;
+                uint64_t dims[3] = {0, 0, 0};
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < sl; ++q) dims[r] |= (uint64_t)d[off + r * sl + q] << (8 * q);
+                m_depth = (int)dims[0]; m_height = (int)dims[1]; m_width = (int)dims[2];
+                have_space = true;
+            } else if (m.type == 0x0003 && m.data.size() >= 8) {          // datatype
+                m_type_class = d[0] & 0x0f;
+                m_type_big_endian = (d[1] & 0x01) != 0;
+                m_type_signed = (d[1] & 0x08) != 0;
+                m_type_size = (int)(d[4] | (d[5] << 8) | (d[6] << 16) | ((uint32_t)d[7] << 24));
+                if (m_type_class > 1) throw std::runtime_error("unsupported HDF5 datatype class " + std::to_string(m_type_class));
+                have_type = true;
+            } else if (m.type == 0x0008 && m.data.size() >= 2) {          // data layout
+                const int version = d[0];
+                if (version == 3) {
+                    if (d[1] != 1) throw std::runtime_error("only contiguous dataset layout is supported without libhdf5");
+                    m_data_offset = 0;
+                    for (int q = 0; q < so; ++q) m_data_offset |= (uint64_t)d[2 + q] << (8 * q);
+                } else if (version == 1 || version == 2) {
+                    if (d[2] != 1) throw std::runtime_error("only contiguous dataset layout is supported without libhdf5");
+                    m_data_offset = 0;
+                    for (int q = 0; q < so; ++q) m_data_offset |= (uint64_t)d[8 + q] << (8 * q);
+                } else throw std::runtime_error("unsupported layout message version");
+                m_data_offset += f.baseAddr();
+                have_layout = true;
+            } else if (m.type == 0x000B) {
+                if (m.data.size() >= 2 && d[1] > 0) throw std::runtime_error("filtered (compressed) datasets need libhdf5");
+            }
+        }
+        if (!(have_space && have_type && have_layout)) throw std::runtime_error("incomplete dataset header");
+        if (m_width <= 0 || m_height <= 0 || m_depth <= 0) throw std::runtime_error("bad dataset dimensions");
+    } catch (const std::exception& e) {
+        amrex::Warning(std::string("[HDF5Reader] ") + e.what());
+        return false;
+    }
+    m_is_read = true;
+    return true;
+}
+
+amrex::Box HDF5Reader::box() const {
+    if (!m_is_read) return amrex::Box();
+    return amrex::Box(amrex::IntVect::TheZeroVector(), amrex::IntVect(m_width - 1, m_height - 1, m_depth - 1));
+}
+
+std::string HDF5Reader::getAttribute(const std::string& attr_name) const {
+    if (!m_is_read) return "<Attribute read error: Metadata not read>";
+    return "<HDF5 Error reading attr '" + attr_name + "'>";   // attributes need libhdf5
+}
+
+void HDF5Reader::threshold(double t, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {
+    if (!m_is_read) amrex::Abort("[HDF5Reader::threshold] metadata not read");
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.boxArray().minimalBox() == this->box(), "HDF5Reader: iMultiFab domain mismatch");
+    std::ifstream in(m_filename, std::ios::binary);
+    if (!in) amrex::Abort("[HDF5Reader::threshold] cannot reopen " + m_filename);
+    const size_t bps = (size_t)m_type_size;
+    std::vector<unsigned char> row((size_t)m_width * bps);
+    for (int k = 0; k < m_depth; ++k)
+        for (int j = 0; j < m_height; ++j) {
+            in.seekg((std::streamoff)(m_data_offset + (((uint64_t)k * m_height + j) * (uint64_t)m_width) * bps));
+            in.read(reinterpret_cast<char*>(row.data()), (std::streamsize)row.size());
+            for (int i = 0; i < m_width; ++i) {
+                unsigned char b[8] = {0};
+                const unsigned char* p = row.data() + (size_t)i * bps;
+                for (size_t q = 0; q < bps && q < 8; ++q) b[q] = m_type_big_endian ? p[bps - 1 - q] : p[q];
+                double v = 0.0;
+                if (m_type_class == 1) {
+                    if (bps == 4) { float x; std::memcpy(&x, b, 4); v = (double)x; }
+                    else if (bps == 8) { std::memcpy(&v, b, 8); }
+                } else if (m_type_signed) {
+                    if (bps == 1) { int8_t x; std::memcpy(&x, b, 1); v = (double)x; }
+                    else if (bps == 2) { int16_t x; std::memcpy(&x, b, 2); v = (double)x; }
+                    else if (bps == 4) { int32_t x; std::memcpy(&x, b, 4); v = (double)x; }
+                    else if (bps == 8) { int64_t x; std::memcpy(&x, b, 8); v = (double)x; }
+                } else {
+                    uint64_t x = 0;
+                    std::memcpy(&x, b, bps > 8 ? 8 : bps);
+                    v = (double)x;
+                }
+                mf(i, j, k) = (v > t) ? value_if_true : value_if_false;
+            }
+        }
+}
+
+void HDF5Reader::threshold(double t, amrex::iMultiFab& mf) const { threshold(t, 1, 0, mf); }
+
+}  // namespace OpenImpala

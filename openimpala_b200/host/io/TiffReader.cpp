@@ -1,0 +1,315 @@
+// Baseline-TIFF decode + threshold, behaviour of src/io/TiffReader.cpp:289-444:
+//   * 1-bit rows are unpacked with the scanline pitch ceil(W/8) for strips
+//     (:419-426) and linearly with the tile width for tiles (:376-381);
+//   * libtiff hands back MSB-first bytes even for FillOrder=2 files and the
+//     reference then reads those LSB-first (:380, :425), i.e. MSB-first bits of the
+//     raw file byte -- reproduced here;
+//   * wider samples are converted through double (:41-79), byte-swapped to host
+//     order as libtiff would;
+//   * PhotometricInterpretation is ignored (the reference never inverts);
+//   * rule: (double(sample) > threshold) ? value_if_true : value_if_false (:434).
+#include "TiffReader.H"
+
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+#include <AMReX_Utility.H>
+
+namespace OpenImpala {
+namespace {
+
+struct Ifd {
+    std::map<int, std::vector<uint64_t>> tags;
+    uint64_t get(int tag, uint64_t dflt) const {
+        auto it = tags.find(tag);
+        return (it == tags.end() || it->second.empty()) ? dflt : it->second[0];
+    }
+    const std::vector<uint64_t>* arr(int tag) const {
+        auto it = tags.find(tag);
+        return it == tags.end() ? nullptr : &it->second;
+    }
+};
+
+class TiffFile {
+public:
+    explicit TiffFile(const std::string& path) : in(path, std::ios::binary) {
+        if (!in) throw std::runtime_error("cannot open TIFF file: " + path);
+        unsigned char h[16];
+        in.read(reinterpret_cast<char*>(h), 16);
+        if (in.gcount() < 8) throw std::runtime_error("not a TIFF file: " + path);
+        if (h[0] == 'I' && h[1] == 'I') little = true;
+        else if (h[0] == 'M' && h[1] == 'M') little = false;
+        else throw std::runtime_error("not a TIFF file: " + path);
+        const uint64_t magic = rd(h + 2, 2);
+        if (magic == 42) { big = false; first = rd(h + 4, 4); }
+        else if (magic == 43) { big = true; first = rd(h + 8, 8); }
+        else throw std::runtime_error("bad TIFF magic: " + path);
+    }
+    std::vector<Ifd> directories() {
+        std::vector<Ifd> out;
+        uint64_t off = first;
+        while (off != 0) {
+            Ifd d;
+            std::vector<unsigned char> cnt(big ? 8 : 2);
+            readAt(off, cnt.data(), cnt.size());
+            const uint64_t n = rd(cnt.data(), cnt.size());
+            const size_t esz = big ? 20 : 12, vsz = big ? 8 : 4;
+            std::vector<unsigned char> ent(n * esz + vsz);
+            readAt(off + cnt.size(), ent.data(), ent.size());
+            for (uint64_t e = 0; e < n; ++e) {
+                const unsigned char* p = ent.data() + e * esz;
+                const int tag = (int)rd(p, 2), type = (int)rd(p + 2, 2);
+                const uint64_t count = rd(p + 4, vsz);
+                const size_t tsz = typeSize(type);
+                if (tsz == 0 || count == 0) continue;
+                std::vector<unsigned char> raw(tsz * count);
+                if (raw.size() <= vsz) std::memcpy(raw.data(), p + 4 + vsz, raw.size());
+                else readAt(rd(p + 4 + vsz, vsz), raw.data(), raw.size());
+                const uint64_t keep = std::min<uint64_t>(count, (type == 2) ? 0 : count);
+                std::vector<uint64_t> vals;
+                vals.reserve(keep);
+                for (uint64_t q = 0; q < keep; ++q) vals.push_back(rd(raw.data() + q * tsz, tsz > 8 ? 8 : tsz));
+                d.tags[tag] = vals;
+            }
+            out.push_back(d);
+            off = rd(ent.data() + n * esz, vsz);
+        }
+        return out;
+    }
+    void readAt(uint64_t off, unsigned char* dst, size_t n) {
+        in.clear();
+        in.seekg((std::streamoff)off);
+        in.read(reinterpret_cast<char*>(dst), (std::streamsize)n);
+        if ((size_t)in.gcount() != n) std::memset(dst + in.gcount(), 0, n - (size_t)in.gcount());
+    }
+    bool littleEndian() const { return little; }
+private:
+    uint64_t rd(const unsigned char* p, size_t n) const {
+        uint64_t v = 0;
+        if (little) for (size_t q = 0; q < n; ++q) v |= (uint64_t)p[q] << (8 * q);
+        else for (size_t q = 0; q < n; ++q) v = (v << 8) | p[q];
+        return v;
+    }
+    static size_t typeSize(int t) {
+        switch (t) {
+            case 1: case 2: case 6: case 7: return 1;
+            case 3: case 8: return 2;
+            case 4: case 9: case 11: case 13: return 4;
+            case 5: case 10: case 12: case 16: case 17: case 18: return 8;
+            default: return 0;
+        }
+    }
+    std::ifstream in;
+    bool little = true, big = false;
+    uint64_t first = 0;
+};
+
+enum { T_WIDTH = 256, T_HEIGHT = 257, T_BPS = 258, T_COMPRESSION = 259, T_FILLORDER = 266,
+       T_STRIPOFFSETS = 273, T_SPP = 277, T_ROWSPERSTRIP = 278, T_STRIPBYTECOUNTS = 279,
+       T_PLANAR = 284, T_TILEWIDTH = 322, T_TILELENGTH = 323, T_TILEOFFSETS = 324,
+       T_TILEBYTECOUNTS = 325, T_SAMPLEFORMAT = 339 };
+
+double sampleAsDouble(const unsigned char* p, int bps, int fmt, bool file_little) {
+    const int nb = bps / 8;
+    unsigned char b[8] = {0};
+    const bool host_little = true;   // x86-64 / aarch64
+    for (int q = 0; q < nb; ++q) b[q] = (file_little == host_little) ? p[q] : p[nb - 1 - q];
+    switch (fmt) {
+        case 1:
+            if (nb == 1) return (double)b[0];
+            if (nb == 2) { uint16_t v; std::memcpy(&v, b, 2); return (double)v; }
+            if (nb == 4) { uint32_t v; std::memcpy(&v, b, 4); return (double)v; }
+            if (nb == 8) { uint64_t v; std::memcpy(&v, b, 8); return (double)v; }
+            return 0.0;
+        case 2:
+            if (nb == 1) { int8_t v; std::memcpy(&v, b, 1); return (double)v; }
+            if (nb == 2) { int16_t v; std::memcpy(&v, b, 2); return (double)v; }
+            if (nb == 4) { int32_t v; std::memcpy(&v, b, 4); return (double)v; }
+            if (nb == 8) { int64_t v; std::memcpy(&v, b, 8); return (double)v; }
+            return 0.0;
+        case 3:
+            if (nb == 4) { float v; std::memcpy(&v, b, 4); return (double)v; }
+            if (nb == 8) { double v; std::memcpy(&v, b, 8); return v; }
+            return 0.0;
+        default: return 0.0;
+    }
+}
+
+std::string sequenceName(const std::string& base, int index, int digits, const std::string& suffix) {
+    std::ostringstream ss;
+    ss << base << std::setw(digits) << std::setfill('0') << index << suffix;
+    return ss.str();
+}
+
+void checkSupported(const Ifd& d, const std::string& name, int& w, int& h, uint16_t& bps, uint16_t& fmt,
+                    uint16_t& spp, uint16_t& fill) {
+    w = (int)d.get(T_WIDTH, 0); h = (int)d.get(T_HEIGHT, 0);
+    bps = (uint16_t)d.get(T_BPS, 1); fmt = (uint16_t)d.get(T_SAMPLEFORMAT, 1);
+    spp = (uint16_t)d.get(T_SPP, 1); fill = (uint16_t)d.get(T_FILLORDER, 1);
+    const uint64_t planar = d.get(T_PLANAR, 1);
+    const bool valid_bps = (bps == 1 || bps == 8 || bps == 16 || bps == 32 || bps == 64);
+    if (w <= 0 || h <= 0 || !valid_bps || planar != 1 || spp != 1) {
+        std::stringstream ss;
+        ss << "[TiffReader] Invalid/unsupported TIFF: " << name << " (W=" << w << ", H=" << h
+           << ", BPS=" << bps << ", Planar=" << planar << ", SPP=" << spp << ").";
+        amrex::Abort(ss.str());
+    }
+    if (d.get(T_COMPRESSION, 1) != 1)
+        amrex::Abort("[TiffReader] compressed TIFF data needs libtiff, which this build does not have: " + name);
+}
+
+}  // namespace
+
+TiffReader::TiffReader() = default;
+
+TiffReader::TiffReader(const std::string& filename) : TiffReader() {
+    if (!readFile(filename)) throw std::runtime_error("TiffReader(filename): Failed to read metadata from file: " + filename);
+}
+
+TiffReader::TiffReader(const std::string& base_pattern, int num_files, int start_index, int digits,
+                       const std::string& suffix) : TiffReader() {
+    if (!readFileSequence(base_pattern, num_files, start_index, digits, suffix))
+        throw std::runtime_error("TiffReader(sequence): Failed to read metadata for sequence: " + base_pattern);
+}
+
+amrex::Box TiffReader::box() const {
+    if (!m_is_read) return amrex::Box();
+    return amrex::Box(amrex::IntVect::TheZeroVector(), amrex::IntVect(m_width - 1, m_height - 1, m_depth - 1));
+}
+
+bool TiffReader::readFile(const std::string& filename) {
+    m_is_sequence = false; m_filename = filename; m_base_pattern.clear();
+    if (filename.empty()) amrex::Abort("[TiffReader::readFile] Filename cannot be empty.");
+    try {
+        TiffFile f(filename);
+        const std::vector<Ifd> dirs = f.directories();
+        if (dirs.empty()) amrex::Abort("[TiffReader::readFile] No directories (depth=0) in: " + filename);
+        checkSupported(dirs[0], filename, m_width, m_height, m_bits_per_sample, m_sample_format,
+                       m_samples_per_pixel, m_fill_order);
+        m_depth = (int)dirs.size();
+    } catch (const std::exception& e) {
+        amrex::Abort(std::string("[TiffReader::readFile] ") + e.what());
+    }
+    m_is_read = true;
+    return true;
+}
+
+bool TiffReader::readFileSequence(const std::string& base_pattern, int num_files, int start_index,
+                                  int digits, const std::string& suffix) {
+    m_is_sequence = true; m_base_pattern = base_pattern; m_start_index = start_index;
+    m_digits = digits; m_suffix = suffix; m_filename.clear();
+    if (num_files <= 0 || digits <= 0 || base_pattern.empty()) amrex::Abort("[TiffReader::readFileSequence] Invalid sequence params.");
+    const std::string first = sequenceName(base_pattern, start_index, digits, suffix);
+    try {
+        TiffFile f(first);
+        const std::vector<Ifd> dirs = f.directories();
+        if (dirs.empty()) amrex::Abort("[TiffReader::readFileSequence] empty file: " + first);
+        checkSupported(dirs[0], first, m_width, m_height, m_bits_per_sample, m_sample_format,
+                       m_samples_per_pixel, m_fill_order);
+        if (dirs.size() > 1) amrex::Warning("[TiffReader::readFileSequence] First sequence file has >1 directory. Using first only for metadata.");
+    } catch (const std::exception& e) {
+        amrex::Abort(std::string("[TiffReader::readFileSequence] ") + e.what());
+    }
+    m_depth = num_files;
+    m_is_read = true;
+    return true;
+}
+
+void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int v_false, double thr) const {
+    if (!m_is_read) amrex::Abort("[TiffReader::readDistributedIntoFab] Metadata not processed.");
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.boxArray().minimalBox() == this->box(), "Dest MF BoxArray domain mismatch.");
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nComp() == 1, "Dest MF must have 1 component.");
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nGrow() == 0, "Dest MF must have 0 ghost cells.");
+    const int W = m_width, H = m_height, bps = m_bits_per_sample;
+    const size_t bytes_per_sample = bps >= 8 ? (size_t)bps / 8 : 1;
+    std::vector<unsigned char> buf;
+
+    auto decodeDirectory = [&](TiffFile& f, const Ifd& d, int k) {
+        const bool file_little = f.littleEndian();
+        if (d.arr(T_TILEOFFSETS)) {                                   // tiled, reference :354-393
+            const int tw = (int)d.get(T_TILEWIDTH, 0), th = (int)d.get(T_TILELENGTH, 0);
+            const auto* offs = d.arr(T_TILEOFFSETS);
+            const auto* cnts = d.arr(T_TILEBYTECOUNTS);
+            if (tw <= 0 || th <= 0 || !cnts) amrex::Abort("Invalid tile params.");
+            const int tiles_x = (W + tw - 1) / tw;
+            for (size_t t = 0; t < offs->size(); ++t) {
+                const size_t nbytes = (size_t)(*cnts)[t];
+                buf.resize(nbytes);
+                f.readAt((*offs)[t], buf.data(), nbytes);
+                const int ox = (int)(t % tiles_x) * tw, oy = (int)(t / tiles_x) * th;
+                for (int j = oy; j < std::min(oy + th, H); ++j)
+                    for (int i = ox; i < std::min(ox + tw, W); ++i) {
+                        double v = 0.0;
+                        if (bps == 1) {
+                            const size_t lin = (size_t)(j - oy) * tw + (size_t)(i - ox);
+                            const size_t byte_i = lin / 8; const int bit_i = (int)(lin % 8);
+                            if (byte_i < nbytes) v = (double)((buf[byte_i] >> (7 - bit_i)) & 1);
+                        } else {
+                            const size_t off = ((size_t)(j - oy) * tw + (size_t)(i - ox)) * bytes_per_sample;
+                            if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
+                        }
+                        dest(i, j, k) = (v > thr) ? v_true : v_false;
+                    }
+            }
+        } else {                                                       // strips, reference :394-437
+            uint64_t rps = d.get(T_ROWSPERSTRIP, (uint64_t)H);
+            if (rps == 0 || rps > (uint64_t)H) rps = (uint64_t)H;
+            const auto* offs = d.arr(T_STRIPOFFSETS);
+            const auto* cnts = d.arr(T_STRIPBYTECOUNTS);
+            if (!offs) amrex::Abort("[TiffReader] TIFF directory without strip offsets.");
+            const size_t pitch1 = ((size_t)W + 7) / 8;                 // TIFFScanlineSize for 1-bit data
+            for (size_t s = 0; s < offs->size(); ++s) {
+                const int oy = (int)(s * rps);
+                if (oy >= H) break;
+                const int rows = (int)std::min<uint64_t>(rps, (uint64_t)(H - oy));
+                const size_t expect = bps == 1 ? pitch1 * rows : (size_t)W * rows * bytes_per_sample;
+                const size_t nbytes = cnts && s < cnts->size() ? std::min<size_t>((size_t)(*cnts)[s], expect) : expect;
+                buf.resize(nbytes);
+                f.readAt((*offs)[s], buf.data(), nbytes);
+                for (int j = oy; j < oy + rows; ++j)
+                    for (int i = 0; i < W; ++i) {
+                        double v = 0.0;
+                        if (bps == 1) {
+                            const size_t byte_i = (size_t)(j - oy) * pitch1 + (size_t)i / 8;
+                            const int bit_i = i % 8;
+                            if (byte_i < nbytes) v = (double)((buf[byte_i] >> (7 - bit_i)) & 1);
+                        } else {
+                            const size_t off = ((size_t)(j - oy) * W + (size_t)i) * bytes_per_sample;
+                            if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
+                        }
+                        dest(i, j, k) = (v > thr) ? v_true : v_false;
+                    }
+            }
+        }
+    };
+
+    try {
+        if (m_is_sequence) {
+            for (int k = 0; k < m_depth; ++k) {
+                const std::string name = sequenceName(m_base_pattern, m_start_index + k, m_digits, m_suffix);
+                TiffFile f(name);
+                const std::vector<Ifd> dirs = f.directories();
+                if (dirs.empty()) amrex::Abort("[TiffReader] Seq: empty file " + name);
+                decodeDirectory(f, dirs[0], k);
+            }
+        } else {
+            TiffFile f(m_filename);                                    // opened once, not once per slice
+            const std::vector<Ifd> dirs = f.directories();
+            for (int k = 0; k < m_depth && k < (int)dirs.size(); ++k) decodeDirectory(f, dirs[k], k);
+        }
+    } catch (const std::exception& e) {
+        amrex::Abort(std::string("[TiffReader] ") + e.what());
+    }
+}
+
+void TiffReader::threshold(double raw_threshold, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {
+    readDistributedIntoFab(mf, value_if_true, value_if_false, raw_threshold);
+}
+
+void TiffReader::threshold(double raw_threshold, amrex::iMultiFab& mf) const { threshold(raw_threshold, 1, 0, mf); }
+
+}  // namespace OpenImpala

@@ -1,0 +1,128 @@
+"""The C++ host front end (openimpala_b200/host): reference-named classes over
+AMReX-shaped shims, readers, and the Diffusion / tTortuosity drivers.  CPU tests
+cover the readers (reference sample files: tTiffReader / tRawReader /
+tHDF5Reader facts); GPU tests run the apps end to end against the golden values."""
+import json
+import math
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+BIN = os.path.join(ROOT, "openimpala_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def host_bins(built_lib):
+    from openimpala_b200 import build
+    build.build_host()
+    for exe in ("Diffusion", "tTortuosity", "tReaders"):
+        assert os.path.exists(os.path.join(BIN, exe))
+    return BIN
+
+
+def run(exe, *args, check=True):
+    r = subprocess.run([os.path.join(BIN, exe), *args], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    if check:
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r
+
+
+def field(out, key):
+    m = re.search(rf"{key}:\s*(.+)", out)
+    assert m, f"{key} not in output"
+    return m.group(1).split()
+
+
+@pytest.mark.parametrize("mode,args,dims,count1", [
+    ("tiff", ["tifffile=tests/golden/SampleData_2Phase_stack_3d_1bit.tif"], [100, 100, 100], 398309),
+    ("tiff", ["tifffile=tests/golden/spheres.tif"], [100, 100, 100], 888024),      # Photometric=0 is NOT inverted
+    ("tiff", ["tifffile=tests/golden/SampleData_2Phase_squared.tif"], [64, 64, 64], 104681),
+    ("raw", ["rawfile=tests/golden/SampleData_2Phase_stack_3d_uint8.raw", "width=100", "height=100", "depth=100",
+             "datatype=UINT8", "threshold=0.5"], [100, 100, 100], 399553),
+    ("hdf5", ["hdf5file=tests/golden/SampleData_2Phase_3d.hdf5", "hdf5dataset=image"], [100, 100, 100], 399553),
+])
+def test_readers_match_reference_fixtures(host_bins, mode, args, dims, count1):
+    r = run("tReaders", f"mode={mode}", "gpu_count=0", *args)
+    assert [int(v) for v in field(r.stdout, "Dims")] == dims
+    assert field(r.stdout, "ThresholdMinMax") == ["0", "1"]
+    assert int(field(r.stdout, "DirectCount1")[0]) == count1
+    if mode == "tiff" and "1bit" in args[0]:
+        assert "BitsPerSample: 1 SampleFormat: 1 SamplesPerPixel: 1" in r.stdout   # tTiffReader.cpp
+
+
+def test_readers_agree_with_oracle_decoder(host_bins):
+    from oracle import oi_numpy as o
+    for name in ("SampleData_2Phase_stack_3d_1bit.tif", "spheres.tif", "SampleData_2Phase_squared.tif"):
+        ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, name)))
+        r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile=tests/golden/{name}")
+        assert int(field(r.stdout, "DirectCount1")[0]) == int(ph.sum())
+
+
+def test_missing_required_key_aborts(host_bins):
+    r = run("Diffusion", "calculation_method=flow_through", check=False)
+    assert r.returncode != 0 and "filename" in r.stderr
+
+
+def test_default_method_is_out_of_scope(host_bins):
+    # the app's default calculation_method is homogenization (Diffusion.cpp:188): not built here
+    r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
+            "results_path=gpurun_out/r0/", check=False)
+    assert r.returncode != 0 and "flow_through" in r.stderr
+
+
+def test_no_gpu_aborts_loudly(host_bins):
+    from openimpala_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = run("tReaders", "mode=tiff", "tifffile=tests/golden/SampleData_2Phase_squared.tif", check=False)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+# ------------------------------------------------------------------ GPU: the apps end to end
+@pytest.mark.gpu
+def test_tvolumefraction_counts_on_gpu(host_bins):
+    r = run("tReaders", "mode=tiff", "tifffile=tests/golden/SampleData_2Phase_stack_3d_1bit.tif")
+    assert "VolumeFractionCount1: 398309 of 1000000" in r.stdout
+    assert "VolumeFractionCount0: 601691 of 1000000" in r.stdout
+    assert "TEST PASSED" in r.stdout
+
+
+@pytest.mark.gpu
+def test_ttortuosity_driver(host_bins):
+    r = run("tTortuosity", "tests/inputs/tTortuosity.inputs")
+    assert "Matrix/vector property checks passed" in r.stdout
+    assert "Conservation Check Status: PASS" in r.stdout
+    assert "TEST PASSED" in r.stdout
+    tau = float(field(r.stdout, "Final Calculated Tortuosity")[0])
+    assert abs(tau - 1.6934074851) <= 1e-6 * 1.6934074851
+
+
+@pytest.mark.gpu
+def test_diffusion_app_results_txt(host_bins):
+    gold = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs")
+    txt = open(os.path.join(ROOT, "gpurun_out", "results_diffusion", "results.txt")).read()
+    lines = [l for l in txt.splitlines() if not l.startswith("#")]
+    vals = dict(l.split(": ") for l in lines)
+    assert list(vals) == ["VolumeFraction", "Tortuosity_X", "Tortuosity_Y", "Tortuosity_Z"]   # map-sorted
+    assert vals["VolumeFraction"] == "0.398309000"                                            # %.9f
+    for d, key in enumerate(["Tortuosity_X", "Tortuosity_Y", "Tortuosity_Z"]):
+        ref = next(c for c in gold["cases"] if c["phase"] == 1 and c["direction"] == d)["tau"]
+        assert abs(float(vals[key]) - ref) <= 1e-6 * ref
+        assert re.fullmatch(r"\d+\.\d{9}", vals[key])
+
+
+@pytest.mark.gpu
+def test_diffusion_cli_overrides_and_blocked_phase(host_bins):
+    # command-line key=value after the inputs file wins (ParmParse), phase 0, one direction
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "phase_id=0", "direction=Z",
+        "results_path=gpurun_out/results_p0/", "verbose=0")
+    txt = open(os.path.join(ROOT, "gpurun_out", "results_p0", "results.txt")).read()
+    assert "# Analysis Phase ID: 0" in txt and "VolumeFraction: 0.601691000" in txt
+    tau = float(re.search(r"Tortuosity_Z: (\S+)", txt).group(1))
+    assert abs(tau - 1.6930525106) <= 1e-6 * 1.6930525106
+    assert "Tortuosity_X" not in txt
