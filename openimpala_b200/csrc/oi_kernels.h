@@ -123,9 +123,14 @@ void build_flags(const Grid& g, const uint8_t* active, uint8_t* flags, int dir,
 // Dirichlet values, which is what the solver starts from.
 void fill_initial_guess(const Grid& g, const uint8_t* flags, double* x, int dir, int n_dir_global,
                         double vlo, double vhi, int mirror_quirk, cudaStream_t st);
-// isolated-voxel filter, one Jacobi-ordered pass (see DESIGN.md on ordering)
-void remspot_pass(const uint8_t* in, uint8_t* out, int nx, int ny, int nz, int z0, int nzg,
-                  cudaStream_t st);
+// isolated-voxel filter with the reference's in-place (sequential) semantics, as a
+// fixed-point iteration on flip flags: one round, then the final xor
+void remspot_round(const uint8_t* v, const uint8_t* fcur, uint8_t* fnext, int nx, int ny, int nz,
+                   int* changed, int n_sm, cudaStream_t st);
+void remspot_apply(uint8_t* v, const uint8_t* f, long long n, unsigned long long* flips, int n_sm,
+                   cudaStream_t st);
+void count_nonbinary_u8(const uint8_t* f, long long n, unsigned long long* out, int n_sm, cudaStream_t st);
+void count_nonbinary_i32(const int32_t* f, long long n, unsigned long long* out, int n_sm, cudaStream_t st);
 // boundary fluxes (TortuosityHypre.cpp:1052-1105): out[0]=sum_in, out[1]=sum_out
 void flux_planes(const Grid& g, const uint8_t* flags, const double* x, int dir, int n_dir_global,
                  double* partials, unsigned int* counter, double* out, cudaStream_t st);

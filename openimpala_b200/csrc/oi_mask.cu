@@ -495,6 +495,82 @@ void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int 
     const long long n = (long long)g.nz * g.plane;
     check_rows_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, flags, active, dir, n_dir, bad);
 }
-void remspot_pass(const uint8_t*, uint8_t*, int, int, int, int, int, cudaStream_t) {}
+namespace {
+// tortuosity_remspot (src/props/Tortuosity_filcc.F90:88-177) is an IN-PLACE sweep in
+// i-fastest order: a cell sees the already-updated values of its -x,-y,-z neighbours
+// and the old values of its +x,+y,+z neighbours.  That is a triangular dependency,
+// solved here by fixed-point iteration on the flip flags (exact after as many rounds
+// as the longest chain of mutually dependent isolated voxels, usually 2-3):
+//   flip_c = no in-domain neighbour equals v_c, with earlier neighbours read as
+//            v ^ flip (current estimate) and later neighbours as v.
+__global__ void __launch_bounds__(BT)
+remspot_round_kernel(const uint8_t* __restrict__ v, const uint8_t* __restrict__ fcur,
+                     uint8_t* __restrict__ fnext, int nx, int ny, int nz, int* changed) {
+    const long long n = (long long)nx * ny * nz;
+    const long long plane = (long long)nx * ny;
+    const long long stride = (long long)gridDim.x * BT;
+    bool any = false;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const int i = (int)(idx % nx);
+        const int j = (int)((idx / nx) % ny);
+        const int k = (int)(idx / plane);
+        const uint8_t c = v[idx];
+        bool connected = false;                                  // outside the domain never matches
+        if (i + 1 < nx) connected |= (v[idx + 1] == c);
+        if (j + 1 < ny) connected |= (v[idx + nx] == c);
+        if (k + 1 < nz) connected |= (v[idx + plane] == c);
+        if (i > 0) connected |= ((uint8_t)(v[idx - 1] ^ fcur[idx - 1]) == c);
+        if (j > 0) connected |= ((uint8_t)(v[idx - nx] ^ fcur[idx - nx]) == c);
+        if (k > 0) connected |= ((uint8_t)(v[idx - plane] ^ fcur[idx - plane]) == c);
+        const uint8_t f = connected ? 0 : 1;
+        if (f != fcur[idx]) any = true;
+        fnext[idx] = f;
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *changed = 1;
+}
+
+__global__ void __launch_bounds__(BT)
+remspot_apply_kernel(uint8_t* __restrict__ v, const uint8_t* __restrict__ f, long long n,
+                     unsigned long long* flips) {
+    const long long stride = (long long)gridDim.x * BT;
+    long long acc = 0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const uint8_t fl = f[idx];
+        v[idx] ^= fl;
+        acc += fl;
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(flips, (unsigned long long)acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT)
+count_nonbinary_kernel(const T* __restrict__ f, long long n, unsigned long long* out) {
+    const long long stride = (long long)gridDim.x * BT;
+    long long acc = 0;
+    for (long long i = (long long)blockIdx.x * BT + threadIdx.x; i < n; i += stride) {
+        const int v = (int)f[i];
+        acc += (v != 0 && v != 1) ? 1 : 0;
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+}
+}  // namespace
+
+void remspot_round(const uint8_t* v, const uint8_t* fcur, uint8_t* fnext, int nx, int ny, int nz,
+                   int* changed, int n_sm, cudaStream_t st) {
+    const long long n = (long long)nx * ny * nz;
+    remspot_round_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(v, fcur, fnext, nx, ny, nz, changed);
+}
+void remspot_apply(uint8_t* v, const uint8_t* f, long long n, unsigned long long* flips, int n_sm,
+                   cudaStream_t st) {
+    remspot_apply_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(v, f, n, flips);
+}
+void count_nonbinary_u8(const uint8_t* f, long long n, unsigned long long* out, int n_sm, cudaStream_t st) {
+    count_nonbinary_kernel<uint8_t><<<nblocks(n, n_sm), BT, 0, st>>>(f, n, out);
+}
+void count_nonbinary_i32(const int32_t* f, long long n, unsigned long long* out, int n_sm, cudaStream_t st) {
+    count_nonbinary_kernel<int32_t><<<nblocks(n, n_sm), BT, 0, st>>>(f, n, out);
+}
 
 }  // namespace oi

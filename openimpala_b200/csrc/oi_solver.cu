@@ -143,7 +143,7 @@ struct oi_solver {
     // setup state
     uint8_t* d_isphase = nullptr;      // [n_local]
     Field<uint8_t> active, flags;
-    long long phase_count_local = -1;
+    long long phase_count_local = -1, nonbinary_local = 0;
     long long n_active = -1, n_in = 0, n_out = 0;
     bool mask_built = false, hierarchy_built = false, solved = false;
     bool levels_allocated = false, vectors_allocated = false;
@@ -723,20 +723,23 @@ void set_phase_common(oi_solver* S, const T* src, bool src_on_device) {
         d_in = d_raw;
     }
     if (!S->d_isphase) CUDA_CHECK(cudaMalloc(&S->d_isphase, (size_t)n));
-    CUDA_CHECK(cudaMemsetAsync(S->d_ull + 4, 0, sizeof(unsigned long long), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->d_ull + 4, 0, 2 * sizeof(unsigned long long), S->st));
     if (sizeof(T) == 1) {
         oi::count_phase_u8(reinterpret_cast<const uint8_t*>(d_in), n, S->prm.phase_id, S->d_ull + 4, S->n_sm, S->st);
+        oi::count_nonbinary_u8(reinterpret_cast<const uint8_t*>(d_in), n, S->d_ull + 5, S->n_sm, S->st);
         oi::phase_u8_to_isphase(reinterpret_cast<const uint8_t*>(d_in), S->d_isphase, n, S->prm.phase_id, S->n_sm, S->st);
     } else {
         oi::count_phase_i32(reinterpret_cast<const int32_t*>(d_in), n, S->prm.phase_id, S->d_ull + 4, S->n_sm, S->st);
+        oi::count_nonbinary_i32(reinterpret_cast<const int32_t*>(d_in), n, S->d_ull + 5, S->n_sm, S->st);
         oi::phase_i32_to_u8(reinterpret_cast<const int32_t*>(d_in), S->d_isphase, n, S->prm.phase_id, S->n_sm, S->st);
     }
-    S->launches += 2;
-    unsigned long long h = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h, S->d_ull + 4, sizeof(h), cudaMemcpyDeviceToHost, S->st));
+    S->launches += 3;
+    unsigned long long h[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(h, S->d_ull + 4, sizeof(h), cudaMemcpyDeviceToHost, S->st));
     CUDA_CHECK(cudaStreamSynchronize(S->st));
     CUDA_CHECK(cudaGetLastError());
-    S->phase_count_local = (long long)h;
+    S->phase_count_local = (long long)h[0];
+    S->nonbinary_local = (long long)h[1];
     if (d_raw) cudaFree(d_raw);
     S->mask_built = false;
     S->solved = false;
@@ -967,7 +970,40 @@ int oi_remspot(oi_solver* S, int32_t passes) {
     return guarded([&] {
         OI_REQUIRE(S, "null handle");
         if (passes <= 0) return;                       // TortuosityHypre.cpp:258-263
-        throw OiError(OI_ERR_INVALID, "tortuosity.remspot_passes > 0 is not implemented yet");
+        OI_REQUIRE(S->d_isphase != nullptr, "oi_remspot: call oi_set_phase_* first");
+        OI_REQUIRE(S->n_ranks == 1, "oi_remspot: the isolated-voxel filter is single-slab only in this build");
+        OI_REQUIRE(S->nonbinary_local == 0 && (S->prm.phase_id == 0 || S->prm.phase_id == 1),
+                   "oi_remspot: the filter flips 0<->1 and needs a binary {0,1} phase field");
+        ensure_device(S);
+        const Grid& g = S->g;
+        const long long n = S->n_local;
+        uint8_t *fa = nullptr, *fb = nullptr;
+        CUDA_CHECK(cudaMalloc(&fa, (size_t)n));
+        CUDA_CHECK(cudaMalloc(&fb, (size_t)n));
+        for (int pass = 0; pass < passes; ++pass) {    // TortuosityHypre.cpp:269-287
+            CUDA_CHECK(cudaMemsetAsync(fa, 0, (size_t)n, S->st));
+            const int max_rounds = 4 * (g.nx + g.ny + g.nz) + 16;
+            int changed = 1, round = 0;
+            while (changed && round < max_rounds) {
+                ++round;
+                CUDA_CHECK(cudaMemsetAsync(S->d_changed, 0, sizeof(int), S->st));
+                oi::remspot_round(S->d_isphase, fa, fb, g.nx, g.ny, g.nz, S->d_changed, S->n_sm, S->st);
+                S->launches++;
+                CUDA_CHECK(cudaMemcpyAsync(&changed, S->d_changed, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+                CUDA_CHECK(cudaStreamSynchronize(S->st));
+                std::swap(fa, fb);
+            }
+            if (changed) {
+                cudaFree(fa); cudaFree(fb);
+                throw OiError(OI_ERR_INVALID, "oi_remspot: flip flags did not reach their fixed point");
+            }
+            oi::remspot_apply(S->d_isphase, fa, n, S->d_ull + 7, S->n_sm, S->st);
+            S->launches++;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(S->st));
+        cudaFree(fa); cudaFree(fb);
+        S->mask_built = false;
+        S->solved = false;
     });
 }
 

@@ -22,6 +22,8 @@ def load():
         lib.oo_num_threads.restype = C.c_int
         lib.oo_count_phase_i32.restype = C.c_int64
         lib.oo_count_phase_i32.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
+        lib.oo_remspot.restype = None
+        lib.oo_remspot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.oo_flood_fill.restype = C.c_int
         lib.oo_flood_fill.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_int]
@@ -58,6 +60,15 @@ def _i32(a):
 def count_phase(phase, phase_id):
     p = _i32(phase)
     return int(load().oo_count_phase_i32(p.ctypes.data, p.size, phase_id))
+
+
+def remspot(phase, passes=1):
+    """tortuosity_remspot, in place order; returns the filtered copy."""
+    q = _i32(phase).copy()
+    nz, ny, nx = q.shape
+    for _ in range(passes):
+        load().oo_remspot(q.ctypes.data, nx, ny, nz)
+    return q
 
 
 def activity_mask(phase, phase_id, direction, capped=False):

@@ -48,6 +48,26 @@ int64_t oo_count_phase_i32(const int32_t* f, int64_t n, int32_t phase) {
     return c;
 }
 
+/* tortuosity_remspot, src/props/Tortuosity_filcc.F90:88-177: in-place, i fastest;
+ * a voxel none of whose in-domain 6 neighbours holds its value flips 0 <-> 1
+ * (any non-zero value becomes 0).  One pass over the whole domain as one box. */
+void oo_remspot(int32_t* q, int nx, int ny, int nz) {
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t c = IDX(i, j, k);
+                const int32_t v = q[c];
+                int connected = 0;
+                if (i > 0 && q[c - 1] == v) connected = 1;
+                else if (i + 1 < nx && q[c + 1] == v) connected = 1;
+                else if (j > 0 && q[c - nx] == v) connected = 1;
+                else if (j + 1 < ny && q[c + nx] == v) connected = 1;
+                else if (k > 0 && q[c - (int64_t)nx * ny] == v) connected = 1;
+                else if (k + 1 < nz && q[c + (int64_t)nx * ny] == v) connected = 1;
+                if (!connected) q[c] = (v == 0) ? 1 : 0;
+            }
+}
+
 /* parallelFloodFill, src/props/TortuosityHypre.cpp:297-389: the literal sweep --
  * in-place lexicographic (i fastest) pass over the whole box, repeated until a
  * pass changes nothing or `max_iter` passes were made (max_iter <= 0: no cap;

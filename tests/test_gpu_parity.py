@@ -216,3 +216,59 @@ def test_preconditioner_is_symmetric(capi):
         lhs, rhs = float((ma * b).sum()), float((a * mb).sum())
         assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
         assert float((ma * a).sum()) > 0.0
+
+
+# ------------------------------------------------------------------ a-3: tortuosity_remspot
+def _remspot_cases():
+    rng = np.random.default_rng(42)
+    noise = (rng.random((14, 18, 22)) < 0.5).astype(np.int32)            # many isolated voxels
+    kk, jj, ii = np.indices((10, 12, 16))
+    checker = ((kk + jj + ii) & 1).astype(np.int32)                       # every voxel isolated: order matters
+    blobs = _blobs((20, 20, 20), 3, 0.5, sigma=0.8)
+    mixed = blobs.copy()
+    mixed[5:12, 5:12, 5:12] = checker[:7, :7, :7]
+    return [noise, checker, blobs, mixed]
+
+
+@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("passes", [1, 2])
+def test_remspot_matches_sequential_reference_order(capi, case, passes):
+    from oracle import oi_c, oi_numpy as o
+    ph = _remspot_cases()[case]
+    ref = oi_c.remspot(ph, passes)
+    if ph.size <= 4000:
+        assert np.array_equal(ref, o.remspot(ph, passes))                 # the two restatements agree
+    for phase_id in (1, 0):
+        with capi.Solver(ph.shape, 0, phase_id) as s:
+            s.set_phase(ph)
+            s.remspot(passes)
+            n_active = s.build_mask()
+            mask_ref = o.activity_mask(ref, phase_id, 0)
+            assert n_active == int(mask_ref.sum())
+            if n_active:
+                assert np.array_equal(s.mask().astype(bool), mask_ref)
+
+
+def test_remspot_rejects_non_binary_field(capi):
+    ph = np.full((6, 6, 6), 2, dtype=np.int32)
+    with capi.Solver(ph.shape, 0, 1) as s:
+        s.set_phase(ph)
+        with pytest.raises(capi.OiError):
+            s.remspot(1)
+        s.remspot(0)                                                       # 0 passes: skipped, like the reference
+
+
+def test_remspot_through_class_parmparse(capi):
+    from oracle import oi_c, oi_numpy as o
+    from openimpala_b200.tortuosity import Direction, ParmParse, SolverType, TortuosityHypre
+    rng = np.random.default_rng(7)
+    ph = _blobs((18, 18, 18), 12, 0.6)
+    ph[rng.random(ph.shape) < 0.03] ^= 1                                   # salt-and-pepper
+    ParmParse.table = {"tortuosity.remspot_passes": 1}
+    try:
+        t = TortuosityHypre(None, None, None, ph, 0.6, 1, Direction.Y, SolverType.FlexGMRES, "", -1.0, 1.0)
+    finally:
+        ParmParse.table = {}
+    ref = o.tortuosity(oi_c.remspot(ph, 1), 1, 1, -1.0, 1.0, eps=1e-13)
+    assert t._n_active == ref.n_active
+    assert abs(t.value() - ref.tau) <= TAU_RTOL * abs(ref.tau)
