@@ -240,7 +240,10 @@ def main():
         kern[name] = {"ms": ms, "gbs": bpc * local_cells / (ms * 1e-3) / 1e9, "bytes_per_cell": bpc}
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("apply_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        # ncu dram bytes per launch of the APPLY kernel, captured at tj["apply_cells"] cells and
+        # scaled to this launch's cell count (traffic is proportional to cells for this kernel)
+        traffic = tj["apply_bytes_per_launch"] / tj["apply_cells"] * local_cells
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "l0_zmarch_kernel<APPLY,dot> (y = A p, p.Ap)",
