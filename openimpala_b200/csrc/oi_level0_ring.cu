@@ -42,6 +42,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
     const int sz = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -59,6 +64,7 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
     double* us = smem;                                          // [RING_R][U_STAGE]
     double* bs = us + RING_R * U_STAGE;                         // [RING_R][B_STAGE]   (MODE != 0)
     double* dtab = bs + (MODE != 0 ? RING_R * B_STAGE : 0);     // [64] diagonal, [64] its inverse
+    unsigned char* fs = reinterpret_cast<unsigned char*>(dtab + 128);   // [RING_R][TY][TX] connectivity bytes
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -96,6 +102,7 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
 
     const int c_off = (ty + 1) * PITCH + 2 + 2 * tx2;           // own centre pair inside a u stage
     const int b_off = ty * TX + 2 * tx2;
+    const int f_off = ty * TX + 2 * tx2;                        // byte offset inside a flag stage
 
     // issue all copies of plane kk into stage st (offset kk*plane is carried by the caller)
     auto issue = [&](long long poff, int st, bool with_b) {
@@ -108,6 +115,8 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
         if (MODE != 0) {
             if (with_b) cp_async16(bs + st * B_STAGE + b_off, b_own + poff, inb);
         }
+        // connectivity bytes of 4 cells (this thread's pair and its odd neighbour's)
+        if (with_b && (tx2 & 1) == 0) cp_async4(fs + st * (TX * TY) + f_off, flags + col + poff, inb);
     };
 
     // prologue: planes k0-1 .. k0+RING_P, one commit group per plane
@@ -120,95 +129,85 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
         poff_issue += g.plane;
         ++kk_issue;
     }
-    int st_issue = 0;                                           // next stage to refill (= stage of plane k-1)
-
-    // flag pairs of planes k0 .. k0+RING_P-1
-    const unsigned short* f_own = reinterpret_cast<const unsigned short*>(flags + col);
-    unsigned int fq[RING_P];
-    long long foff = (long long)k0 * (g.plane >> 1);            // in ushort units (plane even)
-    const long long fplane = g.plane >> 1;
-#pragma unroll
-    for (int s = 0; s < RING_P; ++s) {
-        fq[s] = (inb && (k0 + s) < k1) ? (unsigned int)f_own[foff] : 0u;
-        foff += fplane;
-    }
-
     cp_async_wait<RING_P>();                                    // planes k0-1 and k0 have landed
     __syncthreads();
-    double2 v_m = *reinterpret_cast<const double2*>(us + 0 * U_STAGE + c_off);
-    double2 v_c = *reinterpret_cast<const double2*>(us + 1 * U_STAGE + c_off);
+    // register window over the column: vv[s % 3] = plane k-1, vv[(s+1) % 3] = plane k
+    double2 vv[3];
+    vv[0] = *reinterpret_cast<const double2*>(us + 0 * U_STAGE + c_off);
+    vv[1] = *reinterpret_cast<const double2*>(us + 1 * U_STAGE + c_off);
 
     double dot_acc = 0.0, zpair = 0.0;
-    int sc = 1;                                                 // stage of plane k
     double* out_own = out + col + (long long)k0 * g.plane;      // MODE 0/1
 
-    for (int k = k0; k < k1; ++k) {
-        cp_async_wait<RING_P - 1>();                            // own copies of planes <= k+1 landed
-        __syncthreads();                                        // ... and everybody else's
-
-        const int sp = (sc == RING_R - 1) ? 0 : sc + 1;
-        const double* Sc = us + sc * U_STAGE;
-        const double2 v_p = *reinterpret_cast<const double2*>(us + sp * U_STAGE + c_off);
-        const double xw = Sc[c_off - 1], xe = Sc[c_off + 2];
-        const double2 ys = *reinterpret_cast<const double2*>(Sc + c_off - PITCH);
-        const double2 yn = *reinterpret_cast<const double2*>(Sc + c_off + PITCH);
-        double2 bb = make_double2(0.0, 0.0);
-        if (MODE != 0) bb = *reinterpret_cast<const double2*>(bs + sc * B_STAGE + b_off);
-
-        const unsigned int f2 = fq[0];
+    // The plane loop is unrolled by the ring length, so that stage numbers, the
+    // register window and the flag queue slot are compile-time constants: plane
+    // kb+s always lives in stage (s+1) % RING_R.
+    for (int kb = k0; kb < k1; kb += RING_R) {
 #pragma unroll
-        for (int s = 0; s + 1 < RING_P; ++s) fq[s] = fq[s + 1];
-        fq[RING_P - 1] = (inb && (k + RING_P) < k1) ? (unsigned int)f_own[foff] : 0u;
-        foff += fplane;
+        for (int s = 0; s < RING_R; ++s) {
+            const int k = kb + s;
+            if (k >= k1) break;                                 // CTA-uniform
+            constexpr int R = RING_R;
+            const int sc = (s + 1) % R, sp = (s + 2) % R;       // stages of planes k, k+1
+            cp_async_wait<RING_P - 1>();                        // own copies of planes <= k+1 landed
+            __syncthreads();                                    // ... and everybody else's
 
-        const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
-        // (A u) for the two cells
-        const double au0 = dtab[f0 & 63u] * v_c.x - (g.cx * (xw + v_c.y) + g.cy * (ys.x + yn.x) + g.cz * (v_m.x + v_p.x));
-        const double au1 = dtab[f1 & 63u] * v_c.y - (g.cx * (v_c.x + xe) + g.cy * (ys.y + yn.y) + g.cz * (v_m.y + v_p.y));
-        double2 o = make_double2(0.0, 0.0);
-        double res = 0.0;
-        if (MODE == 0) {
-            if (f0 & F_UNK) o.x = w * au0;
-            if (f1 & F_UNK) o.y = w * au1;
-            if (DOT) dot_acc += v_c.x * o.x + v_c.y * o.y;
-        } else if (MODE == 1) {
-            if (f0 & F_UNK) o.x = v_c.x + w * (bb.x - au0) * dtab[64 + (f0 & 63u)];
-            if (f1 & F_UNK) o.y = v_c.y + w * (bb.y - au1) * dtab[64 + (f1 & 63u)];
-            if (DOT) dot_acc += bb.x * o.x + bb.y * o.y;
-        } else {
-            if (f0 & F_UNK) res = bb.x - au0;
-            if (f1 & F_UNK) res += bb.y - au1;
-        }
-        if (MODE != 2) {
-            if (inb) *reinterpret_cast<double2*>(out_own) = o;
-            out_own += g.plane;
-        } else {
-            // x pair already summed in-thread; y pair = lane ^ 16; z pair carried
-            double s = res + __shfl_xor_sync(0xffffffffu, res, 16);
-            const int kg = g.z0 + k;
-            bool flush = true;
-            if (fz == 2) {
-                if ((kg & 1) == 0) { zpair = s; flush = (k + 1 == k1); }
-                else { s += zpair; zpair = 0.0; }
+            const double* Sc = us + sc * U_STAGE;
+            const double2 v_m = vv[s % 3], v_c = vv[(s + 1) % 3];
+            const double2 v_p = *reinterpret_cast<const double2*>(us + sp * U_STAGE + c_off);
+            vv[(s + 2) % 3] = v_p;
+            const double xw = Sc[c_off - 1], xe = Sc[c_off + 2];
+            const double2 ys = *reinterpret_cast<const double2*>(Sc + c_off - PITCH);
+            const double2 yn = *reinterpret_cast<const double2*>(Sc + c_off + PITCH);
+            double2 bb = make_double2(0.0, 0.0);
+            if (MODE != 0) bb = *reinterpret_cast<const double2*>(bs + sc * B_STAGE + b_off);
+
+            const unsigned int f2 = *reinterpret_cast<const unsigned short*>(fs + sc * (TX * TY) + f_off);
+
+            const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
+            // (A u) for the two cells
+            const double au0 = dtab[f0 & 63u] * v_c.x - (g.cx * (xw + v_c.y) + g.cy * (ys.x + yn.x) + g.cz * (v_m.x + v_p.x));
+            const double au1 = dtab[f1 & 63u] * v_c.y - (g.cx * (v_c.x + xe) + g.cy * (ys.y + yn.y) + g.cz * (v_m.y + v_p.y));
+            double2 o = make_double2(0.0, 0.0);
+            double res = 0.0;
+            if (MODE == 0) {
+                if (f0 & F_UNK) o.x = w * au0;
+                if (f1 & F_UNK) o.y = w * au1;
+                if (DOT) dot_acc += v_c.x * o.x + v_c.y * o.y;
+            } else if (MODE == 1) {
+                if (f0 & F_UNK) o.x = v_c.x + w * (bb.x - au0) * dtab[64 + (f0 & 63u)];
+                if (f1 & F_UNK) o.y = v_c.y + w * (bb.y - au1) * dtab[64 + (f1 & 63u)];
+                if (DOT) dot_acc += bb.x * o.x + bb.y * o.y;
+            } else {
+                if (f0 & F_UNK) res = bb.x - au0;
+                if (f1 & F_UNK) res += bb.y - au1;
             }
-            if (flush && inb && ((j & 1) == 0)) {
-                const int ck = (fz == 2) ? ((kg >> 1) - rc.z0h) : k;
-                out[((long long)ck * rc.cny + (j >> 1)) * rc.cnx + (i >> 1)] = s;
+            if (MODE != 2) {
+                if (inb) *reinterpret_cast<double2*>(out_own) = o;
+                out_own += g.plane;
+            } else {
+                // x pair already summed in-thread; y pair = lane ^ 16; z pair carried
+                double sum = res + __shfl_xor_sync(0xffffffffu, res, 16);
+                const int kg = g.z0 + k;
+                bool flush = true;
+                if (fz == 2) {
+                    if ((kg & 1) == 0) { zpair = sum; flush = (k + 1 == k1); }
+                    else { sum += zpair; zpair = 0.0; }
+                }
+                if (flush && inb && ((j & 1) == 0)) {
+                    const int ck = (fz == 2) ? ((kg >> 1) - rc.z0h) : k;
+                    out[((long long)ck * rc.cny + (j >> 1)) * rc.cnx + (i >> 1)] = sum;
+                }
             }
+
+            // refill the stage that held plane k-1 (stage s) with plane k+RING_P+1.  Its
+            // halo cells are dead and its centre cells are only ever read by their own
+            // thread (as v_p two iterations ago), so no second barrier is needed.
+            if (kk_issue <= k1) issue(poff_issue, s, kk_issue < k1);
+            cp_async_commit();
+            poff_issue += g.plane;
+            ++kk_issue;
         }
-
-        // refill the stage that held plane k-1 with plane k+RING_P+1.  Its halo cells
-        // are dead and its centre cells are only ever read by their own thread (as
-        // v_p two iterations ago), so no second barrier is needed.
-        if (kk_issue <= k1) issue(poff_issue, st_issue, kk_issue < k1);
-        cp_async_commit();
-        poff_issue += g.plane;
-        ++kk_issue;
-        st_issue = (st_issue == RING_R - 1) ? 0 : st_issue + 1;
-
-        v_m = v_c;
-        v_c = v_p;
-        sc = sp;
     }
     cp_async_wait<0>();
 
@@ -239,7 +238,8 @@ prolong_add_kernel(Grid g, const uint8_t* __restrict__ flags, double* __restrict
 
 template <int MODE>
 size_t ring_smem_bytes() {
-    return sizeof(double) * (size_t)(RING_R * U_STAGE + (MODE != 0 ? RING_R * B_STAGE : 0) + 128);
+    return sizeof(double) * (size_t)(RING_R * U_STAGE + (MODE != 0 ? RING_R * B_STAGE : 0) + 128) +
+           (size_t)RING_R * TX * TY;
 }
 
 template <int MODE, bool DOT>
@@ -262,7 +262,8 @@ void launch(const L0Args& a, cudaStream_t st) {
 bool ring_supported(const L0Args& a, int mode) {
     // 16-byte vector accesses need even nx (then every row and plane start is
     // 16-byte aligned: plane 0 of every Field is 256-byte aligned)
-    if (a.g.nx & 1) return false;
+    // ... and the 4-byte copies of the connectivity bytes need nx % 4 == 0
+    if (a.g.nx & 3) return false;
     if (mode == 2 && !(a.fx == 2 && a.fy == 2)) return false;
     return true;
 }
