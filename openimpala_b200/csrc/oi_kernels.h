@@ -71,6 +71,12 @@ void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel&
 void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
                    const double* num, const double* den, double* partials, unsigned int* counter,
                    double* out, int n_sm, cudaStream_t st);
+// same, and q <- w0 * r_new / diag on unknowns (first smoothing sweep of the next
+// preconditioner application, written over the dead q)
+void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
+                         const double* p, double* q, const double* num, const double* den, double w0,
+                         double* partials, unsigned int* counter, double* out, int n_sm,
+                         cudaStream_t st);
 // p = z + (num/den) p
 void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
               int n_sm, cudaStream_t st);

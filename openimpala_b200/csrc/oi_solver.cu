@@ -358,7 +358,13 @@ void coarse_cycle(oi_solver* S, size_t l) {
 }
 
 // z = M^-1 r ; when dot_out != nullptr the last sweep also leaves r.z there
-void apply_precond(oi_solver* S, double* dot_out) {
+double first_smoothing_weight(const oi_solver* S) {
+    return S->levels.empty() ? S->w_coarse[0] : S->w_smooth[0];
+}
+
+// first_done: the first sweep from a zero guess (z1 = w0 r / diag) is already in q
+// (written by the fused axpy2_dot_first kernel of the Krylov update)
+void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     const long long n = S->n_local;
     if (S->prm.precond != OI_PRECOND_MG) {
         oi::l0_jacobi_precond_dot(S->g, S->flags.p, S->r.p, S->z.p, S->d_partials, S->d_counter,
@@ -374,7 +380,7 @@ void apply_precond(oi_solver* S, double* dot_out) {
     const L0Info f0 = l0info(S);
     double* cur = S->q.p;
     double* oth = S->z.p;
-    {
+    if (!first_done) {
         L0Args a = l0args(S, nullptr, S->r.p, cur, w[0], nullptr);
         oi::l0_jacobi_first(a, S->st); S->launches++;
     }
@@ -507,13 +513,20 @@ void run_solve(oi_solver* S) {
                 L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, d_pq);
                 oi::l0_apply(a, true, variant, S->st); S->launches++;       // q = A p, pq = p.q
                 allreduce_sum_f64(S, d_pq, 1);
-                oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
-                                  S->d_counter, d_rr, S->n_sm, S->st); S->launches++;
+                const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
+                if (fuse_first)
+                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq,
+                                            first_smoothing_weight(S), S->d_partials, S->d_counter, d_rr,
+                                            S->n_sm, S->st);
+                else
+                    oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
+                                      S->d_counter, d_rr, S->n_sm, S->st);
+                S->launches++;
                 allreduce_sum_f64(S, d_rr, 1);
                 rr = read_scalar(S, d_rr);
                 if (!std::isfinite(rr)) { fail = true; break; }
                 if (std::sqrt(rr) <= tol) { converged = true; break; }
-                apply_precond(S, d_rzn);
+                apply_precond(S, d_rzn, fuse_first);
                 oi::vec_xpby(n, S->p.p, S->z.p, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
                 std::swap(d_rz, d_rzn);
             }

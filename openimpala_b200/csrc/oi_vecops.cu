@@ -42,6 +42,57 @@ axpy2_dot_kernel(long long n, double* __restrict__ x, double* __restrict__ r,
     grid_reduce<1>(v, partials, counter, out);
 }
 
+// Same update, plus the first smoothing sweep of the next preconditioner
+// application from a zero guess, z1 = w0 * r_new / diag, written over q (q = A p is
+// dead once r has been updated; same thread, same index, so in place is safe).
+// Saves re-reading r and one launch per Krylov iteration.
+__global__ void __launch_bounds__(VT)
+axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, double* __restrict__ x,
+                       double* __restrict__ r, const double* __restrict__ p, double* __restrict__ q,
+                       const double* __restrict__ num, const double* __restrict__ den, double w0,
+                       double* partials, unsigned int* counter, double* out) {
+    __shared__ double winv[64];
+    if (threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        const double d = g.cx * (double)__popc(t & 0x03) + g.cy * (double)__popc(t & 0x0c) +
+                         g.cz * (double)__popc(t & 0x30);
+        winv[t] = d > 0.0 ? w0 / d : 0.0;
+    }
+    __syncthreads();
+    const double a = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT * 2;
+    double acc = 0.0;
+    const long long n2 = n & ~1LL;
+    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
+        double2 xv = *reinterpret_cast<double2*>(x + i);
+        double2 rv = *reinterpret_cast<double2*>(r + i);
+        const double2 pv = *reinterpret_cast<const double2*>(p + i);
+        const double2 qv = *reinterpret_cast<const double2*>(q + i);
+        const unsigned int f2 = *reinterpret_cast<const unsigned short*>(flags + i);
+        xv.x += a * pv.x; xv.y += a * pv.y;
+        rv.x -= a * qv.x; rv.y -= a * qv.y;
+        *reinterpret_cast<double2*>(x + i) = xv;
+        *reinterpret_cast<double2*>(r + i) = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+        const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
+        double2 zv;
+        zv.x = (f0 & F_UNK) ? rv.x * winv[f0 & 63u] : 0.0;
+        zv.y = (f1 & F_UNK) ? rv.y * winv[f1 & 63u] : 0.0;
+        *reinterpret_cast<double2*>(q + i) = zv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
+        const long long i = n2;
+        x[i] += a * p[i];
+        const double rv = r[i] - a * q[i];
+        r[i] = rv;
+        acc += rv * rv;
+        const unsigned int f = flags[i];
+        q[i] = (f & F_UNK) ? rv * winv[f & 63u] : 0.0;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, partials, counter, out);
+}
+
 __global__ void __launch_bounds__(VT)
 xpby_kernel(long long n, double* __restrict__ p, const double* __restrict__ z,
             const double* __restrict__ num, const double* __restrict__ den) {
@@ -110,6 +161,13 @@ void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const dou
                    const double* num, const double* den, double* partials, unsigned int* counter,
                    double* out, int n_sm, cudaStream_t st) {
     axpy2_dot_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, x, r, p, q, num, den, partials, counter, out);
+}
+void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
+                         const double* p, double* q, const double* num, const double* den, double w0,
+                         double* partials, unsigned int* counter, double* out, int n_sm,
+                         cudaStream_t st) {
+    axpy2_dot_first_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, num, den, w0,
+                                                                      partials, counter, out);
 }
 void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
               int n_sm, cudaStream_t st) {
