@@ -86,12 +86,12 @@ build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scale) {
     }
 }
 
-// MODE 1: out = x + w (b - A x)/dg ; MODE 2: out = b - A x
+// MODE 1: out = x + w (b - A x)/dg ; MODE 2: out = b - A x      (all in mg_t arithmetic)
 // 64 x 4 cells per CTA in (x, y), blockIdx.z strides over planes (32-bit index math only).
 template <int MODE>
 __global__ void __launch_bounds__(256)
-coarse_stencil_kernel(CoarseLevel L, const double* __restrict__ x, const double* __restrict__ b,
-                      double* __restrict__ out, double w) {
+coarse_stencil_kernel(CoarseLevel L, const mg_t* __restrict__ x, const mg_t* __restrict__ b,
+                      mg_t* __restrict__ out, mg_t w) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (i >= L.nx || j >= L.ny) return;
@@ -99,28 +99,28 @@ coarse_stencil_kernel(CoarseLevel L, const double* __restrict__ x, const double*
     for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
         const long long idx = (long long)k * L.plane + col;
         const float d = L.dg[idx];
-        double o = 0.0;
+        mg_t o = 0;
         if (d > 0.f) {
-            const double c = x[idx];
-            double acc = (double)d * c;
+            const mg_t c = x[idx];
+            mg_t acc = (mg_t)d * c;
             // couplings are zero across domain faces, so guarded loads suffice
             const float cxp = L.cxp[idx], cyp = L.cyp[idx], czp = L.czp[idx];
-            if (cxp != 0.f) acc -= (double)cxp * x[idx + 1];
-            if (cyp != 0.f) acc -= (double)cyp * x[idx + L.nx];
-            if (czp != 0.f) acc -= (double)czp * x[idx + L.plane];
+            if (cxp != 0.f) acc -= (mg_t)cxp * x[idx + 1];
+            if (cyp != 0.f) acc -= (mg_t)cyp * x[idx + L.nx];
+            if (czp != 0.f) acc -= (mg_t)czp * x[idx + L.plane];
             if (i > 0) {
                 const float cm = L.cxp[idx - 1];
-                if (cm != 0.f) acc -= (double)cm * x[idx - 1];
+                if (cm != 0.f) acc -= (mg_t)cm * x[idx - 1];
             }
             if (j > 0) {
                 const float cm = L.cyp[idx - L.nx];
-                if (cm != 0.f) acc -= (double)cm * x[idx - L.nx];
+                if (cm != 0.f) acc -= (mg_t)cm * x[idx - L.nx];
             }
             {   // k-1 may be the ghost plane (coefficients exchanged at setup)
                 const float cm = L.czp[idx - L.plane];
-                if (cm != 0.f) acc -= (double)cm * x[idx - L.plane];
+                if (cm != 0.f) acc -= (mg_t)cm * x[idx - L.plane];
             }
-            if (MODE == 1) o = c + w * (b[idx] - acc) / (double)d;
+            if (MODE == 1) o = c + w * (b[idx] - acc) / (mg_t)d;
             else           o = b[idx] - acc;
         }
         out[idx] = o;
@@ -129,7 +129,7 @@ coarse_stencil_kernel(CoarseLevel L, const double* __restrict__ x, const double*
 
 // x += P * ec on non-empty cells (prolongation + correction between coarse levels)
 __global__ void __launch_bounds__(256)
-coarse_prolong_add_kernel(CoarseLevel L, double* __restrict__ x, const double* __restrict__ ec,
+coarse_prolong_add_kernel(CoarseLevel L, mg_t* __restrict__ x, const mg_t* __restrict__ ec,
                           int cnx, int cny) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
@@ -148,33 +148,30 @@ coarse_prolong_add_kernel(CoarseLevel L, double* __restrict__ x, const double* _
 }
 
 __global__ void __launch_bounds__(256)
-coarse_jacobi_first_kernel(CoarseLevel L, const double* __restrict__ b, double* __restrict__ out,
-                           double w) {
+coarse_jacobi_first_kernel(CoarseLevel L, const mg_t* __restrict__ b, mg_t* __restrict__ out, mg_t w) {
     const long long n = (long long)L.nz * L.plane;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
         const float d = L.dg[idx];
-        out[idx] = (d > 0.f) ? w * b[idx] / (double)d : 0.0;
+        out[idx] = (d > 0.f) ? w * b[idx] / (mg_t)d : (mg_t)0;
     }
 }
 
 __global__ void __launch_bounds__(256)
-coarse_restrict_kernel(CoarseLevel f, const double* __restrict__ res, CoarseLevel c,
-                       double* __restrict__ bc) {
-    const long long nc = (long long)c.nz * c.plane;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += stride) {
-        const int ci = (int)(I % c.nx);
-        const int cj = (int)((I / c.nx) % c.ny);
-        const int ck = (int)(I / c.plane);
-        const int i0 = ci * f.fx, j0 = cj * f.fy, k0 = ck * f.fz;
-        const int i1 = min(i0 + f.fx, f.nx), j1 = min(j0 + f.fy, f.ny), k1 = min(k0 + f.fz, f.nz);
-        double s = 0.0;
+coarse_restrict_kernel(CoarseLevel f, const mg_t* __restrict__ res, CoarseLevel c, mg_t* __restrict__ bc) {
+    const int ci = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int cj = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ci >= c.nx || cj >= c.ny) return;
+    const int i0 = ci * f.fx, j0 = cj * f.fy;
+    const int i1 = min(i0 + f.fx, f.nx), j1 = min(j0 + f.fy, f.ny);
+    for (int ck = blockIdx.z; ck < c.nz; ck += gridDim.z) {
+        const int k0 = ck * f.fz, k1 = min(k0 + f.fz, f.nz);
+        mg_t s = 0;
         for (int k = k0; k < k1; ++k)
             for (int j = j0; j < j1; ++j)
                 for (int i = i0; i < i1; ++i)
                     s += res[(long long)k * f.plane + (long long)j * f.nx + i];
-        bc[I] = s;
+        bc[(long long)ck * c.plane + (long long)cj * c.nx + ci] = s;
     }
 }
 
@@ -196,8 +193,8 @@ void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double
     build_from_coarse_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, c, scale);
 }
 
-void coarse_jacobi_first(const CoarseLevel& L, const double* b, double* out, double w, cudaStream_t st) {
-    coarse_jacobi_first_kernel<<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, b, out, w);
+void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
+    coarse_jacobi_first_kernel<<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, b, out, (mg_t)w);
 }
 
 static dim3 grid3(const CoarseLevel& L) {
@@ -205,22 +202,20 @@ static dim3 grid3(const CoarseLevel& L) {
     return dim3((L.nx + 63) / 64, (L.ny + 3) / 4, gz > 0 ? gz : 1);
 }
 
-void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, double* out, double w,
-                   const CoarseLevel*, const double*, cudaStream_t st) {
-    coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, w);
+void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
+    coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
 }
 
-void coarse_prolong_add(const CoarseLevel& L, double* x, const CoarseLevel& next, const double* ec,
-                        cudaStream_t st) {
+void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec, cudaStream_t st) {
     coarse_prolong_add_kernel<<<grid3(L), 256, 0, st>>>(L, x, ec, next.nx, next.ny);
 }
 
-void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out, cudaStream_t st) {
-    coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, 0.0);
+void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st) {
+    coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
 }
 
-void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc, cudaStream_t st) {
-    coarse_restrict_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, res, c, bc);
+void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc, cudaStream_t st) {
+    coarse_restrict_kernel<<<grid3(c), 256, 0, st>>>(f, res, c, bc);
 }
 
 }  // namespace oi

@@ -5,14 +5,16 @@
 namespace oi {
 
 // ---------------------------------------------------------------- level 0
+// APPLY works on fp64 fields (Krylov vectors); SMOOTH / RESTRICT / first sweep /
+// prolongation work on mg_t fields (multigrid preconditioner), hence the void*.
 struct L0Args {
     Grid g;
     const uint8_t* flags;      // connectivity bytes, ghost planes at k=-1, k=nz
-    const double* u;           // input field (ghost planes)
-    const double* b;           // rhs (SMOOTH / RESTRICT)
-    double* out;               // output field, or coarse rhs for RESTRICT
+    const void* u;             // input field (ghost planes)
+    const void* b;             // rhs (SMOOTH / RESTRICT)
+    void* out;                 // output field, or coarse rhs for RESTRICT
     double w;                  // Jacobi weight (SMOOTH) or scale (APPLY)
-    const double* ec;          // coarse correction (ADDC) or nullptr
+    const void* ec;            // coarse correction (ADDC / prolongation) or nullptr
     int cnx, cny;              // coarse dims (ADDC / RESTRICT)
     int fx, fy, fz;            // coarsening factors to level 1
     double* red_partials;      // reduction scratch (DOT)
@@ -45,7 +47,7 @@ struct CoarseLevel {
     int fx, fy, fz;            // coarsening factors from this level to the next
     float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
     float* dg;                 // diagonal (0 = empty aggregate)
-    double *x, *b, *t;         // solution, rhs, scratch (ghost planes)
+    mg_t *x, *b, *t;           // solution, rhs, scratch (ghost planes)
 };
 
 void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int dir_axis, int n_dir_global,
@@ -53,17 +55,15 @@ void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int dir_axis, 
                              cudaStream_t st);
 void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double scale,
                               cudaStream_t st);
-void coarse_jacobi_first(const CoarseLevel& L, const double* b, double* out, double w, cudaStream_t st);
-// out = x (+P ec) + w (b - A x') / dg
-void coarse_smooth(const CoarseLevel& L, const double* x, const double* b, double* out, double w,
-                   const CoarseLevel* next /*add P*next->x when non-null*/, const double* ec,
+void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st);
+// out = x + w (b - A x) / dg
+void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w,
                    cudaStream_t st);
-void coarse_residual(const CoarseLevel& L, const double* x, const double* b, double* out,
-                     cudaStream_t st);
+void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st);
 // x += P * ec  (ec lives on level `next`)
-void coarse_prolong_add(const CoarseLevel& L, double* x, const CoarseLevel& next, const double* ec,
+void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec,
                         cudaStream_t st);
-void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel& c, double* bc,
+void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc,
                      cudaStream_t st);
 
 // ---------------------------------------------------------------- vector ops (K4)
@@ -71,21 +71,24 @@ void coarse_restrict(const CoarseLevel& f, const double* res, const CoarseLevel&
 void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
                    const double* num, const double* den, double* partials, unsigned int* counter,
                    double* out, int n_sm, cudaStream_t st);
-// same, and q <- w0 * r_new / diag on unknowns (first smoothing sweep of the next
-// preconditioner application, written over the dead q)
+// same, plus what the next preconditioner application needs: r32 <- mg_t(r_new) and
+// z1 <- w0 * r_new / diag on unknowns (its first smoothing sweep from a zero guess)
 void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
-                         const double* p, double* q, const double* num, const double* den, double w0,
-                         double* partials, unsigned int* counter, double* out, int n_sm,
-                         cudaStream_t st);
-// p = z + (num/den) p
-void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
+                         const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
+                         const double* den, double w0, double* partials, unsigned int* counter,
+                         double* out, int n_sm, cudaStream_t st);
+// p = z + (num/den) p      (z is a multigrid-precision vector)
+void vec_xpby(long long n, double* p, const mg_t* z, const double* num, const double* den,
               int n_sm, cudaStream_t st);
+// conversions between Krylov (fp64) and multigrid precision
+void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st);
+void vec_from_mg(long long n, double* dst, const mg_t* src, int n_sm, cudaStream_t st);
 // out[0] = a.b
 void vec_dot(long long n, const double* a, const double* b, double* partials,
              unsigned int* counter, double* out, int n_sm, cudaStream_t st);
 void vec_copy(long long n, double* dst, const double* src, int n_sm, cudaStream_t st);
 // z = r / diag on unknowns (Jacobi preconditioner), out[0] = r.z
-void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, double* z,
+void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, mg_t* z,
                            double* partials, unsigned int* counter, double* out, int n_sm,
                            cudaStream_t st);
 int vec_max_blocks(int n_sm);

@@ -1,16 +1,20 @@
-// Level-0 (voxel grid) matrix-free stencil kernels for sm_100a.
+// Level-0 (voxel grid) matrix-free stencil kernels for sm_100a: fallback variants.
 //
 // The operator is the reference's 7-point finite-volume matrix
 // (src/props/TortuosityHypreFill.F90:96-228) with the identity rows (inactive
 // cells, Dirichlet planes) eliminated; coefficients are rebuilt from one
 // connectivity byte per cell instead of 7 stored doubles.
 //
-// Main variant: 64x8 xy tile per CTA marching along z.  Every thread owns one
-// (x,y) column and keeps planes k-1,k,k+1 of its column in registers; the +-x,
-// +-y neighbours come from a double-buffered shared-memory copy of plane k
-// (one __syncthreads per plane).  Loads for plane k+2 are issued before plane k
-// is computed.  A warp covers 16(x) x 2(y) cells so that the 2x2x2 restriction
-// needs only two shuffles and one register carried across planes.
+// The default kernels live in oi_level0_ring.cu (shared-memory ring).  This file
+// holds the two independent cross-check / fallback variants, which make no
+// alignment assumptions and select every face by its connectivity bit:
+//   * z-march: 64x8 xy tile per CTA marching along z; every thread owns one (x,y)
+//     column and keeps planes k-1,k,k+1 of its column in registers, the +-x,+-y
+//     neighbours come from a double-buffered shared-memory copy of plane k.  Used
+//     when nx is not a multiple of 4 and for the fused-prolongation sweep.
+//   * gather: one thread per cell straight from global/L1/L2.
+// All kernels are templated on the element type: double for the Krylov operator
+// apply, mg_t for the multigrid sweeps.
 #include "oi_kernels.h"
 
 namespace oi {
@@ -20,34 +24,34 @@ namespace {
 constexpr int TX = 64, TY = 8;           // CTA tile (cells)
 constexpr int NTHREADS = TX * TY;        // 512
 
-__device__ __forceinline__ double diag_of(uint8_t f, const Grid& g) {
-    return g.cx * (double)__popc(f & 0x03u) + g.cy * (double)__popc(f & 0x0cu) +
-           g.cz * (double)__popc(f & 0x30u);
+template <typename T>
+__device__ __forceinline__ T diag_of(uint8_t f, const Grid& g) {
+    return (T)g.cx * (T)__popc(f & 0x03u) + (T)g.cy * (T)__popc(f & 0x0cu) + (T)g.cz * (T)__popc(f & 0x30u);
 }
 
 // A*u at one cell from centre + 6 neighbour values.  Written as a sum of
 // differences (row sum 0, checkMatrixProperties TortuosityHypre.cpp:969-971).
-__device__ __forceinline__ double stencil_au(uint8_t f, const Grid& g, double c, double xm,
-                                             double xp, double ym, double yp, double zm,
-                                             double zp) {
-    double ax = ((f & F_XM) ? (c - xm) : 0.0) + ((f & F_XP) ? (c - xp) : 0.0);
-    double ay = ((f & F_YM) ? (c - ym) : 0.0) + ((f & F_YP) ? (c - yp) : 0.0);
-    double az = ((f & F_ZM) ? (c - zm) : 0.0) + ((f & F_ZP) ? (c - zp) : 0.0);
-    return g.cx * ax + g.cy * ay + g.cz * az;
+template <typename T>
+__device__ __forceinline__ T stencil_au(uint8_t f, const Grid& g, T c, T xm, T xp, T ym, T yp, T zm, T zp) {
+    const T z0 = (T)0;
+    T ax = ((f & F_XM) ? (c - xm) : z0) + ((f & F_XP) ? (c - xp) : z0);
+    T ay = ((f & F_YM) ? (c - ym) : z0) + ((f & F_YP) ? (c - yp) : z0);
+    T az = ((f & F_ZM) ? (c - zm) : z0) + ((f & F_ZP) ? (c - zp) : z0);
+    return (T)g.cx * ax + (T)g.cy * ay + (T)g.cz * az;
 }
 
+template <typename T>
 struct CoarseRef {       // coarse correction added on the fly (prolongation)
-    const double* ec;    // coarse vector (ghost planes allowed), pointer at plane 0
+    const T* ec;         // coarse vector (ghost planes allowed), pointer at plane 0
     int cnx, cny;        // coarse dims
     int fx, fy, fz;      // coarsening factors (1 or 2)
     int z0;              // local plane 0 global index (for fz alignment)
 };
 
-template <bool ADDC>
-__device__ __forceinline__ double load_val(const double* __restrict__ u,
-                                           const uint8_t* __restrict__ flags, long long idx,
-                                           int i, int j, int k, const CoarseRef& cr) {
-    double v = u[idx];
+template <typename T, bool ADDC>
+__device__ __forceinline__ T load_val(const T* __restrict__ u, const uint8_t* __restrict__ flags,
+                                      long long idx, int i, int j, int k, const CoarseRef<T>& cr) {
+    T v = u[idx];
     if (ADDC) {
         if (flags[idx] & F_UNK) {
             int ci = (cr.fx == 2) ? (i >> 1) : i;
@@ -67,13 +71,12 @@ __device__ __forceinline__ double load_val(const double* __restrict__ u,
 //       2 = RESTRICT rc[I] = sum_children (b - A u)        (K6, fused residual)
 // ADDC: u is read as u + P*ec (fused prolongation/correction)
 // DOT : APPLY -> sum u*out ; SMOOTH -> sum b*out  (fused PCG dot, K4)
-template <int MODE, bool ADDC, bool DOT>
+template <typename T, int MODE, bool ADDC, bool DOT>
 __global__ void __launch_bounds__(NTHREADS)
-l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ u,
-                 const double* __restrict__ b, double* __restrict__ out, double w,
-                 CoarseRef cr, int zchunk, double* red_partials, unsigned int* red_counter,
-                 double* red_out) {
-    __shared__ double tile[2][TY + 2][TX + 2];
+l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ u,
+                 const T* __restrict__ b, T* __restrict__ out, T w, CoarseRef<T> cr, int zchunk,
+                 double* red_partials, unsigned int* red_counter, double* red_out) {
+    __shared__ T tile[2][TY + 2][TX + 2];
 
     // warp = 16(x) x 2(y) cells; 4 x 4 warps per CTA
     const int tid = threadIdx.x;
@@ -99,23 +102,23 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
     const long long colhy = (long long)hj_y * g.nx + i;
 
     // register pipeline over planes
-    double v_m = 0.0, v_c = 0.0, v_p = 0.0, v_n = 0.0;
-    double hx_c = 0.0, hy_c = 0.0, hx_n = 0.0, hy_n = 0.0;
+    T v_m = 0, v_c = 0, v_p = 0, v_n = 0;
+    T hx_c = 0, hy_c = 0, hx_n = 0, hy_n = 0;
     uint8_t f_c = 0, f_n = 0;
-    double b_c = 0.0, b_n = 0.0;
+    T b_c = 0, b_n = 0;
 
     if (inb) {
-        v_m = load_val<ADDC>(u, flags, (long long)(k0 - 1) * g.plane + col, i, j, k0 - 1, cr);
-        v_c = load_val<ADDC>(u, flags, (long long)k0 * g.plane + col, i, j, k0, cr);
-        v_p = load_val<ADDC>(u, flags, (long long)(k0 + 1) * g.plane + col, i, j, k0 + 1, cr);
+        v_m = load_val<T, ADDC>(u, flags, (long long)(k0 - 1) * g.plane + col, i, j, k0 - 1, cr);
+        v_c = load_val<T, ADDC>(u, flags, (long long)k0 * g.plane + col, i, j, k0, cr);
+        v_p = load_val<T, ADDC>(u, flags, (long long)(k0 + 1) * g.plane + col, i, j, k0 + 1, cr);
         f_c = flags[(long long)k0 * g.plane + col];
         if (MODE != 0) b_c = b[(long long)k0 * g.plane + col];
     }
-    if (hx_ok) hx_c = load_val<ADDC>(u, flags, (long long)k0 * g.plane + colhx, hi_x, j, k0, cr);
-    if (hy_ok) hy_c = load_val<ADDC>(u, flags, (long long)k0 * g.plane + colhy, i, hj_y, k0, cr);
+    if (hx_ok) hx_c = load_val<T, ADDC>(u, flags, (long long)k0 * g.plane + colhx, hi_x, j, k0, cr);
+    if (hy_ok) hy_c = load_val<T, ADDC>(u, flags, (long long)k0 * g.plane + colhy, i, hj_y, k0, cr);
 
     double dot_acc = 0.0;
-    double zpair = 0.0;  // RESTRICT: residual carried from the even plane
+    T zpair = 0;         // RESTRICT: residual carried from the even plane
     int buf = 0;
 
     for (int k = k0; k < k1; ++k) {
@@ -129,31 +132,31 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
         if (inb) {
             // plane k+2 <= nz is inside the ghost-padded allocation when k+1 < nz
             if (more) {
-                v_n = load_val<ADDC>(u, flags, (long long)(k + 2) * g.plane + col, i, j, k + 2, cr);
+                v_n = load_val<T, ADDC>(u, flags, (long long)(k + 2) * g.plane + col, i, j, k + 2, cr);
                 f_n = flags[(long long)(k + 1) * g.plane + col];
                 if (MODE != 0) b_n = b[(long long)(k + 1) * g.plane + col];
             }
         }
         if (more) {
-            if (hx_ok) hx_n = load_val<ADDC>(u, flags, (long long)(k + 1) * g.plane + colhx, hi_x, j, k + 1, cr);
-            if (hy_ok) hy_n = load_val<ADDC>(u, flags, (long long)(k + 1) * g.plane + colhy, i, hj_y, k + 1, cr);
+            if (hx_ok) hx_n = load_val<T, ADDC>(u, flags, (long long)(k + 1) * g.plane + colhx, hi_x, j, k + 1, cr);
+            if (hy_ok) hy_n = load_val<T, ADDC>(u, flags, (long long)(k + 1) * g.plane + colhy, i, hj_y, k + 1, cr);
         }
         __syncthreads();
 
         // 3. compute plane k
-        double res = 0.0;  // MODE 2 residual
+        T res = 0;  // MODE 2 residual
         if (inb) {
-            double o = 0.0;
+            T o = 0;
             if (f_c & F_UNK) {
-                const double xm = tile[buf][ty + 1][tx], xp = tile[buf][ty + 1][tx + 2];
-                const double ym = tile[buf][ty][tx + 1], yp = tile[buf][ty + 2][tx + 1];
-                const double au = stencil_au(f_c, g, v_c, xm, xp, ym, yp, v_m, v_p);
+                const T xm = tile[buf][ty + 1][tx], xp = tile[buf][ty + 1][tx + 2];
+                const T ym = tile[buf][ty][tx + 1], yp = tile[buf][ty + 2][tx + 1];
+                const T au = stencil_au<T>(f_c, g, v_c, xm, xp, ym, yp, v_m, v_p);
                 if (MODE == 0) {
                     o = w * au;
-                    if (DOT) dot_acc += v_c * o;
+                    if (DOT) dot_acc += (double)v_c * (double)o;
                 } else if (MODE == 1) {
-                    o = v_c + w * (b_c - au) / diag_of(f_c, g);
-                    if (DOT) dot_acc += b_c * o;
+                    o = v_c + w * (b_c - au) / diag_of<T>(f_c, g);
+                    if (DOT) dot_acc += (double)b_c * (double)o;
                 } else {
                     res = b_c - au;
                 }
@@ -162,17 +165,14 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
         }
         if (MODE == 2) {
             // 2x2x2 (or fx x fy x fz) sum: x pair = lanes l, l^1 ; y pair = l, l^16
-            double s = res;
+            T s = res;
             if (cr.fx == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
             if (cr.fy == 2) s += __shfl_xor_sync(0xffffffffu, s, 16);
             const int kg = g.z0 + k;  // global plane: pairs are aligned globally
-            bool flush;
+            bool flush = true;
             if (cr.fz == 2) {
                 if ((kg & 1) == 0) { zpair = s; flush = (k + 1 == k1); }
-                else { s += zpair; zpair = 0.0; flush = true; }
-                if ((kg & 1) == 0 && flush) s = zpair;
-            } else {
-                flush = true;
+                else { s += zpair; zpair = 0; }
             }
             const bool writer = inb && ((cr.fx == 1) || ((i & 1) == 0)) &&
                                 ((cr.fy == 1) || ((j & 1) == 0));
@@ -198,11 +198,11 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
 }
 
 // Simple gather variant (one thread per cell, neighbours straight from
-// global/L1/L2).  Kept as an independent cross-check of the staged kernel.
-template <int MODE, bool ADDC, bool DOT>
+// global/L1/L2).  Kept as an independent cross-check of the staged kernels.
+template <typename T, int MODE, bool ADDC, bool DOT>
 __global__ void __launch_bounds__(256)
-l0_gather_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ u,
-                 const double* __restrict__ b, double* __restrict__ out, double w, CoarseRef cr,
+l0_gather_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ u,
+                 const T* __restrict__ b, T* __restrict__ out, T w, CoarseRef<T> cr,
                  double* red_partials, unsigned int* red_counter, double* red_out) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
@@ -211,23 +211,24 @@ l0_gather_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
     if (i < g.nx && j < g.ny) {
         const long long idx = (long long)k * g.plane + (long long)j * g.nx + i;
         const uint8_t f = flags[idx];
-        double o = 0.0;
+        T o = 0;
         if (f & F_UNK) {
-            const double c = load_val<ADDC>(u, flags, idx, i, j, k, cr);
-            const double xm = (f & F_XM) ? load_val<ADDC>(u, flags, idx - 1, i - 1, j, k, cr) : 0.0;
-            const double xp = (f & F_XP) ? load_val<ADDC>(u, flags, idx + 1, i + 1, j, k, cr) : 0.0;
-            const double ym = (f & F_YM) ? load_val<ADDC>(u, flags, idx - g.nx, i, j - 1, k, cr) : 0.0;
-            const double yp = (f & F_YP) ? load_val<ADDC>(u, flags, idx + g.nx, i, j + 1, k, cr) : 0.0;
-            const double zm = (f & F_ZM) ? load_val<ADDC>(u, flags, idx - g.plane, i, j, k - 1, cr) : 0.0;
-            const double zp = (f & F_ZP) ? load_val<ADDC>(u, flags, idx + g.plane, i, j, k + 1, cr) : 0.0;
-            const double au = stencil_au(f, g, c, xm, xp, ym, yp, zm, zp);
+            const T z0 = 0;
+            const T c = load_val<T, ADDC>(u, flags, idx, i, j, k, cr);
+            const T xm = (f & F_XM) ? load_val<T, ADDC>(u, flags, idx - 1, i - 1, j, k, cr) : z0;
+            const T xp = (f & F_XP) ? load_val<T, ADDC>(u, flags, idx + 1, i + 1, j, k, cr) : z0;
+            const T ym = (f & F_YM) ? load_val<T, ADDC>(u, flags, idx - g.nx, i, j - 1, k, cr) : z0;
+            const T yp = (f & F_YP) ? load_val<T, ADDC>(u, flags, idx + g.nx, i, j + 1, k, cr) : z0;
+            const T zm = (f & F_ZM) ? load_val<T, ADDC>(u, flags, idx - g.plane, i, j, k - 1, cr) : z0;
+            const T zp = (f & F_ZP) ? load_val<T, ADDC>(u, flags, idx + g.plane, i, j, k + 1, cr) : z0;
+            const T au = stencil_au<T>(f, g, c, xm, xp, ym, yp, zm, zp);
             if (MODE == 0) {
                 o = w * au;
-                if (DOT) dot_acc = c * o;
+                if (DOT) dot_acc = (double)c * (double)o;
             } else if (MODE == 1) {
-                const double bb = b[idx];
-                o = c + w * (bb - au) / diag_of(f, g);
-                if (DOT) dot_acc = bb * o;
+                const T bb = b[idx];
+                o = c + w * (bb - au) / diag_of<T>(f, g);
+                if (DOT) dot_acc = (double)bb * (double)o;
             } else {
                 o = b[idx] - au;   // plain residual (restriction is a second kernel)
             }
@@ -241,44 +242,49 @@ l0_gather_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __rest
 }
 
 // First smoothing sweep from a zero guess: out = w * b / diag  (no stencil).
+template <typename T>
 __global__ void __launch_bounds__(256)
-l0_jacobi_first_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ b,
-                       double* __restrict__ out, double w, long long n) {
+l0_jacobi_first_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ b,
+                       T* __restrict__ out, T w, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
         const uint8_t f = flags[idx];
-        out[idx] = (f & F_UNK) ? w * b[idx] / diag_of(f, g) : 0.0;
+        out[idx] = (f & F_UNK) ? w * b[idx] / diag_of<T>(f, g) : (T)0;
     }
 }
 
 // ---------------------------------------------------------------- launchers
 int pick_zchunk(const Grid& g, int n_sm) {
+    // enough CTAs for ~8 waves (tail effect), chunks of 16..64 planes (each chunk
+    // re-reads 2 halo planes and refills its pipeline)
     const long long tiles = (long long)((g.nx + TX - 1) / TX) * ((g.ny + TY - 1) / TY);
-    const long long target = (long long)n_sm * 6;  // ~2 waves at 3 CTAs/SM
+    const long long target = (long long)n_sm * 32;
     long long chunks = (target + tiles - 1) / tiles;
     if (chunks < 1) chunks = 1;
     int zc = (int)((g.nz + chunks - 1) / chunks);
-    if (zc < 8) zc = 8;
-    if (zc > 128) zc = 128;
+    if (zc < 16) zc = 16;
+    if (zc > 64) zc = 64;
     zc = (zc + 1) & ~1;                            // even: restriction pairs stay in one chunk
     return zc;
 }
 
-template <int MODE, bool ADDC, bool DOT>
+template <typename T, int MODE, bool ADDC, bool DOT>
 static void launch_zmarch(const L0Args& a, cudaStream_t st) {
-    CoarseRef cr{a.ec, a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
+    CoarseRef<T> cr{static_cast<const T*>(a.ec), a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + TX - 1) / TX, (a.g.ny + TY - 1) / TY, (a.g.nz + zc - 1) / zc);
-    l0_zmarch_kernel<MODE, ADDC, DOT><<<grid, NTHREADS, 0, st>>>(
-        a.g, a.flags, a.u, a.b, a.out, a.w, cr, zc, a.red_partials, a.red_counter, a.red_out);
+    l0_zmarch_kernel<T, MODE, ADDC, DOT><<<grid, NTHREADS, 0, st>>>(
+        a.g, a.flags, static_cast<const T*>(a.u), static_cast<const T*>(a.b), static_cast<T*>(a.out), (T)a.w,
+        cr, zc, a.red_partials, a.red_counter, a.red_out);
 }
 
-template <int MODE, bool ADDC, bool DOT>
+template <typename T, int MODE, bool ADDC, bool DOT>
 static void launch_gather(const L0Args& a, cudaStream_t st) {
-    CoarseRef cr{a.ec, a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
+    CoarseRef<T> cr{static_cast<const T*>(a.ec), a.cnx, a.cny, a.fx, a.fy, a.fz, a.g.z0};
     dim3 grid((a.g.nx + 63) / 64, (a.g.ny + 3) / 4, a.g.nz);
-    l0_gather_kernel<MODE, ADDC, DOT><<<grid, 256, 0, st>>>(
-        a.g, a.flags, a.u, a.b, a.out, a.w, cr, a.red_partials, a.red_counter, a.red_out);
+    l0_gather_kernel<T, MODE, ADDC, DOT><<<grid, 256, 0, st>>>(
+        a.g, a.flags, static_cast<const T*>(a.u), static_cast<const T*>(a.b), static_cast<T*>(a.out), (T)a.w,
+        cr, a.red_partials, a.red_counter, a.red_out);
 }
 
 long long l0_max_blocks(const Grid& g, int n_sm) {
@@ -289,44 +295,45 @@ long long l0_max_blocks(const Grid& g, int n_sm) {
 }
 
 // variant: 0 = shared-memory ring (cp.async), 2 = register z-march, 1 = gather
-void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {
+void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {           // fp64 fields
     if (variant == 0 && ring_supported(a, 0)) {
         ring_launch(a, 0, dot, st);
     } else if (variant == 0 || variant == 2) {
-        if (dot) launch_zmarch<0, false, true>(a, st); else launch_zmarch<0, false, false>(a, st);
+        if (dot) launch_zmarch<double, 0, false, true>(a, st); else launch_zmarch<double, 0, false, false>(a, st);
     } else {
-        if (dot) launch_gather<0, false, true>(a, st); else launch_gather<0, false, false>(a, st);
+        if (dot) launch_gather<double, 0, false, true>(a, st); else launch_gather<double, 0, false, false>(a, st);
     }
 }
 
-void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st) {
+void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st) {   // mg_t fields
     if (variant == 0 && !addc && ring_supported(a, 1)) {
         ring_launch(a, 1, dot, st);
     } else if (variant == 0 || variant == 2) {
-        if (addc) { if (dot) launch_zmarch<1, true, true>(a, st); else launch_zmarch<1, true, false>(a, st); }
-        else      { if (dot) launch_zmarch<1, false, true>(a, st); else launch_zmarch<1, false, false>(a, st); }
+        if (addc) { if (dot) launch_zmarch<mg_t, 1, true, true>(a, st); else launch_zmarch<mg_t, 1, true, false>(a, st); }
+        else      { if (dot) launch_zmarch<mg_t, 1, false, true>(a, st); else launch_zmarch<mg_t, 1, false, false>(a, st); }
     } else {
-        if (addc) { if (dot) launch_gather<1, true, true>(a, st); else launch_gather<1, true, false>(a, st); }
-        else      { if (dot) launch_gather<1, false, true>(a, st); else launch_gather<1, false, false>(a, st); }
+        if (addc) { if (dot) launch_gather<mg_t, 1, true, true>(a, st); else launch_gather<mg_t, 1, true, false>(a, st); }
+        else      { if (dot) launch_gather<mg_t, 1, false, true>(a, st); else launch_gather<mg_t, 1, false, false>(a, st); }
     }
 }
 
-void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st) {   // out = coarse rhs
+void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st) {   // out = coarse rhs (mg_t)
     if (variant == 0 && ring_supported(a, 2)) ring_launch(a, 2, false, st);
-    else launch_zmarch<2, false, false>(a, st);
+    else launch_zmarch<mg_t, 2, false, false>(a, st);
 }
 
-void l0_residual(const L0Args& a, cudaStream_t st) {            // out = fine residual
-    launch_gather<2, false, false>(a, st);
+void l0_residual(const L0Args& a, cudaStream_t st) {            // out = fine residual (mg_t)
+    launch_gather<mg_t, 2, false, false>(a, st);
 }
 
-void l0_jacobi_first(const L0Args& a, cudaStream_t st) {
+void l0_jacobi_first(const L0Args& a, cudaStream_t st) {        // mg_t fields
     const long long n = (long long)a.g.nz * a.g.plane;
     int blocks = a.n_sm * 8;
     long long need = (n + 255) / 256;
     if (need < blocks) blocks = (int)need;
     if (blocks < 1) blocks = 1;
-    l0_jacobi_first_kernel<<<blocks, 256, 0, st>>>(a.g, a.flags, a.b, a.out, a.w, n);
+    l0_jacobi_first_kernel<mg_t><<<blocks, 256, 0, st>>>(a.g, a.flags, static_cast<const mg_t*>(a.b),
+                                                         static_cast<mg_t*>(a.out), (mg_t)a.w, n);
 }
 
 }  // namespace oi

@@ -1,15 +1,20 @@
-// Level-0 stencil, shared-memory ring variant (default on even nx).
+// Level-0 stencil, shared-memory ring variant (default when nx % 4 == 0).
 //
 // ncu on the register z-march kernel showed it issue-bound, not DRAM-bound
 // (sm__inst_issued 69 %, dram 47 %, ~160 thread-instructions per cell): selects on
 // six face bits, 64-bit index products, an fp64 divide and int->double converts
 // per cell, and a CTA barrier per plane.  This kernel puts the instruction
-// stream on a diet and lets the copy engine side of the LSU do the staging:
+// stream on a diet and lets the copy side of the LSU do the staging:
 //
-//   * every thread owns TWO x-adjacent cells: 16-byte cp.async / LDS.128 / STG.128;
-//   * plane k+RING_P+1 of the input (and of the rhs) is already in flight into a
-//     RING_R-stage shared-memory ring while plane k is computed (cp.async groups,
-//     one per plane), so a CTA keeps ~5 planes x 9.5 KB of loads outstanding;
+//   * every thread owns 16 bytes of x-adjacent cells (2 fp64 or 4 fp32 cells):
+//     16-byte cp.async / LDS.128 / STG.128;
+//   * plane k+RING_P+1 of the input, of the rhs and of the connectivity bytes is
+//     already in flight into a RING_R-stage shared-memory ring while plane k is
+//     computed (cp.async groups, one per plane), so a CTA keeps ~5 planes of loads
+//     outstanding without spending registers (a register queue for the
+//     connectivity bytes was the top stall of the previous version);
+//   * the plane loop is unrolled by the ring length, so stage numbers and the
+//     register window over the column are compile-time constants;
 //   * no face selects: every vector A is applied to is zero on inactive cells
 //     (x0, p, z are built that way and the updates preserve it; out-of-box halo
 //     cells are zero-filled by cp.async), so
@@ -17,35 +22,45 @@
 //     with d_c and 1/d_c looked up by the 6 face bits in a 64-entry table;
 //   * the z neighbours travel in registers (one centre LDS per plane, not three).
 //
-// Algorithmic traffic is unchanged: 17 B/cell (APPLY), 25 (SMOOTH), 17.1 (RESTRICT).
+// Element type: double for the Krylov operator apply, mg_t for multigrid sweeps.
+// Algorithmic traffic per cell: APPLY 17 B (fp64); SMOOTH 2*4+1+4 = 13 B and
+// RESTRICT 9.5 B with mg_t = float (25 / 17.1 B with an fp64 V-cycle).
 #include "oi_kernels.h"
 
 namespace oi {
 
 namespace {
 
-constexpr int TX = 64, TY = 8;             // CTA tile in cells
-constexpr int NT = (TX / 2) * TY;          // 256 threads, two cells each
 constexpr int RING_P = 4;                  // planes in flight beyond k+1
 constexpr int RING_R = RING_P + 2;         // stages: planes k-1 .. k+RING_P
-constexpr int PITCH = TX + 4;              // [pad, west halo, 64 centres, east halo, pad]
-constexpr int U_STAGE = (TY + 2) * PITCH;  // doubles per u stage (rows: south halo, 8, north halo)
-constexpr int B_STAGE = TY * TX;           // doubles per rhs stage
+
+template <typename T>
+struct Cfg {
+    static constexpr int CPT = 16 / (int)sizeof(T);   // cells per thread (2 fp64 / 4 fp32)
+    static constexpr int TX = 64;                     // CTA tile width in cells
+    static constexpr int XT = TX / CPT;               // threads along x (32 / 16)
+    static constexpr int NT = 256;
+    static constexpr int TY = NT / XT;                // CTA tile height (8 / 16 rows)
+    static constexpr int PITCH = TX + 2 * CPT;        // [pad.., west halo | 64 centres | east halo, pad..]
+    static constexpr int U_STAGE = (TY + 2) * PITCH;  // elements per field stage (south halo, rows, north halo)
+    static constexpr int B_STAGE = TY * TX;           // elements per rhs stage
+    static constexpr int F_STAGE = TY * TX;           // bytes per connectivity stage
+    static constexpr int FCOPY = 4 / CPT;             // threads sharing one 4-byte flag copy (2 / 1)
+};
+
+template <typename T>
+struct alignas(16) Pack { T v[16 / sizeof(T)]; };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 16 : 0;          // src-size 0 -> destination zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+    const int sz = valid ? BYTES : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(sa), "l"(gsrc), "n"(BYTES), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -55,71 +70,76 @@ struct RingCoarse { int cnx, cny, z0h; };   // RESTRICT target dims, (z0 >> 1)
 
 // MODE 0 APPLY: out = w * A u (+ dot u.out) ; 1 SMOOTH: out = u + w (b - A u)/d (+ dot b.out)
 // MODE 2 RESTRICT (2x2x2 or 2x2x1): out[coarse] = sum_children (b - A u)
-template <int MODE, bool DOT>
-__global__ void __launch_bounds__(NT)
-l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ u,
-               const double* __restrict__ b, double* __restrict__ out, double w, RingCoarse rc,
-               int fz, int zchunk, double* red_partials, unsigned int* red_counter, double* red_out) {
-    extern __shared__ __align__(16) double smem[];
-    double* us = smem;                                          // [RING_R][U_STAGE]
-    double* bs = us + RING_R * U_STAGE;                         // [RING_R][B_STAGE]   (MODE != 0)
-    double* dtab = bs + (MODE != 0 ? RING_R * B_STAGE : 0);     // [64] diagonal, [64] its inverse
-    unsigned char* fs = reinterpret_cast<unsigned char*>(dtab + 128);   // [RING_R][TY][TX] connectivity bytes
+template <typename T, int MODE, bool DOT>
+__global__ void __launch_bounds__(256)
+l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ u,
+               const T* __restrict__ b, T* __restrict__ out, T w, RingCoarse rc, int fz, int zchunk,
+               double* red_partials, unsigned int* red_counter, double* red_out) {
+    typedef Cfg<T> C;
+    constexpr int CPT = C::CPT, TX = C::TX, TY = C::TY, PITCH = C::PITCH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* us = reinterpret_cast<T*>(smem_raw);                     // [RING_R][U_STAGE]
+    T* bs = us + RING_R * C::U_STAGE;                           // [RING_R][B_STAGE]   (MODE != 0)
+    T* dtab = bs + (MODE != 0 ? RING_R * C::B_STAGE : 0);       // [64] diagonal, [64] its inverse
+    unsigned char* fs = reinterpret_cast<unsigned char*>(dtab + 128);   // [RING_R][F_STAGE]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int tx2 = (warp & 1) * 16 + (lane & 15);              // x pair index inside the tile
-    const int ty = (warp >> 1) * 2 + (lane >> 4);
-    const int i = blockIdx.x * TX + 2 * tx2;                    // first of the two cells (even)
+    constexpr int WX = C::XT / 16;                              // warps side by side in x (2 / 1)
+    const int tx = (warp % WX) * 16 + (lane & 15);              // index of this thread's cell group
+    const int ty = (warp / WX) * 2 + (lane >> 4);
+    const int i = blockIdx.x * TX + CPT * tx;                   // first of the CPT cells (multiple of CPT)
     const int j = blockIdx.y * TY + ty;
-    const bool inb = (i < g.nx) && (j < g.ny);                  // nx even: both cells in or out
+    const bool inb = (i < g.nx) && (j < g.ny);                  // nx % 4 == 0: all CPT cells in or out
     const int k0 = blockIdx.z * zchunk;
     const int k1 = min(k0 + zchunk, g.nz);
+    const T cx = (T)g.cx, cy = (T)g.cy, cz = (T)g.cz;
 
     if (tid < 64) {
-        const double d = g.cx * (double)__popc(tid & 0x03) + g.cy * (double)__popc(tid & 0x0c) +
-                         g.cz * (double)__popc(tid & 0x30);
+        const T d = cx * (T)__popc(tid & 0x03) + cy * (T)__popc(tid & 0x0c) + cz * (T)__popc(tid & 0x30);
         dtab[tid] = d;
-        dtab[64 + tid] = d > 0.0 ? 1.0 / d : 0.0;
+        dtab[64 + tid] = d > (T)0 ? (T)1 / d : (T)0;
     }
 
     // halo duties
-    const bool hw = (tx2 == 0), he = (tx2 == TX / 2 - 1);
+    const bool hw = (tx == 0), he = (tx == C::XT - 1);
     const bool hs = (ty == 0), hn = (ty == TY - 1);
-    const int iw = i - 1, ie = i + 2, js = j - 1, jn = j + 1;
+    const int iw = i - 1, ie = i + CPT, js = j - 1, jn = j + 1;
     const bool hw_ok = hw && (j < g.ny) && iw >= 0;
     const bool he_ok = he && (j < g.ny) && ie < g.nx;
     const bool hs_ok = hs && (i < g.nx) && js >= 0;
     const bool hn_ok = hn && (i < g.nx) && jn < g.ny;
 
     const long long col = inb ? (long long)j * g.nx + i : 0;
-    const double* u_own = u + col;
-    const double* u_w = u + (hw_ok ? (long long)j * g.nx + iw : 0);
-    const double* u_e = u + (he_ok ? (long long)j * g.nx + ie : 0);
-    const double* u_s = u + (hs_ok ? (long long)js * g.nx + i : 0);
-    const double* u_n = u + (hn_ok ? (long long)jn * g.nx + i : 0);
-    const double* b_own = (MODE != 0) ? b + col : nullptr;
+    const T* u_own = u + col;
+    const T* u_w = u + (hw_ok ? (long long)j * g.nx + iw : 0);
+    const T* u_e = u + (he_ok ? (long long)j * g.nx + ie : 0);
+    const T* u_s = u + (hs_ok ? (long long)js * g.nx + i : 0);
+    const T* u_n = u + (hn_ok ? (long long)jn * g.nx + i : 0);
+    const T* b_own = (MODE != 0) ? b + col : nullptr;
+    const uint8_t* f_own = flags + col;
 
-    const int c_off = (ty + 1) * PITCH + 2 + 2 * tx2;           // own centre pair inside a u stage
-    const int b_off = ty * TX + 2 * tx2;
-    const int f_off = ty * TX + 2 * tx2;                        // byte offset inside a flag stage
+    const int c_off = (ty + 1) * PITCH + CPT + CPT * tx;        // own centre group inside a field stage
+    const int b_off = ty * TX + CPT * tx;                       // inside a rhs stage / flag stage
+    const bool f_copy = (tx % C::FCOPY) == 0;                   // this thread copies 4 connectivity bytes
 
-    // issue all copies of plane kk into stage st (offset kk*plane is carried by the caller)
-    auto issue = [&](long long poff, int st, bool with_b) {
-        double* S = us + st * U_STAGE;
+    // issue all copies of plane kk into stage st (poff = kk * plane, carried by the caller);
+    // rhs and connectivity bytes only exist for planes k0 .. k1-1
+    auto issue = [&](long long poff, int st, bool interior) {
+        T* S = us + st * C::U_STAGE;
         cp_async16(S + c_off, u_own + poff, inb);
-        if (hw) cp_async8(S + (ty + 1) * PITCH + 1, u_w + poff, hw_ok);
-        if (he) cp_async8(S + (ty + 1) * PITCH + 2 + TX, u_e + poff, he_ok);
-        if (hs) cp_async16(S + 2 + 2 * tx2, u_s + poff, hs_ok);
-        if (hn) cp_async16(S + (TY + 1) * PITCH + 2 + 2 * tx2, u_n + poff, hn_ok);
-        if (MODE != 0) {
-            if (with_b) cp_async16(bs + st * B_STAGE + b_off, b_own + poff, inb);
+        if (hw) cp_async_small<(int)sizeof(T)>(S + (ty + 1) * PITCH + CPT - 1, u_w + poff, hw_ok);
+        if (he) cp_async_small<(int)sizeof(T)>(S + (ty + 1) * PITCH + CPT + TX, u_e + poff, he_ok);
+        if (hs) cp_async16(S + CPT + CPT * tx, u_s + poff, hs_ok);
+        if (hn) cp_async16(S + (TY + 1) * PITCH + CPT + CPT * tx, u_n + poff, hn_ok);
+        if (interior) {
+            if (MODE != 0) cp_async16(bs + st * C::B_STAGE + b_off, b_own + poff, inb);
+            if (f_copy) cp_async_small<4>(fs + st * C::F_STAGE + b_off, f_own + poff, inb);
         }
-        // connectivity bytes of 4 cells (this thread's pair and its odd neighbour's)
-        if (with_b && (tx2 & 1) == 0) cp_async4(fs + st * (TX * TY) + f_off, flags + col + poff, inb);
     };
 
-    // prologue: planes k0-1 .. k0+RING_P, one commit group per plane
+    // prologue: planes k0-1 .. k0+RING_P, one commit group per plane (empty groups
+    // keep the count uniform at the end of the chunk)
     long long poff_issue = (long long)(k0 - 1) * g.plane;
     int kk_issue = k0 - 1;
 #pragma unroll
@@ -129,74 +149,86 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
         poff_issue += g.plane;
         ++kk_issue;
     }
+
     cp_async_wait<RING_P>();                                    // planes k0-1 and k0 have landed
     __syncthreads();
     // register window over the column: vv[s % 3] = plane k-1, vv[(s+1) % 3] = plane k
-    double2 vv[3];
-    vv[0] = *reinterpret_cast<const double2*>(us + 0 * U_STAGE + c_off);
-    vv[1] = *reinterpret_cast<const double2*>(us + 1 * U_STAGE + c_off);
+    Pack<T> vv[3];
+    vv[0] = *reinterpret_cast<const Pack<T>*>(us + 0 * C::U_STAGE + c_off);
+    vv[1] = *reinterpret_cast<const Pack<T>*>(us + 1 * C::U_STAGE + c_off);
 
-    double dot_acc = 0.0, zpair = 0.0;
-    double* out_own = out + col + (long long)k0 * g.plane;      // MODE 0/1
+    double dot_acc = 0.0;
+    T zpair[CPT / 2];
+#pragma unroll
+    for (int q = 0; q < CPT / 2; ++q) zpair[q] = (T)0;
+    T* out_own = out + col + (long long)k0 * g.plane;           // MODE 0/1
 
-    // The plane loop is unrolled by the ring length, so that stage numbers, the
-    // register window and the flag queue slot are compile-time constants: plane
-    // kb+s always lives in stage (s+1) % RING_R.
+    // The plane loop is unrolled by the ring length: plane kb+s always lives in
+    // stage (s+1) % RING_R.
     for (int kb = k0; kb < k1; kb += RING_R) {
 #pragma unroll
         for (int s = 0; s < RING_R; ++s) {
             const int k = kb + s;
             if (k >= k1) break;                                 // CTA-uniform
-            constexpr int R = RING_R;
-            const int sc = (s + 1) % R, sp = (s + 2) % R;       // stages of planes k, k+1
+            const int sc = (s + 1) % RING_R, sp = (s + 2) % RING_R;   // stages of planes k, k+1
             cp_async_wait<RING_P - 1>();                        // own copies of planes <= k+1 landed
             __syncthreads();                                    // ... and everybody else's
 
-            const double* Sc = us + sc * U_STAGE;
-            const double2 v_m = vv[s % 3], v_c = vv[(s + 1) % 3];
-            const double2 v_p = *reinterpret_cast<const double2*>(us + sp * U_STAGE + c_off);
+            const T* Sc = us + sc * C::U_STAGE;
+            const Pack<T> v_m = vv[s % 3], v_c = vv[(s + 1) % 3];
+            const Pack<T> v_p = *reinterpret_cast<const Pack<T>*>(us + sp * C::U_STAGE + c_off);
             vv[(s + 2) % 3] = v_p;
-            const double xw = Sc[c_off - 1], xe = Sc[c_off + 2];
-            const double2 ys = *reinterpret_cast<const double2*>(Sc + c_off - PITCH);
-            const double2 yn = *reinterpret_cast<const double2*>(Sc + c_off + PITCH);
-            double2 bb = make_double2(0.0, 0.0);
-            if (MODE != 0) bb = *reinterpret_cast<const double2*>(bs + sc * B_STAGE + b_off);
+            const T xw = Sc[c_off - 1], xe = Sc[c_off + CPT];
+            const Pack<T> ys = *reinterpret_cast<const Pack<T>*>(Sc + c_off - PITCH);
+            const Pack<T> yn = *reinterpret_cast<const Pack<T>*>(Sc + c_off + PITCH);
+            Pack<T> bb;
+            if (MODE != 0) bb = *reinterpret_cast<const Pack<T>*>(bs + sc * C::B_STAGE + b_off);
 
-            const unsigned int f2 = *reinterpret_cast<const unsigned short*>(fs + sc * (TX * TY) + f_off);
+            unsigned int fword;
+            if (CPT == 2) fword = *reinterpret_cast<const unsigned short*>(fs + sc * C::F_STAGE + b_off);
+            else          fword = *reinterpret_cast<const unsigned int*>(fs + sc * C::F_STAGE + b_off);
 
-            const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
-            // (A u) for the two cells
-            const double au0 = dtab[f0 & 63u] * v_c.x - (g.cx * (xw + v_c.y) + g.cy * (ys.x + yn.x) + g.cz * (v_m.x + v_p.x));
-            const double au1 = dtab[f1 & 63u] * v_c.y - (g.cx * (v_c.x + xe) + g.cy * (ys.y + yn.y) + g.cz * (v_m.y + v_p.y));
-            double2 o = make_double2(0.0, 0.0);
-            double res = 0.0;
-            if (MODE == 0) {
-                if (f0 & F_UNK) o.x = w * au0;
-                if (f1 & F_UNK) o.y = w * au1;
-                if (DOT) dot_acc += v_c.x * o.x + v_c.y * o.y;
-            } else if (MODE == 1) {
-                if (f0 & F_UNK) o.x = v_c.x + w * (bb.x - au0) * dtab[64 + (f0 & 63u)];
-                if (f1 & F_UNK) o.y = v_c.y + w * (bb.y - au1) * dtab[64 + (f1 & 63u)];
-                if (DOT) dot_acc += bb.x * o.x + bb.y * o.y;
-            } else {
-                if (f0 & F_UNK) res = bb.x - au0;
-                if (f1 & F_UNK) res += bb.y - au1;
+            Pack<T> o;
+            T res[CPT / 2];
+#pragma unroll
+            for (int q = 0; q < CPT / 2; ++q) res[q] = (T)0;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const unsigned int f = (fword >> (8 * c)) & 0xffu;
+                const T west = (c == 0) ? xw : v_c.v[c > 0 ? c - 1 : 0];
+                const T east = (c == CPT - 1) ? xe : v_c.v[c < CPT - 1 ? c + 1 : CPT - 1];
+                const T au = dtab[f & 63u] * v_c.v[c] -
+                             (cx * (west + east) + cy * (ys.v[c] + yn.v[c]) + cz * (v_m.v[c] + v_p.v[c]));
+                const bool unk = (f & F_UNK) != 0;
+                if (MODE == 0) {
+                    o.v[c] = unk ? w * au : (T)0;
+                    if (DOT) dot_acc += (double)v_c.v[c] * (double)o.v[c];
+                } else if (MODE == 1) {
+                    o.v[c] = unk ? v_c.v[c] + w * (bb.v[c] - au) * dtab[64 + (f & 63u)] : (T)0;
+                    if (DOT) dot_acc += (double)bb.v[c] * (double)o.v[c];
+                } else {
+                    if (unk) res[c >> 1] += bb.v[c] - au;       // x pair summed in-thread
+                }
             }
             if (MODE != 2) {
-                if (inb) *reinterpret_cast<double2*>(out_own) = o;
+                if (inb) *reinterpret_cast<Pack<T>*>(out_own) = o;
                 out_own += g.plane;
             } else {
-                // x pair already summed in-thread; y pair = lane ^ 16; z pair carried
-                double sum = res + __shfl_xor_sync(0xffffffffu, res, 16);
+                // y pair = lane ^ 16; z pair carried across two planes
                 const int kg = g.z0 + k;
-                bool flush = true;
-                if (fz == 2) {
-                    if ((kg & 1) == 0) { zpair = sum; flush = (k + 1 == k1); }
-                    else { sum += zpair; zpair = 0.0; }
-                }
-                if (flush && inb && ((j & 1) == 0)) {
-                    const int ck = (fz == 2) ? ((kg >> 1) - rc.z0h) : k;
-                    out[((long long)ck * rc.cny + (j >> 1)) * rc.cnx + (i >> 1)] = sum;
+                const bool even = (fz == 2) && ((kg & 1) == 0);
+                const bool flush = !even || (k + 1 == k1);
+#pragma unroll
+                for (int q = 0; q < CPT / 2; ++q) {
+                    T sum = res[q] + __shfl_xor_sync(0xffffffffu, res[q], 16);
+                    if (fz == 2) {
+                        if (even) zpair[q] = sum;
+                        else { sum += zpair[q]; zpair[q] = (T)0; }
+                    }
+                    if (flush && inb && ((j & 1) == 0)) {
+                        const int ck = (fz == 2) ? ((kg >> 1) - rc.z0h) : k;
+                        out[((long long)ck * rc.cny + (j >> 1)) * rc.cnx + (i >> 1) + q] = sum;
+                    }
                 }
             }
 
@@ -217,9 +249,10 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restri
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-prolong_add_kernel(Grid g, const uint8_t* __restrict__ flags, double* __restrict__ z,
-                   const double* __restrict__ ec, int cnx, int cny, int fx, int fy, int fz) {
+prolong_add_kernel(Grid g, const uint8_t* __restrict__ flags, T* __restrict__ z,
+                   const T* __restrict__ ec, int cnx, int cny, int fx, int fy, int fz) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (i >= g.nx || j >= g.ny) return;
@@ -236,48 +269,52 @@ prolong_add_kernel(Grid g, const uint8_t* __restrict__ flags, double* __restrict
     }
 }
 
-template <int MODE>
+template <typename T, int MODE>
 size_t ring_smem_bytes() {
-    return sizeof(double) * (size_t)(RING_R * U_STAGE + (MODE != 0 ? RING_R * B_STAGE : 0) + 128) +
-           (size_t)RING_R * TX * TY;
+    typedef Cfg<T> C;
+    return sizeof(T) * (size_t)(RING_R * C::U_STAGE + (MODE != 0 ? RING_R * C::B_STAGE : 0) + 128) +
+           (size_t)RING_R * C::F_STAGE;
 }
 
-template <int MODE, bool DOT>
+template <typename T, int MODE, bool DOT>
 void launch(const L0Args& a, cudaStream_t st) {
+    typedef Cfg<T> C;
     static bool configured = false;
-    const size_t smem = ring_smem_bytes<MODE>();
+    const size_t smem = ring_smem_bytes<T, MODE>();
     if (!configured) {
-        cudaFuncSetAttribute(l0_ring_kernel<MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_ring_kernel<T, MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     const int zc = pick_zchunk(a.g, a.n_sm);
-    dim3 grid((a.g.nx + TX - 1) / TX, (a.g.ny + TY - 1) / TY, (a.g.nz + zc - 1) / zc);
+    dim3 grid((a.g.nx + C::TX - 1) / C::TX, (a.g.ny + C::TY - 1) / C::TY, (a.g.nz + zc - 1) / zc);
     RingCoarse rc{a.cnx, a.cny, a.g.z0 >> 1};
-    l0_ring_kernel<MODE, DOT><<<grid, NT, smem, st>>>(a.g, a.flags, a.u, a.b, a.out, a.w, rc, a.fz, zc,
-                                                       a.red_partials, a.red_counter, a.red_out);
+    l0_ring_kernel<T, MODE, DOT><<<grid, C::NT, smem, st>>>(
+        a.g, a.flags, static_cast<const T*>(a.u), static_cast<const T*>(a.b), static_cast<T*>(a.out), (T)a.w, rc,
+        a.fz, zc, a.red_partials, a.red_counter, a.red_out);
 }
 
 }  // namespace
 
 bool ring_supported(const L0Args& a, int mode) {
-    // 16-byte vector accesses need even nx (then every row and plane start is
-    // 16-byte aligned: plane 0 of every Field is 256-byte aligned)
-    // ... and the 4-byte copies of the connectivity bytes need nx % 4 == 0
+    // 16-byte vector accesses and the 4-byte copies of the connectivity bytes need
+    // nx % 4 == 0 (then every row and plane start is suitably aligned: plane 0 of
+    // every Field is 256-byte aligned)
     if (a.g.nx & 3) return false;
     if (mode == 2 && !(a.fx == 2 && a.fy == 2)) return false;
     return true;
 }
 
 void ring_launch(const L0Args& a, int mode, bool dot, cudaStream_t st) {
-    if (mode == 0) { if (dot) launch<0, true>(a, st); else launch<0, false>(a, st); }
-    else if (mode == 1) { if (dot) launch<1, true>(a, st); else launch<1, false>(a, st); }
-    else launch<2, false>(a, st);
+    if (mode == 0) { if (dot) launch<double, 0, true>(a, st); else launch<double, 0, false>(a, st); }
+    else if (mode == 1) { if (dot) launch<mg_t, 1, true>(a, st); else launch<mg_t, 1, false>(a, st); }
+    else launch<mg_t, 2, false>(a, st);
 }
 
 void l0_prolong_add(const L0Args& a, cudaStream_t st) {
     int gz = a.g.nz < 64 ? a.g.nz : 64;
     dim3 grid((a.g.nx + 63) / 64, (a.g.ny + 3) / 4, gz);
-    prolong_add_kernel<<<grid, 256, 0, st>>>(a.g, a.flags, a.out, a.ec, a.cnx, a.cny, a.fx, a.fy, a.fz);
+    prolong_add_kernel<mg_t><<<grid, 256, 0, st>>>(a.g, a.flags, static_cast<mg_t*>(a.out),
+                                                   static_cast<const mg_t*>(a.ec), a.cnx, a.cny, a.fx, a.fy, a.fz);
 }
 
 }  // namespace oi

@@ -119,7 +119,7 @@ struct Field {
 struct HostLevel {
     oi::CoarseLevel L{};
     Field<float> cxp, cyp, czp, dg;
-    Field<double> x, b, t;
+    Field<oi::mg_t> x, b, t;
 };
 
 }  // namespace
@@ -148,8 +148,11 @@ struct oi_solver {
     bool mask_built = false, hierarchy_built = false, solved = false;
     bool levels_allocated = false, vectors_allocated = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    // Krylov vectors
-    Field<double> x, r, p, q, z;
+    // Krylov vectors (fp64) and the level-0 multigrid vectors (mg_t): residual copy
+    // and two ping-pong iterates; zres points at the one holding z = M^-1 r
+    Field<double> x, r, p, q;
+    Field<oi::mg_t> r32, za, zb;
+    oi::mg_t* zres = nullptr;
     // scalars / reductions
     double* d_scal = nullptr;          // [16]
     double* d_partials = nullptr;
@@ -209,11 +212,14 @@ void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long lo
     NCCL_CHECK(N.GroupEnd());
 }
 
-inline void halo0(oi_solver* S, double* v) {
-    halo_exchange_bytes(S, v, (size_t)S->g.plane * sizeof(double), S->g.nz);
+using oi::mg_t;
+
+template <typename T>
+inline void halo0(oi_solver* S, T* v) {
+    halo_exchange_bytes(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz);
 }
-inline void haloL(oi_solver* S, const CoarseLevel& L, double* v) {
-    halo_exchange_bytes(S, v, (size_t)L.plane * sizeof(double), L.nz);
+inline void haloL(oi_solver* S, const CoarseLevel& L, mg_t* v) {
+    halo_exchange_bytes(S, v, (size_t)L.plane * sizeof(mg_t), L.nz);
 }
 
 void allreduce_sum_f64(oi_solver* S, double* d, int n) {
@@ -230,7 +236,7 @@ void allreduce_max_i32(oi_solver* S, int* d, int n) {
 }
 
 // ------------------------------------------------------------------ launch helpers
-L0Args l0args(oi_solver* S, const double* u, const double* b, double* out, double w, double* red_out) {
+L0Args l0args(oi_solver* S, const void* u, const void* b, void* out, double w, double* red_out) {
     L0Args a{};
     a.g = S->g;
     a.flags = S->flags.p;
@@ -262,7 +268,9 @@ void free_levels(oi_solver* S) {
 }
 
 void free_vectors(oi_solver* S) {
-    S->x.release(); S->r.release(); S->p.release(); S->q.release(); S->z.release();
+    S->x.release(); S->r.release(); S->p.release(); S->q.release();
+    S->r32.release(); S->za.release(); S->zb.release();
+    S->zres = nullptr;
 }
 
 // ------------------------------------------------------------------ hierarchy
@@ -332,12 +340,12 @@ void coarse_cycle(oi_solver* S, size_t l) {
     const bool last = (l + 1 == S->levels.size());
     const std::vector<double>& w = last ? S->w_coarse : S->w_smooth;
     const int deg = (int)w.size();
-    double* cur = L.t;
-    double* oth = L.x;
+    mg_t* cur = L.t;
+    mg_t* oth = L.x;
     oi::coarse_jacobi_first(L, L.b, cur, w[0], S->st); S->launches++;
     for (int s = 1; s < deg; ++s) {
         haloL(S, L, cur);
-        oi::coarse_smooth(L, cur, L.b, oth, w[s], nullptr, nullptr, S->st); S->launches++;
+        oi::coarse_smooth(L, cur, L.b, oth, w[s], S->st); S->launches++;
         std::swap(cur, oth);
     }
     if (!last) {
@@ -349,7 +357,7 @@ void coarse_cycle(oi_solver* S, size_t l) {
         oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
         for (int s = 0; s < deg; ++s) {
             haloL(S, L, cur);
-            oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], nullptr, nullptr, S->st);
+            oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], S->st);
             S->launches++;
             std::swap(cur, oth);
         }
@@ -362,31 +370,36 @@ double first_smoothing_weight(const oi_solver* S) {
     return S->levels.empty() ? S->w_coarse[0] : S->w_smooth[0];
 }
 
-// first_done: the first sweep from a zero guess (z1 = w0 r / diag) is already in q
-// (written by the fused axpy2_dot_first kernel of the Krylov update)
+// z = M^-1 r in multigrid precision; the result is S->zres.  Input: S->r32 (the
+// residual in mg_t) -- and, when first_done, the first sweep from a zero guess
+// (z1 = w0 r / diag) already sitting in S->za; both are written by the fused
+// axpy2_dot_first kernel of the Krylov update.  Otherwise they are made from S->r.
 void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     const long long n = S->n_local;
     if (S->prm.precond != OI_PRECOND_MG) {
-        oi::l0_jacobi_precond_dot(S->g, S->flags.p, S->r.p, S->z.p, S->d_partials, S->d_counter,
+        oi::l0_jacobi_precond_dot(S->g, S->flags.p, S->r.p, S->za.p, S->d_partials, S->d_counter,
                                   dot_out ? dot_out : S->d_scal + 15, S->n_sm, S->st);
         S->launches++;
+        S->zres = S->za.p;
         if (dot_out) allreduce_sum_f64(S, dot_out, 1);
         return;
     }
+    if (!first_done) { oi::vec_to_mg(n, S->r32.p, S->r.p, S->n_sm, S->st); S->launches++; }
+    const mg_t* rhs = S->r32.p;
     const int variant = S->prm.stencil_variant;
     const bool have_coarse = !S->levels.empty();
     const std::vector<double>& w = have_coarse ? S->w_smooth : S->w_coarse;
     const int deg = (int)w.size();
     const L0Info f0 = l0info(S);
-    double* cur = S->q.p;
-    double* oth = S->z.p;
+    mg_t* cur = S->za.p;
+    mg_t* oth = S->zb.p;
     if (!first_done) {
-        L0Args a = l0args(S, nullptr, S->r.p, cur, w[0], nullptr);
+        L0Args a = l0args(S, nullptr, rhs, cur, w[0], nullptr);
         oi::l0_jacobi_first(a, S->st); S->launches++;
     }
     for (int s = 1; s < deg; ++s) {
         halo0(S, cur);
-        L0Args a = l0args(S, cur, S->r.p, oth, w[s], dot_out);
+        L0Args a = l0args(S, cur, rhs, oth, w[s], dot_out);
         const bool dot = (!have_coarse && s == deg - 1 && dot_out);
         oi::l0_smooth(a, false, dot, variant, S->st); S->launches++;
         std::swap(cur, oth);
@@ -395,7 +408,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         HostLevel& h1 = S->levels[0];
         halo0(S, cur);
         {
-            L0Args a = l0args(S, cur, S->r.p, h1.L.b, 0.0, nullptr);
+            L0Args a = l0args(S, cur, rhs, h1.L.b, 0.0, nullptr);
             a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
             if (variant != 1) {
                 oi::l0_residual_restrict(a, variant, S->st); S->launches++;
@@ -413,7 +426,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         haloL(S, h1.L, h1.L.x);
         for (int s = 0; s < deg; ++s) {
             const bool dot = (s == deg - 1) && dot_out;
-            L0Args a = l0args(S, cur, S->r.p, oth, w[deg - 1 - s], dot_out);
+            L0Args a = l0args(S, cur, rhs, oth, w[deg - 1 - s], dot_out);
             a.ec = h1.L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
             bool addc = (s == 0);
             if (addc && variant == 0 && oi::ring_supported(a, 1)) {
@@ -430,9 +443,10 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             std::swap(cur, oth);
         }
     } else if (deg == 1 && dot_out) {
-        oi::vec_dot(n, S->r.p, cur, S->d_partials, S->d_counter, dot_out, S->n_sm, S->st); S->launches++;
+        oi::vec_from_mg(n, S->q.p, cur, S->n_sm, S->st);
+        oi::vec_dot(n, S->r.p, S->q.p, S->d_partials, S->d_counter, dot_out, S->n_sm, S->st); S->launches += 2;
     }
-    if (cur != S->z.p) std::swap(S->z, S->q);
+    S->zres = cur;
     if (dot_out) allreduce_sum_f64(S, dot_out, 1);
 }
 
@@ -506,7 +520,7 @@ void run_solve(oi_solver* S) {
         if (!converged) {
             // (re)start: z = M r, p = z
             apply_precond(S, d_rz);
-            oi::vec_copy(n, S->p.p, S->z.p, S->n_sm, S->st); S->launches++;
+            oi::vec_from_mg(n, S->p.p, S->zres, S->n_sm, S->st); S->launches++;
             while (it < S->prm.maxiter) {
                 ++it;
                 halo0(S, S->p.p);
@@ -515,9 +529,9 @@ void run_solve(oi_solver* S) {
                 allreduce_sum_f64(S, d_pq, 1);
                 const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
                 if (fuse_first)
-                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq,
-                                            first_smoothing_weight(S), S->d_partials, S->d_counter, d_rr,
-                                            S->n_sm, S->st);
+                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->r.p, S->p.p, S->q.p, S->r32.p,
+                                            S->za.p, d_rz, d_pq, first_smoothing_weight(S), S->d_partials,
+                                            S->d_counter, d_rr, S->n_sm, S->st);
                 else
                     oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
                                       S->d_counter, d_rr, S->n_sm, S->st);
@@ -527,7 +541,7 @@ void run_solve(oi_solver* S) {
                 if (!std::isfinite(rr)) { fail = true; break; }
                 if (std::sqrt(rr) <= tol) { converged = true; break; }
                 apply_precond(S, d_rzn, fuse_first);
-                oi::vec_xpby(n, S->p.p, S->z.p, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
+                oi::vec_xpby(n, S->p.p, S->zres, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
                 std::swap(d_rz, d_rzn);
             }
             if (fail || !converged) break;
@@ -582,12 +596,13 @@ void build_mask(oi_solver* S) {
     // in the steady-state step): labels -> p, reach bytes -> q, plane bits -> z.
     if (!S->vectors_allocated) {
         S->x.alloc(g.plane, g.nz); S->r.alloc(g.plane, g.nz); S->p.alloc(g.plane, g.nz);
-        S->q.alloc(g.plane, g.nz); S->z.alloc(g.plane, g.nz);
+        S->q.alloc(g.plane, g.nz);
+        S->r32.alloc(g.plane, g.nz); S->za.alloc(g.plane, g.nz); S->zb.alloc(g.plane, g.nz);
         S->vectors_allocated = true;
     }
     int* d_labels = reinterpret_cast<int*>(S->p.p);
     unsigned int* d_reach = reinterpret_cast<unsigned int*>(S->q.p);
-    uint8_t* d_bits = reinterpret_cast<uint8_t*>(S->z.p);   // 4 planes: send lo, send hi, recv lo, recv hi
+    uint8_t* d_bits = reinterpret_cast<uint8_t*>(S->r.p);   // 4 planes: send lo, send hi, recv lo, recv hi
     const size_t reach_words = (size_t)(n + 3) / 4 + 1;
     CUDA_CHECK(cudaMemsetAsync(d_reach, 0, reach_words * sizeof(unsigned int), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
@@ -650,7 +665,7 @@ void build_mask(oi_solver* S) {
     // everywhere, ghost planes included) before they are used as fp64 fields
     CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
-    CUDA_CHECK(cudaMemsetAsync(S->z.base, 0, S->z.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->r.base, 0, S->r.count * sizeof(double), S->st));
 
     // initial guess (skipped when nothing percolates, like the reference's early
     // return TortuosityHypre.cpp:170-178)
@@ -1093,20 +1108,20 @@ int oi_set_solution(oi_solver* S, const double* host) {
 }
 int oi_get_initial_guess(oi_solver* S, double* host) {
     return guarded([&] {
-        OI_REQUIRE(S && host && S->mask_built && S->z.p, "oi_get_initial_guess: mask not built / empty");
+        OI_REQUIRE(S && host && S->mask_built && S->q.p, "oi_get_initial_guess: mask not built / empty");
         ensure_device(S);
-        oi::fill_initial_guess(S->g, S->flags.p, S->z.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, 1, S->st);
+        oi::fill_initial_guess(S->g, S->flags.p, S->q.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, 1, S->st);
         S->launches++;
-        copy_out(S, S->z.p, host, (size_t)S->n_local);
+        copy_out(S, S->q.p, host, (size_t)S->n_local);
     });
 }
 int oi_get_rhs(oi_solver* S, double* host) {
     return guarded([&] {
-        OI_REQUIRE(S && host && S->mask_built && S->z.p, "oi_get_rhs: mask not built / empty");
+        OI_REQUIRE(S && host && S->mask_built && S->q.p, "oi_get_rhs: mask not built / empty");
         ensure_device(S);
-        oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, nullptr, S->z.p, S->st);
+        oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, nullptr, S->q.p, S->st);
         S->launches++;
-        copy_out(S, S->z.p, host, (size_t)S->n_local);
+        copy_out(S, S->q.p, host, (size_t)S->n_local);
     });
 }
 int oi_get_matrix_rows(oi_solver* S, double* host) {
@@ -1140,7 +1155,8 @@ int oi_apply_precond(oi_solver* S, const double* hr, double* hz) {
         if (!S->hierarchy_built) build_hierarchy(S);
         CUDA_CHECK(cudaMemcpyAsync(S->r.p, hr, (size_t)S->n_local * sizeof(double), cudaMemcpyHostToDevice, S->st));
         apply_precond(S, S->d_scal + 13);
-        copy_out(S, S->z.p, hz, (size_t)S->n_local);
+        oi::vec_from_mg(S->n_local, S->q.p, S->zres, S->n_sm, S->st); S->launches++;
+        copy_out(S, S->q.p, hz, (size_t)S->n_local);
         CUDA_CHECK(cudaGetLastError());
     });
 }
@@ -1163,25 +1179,26 @@ int oi_time_kernel(oi_solver* S, const char* name, int32_t reps, double* avg_ms,
                 L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, S->d_scal + 12);
                 oi::l0_apply(a, true, variant, S->st);
             } else if (k == "smooth") {
-                L0Args a = l0args(S, S->z.p, S->r.p, S->q.p, 0.5, nullptr);
+                L0Args a = l0args(S, S->za.p, S->r32.p, S->zb.p, 0.5, nullptr);
                 oi::l0_smooth(a, false, false, variant, S->st);
             } else if (k == "smooth_prolong") {
                 OI_REQUIRE(!S->levels.empty(), "no coarse level");
-                L0Args a = l0args(S, S->z.p, S->r.p, S->q.p, 0.5, nullptr);
+                L0Args a = l0args(S, S->za.p, S->r32.p, S->zb.p, 0.5, nullptr);
                 a.ec = S->levels[0].L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
                 oi::l0_smooth(a, true, false, variant, S->st);
             } else if (k == "residual_restrict") {
                 OI_REQUIRE(!S->levels.empty(), "no coarse level");
-                L0Args a = l0args(S, S->z.p, S->r.p, S->levels[0].L.b, 0.0, nullptr);
+                L0Args a = l0args(S, S->za.p, S->r32.p, S->levels[0].L.b, 0.0, nullptr);
                 a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
                 oi::l0_residual_restrict(a, variant == 1 ? 0 : variant, S->st);
             } else if (k == "axpy2_dot") {
-                oi::vec_axpy2_dot(n, S->z.p, S->q.p, S->p.p, S->r.p, S->d_scal + 10, S->d_scal + 11,
-                                  S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);
+                oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->q.p, S->p.p, S->r.p, S->r32.p, S->za.p,
+                                        S->d_scal + 10, S->d_scal + 11, 0.5, S->d_partials, S->d_counter,
+                                        S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "xpby") {
-                oi::vec_xpby(n, S->q.p, S->z.p, S->d_scal + 10, S->d_scal + 11, S->n_sm, S->st);
+                oi::vec_xpby(n, S->q.p, S->za.p, S->d_scal + 10, S->d_scal + 11, S->n_sm, S->st);
             } else if (k == "dot") {
-                oi::vec_dot(n, S->r.p, S->z.p, S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);
+                oi::vec_dot(n, S->r.p, S->q.p, S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "precond") {
                 apply_precond(S, S->d_scal + 12);
             } else {

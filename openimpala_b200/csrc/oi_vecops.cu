@@ -42,15 +42,15 @@ axpy2_dot_kernel(long long n, double* __restrict__ x, double* __restrict__ r,
     grid_reduce<1>(v, partials, counter, out);
 }
 
-// Same update, plus the first smoothing sweep of the next preconditioner
-// application from a zero guess, z1 = w0 * r_new / diag, written over q (q = A p is
-// dead once r has been updated; same thread, same index, so in place is safe).
-// Saves re-reading r and one launch per Krylov iteration.
+// Same update, plus what the next preconditioner application needs: the residual in
+// multigrid precision (r32) and its first smoothing sweep from a zero guess,
+// z1 = w0 * r_new / diag.  Saves re-reading r and one launch per Krylov iteration.
 __global__ void __launch_bounds__(VT)
 axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, double* __restrict__ x,
-                       double* __restrict__ r, const double* __restrict__ p, double* __restrict__ q,
-                       const double* __restrict__ num, const double* __restrict__ den, double w0,
-                       double* partials, unsigned int* counter, double* out) {
+                       double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
+                       mg_t* __restrict__ r32, mg_t* __restrict__ z1, const double* __restrict__ num,
+                       const double* __restrict__ den, double w0, double* partials, unsigned int* counter,
+                       double* out) {
     __shared__ double winv[64];
     if (threadIdx.x < 64) {
         const int t = threadIdx.x;
@@ -63,6 +63,7 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     const long long stride = (long long)gridDim.x * VT * 2;
     double acc = 0.0;
     const long long n2 = n & ~1LL;
+    typedef typename Vec2<mg_t>::type mg2;
     for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
         double2 xv = *reinterpret_cast<double2*>(x + i);
         double2 rv = *reinterpret_cast<double2*>(r + i);
@@ -75,10 +76,12 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
         *reinterpret_cast<double2*>(r + i) = rv;
         acc += rv.x * rv.x + rv.y * rv.y;
         const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
-        double2 zv;
-        zv.x = (f0 & F_UNK) ? rv.x * winv[f0 & 63u] : 0.0;
-        zv.y = (f1 & F_UNK) ? rv.y * winv[f1 & 63u] : 0.0;
-        *reinterpret_cast<double2*>(q + i) = zv;
+        mg2 rr, zv;
+        rr.x = (mg_t)rv.x; rr.y = (mg_t)rv.y;
+        zv.x = (f0 & F_UNK) ? (mg_t)(rv.x * winv[f0 & 63u]) : (mg_t)0;
+        zv.y = (f1 & F_UNK) ? (mg_t)(rv.y * winv[f1 & 63u]) : (mg_t)0;
+        *reinterpret_cast<mg2*>(r32 + i) = rr;
+        *reinterpret_cast<mg2*>(z1 + i) = zv;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
         const long long i = n2;
@@ -87,25 +90,34 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
         r[i] = rv;
         acc += rv * rv;
         const unsigned int f = flags[i];
-        q[i] = (f & F_UNK) ? rv * winv[f & 63u] : 0.0;
+        r32[i] = (mg_t)rv;
+        z1[i] = (f & F_UNK) ? (mg_t)(rv * winv[f & 63u]) : (mg_t)0;
     }
     double v[1] = {acc};
     grid_reduce<1>(v, partials, counter, out);
 }
 
 __global__ void __launch_bounds__(VT)
-xpby_kernel(long long n, double* __restrict__ p, const double* __restrict__ z,
+xpby_kernel(long long n, double* __restrict__ p, const mg_t* __restrict__ z,
             const double* __restrict__ num, const double* __restrict__ den) {
     const double bta = num[0] / den[0];
     const long long stride = (long long)gridDim.x * VT * 2;
     const long long n2 = n & ~1LL;
+    typedef typename Vec2<mg_t>::type mg2;
     for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
         double2 pv = *reinterpret_cast<double2*>(p + i);
-        const double2 zv = *reinterpret_cast<const double2*>(z + i);
-        pv.x = zv.x + bta * pv.x; pv.y = zv.y + bta * pv.y;
+        const mg2 zv = *reinterpret_cast<const mg2*>(z + i);
+        pv.x = (double)zv.x + bta * pv.x; pv.y = (double)zv.y + bta * pv.y;
         *reinterpret_cast<double2*>(p + i) = pv;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = z[n2] + bta * p[n2];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = (double)z[n2] + bta * p[n2];
+}
+
+template <typename D, typename S>
+__global__ void __launch_bounds__(VT)
+convert_kernel(long long n, D* __restrict__ d, const S* __restrict__ s) {
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride) d[i] = (D)s[i];
 }
 
 __global__ void __launch_bounds__(VT)
@@ -126,7 +138,7 @@ copy_kernel(long long n, double* __restrict__ d, const double* __restrict__ s) {
 
 __global__ void __launch_bounds__(VT)
 jacobi_precond_dot_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ r,
-                          double* __restrict__ z, long long n, double* partials,
+                          mg_t* __restrict__ z, long long n, double* partials,
                           unsigned int* counter, double* out) {
     const long long stride = (long long)gridDim.x * VT;
     double acc = 0.0;
@@ -140,7 +152,7 @@ jacobi_precond_dot_kernel(Grid g, const uint8_t* __restrict__ flags, const doubl
             zv = rv / d;
             acc += rv * zv;
         }
-        z[i] = zv;
+        z[i] = (mg_t)zv;
     }
     double v[1] = {acc};
     grid_reduce<1>(v, partials, counter, out);
@@ -163,15 +175,21 @@ void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const dou
     axpy2_dot_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, x, r, p, q, num, den, partials, counter, out);
 }
 void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
-                         const double* p, double* q, const double* num, const double* den, double w0,
-                         double* partials, unsigned int* counter, double* out, int n_sm,
-                         cudaStream_t st) {
-    axpy2_dot_first_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, num, den, w0,
-                                                                      partials, counter, out);
+                         const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
+                         const double* den, double w0, double* partials, unsigned int* counter,
+                         double* out, int n_sm, cudaStream_t st) {
+    axpy2_dot_first_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den,
+                                                                      w0, partials, counter, out);
 }
-void vec_xpby(long long n, double* p, const double* z, const double* num, const double* den,
+void vec_xpby(long long n, double* p, const mg_t* z, const double* num, const double* den,
               int n_sm, cudaStream_t st) {
     xpby_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, p, z, num, den);
+}
+void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st) {
+    convert_kernel<mg_t, double><<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);
+}
+void vec_from_mg(long long n, double* dst, const mg_t* src, int n_sm, cudaStream_t st) {
+    convert_kernel<double, mg_t><<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);
 }
 void vec_dot(long long n, const double* a, const double* b, double* partials, unsigned int* counter,
              double* out, int n_sm, cudaStream_t st) {
@@ -180,7 +198,7 @@ void vec_dot(long long n, const double* a, const double* b, double* partials, un
 void vec_copy(long long n, double* dst, const double* src, int n_sm, cudaStream_t st) {
     copy_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);
 }
-void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, double* z,
+void l0_jacobi_precond_dot(const Grid& g, const uint8_t* flags, const double* r, mg_t* z,
                            double* partials, unsigned int* counter, double* out, int n_sm,
                            cudaStream_t st) {
     const long long n = (long long)g.nz * g.plane;

@@ -214,7 +214,8 @@ def test_preconditioner_is_symmetric(capi):
         b = np.where(unk, rng.standard_normal(ph.shape), 0.0)
         ma, mb = s.apply_precond(a), s.apply_precond(b)
         lhs, rhs = float((ma * b).sum()), float((a * mb).sum())
-        assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+        # the V-cycle runs in fp32 (mg_t): symmetric up to single-precision rounding
+        assert abs(lhs - rhs) <= 5e-5 * max(abs(lhs), abs(rhs))
         assert float((ma * a).sum()) > 0.0
 
 
