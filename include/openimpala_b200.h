@@ -64,7 +64,7 @@ typedef struct oi_params {
     int32_t stencil_variant;   /* 0 = z-plane ring in shared memory (cp.async, default),
                                   2 = register z-march, 1 = simple gather            */
     int32_t flux_polish;       /* 1: keep iterating (<= maxiter) until the flux
-                                  imbalance is 10x inside the reference's 1e-6
+                                  imbalance is 2x inside the reference's 1e-6
                                   gate (TortuosityHypre.cpp:794-803); 0: stop on
                                   the residual rule alone                          */
     struct oi_comm* comm;      /* z-slab communicator (oi_comm_create) or NULL for

@@ -127,6 +127,58 @@ coarse_stencil_kernel(CoarseLevel L, const mg_t* __restrict__ x, const mg_t* __r
     }
 }
 
+// Vectorised variant for fp32 levels whose nx is a multiple of 4: each thread owns
+// four x-adjacent cells (16-byte loads of x, b and of every coefficient array), a
+// CTA covers 64 x 16 cells of one plane.  Same arithmetic as the scalar kernel.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const float* __restrict__ b,
+                           float* __restrict__ out, float w) {
+    const int i = blockIdx.x * 64 + (threadIdx.x & 15) * 4;
+    const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (i >= L.nx || j >= L.ny) return;
+    const long long col = (long long)j * L.nx + i;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
+        const long long idx = (long long)k * L.plane + col;
+        const float4 d = ld4(L.dg + idx);
+        float4 o = zero4;
+        if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
+            const float4 c = ld4(x + idx);
+            const float4 cxp = ld4(L.cxp + idx), cyp = ld4(L.cyp + idx), czp = ld4(L.czp + idx);
+            const float cxw = (i > 0) ? L.cxp[idx - 1] : 0.f;
+            const float xw = (i > 0) ? x[idx - 1] : 0.f;
+            const float xe = (i + 4 < L.nx) ? x[idx + 4] : 0.f;
+            const float4 cym = (j > 0) ? ld4(L.cyp + idx - L.nx) : zero4;
+            const float4 ys = (j > 0) ? ld4(x + idx - L.nx) : zero4;
+            const float4 yn = (j + 1 < L.ny) ? ld4(x + idx + L.nx) : zero4;
+            const float4 czm = ld4(L.czp + idx - L.plane);          // k-1 may be the ghost plane
+            const float4 zd = ld4(x + idx - L.plane);
+            const float4 zu = ld4(x + idx + L.plane);
+            float4 acc;
+            acc.x = d.x * c.x - cxp.x * c.y - cxw * xw - cyp.x * yn.x - cym.x * ys.x - czp.x * zu.x - czm.x * zd.x;
+            acc.y = d.y * c.y - cxp.y * c.z - cxp.x * c.x - cyp.y * yn.y - cym.y * ys.y - czp.y * zu.y - czm.y * zd.y;
+            acc.z = d.z * c.z - cxp.z * c.w - cxp.y * c.y - cyp.z * yn.z - cym.z * ys.z - czp.z * zu.z - czm.z * zd.z;
+            acc.w = d.w * c.w - cxp.w * xe - cxp.z * c.z - cyp.w * yn.w - cym.w * ys.w - czp.w * zu.w - czm.w * zd.w;
+            const float4 bb = ld4(b + idx);
+            if (MODE == 1) {
+                o.x = d.x > 0.f ? c.x + w * (bb.x - acc.x) / d.x : 0.f;
+                o.y = d.y > 0.f ? c.y + w * (bb.y - acc.y) / d.y : 0.f;
+                o.z = d.z > 0.f ? c.z + w * (bb.z - acc.z) / d.z : 0.f;
+                o.w = d.w > 0.f ? c.w + w * (bb.w - acc.w) / d.w : 0.f;
+            } else {
+                o.x = d.x > 0.f ? bb.x - acc.x : 0.f;
+                o.y = d.y > 0.f ? bb.y - acc.y : 0.f;
+                o.z = d.z > 0.f ? bb.z - acc.z : 0.f;
+                o.w = d.w > 0.f ? bb.w - acc.w : 0.f;
+            }
+        }
+        *reinterpret_cast<float4*>(out + idx) = o;
+    }
+}
+
 // x += P * ec on non-empty cells (prolongation + correction between coarse levels)
 __global__ void __launch_bounds__(256)
 coarse_prolong_add_kernel(CoarseLevel L, mg_t* __restrict__ x, const mg_t* __restrict__ ec,
@@ -202,8 +254,21 @@ static dim3 grid3(const CoarseLevel& L) {
     return dim3((L.nx + 63) / 64, (L.ny + 3) / 4, gz > 0 ? gz : 1);
 }
 
+// the 16-byte path needs fp32 vectors and every row / plane start 16-byte aligned
+static bool vec4_ok(const CoarseLevel& L) {
+    return sizeof(mg_t) == 4 && (L.nx & 3) == 0 && L.nx >= 16;
+}
+static dim3 grid_vec4(const CoarseLevel& L) {
+    int gz = L.nz < 128 ? L.nz : 128;
+    return dim3((L.nx + 63) / 64, (L.ny + 15) / 16, gz > 0 ? gz : 1);
+}
+
 void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
-    coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
+    if (vec4_ok(L))
+        coarse_stencil_vec4_kernel<1><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), (float)w);
+    else
+        coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
 }
 
 void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec, cudaStream_t st) {
@@ -211,7 +276,11 @@ void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, 
 }
 
 void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st) {
-    coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
+    if (vec4_ok(L))
+        coarse_stencil_vec4_kernel<2><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
+    else
+        coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
 }
 
 void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc, cudaStream_t st) {

@@ -558,7 +558,8 @@ void run_solve(oi_solver* S) {
             double fin, fout;
             compute_fluxes(S, &fin, &fout);
             const double avg = 0.5 * (std::fabs(fin) + std::fabs(fout));
-            if (avg > 1e-15 && std::fabs(std::fabs(fin) - std::fabs(fout)) / avg > 1e-7) {
+            // the reference returns NaN above 1e-6 (TortuosityHypre.cpp:794-803); keep a 2x margin
+            if (avg > 1e-15 && std::fabs(std::fabs(fin) - std::fabs(fout)) / avg > 5e-7) {
                 ++polish_rounds;
                 tol *= 0.1;
                 converged = false;
