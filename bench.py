@@ -213,6 +213,7 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
     launches = S.launch_count() - l0
+    halo_mode, halo_peer_exchanges = S.halo_info()
     tmax = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -247,7 +248,7 @@ def main():
         traffic = tj["apply_bytes_per_launch"] / tj["apply_cells"] * local_cells
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "l0_zmarch_kernel<APPLY,dot> (y = A p, p.Ap)",
+    roofline = {"bound": "hbm", "kernel": "l0_ring_kernel<double,APPLY,dot> (y = A p, p.Ap)",
                 "achieved": kern["apply"]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kern["apply"]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": 17.0, "cells_per_launch": local_cells,
@@ -307,6 +308,8 @@ def main():
             "config": {"workload": f"sphere-packing {n}^3 uint8 (seed {SEED}, R {RADIUS}, solid {SOLID}), "
                                    f"tau in {'XYZ'[direction]}, phase 1, eps 1e-9, MG-PCG",
                        "parallelism": f"z-slabs x{world}",
+                       "halo": {0: "none (single slab)", 1: "NCCL send/recv",
+                                2: "peer-memory stores over NVLink (CUDA IPC) + stream wait on flag words"}[halo_mode],
                        "l2_policy": "inputs larger than L2 (every fp64 vector >= 1 GiB at 512^3+)",
                        "porosity": float(slab.mean()) if world == 1 else None,
                        "generate_s": t_gen},

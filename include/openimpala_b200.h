@@ -46,6 +46,12 @@ typedef enum oi_direction { OI_DIR_X = 0, OI_DIR_Y = 1, OI_DIR_Z = 2 } oi_direct
  * src/props/TortuosityHypre.cpp:664-678; every SolverType maps to PCG here). */
 typedef enum oi_precond { OI_PRECOND_MG = 0, OI_PRECOND_JACOBI = 1 } oi_precond;
 
+/* Ghost-plane exchange between z-slabs (AMReX FillBoundary in the reference,
+ * TortuosityHypre.cpp:339, 584-585, 1033).  AUTO = peer-memory stores over
+ * NVLink (CUDA IPC) when every rank can map its neighbours, else NCCL
+ * send/recv.  The environment variable OI_HALO_MODE=nccl|p2p overrides. */
+typedef enum oi_halo_mode { OI_HALO_AUTO = 0, OI_HALO_NCCL = 1, OI_HALO_PEER = 2 } oi_halo_mode;
+
 struct oi_comm;
 
 typedef struct oi_params {
@@ -67,6 +73,7 @@ typedef struct oi_params {
                                   imbalance is 2x inside the reference's 1e-6
                                   gate (TortuosityHypre.cpp:794-803); 0: stop on
                                   the residual rule alone                          */
+    int32_t halo_mode;         /* oi_halo_mode: how ghost planes travel between z-slabs */
     struct oi_comm* comm;      /* z-slab communicator (oi_comm_create) or NULL for
                                   a single slab; must outlive the handle            */
 } oi_params;
@@ -167,6 +174,14 @@ int oi_time_kernel(oi_solver* h, const char* name, int32_t reps, double* avg_ms,
  * recorded slots (synchronises on the later one). */
 int oi_timer_record(oi_solver* h, int32_t slot);
 int oi_timer_elapsed_ms(oi_solver* h, int32_t slot_begin, int32_t slot_end, double* ms);
+/* Device blocks of destroyed handles are kept in a process-wide cache so that the
+ * next handle of the same shape allocates nothing (OI_NO_MEM_CACHE=1 disables it).
+ * This returns the idle blocks to the driver; call it only while no multi-slab
+ * handle is alive on any rank (neighbours may have the blocks mapped). */
+int oi_release_cached_memory(int64_t* bytes_released);
+/* Which halo path the handle uses (oi_halo_mode; AUTO for a single slab) and how
+ * many ghost-plane exchanges went through peer memory so far. */
+int oi_halo_info(oi_solver* h, int32_t* mode, int64_t* peer_exchanges);
 /* Number of kernels this handle has launched since creation. */
 int oi_launch_count(oi_solver* h, int64_t* launches);
 

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libopenimpala_b200.so")
 
 OI_OK = 0
 OI_PRECOND_MG, OI_PRECOND_JACOBI = 0, 1
+OI_HALO_AUTO, OI_HALO_NCCL, OI_HALO_PEER = 0, 1, 2
 
 
 class OiError(RuntimeError):
@@ -35,7 +36,7 @@ class oi_params(C.Structure):
         ("eps", C.c_double),
         ("maxiter", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32),
         ("precond", C.c_int32), ("mg_degree", C.c_int32), ("stencil_variant", C.c_int32),
-        ("flux_polish", C.c_int32),
+        ("flux_polish", C.c_int32), ("halo_mode", C.c_int32),
         ("comm", C.c_void_p),
     ]
 
@@ -83,6 +84,8 @@ _SIGS = {
     "oi_time_kernel": (C.c_int, [_P, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "oi_timer_record": (C.c_int, [_P, C.c_int32]),
     "oi_timer_elapsed_ms": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    "oi_release_cached_memory": (C.c_int, [C.POINTER(C.c_int64)]),
+    "oi_halo_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "oi_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -133,6 +136,13 @@ def count_phase(field: np.ndarray, phase: int):
         a = np.ascontiguousarray(a, dtype=np.int32)
         _check(lib.oi_count_phase_i32(a.ctypes.data, a.size, phase, C.byref(pc), C.byref(tc)))
     return pc.value, tc.value
+
+
+def release_cached_memory() -> int:
+    """Return idle cached device blocks to the driver; -> bytes released."""
+    b = C.c_int64(0)
+    _check(load().oi_release_cached_memory(C.byref(b)))
+    return b.value
 
 
 def comm_unique_id() -> bytes:
@@ -190,7 +200,8 @@ class Solver:
     def __init__(self, shape, direction: int, phase_id: int = 1, vlo: float = 0.0, vhi: float = 1.0,
                  eps: float = 1e-9, maxiter: int = 200, dx=(1.0, 1.0, 1.0), precond: int = OI_PRECOND_MG,
                  mg_degree: int = 0, stencil_variant: int = 0, flux_polish: int = 1, device: int = -1,
-                 z_begin: int = 0, nz_local: int = 0, comm: "Comm | None" = None, verbose: int = 0):
+                 z_begin: int = 0, nz_local: int = 0, comm: "Comm | None" = None, verbose: int = 0,
+                 halo_mode: int = OI_HALO_AUTO):
         self._lib = load()
         self._h = _P(None)
         nz, ny, nx = (int(s) for s in shape)
@@ -203,6 +214,7 @@ class Solver:
         p.eps, p.maxiter, p.verbose, p.device = float(eps), int(maxiter), int(verbose), int(device)
         p.precond, p.mg_degree, p.stencil_variant = int(precond), int(mg_degree), int(stencil_variant)
         p.flux_polish = int(flux_polish)
+        p.halo_mode = int(halo_mode)
         self._comm = comm                       # keep the communicator alive
         p.comm = comm.handle if comm is not None else None
         self.params = p
@@ -321,6 +333,12 @@ class Solver:
         ms = C.c_double(0)
         _check(self._lib.oi_timer_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    def halo_info(self):
+        """(oi_halo_mode in use, ghost-plane exchanges done through peer memory)."""
+        m, n = C.c_int32(0), C.c_int64(0)
+        _check(self._lib.oi_halo_info(self._h, C.byref(m), C.byref(n)))
+        return m.value, n.value
 
     def launch_count(self) -> int:
         n = C.c_int64(0)

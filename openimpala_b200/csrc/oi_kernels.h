@@ -151,4 +151,17 @@ void export_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int
 void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
                 int n_dir_global, unsigned long long* bad, cudaStream_t st);
 
+
+// ---------------------------------------------------------------- peer halo (oi_halo.cu)
+// Store this slab's bottom plane into the lower neighbour's top ghost plane and its
+// top plane into the upper neighbour's bottom ghost plane (peer pointers, either
+// may be null), then write `seq` into the neighbours' flag words.
+void halo_push(const void* src_lo, void* dst_lo, const void* src_hi, void* dst_hi, size_t plane_bytes,
+               unsigned int* flag_lo, unsigned int* flag_hi, unsigned int seq, unsigned int* counter,
+               int n_sm, cudaStream_t st);
+// Spin until the local flag words reach `seq` (used when stream memory operations
+// are not available; the default wait is cuStreamWaitValue32).
+void halo_wait_spin(const unsigned int* flag_a, const unsigned int* flag_b, unsigned int seq,
+                    cudaStream_t st);
+
 }  // namespace oi

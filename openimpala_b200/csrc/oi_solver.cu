@@ -6,17 +6,24 @@
 // five fp64 Krylov vectors and the multigrid hierarchy.  Slabs talk through NCCL
 // (halo planes with send/recv, dots with all-reduce); NCCL is loaded lazily so
 // a single-GPU process never needs it.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/openimpala_b200.h"
@@ -94,7 +101,109 @@ NcclApi& nccl_api() {
                                            " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
     } while (0)
 
+// ------------------------------------------------------------------ device memory cache
+// Process-wide cache of device blocks, keyed by (device, size): a handle that is
+// created after another one of the same shape was destroyed reuses its blocks, so a
+// steady-state TortuosityHypre construct/solve/destroy cycle makes no cudaMalloc or
+// cudaFree calls (the reference pays AMReX arena + HYPRE allocations per object,
+// src/props/TortuosityHypre.cpp:100-191).  Blocks go back to the driver on
+// oi_release_cached_memory(), when an allocation fails, or at process exit.
+// OI_NO_MEM_CACHE=1 turns the cache off.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> idle;
+    std::unordered_map<void*, std::pair<int, size_t>> live;      // every block handed out
+    std::unordered_map<void*, unsigned long long> serial;        // per real cudaMalloc
+    unsigned long long next_serial = 1;
+    bool enabled = true;
+    DevCache() { const char* e = getenv("OI_NO_MEM_CACHE"); enabled = !(e && e[0] == '1'); }
+    static size_t round_up(size_t b) {
+        const size_t q = b >= (1u << 20) ? (size_t)2 << 20 : 512;
+        return (b + q - 1) / q * q;
+    }
+    std::unordered_set<void*> exported;                          // mapped by other processes (CUDA IPC)
+    void release_idle_locked() {
+        // a block another process may have mapped is never handed back to the driver
+        // (freeing exported memory before the importer unmaps it is undefined)
+        for (auto it = idle.begin(); it != idle.end();) {
+            if (exported.count(it->second)) { ++it; continue; }
+            serial.erase(it->second);
+            cudaFree(it->second);
+            it = idle.erase(it);
+        }
+    }
+    void mark_exported(void* p) { std::lock_guard<std::mutex> lk(mu); exported.insert(p); }
+    cudaError_t alloc(void** out, size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t sz = round_up(bytes ? bytes : 1);
+        auto it = idle.find({dev, sz});
+        if (it != idle.end()) {
+            *out = it->second;
+            idle.erase(it);
+            live[*out] = {dev, sz};
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, sz);
+        if (e != cudaSuccess && !idle.empty()) {
+            cudaGetLastError();
+            release_idle_locked();
+            e = cudaMalloc(out, sz);
+        }
+        if (e == cudaSuccess) { live[*out] = {dev, sz}; serial[*out] = next_serial++; }
+        return e;
+    }
+    void free(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(p);
+        if (it == live.end()) { cudaFree(p); return; }
+        if (enabled || exported.count(p)) idle.insert({it->second, p});
+        else { serial.erase(p); cudaFree(p); }
+        live.erase(it);
+    }
+    unsigned long long serial_of(void* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = serial.find(p);
+        return it == serial.end() ? 0ull : it->second;
+    }
+    size_t idle_bytes() {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t b = 0;
+        for (auto& kv : idle) b += kv.first.second;
+        return b;
+    }
+};
+DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }   // leaked on purpose: outlives atexit
+template <typename T>
+cudaError_t cmalloc(T** p, size_t bytes) { return dev_cache().alloc(reinterpret_cast<void**>(p), bytes); }
+inline void cfree(void* p) { dev_cache().free(p); }
+
+// Mappings of neighbours' arenas (CUDA IPC) are kept for the life of the process,
+// keyed by the exporting process and the serial number of its allocation, so a
+// re-created handle whose neighbours reuse their cached arenas maps nothing.
+struct PeerMapCache {
+    std::mutex mu;
+    std::map<std::pair<long long, unsigned long long>, void*> maps;
+};
+PeerMapCache& peer_maps() { static PeerMapCache* c = new PeerMapCache(); return *c; }
+
 // ------------------------------------------------------------------ device buffers
+// One cudaMalloc shared by every field whose ghost planes a z-neighbour writes
+// into; a single CUDA IPC handle exposes it to the neighbouring processes.
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, off = 0;
+    void* take(size_t bytes) {
+        off = (off + 255) / 256 * 256;
+        if (off + bytes > size) throw OiError(OI_ERR_NOMEM, "halo arena exhausted");
+        void* p = base + off;
+        off += bytes;
+        return p;
+    }
+};
+
 // A field with one ghost plane below and above; `p` points at plane 0 and is
 // 256-byte aligned.
 template <typename T>
@@ -102,19 +211,77 @@ struct Field {
     T* base = nullptr;
     T* p = nullptr;
     size_t lead = 0, count = 0;
-    void alloc(long long plane, long long nz) {
-        lead = (size_t)((plane * sizeof(T) + 255) / 256 * 256 / sizeof(T));
-        while (lead < (size_t)plane) lead += 256 / sizeof(T);
+    bool owned = true;
+    static size_t lead_elems(long long plane) {
+        size_t l = (size_t)((plane * sizeof(T) + 255) / 256 * 256 / sizeof(T));
+        while (l < (size_t)plane) l += 256 / sizeof(T);
+        return l;
+    }
+    static size_t bytes_needed(long long plane, long long nz) {
+        return (lead_elems(plane) + (size_t)plane * (size_t)(nz + 1)) * sizeof(T);
+    }
+    // arena != nullptr: carve from the (already zeroed) halo arena instead of cudaMalloc
+    // Zeroed on `st` (the handle's stream): every later use of the field is ordered behind it.
+    void alloc(long long plane, long long nz, cudaStream_t st, Arena* arena = nullptr) {
+        lead = lead_elems(plane);
         count = lead + (size_t)plane * (size_t)(nz + 1);
-        CUDA_CHECK(cudaMalloc(&base, count * sizeof(T)));
-        CUDA_CHECK(cudaMemset(base, 0, count * sizeof(T)));
+        if (arena) {
+            base = static_cast<T*>(arena->take(count * sizeof(T)));
+            owned = false;
+        } else {
+            CUDA_CHECK(cmalloc(&base, count * sizeof(T)));
+            CUDA_CHECK(cudaMemsetAsync(base, 0, count * sizeof(T), st));
+            owned = true;
+        }
         p = base + lead;
     }
     void release() {
-        if (base) cudaFree(base);
+        if (base && owned) cfree(base);
         base = p = nullptr;
     }
 };
+
+// ------------------------------------------------------------------ peer halo state
+constexpr int OI_MAX_HALO_FIELDS = 48;
+struct HaloDesc { unsigned long long off0, plane_bytes; long long nz; };   // plane 0 offset in the arena
+struct PeerBlob {
+    cudaIpcMemHandle_t handle;
+    unsigned long long arena_bytes, flag_off;
+    long long pid;                    // exporting process and the serial number of its
+    unsigned long long serial;        // allocation: key of the importer's mapping cache
+    int n_fields, pad;
+    HaloDesc f[OI_MAX_HALO_FIELDS];
+};
+struct PeerHalo {
+    bool on = false;
+    Arena arena;
+    std::vector<HaloDesc> mine;
+    PeerBlob lo{}, hi{};              // tables of the lower / upper z-neighbour
+    char* lo_base = nullptr;          // their arenas mapped into this process
+    char* hi_base = nullptr;
+    unsigned int* flags = nullptr;    // mine: [0] written by the lower neighbour, [1] by the upper
+    unsigned int* counter = nullptr;  // push-kernel block counter
+    unsigned int seq = 0;
+    bool spin_wait = false;
+    long long exchanges = 0;
+};
+
+typedef CUresult (*PFN_stream_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+PFN_stream_wait32 driver_wait32() {
+    static bool tried = false;
+    static PFN_stream_wait32 fn = nullptr;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_stream_wait32>(f);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
 
 struct HostLevel {
     oi::CoarseLevel L{};
@@ -140,13 +307,14 @@ struct oi_solver {
     // comm
     ncclComm_t comm = nullptr;
     std::vector<int> all_z0, all_nz;   // slab table (every rank)
+    PeerHalo peer;                     // peer-memory halo exchange (n_ranks > 1)
     // setup state
     uint8_t* d_isphase = nullptr;      // [n_local]
     Field<uint8_t> active, flags;
     long long phase_count_local = -1, nonbinary_local = 0;
     long long n_active = -1, n_in = 0, n_out = 0;
     bool mask_built = false, hierarchy_built = false, solved = false;
-    bool levels_allocated = false, vectors_allocated = false;
+    bool levels_planned = false, levels_allocated = false, vectors_allocated = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // Krylov vectors (fp64) and the level-0 multigrid vectors (mg_t): residual copy
     // and two ping-pong iterates; zres points at the one holding z = M^-1 r
@@ -194,9 +362,57 @@ std::vector<double> cheb_weights(int degree, double lo_frac, double lmax = 2.0) 
 template <typename T>
 ncclDataType_t nccl_bytes_type() { return ncclUint8; }
 
+// Peer path: boundary planes are stored straight into the neighbours' ghost planes
+// and the neighbours' flag words advance to this exchange's sequence number; the
+// local stream then waits on its own two flag words.  Ranks run the same sequence
+// of exchanges (SPMD), so one counter per handle orders them, and because every
+// stencil kernel is preceded by such a wait a neighbour can be at most one kernel
+// ahead: it never overwrites a ghost plane that is still being read.
+bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz) {
+    PeerHalo& P = S->peer;
+    if (!P.on) return false;
+    const unsigned long long off0 = (unsigned long long)(p0 - P.arena.base);
+    int id = -1;
+    for (size_t i = 0; i < P.mine.size(); ++i)
+        if (P.mine[i].off0 == off0) { id = (int)i; break; }
+    if (id < 0) return false;
+    const int rk = S->rank, nr = S->n_ranks;
+    const unsigned int seq = ++P.seq;
+    char *dst_lo = nullptr, *dst_hi = nullptr;
+    unsigned int *flag_lo = nullptr, *flag_hi = nullptr;
+    if (rk > 0) {          // my bottom plane -> lower neighbour's ghost plane above its top
+        const HaloDesc& d = P.lo.f[id];
+        dst_lo = P.lo_base + d.off0 + d.plane_bytes * (unsigned long long)d.nz;
+        flag_lo = reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1;
+    }
+    if (rk < nr - 1) {     // my top plane -> upper neighbour's ghost plane below its plane 0
+        const HaloDesc& d = P.hi.f[id];
+        dst_hi = P.hi_base + d.off0 - d.plane_bytes;
+        flag_hi = reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0;
+    }
+    oi::halo_push(p0, dst_lo, p0 + plane_bytes * (size_t)(nz - 1), dst_hi, plane_bytes, flag_lo, flag_hi,
+                  seq, P.counter, S->n_sm, S->st);
+    S->launches++;
+    P.exchanges++;
+    const unsigned int* wa = rk > 0 ? P.flags + 0 : nullptr;
+    const unsigned int* wb = rk < nr - 1 ? P.flags + 1 : nullptr;
+    PFN_stream_wait32 wait32 = P.spin_wait ? nullptr : driver_wait32();
+    if (wait32) {
+        if (wa && wait32(S->st, (CUdeviceptr)(uintptr_t)wa, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
+        if (wb && wait32(S->st, (CUdeviceptr)(uintptr_t)wb, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
+    } else {
+        oi::halo_wait_spin(wa, wb, seq, S->st);
+        S->launches++;
+    }
+    return true;
+}
+
 void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long long nz) {
     // send plane 0 down / plane nz-1 up; receive into plane -1 / plane nz
     if (S->n_ranks <= 1) return;
+    if (halo_exchange_peer(S, static_cast<char*>(plane0), plane_bytes, nz)) return;
     NcclApi& N = nccl_api();
     char* p0 = static_cast<char*>(plane0);
     const int rk = S->rank, nr = S->n_ranks;
@@ -265,6 +481,7 @@ void free_levels(oi_solver* S) {
     S->levels.clear();
     S->hierarchy_built = false;
     S->levels_allocated = false;
+    S->levels_planned = false;
 }
 
 void free_vectors(oi_solver* S) {
@@ -274,10 +491,9 @@ void free_vectors(oi_solver* S) {
 }
 
 // ------------------------------------------------------------------ hierarchy
-void allocate_hierarchy(oi_solver* S) {
-    // Level shapes depend only on the box and the slab table, so the arrays are
-    // allocated once per handle and reused by every rebuild.
-    if (S->levels_allocated) return;
+// Level shapes depend only on the box and the slab table.
+void plan_hierarchy(oi_solver* S) {
+    if (S->levels_planned) return;
     const int nr = S->n_ranks, rk = S->rank;
     std::vector<int> z0 = S->all_z0, nz = S->all_nz;
     int nx = S->g.nx, ny = S->g.ny, nzg = S->g.nzg;
@@ -303,14 +519,160 @@ void allocate_hierarchy(oi_solver* S) {
         h.L.nx = nx; h.L.ny = ny; h.L.nz = nz[rk]; h.L.z0 = z0[rk]; h.L.nzg = nzg;
         h.L.plane = (long long)nx * ny;
         h.L.fx = h.L.fy = h.L.fz = 1;
-        h.cxp.alloc(h.L.plane, h.L.nz); h.cyp.alloc(h.L.plane, h.L.nz);
-        h.czp.alloc(h.L.plane, h.L.nz); h.dg.alloc(h.L.plane, h.L.nz);
-        h.x.alloc(h.L.plane, h.L.nz); h.b.alloc(h.L.plane, h.L.nz); h.t.alloc(h.L.plane, h.L.nz);
+    }
+    S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
+    S->levels_planned = true;
+}
+
+void allocate_hierarchy(oi_solver* S) {
+    // The arrays are allocated once per handle and reused by every rebuild; the
+    // iterates x, t (the fields with halo traffic) may already sit in the peer arena.
+    if (S->levels_allocated) return;
+    plan_hierarchy(S);
+    for (HostLevel& h : S->levels) {
+        h.cxp.alloc(h.L.plane, h.L.nz, S->st); h.cyp.alloc(h.L.plane, h.L.nz, S->st);
+        h.czp.alloc(h.L.plane, h.L.nz, S->st); h.dg.alloc(h.L.plane, h.L.nz, S->st);
+        if (!h.x.base) h.x.alloc(h.L.plane, h.L.nz, S->st);
+        if (!h.t.base) h.t.alloc(h.L.plane, h.L.nz, S->st);
+        h.b.alloc(h.L.plane, h.L.nz, S->st);
         h.L.cxp = h.cxp.p; h.L.cyp = h.cyp.p; h.L.czp = h.czp.p; h.L.dg = h.dg.p;
         h.L.x = h.x.p; h.L.b = h.b.p; h.L.t = h.t.p;
     }
-    S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
     S->levels_allocated = true;
+}
+
+// ------------------------------------------------------------------ peer halo setup
+void barrier_ranks(oi_solver* S) {
+    if (S->n_ranks <= 1) return;
+    CUDA_CHECK(cudaStreamSynchronize(S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->d_changed, 0, sizeof(int), S->st));
+    allreduce_max_i32(S, S->d_changed, 1);
+    CUDA_CHECK(cudaStreamSynchronize(S->st));
+}
+
+void peer_teardown(oi_solver* S) {
+    // the mappings themselves stay in the process-wide cache (peer_maps)
+    PeerHalo& P = S->peer;
+    P.lo_base = P.hi_base = nullptr;
+    P.on = false;
+}
+
+// Put every field with steady-state halo traffic (x, p, the two level-0 multigrid
+// iterates, x/t of every coarse level) into one arena, exchange its IPC handle and
+// field table with the z-neighbours, and prove the path with one flag round trip.
+// Returns false (and leaves the NCCL send/recv path in charge) if any rank cannot
+// map its neighbours.
+bool peer_setup(oi_solver* S) {
+    PeerHalo& P = S->peer;
+    const Grid& g = S->g;
+    const int rk = S->rank, nr = S->n_ranks;
+    const bool mg = (S->prm.precond == OI_PRECOND_MG);
+    if (mg) plan_hierarchy(S);
+    size_t need = 4096;
+    auto add = [&](size_t b) { need += b + 256; };
+    add(Field<double>::bytes_needed(g.plane, g.nz)); add(Field<double>::bytes_needed(g.plane, g.nz));
+    add(Field<mg_t>::bytes_needed(g.plane, g.nz)); add(Field<mg_t>::bytes_needed(g.plane, g.nz));
+    if (mg) for (HostLevel& h : S->levels) { add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); }
+    int ok = 1;
+    if (cmalloc(&P.arena.base, need) != cudaSuccess) { cudaGetLastError(); P.arena.base = nullptr; ok = 0; }
+    PeerBlob mine{};
+    if (ok) {
+        P.arena.size = need; P.arena.off = 0;
+        CUDA_CHECK(cudaMemsetAsync(P.arena.base, 0, need, S->st));
+        P.flags = static_cast<unsigned int*>(P.arena.take(256));
+        P.counter = P.flags + 8;
+        auto reg = [&](char* plane0, size_t plane_bytes, long long nz) {
+            HaloDesc d{(unsigned long long)(plane0 - P.arena.base), (unsigned long long)plane_bytes, nz};
+            P.mine.push_back(d);
+        };
+        S->x.alloc(g.plane, g.nz, S->st, &P.arena);  reg((char*)S->x.p, g.plane * sizeof(double), g.nz);
+        S->p.alloc(g.plane, g.nz, S->st, &P.arena);  reg((char*)S->p.p, g.plane * sizeof(double), g.nz);
+        S->za.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->za.p, g.plane * sizeof(mg_t), g.nz);
+        S->zb.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->zb.p, g.plane * sizeof(mg_t), g.nz);
+        if (mg) for (HostLevel& h : S->levels) {
+            h.x.alloc(h.L.plane, h.L.nz, S->st, &P.arena); reg((char*)h.x.p, h.L.plane * sizeof(mg_t), h.L.nz);
+            h.t.alloc(h.L.plane, h.L.nz, S->st, &P.arena); reg((char*)h.t.p, h.L.plane * sizeof(mg_t), h.L.nz);
+        }
+        if ((int)P.mine.size() > OI_MAX_HALO_FIELDS) ok = 0;
+    }
+    if (ok) {
+        if (cudaIpcGetMemHandle(&mine.handle, P.arena.base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        mine.arena_bytes = need;
+        mine.pid = (long long)getpid();
+        mine.serial = dev_cache().serial_of(P.arena.base);
+        if (ok) dev_cache().mark_exported(P.arena.base);
+        mine.flag_off = (unsigned long long)((char*)P.flags - P.arena.base);
+        mine.n_fields = ok ? (int)P.mine.size() : 0;
+        for (int i = 0; i < mine.n_fields; ++i) mine.f[i] = P.mine[i];
+    }
+    // all-gather the blobs (also a barrier: every arena is zeroed before anyone maps it)
+    NcclApi& N = nccl_api();
+    char* d_blobs = nullptr;
+    CUDA_CHECK(cmalloc(&d_blobs, sizeof(PeerBlob) * (size_t)(nr + 1)));
+    CUDA_CHECK(cudaMemcpyAsync(d_blobs + sizeof(PeerBlob) * (size_t)nr, &mine, sizeof(PeerBlob), cudaMemcpyHostToDevice, S->st));
+    NCCL_CHECK(N.AllGather(d_blobs + sizeof(PeerBlob) * (size_t)nr, d_blobs, sizeof(PeerBlob), ncclUint8, S->comm, S->st));
+    std::vector<PeerBlob> all(nr);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_blobs, sizeof(PeerBlob) * (size_t)nr, cudaMemcpyDeviceToHost, S->st));
+    CUDA_CHECK(cudaStreamSynchronize(S->st));
+    cfree(d_blobs);
+    for (int r = 0; r < nr; ++r) if (all[r].n_fields != mine.n_fields || mine.n_fields == 0) ok = 0;
+    auto map_peer = [&](const PeerBlob& b) -> char* {
+        PeerMapCache& C = peer_maps();
+        std::lock_guard<std::mutex> lk(C.mu);
+        const std::pair<long long, unsigned long long> key(b.pid, b.serial);
+        if (b.serial != 0) {
+            auto it = C.maps.find(key);
+            if (it != C.maps.end()) return static_cast<char*>(it->second);
+        }
+        void* m = nullptr;
+        if (cudaIpcOpenMemHandle(&m, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        if (b.serial != 0) C.maps[key] = m;
+        return static_cast<char*>(m);
+    };
+    if (ok && rk > 0) {
+        P.lo = all[rk - 1];
+        P.lo_base = map_peer(P.lo);
+        if (!P.lo_base) ok = 0;
+    }
+    if (ok && rk < nr - 1) {
+        P.hi = all[rk + 1];
+        P.hi_base = map_peer(P.hi);
+        if (!P.hi_base) ok = 0;
+    }
+    // flag round trip (sequence number 1), checked from the host so a broken path
+    // cannot hang a stream
+    if (ok) {
+        unsigned int* flo = rk > 0 ? reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1 : nullptr;
+        unsigned int* fhi = rk < nr - 1 ? reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0 : nullptr;
+        oi::halo_push(nullptr, nullptr, nullptr, nullptr, 0, flo, fhi, 1u, P.counter, S->n_sm, S->st);
+        S->launches++;
+        if (cudaStreamSynchronize(S->st) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    barrier_ranks(S);
+    if (ok) {
+        unsigned int hf[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpy(hf, P.flags, sizeof(hf), cudaMemcpyDeviceToHost));
+        if (rk > 0 && hf[0] != 1u) ok = 0;
+        if (rk < nr - 1 && hf[1] != 1u) ok = 0;
+    }
+    // every rank must take the same path
+    int neg = ok ? 0 : 1;
+    CUDA_CHECK(cudaMemcpyAsync(S->d_changed, &neg, sizeof(int), cudaMemcpyHostToDevice, S->st));
+    allreduce_max_i32(S, S->d_changed, 1);
+    CUDA_CHECK(cudaMemcpyAsync(&neg, S->d_changed, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CUDA_CHECK(cudaStreamSynchronize(S->st));
+    P.seq = 1;
+    P.on = (neg == 0);
+    if (!P.on) {
+        barrier_ranks(S);
+        peer_teardown(S);
+    }
+    const char* w = getenv("OI_HALO_WAIT");
+    P.spin_wait = (w && std::strcmp(w, "spin") == 0) || driver_wait32() == nullptr;
+    return P.on;
 }
 
 void build_hierarchy(oi_solver* S) {
@@ -596,9 +958,12 @@ void build_mask(oi_solver* S) {
     // they are dead, so the labelling scratch aliases them (no cudaMalloc/cudaFree
     // in the steady-state step): labels -> p, reach bytes -> q, plane bits -> z.
     if (!S->vectors_allocated) {
-        S->x.alloc(g.plane, g.nz); S->r.alloc(g.plane, g.nz); S->p.alloc(g.plane, g.nz);
-        S->q.alloc(g.plane, g.nz);
-        S->r32.alloc(g.plane, g.nz); S->za.alloc(g.plane, g.nz); S->zb.alloc(g.plane, g.nz);
+        // x, p, za, zb may already live in the peer-halo arena (peer_setup)
+        if (!S->x.base) S->x.alloc(g.plane, g.nz, S->st);
+        if (!S->p.base) S->p.alloc(g.plane, g.nz, S->st);
+        if (!S->za.base) S->za.alloc(g.plane, g.nz, S->st);
+        if (!S->zb.base) S->zb.alloc(g.plane, g.nz, S->st);
+        S->r.alloc(g.plane, g.nz, S->st); S->q.alloc(g.plane, g.nz, S->st); S->r32.alloc(g.plane, g.nz, S->st);
         S->vectors_allocated = true;
     }
     int* d_labels = reinterpret_cast<int*>(S->p.p);
@@ -648,8 +1013,8 @@ void build_mask(oi_solver* S) {
         }
     }
 
-    if (!S->active.base) S->active.alloc(g.plane, g.nz);
-    if (!S->flags.base) S->flags.alloc(g.plane, g.nz);
+    if (!S->active.base) S->active.alloc(g.plane, g.nz, S->st);
+    if (!S->flags.base) S->flags.alloc(g.plane, g.nz, S->st);
     oi::build_active(S->d_isphase, d_labels, d_reach, S->active.p, g.nx, g.ny, g.nz, S->d_ull + 0,
                      S->n_sm, S->st); S->launches++;
     halo_exchange_bytes(S, S->active.p, (size_t)g.plane, g.nz);
@@ -725,15 +1090,15 @@ int count_host_field(const T* host, int64_t n, int32_t phase, int64_t* pc, int64
             int dev = 0, n_sm = 148;
             CUDA_CHECK(cudaGetDevice(&dev));
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            CUDA_CHECK(cudaMalloc(&d, (size_t)n * sizeof(T)));
-            CUDA_CHECK(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+            CUDA_CHECK(cmalloc(&d, (size_t)n * sizeof(T)));
+            CUDA_CHECK(cmalloc(&d_cnt, sizeof(unsigned long long)));
             CUDA_CHECK(cudaMemset(d_cnt, 0, sizeof(unsigned long long)));
             CUDA_CHECK(cudaMemcpy(d, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
             if (sizeof(T) == 1) oi::count_phase_u8(reinterpret_cast<const uint8_t*>(d), n, phase, d_cnt, n_sm, 0);
             else oi::count_phase_i32(reinterpret_cast<const int32_t*>(d), n, phase, d_cnt, n_sm, 0);
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaMemcpy(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
-            cudaFree(d); cudaFree(d_cnt);
+            cfree(d); cfree(d_cnt);
         }
         if (pc) *pc = (int64_t)h;
         if (tc) *tc = n;
@@ -747,11 +1112,11 @@ void set_phase_common(oi_solver* S, const T* src, bool src_on_device) {
     T* d_raw = nullptr;
     const T* d_in = src;
     if (!src_on_device) {
-        CUDA_CHECK(cudaMalloc(&d_raw, (size_t)n * sizeof(T)));
+        CUDA_CHECK(cmalloc(&d_raw, (size_t)n * sizeof(T)));
         CUDA_CHECK(cudaMemcpyAsync(d_raw, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, S->st));
         d_in = d_raw;
     }
-    if (!S->d_isphase) CUDA_CHECK(cudaMalloc(&S->d_isphase, (size_t)n));
+    if (!S->d_isphase) CUDA_CHECK(cmalloc(&S->d_isphase, (size_t)n));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull + 4, 0, 2 * sizeof(unsigned long long), S->st));
     if (sizeof(T) == 1) {
         oi::count_phase_u8(reinterpret_cast<const uint8_t*>(d_in), n, S->prm.phase_id, S->d_ull + 4, S->n_sm, S->st);
@@ -769,7 +1134,7 @@ void set_phase_common(oi_solver* S, const T* src, bool src_on_device) {
     CUDA_CHECK(cudaGetLastError());
     S->phase_count_local = (long long)h[0];
     S->nonbinary_local = (long long)h[1];
-    if (d_raw) cudaFree(d_raw);
+    if (d_raw) cfree(d_raw);
     S->mask_built = false;
     S->solved = false;
 }
@@ -810,6 +1175,7 @@ void oi_default_params(oi_params* p) {
     p->mg_degree = 0;
     p->stencil_variant = 0;
     p->flux_polish = 1;
+    p->halo_mode = OI_HALO_AUTO;
     p->comm = nullptr;
 }
 
@@ -906,16 +1272,16 @@ int oi_create(oi_solver** out, const oi_params* p) {
         static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
         S->w_smooth = cheb_weights(deg, deg <= 8 ? lo_tab[deg] : 0.07);
         S->w_coarse = cheb_weights(8, 0.05);
-        CUDA_CHECK(cudaMalloc(&S->d_scal, 16 * sizeof(double)));
-        CUDA_CHECK(cudaMemset(S->d_scal, 0, 16 * sizeof(double)));
+        CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
+        CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));
         long long nb = std::max<long long>(oi::l0_max_blocks(g, S->n_sm), oi::vec_max_blocks(S->n_sm));
         nb = std::max<long long>(nb, (long long)S->n_sm * 8);
-        CUDA_CHECK(cudaMalloc(&S->d_partials, (size_t)nb * 2 * sizeof(double)));
-        CUDA_CHECK(cudaMalloc(&S->d_counter, sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemset(S->d_counter, 0, sizeof(unsigned int)));
-        CUDA_CHECK(cudaMalloc(&S->d_ull, 8 * sizeof(unsigned long long)));
-        CUDA_CHECK(cudaMemset(S->d_ull, 0, 8 * sizeof(unsigned long long)));
-        CUDA_CHECK(cudaMalloc(&S->d_changed, sizeof(int)));
+        CUDA_CHECK(cmalloc(&S->d_partials, (size_t)nb * 2 * sizeof(double)));
+        CUDA_CHECK(cmalloc(&S->d_counter, sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int), S->st));
+        CUDA_CHECK(cmalloc(&S->d_ull, 8 * sizeof(unsigned long long)));
+        CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
+        CUDA_CHECK(cmalloc(&S->d_changed, sizeof(int)));
         CUDA_CHECK(cudaMallocHost(&S->h_pinned, 16 * sizeof(double)));
         S->all_z0.assign(n_ranks, 0);
         S->all_nz.assign(n_ranks, 0);
@@ -923,14 +1289,14 @@ int oi_create(oi_solver** out, const oi_params* p) {
         if (n_ranks > 1) {
             NcclApi& N = nccl_api();
             int* d_tab = nullptr;
-            CUDA_CHECK(cudaMalloc(&d_tab, (size_t)(2 * n_ranks + 2) * sizeof(int)));
+            CUDA_CHECK(cmalloc(&d_tab, (size_t)(2 * n_ranks + 2) * sizeof(int)));
             int mine[2] = {z0, nzl};
             CUDA_CHECK(cudaMemcpyAsync(d_tab, mine, sizeof(mine), cudaMemcpyHostToDevice, S->st));
             NCCL_CHECK(N.AllGather(d_tab, d_tab + 2, 2, ncclInt32, S->comm, S->st));
             std::vector<int> tab(2 * n_ranks);
             CUDA_CHECK(cudaMemcpyAsync(tab.data(), d_tab + 2, tab.size() * sizeof(int), cudaMemcpyDeviceToHost, S->st));
             CUDA_CHECK(cudaStreamSynchronize(S->st));
-            cudaFree(d_tab);
+            cfree(d_tab);
             int expect = 0;
             for (int r = 0; r < n_ranks; ++r) {
                 S->all_z0[r] = tab[2 * r]; S->all_nz[r] = tab[2 * r + 1];
@@ -938,6 +1304,20 @@ int oi_create(oi_solver** out, const oi_params* p) {
                 expect += S->all_nz[r];
             }
             OI_REQUIRE(expect == p->nz, "z-slabs must cover the whole box");
+            // halo path: peer memory unless told otherwise (halo_mode / OI_HALO_MODE=nccl|p2p)
+            int mode = p->halo_mode;
+            if (const char* e = getenv("OI_HALO_MODE")) {
+                if (std::strcmp(e, "nccl") == 0) mode = OI_HALO_NCCL;
+                else if (std::strcmp(e, "p2p") == 0) mode = OI_HALO_PEER;
+            }
+            OI_REQUIRE(mode >= OI_HALO_AUTO && mode <= OI_HALO_PEER, "bad halo_mode");
+            if (mode != OI_HALO_NCCL) {
+                const bool on = peer_setup(S.get());
+                if (!on && mode == OI_HALO_PEER)
+                    throw OiError(OI_ERR_CUDA, "halo_mode = peer but the neighbours' memory cannot be mapped (CUDA IPC)");
+                if (!on && p->verbose > 0)
+                    std::fprintf(stderr, "openimpala_b200: peer halo path unavailable, using NCCL send/recv\n");
+            }
         }
         *out = S.release();
     });
@@ -948,15 +1328,21 @@ int oi_destroy(oi_solver* S) {
     return guarded([&] {
         cudaSetDevice(S->device);
         if (S->st) cudaStreamSynchronize(S->st);
+        if (S->peer.on) {
+            // collective: nobody unmaps or frees while a neighbour may still be storing
+            barrier_ranks(S);
+            peer_teardown(S);
+        }
         free_levels(S);
         free_vectors(S);
         S->active.release(); S->flags.release();
-        if (S->d_isphase) cudaFree(S->d_isphase);
-        if (S->d_scal) cudaFree(S->d_scal);
-        if (S->d_partials) cudaFree(S->d_partials);
-        if (S->d_counter) cudaFree(S->d_counter);
-        if (S->d_ull) cudaFree(S->d_ull);
-        if (S->d_changed) cudaFree(S->d_changed);
+        if (S->peer.arena.base) cfree(S->peer.arena.base);
+        if (S->d_isphase) cfree(S->d_isphase);
+        if (S->d_scal) cfree(S->d_scal);
+        if (S->d_partials) cfree(S->d_partials);
+        if (S->d_counter) cfree(S->d_counter);
+        if (S->d_ull) cfree(S->d_ull);
+        if (S->d_changed) cfree(S->d_changed);
         if (S->h_pinned) cudaFreeHost(S->h_pinned);
         for (auto& e : S->timer) if (e) cudaEventDestroy(e);
         for (auto& e : S->ev) if (e) cudaEventDestroy(e);
@@ -1007,8 +1393,8 @@ int oi_remspot(oi_solver* S, int32_t passes) {
         const Grid& g = S->g;
         const long long n = S->n_local;
         uint8_t *fa = nullptr, *fb = nullptr;
-        CUDA_CHECK(cudaMalloc(&fa, (size_t)n));
-        CUDA_CHECK(cudaMalloc(&fb, (size_t)n));
+        CUDA_CHECK(cmalloc(&fa, (size_t)n));
+        CUDA_CHECK(cmalloc(&fb, (size_t)n));
         for (int pass = 0; pass < passes; ++pass) {    // TortuosityHypre.cpp:269-287
             CUDA_CHECK(cudaMemsetAsync(fa, 0, (size_t)n, S->st));
             const int max_rounds = 4 * (g.nx + g.ny + g.nz) + 16;
@@ -1023,14 +1409,14 @@ int oi_remspot(oi_solver* S, int32_t passes) {
                 std::swap(fa, fb);
             }
             if (changed) {
-                cudaFree(fa); cudaFree(fb);
+                cfree(fa); cfree(fb);
                 throw OiError(OI_ERR_INVALID, "oi_remspot: flip flags did not reach their fixed point");
             }
             oi::remspot_apply(S->d_isphase, fa, n, S->d_ull + 7, S->n_sm, S->st);
             S->launches++;
         }
         CUDA_CHECK(cudaStreamSynchronize(S->st));
-        cudaFree(fa); cudaFree(fb);
+        cfree(fa); cfree(fb);
         S->mask_built = false;
         S->solved = false;
     });
@@ -1130,11 +1516,11 @@ int oi_get_matrix_rows(oi_solver* S, double* host) {
         OI_REQUIRE(S && host && S->mask_built, "oi_get_matrix_rows: mask not built");
         ensure_device(S);
         double* d = nullptr;
-        CUDA_CHECK(cudaMalloc(&d, (size_t)S->n_local * 7 * sizeof(double)));
+        CUDA_CHECK(cmalloc(&d, (size_t)S->n_local * 7 * sizeof(double)));
         oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, d, nullptr, S->st);
         S->launches++;
         copy_out(S, d, host, (size_t)S->n_local * 7);
-        cudaFree(d);
+        cfree(d);
     });
 }
 int oi_apply_operator(oi_solver* S, const double* hx, double* hy) {
@@ -1241,6 +1627,26 @@ int oi_timer_elapsed_ms(oi_solver* S, int32_t a, int32_t b, double* ms) {
         float f = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&f, S->timer[a], S->timer[b]));
         *ms = (double)f;
+    });
+}
+
+int oi_release_cached_memory(int64_t* bytes_released) {
+    return guarded([&] {
+        DevCache& C = dev_cache();
+        const size_t b = C.idle_bytes();
+        {
+            std::lock_guard<std::mutex> lk(C.mu);
+            C.release_idle_locked();
+        }
+        if (bytes_released) *bytes_released = (int64_t)b;
+    });
+}
+
+int oi_halo_info(oi_solver* S, int32_t* mode, int64_t* peer_exchanges) {
+    return guarded([&] {
+        OI_REQUIRE(S, "null handle");
+        if (mode) *mode = S->n_ranks <= 1 ? OI_HALO_AUTO : (S->peer.on ? OI_HALO_PEER : OI_HALO_NCCL);
+        if (peer_exchanges) *peer_exchanges = S->peer.exchanges;
     });
 }
 

@@ -30,11 +30,21 @@ def main():
     comm = capi.Comm(rank, world, idt.cpu().numpy().tobytes(), device=local)
     ok = True
     cases = [((96, 64, 80), 2, 6), ((96, 64, 80), 0, 6), ((64, 100, 36), 1, 5), ((128, 128, 128), 2, 8)]
-    for shape, direction, radius in cases:
+    # every case through the default halo path (peer memory when the ranks can map
+    # each other, which is required on an NVLink box), the first two also through
+    # NCCL send/recv: both must give the single-GPU answer
+    runs = [(c, capi.OI_HALO_AUTO) for c in cases] + [(c, capi.OI_HALO_NCCL) for c in cases[:2]]
+    want_peer = os.environ.get("OI_HALO_MODE", "") != "nccl"
+    for (shape, direction, radius), halo_mode in runs:
         full = synth.sphere_packing_slab(shape, seed=11, radius=radius, solid_target=0.5)
         z0, nzl = capi.slab_partition(shape[0], world)[rank]
         slab = np.ascontiguousarray(full[z0:z0 + nzl])
-        s = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local, z_begin=z0, nz_local=nzl, comm=comm)
+        s = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local, z_begin=z0, nz_local=nzl, comm=comm,
+                        halo_mode=halo_mode)
+        mode_used, _ = s.halo_info()
+        if halo_mode == capi.OI_HALO_AUTO and want_peer and mode_used != capi.OI_HALO_PEER:
+            print(f"rank {rank}: peer halo path not active (mode {mode_used})", flush=True)
+            ok = False
         s.set_phase(slab)
         pc, tc = s.volume_fraction()
         n_active = s.build_mask()
@@ -44,6 +54,7 @@ def main():
         fin, fout, ni, no = s.fluxes()
         tau, _, _ = tau_from_fluxes(fin, fout, n_active / full.size, float(shape[2 - direction]),
                                     float(full.size / shape[2 - direction]), -1.0, 1.0)
+        n_peer = s.halo_info()[1]
         s.close()
         if rank == 0:
             r = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local)
@@ -59,7 +70,7 @@ def main():
             good = ((pc, tc, n_active, ni, no) == (pc1, tc1, n1, ni1, no1) and chk and
                     np.array_equal(mask, mask1[z0:z0 + nzl]) and info.converged and
                     abs(tau - tau1) <= 1e-8 * abs(tau1))
-            print(f"case {shape} dir {direction}: ranks={world} n_active={n_active}/{n1} iters={info.iterations}/"
+            print(f"case {shape} dir {direction} halo={mode_used} peer_exchanges={n_peer}: ranks={world} n_active={n_active}/{n1} iters={info.iterations}/"
                   f"{info1.iterations} tau={tau:.10f}/{tau1:.10f} {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
         else:
