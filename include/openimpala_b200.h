@@ -52,6 +52,14 @@ typedef enum oi_precond { OI_PRECOND_MG = 0, OI_PRECOND_JACOBI = 1 } oi_precond;
  * send/recv.  The environment variable OI_HALO_MODE=nccl|p2p overrides. */
 typedef enum oi_halo_mode { OI_HALO_AUTO = 0, OI_HALO_NCCL = 1, OI_HALO_PEER = 2 } oi_halo_mode;
 
+/* Which linear problem the handle solves.
+ * TORTUOSITY: flow-through Laplace solve of TortuosityHypre (Dirichlet inlet /
+ *   outlet, percolation mask), src/props/TortuosityHypre.cpp.
+ * CELL: the periodic cell problem for the corrector chi_k of the homogenisation
+ *   path, EffectiveDiffusivityHypre (src/props/EffectiveDiffusivityHypre.cpp:104-745,
+ *   src/props/EffDiffFillMtx.F90:109-258); `direction` is k; vlo/vhi are unused. */
+typedef enum oi_problem { OI_PROBLEM_TORTUOSITY = 0, OI_PROBLEM_CELL = 1 } oi_problem;
+
 struct oi_comm;
 
 typedef struct oi_params {
@@ -74,6 +82,7 @@ typedef struct oi_params {
                                   gate (TortuosityHypre.cpp:794-803); 0: stop on
                                   the residual rule alone                          */
     int32_t halo_mode;         /* oi_halo_mode: how ghost planes travel between z-slabs */
+    int32_t problem;           /* oi_problem                                      */
     struct oi_comm* comm;      /* z-slab communicator (oi_comm_create) or NULL for
                                   a single slab; must outlive the handle            */
 } oi_params;
@@ -144,6 +153,12 @@ int oi_solve(oi_solver* h, oi_solve_info* info);
 /* global_fluxes(), TortuosityHypre.cpp:1000-1134 (already x face area). */
 int oi_fluxes(oi_solver* h, double* flux_in, double* flux_out,
               int64_t* n_active_in, int64_t* n_active_out);
+
+/* Cell problem only.  sums3[a] = sum over active cells of the central difference
+ * d(chi_k)/dx_a of the solved corrector (periodic box, chi = 0 in the solid):
+ * the per-direction ingredient of calculate_Deff_tensor_homogenization
+ * (src/props/Diffusion.cpp:60-167): D_eff[a][k] = (delta_ak * n_active - sums3[a]) / N. */
+int oi_cell_gradient_sums(oi_solver* h, double* sums3, int64_t* n_active);
 
 /* checkMatrixProperties(), TortuosityHypre.cpp:896-982: device-side check of the
  * same invariants on the matrix-free rows.  ok = 1 when all pass (global). */

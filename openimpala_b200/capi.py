@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libopenimpala_b200.so")
 OI_OK = 0
 OI_PRECOND_MG, OI_PRECOND_JACOBI = 0, 1
 OI_HALO_AUTO, OI_HALO_NCCL, OI_HALO_PEER = 0, 1, 2
+OI_PROBLEM_TORTUOSITY, OI_PROBLEM_CELL = 0, 1
 
 
 class OiError(RuntimeError):
@@ -36,7 +37,7 @@ class oi_params(C.Structure):
         ("eps", C.c_double),
         ("maxiter", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32),
         ("precond", C.c_int32), ("mg_degree", C.c_int32), ("stencil_variant", C.c_int32),
-        ("flux_polish", C.c_int32), ("halo_mode", C.c_int32),
+        ("flux_polish", C.c_int32), ("halo_mode", C.c_int32), ("problem", C.c_int32),
         ("comm", C.c_void_p),
     ]
 
@@ -72,6 +73,7 @@ _SIGS = {
     "oi_solve": (C.c_int, [_P, C.POINTER(oi_solve_info)]),
     "oi_fluxes": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double),
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "oi_cell_gradient_sums": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "oi_check_matrix_properties": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "oi_get_mask_u8": (C.c_int, [_P, _P]),
     "oi_get_solution": (C.c_int, [_P, _P]),
@@ -201,7 +203,7 @@ class Solver:
                  eps: float = 1e-9, maxiter: int = 200, dx=(1.0, 1.0, 1.0), precond: int = OI_PRECOND_MG,
                  mg_degree: int = 0, stencil_variant: int = 0, flux_polish: int = 1, device: int = -1,
                  z_begin: int = 0, nz_local: int = 0, comm: "Comm | None" = None, verbose: int = 0,
-                 halo_mode: int = OI_HALO_AUTO):
+                 halo_mode: int = OI_HALO_AUTO, problem: int = OI_PROBLEM_TORTUOSITY):
         self._lib = load()
         self._h = _P(None)
         nz, ny, nx = (int(s) for s in shape)
@@ -215,6 +217,7 @@ class Solver:
         p.precond, p.mg_degree, p.stencil_variant = int(precond), int(mg_degree), int(stencil_variant)
         p.flux_polish = int(flux_polish)
         p.halo_mode = int(halo_mode)
+        p.problem = int(problem)
         self._comm = comm                       # keep the communicator alive
         p.comm = comm.handle if comm is not None else None
         self.params = p
@@ -278,6 +281,13 @@ class Solver:
         ni, no = C.c_int64(0), C.c_int64(0)
         _check(self._lib.oi_fluxes(self._h, C.byref(fi), C.byref(fo), C.byref(ni), C.byref(no)))
         return fi.value, fo.value, ni.value, no.value
+
+    def cell_gradient_sums(self):
+        """Cell problem: (sum_active d chi/dx, d chi/dy, d chi/dz), n_active."""
+        sums = (C.c_double * 3)()
+        n = C.c_int64(0)
+        _check(self._lib.oi_cell_gradient_sums(self._h, sums, C.byref(n)))
+        return (sums[0], sums[1], sums[2]), n.value
 
     def check_matrix_properties(self) -> bool:
         ok = C.c_int32(0)

@@ -13,10 +13,9 @@ namespace oi {
 
 namespace {
 
-__device__ __forceinline__ double diag0(uint8_t f, const Grid& g) {
-    return g.cx * (double)__popc(f & 0x03u) + g.cy * (double)__popc(f & 0x0cu) +
-           g.cz * (double)__popc(f & 0x30u);
-}
+// diagonal of a fine row (couplings + sink terms: Dirichlet neighbours, and for the
+// cell problem the faces towards the solid)
+__device__ __forceinline__ double diag0(uint8_t f, const Grid& g) { return row_diag<double>(f, g); }
 
 // level 1 from connectivity bytes
 __global__ void __launch_bounds__(256)
@@ -40,10 +39,13 @@ build_from_flags_kernel(Grid g, const uint8_t* __restrict__ flags, CoarseLevel c
                     sd += diag0(f, g);
                     // +x, +y, +z couplings to UNKNOWN neighbours (Dirichlet
                     // neighbours stay in the diagonal as sink terms)
-                    if ((f & F_XP) && (flags[idx + 1] & F_UNK)) {
+                    // (a set bit at the box edge means a periodic neighbour on the far side)
+                    const long long ixp = (i + 1 < g.nx) ? idx + 1 : idx - i;
+                    const long long iyp = (j + 1 < g.ny) ? idx + g.nx : idx - (long long)j * g.nx;
+                    if ((f & F_XP) && (flags[ixp] & F_UNK)) {
                         if (i + 1 < i1) internal += g.cx; else sx += g.cx;
                     }
-                    if ((f & F_YP) && (flags[idx + g.nx] & F_UNK)) {
+                    if ((f & F_YP) && (flags[iyp] & F_UNK)) {
                         if (j + 1 < j1) internal += g.cy; else sy += g.cy;
                     }
                     if ((f & F_ZP) && (flags[idx + g.plane] & F_UNK)) {
@@ -105,16 +107,19 @@ coarse_stencil_kernel(CoarseLevel L, const mg_t* __restrict__ x, const mg_t* __r
             mg_t acc = (mg_t)d * c;
             // couplings are zero across domain faces, so guarded loads suffice
             const float cxp = L.cxp[idx], cyp = L.cyp[idx], czp = L.czp[idx];
-            if (cxp != 0.f) acc -= (mg_t)cxp * x[idx + 1];
-            if (cyp != 0.f) acc -= (mg_t)cyp * x[idx + L.nx];
+            // (a coupling across a box face exists only when the box is periodic)
+            if (cxp != 0.f) acc -= (mg_t)cxp * x[(i + 1 < L.nx) ? idx + 1 : idx - i];
+            if (cyp != 0.f) acc -= (mg_t)cyp * x[(j + 1 < L.ny) ? idx + L.nx : idx - (long long)j * L.nx];
             if (czp != 0.f) acc -= (mg_t)czp * x[idx + L.plane];
-            if (i > 0) {
-                const float cm = L.cxp[idx - 1];
-                if (cm != 0.f) acc -= (mg_t)cm * x[idx - 1];
+            if (i > 0 || (L.periodic & PER_X)) {
+                const long long im = (i > 0) ? idx - 1 : idx + (L.nx - 1);
+                const float cm = L.cxp[im];
+                if (cm != 0.f) acc -= (mg_t)cm * x[im];
             }
-            if (j > 0) {
-                const float cm = L.cyp[idx - L.nx];
-                if (cm != 0.f) acc -= (mg_t)cm * x[idx - L.nx];
+            if (j > 0 || (L.periodic & PER_Y)) {
+                const long long jm = (j > 0) ? idx - L.nx : idx + (long long)(L.ny - 1) * L.nx;
+                const float cm = L.cyp[jm];
+                if (cm != 0.f) acc -= (mg_t)cm * x[jm];
             }
             {   // k-1 may be the ghost plane (coefficients exchanged at setup)
                 const float cm = L.czp[idx - L.plane];
@@ -148,12 +153,16 @@ coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const flo
         if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
             const float4 c = ld4(x + idx);
             const float4 cxp = ld4(L.cxp + idx), cyp = ld4(L.cyp + idx), czp = ld4(L.czp + idx);
-            const float cxw = (i > 0) ? L.cxp[idx - 1] : 0.f;
-            const float xw = (i > 0) ? x[idx - 1] : 0.f;
-            const float xe = (i + 4 < L.nx) ? x[idx + 4] : 0.f;
-            const float4 cym = (j > 0) ? ld4(L.cyp + idx - L.nx) : zero4;
-            const float4 ys = (j > 0) ? ld4(x + idx - L.nx) : zero4;
-            const float4 yn = (j + 1 < L.ny) ? ld4(x + idx + L.nx) : zero4;
+            const bool px = (L.periodic & PER_X) != 0, py = (L.periodic & PER_Y) != 0;
+            const long long iw = (i > 0) ? idx - 1 : idx + (L.nx - 1);
+            const long long js = (j > 0) ? idx - L.nx : idx + (long long)(L.ny - 1) * L.nx;
+            const long long jn = (j + 1 < L.ny) ? idx + L.nx : idx - (long long)j * L.nx;
+            const float cxw = (i > 0 || px) ? L.cxp[iw] : 0.f;
+            const float xw = (i > 0 || px) ? x[iw] : 0.f;
+            const float xe = (i + 4 < L.nx) ? x[idx + 4] : (px ? x[idx - i] : 0.f);
+            const float4 cym = (j > 0 || py) ? ld4(L.cyp + js) : zero4;
+            const float4 ys = (j > 0 || py) ? ld4(x + js) : zero4;
+            const float4 yn = (j + 1 < L.ny || py) ? ld4(x + jn) : zero4;
             const float4 czm = ld4(L.czp + idx - L.plane);          // k-1 may be the ghost plane
             const float4 zd = ld4(x + idx - L.plane);
             const float4 zu = ld4(x + idx + L.plane);

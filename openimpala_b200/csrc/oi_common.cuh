@@ -42,7 +42,26 @@ struct Grid {
     int z0;                // global index of local plane 0
     long long plane;       // nx*ny
     double cx, cy, cz;     // 1/dx^2, 1/dy^2, 1/dz^2  (TortuosityHypre.cpp:580-582)
+    // Cell problem of the homogenisation path (EffectiveDiffusivityHypre,
+    // src/props/EffDiffFillMtx.F90:109-258): the box is periodic and every active row
+    // has the full diagonal 2(cx+cy+cz) because a face towards the solid adds 1/dx^2
+    // to the diagonal without a coupling (F90:156-165).  Zero / 0.0 for tortuosity.
+    int periodic;          // bit 0: x, bit 1: y, bit 2: z
+    double diag_full;      // > 0: diagonal of every unknown row; 0: sum of its couplings
+    double hx, hy, hz;     // cell sizes (Geometry::CellSize)
 };
+
+enum : int { PER_X = 1, PER_Y = 2, PER_Z = 4 };
+
+// diagonal of an unknown row from its connectivity bits
+template <typename T>
+__device__ __forceinline__ T row_diag(unsigned int f, const Grid& g) {
+    if (g.diag_full > 0.0) return (T)g.diag_full;
+    return (T)g.cx * (T)__popc(f & 0x03u) + (T)g.cy * (T)__popc(f & 0x0cu) + (T)g.cz * (T)__popc(f & 0x30u);
+}
+// x / y index of the -1 / +1 neighbour with periodic wrap; -1 = outside the box
+__device__ __forceinline__ int wrap_lo(int i, int n, bool periodic) { return i > 0 ? i - 1 : (periodic ? n - 1 : -1); }
+__device__ __forceinline__ int wrap_hi(int i, int n, bool periodic) { return i + 1 < n ? i + 1 : (periodic ? 0 : -1); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

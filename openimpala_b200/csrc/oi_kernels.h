@@ -45,6 +45,7 @@ struct CoarseLevel {
     int nzg;                   // global planes at this level
     long long plane;
     int fx, fy, fz;            // coarsening factors from this level to the next
+    int periodic;              // PER_X | PER_Y | PER_Z of the box (cell problem), else 0
     float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
     float* dg;                 // diagonal (0 = empty aggregate)
     mg_t *x, *b, *t;           // solution, rhs, scratch (ghost planes)
@@ -147,6 +148,13 @@ void flux_planes(const Grid& g, const uint8_t* flags, const double* x, int dir, 
 void export_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
                  int n_dir_global, double vlo, double vhi, double* a7, double* rhs,
                  cudaStream_t st);
+// cell problem of the homogenisation path (EffectiveDiffusivityHypre):
+// r += sign * b (r may be null) and out[0] = ||b||^2 ; out[0..2] = sum over active
+// cells of d(chi)/dx, d(chi)/dy, d(chi)/dz by central differences
+void cellp_rhs(const Grid& g, const uint8_t* flags, double* r, int dir, double sign, double* partials,
+               unsigned int* counter, double* out, cudaStream_t st);
+void cellp_grad_sums(const Grid& g, const uint8_t* flags, const double* x, double* partials,
+                     unsigned int* counter, double* out, cudaStream_t st);
 // device-side checkMatrixProperties; bad[0] incremented per violation
 void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
                 int n_dir_global, unsigned long long* bad, cudaStream_t st);

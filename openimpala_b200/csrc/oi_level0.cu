@@ -25,9 +25,7 @@ constexpr int TX = 64, TY = 8;           // CTA tile (cells)
 constexpr int NTHREADS = TX * TY;        // 512
 
 template <typename T>
-__device__ __forceinline__ T diag_of(uint8_t f, const Grid& g) {
-    return (T)g.cx * (T)__popc(f & 0x03u) + (T)g.cy * (T)__popc(f & 0x0cu) + (T)g.cz * (T)__popc(f & 0x30u);
-}
+__device__ __forceinline__ T diag_of(uint8_t f, const Grid& g) { return row_diag<T>(f, g); }
 
 // A*u at one cell from centre + 6 neighbour values.  Written as a sum of
 // differences (row sum 0, checkMatrixProperties TortuosityHypre.cpp:969-971).
@@ -37,7 +35,12 @@ __device__ __forceinline__ T stencil_au(uint8_t f, const Grid& g, T c, T xm, T x
     T ax = ((f & F_XM) ? (c - xm) : z0) + ((f & F_XP) ? (c - xp) : z0);
     T ay = ((f & F_YM) ? (c - ym) : z0) + ((f & F_YP) ? (c - yp) : z0);
     T az = ((f & F_ZM) ? (c - zm) : z0) + ((f & F_ZP) ? (c - zp) : z0);
-    return (T)g.cx * ax + (T)g.cy * ay + (T)g.cz * az;
+    T au = (T)g.cx * ax + (T)g.cy * ay + (T)g.cz * az;
+    // cell problem: faces without a coupling still carry their 1/dx^2 on the diagonal
+    if (g.diag_full > 0.0)
+        au += ((T)g.diag_full - ((T)g.cx * (T)__popc(f & 0x03u) + (T)g.cy * (T)__popc(f & 0x0cu) +
+                                 (T)g.cz * (T)__popc(f & 0x30u))) * c;
+    return au;
 }
 
 template <typename T>
@@ -92,10 +95,15 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict_
     // halo duty: each thread may own one x-halo and one y-halo cell of the tile
     const bool hx_l = (tx == 0), hx_r = (tx == TX - 1);
     const bool hy_t = (ty == 0), hy_b = (ty == TY - 1);
-    const int hi_x = hx_l ? i - 1 : i + 1;
-    const int hj_y = hy_t ? j - 1 : j + 1;
-    const bool hx_ok = (hx_l || hx_r) && (j < g.ny) && hi_x >= 0 && hi_x < g.nx;
-    const bool hy_ok = (hy_t || hy_b) && (i < g.nx) && hj_y >= 0 && hj_y < g.ny;
+    // (a partial edge tile of a periodic box is handled below: the last in-box column /
+    // row takes its wrapped neighbour straight from global memory)
+    const int hi_x = (i < g.nx) ? (hx_l ? wrap_lo(i, g.nx, g.periodic & PER_X) : wrap_hi(i, g.nx, g.periodic & PER_X)) : -1;
+    const int hj_y = (j < g.ny) ? (hy_t ? wrap_lo(j, g.ny, g.periodic & PER_Y) : wrap_hi(j, g.ny, g.periodic & PER_Y)) : -1;
+    const bool hx_ok = (hx_l || hx_r) && (j < g.ny) && hi_x >= 0;
+    const bool hy_ok = (hy_t || hy_b) && (i < g.nx) && hj_y >= 0;
+    // last in-box column / row of a partial tile: its +x / +y neighbour is not a halo slot
+    const bool edge_x = (g.periodic & PER_X) && i == g.nx - 1 && !hx_r && j < g.ny;
+    const bool edge_y = (g.periodic & PER_Y) && j == g.ny - 1 && !hy_b && i < g.nx;
 
     const long long col = (long long)j * g.nx + i;
     const long long colhx = (long long)j * g.nx + hi_x;
@@ -148,8 +156,12 @@ l0_zmarch_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict_
         if (inb) {
             T o = 0;
             if (f_c & F_UNK) {
-                const T xm = tile[buf][ty + 1][tx], xp = tile[buf][ty + 1][tx + 2];
-                const T ym = tile[buf][ty][tx + 1], yp = tile[buf][ty + 2][tx + 1];
+                const T xm = tile[buf][ty + 1][tx];
+                T xp = tile[buf][ty + 1][tx + 2];
+                const T ym = tile[buf][ty][tx + 1];
+                T yp = tile[buf][ty + 2][tx + 1];
+                if (edge_x) xp = load_val<T, ADDC>(u, flags, (long long)k * g.plane + (long long)j * g.nx, 0, j, k, cr);
+                if (edge_y) yp = load_val<T, ADDC>(u, flags, (long long)k * g.plane + i, i, 0, k, cr);
                 const T au = stencil_au<T>(f_c, g, v_c, xm, xp, ym, yp, v_m, v_p);
                 if (MODE == 0) {
                     o = w * au;
@@ -215,10 +227,14 @@ l0_gather_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict_
         if (f & F_UNK) {
             const T z0 = 0;
             const T c = load_val<T, ADDC>(u, flags, idx, i, j, k, cr);
-            const T xm = (f & F_XM) ? load_val<T, ADDC>(u, flags, idx - 1, i - 1, j, k, cr) : z0;
-            const T xp = (f & F_XP) ? load_val<T, ADDC>(u, flags, idx + 1, i + 1, j, k, cr) : z0;
-            const T ym = (f & F_YM) ? load_val<T, ADDC>(u, flags, idx - g.nx, i, j - 1, k, cr) : z0;
-            const T yp = (f & F_YP) ? load_val<T, ADDC>(u, flags, idx + g.nx, i, j + 1, k, cr) : z0;
+            // (set bits imply an in-box or wrapped neighbour)
+            const int im = wrap_lo(i, g.nx, true), ip = wrap_hi(i, g.nx, true);
+            const int jm = wrap_lo(j, g.ny, true), jp = wrap_hi(j, g.ny, true);
+            const long long row = idx - i, colk = idx - (long long)j * g.nx;
+            const T xm = (f & F_XM) ? load_val<T, ADDC>(u, flags, row + im, im, j, k, cr) : z0;
+            const T xp = (f & F_XP) ? load_val<T, ADDC>(u, flags, row + ip, ip, j, k, cr) : z0;
+            const T ym = (f & F_YM) ? load_val<T, ADDC>(u, flags, colk + (long long)jm * g.nx, i, jm, k, cr) : z0;
+            const T yp = (f & F_YP) ? load_val<T, ADDC>(u, flags, colk + (long long)jp * g.nx, i, jp, k, cr) : z0;
             const T zm = (f & F_ZM) ? load_val<T, ADDC>(u, flags, idx - g.plane, i, j, k - 1, cr) : z0;
             const T zp = (f & F_ZP) ? load_val<T, ADDC>(u, flags, idx + g.plane, i, j, k + 1, cr) : z0;
             const T au = stencil_au<T>(f, g, c, xm, xp, ym, yp, zm, zp);

@@ -17,7 +17,7 @@
 //     register window over the column are compile-time constants;
 //   * no face selects: every vector A is applied to is zero on inactive cells
 //     (x0, p, z are built that way and the updates preserve it; out-of-box halo
-//     cells are zero-filled by cp.async), so
+//     cells are zero-filled by cp.async, or wrapped when the box is periodic), so
 //         (A u)_c = d_c u_c - cx (u_w + u_e) - cy (u_s + u_n) - cz (u_d + u_u)
 //     with d_c and 1/d_c looked up by the 6 face bits in a 64-entry table;
 //   * the z neighbours travel in registers (one centre LDS per plane, not three).
@@ -96,7 +96,7 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
     const T cx = (T)g.cx, cy = (T)g.cy, cz = (T)g.cz;
 
     if (tid < 64) {
-        const T d = cx * (T)__popc(tid & 0x03) + cy * (T)__popc(tid & 0x0c) + cz * (T)__popc(tid & 0x30);
+        const T d = row_diag<T>((unsigned int)tid, g);
         dtab[tid] = d;
         dtab[64 + tid] = d > (T)0 ? (T)1 / d : (T)0;
     }
@@ -104,14 +104,24 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
     // halo duties
     const bool hw = (tx == 0), he = (tx == C::XT - 1);
     const bool hs = (ty == 0), hn = (ty == TY - 1);
-    const int iw = i - 1, ie = i + CPT, js = j - 1, jn = j + 1;
+    // (periodic box: the halo of an edge tile comes from the opposite side)
+    const int iw = (i < g.nx) ? wrap_lo(i, g.nx, g.periodic & PER_X) : -1;
+    const int ie = (i + CPT < g.nx) ? i + CPT : ((i < g.nx && (g.periodic & PER_X)) ? 0 : -1);
+    const int js = (j < g.ny) ? wrap_lo(j, g.ny, g.periodic & PER_Y) : -1;
+    const int jn = (j < g.ny) ? wrap_hi(j, g.ny, g.periodic & PER_Y) : -1;
     const bool hw_ok = hw && (j < g.ny) && iw >= 0;
-    const bool he_ok = he && (j < g.ny) && ie < g.nx;
+    const bool he_ok = he && (j < g.ny) && ie >= 0;
     const bool hs_ok = hs && (i < g.nx) && js >= 0;
-    const bool hn_ok = hn && (i < g.nx) && jn < g.ny;
+    const bool hn_ok = hn && (i < g.nx) && jn >= 0;
 
     const long long col = inb ? (long long)j * g.nx + i : 0;
-    const T* u_own = u + col;
+    // periodic box, partial edge tile: the first cell group / row past the edge stands in
+    // for the east / north halo and loads the wrapped column 0 / row 0
+    const bool wrap_col = (g.periodic & PER_X) && i == g.nx;
+    const bool wrap_row = (g.periodic & PER_Y) && j == g.ny;
+    const int il = wrap_col ? 0 : i, jl = wrap_row ? 0 : j;
+    const bool ld_ok = (il < g.nx) && (jl < g.ny);
+    const T* u_own = u + (ld_ok ? (long long)jl * g.nx + il : 0);
     const T* u_w = u + (hw_ok ? (long long)j * g.nx + iw : 0);
     const T* u_e = u + (he_ok ? (long long)j * g.nx + ie : 0);
     const T* u_s = u + (hs_ok ? (long long)js * g.nx + i : 0);
@@ -127,7 +137,7 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
     // rhs and connectivity bytes only exist for planes k0 .. k1-1
     auto issue = [&](long long poff, int st, bool interior) {
         T* S = us + st * C::U_STAGE;
-        cp_async16(S + c_off, u_own + poff, inb);
+        cp_async16(S + c_off, u_own + poff, ld_ok);
         if (hw) cp_async_small<(int)sizeof(T)>(S + (ty + 1) * PITCH + CPT - 1, u_w + poff, hw_ok);
         if (he) cp_async_small<(int)sizeof(T)>(S + (ty + 1) * PITCH + CPT + TX, u_e + poff, he_ok);
         if (hs) cp_async16(S + CPT + CPT * tx, u_s + poff, hs_ok);

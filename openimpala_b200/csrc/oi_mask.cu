@@ -243,14 +243,19 @@ build_flags_kernel(Grid g, const uint8_t* __restrict__ active, uint8_t* __restri
             const int j = (int)((idx / g.nx) % g.ny);
             const int k = (int)(idx / g.plane);
             const int d = dir_index(dir, i, j, g.z0 + k);
-            if (d == 0) { f = F_DIR; ++c_in; }                       // F90:193-197
-            else if (d == n_dir - 1) { f = F_DIR; ++c_out; }         // F90:198-202
+            // cell problem (diag_full > 0): no Dirichlet planes, every active cell is a row
+            const bool cellp = g.diag_full > 0.0;
+            if (!cellp && d == 0) { f = F_DIR; ++c_in; }             // F90:193-197
+            else if (!cellp && d == n_dir - 1) { f = F_DIR; ++c_out; }   // F90:198-202
             else {
-                f = F_UNK;                                           // F90:126-166
-                if (i > 0 && active[idx - 1]) f |= F_XM;
-                if (i + 1 < g.nx && active[idx + 1]) f |= F_XP;
-                if (j > 0 && active[idx - g.nx]) f |= F_YM;
-                if (j + 1 < g.ny && active[idx + g.nx]) f |= F_YP;
+                f = F_UNK;                                           // F90:126-166 / EffDiffFillMtx.F90:150-220
+                const int im = wrap_lo(i, g.nx, g.periodic & PER_X), ip = wrap_hi(i, g.nx, g.periodic & PER_X);
+                const int jm = wrap_lo(j, g.ny, g.periodic & PER_Y), jp = wrap_hi(j, g.ny, g.periodic & PER_Y);
+                const long long row = idx - i, colk = idx - (long long)j * g.nx;
+                if (im >= 0 && active[row + im]) f |= F_XM;
+                if (ip >= 0 && active[row + ip]) f |= F_XP;
+                if (jm >= 0 && active[colk + (long long)jm * g.nx]) f |= F_YM;
+                if (jp >= 0 && active[colk + (long long)jp * g.nx]) f |= F_YP;
                 // z neighbours: ghost planes of `active` hold the neighbour slab's
                 // plane, or 0 outside the global box
                 if (active[idx - g.plane]) f |= F_ZM;
@@ -338,11 +343,42 @@ flux_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict_
 }
 
 // ------------------------------------------------------------------ rows / checks
+// rhs of the cell problem for chi_dir at an active cell (EffDiffFillMtx.F90:150-234,
+// same operation order): -(D_p - D_m)/(2 dx) plus +-1/dx for each face of that
+// direction that looks at the solid.
+__device__ __forceinline__ double cellp_rhs_at(const Grid& g, uint8_t f, int dir) {
+    if (!(f & F_UNK)) return 0.0;
+    const double h = dir == 0 ? g.hx : (dir == 1 ? g.hy : g.hz);
+    const uint8_t bm = dir == 0 ? F_XM : (dir == 1 ? F_YM : F_ZM);
+    const uint8_t bp = dir == 0 ? F_XP : (dir == 1 ? F_YP : F_ZP);
+    const double dm = (f & bm) ? 1.0 : 0.0, dp = (f & bp) ? 1.0 : 0.0;
+    double flux = 0.0;
+    if (!(f & bm)) flux = flux + (1.0 / h);
+    if (!(f & bp)) flux = flux - (1.0 / h);
+    const double div = -(dp - dm) * (1.0 / (2.0 * h));
+    return div + flux;
+}
+
 __device__ __forceinline__ void make_row(const Grid& g, uint8_t f, int d, int n_dir, double vlo,
-                                         double vhi, double (&a)[7], double& rhs) {
+                                         double vhi, double (&a)[7], double& rhs, int dir = 0) {
 #pragma unroll
     for (int s = 0; s < 7; ++s) a[s] = 0.0;
     rhs = 0.0;
+    if (g.diag_full > 0.0) {                         // EffDiffFillMtx.F90:124-236
+        if (f & F_UNK) {
+            if (f & F_XM) a[1] = -g.cx;
+            if (f & F_XP) a[2] = -g.cx;
+            if (f & F_YM) a[3] = -g.cy;
+            if (f & F_YP) a[4] = -g.cy;
+            if (f & F_ZM) a[5] = -g.cz;
+            if (f & F_ZP) a[6] = -g.cz;
+            a[0] = g.cx + g.cx + g.cy + g.cy + g.cz + g.cz;
+            rhs = cellp_rhs_at(g, f, dir);
+        } else {
+            a[0] = 1.0;
+        }
+        return;
+    }
     if (f & F_UNK) {
         double dg = 0.0;
         if (f & F_XM) { a[1] = -g.cx; dg += g.cx; }
@@ -368,7 +404,7 @@ export_rows_kernel(Grid g, const uint8_t* __restrict__ flags, int dir, int n_dir
         const int j = (int)((idx / g.nx) % g.ny);
         const int k = (int)(idx / g.plane);
         double a[7], r;
-        make_row(g, flags[idx], dir_index(dir, i, j, g.z0 + k), n_dir, vlo, vhi, a, r);
+        make_row(g, flags[idx], dir_index(dir, i, j, g.z0 + k), n_dir, vlo, vhi, a, r, dir);
         if (a7) {
 #pragma unroll
             for (int s = 0; s < 7; ++s) a7[idx * 7 + s] = a[s];
@@ -390,11 +426,12 @@ check_rows_kernel(Grid g, const uint8_t* __restrict__ flags, const uint8_t* __re
         const int k = (int)(idx / g.plane);
         const int d = dir_index(dir, i, j, g.z0 + k);
         double a[7], r;
-        make_row(g, flags[idx], d, n_dir, 0.25, 0.75, a, r);
+        make_row(g, flags[idx], d, n_dir, 0.25, 0.75, a, r, dir);
         bool ok = true;
         for (int s = 0; s < 7; ++s) ok = ok && isfinite(a[s]);
         const bool act = active[idx] != 0;
-        const bool dirichlet = act && (d == 0 || d == n_dir - 1);     // :950-956
+        const bool cellp = g.diag_full > 0.0;
+        const bool dirichlet = !cellp && act && (d == 0 || d == n_dir - 1);     // :950-956
         double off = 0.0;
         for (int s = 1; s < 7; ++s) off = fmax(off, fabs(a[s]));
         if (!act) {                                                   // :957-960
@@ -405,13 +442,18 @@ check_rows_kernel(Grid g, const uint8_t* __restrict__ flags, const uint8_t* __re
         } else {                                                      // :966-972
             double row = 0.0;
             for (int s = 0; s < 7; ++s) row += a[s];
-            ok = ok && (a[0] > tol) && fabs(r) <= tol && fabs(row) <= tol;
+            // tortuosity rows sum to zero; cell-problem rows are weakly diagonally dominant
+            if (!cellp) ok = ok && (a[0] > tol) && fabs(r) <= tol && fabs(row) <= tol;
+            else ok = ok && (a[0] > tol) && row >= -tol && isfinite(r);
             // and the stored couplings must mirror the active neighbours
             uint8_t e = F_UNK;
-            if (i > 0 && active[idx - 1]) e |= F_XM;
-            if (i + 1 < g.nx && active[idx + 1]) e |= F_XP;
-            if (j > 0 && active[idx - g.nx]) e |= F_YM;
-            if (j + 1 < g.ny && active[idx + g.nx]) e |= F_YP;
+            const int im = wrap_lo(i, g.nx, g.periodic & PER_X), ip = wrap_hi(i, g.nx, g.periodic & PER_X);
+            const int jm = wrap_lo(j, g.ny, g.periodic & PER_Y), jp = wrap_hi(j, g.ny, g.periodic & PER_Y);
+            const long long rowi = idx - i, colk = idx - (long long)j * g.nx;
+            if (im >= 0 && active[rowi + im]) e |= F_XM;
+            if (ip >= 0 && active[rowi + ip]) e |= F_XP;
+            if (jm >= 0 && active[colk + (long long)jm * g.nx]) e |= F_YM;
+            if (jp >= 0 && active[colk + (long long)jp * g.nx]) e |= F_YP;
             if (active[idx - g.plane]) e |= F_ZM;
             if (active[idx + g.plane]) e |= F_ZP;
             ok = ok && (e == flags[idx]);
@@ -422,7 +464,63 @@ check_rows_kernel(Grid g, const uint8_t* __restrict__ flags, const uint8_t* __re
     if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, (unsigned long long)nbad);
 }
 
+// ------------------------------------------------------------------ cell problem (homogenisation)
+// r += sign * b with b the rhs of the chi_dir cell problem (r may be null), and
+// out[0] = sum b^2 (HYPRE's stop rule is relative to ||b||_2).
+__global__ void __launch_bounds__(BT)
+cellp_rhs_kernel(Grid g, const uint8_t* __restrict__ flags, double* __restrict__ r, int dir, double sign,
+                 double* partials, unsigned int* counter, double* out) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    double acc = 0.0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        const double b = cellp_rhs_at(g, flags[idx], dir);
+        if (b != 0.0) {
+            if (r) r[idx] += sign * b;
+            acc += b * b;
+        }
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, partials, counter, out);
+}
+
+// out[a] = sum over active cells of the central difference of chi along axis a
+// (calculate_Deff_tensor_homogenization, src/props/Diffusion.cpp:115-131); chi is zero
+// in the solid and the box is periodic (z through the ghost planes).
+__global__ void __launch_bounds__(BT)
+cellp_grad_sums_kernel(Grid g, const uint8_t* __restrict__ flags, const double* __restrict__ x,
+                       double* partials, unsigned int* counter, double* out) {
+    const long long n = (long long)g.nz * g.plane;
+    const long long stride = (long long)gridDim.x * BT;
+    const double i2x = 1.0 / (2.0 * g.hx), i2y = 1.0 / (2.0 * g.hy), i2z = 1.0 / (2.0 * g.hz);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (long long idx = (long long)blockIdx.x * BT + threadIdx.x; idx < n; idx += stride) {
+        if (!(flags[idx] & F_UNK)) continue;
+        const int i = (int)(idx % g.nx);
+        const int j = (int)((idx / g.nx) % g.ny);
+        const int im = wrap_lo(i, g.nx, true), ip = wrap_hi(i, g.nx, true);
+        const int jm = wrap_lo(j, g.ny, true), jp = wrap_hi(j, g.ny, true);
+        const long long row = idx - i, colk = idx - (long long)j * g.nx;
+        sx += (x[row + ip] - x[row + im]) * i2x;
+        sy += (x[colk + (long long)jp * g.nx] - x[colk + (long long)jm * g.nx]) * i2y;
+        sz += (x[idx + g.plane] - x[idx - g.plane]) * i2z;
+    }
+    double v[3] = {sx, sy, sz};
+    grid_reduce<3>(v, partials, counter, out);
+}
+
 }  // namespace
+
+void cellp_rhs(const Grid& g, const uint8_t* flags, double* r, int dir, double sign, double* partials,
+               unsigned int* counter, double* out, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    cellp_rhs_kernel<<<nblocks(n, 148, 4), BT, 0, st>>>(g, flags, r, dir, sign, partials, counter, out);
+}
+void cellp_grad_sums(const Grid& g, const uint8_t* flags, const double* x, double* partials,
+                     unsigned int* counter, double* out, cudaStream_t st) {
+    const long long n = (long long)g.nz * g.plane;
+    cellp_grad_sums_kernel<<<nblocks(n, 148, 4), BT, 0, st>>>(g, flags, x, partials, counter, out);
+}
 
 // ------------------------------------------------------------------ launchers
 void count_phase_u8(const uint8_t* f, long long n, int phase, unsigned long long* out, int n_sm, cudaStream_t st) {

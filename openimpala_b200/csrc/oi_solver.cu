@@ -308,11 +308,16 @@ struct oi_solver {
     ncclComm_t comm = nullptr;
     std::vector<int> all_z0, all_nz;   // slab table (every rank)
     PeerHalo peer;                     // peer-memory halo exchange (n_ranks > 1)
+    // OI_PROFILE=1: CUDA-event marks at phase boundaries of the solve, summed per phase
+    bool prof_on = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
+    std::vector<cudaEvent_t> prof_pool;
     // setup state
     uint8_t* d_isphase = nullptr;      // [n_local]
     Field<uint8_t> active, flags;
     long long phase_count_local = -1, nonbinary_local = 0;
     long long n_active = -1, n_in = 0, n_out = 0;
+    double cellp_b2 = 0.0;             // ||b||^2 of the cell problem
     bool mask_built = false, hierarchy_built = false, solved = false;
     bool levels_planned = false, levels_allocated = false, vectors_allocated = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -411,7 +416,15 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
 
 void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long long nz) {
     // send plane 0 down / plane nz-1 up; receive into plane -1 / plane nz
-    if (S->n_ranks <= 1) return;
+    if (S->n_ranks <= 1) {
+        if (S->g.periodic & oi::PER_Z) {      // periodic box on one slab: wrap the ghost planes locally
+            char* q = static_cast<char*>(plane0);
+            CUDA_CHECK(cudaMemcpyAsync(q - plane_bytes, q + plane_bytes * (size_t)(nz - 1), plane_bytes,
+                                       cudaMemcpyDeviceToDevice, S->st));
+            CUDA_CHECK(cudaMemcpyAsync(q + plane_bytes * (size_t)nz, q, plane_bytes, cudaMemcpyDeviceToDevice, S->st));
+        }
+        return;
+    }
     if (halo_exchange_peer(S, static_cast<char*>(plane0), plane_bytes, nz)) return;
     NcclApi& N = nccl_api();
     char* p0 = static_cast<char*>(plane0);
@@ -470,6 +483,37 @@ L0Args l0args(oi_solver* S, const void* u, const void* b, void* out, double w, d
     return a;
 }
 
+// phase profile (OI_PROFILE=1): the time from one mark to the next is charged to the
+// phase named by the earlier mark
+inline void prof_mark(oi_solver* S, const char* phase) {
+    if (!S->prof_on) return;
+    cudaEvent_t e;
+    if (!S->prof_pool.empty()) { e = S->prof_pool.back(); S->prof_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, S->st);
+    S->prof_marks.emplace_back(phase, e);
+}
+void prof_report(oi_solver* S, int iterations) {
+    if (!S->prof_on || S->prof_marks.size() < 2) return;
+    cudaEventSynchronize(S->prof_marks.back().second);
+    std::vector<std::pair<std::string, double>> acc;
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < S->prof_marks.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, S->prof_marks[i].second, S->prof_marks[i + 1].second);
+        total += ms;
+        bool found = false;
+        for (auto& a : acc) if (a.first == S->prof_marks[i].first) { a.second += ms; found = true; break; }
+        if (!found) acc.emplace_back(S->prof_marks[i].first, (double)ms);
+    }
+    std::fprintf(stderr, "[oi profile] rank %d: %d iterations, %.3f ms marked\n", S->rank, iterations, total);
+    for (auto& a : acc)
+        std::fprintf(stderr, "[oi profile] rank %d   %-22s %9.3f ms  %5.1f%%  %8.3f ms/iter\n", S->rank,
+                     a.first.c_str(), a.second, 100.0 * a.second / total, a.second / std::max(1, iterations));
+    for (auto& m : S->prof_marks) S->prof_pool.push_back(m.second);
+    S->prof_marks.clear();
+}
+
 struct L0Info { int fx, fy, fz; };
 inline L0Info l0info(const oi_solver* S) { return L0Info{S->fx0, S->fy0, S->fz0}; }
 
@@ -519,6 +563,7 @@ void plan_hierarchy(oi_solver* S) {
         h.L.nx = nx; h.L.ny = ny; h.L.nz = nz[rk]; h.L.z0 = z0[rk]; h.L.nzg = nzg;
         h.L.plane = (long long)nx * ny;
         h.L.fx = h.L.fy = h.L.fz = 1;
+        h.L.periodic = S->g.periodic;
     }
     S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
     S->levels_planned = true;
@@ -704,6 +749,8 @@ void coarse_cycle(oi_solver* S, size_t l) {
     const int deg = (int)w.size();
     mg_t* cur = L.t;
     mg_t* oth = L.x;
+    static const char* lvl_names[] = {"mg level 1", "mg level 2", "mg level 3", "mg level 4", "mg levels 5+"};
+    prof_mark(S, lvl_names[l < 4 ? l : 4]);
     oi::coarse_jacobi_first(L, L.b, cur, w[0], S->st); S->launches++;
     for (int s = 1; s < deg; ++s) {
         haloL(S, L, cur);
@@ -716,6 +763,7 @@ void coarse_cycle(oi_solver* S, size_t l) {
         oi::coarse_residual(L, cur, L.b, oth, S->st); S->launches++;
         oi::coarse_restrict(L, oth, hn.L, hn.L.b, S->st); S->launches++;
         coarse_cycle(S, l + 1);
+        prof_mark(S, lvl_names[l < 4 ? l : 4]);
         oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
         for (int s = 0; s < deg; ++s) {
             haloL(S, L, cur);
@@ -746,6 +794,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         if (dot_out) allreduce_sum_f64(S, dot_out, 1);
         return;
     }
+    prof_mark(S, "l0 pre-smooth");
     if (!first_done) { oi::vec_to_mg(n, S->r32.p, S->r.p, S->n_sm, S->st); S->launches++; }
     const mg_t* rhs = S->r32.p;
     const int variant = S->prm.stencil_variant;
@@ -768,6 +817,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     }
     if (have_coarse) {
         HostLevel& h1 = S->levels[0];
+        prof_mark(S, "l0 residual+restrict");
         halo0(S, cur);
         {
             L0Args a = l0args(S, cur, rhs, h1.L.b, 0.0, nullptr);
@@ -785,13 +835,14 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             }
         }
         coarse_cycle(S, 0);
+        prof_mark(S, "l0 prolong+post-smooth");
         haloL(S, h1.L, h1.L.x);
         for (int s = 0; s < deg; ++s) {
             const bool dot = (s == deg - 1) && dot_out;
             L0Args a = l0args(S, cur, rhs, oth, w[deg - 1 - s], dot_out);
             a.ec = h1.L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
             bool addc = (s == 0);
-            if (addc && variant == 0 && oi::ring_supported(a, 1)) {
+            if (addc && ((variant == 0 && oi::ring_supported(a, 1)) || S->g.periodic)) {
                 // ring kernels take the field as is: apply the correction first
                 L0Args pa = a;
                 pa.out = cur;
@@ -809,6 +860,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         oi::vec_dot(n, S->r.p, S->q.p, S->d_partials, S->d_counter, dot_out, S->n_sm, S->st); S->launches += 2;
     }
     S->zres = cur;
+    prof_mark(S, "allreduce r.z");
     if (dot_out) allreduce_sum_f64(S, dot_out, 1);
 }
 
@@ -839,6 +891,11 @@ double true_residual(oi_solver* S) {
     halo0(S, S->x.p);
     L0Args a = l0args(S, S->x.p, nullptr, S->r.p, -1.0, nullptr);
     oi::l0_apply(a, false, S->prm.stencil_variant, S->st); S->launches++;
+    if (S->prm.problem == OI_PROBLEM_CELL) {     // r = b - A chi
+        oi::cellp_rhs(S->g, S->flags.p, S->r.p, S->prm.direction, 1.0, S->d_partials, S->d_counter,
+                      S->d_scal + 7, S->st);
+        S->launches++;
+    }
     double* d = S->d_scal + 2;
     oi::vec_dot(S->n_local, S->r.p, S->r.p, S->d_partials, S->d_counter, d, S->n_sm, S->st);
     S->launches++;
@@ -853,9 +910,17 @@ void run_solve(oi_solver* S) {
     info.iterations = 0;
     info.rel_residual = std::nan("");
     const double vlo = S->prm.vlo, vhi = S->prm.vhi;
-    const double bnorm = std::sqrt((double)S->n_in * vlo * vlo + (double)S->n_out * vhi * vhi);
+    const bool cellp = (S->prm.problem == OI_PROBLEM_CELL);
+    const double bnorm = cellp ? std::sqrt(S->cellp_b2)
+                               : std::sqrt((double)S->n_in * vlo * vlo + (double)S->n_out * vhi * vhi);
     info.b_norm = bnorm;
-    if (S->n_active <= 0) { info.converged = 0; return; }
+    if (S->n_active <= 0) {
+        // tortuosity: nothing percolates -> not converged (value() returns NaN);
+        // cell problem: chi = 0, converged (EffectiveDiffusivityHypre.cpp:186-196)
+        info.converged = cellp ? 1 : 0;
+        if (cellp) info.rel_residual = 0.0;
+        return;
+    }
 
     for (auto& e : S->ev) if (!e) CUDA_CHECK(cudaEventCreate(&e));
     cudaEvent_t e0 = S->ev[0], e1 = S->ev[1], e2 = S->ev[2];
@@ -868,6 +933,7 @@ void run_solve(oi_solver* S) {
     double* sc = S->d_scal;   // [0]=rz [1]=pq [2]=rr [3]=rz_new
     double* d_rz = sc + 0; double* d_pq = sc + 1; double* d_rr = sc + 2; double* d_rzn = sc + 3;
 
+    prof_mark(S, "setup/restart/checks");
     double rr = true_residual(S);
     const double r0 = std::sqrt(rr);
     // HYPRE: ||r|| <= max(atol, eps*||b||), ||b|| = 0 -> relative to ||r0||
@@ -885,10 +951,13 @@ void run_solve(oi_solver* S) {
             oi::vec_from_mg(n, S->p.p, S->zres, S->n_sm, S->st); S->launches++;
             while (it < S->prm.maxiter) {
                 ++it;
+                prof_mark(S, "apply q=Ap (+halo)");
                 halo0(S, S->p.p);
                 L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, d_pq);
                 oi::l0_apply(a, true, variant, S->st); S->launches++;       // q = A p, pq = p.q
+                prof_mark(S, "allreduce p.q");
                 allreduce_sum_f64(S, d_pq, 1);
+                prof_mark(S, "axpy2+dot+first sweep");
                 const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
                 if (fuse_first)
                     oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->r.p, S->p.p, S->q.p, S->r32.p,
@@ -898,15 +967,18 @@ void run_solve(oi_solver* S) {
                     oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
                                       S->d_counter, d_rr, S->n_sm, S->st);
                 S->launches++;
+                prof_mark(S, "allreduce r.r + readback");
                 allreduce_sum_f64(S, d_rr, 1);
                 rr = read_scalar(S, d_rr);
                 if (!std::isfinite(rr)) { fail = true; break; }
                 if (std::sqrt(rr) <= tol) { converged = true; break; }
                 apply_precond(S, d_rzn, fuse_first);
+                prof_mark(S, "xpby");
                 oi::vec_xpby(n, S->p.p, S->zres, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
                 std::swap(d_rz, d_rzn);
             }
             if (fail || !converged) break;
+            prof_mark(S, "setup/restart/checks");
             // confirm on the true residual (recurrence drift)
             rr = true_residual(S);
             if (!(std::sqrt(rr) <= tol * 1.0000001)) {
@@ -916,7 +988,7 @@ void run_solve(oi_solver* S) {
             }
         }
         // optional flux polish: stay well inside the reference's 1e-6 conservation gate
-        if (S->prm.flux_polish && polish_rounds < 4 && it < S->prm.maxiter && rr > 0.0) {
+        if (S->prm.flux_polish && !cellp && polish_rounds < 4 && it < S->prm.maxiter && rr > 0.0) {
             double fin, fout;
             compute_fluxes(S, &fin, &fout);
             const double avg = 0.5 * (std::fabs(fin) + std::fabs(fout));
@@ -930,8 +1002,10 @@ void run_solve(oi_solver* S) {
         }
         break;
     }
+    prof_mark(S, "end");
     CUDA_CHECK(cudaEventRecord(e2, S->st));
     CUDA_CHECK(cudaEventSynchronize(e2));
+    prof_report(S, it);
     float ms01 = 0, ms12 = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms01, e0, e1));
     CUDA_CHECK(cudaEventElapsedTime(&ms12, e1, e2));
@@ -947,6 +1021,28 @@ void run_solve(oi_solver* S) {
 }
 
 // ------------------------------------------------------------------ mask
+// Cell problem (EffectiveDiffusivityHypre::generateActiveMask + setupMatrixEquation,
+// src/props/EffectiveDiffusivityHypre.cpp:213-330, 425-520): the mask is phase == id,
+// no percolation filter; the box is periodic; chi starts from zero.
+void build_mask_cell_problem(oi_solver* S) {
+    const Grid& g = S->g;
+    const long long n = S->n_local;
+    if (!S->active.base) S->active.alloc(g.plane, g.nz, S->st);
+    if (!S->flags.base) S->flags.alloc(g.plane, g.nz, S->st);
+    CUDA_CHECK(cudaMemcpyAsync(S->active.p, S->d_isphase, (size_t)n, cudaMemcpyDeviceToDevice, S->st));
+    halo_exchange_bytes(S, S->active.p, (size_t)g.plane, g.nz);
+    CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
+    oi::build_flags(g, S->active.p, S->flags.p, S->prm.direction, S->d_ull + 1, S->st); S->launches++;
+    halo_exchange_bytes(S, S->flags.p, (size_t)g.plane, g.nz);
+    CUDA_CHECK(cudaMemsetAsync(S->x.base, 0, S->x.count * sizeof(double), S->st));
+    oi::cellp_rhs(g, S->flags.p, nullptr, S->prm.direction, 1.0, S->d_partials, S->d_counter, S->d_scal + 7, S->st);
+    S->launches++;
+    S->cellp_b2 = read_scalar(S, S->d_scal + 7);
+    S->n_active = S->phase_count_local;        // single slab (checked at create)
+    S->n_in = S->n_out = 0;
+    S->mask_built = true;
+}
+
 void build_mask(oi_solver* S) {
     OI_REQUIRE(S->d_isphase != nullptr, "oi_build_mask: call oi_set_phase_* first");
     const Grid& g = S->g;
@@ -966,6 +1062,7 @@ void build_mask(oi_solver* S) {
         S->r.alloc(g.plane, g.nz, S->st); S->q.alloc(g.plane, g.nz, S->st); S->r32.alloc(g.plane, g.nz, S->st);
         S->vectors_allocated = true;
     }
+    if (S->prm.problem == OI_PROBLEM_CELL) { build_mask_cell_problem(S); return; }
     int* d_labels = reinterpret_cast<int*>(S->p.p);
     unsigned int* d_reach = reinterpret_cast<unsigned int*>(S->q.p);
     uint8_t* d_bits = reinterpret_cast<uint8_t*>(S->r.p);   // 4 planes: send lo, send hi, recv lo, recv hi
@@ -1176,6 +1273,7 @@ void oi_default_params(oi_params* p) {
     p->stencil_variant = 0;
     p->flux_polish = 1;
     p->halo_mode = OI_HALO_AUTO;
+    p->problem = OI_PROBLEM_TORTUOSITY;
     p->comm = nullptr;
 }
 
@@ -1265,6 +1363,15 @@ int oi_create(oi_solver** out, const oi_params* p) {
         g.cx = 1.0 / (p->dx[0] * p->dx[0]);     // TortuosityHypre.cpp:580-582
         g.cy = 1.0 / (p->dx[1] * p->dx[1]);
         g.cz = 1.0 / (p->dx[2] * p->dx[2]);
+        g.hx = p->dx[0]; g.hy = p->dx[1]; g.hz = p->dx[2];
+        g.periodic = 0; g.diag_full = 0.0;
+        OI_REQUIRE(p->problem == OI_PROBLEM_TORTUOSITY || p->problem == OI_PROBLEM_CELL, "bad problem kind");
+        if (p->problem == OI_PROBLEM_CELL) {
+            OI_REQUIRE(n_ranks == 1, "the homogenisation cell problem is single-slab in this build");
+            g.periodic = oi::PER_X | oi::PER_Y | oi::PER_Z;            // Diffusion.cpp:306-308
+            g.diag_full = 2.0 * (g.cx + g.cy + g.cz);                  // EffDiffFillMtx.F90:150-220
+        }
+        { const char* e = getenv("OI_PROFILE"); S->prof_on = (e && e[0] == '1'); }
         S->n_local = g.plane * nzl;
         S->n_dir = p->direction == 0 ? p->nx : (p->direction == 1 ? p->ny : p->nz);
         const int deg = p->mg_degree > 0 ? p->mg_degree : 4;
@@ -1345,6 +1452,8 @@ int oi_destroy(oi_solver* S) {
         if (S->d_changed) cfree(S->d_changed);
         if (S->h_pinned) cudaFreeHost(S->h_pinned);
         for (auto& e : S->timer) if (e) cudaEventDestroy(e);
+        for (auto& m : S->prof_marks) cudaEventDestroy(m.second);
+        for (auto& e : S->prof_pool) cudaEventDestroy(e);
         for (auto& e : S->ev) if (e) cudaEventDestroy(e);
         if (S->st) cudaStreamDestroy(S->st);
         delete S;
@@ -1446,6 +1555,7 @@ int oi_fluxes(oi_solver* S, double* fin, double* fout, int64_t* nin, int64_t* no
     return guarded([&] {
         OI_REQUIRE(S, "null handle");
         OI_REQUIRE(S->mask_built, "oi_fluxes: call oi_build_mask first");
+        OI_REQUIRE(S->prm.problem == OI_PROBLEM_TORTUOSITY, "oi_fluxes: not defined for the cell problem");
         ensure_device(S);
         double a = 0.0, b = 0.0;
         if (S->n_active > 0) compute_fluxes(S, &a, &b);
@@ -1453,6 +1563,24 @@ int oi_fluxes(oi_solver* S, double* fin, double* fout, int64_t* nin, int64_t* no
         if (fout) *fout = b;
         if (nin) *nin = S->n_in;
         if (nout) *nout = S->n_out;
+    });
+}
+
+int oi_cell_gradient_sums(oi_solver* S, double* sums3, int64_t* n_active) {
+    return guarded([&] {
+        OI_REQUIRE(S && sums3, "null argument");
+        OI_REQUIRE(S->mask_built && S->prm.problem == OI_PROBLEM_CELL, "oi_cell_gradient_sums: cell-problem handle with a built mask required");
+        ensure_device(S);
+        sums3[0] = sums3[1] = sums3[2] = 0.0;
+        if (S->n_active > 0) {
+            halo0(S, S->x.p);
+            oi::cellp_grad_sums(S->g, S->flags.p, S->x.p, S->d_partials, S->d_counter, S->d_scal + 4, S->st);
+            S->launches++;
+            CUDA_CHECK(cudaMemcpyAsync(S->h_pinned + 4, S->d_scal + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+            CUDA_CHECK(cudaStreamSynchronize(S->st));
+            for (int a = 0; a < 3; ++a) sums3[a] = S->h_pinned[4 + a];
+        }
+        if (n_active) *n_active = S->n_active;
     });
 }
 

@@ -54,8 +54,7 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     __shared__ double winv[64];
     if (threadIdx.x < 64) {
         const int t = threadIdx.x;
-        const double d = g.cx * (double)__popc(t & 0x03) + g.cy * (double)__popc(t & 0x0c) +
-                         g.cz * (double)__popc(t & 0x30);
+        const double d = row_diag<double>((unsigned int)t, g);
         winv[t] = d > 0.0 ? w0 / d : 0.0;
     }
     __syncthreads();
@@ -146,8 +145,7 @@ jacobi_precond_dot_kernel(Grid g, const uint8_t* __restrict__ flags, const doubl
         const uint8_t f = flags[i];
         double zv = 0.0;
         if (f & F_UNK) {
-            const double d = g.cx * (double)__popc(f & 0x03u) + g.cy * (double)__popc(f & 0x0cu) +
-                             g.cz * (double)__popc(f & 0x30u);
+            const double d = row_diag<double>(f, g);
             const double rv = r[i];
             zv = rv / d;
             acc += rv * zv;

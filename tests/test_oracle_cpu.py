@@ -168,3 +168,46 @@ def test_vlo_vhi_independence(oc):
     a = oc.tortuosity(ph, 1, 0, -1.0, 1.0, eps=1e-12)["tau"]
     b = oc.tortuosity(ph, 1, 0, 0.0, 1.0, eps=1e-12)["tau"]
     assert abs(a - b) <= 1e-9 * abs(a)
+
+
+# ------------------------------------------------------------------ homogenisation cell problem (row f-1)
+def test_effdiff_oracle_rows_are_symmetric_and_dominant():
+    from oracle import oi_effdiff as oe
+    rng = np.random.default_rng(3)
+    ph = (rng.random((6, 7, 9)) < 0.6).astype(np.int32)
+    for direction in range(3):
+        a, rhs, x0 = oe.fill_matrix(ph, 1, direction, dx=(0.5, 1.0, 2.0))
+        A = oe.assemble_csr_periodic(a, ph.shape)
+        assert abs(A - A.T).max() == 0.0                          # couplings are mutual
+        act = (ph == 1).ravel()
+        full_diag = 2.0 * (1 / 0.25 + 1.0 + 0.25)
+        assert np.all(a[act, 0] == full_diag) and np.all(a[~act, 0] == 1.0)    # F90:153-220, 124-129
+        assert np.all(a[~act, 1:] == 0.0) and np.all(rhs[~act] == 0.0) and not x0.any()
+        assert np.all(a[act, 0] + a[act, 1:].sum(axis=1) >= -1e-14)            # weak diagonal dominance
+        # rhs closed form: (a_p - a_m) / (2 h) along the corrector direction
+        h = (0.5, 1.0, 2.0)[direction]
+        ax = 2 - direction
+        a_p, a_m = np.roll(ph == 1, -1, axis=ax), np.roll(ph == 1, 1, axis=ax)
+        closed = np.where(ph == 1, (a_p.astype(float) - a_m.astype(float)) / (2 * h), 0.0)
+        np.testing.assert_allclose(rhs.reshape(ph.shape), closed, rtol=0, atol=1e-15)
+
+
+def test_effdiff_oracle_analytic_cases():
+    from oracle import oi_effdiff as oe
+    np.testing.assert_array_equal(oe.deff_tensor(np.ones((4, 5, 6), np.int32), 1), np.eye(3))
+    ph = np.zeros((4, 4, 12), dtype=np.int32)
+    ph[:, :, 3:9] = 1
+    D = oe.deff_tensor(ph, 1)
+    assert D[1][1] == 0.5 and D[2][2] == 0.5
+    assert abs(D - np.diag(np.diag(D))).max() < 1e-14
+    assert np.all(oe.deff_tensor(np.zeros((3, 3, 3), np.int32), 1) == 0.0)
+
+
+def test_effdiff_golden_is_symmetric_and_near_porosity(sample_phase):
+    import json
+    g = json.load(open(os.path.join(GOLDEN, "effdiff_golden.json")))
+    for pid, n in ((1, 398309), (0, 601691)):
+        D = np.array(g[f"phase{pid}"]["deff"])
+        assert g[f"phase{pid}"]["n_active"] == n == int((sample_phase == pid).sum())
+        np.testing.assert_allclose(D, D.T, rtol=0, atol=1e-9)
+        assert np.all(np.abs(np.diag(D) - n / 1e6) < 0.02)
