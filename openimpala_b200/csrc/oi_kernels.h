@@ -78,9 +78,9 @@ void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, doubl
                          const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
                          const double* den, double w0, double* partials, unsigned int* counter,
                          double* out, int n_sm, cudaStream_t st);
-// p = z + (num/den) p      (z is a multigrid-precision vector)
-void vec_xpby(long long n, double* p, const mg_t* z, const double* num, const double* den,
-              int n_sm, cudaStream_t st);
+// p = z + (num/den) p      (z is a multigrid-precision vector; both zero off the unknowns)
+void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
+              const double* den, int n_sm, cudaStream_t st);
 // conversions between Krylov (fp64) and multigrid precision
 void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st);
 void vec_from_mg(long long n, double* dst, const mg_t* src, int n_sm, cudaStream_t st);

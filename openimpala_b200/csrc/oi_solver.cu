@@ -974,7 +974,7 @@ void run_solve(oi_solver* S) {
                 if (std::sqrt(rr) <= tol) { converged = true; break; }
                 apply_precond(S, d_rzn, fuse_first);
                 prof_mark(S, "xpby");
-                oi::vec_xpby(n, S->p.p, S->zres, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
+                oi::vec_xpby(n, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
                 std::swap(d_rz, d_rzn);
             }
             if (fail || !converged) break;
@@ -1711,7 +1711,7 @@ int oi_time_kernel(oi_solver* S, const char* name, int32_t reps, double* avg_ms,
                                         S->d_scal + 10, S->d_scal + 11, 0.5, S->d_partials, S->d_counter,
                                         S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "xpby") {
-                oi::vec_xpby(n, S->q.p, S->za.p, S->d_scal + 10, S->d_scal + 11, S->n_sm, S->st);
+                oi::vec_xpby(n, S->flags.p, S->q.p, S->za.p, S->d_scal + 10, S->d_scal + 11, S->n_sm, S->st);
             } else if (k == "dot") {
                 oi::vec_dot(n, S->r.p, S->q.p, S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "precond") {

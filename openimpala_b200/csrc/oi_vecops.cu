@@ -63,12 +63,15 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     double acc = 0.0;
     const long long n2 = n & ~1LL;
     typedef typename Vec2<mg_t>::type mg2;
-    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
+    // Every vector here is zero on cells that are not unknowns (solid, non-percolating,
+    // Dirichlet planes: p = q = r = 0 there and x keeps its value), so a 16-byte pair
+    // without an unknown is skipped: its sectors are never fetched or written.  Two
+    // pairs per trip keep two dependent flag -> data chains in flight.
+    auto body = [&](long long i, unsigned int f2) {
         double2 xv = *reinterpret_cast<double2*>(x + i);
         double2 rv = *reinterpret_cast<double2*>(r + i);
         const double2 pv = *reinterpret_cast<const double2*>(p + i);
         const double2 qv = *reinterpret_cast<const double2*>(q + i);
-        const unsigned int f2 = *reinterpret_cast<const unsigned short*>(flags + i);
         xv.x += a * pv.x; xv.y += a * pv.y;
         rv.x -= a * qv.x; rv.y -= a * qv.y;
         *reinterpret_cast<double2*>(x + i) = xv;
@@ -81,6 +84,14 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
         zv.y = (f1 & F_UNK) ? (mg_t)(rv.y * winv[f1 & 63u]) : (mg_t)0;
         *reinterpret_cast<mg2*>(r32 + i) = rr;
         *reinterpret_cast<mg2*>(z1 + i) = zv;
+    };
+    constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
+    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const unsigned int fa = *reinterpret_cast<const unsigned short*>(flags + i);
+        const unsigned int fb = (i2 < n2) ? *reinterpret_cast<const unsigned short*>(flags + i2) : 0u;
+        if (fa & UNK2) body(i, fa);
+        if (fb & UNK2) body(i2, fb);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
         const long long i = n2;
@@ -96,18 +107,27 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     grid_reduce<1>(v, partials, counter, out);
 }
 
+// p = z + beta p, skipping 16-byte pairs without an unknown (z = p = 0 there)
 __global__ void __launch_bounds__(VT)
-xpby_kernel(long long n, double* __restrict__ p, const mg_t* __restrict__ z,
+xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ p, const mg_t* __restrict__ z,
             const double* __restrict__ num, const double* __restrict__ den) {
     const double bta = num[0] / den[0];
     const long long stride = (long long)gridDim.x * VT * 2;
     const long long n2 = n & ~1LL;
     typedef typename Vec2<mg_t>::type mg2;
-    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += stride) {
+    constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
+    auto body = [&](long long i) {
         double2 pv = *reinterpret_cast<double2*>(p + i);
         const mg2 zv = *reinterpret_cast<const mg2*>(z + i);
         pv.x = (double)zv.x + bta * pv.x; pv.y = (double)zv.y + bta * pv.y;
         *reinterpret_cast<double2*>(p + i) = pv;
+    };
+    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const unsigned int fa = *reinterpret_cast<const unsigned short*>(flags + i);
+        const unsigned int fb = (i2 < n2) ? *reinterpret_cast<const unsigned short*>(flags + i2) : 0u;
+        if (fa & UNK2) body(i);
+        if (fb & UNK2) body(i2);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = (double)z[n2] + bta * p[n2];
 }
@@ -179,9 +199,9 @@ void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, doubl
     axpy2_dot_first_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den,
                                                                       w0, partials, counter, out);
 }
-void vec_xpby(long long n, double* p, const mg_t* z, const double* num, const double* den,
-              int n_sm, cudaStream_t st) {
-    xpby_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, p, z, num, den);
+void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
+              const double* den, int n_sm, cudaStream_t st) {
+    xpby_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den);
 }
 void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st) {
     convert_kernel<mg_t, double><<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);

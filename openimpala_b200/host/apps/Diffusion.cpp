@@ -1,8 +1,11 @@
 // `Diffusion <inputs> [key=value ...]` -- the reference's application driver
-// (src/props/Diffusion.cpp) for calculation_method = flow_through: same inputs
-// keys and defaults (:200-223, :605-611), same readers by file extension
-// (:262-300), same results.txt (:709-732).  The homogenisation / REV branches
-// (:317-589) are outside the scope of this build and abort with a message.
+// (src/props/Diffusion.cpp): same inputs keys and defaults (:200-223, :605-611),
+// same readers by file extension (:262-300).
+//   calculation_method = homogenization (the default, :511-589): three periodic
+//     corrector solves (EffectiveDiffusivityHypre) and the D_eff tensor (:60-167);
+//   calculation_method = flow_through (:590-732): TortuosityHypre per direction and
+//     results.txt.
+// The REV study (:317-504) is outside the scope of this build and aborts with a message.
 #include <algorithm>
 #include <filesystem>
 #include <fstream>
@@ -19,6 +22,7 @@
 #include "../io/HDF5Reader.H"
 #include "../io/RawReader.H"
 #include "../io/TiffReader.H"
+#include "../props/EffectiveDiffusivityHypre.H"
 #include "../props/TortuosityHypre.H"
 #include "../props/VolumeFraction.H"
 
@@ -37,6 +41,34 @@ OpenImpala::TortuosityHypre::SolverType stringToSolverType(const std::string& so
     if (s == "pfmg") return ST::PFMG;
     amrex::Abort("Invalid solver string: '" + solver_str + "'.");
     return ST::GMRES;
+}
+
+// calculate_Deff_tensor_homogenization, src/props/Diffusion.cpp:60-167: host restatement
+// on the corrector fields (1 ghost cell, periodic), used to cross-check the device sums.
+void calculate_Deff_tensor_homogenization(amrex::Real Deff_tensor[AMREX_SPACEDIM][AMREX_SPACEDIM],
+                                          const amrex::MultiFab& chi_x, const amrex::MultiFab& chi_y,
+                                          const amrex::MultiFab& chi_z, const amrex::iMultiFab& active_mask,
+                                          const amrex::Geometry& geom, int /*verbose_level*/) {
+    const amrex::MultiFab* chi[3] = {&chi_x, &chi_y, &chi_z};
+    const amrex::Box& bx = geom.Domain();
+    double inv_2dx[3];
+    for (int d = 0; d < 3; ++d) inv_2dx[d] = 1.0 / (2.0 * geom.CellSize(d));
+    double sum[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = bx.smallEnd(2); k <= bx.bigEnd(2); ++k)
+        for (int j = bx.smallEnd(1); j <= bx.bigEnd(1); ++j)
+            for (int i = bx.smallEnd(0); i <= bx.bigEnd(0); ++i) {
+                if (active_mask(i, j, k, 0) != 1) continue;
+                for (int c = 0; c < 3; ++c) {          // corrector chi_c -> column c
+                    const amrex::MultiFab& f = *chi[c];
+                    const double g[3] = {(f(i + 1, j, k) - f(i - 1, j, k)) * inv_2dx[0],
+                                         (f(i, j + 1, k) - f(i, j - 1, k)) * inv_2dx[1],
+                                         (f(i, j, k + 1) - f(i, j, k - 1)) * inv_2dx[2]};
+                    for (int r = 0; r < 3; ++r) sum[r][c] += (r == c ? 1.0 : 0.0) - g[r];
+                }
+            }
+    const long long n = bx.numPts();
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Deff_tensor[r][c] = n > 0 ? sum[r][c] / (amrex::Real)n : 0.0;
 }
 
 template <class Reader>
@@ -135,9 +167,84 @@ int main(int argc, char* argv[]) {
             amrex::Abort("Full domain data loading failed.");
         }
 
-        if (method != "flow_through")
-            amrex::Abort("calculation_method = '" + method + "' is outside this build; set calculation_method = flow_through "
-                         "(homogenisation / REV study: see DESIGN.md, out of scope).");
+        {
+            int rev_do_study = 0;
+            amrex::ParmParse pp_rev("rev");
+            pp_rev.query("do_study", rev_do_study);
+            if (rev_do_study)
+                amrex::Abort("rev.do_study = 1: the REV study (Diffusion.cpp:317-504) is outside this build; see DESIGN.md.");
+        }
+        if (method != "flow_through" && method != "homogenization")
+            amrex::Abort("Invalid calculation_method: '" + method + "'. Use homogenization or flow_through.");
+
+        if (method == "homogenization") {                                           // reference :509-589
+            if (verbose >= 1) amrex::Print() << "\n--- Effective Diffusivity via Homogenization (Full Domain) ---\n";
+            amrex::MultiFab chi[3] = {amrex::MultiFab(ba, dm, 1, 1), amrex::MultiFab(ba, dm, 1, 1),
+                                      amrex::MultiFab(ba, dm, 1, 1)};
+            int check_host_tensor = 0;
+            amrex::ParmParse pp_b200("b200");
+            pp_b200.query("check_host_tensor", check_host_tensor);
+            const auto st_eff = static_cast<OpenImpala::EffectiveDiffusivityHypre::SolverType>(stringToSolverType(solver_str));
+            amrex::Real Deff[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            const long long n_total = domain.numPts();
+            bool all_converged = true;
+            const OpenImpala::Direction dirs3[3] = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
+            for (int c = 0; c < 3; ++c) {
+                const char* dc = c == 0 ? "X" : (c == 1 ? "Y" : "Z");
+                if (verbose >= 1) amrex::Print() << "\n--- Solving for Full Domain chi_" << dc << " ---\n";
+                OpenImpala::EffectiveDiffusivityHypre solver(geom_full, ba, dm, mf_phase, phase_id, dirs3[c], st_eff,
+                                                             (results_dir / (std::string("FullDomain_chi_") + dc)).string(),
+                                                             verbose, write_plotfile != 0);
+                if (!solver.solve()) { all_converged = false; break; }              // :546-549
+                amrex::Real sums[3];
+                long long n_active = 0;
+                solver.gradientSums(sums, n_active);
+                for (int r = 0; r < 3; ++r)
+                    Deff[r][c] = n_total > 0 ? ((r == c ? (amrex::Real)n_active : 0.0) - sums[r]) / (amrex::Real)n_total : 0.0;
+                if (check_host_tensor) solver.getChiSolution(chi[c]);
+            }
+            if (all_converged) {
+                if (check_host_tensor) {
+                    amrex::iMultiFab active(ba, dm, 1, 0);
+                    for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
+                        for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
+                            for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i)
+                                active(i, j, k, 0) = (mf_phase(i, j, k, 0) == phase_id) ? 1 : 0;
+                    amrex::Real Dh[3][3];
+                    calculate_Deff_tensor_homogenization(Dh, chi[0], chi[1], chi[2], active, geom_full, verbose);
+                    amrex::Real worst = 0.0;
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) worst = std::max(worst, std::abs(Dh[r][c] - Deff[r][c]));
+                    amrex::Print() << "Host tensor check: max |D_host - D_device| = " << std::scientific << worst << "\n";
+                    if (!(worst <= 1e-10)) amrex::Abort("host / device D_eff tensors disagree");
+                }
+                amrex::Print() << "Full Domain Effective Diffusivity Tensor D_eff / D_material:\n";
+                for (int r = 0; r < 3; ++r) {
+                    amrex::Print() << "  [";
+                    for (int c = 0; c < 3; ++c)
+                        amrex::Print() << std::scientific << std::setprecision(8) << Deff[r][c] << (c == 2 ? "" : ", ");
+                    amrex::Print() << "]\n";
+                }
+                // (the reference prints the tensor only; the file is an addition of this build)
+                const std::filesystem::path out_path = results_dir / output_filename;
+                std::ofstream out(out_path);
+                if (out.is_open()) {
+                    out << "# Effective Diffusivity Results (Homogenization Method)\n";
+                    out << "# Input File: " << filename << "\n";
+                    out << "# Analysis Phase ID: " << phase_id << "\n";
+                    out << "# -----------------------------\n";
+                    const char* ax = "xyz";
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c)
+                            out << "Deff_" << ax[r] << ax[c] << ": " << std::scientific << std::setprecision(9) << Deff[r][c] << "\n";
+                }
+            } else {
+                amrex::Print() << "Full domain D_eff calculation skipped due to chi_k non-convergence.\n";
+            }
+            amrex::Print() << std::endl << "Total run time (seconds) = " << (amrex::second() - t_start) << std::endl;
+            amrex::Finalize();
+            return 0;
+        }
 
         if (verbose >= 1) amrex::Print() << "\n--- Full Domain Calculation: Tortuosity via Flow-Through ---\n";
         amrex::Real vlo = -1.0, vhi = 1.0;                                            // reference :605-611

@@ -67,11 +67,14 @@ def test_missing_required_key_aborts(host_bins):
     assert r.returncode != 0 and "filename" in r.stderr
 
 
-def test_default_method_is_out_of_scope(host_bins):
-    # the app's default calculation_method is homogenization (Diffusion.cpp:188): not built here
+def test_rev_study_and_unknown_method_abort(host_bins):
+    # the REV study (Diffusion.cpp:317-504) is not built; an unknown method is rejected like the reference
     r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
-            "results_path=gpurun_out/r0/", check=False)
-    assert r.returncode != 0 and "flow_through" in r.stderr
+            "results_path=gpurun_out/r0/", "rev.do_study=1", check=False)
+    assert r.returncode != 0 and "REV study" in r.stderr
+    r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
+            "results_path=gpurun_out/r0/", "calculation_method=nonsense", check=False)
+    assert r.returncode != 0 and "Invalid calculation_method" in r.stderr
 
 
 def test_no_gpu_aborts_loudly(host_bins):
@@ -126,3 +129,21 @@ def test_diffusion_cli_overrides_and_blocked_phase(host_bins):
     tau = float(re.search(r"Tortuosity_Z: (\S+)", txt).group(1))
     assert abs(tau - 1.6930525106) <= 1e-6 * 1.6930525106
     assert "Tortuosity_X" not in txt
+
+
+@pytest.mark.gpu
+def test_diffusion_default_method_is_homogenization(host_bins):
+    # the app's default calculation_method (Diffusion.cpp:188, 509-589): three corrector solves + D_eff tensor
+    gold = json.load(open(os.path.join(GOLDEN, "effdiff_golden.json")))
+    r = run("Diffusion", "filename=SampleData_2Phase_stack_3d_1bit.tif", "data_path=tests/golden/",
+            "results_path=gpurun_out/results_homog/", "phase_id=1", "verbose=1", "b200.check_host_tensor=1")
+    assert "Full Domain Effective Diffusivity Tensor D_eff / D_material:" in r.stdout
+    rows = re.findall(r"^  \[(.+)\]$", r.stdout, flags=re.M)
+    D = [[float(v) for v in row.split(",")] for row in rows[-3:]]
+    ref = gold["phase1"]["deff"]
+    for a in range(3):
+        for b in range(3):
+            assert abs(D[a][b] - ref[a][b]) <= 1e-6
+    assert "Host tensor check" in r.stdout
+    txt = open(os.path.join(ROOT, "gpurun_out", "results_homog", "results.txt")).read()
+    assert abs(float(re.search(r"Deff_xx: (\S+)", txt).group(1)) - ref[0][0]) <= 1e-6
