@@ -194,6 +194,10 @@ int oi_timer_elapsed_ms(oi_solver* h, int32_t slot_begin, int32_t slot_end, doub
  * This returns the idle blocks to the driver; call it only while no multi-slab
  * handle is alive on any rank (neighbours may have the blocks mapped). */
 int oi_release_cached_memory(int64_t* bytes_released);
+/* Local slab: stats3[0] = unknowns, [1] = aligned 2-cell groups and [2] = aligned 4-cell
+ * groups that hold at least one unknown.  The fp64 / fp32 kernels skip a 16-byte group
+ * without unknowns, so these are the granules that are actually read and written. */
+int oi_sparsity(oi_solver* h, int64_t* stats3);
 /* Which halo path the handle uses (oi_halo_mode; AUTO for a single slab) and how
  * many ghost-plane exchanges went through peer memory so far. */
 int oi_halo_info(oi_solver* h, int32_t* mode, int64_t* peer_exchanges);

@@ -87,6 +87,7 @@ _SIGS = {
     "oi_timer_record": (C.c_int, [_P, C.c_int32]),
     "oi_timer_elapsed_ms": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "oi_release_cached_memory": (C.c_int, [C.POINTER(C.c_int64)]),
+    "oi_sparsity": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "oi_halo_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "oi_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
 }
@@ -343,6 +344,12 @@ class Solver:
         ms = C.c_double(0)
         _check(self._lib.oi_timer_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    def sparsity(self):
+        """(unknowns, 2-cell groups with an unknown, 4-cell groups with an unknown) of the local slab."""
+        a = (C.c_int64 * 3)()
+        _check(self._lib.oi_sparsity(self._h, a))
+        return a[0], a[1], a[2]
 
     def halo_info(self):
         """(oi_halo_mode in use, ghost-plane exchanges done through peer memory)."""

@@ -155,6 +155,9 @@ void cellp_rhs(const Grid& g, const uint8_t* flags, double* r, int dir, double s
                unsigned int* counter, double* out, cudaStream_t st);
 void cellp_grad_sums(const Grid& g, const uint8_t* flags, const double* x, double* partials,
                      unsigned int* counter, double* out, cudaStream_t st);
+// out[0..2] += unknowns, aligned 2-cell groups and aligned 4-cell groups holding an unknown
+// (n rounded down to a multiple of 4)
+void flag_stats(const uint8_t* flags, long long n, unsigned long long* out, cudaStream_t st);
 // device-side checkMatrixProperties; bad[0] incremented per violation
 void check_rows(const Grid& g, const uint8_t* flags, const uint8_t* active, int dir,
                 int n_dir_global, unsigned long long* bad, cudaStream_t st);

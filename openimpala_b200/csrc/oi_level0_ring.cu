@@ -221,7 +221,10 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
                 }
             }
             if (MODE != 2) {
-                if (inb) *reinterpret_cast<Pack<T>*>(out_own) = o;
+                // a 16-byte group without an unknown stays zero (every output field is
+                // zero off the unknowns from allocation on): its sector is never written
+                constexpr unsigned int UNKS = (CPT == 2) ? 0x4040u : 0x40404040u;
+                if (inb && (fword & UNKS)) *reinterpret_cast<Pack<T>*>(out_own) = o;
                 out_own += g.plane;
             } else {
                 // y pair = lane ^ 16; z pair carried across two planes

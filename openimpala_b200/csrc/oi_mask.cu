@@ -509,7 +509,31 @@ cellp_grad_sums_kernel(Grid g, const uint8_t* __restrict__ flags, const double* 
     grid_reduce<3>(v, partials, counter, out);
 }
 
+// out[0] = unknowns, out[1] = aligned 2-cell groups holding an unknown, out[2] = aligned
+// 4-cell groups holding one (the 16-byte granules the fp64 / fp32 kernels skip when empty)
+__global__ void __launch_bounds__(BT)
+flag_stats_kernel(const uint8_t* __restrict__ flags, long long n4, unsigned long long* out) {
+    const long long stride = (long long)gridDim.x * BT;
+    long long unk = 0, pairs = 0, quads = 0;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < n4; t += stride) {
+        const unsigned int f = *reinterpret_cast<const unsigned int*>(flags + 4 * t) & 0x40404040u;
+        unk += __popc(f);
+        pairs += ((f & 0x00004040u) ? 1 : 0) + ((f & 0x40400000u) ? 1 : 0);
+        quads += f ? 1 : 0;
+    }
+    unk = warp_sum_ll(unk); pairs = warp_sum_ll(pairs); quads = warp_sum_ll(quads);
+    if ((threadIdx.x & 31) == 0) {
+        if (unk) atomicAdd(&out[0], (unsigned long long)unk);
+        if (pairs) atomicAdd(&out[1], (unsigned long long)pairs);
+        if (quads) atomicAdd(&out[2], (unsigned long long)quads);
+    }
+}
+
 }  // namespace
+
+void flag_stats(const uint8_t* flags, long long n, unsigned long long* out, cudaStream_t st) {
+    flag_stats_kernel<<<nblocks(n / 4, 148, 4), BT, 0, st>>>(flags, n / 4, out);
+}
 
 void cellp_rhs(const Grid& g, const uint8_t* flags, double* r, int dir, double sign, double* partials,
                unsigned int* counter, double* out, cudaStream_t st) {

@@ -1020,6 +1020,14 @@ void run_solve(oi_solver* S) {
     S->solved = true;
 }
 
+// The solve kernels never touch 16-byte groups without an unknown, which is only
+// right if every vector is zero there: (re)establish that whenever the mask changes.
+void zero_mg_vectors(oi_solver* S) {
+    CUDA_CHECK(cudaMemsetAsync(S->r32.base, 0, S->r32.count * sizeof(mg_t), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->za.base, 0, S->za.count * sizeof(mg_t), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->zb.base, 0, S->zb.count * sizeof(mg_t), S->st));
+}
+
 // ------------------------------------------------------------------ mask
 // Cell problem (EffectiveDiffusivityHypre::generateActiveMask + setupMatrixEquation,
 // src/props/EffectiveDiffusivityHypre.cpp:213-330, 425-520): the mask is phase == id,
@@ -1035,6 +1043,10 @@ void build_mask_cell_problem(oi_solver* S) {
     oi::build_flags(g, S->active.p, S->flags.p, S->prm.direction, S->d_ull + 1, S->st); S->launches++;
     halo_exchange_bytes(S, S->flags.p, (size_t)g.plane, g.nz);
     CUDA_CHECK(cudaMemsetAsync(S->x.base, 0, S->x.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
+    CUDA_CHECK(cudaMemsetAsync(S->r.base, 0, S->r.count * sizeof(double), S->st));
+    zero_mg_vectors(S);
     oi::cellp_rhs(g, S->flags.p, nullptr, S->prm.direction, 1.0, S->d_partials, S->d_counter, S->d_scal + 7, S->st);
     S->launches++;
     S->cellp_b2 = read_scalar(S, S->d_scal + 7);
@@ -1129,6 +1141,7 @@ void build_mask(oi_solver* S) {
     CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->r.base, 0, S->r.count * sizeof(double), S->st));
+    zero_mg_vectors(S);
 
     // initial guess (skipped when nothing percolates, like the reference's early
     // return TortuosityHypre.cpp:170-178)
@@ -1628,6 +1641,7 @@ int oi_get_initial_guess(oi_solver* S, double* host) {
         oi::fill_initial_guess(S->g, S->flags.p, S->q.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, 1, S->st);
         S->launches++;
         copy_out(S, S->q.p, host, (size_t)S->n_local);
+        CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));   // scratch use: restore the zero invariant
     });
 }
 int oi_get_rhs(oi_solver* S, double* host) {
@@ -1637,6 +1651,7 @@ int oi_get_rhs(oi_solver* S, double* host) {
         oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, nullptr, S->q.p, S->st);
         S->launches++;
         copy_out(S, S->q.p, host, (size_t)S->n_local);
+        CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
     });
 }
 int oi_get_matrix_rows(oi_solver* S, double* host) {
@@ -1655,11 +1670,15 @@ int oi_apply_operator(oi_solver* S, const double* hx, double* hy) {
     return guarded([&] {
         OI_REQUIRE(S && hx && hy && S->mask_built && S->p.p, "oi_apply_operator: mask not built / empty");
         ensure_device(S);
+        CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
         CUDA_CHECK(cudaMemcpyAsync(S->p.p, hx, (size_t)S->n_local * sizeof(double), cudaMemcpyHostToDevice, S->st));
         halo0(S, S->p.p);
         L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, S->d_scal + 14);
         oi::l0_apply(a, true, S->prm.stencil_variant, S->st); S->launches++;
         copy_out(S, S->q.p, hy, (size_t)S->n_local);
+        // the caller's x need not vanish off the unknowns: restore the invariant
+        CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
+        CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
         CUDA_CHECK(cudaGetLastError());
     });
 }
@@ -1672,6 +1691,9 @@ int oi_apply_precond(oi_solver* S, const double* hr, double* hz) {
         apply_precond(S, S->d_scal + 13);
         oi::vec_from_mg(S->n_local, S->q.p, S->zres, S->n_sm, S->st); S->launches++;
         copy_out(S, S->q.p, hz, (size_t)S->n_local);
+        // the caller's r need not vanish off the unknowns: restore the invariant
+        CUDA_CHECK(cudaMemsetAsync(S->r.base, 0, S->r.count * sizeof(double), S->st));
+        CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
         CUDA_CHECK(cudaGetLastError());
     });
 }
@@ -1767,6 +1789,20 @@ int oi_release_cached_memory(int64_t* bytes_released) {
             C.release_idle_locked();
         }
         if (bytes_released) *bytes_released = (int64_t)b;
+    });
+}
+
+int oi_sparsity(oi_solver* S, int64_t* stats3) {
+    return guarded([&] {
+        OI_REQUIRE(S && stats3 && S->mask_built, "oi_sparsity: mask not built");
+        ensure_device(S);
+        CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 3 * sizeof(unsigned long long), S->st));
+        oi::flag_stats(S->flags.p, S->n_local, S->d_ull, S->st);
+        S->launches++;
+        unsigned long long h[3];
+        CUDA_CHECK(cudaMemcpyAsync(h, S->d_ull, sizeof(h), cudaMemcpyDeviceToHost, S->st));
+        CUDA_CHECK(cudaStreamSynchronize(S->st));
+        for (int i = 0; i < 3; ++i) stats3[i] = (int64_t)h[i];
     });
 }
 
