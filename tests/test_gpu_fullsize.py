@@ -71,7 +71,7 @@ def test_mask_idempotent_and_maximum_principle(capi, packing):
         s.solve()
         x = s.solution()
         act = mask.astype(bool)
-        assert x[act].min() >= -1.0 - 1e-9 and x[act].max() <= 1.0 + 1e-9     # discrete maximum principle
+        assert x[act].min() >= -1.0 - 1e-6 and x[act].max() <= 1.0 + 1e-6     # discrete maximum principle (to solver accuracy)
         assert not x[~act].any()                                               # zero off the active cells
         s.set_phase(mask)                                                      # the mask as a phase field
         assert s.build_mask() == n1
