@@ -46,6 +46,7 @@ struct CoarseLevel {
     long long plane;
     int fx, fy, fz;            // coarsening factors from this level to the next
     int periodic;              // PER_X | PER_Y | PER_Z of the box (cell problem), else 0
+    int replicated;            // multi-rank: this level holds the whole box on every rank (no halo)
     float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
     float* dg;                 // diagonal (0 = empty aggregate)
     mg_t *x, *b, *t;           // solution, rhs, scratch (ghost planes)

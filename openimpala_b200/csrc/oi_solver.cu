@@ -59,6 +59,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -85,6 +86,7 @@ NcclApi& nccl_api() {
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
@@ -287,6 +289,12 @@ struct HostLevel {
     oi::CoarseLevel L{};
     Field<float> cxp, cyp, czp, dg;
     Field<oi::mg_t> x, b, t;
+    // Agglomeration (n_ranks > 1): the first level small enough is kept twice -- once
+    // distributed (`gather_point`: it only receives the restricted residual and hands back
+    // the correction) and once whole on every rank (`replicated`, the next entry), where
+    // it and everything below are cycled redundantly without any halo traffic.
+    bool gather_point = false, replicated = false;
+    std::vector<int> slab_z0, slab_nz;      // gather_point: every rank's planes at this level
 };
 
 }  // namespace
@@ -448,7 +456,22 @@ inline void halo0(oi_solver* S, T* v) {
     halo_exchange_bytes(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz);
 }
 inline void haloL(oi_solver* S, const CoarseLevel& L, mg_t* v) {
+    if (L.replicated) return;          // whole level on every rank: ghost planes are the (zero) box faces
     halo_exchange_bytes(S, v, (size_t)L.plane * sizeof(mg_t), L.nz);
+}
+
+// Every rank's slab of a distributed level array -> the whole array on every rank.
+template <typename T>
+void gather_level(oi_solver* S, const HostLevel& dist, const T* src_plane0, T* dst_plane0) {
+    NcclApi& N = nccl_api();
+    const size_t plane = (size_t)dist.L.plane;
+    NCCL_CHECK(N.GroupStart());
+    for (int r = 0; r < S->n_ranks; ++r) {
+        T* dst = dst_plane0 + plane * (size_t)dist.slab_z0[r];
+        NCCL_CHECK(N.Broadcast(r == S->rank ? (const void*)src_plane0 : (const void*)dst, dst,
+                               plane * (size_t)dist.slab_nz[r] * sizeof(T), ncclUint8, r, S->comm, S->st));
+    }
+    NCCL_CHECK(N.GroupEnd());
 }
 
 void allreduce_sum_f64(oi_solver* S, double* d, int n) {
@@ -538,8 +561,12 @@ void free_vectors(oi_solver* S) {
 // Level shapes depend only on the box and the slab table.
 void plan_hierarchy(oi_solver* S) {
     if (S->levels_planned) return;
-    const int nr = S->n_ranks, rk = S->rank;
+    int nr = S->n_ranks, rk = S->rank;
     std::vector<int> z0 = S->all_z0, nz = S->all_nz;
+    // levels with at most this many cells (whole box) are gathered onto every rank
+    long long agg_cells = 64LL * 64 * 64;
+    if (const char* e = getenv("OI_AGG_CELLS")) agg_cells = std::atoll(e);
+    bool gathered = (nr == 1) || agg_cells <= 0;
     int nx = S->g.nx, ny = S->g.ny, nzg = S->g.nzg;
     L0Info f0{1, 1, 1};
     std::vector<HostLevel>& lv = S->levels;
@@ -564,6 +591,22 @@ void plan_hierarchy(oi_solver* S) {
         h.L.plane = (long long)nx * ny;
         h.L.fx = h.L.fy = h.L.fz = 1;
         h.L.periodic = S->g.periodic;
+        h.L.replicated = (S->n_ranks > 1 && nr == 1) ? 1 : 0;
+        h.replicated = h.L.replicated != 0;
+        if (!gathered && (long long)nx * ny * nzg <= agg_cells) {
+            // this level becomes the gather point; its twin holds the whole box on every rank
+            gathered = true;
+            h.gather_point = true;
+            h.slab_z0 = z0; h.slab_nz = nz;
+            lv.emplace_back();
+            HostLevel& w = lv.back();
+            w.L = lv[lv.size() - 2].L;
+            w.L.nz = nzg; w.L.z0 = 0;
+            w.L.replicated = 1;
+            w.replicated = true;
+            nr = 1; rk = 0;
+            z0.assign(1, 0); nz.assign(1, nzg);
+        }
     }
     S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
     S->levels_planned = true;
@@ -617,7 +660,10 @@ bool peer_setup(oi_solver* S) {
     auto add = [&](size_t b) { need += b + 256; };
     add(Field<double>::bytes_needed(g.plane, g.nz)); add(Field<double>::bytes_needed(g.plane, g.nz));
     add(Field<mg_t>::bytes_needed(g.plane, g.nz)); add(Field<mg_t>::bytes_needed(g.plane, g.nz));
-    if (mg) for (HostLevel& h : S->levels) { add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); }
+    if (mg) for (HostLevel& h : S->levels) {
+        if (h.replicated) continue;        // no halo traffic on a level every rank holds whole
+        add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz));
+    }
     int ok = 1;
     if (cmalloc(&P.arena.base, need) != cudaSuccess) { cudaGetLastError(); P.arena.base = nullptr; ok = 0; }
     PeerBlob mine{};
@@ -635,6 +681,7 @@ bool peer_setup(oi_solver* S) {
         S->za.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->za.p, g.plane * sizeof(mg_t), g.nz);
         S->zb.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->zb.p, g.plane * sizeof(mg_t), g.nz);
         if (mg) for (HostLevel& h : S->levels) {
+            if (h.replicated) continue;
             h.x.alloc(h.L.plane, h.L.nz, S->st, &P.arena); reg((char*)h.x.p, h.L.plane * sizeof(mg_t), h.L.nz);
             h.t.alloc(h.L.plane, h.L.nz, S->st, &P.arena); reg((char*)h.t.p, h.L.plane * sizeof(mg_t), h.L.nz);
         }
@@ -725,6 +772,14 @@ void build_hierarchy(oi_solver* S) {
     allocate_hierarchy(S);
     std::vector<HostLevel>& lv = S->levels;
     for (size_t l = 0; l < lv.size(); ++l) {
+        if (l > 0 && lv[l - 1].gather_point) {
+            // the whole-box twin of the gather point: collect every rank's coefficients
+            gather_level(S, lv[l - 1], lv[l - 1].cxp.p, lv[l].cxp.p);
+            gather_level(S, lv[l - 1], lv[l - 1].cyp.p, lv[l].cyp.p);
+            gather_level(S, lv[l - 1], lv[l - 1].czp.p, lv[l].czp.p);
+            gather_level(S, lv[l - 1], lv[l - 1].dg.p, lv[l].dg.p);
+            continue;
+        }
         if (l == 0) {
             oi::coarse_build_from_flags(S->g, S->flags.p, S->prm.direction, S->n_dir, lv[0].L,
                                         S->fx0, S->fy0, S->fz0, S->mg_scale, S->st);
@@ -732,6 +787,7 @@ void build_hierarchy(oi_solver* S) {
             oi::coarse_build_from_coarse(lv[l - 1].L, lv[l].L, S->mg_scale, S->st);
         }
         S->launches++;
+        if (lv[l].replicated) continue;
         // ghost planes of the z-coupling and the diagonal (read by the -z neighbour
         // coupling and by the fused prolongation)
         halo_exchange_bytes(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
@@ -744,6 +800,20 @@ void build_hierarchy(oi_solver* S) {
 void coarse_cycle(oi_solver* S, size_t l) {
     HostLevel& h = S->levels[l];
     CoarseLevel& L = h.L;
+    if (h.gather_point) {
+        // residual of every slab -> whole level on every rank; cycle it (and everything
+        // below) redundantly with no halo traffic; take this slab of the correction back,
+        // ghost planes included (the neighbours' planes are in the local copy)
+        HostLevel& w = S->levels[l + 1];
+        prof_mark(S, "mg gather");
+        gather_level(S, h, L.b, w.L.b);
+        coarse_cycle(S, l + 1);
+        prof_mark(S, "mg gather");
+        const size_t plane = (size_t)L.plane;
+        CUDA_CHECK(cudaMemcpyAsync(L.x - plane, w.L.x + plane * (size_t)L.z0 - plane, plane * (size_t)(L.nz + 2) * sizeof(mg_t),
+                                   cudaMemcpyDeviceToDevice, S->st));
+        return;
+    }
     const bool last = (l + 1 == S->levels.size());
     const std::vector<double>& w = last ? S->w_coarse : S->w_smooth;
     const int deg = (int)w.size();
