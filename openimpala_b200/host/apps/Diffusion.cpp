@@ -5,12 +5,15 @@
 //     corrector solves (EffectiveDiffusivityHypre) and the D_eff tensor (:60-167);
 //   calculation_method = flow_through (:590-732): TortuosityHypre per direction and
 //     results.txt.
-// The REV study (:317-504) is outside the scope of this build and aborts with a message.
+//   rev.do_study = 1 (:317-504): D_eff tensors of random sub-volumes -> rev_study_Deff.csv.
 #include <algorithm>
 #include <filesystem>
 #include <fstream>
 #include <iomanip>
+#include <limits>
 #include <map>
+#include <memory>
+#include <random>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -167,15 +170,119 @@ int main(int argc, char* argv[]) {
             amrex::Abort("Full domain data loading failed.");
         }
 
+        // ---- REV study (reference :317-504): D_eff tensors of random cubic sub-volumes, each
+        // treated as its own periodic box, one CSV row per (sample, size)
         {
-            int rev_do_study = 0;
-            amrex::ParmParse pp_rev("rev");
-            pp_rev.query("do_study", rev_do_study);
-            if (rev_do_study)
-                amrex::Abort("rev.do_study = 1: the REV study (Diffusion.cpp:317-504) is outside this build; see DESIGN.md.");
+            int rev_do_study = 0, rev_num_samples = 3, rev_write_plotfiles = 0, rev_verbose = 1;
+            std::string rev_sizes_str = "32 64 96", rev_solver_str = "FlexGMRES", rev_results_filename = "rev_study_Deff.csv";
+            amrex::ParmParse ppr("rev");
+            ppr.query("do_study", rev_do_study);
+            ppr.query("num_samples", rev_num_samples);
+            ppr.query("sizes", rev_sizes_str);
+            {   // unquoted `rev.sizes = 32 64 96` arrives as several values
+                std::vector<std::string> all;
+                if (ppr.queryarr("sizes", all) && all.size() > 1) {
+                    rev_sizes_str.clear();
+                    for (const auto& v : all) rev_sizes_str += v + " ";
+                }
+            }
+            ppr.query("solver_type", rev_solver_str);
+            ppr.query("results_file", rev_results_filename);
+            ppr.query("write_plotfiles", rev_write_plotfiles);
+            ppr.query("verbose", rev_verbose);
+            if (rev_do_study) {
+                if (verbose >= 1) {
+                    amrex::Print() << "\n--- Starting REV Study (Homogenization Method) for Phase ID " << phase_id << " ---\n";
+                    amrex::Print() << "  Number of samples per size: " << rev_num_samples << std::endl;
+                    amrex::Print() << "  Target REV sizes: " << rev_sizes_str << std::endl;
+                    amrex::Print() << "  REV Solver: " << rev_solver_str << std::endl;
+                }
+                std::vector<int> sizes;
+                {
+                    std::stringstream ss(rev_sizes_str);
+                    int v;
+                    while (ss >> v) sizes.push_back(v);
+                }
+                if (sizes.empty()) {
+                    amrex::Warning("REV sizes string is empty or invalid. Skipping REV study.");
+                } else {
+                    std::ofstream csv((results_dir / rev_results_filename).string());
+                    csv << "SampleNo,SeedX,SeedY,SeedZ,REV_Size_Target,ActualSizeX,ActualSizeY,ActualSizeZ,D_xx,D_yy,D_zz,D_xy,D_xz,D_yz\n";
+                    std::mt19937 gen(amrex::ParallelDescriptor::MyProc() + 12345 + rev_num_samples);     // :341
+                    const auto st_rev = static_cast<OpenImpala::EffectiveDiffusivityHypre::SolverType>(stringToSolverType(rev_solver_str));
+                    for (int s_idx = 0; s_idx < rev_num_samples; ++s_idx) {
+                        for (int target : sizes) {
+                            amrex::IntVect seed_lo;
+                            for (int d = 0; d < 3; ++d) {                                               // :346-355
+                                const int min_c = domain.smallEnd(d), max_c = domain.bigEnd(d) - (target - 1);
+                                if (min_c > max_c || target > domain.length(d)) seed_lo[d] = domain.smallEnd(d);
+                                else { std::uniform_int_distribution<> distr(min_c, max_c); seed_lo[d] = distr(gen); }
+                            }
+                            amrex::Box bx(seed_lo, seed_lo + amrex::IntVect(target - 1, target - 1, target - 1));
+                            bx &= domain;
+                            const int longside = bx.isEmpty() ? 0 : std::max(bx.length(0), std::max(bx.length(1), bx.length(2)));
+                            if (bx.isEmpty() || longside < 8) {                                         // :361-369
+                                if (rev_verbose >= 1)
+                                    amrex::Warning("Skipping REV for sample " + std::to_string(s_idx + 1) + " target size " +
+                                                   std::to_string(target) + " due to small/empty box after intersection");
+                                continue;
+                            }
+                            if (rev_verbose >= 1)
+                                amrex::Print() << " REV Sample " << s_idx + 1 << ", Target Size " << target << ", Seed Lo (global): "
+                                               << seed_lo << ", Actual REV Box (global): " << bx << std::endl;
+                            // the sub-volume as its own periodic box with origin 0 (:377-420)
+                            const amrex::Box rel(amrex::IntVect(0, 0, 0), bx.bigEnd() - bx.smallEnd());
+                            amrex::Geometry geom_rev;
+                            amrex::RealBox rb_rev({AMREX_D_DECL(0.0, 0.0, 0.0)},
+                                                  {AMREX_D_DECL(amrex::Real(rel.length(0)), amrex::Real(rel.length(1)), amrex::Real(rel.length(2)))});
+                            amrex::Array<int, AMREX_SPACEDIM> per_rev = {AMREX_D_DECL(1, 1, 1)};
+                            geom_rev.define(rel, &rb_rev, 0, per_rev.data());
+                            amrex::BoxArray ba_rev(rel);
+                            ba_rev.maxSize(box_size);
+                            amrex::DistributionMapping dm_rev(ba_rev);
+                            amrex::iMultiFab mf_rev(ba_rev, dm_rev, 1, 1);
+                            mf_rev.setVal(0);
+                            for (int k = rel.smallEnd(2); k <= rel.bigEnd(2); ++k)
+                                for (int j = rel.smallEnd(1); j <= rel.bigEnd(1); ++j)
+                                    for (int i = rel.smallEnd(0); i <= rel.bigEnd(0); ++i)
+                                        mf_rev(i, j, k, 0) = mf_phase(i + bx.smallEnd(0), j + bx.smallEnd(1), k + bx.smallEnd(2), 0);
+                            mf_rev.FillBoundary(geom_rev.periodicity());
+                            amrex::Real D[3][3];
+                            for (auto& row : D) for (auto& v : row) v = std::numeric_limits<amrex::Real>::quiet_NaN();
+                            amrex::Real Dtmp[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                            bool all_ok = true;
+                            const long long n_rev = rel.numPts();
+                            const OpenImpala::Direction dirs3[3] = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
+                            for (int c = 0; c < 3 && all_ok; ++c) {
+                                OpenImpala::EffectiveDiffusivityHypre solver(geom_rev, ba_rev, dm_rev, mf_rev, phase_id, dirs3[c], st_rev,
+                                                                             results_path, rev_verbose > 1 ? rev_verbose : 0, rev_write_plotfiles != 0);
+                                if (!solver.solve()) {
+                                    all_ok = false;
+                                    if (rev_verbose >= 1) amrex::Print() << "    REV Chi solve FAILED for dir " << c << std::endl;
+                                    break;
+                                }
+                                amrex::Real sums[3];
+                                long long n_active = 0;
+                                solver.gradientSums(sums, n_active);
+                                for (int r = 0; r < 3; ++r) Dtmp[r][c] = ((r == c ? (amrex::Real)n_active : 0.0) - sums[r]) / (amrex::Real)n_rev;
+                            }
+                            if (all_ok) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) D[r][c] = Dtmp[r][c];
+                            csv << s_idx + 1 << "," << seed_lo[0] << "," << seed_lo[1] << "," << seed_lo[2] << "," << target << ","
+                                << bx.length(0) << "," << bx.length(1) << "," << bx.length(2) << "," << std::fixed << std::setprecision(8)
+                                << D[0][0] << "," << D[1][1] << "," << D[2][2] << "," << D[0][1] << "," << D[0][2] << "," << D[1][2] << "\n";
+                            csv.flush();
+                        }
+                    }
+                }
+            }
         }
-        if (method != "flow_through" && method != "homogenization")
-            amrex::Abort("Invalid calculation_method: '" + method + "'. Use homogenization or flow_through.");
+        if (method != "flow_through" && method != "homogenization" && method != "skip_if_rev")
+            amrex::Abort("Invalid calculation_method: '" + method + "'. Use homogenization, flow_through or skip_if_rev.");
+        if (method == "skip_if_rev") {                      // reference :507: no full-domain calculation
+            amrex::Print() << std::endl << "Total run time (seconds) = " << (amrex::second() - t_start) << std::endl;
+            amrex::Finalize();
+            return 0;
+        }
 
         if (method == "homogenization") {                                           // reference :509-589
             if (verbose >= 1) amrex::Print() << "\n--- Effective Diffusivity via Homogenization (Full Domain) ---\n";

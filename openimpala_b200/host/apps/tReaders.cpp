@@ -1,6 +1,6 @@
 // Reader + VolumeFraction checks in the mould of src/io/tTiffReader.cpp,
 // tRawReader.cpp, tHDF5Reader.cpp and src/props/tVolumeFraction.cpp:
-//   mode = tiff | raw | hdf5 ; prints dims, sample metadata, thresholded min/max
+//   mode = tiff | raw | hdf5 | dat ; prints dims, sample metadata, thresholded min/max
 //   and the phase counts, compares the GPU count with a direct host loop.
 #include <iomanip>
 #include <string>
@@ -9,6 +9,7 @@
 #include <AMReX_ParmParse.H>
 #include <AMReX_Print.H>
 
+#include "../io/DatReader.H"
 #include "../io/HDF5Reader.H"
 #include "../io/RawReader.H"
 #include "../io/TiffReader.H"
@@ -24,7 +25,8 @@ int main(int argc, char* argv[]) {
         amrex::Real threshold = 0.5;
         amrex::ParmParse pp;
         pp.query("mode", mode);
-        if (!pp.query("tifffile", file) && !pp.query("rawfile", file) && !pp.query("hdf5file", file)) pp.get("filename", file);
+        if (!pp.query("tifffile", file) && !pp.query("rawfile", file) && !pp.query("hdf5file", file) &&
+            !pp.query("datfile", file)) pp.get("filename", file);
         pp.query("hdf5dataset", dataset);
         pp.query("datatype", datatype);
         pp.query("width", width); pp.query("height", height); pp.query("depth", depth);
@@ -60,6 +62,12 @@ int main(int argc, char* argv[]) {
                 OpenImpala::HDF5Reader r(file, dataset);
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
+            } else if (mode == "dat") {
+                OpenImpala::DatReader r(file);
+                prepare(r.box());
+                r.threshold(static_cast<OpenImpala::DatReader::DataType>(threshold), 1, 0, mf);
+                amrex::Print() << "RawCorner: " << r.getRawValue(0, 0, 0) << " "
+                               << r.getRawValue(r.width() - 1, r.height() - 1, r.depth() - 1) << "\n";
             } else {
                 fail("unknown mode " + mode);
             }

@@ -62,16 +62,33 @@ def test_readers_agree_with_oracle_decoder(host_bins):
         assert int(field(r.stdout, "DirectCount1")[0]) == int(ph.sum())
 
 
+def test_dat_reader(host_bins, tmp_path):
+    # src/io/DatReader.cpp:60-248: int32 LE (W, H, D) header + uint16 LE voxels, x fastest
+    import numpy as np
+    rng = np.random.default_rng(9)
+    vol = rng.integers(0, 4000, size=(5, 7, 9), dtype=np.uint16)          # [z, y, x]
+    f = tmp_path / "vol.dat"
+    with open(f, "wb") as fh:
+        fh.write(np.array([9, 7, 5], dtype="<i4").tobytes())
+        fh.write(vol.astype("<u2").tobytes())
+        fh.write(b"extra")                                                # trailing bytes are ignored with a warning
+    r = run("tReaders", "mode=dat", "gpu_count=0", f"datfile={f}", "threshold=1999")
+    assert [int(v) for v in field(r.stdout, "Dims")] == [9, 7, 5]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > 1999).sum())
+    assert [int(v) for v in field(r.stdout, "RawCorner")] == [int(vol[0, 0, 0]), int(vol[-1, -1, -1])]
+    # truncated payload and bad header are rejected
+    (tmp_path / "short.dat").write_bytes(np.array([9, 7, 5], dtype="<i4").tobytes() + b"\0" * 10)
+    assert run("tReaders", "mode=dat", "gpu_count=0", f"datfile={tmp_path / 'short.dat'}", check=False).returncode != 0
+    (tmp_path / "bad.dat").write_bytes(np.array([0, 7, 5], dtype="<i4").tobytes())
+    assert run("tReaders", "mode=dat", "gpu_count=0", f"datfile={tmp_path / 'bad.dat'}", check=False).returncode != 0
+
+
 def test_missing_required_key_aborts(host_bins):
     r = run("Diffusion", "calculation_method=flow_through", check=False)
     assert r.returncode != 0 and "filename" in r.stderr
 
 
-def test_rev_study_and_unknown_method_abort(host_bins):
-    # the REV study (Diffusion.cpp:317-504) is not built; an unknown method is rejected like the reference
-    r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
-            "results_path=gpurun_out/r0/", "rev.do_study=1", check=False)
-    assert r.returncode != 0 and "REV study" in r.stderr
+def test_unknown_method_aborts(host_bins):
     r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
             "results_path=gpurun_out/r0/", "calculation_method=nonsense", check=False)
     assert r.returncode != 0 and "Invalid calculation_method" in r.stderr
@@ -147,3 +164,30 @@ def test_diffusion_default_method_is_homogenization(host_bins):
     assert "Host tensor check" in r.stdout
     txt = open(os.path.join(ROOT, "gpurun_out", "results_homog", "results.txt")).read()
     assert abs(float(re.search(r"Deff_xx: (\S+)", txt).group(1)) - ref[0][0]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_diffusion_rev_study_csv(host_bins):
+    # rev.do_study (Diffusion.cpp:317-504): random sub-volumes as periodic boxes -> one CSV row each;
+    # every row must equal the oracle's tensor of that very sub-volume
+    import numpy as np
+    from oracle import oi_effdiff as oe
+    from oracle import oi_numpy as o
+    run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
+        "results_path=gpurun_out/results_rev/", "rev.do_study=1", "rev.num_samples=2", "rev.sizes=16 24 200",
+        "calculation_method=skip_if_rev", "rev.verbose=0", "verbose=0")
+    lines = open(os.path.join(ROOT, "gpurun_out", "results_rev", "rev_study_Deff.csv")).read().splitlines()
+    assert lines[0] == ("SampleNo,SeedX,SeedY,SeedZ,REV_Size_Target,ActualSizeX,ActualSizeY,ActualSizeZ,"
+                        "D_xx,D_yy,D_zz,D_xy,D_xz,D_yz")
+    rows = [l.split(",") for l in lines[1:]]
+    assert len(rows) == 6 and [int(r[4]) for r in rows] == [16, 24, 200] * 2
+    ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, "SampleData_2Phase_squared.tif")), 0.5)
+    for r in rows:
+        sx, sy, sz, target = int(r[1]), int(r[2]), int(r[3]), int(r[4])
+        ax, ay, az = int(r[5]), int(r[6]), int(r[7])
+        assert (ax, ay, az) == ((target,) * 3 if target <= 64 else (64, 64, 64))    # clipped to the domain
+        sub = ph[sz:sz + az, sy:sy + ay, sx:sx + ax]
+        D = oe.deff_tensor(sub, 1)
+        got = [float(v) for v in r[8:14]]
+        ref = [D[0][0], D[1][1], D[2][2], D[0][1], D[0][2], D[1][2]]
+        assert max(abs(a - b) for a, b in zip(got, ref)) <= 1e-6
