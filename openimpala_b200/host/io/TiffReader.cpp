@@ -17,6 +17,8 @@
 #include <sstream>
 #include <stdexcept>
 
+#include <zlib.h>
+
 #include <AMReX_Utility.H>
 
 namespace OpenImpala {
@@ -110,8 +112,106 @@ private:
 
 enum { T_WIDTH = 256, T_HEIGHT = 257, T_BPS = 258, T_COMPRESSION = 259, T_FILLORDER = 266,
        T_STRIPOFFSETS = 273, T_SPP = 277, T_ROWSPERSTRIP = 278, T_STRIPBYTECOUNTS = 279,
-       T_PLANAR = 284, T_TILEWIDTH = 322, T_TILELENGTH = 323, T_TILEOFFSETS = 324,
+       T_PLANAR = 284, T_PREDICTOR = 317, T_TILEWIDTH = 322, T_TILELENGTH = 323, T_TILEOFFSETS = 324,
        T_TILEBYTECOUNTS = 325, T_SAMPLEFORMAT = 339 };
+enum { C_NONE = 1, C_LZW = 5, C_DEFLATE = 8, C_DEFLATE_OLD = 32946, C_PACKBITS = 32773 };
+
+// ---- strip / tile decompression (the reference gets these from libtiff) ----------------
+// TIFF 6.0 LZW: MSB-first codes of 9..12 bits, Clear = 256, EOI = 257, "early change".
+std::vector<unsigned char> lzwDecode(const unsigned char* in, size_t n, size_t expect) {
+    std::vector<unsigned char> out;
+    out.reserve(expect);
+    std::vector<int> prefix(4096, -1), length(4096, 1);
+    std::vector<unsigned char> suffix(4096, 0), first(4096, 0);
+    for (int i = 0; i < 256; ++i) { suffix[i] = first[i] = (unsigned char)i; }
+    int next = 258, width = 9, old = -1;
+    uint64_t bitbuf = 0;
+    int bits = 0;
+    size_t pos = 0;
+    auto emit = [&](int c) {
+        const int l = length[c];
+        const size_t base = out.size();
+        out.resize(base + (size_t)l);
+        for (int q = l - 1, cur = c; q >= 0; --q) { out[base + (size_t)q] = suffix[cur]; cur = prefix[cur]; }
+    };
+    while (out.size() < expect) {
+        while (bits < width && pos < n) { bitbuf = (bitbuf << 8) | in[pos++]; bits += 8; }
+        if (bits < width) break;
+        const int code = (int)((bitbuf >> (bits - width)) & ((1u << width) - 1u));
+        bits -= width;
+        if (code == 257) break;
+        if (code == 256) { next = 258; width = 9; old = -1; continue; }
+        if (old < 0) {
+            if (code >= 256) throw std::runtime_error("corrupt LZW stream");
+            emit(code);
+        } else {
+            if (code > next || next >= 4096) throw std::runtime_error("corrupt LZW stream");
+            prefix[next] = old;
+            length[next] = length[old] + 1;
+            first[next] = first[old];
+            suffix[next] = (code < next) ? first[code] : first[old];      // KwKwK when code == next
+            ++next;
+            emit(code);
+        }
+        old = code;
+        if (next >= (1 << width) - 1 && width < 12) ++width;
+    }
+    return out;
+}
+
+std::vector<unsigned char> packBitsDecode(const unsigned char* in, size_t n, size_t expect) {
+    std::vector<unsigned char> out;
+    out.reserve(expect);
+    size_t i = 0;
+    while (i < n && out.size() < expect) {
+        const int c = (int)(signed char)in[i++];
+        if (c >= 0) {
+            const size_t m = std::min<size_t>((size_t)c + 1, n - i);
+            out.insert(out.end(), in + i, in + i + m);
+            i += m;
+        } else if (c != -128 && i < n) {
+            out.insert(out.end(), (size_t)(1 - c), in[i++]);
+        }
+    }
+    return out;
+}
+
+std::vector<unsigned char> inflateAll(const unsigned char* in, size_t n, size_t expect) {
+    std::vector<unsigned char> out(expect);
+    uLongf len = (uLongf)expect;
+    const int rc = uncompress(out.data(), &len, in, (uLong)n);
+    if (rc != Z_OK && rc != Z_BUF_ERROR) throw std::runtime_error("corrupt Deflate stream in TIFF");
+    out.resize((size_t)len);
+    return out;
+}
+
+// Decode one strip / tile in place: `buf` holds the file bytes on entry and the samples on exit.
+void decodeSegment(std::vector<unsigned char>& buf, uint64_t compression, uint64_t predictor, size_t expect,
+                   size_t row_samples, size_t bytes_per_sample, bool file_little) {
+    if (compression == C_LZW) buf = lzwDecode(buf.data(), buf.size(), expect);
+    else if (compression == C_PACKBITS) buf = packBitsDecode(buf.data(), buf.size(), expect);
+    else if (compression == C_DEFLATE || compression == C_DEFLATE_OLD) buf = inflateAll(buf.data(), buf.size(), expect);
+    if (predictor == 2 && row_samples > 0) {                        // horizontal differencing, integer samples
+        const size_t row_bytes = row_samples * bytes_per_sample;
+        for (size_t r0 = 0; r0 + row_bytes <= buf.size(); r0 += row_bytes) {
+            unsigned char* row = buf.data() + r0;
+            if (bytes_per_sample == 1) {
+                for (size_t i = 1; i < row_samples; ++i) row[i] = (unsigned char)(row[i] + row[i - 1]);
+            } else {
+                uint64_t prev = 0;
+                for (size_t i = 0; i < row_samples; ++i) {
+                    uint64_t v = 0;
+                    for (size_t q = 0; q < bytes_per_sample; ++q)
+                        v |= (uint64_t)row[i * bytes_per_sample + (file_little ? q : bytes_per_sample - 1 - q)] << (8 * q);
+                    v = (i == 0) ? v : v + prev;
+                    prev = v;
+                    for (size_t q = 0; q < bytes_per_sample; ++q)
+                        row[i * bytes_per_sample + (file_little ? q : bytes_per_sample - 1 - q)] = (unsigned char)(v >> (8 * q));
+                }
+            }
+        }
+    }
+}
 
 double sampleAsDouble(const unsigned char* p, int bps, int fmt, bool file_little) {
     const int nb = bps / 8;
@@ -158,8 +258,13 @@ void checkSupported(const Ifd& d, const std::string& name, int& w, int& h, uint1
            << ", BPS=" << bps << ", Planar=" << planar << ", SPP=" << spp << ").";
         amrex::Abort(ss.str());
     }
-    if (d.get(T_COMPRESSION, 1) != 1)
-        amrex::Abort("[TiffReader] compressed TIFF data needs libtiff, which this build does not have: " + name);
+    const uint64_t comp = d.get(T_COMPRESSION, 1);
+    if (comp != C_NONE && comp != C_LZW && comp != C_DEFLATE && comp != C_DEFLATE_OLD && comp != C_PACKBITS)
+        amrex::Abort("[TiffReader] unsupported TIFF compression scheme " + std::to_string(comp) + " in: " + name +
+                     " (supported: none, LZW, Deflate, PackBits)");
+    const uint64_t pred = d.get(T_PREDICTOR, 1);
+    if (pred != 1 && !(pred == 2 && bps >= 8 && fmt != 3))
+        amrex::Abort("[TiffReader] unsupported TIFF predictor " + std::to_string(pred) + " in: " + name);
 }
 
 }  // namespace
@@ -230,6 +335,7 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
 
     auto decodeDirectory = [&](TiffFile& f, const Ifd& d, int k) {
         const bool file_little = f.littleEndian();
+        const uint64_t comp = d.get(T_COMPRESSION, 1), pred = d.get(T_PREDICTOR, 1);
         if (d.arr(T_TILEOFFSETS)) {                                   // tiled, reference :354-393
             const int tw = (int)d.get(T_TILEWIDTH, 0), th = (int)d.get(T_TILELENGTH, 0);
             const auto* offs = d.arr(T_TILEOFFSETS);
@@ -237,9 +343,12 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
             if (tw <= 0 || th <= 0 || !cnts) amrex::Abort("Invalid tile params.");
             const int tiles_x = (W + tw - 1) / tw;
             for (size_t t = 0; t < offs->size(); ++t) {
-                const size_t nbytes = (size_t)(*cnts)[t];
-                buf.resize(nbytes);
-                f.readAt((*offs)[t], buf.data(), nbytes);
+                buf.resize((size_t)(*cnts)[t]);
+                f.readAt((*offs)[t], buf.data(), buf.size());
+                if (comp != C_NONE || pred != 1)
+                    decodeSegment(buf, comp, pred, bps == 1 ? ((size_t)tw * th + 7) / 8 : (size_t)tw * th * bytes_per_sample,
+                                  (size_t)tw, bytes_per_sample, file_little);
+                const size_t nbytes = buf.size();
                 const int ox = (int)(t % tiles_x) * tw, oy = (int)(t / tiles_x) * th;
                 for (int j = oy; j < std::min(oy + th, H); ++j)
                     for (int i = ox; i < std::min(ox + tw, W); ++i) {
@@ -267,9 +376,16 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
                 if (oy >= H) break;
                 const int rows = (int)std::min<uint64_t>(rps, (uint64_t)(H - oy));
                 const size_t expect = bps == 1 ? pitch1 * rows : (size_t)W * rows * bytes_per_sample;
-                const size_t nbytes = cnts && s < cnts->size() ? std::min<size_t>((size_t)(*cnts)[s], expect) : expect;
-                buf.resize(nbytes);
-                f.readAt((*offs)[s], buf.data(), nbytes);
+                if (comp == C_NONE) {
+                    buf.resize(cnts && s < cnts->size() ? std::min<size_t>((size_t)(*cnts)[s], expect) : expect);
+                    f.readAt((*offs)[s], buf.data(), buf.size());
+                } else {
+                    if (!cnts || s >= cnts->size()) amrex::Abort("[TiffReader] compressed TIFF without strip byte counts.");
+                    buf.resize((size_t)(*cnts)[s]);
+                    f.readAt((*offs)[s], buf.data(), buf.size());
+                }
+                if (comp != C_NONE || pred != 1) decodeSegment(buf, comp, pred, expect, (size_t)W, bytes_per_sample, file_little);
+                const size_t nbytes = buf.size();
                 for (int j = oy; j < oy + rows; ++j)
                     for (int i = 0; i < W; ++i) {
                         double v = 0.0;

@@ -62,6 +62,40 @@ def test_readers_agree_with_oracle_decoder(host_bins):
         assert int(field(r.stdout, "DirectCount1")[0]) == int(ph.sum())
 
 
+@pytest.mark.parametrize("compression", ["tiff_lzw", "tiff_adobe_deflate", "packbits"])
+@pytest.mark.parametrize("kind", ["u8", "u16", "bit", "u8_pred"])
+def test_compressed_tiff_stacks(host_bins, tmp_path, compression, kind):
+    """Compressed stacks (libtiff decodes them for the reference, src/io/TiffReader.cpp:289-444):
+    written with Pillow, read back by the host reader, counted against numpy."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(17)
+    nz, ny, nx = 5, 37, 70                                   # not multiples of 8: partial bytes / strips
+    base = (rng.random((nz, ny, nx)) < 0.4)
+    base[:, 10:20, :] = True                                 # long runs so the coders really compress
+    extra = {}
+    if kind == "u8":
+        vol, thr = (base * 200 + rng.integers(0, 50, base.shape)).astype(np.uint8), 100
+        pages = [Image.fromarray(p) for p in vol]
+    elif kind == "u8_pred":
+        if compression == "packbits":
+            pytest.skip("predictor applies to LZW / Deflate only")
+        vol, thr = (base * 200 + rng.integers(0, 50, base.shape)).astype(np.uint8), 100
+        pages = [Image.fromarray(p) for p in vol]
+        extra = {"tiffinfo": {317: 2}}
+    elif kind == "u16":
+        vol, thr = (base * 30000 + rng.integers(0, 5000, base.shape)).astype(np.uint16), 20000
+        pages = [Image.fromarray(p) for p in vol]
+    else:
+        vol, thr = base.astype(np.uint8), 0.5
+        pages = [Image.fromarray(p * 255).convert("1") for p in vol]
+    f = tmp_path / f"stack_{kind}_{compression}.tif"
+    pages[0].save(f, save_all=True, append_images=pages[1:], compression=compression, **extra)
+    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}")
+    assert [int(v) for v in field(r.stdout, "Dims")] == [nx, ny, nz]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > thr).sum())
+
+
 def test_dat_reader(host_bins, tmp_path):
     # src/io/DatReader.cpp:60-248: int32 LE (W, H, D) header + uint16 LE voxels, x fastest
     import numpy as np
