@@ -65,33 +65,56 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     typedef typename Vec2<mg_t>::type mg2;
     // Every vector here is zero on cells that are not unknowns (solid, non-percolating,
     // Dirichlet planes: p = q = r = 0 there and x keeps its value), so a 16-byte pair
-    // without an unknown is skipped: its sectors are never fetched or written.  Two
-    // pairs per trip keep two dependent flag -> data chains in flight.
-    auto body = [&](long long i, unsigned int f2) {
-        double2 xv = *reinterpret_cast<double2*>(x + i);
-        double2 rv = *reinterpret_cast<double2*>(r + i);
-        const double2 pv = *reinterpret_cast<const double2*>(p + i);
-        const double2 qv = *reinterpret_cast<const double2*>(q + i);
-        xv.x += a * pv.x; xv.y += a * pv.y;
-        rv.x -= a * qv.x; rv.y -= a * qv.y;
-        *reinterpret_cast<double2*>(x + i) = xv;
-        *reinterpret_cast<double2*>(r + i) = rv;
-        acc += rv.x * rv.x + rv.y * rv.y;
-        const unsigned int f0 = f2 & 0xffu, f1 = f2 >> 8;
-        mg2 rr, zv;
-        rr.x = (mg_t)rv.x; rr.y = (mg_t)rv.y;
-        zv.x = (f0 & F_UNK) ? (mg_t)(rv.x * winv[f0 & 63u]) : (mg_t)0;
-        zv.y = (f1 & F_UNK) ? (mg_t)(rv.y * winv[f1 & 63u]) : (mg_t)0;
-        *reinterpret_cast<mg2*>(r32 + i) = rr;
-        *reinterpret_cast<mg2*>(z1 + i) = zv;
-    };
+    // without an unknown is skipped: its sectors are never fetched or written.  NC pairs
+    // per trip, all their loads issued before the first store (the compiler cannot
+    // reorder a load of x[i2] over a store to x[i]), and the flags of the next trip are
+    // fetched a trip ahead, so the flag -> data dependency is off the critical path.
+    constexpr int NC = 4;
     constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
-    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += 2 * stride) {
-        const long long i2 = i + stride;
-        const unsigned int fa = *reinterpret_cast<const unsigned short*>(flags + i);
-        const unsigned int fb = (i2 < n2) ? *reinterpret_cast<const unsigned short*>(flags + i2) : 0u;
-        if (fa & UNK2) body(i, fa);
-        if (fb & UNK2) body(i2, fb);
+    const long long i0 = ((long long)blockIdx.x * VT + threadIdx.x) * 2;
+    unsigned int fnext[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const long long ii = i0 + c * stride;
+        fnext[c] = (ii < n2) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
+    }
+    for (long long i = i0; i < n2; i += NC * stride) {
+        unsigned int f[NC];
+        double2 xv[NC], rv[NC], pv[NC], qv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            f[c] = fnext[c];
+            const long long in = i + (NC + c) * stride;
+            fnext[c] = (in < n2) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (f[c] & UNK2) {
+                const long long ii = i + c * stride;
+                xv[c] = *reinterpret_cast<const double2*>(x + ii);
+                rv[c] = *reinterpret_cast<const double2*>(r + ii);
+                pv[c] = *reinterpret_cast<const double2*>(p + ii);
+                qv[c] = *reinterpret_cast<const double2*>(q + ii);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (f[c] & UNK2) {
+                const long long ii = i + c * stride;
+                xv[c].x += a * pv[c].x; xv[c].y += a * pv[c].y;
+                rv[c].x -= a * qv[c].x; rv[c].y -= a * qv[c].y;
+                *reinterpret_cast<double2*>(x + ii) = xv[c];
+                *reinterpret_cast<double2*>(r + ii) = rv[c];
+                acc += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
+                const unsigned int f0 = f[c] & 0xffu, f1 = f[c] >> 8;
+                mg2 rr, zv;
+                rr.x = (mg_t)rv[c].x; rr.y = (mg_t)rv[c].y;
+                zv.x = (f0 & F_UNK) ? (mg_t)(rv[c].x * winv[f0 & 63u]) : (mg_t)0;
+                zv.y = (f1 & F_UNK) ? (mg_t)(rv[c].y * winv[f1 & 63u]) : (mg_t)0;
+                *reinterpret_cast<mg2*>(r32 + ii) = rr;
+                *reinterpret_cast<mg2*>(z1 + ii) = zv;
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
         const long long i = n2;
@@ -116,18 +139,38 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
     const long long n2 = n & ~1LL;
     typedef typename Vec2<mg_t>::type mg2;
     constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
-    auto body = [&](long long i) {
-        double2 pv = *reinterpret_cast<double2*>(p + i);
-        const mg2 zv = *reinterpret_cast<const mg2*>(z + i);
-        pv.x = (double)zv.x + bta * pv.x; pv.y = (double)zv.y + bta * pv.y;
-        *reinterpret_cast<double2*>(p + i) = pv;
-    };
-    for (long long i = ((long long)blockIdx.x * VT + threadIdx.x) * 2; i < n2; i += 2 * stride) {
-        const long long i2 = i + stride;
-        const unsigned int fa = *reinterpret_cast<const unsigned short*>(flags + i);
-        const unsigned int fb = (i2 < n2) ? *reinterpret_cast<const unsigned short*>(flags + i2) : 0u;
-        if (fa & UNK2) body(i);
-        if (fb & UNK2) body(i2);
+    constexpr int NC = 4;            // pairs per trip: loads first, then stores (see axpy2_dot_first_kernel)
+    const long long i0 = ((long long)blockIdx.x * VT + threadIdx.x) * 2;
+    unsigned int fnext[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const long long ii = i0 + c * stride;
+        fnext[c] = (ii < n2) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
+    }
+    for (long long i = i0; i < n2; i += NC * stride) {
+        unsigned int f[NC];
+        double2 pv[NC];
+        mg2 zv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            f[c] = fnext[c];
+            const long long in = i + (NC + c) * stride;
+            fnext[c] = (in < n2) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (f[c] & UNK2) {
+                pv[c] = *reinterpret_cast<const double2*>(p + i + c * stride);
+                zv[c] = *reinterpret_cast<const mg2*>(z + i + c * stride);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (f[c] & UNK2) {
+                pv[c].x = (double)zv[c].x + bta * pv[c].x; pv[c].y = (double)zv[c].y + bta * pv[c].y;
+                *reinterpret_cast<double2*>(p + i + c * stride) = pv[c];
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = (double)z[n2] + bta * p[n2];
 }
