@@ -390,15 +390,16 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
         if (P.mine[i].off0 == off0) { id = (int)i; break; }
     if (id < 0) return false;
     const int rk = S->rank, nr = S->n_ranks;
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;     // periodic box: rank 0 and rank nr-1 are neighbours
     const unsigned int seq = ++P.seq;
     char *dst_lo = nullptr, *dst_hi = nullptr;
     unsigned int *flag_lo = nullptr, *flag_hi = nullptr;
-    if (rk > 0) {          // my bottom plane -> lower neighbour's ghost plane above its top
+    if (rk > 0 || wrap) {  // my bottom plane -> lower neighbour's ghost plane above its top
         const HaloDesc& d = P.lo.f[id];
         dst_lo = P.lo_base + d.off0 + d.plane_bytes * (unsigned long long)d.nz;
         flag_lo = reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1;
     }
-    if (rk < nr - 1) {     // my top plane -> upper neighbour's ghost plane below its plane 0
+    if (rk < nr - 1 || wrap) {   // my top plane -> upper neighbour's ghost plane below its plane 0
         const HaloDesc& d = P.hi.f[id];
         dst_hi = P.hi_base + d.off0 - d.plane_bytes;
         flag_hi = reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0;
@@ -407,8 +408,8 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
                   seq, P.counter, S->n_sm, S->st);
     S->launches++;
     P.exchanges++;
-    const unsigned int* wa = rk > 0 ? P.flags + 0 : nullptr;
-    const unsigned int* wb = rk < nr - 1 ? P.flags + 1 : nullptr;
+    const unsigned int* wa = (rk > 0 || wrap) ? P.flags + 0 : nullptr;
+    const unsigned int* wb = (rk < nr - 1 || wrap) ? P.flags + 1 : nullptr;
     PFN_stream_wait32 wait32 = P.spin_wait ? nullptr : driver_wait32();
     if (wait32) {
         if (wa && wait32(S->st, (CUdeviceptr)(uintptr_t)wa, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
@@ -422,30 +423,35 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
     return true;
 }
 
+// whole box in z on this rank and periodic: the ghost planes are the opposite faces
+void wrap_ghosts_locally(oi_solver* S, void* plane0, size_t plane_bytes, long long nz) {
+    if (!(S->g.periodic & oi::PER_Z)) return;
+    char* q = static_cast<char*>(plane0);
+    CUDA_CHECK(cudaMemcpyAsync(q - plane_bytes, q + plane_bytes * (size_t)(nz - 1), plane_bytes,
+                               cudaMemcpyDeviceToDevice, S->st));
+    CUDA_CHECK(cudaMemcpyAsync(q + plane_bytes * (size_t)nz, q, plane_bytes, cudaMemcpyDeviceToDevice, S->st));
+}
+
 void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long long nz) {
     // send plane 0 down / plane nz-1 up; receive into plane -1 / plane nz
     if (S->n_ranks <= 1) {
-        if (S->g.periodic & oi::PER_Z) {      // periodic box on one slab: wrap the ghost planes locally
-            char* q = static_cast<char*>(plane0);
-            CUDA_CHECK(cudaMemcpyAsync(q - plane_bytes, q + plane_bytes * (size_t)(nz - 1), plane_bytes,
-                                       cudaMemcpyDeviceToDevice, S->st));
-            CUDA_CHECK(cudaMemcpyAsync(q + plane_bytes * (size_t)nz, q, plane_bytes, cudaMemcpyDeviceToDevice, S->st));
-        }
+        wrap_ghosts_locally(S, plane0, plane_bytes, nz);
         return;
     }
     if (halo_exchange_peer(S, static_cast<char*>(plane0), plane_bytes, nz)) return;
     NcclApi& N = nccl_api();
     char* p0 = static_cast<char*>(plane0);
     const int rk = S->rank, nr = S->n_ranks;
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+    const int lo = rk > 0 ? rk - 1 : (wrap ? nr - 1 : -1);
+    const int hi = rk < nr - 1 ? rk + 1 : (wrap ? 0 : -1);
+    // posting order bottom-send, top-ghost-recv, top-send, bottom-ghost-recv also pairs up
+    // correctly when lo == hi (two slabs of a periodic box)
     NCCL_CHECK(N.GroupStart());
-    if (rk > 0) {
-        NCCL_CHECK(N.Send(p0, plane_bytes, ncclUint8, rk - 1, S->comm, S->st));
-        NCCL_CHECK(N.Recv(p0 - plane_bytes, plane_bytes, ncclUint8, rk - 1, S->comm, S->st));
-    }
-    if (rk < nr - 1) {
-        NCCL_CHECK(N.Send(p0 + plane_bytes * (size_t)(nz - 1), plane_bytes, ncclUint8, rk + 1, S->comm, S->st));
-        NCCL_CHECK(N.Recv(p0 + plane_bytes * (size_t)nz, plane_bytes, ncclUint8, rk + 1, S->comm, S->st));
-    }
+    if (lo >= 0) NCCL_CHECK(N.Send(p0, plane_bytes, ncclUint8, lo, S->comm, S->st));
+    if (hi >= 0) NCCL_CHECK(N.Recv(p0 + plane_bytes * (size_t)nz, plane_bytes, ncclUint8, hi, S->comm, S->st));
+    if (hi >= 0) NCCL_CHECK(N.Send(p0 + plane_bytes * (size_t)(nz - 1), plane_bytes, ncclUint8, hi, S->comm, S->st));
+    if (lo >= 0) NCCL_CHECK(N.Recv(p0 - plane_bytes, plane_bytes, ncclUint8, lo, S->comm, S->st));
     NCCL_CHECK(N.GroupEnd());
 }
 
@@ -456,7 +462,10 @@ inline void halo0(oi_solver* S, T* v) {
     halo_exchange_bytes(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz);
 }
 inline void haloL(oi_solver* S, const CoarseLevel& L, mg_t* v) {
-    if (L.replicated) return;          // whole level on every rank: ghost planes are the (zero) box faces
+    if (L.replicated) {                // whole level on every rank: ghost planes are the box faces
+        wrap_ghosts_locally(S, v, (size_t)L.plane * sizeof(mg_t), L.nz);
+        return;
+    }
     halo_exchange_bytes(S, v, (size_t)L.plane * sizeof(mg_t), L.nz);
 }
 
@@ -724,21 +733,23 @@ bool peer_setup(oi_solver* S) {
         if (b.serial != 0) C.maps[key] = m;
         return static_cast<char*>(m);
     };
-    if (ok && rk > 0) {
-        P.lo = all[rk - 1];
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+    const bool has_lo = rk > 0 || wrap, has_hi = rk < nr - 1 || wrap;
+    if (ok && has_lo) {
+        P.lo = all[(rk + nr - 1) % nr];
         P.lo_base = map_peer(P.lo);
         if (!P.lo_base) ok = 0;
     }
-    if (ok && rk < nr - 1) {
-        P.hi = all[rk + 1];
+    if (ok && has_hi) {
+        P.hi = all[(rk + 1) % nr];
         P.hi_base = map_peer(P.hi);
         if (!P.hi_base) ok = 0;
     }
     // flag round trip (sequence number 1), checked from the host so a broken path
     // cannot hang a stream
     if (ok) {
-        unsigned int* flo = rk > 0 ? reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1 : nullptr;
-        unsigned int* fhi = rk < nr - 1 ? reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0 : nullptr;
+        unsigned int* flo = has_lo ? reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1 : nullptr;
+        unsigned int* fhi = has_hi ? reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0 : nullptr;
         oi::halo_push(nullptr, nullptr, nullptr, nullptr, 0, flo, fhi, 1u, P.counter, S->n_sm, S->st);
         S->launches++;
         if (cudaStreamSynchronize(S->st) != cudaSuccess) { cudaGetLastError(); ok = 0; }
@@ -747,8 +758,8 @@ bool peer_setup(oi_solver* S) {
     if (ok) {
         unsigned int hf[2] = {0, 0};
         CUDA_CHECK(cudaMemcpy(hf, P.flags, sizeof(hf), cudaMemcpyDeviceToHost));
-        if (rk > 0 && hf[0] != 1u) ok = 0;
-        if (rk < nr - 1 && hf[1] != 1u) ok = 0;
+        if (has_lo && hf[0] != 1u) ok = 0;
+        if (has_hi && hf[1] != 1u) ok = 0;
     }
     // every rank must take the same path
     int neg = ok ? 0 : 1;
@@ -778,6 +789,8 @@ void build_hierarchy(oi_solver* S) {
             gather_level(S, lv[l - 1], lv[l - 1].cyp.p, lv[l].cyp.p);
             gather_level(S, lv[l - 1], lv[l - 1].czp.p, lv[l].czp.p);
             gather_level(S, lv[l - 1], lv[l - 1].dg.p, lv[l].dg.p);
+            wrap_ghosts_locally(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
+            wrap_ghosts_locally(S, lv[l].dg.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
             continue;
         }
         if (l == 0) {
@@ -787,7 +800,11 @@ void build_hierarchy(oi_solver* S) {
             oi::coarse_build_from_coarse(lv[l - 1].L, lv[l].L, S->mg_scale, S->st);
         }
         S->launches++;
-        if (lv[l].replicated) continue;
+        if (lv[l].replicated) {
+            wrap_ghosts_locally(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
+            wrap_ghosts_locally(S, lv[l].dg.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
+            continue;
+        }
         // ghost planes of the z-coupling and the diagonal (read by the -z neighbour
         // coupling and by the fused prolongation)
         halo_exchange_bytes(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
@@ -810,6 +827,7 @@ void coarse_cycle(oi_solver* S, size_t l) {
         coarse_cycle(S, l + 1);
         prof_mark(S, "mg gather");
         const size_t plane = (size_t)L.plane;
+        wrap_ghosts_locally(S, w.L.x, plane * sizeof(mg_t), w.L.nz);
         CUDA_CHECK(cudaMemcpyAsync(L.x - plane, w.L.x + plane * (size_t)L.z0 - plane, plane * (size_t)(L.nz + 2) * sizeof(mg_t),
                                    cudaMemcpyDeviceToDevice, S->st));
         return;
@@ -1119,8 +1137,18 @@ void build_mask_cell_problem(oi_solver* S) {
     zero_mg_vectors(S);
     oi::cellp_rhs(g, S->flags.p, nullptr, S->prm.direction, 1.0, S->d_partials, S->d_counter, S->d_scal + 7, S->st);
     S->launches++;
+    allreduce_sum_f64(S, S->d_scal + 7, 1);
     S->cellp_b2 = read_scalar(S, S->d_scal + 7);
-    S->n_active = S->phase_count_local;        // single slab (checked at create)
+    {
+        unsigned long long h = (unsigned long long)S->phase_count_local;
+        if (S->n_ranks > 1) {
+            CUDA_CHECK(cudaMemcpyAsync(S->d_ull + 5, &h, sizeof(h), cudaMemcpyHostToDevice, S->st));
+            allreduce_sum_u64(S, S->d_ull + 5, 1);
+            CUDA_CHECK(cudaMemcpyAsync(&h, S->d_ull + 5, sizeof(h), cudaMemcpyDeviceToHost, S->st));
+            CUDA_CHECK(cudaStreamSynchronize(S->st));
+        }
+        S->n_active = (long long)h;
+    }
     S->n_in = S->n_out = 0;
     S->mask_built = true;
 }
@@ -1450,7 +1478,6 @@ int oi_create(oi_solver** out, const oi_params* p) {
         g.periodic = 0; g.diag_full = 0.0;
         OI_REQUIRE(p->problem == OI_PROBLEM_TORTUOSITY || p->problem == OI_PROBLEM_CELL, "bad problem kind");
         if (p->problem == OI_PROBLEM_CELL) {
-            OI_REQUIRE(n_ranks == 1, "the homogenisation cell problem is single-slab in this build");
             g.periodic = oi::PER_X | oi::PER_Y | oi::PER_Z;            // Diffusion.cpp:306-308
             g.diag_full = 2.0 * (g.cx + g.cy + g.cz);                  // EffDiffFillMtx.F90:150-220
         }
@@ -1659,6 +1686,7 @@ int oi_cell_gradient_sums(oi_solver* S, double* sums3, int64_t* n_active) {
             halo0(S, S->x.p);
             oi::cellp_grad_sums(S->g, S->flags.p, S->x.p, S->d_partials, S->d_counter, S->d_scal + 4, S->st);
             S->launches++;
+            allreduce_sum_f64(S, S->d_scal + 4, 3);
             CUDA_CHECK(cudaMemcpyAsync(S->h_pinned + 4, S->d_scal + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
             CUDA_CHECK(cudaStreamSynchronize(S->st));
             for (int a = 0; a < 3; ++a) sums3[a] = S->h_pinned[4 + a];

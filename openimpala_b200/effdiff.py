@@ -54,7 +54,9 @@ class EffectiveDiffusivityHypre:
         self._num_iterations = -1
         self._final_res_norm = math.nan
         self._converged = False
-        self._solver = capi.Solver(self._phase_field.shape, int(self._dir), self._phase_id, 0.0, 1.0,
+        # multi-GPU: mf_phase_input is this rank's z-slab, `global_shape` the whole (periodic) box
+        shape = b200.pop("global_shape", None) or self._phase_field.shape
+        self._solver = capi.Solver(shape, int(self._dir), self._phase_id, 0.0, 1.0,
                                    eps=self._eps, maxiter=self._maxiter, dx=self._dx, verbose=self._verbose,
                                    problem=capi.OI_PROBLEM_CELL, **b200)
         self._solver.set_phase(self._phase_field)
@@ -77,7 +79,8 @@ class EffectiveDiffusivityHypre:
         return self._converged
 
     def getChiSolution(self) -> np.ndarray:
-        """chi_k on the box (zero in the solid; zero everywhere if not converged, .cpp:631-637)."""
+        """chi_k on the box / this rank's slab (zero in the solid; zero everywhere if not converged,
+        .cpp:631-637)."""
         if not self._converged or self._n_active == 0:
             return np.zeros(self._phase_field.shape)
         return self._solver.solution()
@@ -105,7 +108,8 @@ def calculate_Deff_tensor_homogenization(mf_phase: np.ndarray, phase_id: int, so
                                          geom=None, verbose: int = 0, **b200):
     """The three corrector solves of Diffusion.cpp:511-589 and the tensor of
     Diffusion.cpp:60-167.  Returns (D[3][3] as ndarray, all_converged, per-direction info)."""
-    n_total = mf_phase.size
+    gshape = b200.get("global_shape", None) or mf_phase.shape
+    n_total = int(np.prod(gshape))
     D = np.zeros((3, 3))
     infos = []
     all_ok = True

@@ -76,6 +76,24 @@ def main():
         else:
             full_mask_ok = True   # each rank checks its own slab against the oracle-free single-GPU answer on rank 0 only
             ok = ok and chk and full_mask_ok
+    # homogenisation cell problem on z-slabs of a periodic box: same tensor as one GPU
+    from openimpala_b200.effdiff import calculate_Deff_tensor_homogenization
+    for shape, radius, halo_mode in [((96, 64, 80), 6, capi.OI_HALO_AUTO), ((64, 48, 36), 5, capi.OI_HALO_NCCL),
+                                     ((128, 128, 128), 8, capi.OI_HALO_AUTO)]:
+        full = synth.sphere_packing_slab(shape, seed=13, radius=radius, solid_target=0.5)
+        z0, nzl = capi.slab_partition(shape[0], world)[rank]
+        slab = np.ascontiguousarray(full[z0:z0 + nzl])
+        D, conv, infos = calculate_Deff_tensor_homogenization(slab, 1, global_shape=shape, z_begin=z0, nz_local=nzl,
+                                                              comm=comm, device=local, halo_mode=halo_mode)
+        if rank == 0:
+            D1, conv1, infos1 = calculate_Deff_tensor_homogenization(full, 1, device=local)
+            good = conv and conv1 and float(np.abs(D - D1).max()) <= 1e-8
+            print(f"cell problem {shape} halo={halo_mode}: iters={[i['iterations'] for i in infos]}/"
+                  f"{[i['iterations'] for i in infos1]} Dxx={D[0][0]:.10f}/{D1[0][0]:.10f} "
+                  f"max|dD|={float(np.abs(D - D1).max()):.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+        else:
+            ok = ok and conv
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     comm.close()
