@@ -78,12 +78,22 @@ to_isphase_kernel(const T* __restrict__ in, uint8_t* __restrict__ out, long long
 // ------------------------------------------------------------------ K2: union-find CCL
 // Read-only root search: safe while other threads hook roots with atomicMin
 // (every value ever stored in L[i] is a smaller index of the same final set).
-__device__ __forceinline__ int uf_find(const int* L, int i) {
-    while (true) {
-        const int p = __ldcg(&L[i]);   // L2: other SMs hook roots concurrently
-        if (p == i) return i;
-        i = p;
+// Parents are always smaller indices of the same set, so a chain is strictly
+// decreasing; on the way up every visited node is re-pointed at its grandparent
+// (path halving with plain L2 stores, as in ECL-CC): a racing store can only replace
+// one valid ancestor by another, never leave the set.  Without it the giant pore
+// component of a packing builds parent chains thousands of links long.
+__device__ __forceinline__ int uf_find(int* L, int i) {
+    int curr = __ldcg(&L[i]);          // L2: other SMs hook roots concurrently
+    if (curr != i) {
+        int prev = i, next;
+        while (curr > (next = __ldcg(&L[curr]))) {
+            __stcg(&L[prev], next);
+            prev = curr;
+            curr = next;
+        }
     }
+    return curr;
 }
 
 // Label-equivalence union (Komura / Playne-Hawick): hook the larger root under
