@@ -133,6 +133,19 @@ int oi_set_phase_i32(oi_solver* h, const int32_t* host_phase);
 int oi_set_phase_u8(oi_solver* h, const uint8_t* host_phase);
 int oi_set_phase_device_u8(oi_solver* h, const void* device_phase);
 
+/* Streamed alternative to oi_set_phase_u8 for images that should never sit whole in host
+ * memory (the reference re-opens the TIFF per tile and z-slice, src/io/TiffReader.cpp:320-338):
+ * the slab arrives in z-chunks of at most max_planes_per_chunk planes through two
+ * library-owned PINNED staging buffers.  The caller decodes a chunk straight into
+ * oi_phase_stream_buffer(h, which), submits it (asynchronous H2D copy + count + conversion
+ * to the device mask) and decodes the next chunk into the other buffer meanwhile;
+ * oi_phase_stream_buffer waits until the upload that last used that buffer has left it.
+ * Every plane of the slab must be submitted exactly once before oi_phase_stream_end. */
+int oi_phase_stream_begin(oi_solver* h, int32_t max_planes_per_chunk);
+int oi_phase_stream_buffer(oi_solver* h, int32_t which, uint8_t** host_buffer);
+int oi_phase_stream_submit(oi_solver* h, int32_t which, int32_t z_local_begin, int32_t nz_chunk);
+int oi_phase_stream_end(oi_solver* h);
+
 /* Global counts over the resident phase field (VolumeFraction.cpp:22-66). */
 int oi_volume_fraction(oi_solver* h, int64_t* phase_count, int64_t* total_count);
 

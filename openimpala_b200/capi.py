@@ -67,6 +67,10 @@ _SIGS = {
     "oi_set_phase_i32": (C.c_int, [_P, _P]),
     "oi_set_phase_u8": (C.c_int, [_P, _P]),
     "oi_set_phase_device_u8": (C.c_int, [_P, _P]),
+    "oi_phase_stream_begin": (C.c_int, [_P, C.c_int32]),
+    "oi_phase_stream_buffer": (C.c_int, [_P, C.c_int32, C.POINTER(C.POINTER(C.c_uint8))]),
+    "oi_phase_stream_submit": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "oi_phase_stream_end": (C.c_int, [_P]),
     "oi_volume_fraction": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_remspot": (C.c_int, [_P, C.c_int32]),
     "oi_build_mask": (C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -254,6 +258,24 @@ class Solver:
         else:
             a = np.ascontiguousarray(a, dtype=np.int32)
             _check(self._lib.oi_set_phase_i32(self._h, a.ctypes.data))
+
+    def set_phase_streamed(self, read_planes, planes_per_chunk: int = 16):
+        """Streamed upload: read_planes(z0, nz, out) fills out[nz, ny, nx] (uint8, a view of a
+        pinned staging buffer) with planes z0 .. z0+nz-1 of the local slab; decoding of chunk
+        k+1 overlaps the upload of chunk k."""
+        nz, ny, nx = self.local_shape
+        chunk = max(1, min(int(planes_per_chunk), nz))
+        _check(self._lib.oi_phase_stream_begin(self._h, chunk))
+        which = 0
+        for z0 in range(0, nz, chunk):
+            n = min(chunk, nz - z0)
+            buf = C.POINTER(C.c_uint8)()
+            _check(self._lib.oi_phase_stream_buffer(self._h, which, C.byref(buf)))
+            view = np.ctypeslib.as_array(buf, shape=(chunk, ny, nx))
+            read_planes(z0, n, view[:n])
+            _check(self._lib.oi_phase_stream_submit(self._h, which, z0, n))
+            which ^= 1
+        _check(self._lib.oi_phase_stream_end(self._h))
 
     def set_phase_device(self, dev_ptr: int):
         _check(self._lib.oi_set_phase_device_u8(self._h, _P(dev_ptr)))

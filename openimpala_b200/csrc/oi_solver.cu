@@ -201,6 +201,24 @@ struct PinnedCache {
 };
 PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
 
+// Large pinned staging buffers of the streamed upload, recycled by exact size.
+struct PinnedStageCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> idle;
+    void* get(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = idle.find(bytes);
+            if (it != idle.end()) { void* p = it->second; idle.erase(it); return p; }
+        }
+        void* p = nullptr;
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return p;
+    }
+    void put(size_t bytes, void* p) { if (p) { std::lock_guard<std::mutex> lk(mu); idle.insert({bytes, p}); } }
+};
+PinnedStageCache& stage_cache() { static PinnedStageCache* c = new PinnedStageCache(); return *c; }
+
 // Mappings of neighbours' arenas (CUDA IPC) are kept for the life of the process,
 // keyed by the exporting process and the serial number of its allocation, so a
 // re-created handle whose neighbours reuse their cached arenas maps nothing.
@@ -335,6 +353,13 @@ struct oi_solver {
     ncclComm_t comm = nullptr;
     std::vector<int> all_z0, all_nz;   // slab table (every rank)
     PeerHalo peer;                     // peer-memory halo exchange (n_ranks > 1)
+    // streamed phase upload (oi_phase_stream_*): two pinned host / device staging pairs
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
+    int stage_planes = 0;
+    long long stream_planes_received = -1;      // -1: no stream open
     // OI_PROFILE=1: CUDA-event marks at phase boundaries of the solve, summed per phase
     bool prof_on = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
@@ -1590,6 +1615,11 @@ int oi_destroy(oi_solver* S) {
         if (S->d_changed) cfree(S->d_changed);
         const auto t2 = now();
         pinned_cache().put(S->h_pinned);
+        for (int w = 0; w < 2; ++w) {
+            if (S->h_stage[w]) stage_cache().put((size_t)S->stage_planes * (size_t)S->g.plane, S->h_stage[w]);
+            if (S->d_stage[w]) cfree(S->d_stage[w]);
+            if (S->stage_done[w]) cudaEventDestroy(S->stage_done[w]);
+        }
         const auto t3 = now();
         for (auto& e : S->timer) if (e) cudaEventDestroy(e);
         for (auto& m : S->prof_marks) cudaEventDestroy(m.second);
@@ -1613,6 +1643,89 @@ int oi_set_phase_device_u8(oi_solver* S, const void* dev) {
     return guarded([&] {
         OI_REQUIRE(S && dev, "null argument");
         set_phase_common<uint8_t>(S, static_cast<const uint8_t*>(dev), true);
+    });
+}
+
+int oi_phase_stream_begin(oi_solver* S, int32_t max_planes_per_chunk) {
+    return guarded([&] {
+        OI_REQUIRE(S, "null handle");
+        OI_REQUIRE(max_planes_per_chunk > 0, "chunk size must be positive");
+        ensure_device(S);
+        const int planes = std::min<int>(max_planes_per_chunk, S->g.nz);
+        if (S->stage_planes != planes) {
+            for (int w = 0; w < 2; ++w) {
+                if (S->h_stage[w]) stage_cache().put((size_t)S->stage_planes * (size_t)S->g.plane, S->h_stage[w]);
+                if (S->d_stage[w]) cfree(S->d_stage[w]);
+                S->h_stage[w] = nullptr; S->d_stage[w] = nullptr;
+            }
+            S->stage_planes = planes;
+        }
+        const size_t bytes = (size_t)planes * (size_t)S->g.plane;
+        for (int w = 0; w < 2; ++w) {
+            if (!S->h_stage[w]) {
+                S->h_stage[w] = static_cast<uint8_t*>(stage_cache().get(bytes));
+                if (!S->h_stage[w]) throw OiError(OI_ERR_NOMEM, "cannot allocate the pinned staging buffer");
+            }
+            if (!S->d_stage[w]) CUDA_CHECK(cmalloc(&S->d_stage[w], bytes));
+            if (!S->stage_done[w]) CUDA_CHECK(cudaEventCreateWithFlags(&S->stage_done[w], cudaEventDisableTiming));
+            S->stage_busy[w] = false;
+        }
+        if (!S->d_isphase) CUDA_CHECK(cmalloc(&S->d_isphase, (size_t)S->n_local));
+        CUDA_CHECK(cudaMemsetAsync(S->d_ull + 4, 0, 2 * sizeof(unsigned long long), S->st));
+        S->stream_planes_received = 0;
+        S->phase_count_local = -1;
+        S->mask_built = false;
+        S->solved = false;
+    });
+}
+
+int oi_phase_stream_buffer(oi_solver* S, int32_t which, uint8_t** host_buffer) {
+    return guarded([&] {
+        OI_REQUIRE(S && host_buffer && (which == 0 || which == 1), "bad argument");
+        OI_REQUIRE(S->stream_planes_received >= 0, "oi_phase_stream_buffer: call oi_phase_stream_begin first");
+        ensure_device(S);
+        if (S->stage_busy[which]) {          // the upload that last used this buffer must have left it
+            CUDA_CHECK(cudaEventSynchronize(S->stage_done[which]));
+            S->stage_busy[which] = false;
+        }
+        *host_buffer = S->h_stage[which];
+    });
+}
+
+int oi_phase_stream_submit(oi_solver* S, int32_t which, int32_t z_local_begin, int32_t nz_chunk) {
+    return guarded([&] {
+        OI_REQUIRE(S && (which == 0 || which == 1), "bad argument");
+        OI_REQUIRE(S->stream_planes_received >= 0, "oi_phase_stream_submit: call oi_phase_stream_begin first");
+        OI_REQUIRE(nz_chunk > 0 && nz_chunk <= S->stage_planes && z_local_begin >= 0 &&
+                   z_local_begin + nz_chunk <= S->g.nz, "chunk outside the slab or larger than the staging buffer");
+        ensure_device(S);
+        const long long n = (long long)nz_chunk * S->g.plane;
+        uint8_t* d_in = S->d_stage[which];
+        CUDA_CHECK(cudaMemcpyAsync(d_in, S->h_stage[which], (size_t)n, cudaMemcpyHostToDevice, S->st));
+        oi::count_phase_u8(d_in, n, S->prm.phase_id, S->d_ull + 4, S->n_sm, S->st);
+        oi::count_nonbinary_u8(d_in, n, S->d_ull + 5, S->n_sm, S->st);
+        oi::phase_u8_to_isphase(d_in, S->d_isphase + (long long)z_local_begin * S->g.plane, n, S->prm.phase_id, S->n_sm, S->st);
+        S->launches += 3;
+        CUDA_CHECK(cudaEventRecord(S->stage_done[which], S->st));
+        S->stage_busy[which] = true;
+        S->stream_planes_received += nz_chunk;
+    });
+}
+
+int oi_phase_stream_end(oi_solver* S) {
+    return guarded([&] {
+        OI_REQUIRE(S, "null handle");
+        OI_REQUIRE(S->stream_planes_received >= 0, "oi_phase_stream_end: no stream open");
+        OI_REQUIRE(S->stream_planes_received == S->g.nz, "oi_phase_stream_end: every plane of the slab must be submitted exactly once");
+        ensure_device(S);
+        unsigned long long h[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(h, S->d_ull + 4, sizeof(h), cudaMemcpyDeviceToHost, S->st));
+        CUDA_CHECK(cudaStreamSynchronize(S->st));
+        CUDA_CHECK(cudaGetLastError());
+        S->stage_busy[0] = S->stage_busy[1] = false;
+        S->phase_count_local = (long long)h[0];
+        S->nonbinary_local = (long long)h[1];
+        S->stream_planes_received = -1;
     });
 }
 

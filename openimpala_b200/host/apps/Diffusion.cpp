@@ -402,9 +402,31 @@ int main(int argc, char* argv[]) {
                 amrex::Array<int, AMREX_SPACEDIM> np = {AMREX_D_DECL(0, 0, 0)};
                 geom_tort.define(geom_full.Domain(), &rb, 0, np.data());
             }
-            OpenImpala::TortuosityHypre solver(geom_tort, ba, dm, mf_phase, volume_fraction, phase_id, dir,
-                                               stringToSolverType(solver_str), results_path, vlo, vhi, verbose,
-                                               write_plotfile != 0);
+            // b200.stream_upload = N (TIFF input): skip the int32 iMultiFab on the way to the GPU and
+            // decode N planes at a time straight into the pinned staging buffers
+            int stream_upload = 0;
+            {
+                amrex::ParmParse pp_b200("b200");
+                pp_b200.query("stream_upload", stream_upload);
+            }
+            std::string ext_l = input.extension().string();
+            std::transform(ext_l.begin(), ext_l.end(), ext_l.begin(), ::tolower);
+            std::unique_ptr<OpenImpala::TortuosityHypre> solver_ptr;
+            if (stream_upload > 0 && (ext_l == ".tif" || ext_l == ".tiff")) {
+                OpenImpala::TiffReader reader(input.string());
+                const double thr = threshold_val;
+                solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
+                    geom_tort, ba, dm,
+                    [&](int z0, int nz, unsigned char* out) { reader.thresholdPlanesU8(thr, 1, 0, z0, nz, out); },
+                    stream_upload, volume_fraction, phase_id, dir, stringToSolverType(solver_str), results_path, vlo, vhi,
+                    verbose, write_plotfile != 0);
+                if (verbose >= 1) amrex::Print() << "  (phase field streamed from the TIFF in chunks of " << stream_upload << " planes)\n";
+            } else {
+                solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
+                    geom_tort, ba, dm, mf_phase, volume_fraction, phase_id, dir, stringToSolverType(solver_str),
+                    results_path, vlo, vhi, verbose, write_plotfile != 0);
+            }
+            OpenImpala::TortuosityHypre& solver = *solver_ptr;
             const amrex::Real tau = solver.value();
             results["Tortuosity_" + dc] = tau;
             amrex::Print() << "  >>> Calculated Tortuosity (" << dc << "): " << std::fixed << std::setprecision(8) << tau << " <<<\n";

@@ -329,6 +329,21 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.boxArray().minimalBox() == this->box(), "Dest MF BoxArray domain mismatch.");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nComp() == 1, "Dest MF must have 1 component.");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nGrow() == 0, "Dest MF must have 0 ghost cells.");
+    decodePlanes(0, m_depth, [&](int i, int j, int k, double v) { dest(i, j, k) = (v > thr) ? v_true : v_false; });
+}
+
+void TiffReader::thresholdPlanesU8(double raw_threshold, unsigned char value_if_true, unsigned char value_if_false,
+                                   int z_begin, int nz, unsigned char* out) const {
+    if (!m_is_read) amrex::Abort("[TiffReader::thresholdPlanesU8] Metadata not processed.");
+    if (z_begin < 0 || nz < 0 || z_begin + nz > m_depth) amrex::Abort("[TiffReader::thresholdPlanesU8] plane range outside the stack.");
+    const size_t W = (size_t)m_width, H = (size_t)m_height;
+    decodePlanes(z_begin, nz, [&](int i, int j, int k, double v) {
+        out[((size_t)(k - z_begin) * H + (size_t)j) * W + (size_t)i] = (v > raw_threshold) ? value_if_true : value_if_false;
+    });
+}
+
+// Decode planes [z_begin, z_begin + nz) and hand every sample to sink(i, j, k, value).
+void TiffReader::decodePlanes(int z_begin, int nz, const std::function<void(int, int, int, double)>& sink) const {
     const int W = m_width, H = m_height, bps = m_bits_per_sample;
     const size_t bytes_per_sample = bps >= 8 ? (size_t)bps / 8 : 1;
     std::vector<unsigned char> buf;
@@ -361,7 +376,7 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
                             const size_t off = ((size_t)(j - oy) * tw + (size_t)(i - ox)) * bytes_per_sample;
                             if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
                         }
-                        dest(i, j, k) = (v > thr) ? v_true : v_false;
+                        sink(i, j, k, v);
                     }
             }
         } else {                                                       // strips, reference :394-437
@@ -397,7 +412,7 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
                             const size_t off = ((size_t)(j - oy) * W + (size_t)i) * bytes_per_sample;
                             if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
                         }
-                        dest(i, j, k) = (v > thr) ? v_true : v_false;
+                        sink(i, j, k, v);
                     }
             }
         }
@@ -405,7 +420,7 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
 
     try {
         if (m_is_sequence) {
-            for (int k = 0; k < m_depth; ++k) {
+            for (int k = z_begin; k < z_begin + nz; ++k) {
                 const std::string name = sequenceName(m_base_pattern, m_start_index + k, m_digits, m_suffix);
                 TiffFile f(name);
                 const std::vector<Ifd> dirs = f.directories();
@@ -415,7 +430,7 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
         } else {
             TiffFile f(m_filename);                                    // opened once, not once per slice
             const std::vector<Ifd> dirs = f.directories();
-            for (int k = 0; k < m_depth && k < (int)dirs.size(); ++k) decodeDirectory(f, dirs[k], k);
+            for (int k = z_begin; k < z_begin + nz && k < (int)dirs.size(); ++k) decodeDirectory(f, dirs[k], k);
         }
     } catch (const std::exception& e) {
         amrex::Abort(std::string("[TiffReader] ") + e.what());

@@ -8,8 +8,10 @@
 // through include/openimpala_b200.h.
 #include "TortuosityHypre.H"
 
+#include <algorithm>
 #include <cmath>
 #include <iomanip>
+#include <vector>
 
 #include <AMReX_ParallelDescriptor.H>
 #include <AMReX_ParmParse.H>
@@ -44,6 +46,42 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
                                  const amrex::Real vhi, int verbose, bool write_plotfile)
     : m_solvertype(st), m_resultspath(resultspath), m_phase(phase), m_dir(dir), m_vlo(vlo), m_vhi(vhi),
       m_verbose(verbose), m_vf(vf), m_write_plotfile(write_plotfile), m_geom(geom), m_ba(ba), m_dm(dm) {
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf_phase_input.nGrow() >= 1, "Phase fab needs ghost cells");
+    // the phase field is deep-copied (valid cells only: every out-of-domain neighbour is
+    // inactive, which is what the reference's non-periodic mask ghosts amount to, :309, :522)
+    initialize([&](oi_solver* h) {
+        const std::vector<int> cells = mf_phase_input.validCopy(0);
+        oi_check(oi_set_phase_i32(h, cells.data()), "oi_set_phase_i32");
+    });
+}
+
+TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxArray& ba,
+                                 const amrex::DistributionMapping& dm, const PhaseStream& phase_stream,
+                                 int planes_per_chunk, const amrex::Real vf, const int phase,
+                                 const OpenImpala::Direction dir, const SolverType st,
+                                 const std::string& resultspath, const amrex::Real vlo, const amrex::Real vhi,
+                                 int verbose, bool write_plotfile)
+    : m_solvertype(st), m_resultspath(resultspath), m_phase(phase), m_dir(dir), m_vlo(vlo), m_vhi(vhi),
+      m_verbose(verbose), m_vf(vf), m_write_plotfile(write_plotfile), m_geom(geom), m_ba(ba), m_dm(dm) {
+    // the phase field arrives in z-chunks decoded straight into pinned staging buffers;
+    // decoding of chunk k+1 overlaps the upload of chunk k
+    initialize([&](oi_solver* h) {
+        const int nz = m_geom.Domain().length(2);
+        const int chunk = std::max(1, std::min(planes_per_chunk, nz));
+        oi_check(oi_phase_stream_begin(h, chunk), "oi_phase_stream_begin");
+        int which = 0;
+        for (int z0 = 0; z0 < nz; z0 += chunk, which ^= 1) {
+            const int n = std::min(chunk, nz - z0);
+            uint8_t* buf = nullptr;
+            oi_check(oi_phase_stream_buffer(h, which, &buf), "oi_phase_stream_buffer");
+            phase_stream(z0, n, buf);
+            oi_check(oi_phase_stream_submit(h, which, z0, n), "oi_phase_stream_submit");
+        }
+        oi_check(oi_phase_stream_end(h), "oi_phase_stream_end");
+    });
+}
+
+void TortuosityHypre::initialize(const std::function<void(oi_solver*)>& upload_phase) {
     const bool io = amrex::ParallelDescriptor::IOProcessor();
     if (m_verbose > 0 && io) {
         amrex::Print() << "TortuosityHypre: Initializing..." << std::endl;
@@ -65,11 +103,8 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_vf >= 0.0 && m_vf <= 1.0, "Original Volume fraction must be between 0 and 1");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_eps > 0.0, "Solver tolerance (eps) must be positive");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_maxiter > 0, "Solver max iterations must be positive");
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf_phase_input.nGrow() >= 1, "Phase fab needs ghost cells");
 
-    // device handle; the phase field is deep-copied (valid cells only: every
-    // out-of-domain neighbour is inactive, which is what the reference's
-    // non-periodic mask ghosts amount to, :309, :522)
+    // device handle
     const amrex::Box& domain = m_geom.Domain();
     oi_params p;
     oi_default_params(&p);
@@ -87,10 +122,7 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
     pp_b200.query("stencil_variant", p.stencil_variant);
     pp_b200.query("precond", p.precond);
     oi_check(oi_create(&m_solver, &p), "oi_create");
-    {
-        const std::vector<int> cells = mf_phase_input.validCopy(0);
-        oi_check(oi_set_phase_i32(m_solver, cells.data()), "oi_set_phase_i32");
-    }
+    upload_phase(m_solver);
 
     int num_remspot_passes = 0;                  // reference :254-263
     pp_tort.query("remspot_passes", num_remspot_passes);

@@ -273,3 +273,43 @@ def test_remspot_through_class_parmparse(capi):
     ref = o.tortuosity(oi_c.remspot(ph, 1), 1, 1, -1.0, 1.0, eps=1e-13)
     assert t._n_active == ref.n_active
     assert abs(t.value() - ref.tau) <= TAU_RTOL * abs(ref.tau)
+
+
+# ------------------------------------------------------------------ streamed upload (row f-2)
+@pytest.mark.parametrize("chunk", [1, 5, 16, 100])
+def test_streamed_upload_matches_one_shot(capi, chunk):
+    from oracle import oi_numpy as o
+    shape = (37, 20, 24)
+    ph = _blobs(shape, 31, 0.55).astype(np.uint8)
+    with capi.Solver(shape, 2, 1, -1.0, 1.0) as a, capi.Solver(shape, 2, 1, -1.0, 1.0) as b:
+        a.set_phase(ph)
+        calls = []
+
+        def read(z0, nz, out):
+            calls.append((z0, nz))
+            out[...] = ph[z0:z0 + nz]
+        b.set_phase_streamed(read, planes_per_chunk=chunk)
+        assert sum(n for _, n in calls) == shape[0] and calls[0][0] == 0
+        assert a.volume_fraction() == b.volume_fraction() == o.volume_fraction_counts(ph, 1)
+        assert a.build_mask() == b.build_mask()
+        assert np.array_equal(a.mask(), b.mask())
+        ia, ib = a.solve(), b.solve()
+        assert ia.iterations == ib.iterations and a.fluxes() == b.fluxes()
+        # the same handle can be re-filled either way
+        b.set_phase(ph)
+        assert b.build_mask() == a.build_mask()
+
+
+def test_streamed_upload_rejects_incomplete_slab(capi):
+    import ctypes as C
+    shape = (8, 4, 4)
+    with capi.Solver(shape, 2, 1) as s:
+        lib = capi.load()
+        assert lib.oi_phase_stream_begin(s._h, 3) == 0
+        buf = C.POINTER(C.c_uint8)()
+        assert lib.oi_phase_stream_buffer(s._h, 0, C.byref(buf)) == 0
+        assert lib.oi_phase_stream_submit(s._h, 0, 0, 3) == 0
+        assert lib.oi_phase_stream_submit(s._h, 0, 6, 3) != 0          # runs past the slab
+        assert lib.oi_phase_stream_submit(s._h, 0, 0, 4) != 0          # larger than the staging buffer
+        assert lib.oi_phase_stream_end(s._h) != 0                      # 3 of 8 planes only
+        assert b"every plane" in lib.oi_last_error()

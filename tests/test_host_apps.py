@@ -225,3 +225,16 @@ def test_diffusion_rev_study_csv(host_bins):
         got = [float(v) for v in r[8:14]]
         ref = [D[0][0], D[1][1], D[2][2], D[0][1], D[0][2], D[1][2]]
         assert max(abs(a - b) for a, b in zip(got, ref)) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_diffusion_streamed_tiff_upload(host_bins):
+    # b200.stream_upload: planes decoded straight into the pinned staging buffers (no int32 copy)
+    gold = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "direction=X", "b200.stream_upload=7",
+            "results_path=gpurun_out/results_stream/")
+    assert "streamed from the TIFF in chunks of 7 planes" in r.stdout
+    txt = open(os.path.join(ROOT, "gpurun_out", "results_stream", "results.txt")).read()
+    tau = float(re.search(r"Tortuosity_X: (\S+)", txt).group(1))
+    ref = next(c for c in gold["cases"] if c["phase"] == 1 and c["direction"] == 0)["tau"]
+    assert abs(tau - ref) <= 1e-6 * ref
