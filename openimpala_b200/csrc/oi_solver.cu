@@ -1329,6 +1329,37 @@ void require_gpu(int* count_out = nullptr) {
     if (count_out) *count_out = n;
 }
 
+// Everything a handle owns goes back to the caches (also used when oi_create fails half way).
+void release_resources(oi_solver* S) {
+    free_levels(S);
+    free_vectors(S);
+    S->active.release(); S->flags.release();
+    if (S->peer.arena.base) cfree(S->peer.arena.base);
+    if (S->d_isphase) cfree(S->d_isphase);
+    if (S->d_scal) cfree(S->d_scal);
+    if (S->d_partials) cfree(S->d_partials);
+    if (S->d_counter) cfree(S->d_counter);
+    if (S->d_ull) cfree(S->d_ull);
+    if (S->d_changed) cfree(S->d_changed);
+    S->peer.arena.base = nullptr;
+    S->d_isphase = nullptr; S->d_scal = S->d_partials = nullptr; S->d_counter = nullptr;
+    S->d_ull = nullptr; S->d_changed = nullptr;
+    pinned_cache().put(S->h_pinned);
+    S->h_pinned = nullptr;
+    for (int w = 0; w < 2; ++w) {
+        if (S->h_stage[w]) stage_cache().put((size_t)S->stage_planes * (size_t)S->g.plane, S->h_stage[w]);
+        if (S->d_stage[w]) cfree(S->d_stage[w]);
+        if (S->stage_done[w]) cudaEventDestroy(S->stage_done[w]);
+        S->h_stage[w] = nullptr; S->d_stage[w] = nullptr; S->stage_done[w] = nullptr;
+    }
+    for (auto& e : S->timer) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& m : S->prof_marks) cudaEventDestroy(m.second);
+    for (auto& e : S->prof_pool) cudaEventDestroy(e);
+    S->prof_marks.clear(); S->prof_pool.clear();
+    for (auto& e : S->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (S->st) { cudaStreamDestroy(S->st); S->st = nullptr; }
+}
+
 template <typename T>
 int count_host_field(const T* host, int64_t n, int32_t phase, int64_t* pc, int64_t* tc) {
     return guarded([&] {
@@ -1495,7 +1526,9 @@ int oi_create(oi_solver** out, const oi_params* p) {
                    "slab exceeds 2^31 cells; use more z-slabs");
         int ndev = 0;
         require_gpu(&ndev);
-        std::unique_ptr<oi_solver> S(new oi_solver());
+        // (a failure below hands every block already taken back to the caches)
+        struct Releaser { void operator()(oi_solver* h) const { if (h) { release_resources(h); delete h; } } };
+        std::unique_ptr<oi_solver, Releaser> S(new oi_solver());
         S->prm = *p;
         S->prm.nz_local = nzl; S->prm.z_begin = z0;
         S->rank = rank; S->n_ranks = n_ranks;
@@ -1603,33 +1636,12 @@ int oi_destroy(oi_solver* S) {
             peer_teardown(S);
         }
         const auto t1 = now();
-        free_levels(S);
-        free_vectors(S);
-        S->active.release(); S->flags.release();
-        if (S->peer.arena.base) cfree(S->peer.arena.base);
-        if (S->d_isphase) cfree(S->d_isphase);
-        if (S->d_scal) cfree(S->d_scal);
-        if (S->d_partials) cfree(S->d_partials);
-        if (S->d_counter) cfree(S->d_counter);
-        if (S->d_ull) cfree(S->d_ull);
-        if (S->d_changed) cfree(S->d_changed);
-        const auto t2 = now();
-        pinned_cache().put(S->h_pinned);
-        for (int w = 0; w < 2; ++w) {
-            if (S->h_stage[w]) stage_cache().put((size_t)S->stage_planes * (size_t)S->g.plane, S->h_stage[w]);
-            if (S->d_stage[w]) cfree(S->d_stage[w]);
-            if (S->stage_done[w]) cudaEventDestroy(S->stage_done[w]);
-        }
+        release_resources(S);
         const auto t3 = now();
-        for (auto& e : S->timer) if (e) cudaEventDestroy(e);
-        for (auto& m : S->prof_marks) cudaEventDestroy(m.second);
-        for (auto& e : S->prof_pool) cudaEventDestroy(e);
-        for (auto& e : S->ev) if (e) cudaEventDestroy(e);
-        if (S->st) cudaStreamDestroy(S->st);
         delete S;
         if (prof)
-            std::fprintf(stderr, "[oi profile] rank %d destroy: sync %.3f ms, blocks to cache %.3f ms, pinned to cache %.3f ms, "
-                                 "events+stream %.3f ms\n", rank, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
+            std::fprintf(stderr, "[oi profile] rank %d destroy: sync %.3f ms, blocks / pinned / events / stream back to their "
+                                 "caches %.3f ms\n", rank, ms(t0, t1), ms(t1, t3));
     });
 }
 

@@ -130,3 +130,62 @@ def test_sphere_packing_slabs_agree():
     assert np.array_equal(full, np.concatenate(parts))
     assert 0.3 < full.mean() < 0.55
     assert synth.describe(full)["sha256"] == synth.describe(np.concatenate(parts))["sha256"]
+
+
+def test_ctypes_struct_layout_matches_the_header(tmp_path):
+    """oi_params / oi_solve_info as the C compiler lays them out == the ctypes mirror
+    (an ABI drift here corrupts every call silently)."""
+    import ctypes as C
+    import subprocess
+    from openimpala_b200 import capi
+    fields_p = [f[0] for f in capi.oi_params._fields_]
+    fields_i = [f[0] for f in capi.oi_solve_info._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "openimpala_b200.h"', 'int main(void) {',
+             '  printf("%zu %zu\\n", sizeof(oi_params), sizeof(oi_solve_info));']
+    for f in fields_p:
+        lines.append(f'  printf("p {f} %zu\\n", offsetof(oi_params, {f}));')
+    for f in fields_i:
+        lines.append(f'  printf("i {f} %zu\\n", offsetof(oi_solve_info, {f}));')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert [int(v) for v in out[0].split()] == [C.sizeof(capi.oi_params), C.sizeof(capi.oi_solve_info)]
+    for line in out[1:]:
+        kind, name, off = line.split()
+        st = capi.oi_params if kind == "p" else capi.oi_solve_info
+        assert getattr(st, name).offset == int(off), (kind, name)
+    # and the header compiles as plain C (extern "C" boundary, no C++ types)
+    assert "oi_comm" in open(os.path.join(ROOT, "include", "openimpala_b200.h")).read()
+
+
+def test_default_params_match_the_reference_defaults(built_lib):
+    from openimpala_b200 import capi
+    p = capi.default_params()
+    assert (p.eps, p.maxiter) == (1e-9, 200)                 # TortuosityHypre.cpp:142-143
+    assert (p.vlo, p.vhi) == (0.0, 1.0)                      # TortuosityHypre.H:77-78
+    assert tuple(p.dx) == (1.0, 1.0, 1.0) and p.phase_id == 1 and p.direction == 0
+    assert p.problem == capi.OI_PROBLEM_TORTUOSITY and p.halo_mode == capi.OI_HALO_AUTO and not p.comm
+
+
+def test_argument_validation_needs_no_gpu(built_lib):
+    """Bad arguments are rejected with OI_ERR_INVALID (-1) and a message, GPU or not."""
+    import ctypes as C
+    from openimpala_b200 import capi
+    lib = built_lib
+    h = C.c_void_p(None)
+    for mutate, needle in [(lambda p: setattr(p, "nx", 0), "dimensions"), (lambda p: setattr(p, "direction", 3), "direction"),
+                           (lambda p: setattr(p, "eps", 0.0), "eps"), (lambda p: setattr(p, "maxiter", 0), "iterations")]:
+        p = capi.default_params()
+        p.nx = p.ny = p.nz = 8
+        mutate(p)
+        assert lib.oi_create(C.byref(h), C.byref(p)) == -1 and not h.value
+        assert needle in lib.oi_last_error().decode()
+    assert lib.oi_create(None, None) == -1
+    assert lib.oi_solve(None, None) == -1 and lib.oi_build_mask(None, None) == -1
+    assert lib.oi_destroy(None) == 0                         # destroying nothing is fine
+    pc, tc = C.c_int64(0), C.c_int64(0)
+    assert lib.oi_count_phase_u8(None, 5, 1, C.byref(pc), C.byref(tc)) == -1
+    assert lib.oi_count_phase_u8(None, -1, 1, C.byref(pc), C.byref(tc)) == -1
