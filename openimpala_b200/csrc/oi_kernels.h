@@ -106,8 +106,8 @@ void phase_u8_to_isphase(const uint8_t* in, uint8_t* is_phase, long long n, int 
                          cudaStream_t st);
 
 // connected components of {is_phase}: labels = min linear index of the component
-void ccl_label(const uint8_t* is_phase /*ghost planes*/, int* labels, int nx, int ny, int nz,
-               int n_sm, cudaStream_t st);
+// (returns the number of kernels it launched)
+int ccl_label(const uint8_t* is_phase, int* labels, int nx, int ny, int nz, int n_sm, cudaStream_t st);
 // reach[root] |= 1 (touches inlet plane) | 2 (touches outlet plane); planes given
 // in local coordinates, -1 = not on this slab
 void ccl_mark_planes(const uint8_t* is_phase, const int* labels, unsigned int* reach, int nx,

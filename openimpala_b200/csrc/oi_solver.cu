@@ -416,9 +416,6 @@ std::vector<double> cheb_weights(int degree, double lo_frac, double lmax = 2.0) 
 }
 
 // ------------------------------------------------------------------ comm helpers
-template <typename T>
-ncclDataType_t nccl_bytes_type() { return ncclUint8; }
-
 // Peer path: boundary planes are stored straight into the neighbours' ghost planes
 // and the neighbours' flag words advance to this exchange's sequence number; the
 // local stream then waits on its own two flag words.  Ranks run the same sequence
@@ -1224,7 +1221,7 @@ void build_mask(oi_solver* S) {
     CUDA_CHECK(cudaMemsetAsync(d_reach, 0, reach_words * sizeof(unsigned int), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
 
-    oi::ccl_label(S->d_isphase, d_labels, g.nx, g.ny, g.nz, S->n_sm, S->st); S->launches += 3;
+    S->launches += oi::ccl_label(S->d_isphase, d_labels, g.nx, g.ny, g.nz, S->n_sm, S->st);
     int lo_local = 0, hi_local = S->n_dir - 1;
     if (dir == 2) {
         lo_local = (g.z0 == 0) ? 0 : -1;
