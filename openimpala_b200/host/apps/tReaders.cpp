@@ -1,6 +1,6 @@
 // Reader + VolumeFraction checks in the mould of src/io/tTiffReader.cpp,
 // tRawReader.cpp, tHDF5Reader.cpp and src/props/tVolumeFraction.cpp:
-//   mode = tiff | raw | hdf5 | dat ; prints dims, sample metadata, thresholded min/max
+//   mode = tiff | tiffseq | raw | hdf5 | dat ; prints dims, sample metadata, thresholded min/max
 //   and the phase counts, compares the GPU count with a direct host loop.
 #include <iomanip>
 #include <string>
@@ -46,6 +46,16 @@ int main(int argc, char* argv[]) {
                 OpenImpala::TiffReader r(file);
                 amrex::Print() << "BitsPerSample: " << r.bitsPerSample() << " SampleFormat: " << r.sampleFormat()
                                << " SamplesPerPixel: " << r.samplesPerPixel() << "\n";
+                prepare(r.box());
+                r.threshold(threshold, 1, 0, mf);
+            } else if (mode == "tiffseq") {
+                std::string suffix = ".tif";
+                int num_files = 0, start_index = 0, digits = 1;
+                pp.get("num_files", num_files);
+                pp.query("start_index", start_index);
+                pp.query("digits", digits);
+                pp.query("suffix", suffix);
+                OpenImpala::TiffReader r(file, num_files, start_index, digits, suffix);   // file = base pattern
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
             } else if (mode == "raw") {

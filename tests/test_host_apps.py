@@ -96,6 +96,122 @@ def test_compressed_tiff_stacks(host_bins, tmp_path, compression, kind):
     assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > thr).sum())
 
 
+def _write_tiff(path, vol, *, big=False, little=True, tile=None, rows_per_strip=None):
+    """Minimal TIFF writer for the reader tests: classic or BigTIFF, either byte order, strips
+    or tiles, one IFD per z-plane, uint8 / uint16 / float32 samples."""
+    import struct
+    import numpy as np
+    bo = "<" if little else ">"
+    fmt = {np.dtype("uint8"): 1, np.dtype("uint16"): 1, np.dtype("float32"): 3}[vol.dtype]
+    bps = vol.dtype.itemsize * 8
+    nz, ny, nx = vol.shape
+    data = vol.astype(vol.dtype.newbyteorder(bo))
+    out = bytearray()
+    out += (b"II" if little else b"MM")
+    out += struct.pack(bo + "H", 43 if big else 42)
+    out += struct.pack(bo + "HHQ", 8, 0, 0) if big else struct.pack(bo + "I", 0)
+    first_off_pos = 8 if big else 4
+    prev_next_pos = first_off_pos
+    for k in range(nz):
+        plane = data[k]
+        segs = []
+        if tile:
+            tw, th = tile
+            for oy in range(0, ny, th):
+                for ox in range(0, nx, tw):
+                    t = np.zeros((th, tw), dtype=plane.dtype)
+                    blk = plane[oy:oy + th, ox:ox + tw]
+                    t[:blk.shape[0], :blk.shape[1]] = blk
+                    segs.append(t.tobytes())
+        else:
+            rps = rows_per_strip or ny
+            for oy in range(0, ny, rps):
+                segs.append(plane[oy:oy + rps].tobytes())
+        offs = []
+        for sg in segs:
+            if len(out) % 2:
+                out += b"\0"
+            offs.append(len(out))
+            out += sg
+        cnts = [len(sg) for sg in segs]
+        tags = [(256, nx), (257, ny), (258, bps), (259, 1), (262, 1), (277, 1), (284, 1), (339, fmt)]
+        arrays = {}
+        if tile:
+            tags += [(322, tile[0]), (323, tile[1])]
+            arrays[324], arrays[325] = offs, cnts
+        else:
+            tags += [(278, rows_per_strip or ny)]
+            arrays[273], arrays[279] = offs, cnts
+        # array payloads (LONG8 in BigTIFF, LONG otherwise)
+        arr_pos = {}
+        for tag, vals in arrays.items():
+            if len(out) % 2:
+                out += b"\0"
+            arr_pos[tag] = len(out)
+            out += struct.pack(bo + ("Q" if big else "I") * len(vals), *vals)
+        if len(out) % 2:
+            out += b"\0"
+        ifd_pos = len(out)
+        entries = []
+        for tag, v in tags:
+            entries.append((tag, 4, 1, v, None))                     # LONG scalar
+        for tag, vals in arrays.items():
+            entries.append((tag, 16 if big else 4, len(vals), vals, arr_pos[tag]))
+        entries.sort(key=lambda e: e[0])
+        out += struct.pack(bo + ("Q" if big else "H"), len(entries))
+        inline = 8 if big else 4
+        for tag, typ, cnt, v, pos in entries:
+            out += struct.pack(bo + "HH" + ("Q" if big else "I"), tag, typ, cnt)
+            size = (8 if typ == 16 else 4) * cnt
+            if pos is not None and size > inline:
+                out += struct.pack(bo + ("Q" if big else "I"), pos)
+            else:
+                vals = v if isinstance(v, list) else [v]
+                raw = struct.pack(bo + ("Q" if typ == 16 else "I") * cnt, *vals)
+                out += raw + b"\0" * (inline - len(raw))
+        next_pos = len(out)
+        out += struct.pack(bo + ("Q" if big else "I"), 0)
+        struct.pack_into(bo + ("Q" if big else "I"), out, prev_next_pos, ifd_pos)
+        prev_next_pos = next_pos
+    open(path, "wb").write(bytes(out))
+
+
+@pytest.mark.parametrize("variant", ["classic_le_strips", "classic_be_strips", "bigtiff_le_tiles", "classic_be_tiles",
+                                     "bigtiff_be_strips_f32", "classic_le_multi_strip_u16"])
+def test_tiff_container_variants(host_bins, tmp_path, variant):
+    """Byte orders, classic / BigTIFF containers, strips / tiles, integer and float samples
+    (what libtiff gives the reference for free, src/io/TiffReader.cpp:289-444)."""
+    import numpy as np
+    rng = np.random.default_rng(23)
+    nz, ny, nx = 4, 23, 41
+    if "f32" in variant:
+        vol, thr = rng.random((nz, ny, nx)).astype(np.float32), 0.6
+    elif "u16" in variant:
+        vol, thr = rng.integers(0, 60000, (nz, ny, nx)).astype(np.uint16), 30000
+    else:
+        vol, thr = rng.integers(0, 255, (nz, ny, nx)).astype(np.uint8), 120
+    f = tmp_path / f"{variant}.tif"
+    _write_tiff(f, vol, big="bigtiff" in variant, little="_le_" in variant,
+                tile=(16, 16) if "tiles" in variant else None,
+                rows_per_strip=5 if "multi_strip" in variant else None)
+    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}")
+    assert [int(v) for v in field(r.stdout, "Dims")] == [nx, ny, nz]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > thr).sum())
+
+
+def test_tiff_file_sequence(host_bins, tmp_path):
+    # numbered single-plane files: base pattern + zero-padded index + suffix (TiffReader.H:63-120)
+    import numpy as np
+    rng = np.random.default_rng(29)
+    vol = rng.integers(0, 255, (6, 12, 18)).astype(np.uint8)
+    for k in range(6):
+        _write_tiff(tmp_path / f"slice_{k + 3:04d}.tif", vol[k:k + 1])
+    r = run("tReaders", "mode=tiffseq", "gpu_count=0", f"tifffile={tmp_path / 'slice_'}", "num_files=6",
+            "start_index=3", "digits=4", "threshold=99")
+    assert [int(v) for v in field(r.stdout, "Dims")] == [18, 12, 6]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > 99).sum())
+
+
 def test_dat_reader(host_bins, tmp_path):
     # src/io/DatReader.cpp:60-248: int32 LE (W, H, D) header + uint16 LE voxels, x fastest
     import numpy as np
