@@ -3,9 +3,14 @@
 // Coarse operators are aggregation-Galerkin: a coarse cell is a (fx x fy x fz)
 // block of finer cells, the coupling across a coarse face is the sum of the
 // finer couplings crossing it, the diagonal is the sum of outward couplings plus
-// the children's Dirichlet sink terms.  Each level is scaled by `scale`
-// (0.5 = the over-correction that turns piecewise-constant aggregation into the
-// rediscretised cell-centred operator).  This replaces HYPRE SMG/PFMG's coarse
+// the children's sink terms (Dirichlet neighbours, solid faces of the cell problem).
+// Couplings and sinks along axis a are scaled by 1/f_a: the aggregate sums
+// (area) faces but the cell distance grows by f_a, so this is what turns
+// piecewise-constant aggregation into the rediscretised cell-centred operator (1/2 for
+// every axis under full coarsening).  The diagonal is kept split by axis (dgx, dgy,
+// dgz; build-time only) so that the next level can scale each share on its own:
+// anisotropic cells are semicoarsened (only the strongly coupled axes) until the
+// couplings even out.  This replaces HYPRE SMG/PFMG's coarse
 // operator build (reference call site src/props/TortuosityHypre.cpp:671-681).
 #include "oi_kernels.h"
 
@@ -15,12 +20,15 @@ namespace {
 
 // diagonal of a fine row (couplings + sink terms: Dirichlet neighbours, and for the
 // cell problem the faces towards the solid)
-__device__ __forceinline__ double diag0(uint8_t f, const Grid& g) { return row_diag<double>(f, g); }
+__device__ __forceinline__ void diag0_by_axis(uint8_t f, const Grid& g, double& dx, double& dy, double& dz) {
+    if (g.diag_full > 0.0) { dx = 2.0 * g.cx; dy = 2.0 * g.cy; dz = 2.0 * g.cz; return; }
+    dx = g.cx * (double)__popc(f & 0x03u); dy = g.cy * (double)__popc(f & 0x0cu); dz = g.cz * (double)__popc(f & 0x30u);
+}
 
 // level 1 from connectivity bytes
 __global__ void __launch_bounds__(256)
 build_from_flags_kernel(Grid g, const uint8_t* __restrict__ flags, CoarseLevel c, int fx, int fy,
-                        int fz, double scale) {
+                        int fz, double scx, double scy, double scz) {
     const long long nc = (long long)c.nz * c.plane;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += stride) {
@@ -29,38 +37,43 @@ build_from_flags_kernel(Grid g, const uint8_t* __restrict__ flags, CoarseLevel c
         const int ck = (int)(I / c.plane);
         const int i0 = ci * fx, j0 = cj * fy, k0 = ck * fz;
         const int i1 = min(i0 + fx, g.nx), j1 = min(j0 + fy, g.ny), k1 = min(k0 + fz, g.nz);
-        double sx = 0.0, sy = 0.0, sz = 0.0, sd = 0.0, internal = 0.0;
+        double sx = 0.0, sy = 0.0, sz = 0.0, sdx = 0.0, sdy = 0.0, sdz = 0.0, inx = 0.0, iny = 0.0, inz = 0.0;
         for (int k = k0; k < k1; ++k)
             for (int j = j0; j < j1; ++j)
                 for (int i = i0; i < i1; ++i) {
                     const long long idx = (long long)k * g.plane + (long long)j * g.nx + i;
                     const uint8_t f = flags[idx];
                     if (!(f & F_UNK)) continue;
-                    sd += diag0(f, g);
+                    double ddx, ddy, ddz;
+                    diag0_by_axis(f, g, ddx, ddy, ddz);
+                    sdx += ddx; sdy += ddy; sdz += ddz;
                     // +x, +y, +z couplings to UNKNOWN neighbours (Dirichlet
                     // neighbours stay in the diagonal as sink terms)
                     // (a set bit at the box edge means a periodic neighbour on the far side)
                     const long long ixp = (i + 1 < g.nx) ? idx + 1 : idx - i;
                     const long long iyp = (j + 1 < g.ny) ? idx + g.nx : idx - (long long)j * g.nx;
                     if ((f & F_XP) && (flags[ixp] & F_UNK)) {
-                        if (i + 1 < i1) internal += g.cx; else sx += g.cx;
+                        if (i + 1 < i1) inx += g.cx; else sx += g.cx;
                     }
                     if ((f & F_YP) && (flags[iyp] & F_UNK)) {
-                        if (j + 1 < j1) internal += g.cy; else sy += g.cy;
+                        if (j + 1 < j1) iny += g.cy; else sy += g.cy;
                     }
                     if ((f & F_ZP) && (flags[idx + g.plane] & F_UNK)) {
-                        if (k + 1 < k1) internal += g.cz; else sz += g.cz;
+                        if (k + 1 < k1) inz += g.cz; else sz += g.cz;
                     }
                 }
-        c.cxp[I] = (float)(scale * sx);
-        c.cyp[I] = (float)(scale * sy);
-        c.czp[I] = (float)(scale * sz);
-        c.dg[I] = (float)(scale * (sd - 2.0 * internal));
+        const float dx = (float)(scx * (sdx - 2.0 * inx)), dy = (float)(scy * (sdy - 2.0 * iny)),
+                    dz = (float)(scz * (sdz - 2.0 * inz));
+        c.cxp[I] = (float)(scx * sx);
+        c.cyp[I] = (float)(scy * sy);
+        c.czp[I] = (float)(scz * sz);
+        c.dgx[I] = dx; c.dgy[I] = dy; c.dgz[I] = dz;
+        c.dg[I] = dx + dy + dz;
     }
 }
 
 __global__ void __launch_bounds__(256)
-build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scale) {
+build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scx, double scy, double scz) {
     const long long nc = (long long)c.nz * c.plane;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int fx = f.fx, fy = f.fy, fz = f.fz;
@@ -70,21 +83,24 @@ build_from_coarse_kernel(CoarseLevel f, CoarseLevel c, double scale) {
         const int ck = (int)(I / c.plane);
         const int i0 = ci * fx, j0 = cj * fy, k0 = ck * fz;
         const int i1 = min(i0 + fx, f.nx), j1 = min(j0 + fy, f.ny), k1 = min(k0 + fz, f.nz);
-        double sx = 0.0, sy = 0.0, sz = 0.0, sd = 0.0, internal = 0.0;
+        double sx = 0.0, sy = 0.0, sz = 0.0, sdx = 0.0, sdy = 0.0, sdz = 0.0, inx = 0.0, iny = 0.0, inz = 0.0;
         for (int k = k0; k < k1; ++k)
             for (int j = j0; j < j1; ++j)
                 for (int i = i0; i < i1; ++i) {
                     const long long idx = (long long)k * f.plane + (long long)j * f.nx + i;
-                    sd += (double)f.dg[idx];
+                    sdx += (double)f.dgx[idx]; sdy += (double)f.dgy[idx]; sdz += (double)f.dgz[idx];
                     const double ax = (double)f.cxp[idx], ay = (double)f.cyp[idx], az = (double)f.czp[idx];
-                    if (i + 1 < i1) internal += ax; else sx += ax;
-                    if (j + 1 < j1) internal += ay; else sy += ay;
-                    if (k + 1 < k1) internal += az; else sz += az;
+                    if (i + 1 < i1) inx += ax; else sx += ax;
+                    if (j + 1 < j1) iny += ay; else sy += ay;
+                    if (k + 1 < k1) inz += az; else sz += az;
                 }
-        c.cxp[I] = (float)(scale * sx);
-        c.cyp[I] = (float)(scale * sy);
-        c.czp[I] = (float)(scale * sz);
-        c.dg[I] = (float)(scale * (sd - 2.0 * internal));
+        const float dx = (float)(scx * (sdx - 2.0 * inx)), dy = (float)(scy * (sdy - 2.0 * iny)),
+                    dz = (float)(scz * (sdz - 2.0 * inz));
+        c.cxp[I] = (float)(scx * sx);
+        c.cyp[I] = (float)(scy * sy);
+        c.czp[I] = (float)(scz * sz);
+        c.dgx[I] = dx; c.dgy[I] = dy; c.dgz[I] = dz;
+        c.dg[I] = dx + dy + dz;
     }
 }
 
@@ -246,12 +262,14 @@ inline int blocks_for(long long n) {
 }  // namespace
 
 void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int, int, const CoarseLevel& c,
-                             int fx, int fy, int fz, double scale, cudaStream_t st) {
-    build_from_flags_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(g, flags, c, fx, fy, fz, scale);
+                             int fx, int fy, int fz, cudaStream_t st) {
+    build_from_flags_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(g, flags, c, fx, fy, fz,
+                                                                                  1.0 / fx, 1.0 / fy, 1.0 / fz);
 }
 
-void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double scale, cudaStream_t st) {
-    build_from_coarse_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, c, scale);
+void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, cudaStream_t st) {
+    build_from_coarse_kernel<<<blocks_for((long long)c.nz * c.plane), 256, 0, st>>>(f, c, 1.0 / f.fx, 1.0 / f.fy,
+                                                                                   1.0 / f.fz);
 }
 
 void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st) {

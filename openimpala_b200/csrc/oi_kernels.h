@@ -49,14 +49,13 @@ struct CoarseLevel {
     int replicated;            // multi-rank: this level holds the whole box on every rank (no halo)
     float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
     float* dg;                 // diagonal (0 = empty aggregate)
+    float *dgx, *dgy, *dgz;    // its shares by axis (build time only: each is scaled by 1/f_axis)
     mg_t *x, *b, *t;           // solution, rhs, scratch (ghost planes)
 };
 
 void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int dir_axis, int n_dir_global,
-                             const CoarseLevel& c, int fx, int fy, int fz, double scale,
-                             cudaStream_t st);
-void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, double scale,
-                              cudaStream_t st);
+                             const CoarseLevel& c, int fx, int fy, int fz, cudaStream_t st);
+void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, cudaStream_t st);
 void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st);
 // out = x + w (b - A x) / dg
 void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w,

@@ -325,6 +325,7 @@ PFN_stream_wait32 driver_wait32() {
 struct HostLevel {
     oi::CoarseLevel L{};
     Field<float> cxp, cyp, czp, dg;
+    Field<float> dgx, dgy, dgz;             // diagonal by axis, read only by the next level's build
     Field<oi::mg_t> x, b, t;
     // Agglomeration (n_ranks > 1): the first level small enough is kept twice -- once
     // distributed (`gather_point`: it only receives the restricted residual and hands back
@@ -388,7 +389,6 @@ struct oi_solver {
     // multigrid
     std::vector<HostLevel> levels;     // levels[0] is MG level 1
     std::vector<double> w_smooth, w_coarse;
-    double mg_scale = 0.5;
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
     // results
     oi_solve_info info{};
@@ -593,6 +593,7 @@ inline L0Info l0info(const oi_solver* S) { return L0Info{S->fx0, S->fy0, S->fz0}
 void free_levels(oi_solver* S) {
     for (auto& h : S->levels) {
         h.cxp.release(); h.cyp.release(); h.czp.release(); h.dg.release();
+        h.dgx.release(); h.dgy.release(); h.dgz.release();
         h.x.release(); h.b.release(); h.t.release();
     }
     S->levels.clear();
@@ -617,20 +618,31 @@ void plan_hierarchy(oi_solver* S) {
     long long agg_cells = 64LL * 64 * 64;
     if (const char* e = getenv("OI_AGG_CELLS")) agg_cells = std::atoll(e);
     bool gathered = (nr == 1) || agg_cells <= 0;
+    double lc[3] = {S->g.cx, S->g.cy, S->g.cz};       // representative couplings of the current level
     int nx = S->g.nx, ny = S->g.ny, nzg = S->g.nzg;
     L0Info f0{1, 1, 1};
     std::vector<HostLevel>& lv = S->levels;
     for (int l = 1; l <= 16; ++l) {
         if ((long long)nx * ny * nzg <= 64) break;
-        int fx = nx >= 3 ? 2 : 1, fy = ny >= 3 ? 2 : 1, fz = nzg >= 3 ? 2 : 1;
-        if (fz == 2) {   // every slab must start on an even plane and (except the last) be even
+        bool canx = nx >= 3, cany = ny >= 3, canz = nzg >= 3;
+        if (canz) {      // every slab must start on an even plane and (except the last) be even
             for (int r = 0; r < nr; ++r) {
-                if (z0[r] & 1) fz = 1;
-                if (r < nr - 1 && (nz[r] & 1)) fz = 1;
-                if (nz[r] < 2 && nr > 1) fz = 1;
+                if (z0[r] & 1) canz = false;
+                if (r < nr - 1 && (nz[r] & 1)) canz = false;
+                if (nz[r] < 2 && nr > 1) canz = false;
             }
         }
+        // Semicoarsening for anisotropic cells: among the axes that can still be halved,
+        // only those whose coupling is within a factor 2 of the strongest one are (the
+        // point smoother does nothing for the weak axes, so they stay resolved until the
+        // couplings even out).  Isotropic cells: every axis, i.e. full 2x2x2 coarsening.
+        const double cmax = std::max(canx ? lc[0] : 0.0, std::max(cany ? lc[1] : 0.0, canz ? lc[2] : 0.0));
+        const int fx = (canx && lc[0] >= 0.5 * cmax) ? 2 : 1;
+        const int fy = (cany && lc[1] >= 0.5 * cmax) ? 2 : 1;
+        const int fz = (canz && lc[2] >= 0.5 * cmax) ? 2 : 1;
         if (fx == 1 && fy == 1 && fz == 1) break;
+        // couplings of the level being created: (faces summed) x 1/f_axis
+        lc[0] *= (double)(fy * fz) / fx; lc[1] *= (double)(fx * fz) / fy; lc[2] *= (double)(fx * fy) / fz;
         if (l == 1) { f0.fx = fx; f0.fy = fy; f0.fz = fz; }
         else { lv.back().L.fx = fx; lv.back().L.fy = fy; lv.back().L.fz = fz; }
         nx = (nx + fx - 1) / fx; ny = (ny + fy - 1) / fy; nzg = (nzg + fz - 1) / fz;
@@ -670,10 +682,12 @@ void allocate_hierarchy(oi_solver* S) {
     for (HostLevel& h : S->levels) {
         h.cxp.alloc(h.L.plane, h.L.nz, S->st); h.cyp.alloc(h.L.plane, h.L.nz, S->st);
         h.czp.alloc(h.L.plane, h.L.nz, S->st); h.dg.alloc(h.L.plane, h.L.nz, S->st);
+        h.dgx.alloc(h.L.plane, h.L.nz, S->st); h.dgy.alloc(h.L.plane, h.L.nz, S->st); h.dgz.alloc(h.L.plane, h.L.nz, S->st);
         if (!h.x.base) h.x.alloc(h.L.plane, h.L.nz, S->st);
         if (!h.t.base) h.t.alloc(h.L.plane, h.L.nz, S->st);
         h.b.alloc(h.L.plane, h.L.nz, S->st);
         h.L.cxp = h.cxp.p; h.L.cyp = h.cyp.p; h.L.czp = h.czp.p; h.L.dg = h.dg.p;
+        h.L.dgx = h.dgx.p; h.L.dgy = h.dgy.p; h.L.dgz = h.dgz.p;
         h.L.x = h.x.p; h.L.b = h.b.p; h.L.t = h.t.p;
     }
     S->levels_allocated = true;
@@ -830,15 +844,18 @@ void build_hierarchy(oi_solver* S) {
             gather_level(S, lv[l - 1], lv[l - 1].cyp.p, lv[l].cyp.p);
             gather_level(S, lv[l - 1], lv[l - 1].czp.p, lv[l].czp.p);
             gather_level(S, lv[l - 1], lv[l - 1].dg.p, lv[l].dg.p);
+            gather_level(S, lv[l - 1], lv[l - 1].dgx.p, lv[l].dgx.p);
+            gather_level(S, lv[l - 1], lv[l - 1].dgy.p, lv[l].dgy.p);
+            gather_level(S, lv[l - 1], lv[l - 1].dgz.p, lv[l].dgz.p);
             wrap_ghosts_locally(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
             wrap_ghosts_locally(S, lv[l].dg.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
             continue;
         }
         if (l == 0) {
             oi::coarse_build_from_flags(S->g, S->flags.p, S->prm.direction, S->n_dir, lv[0].L,
-                                        S->fx0, S->fy0, S->fz0, S->mg_scale, S->st);
+                                        S->fx0, S->fy0, S->fz0, S->st);
         } else {
-            oi::coarse_build_from_coarse(lv[l - 1].L, lv[l].L, S->mg_scale, S->st);
+            oi::coarse_build_from_coarse(lv[l - 1].L, lv[l].L, S->st);
         }
         S->launches++;
         if (lv[l].replicated) {

@@ -181,6 +181,29 @@ def test_anisotropic_cell_size(capi):
         assert abs(t.value() - ref.tau) <= TAU_RTOL * abs(ref.tau)
 
 
+@pytest.mark.parametrize("dx,direction,max_iters", [((1.0, 1.0, 5.0), 2, 70), ((1.0, 1.0, 5.0), 0, 70),
+                                                    ((3.0, 1.0, 1.0), 0, 60), ((1.0, 4.0, 1.0), 1, 70)])
+def test_strongly_anisotropic_cells_semicoarsen(capi, dx, direction, max_iters):
+    """Voxels five times longer along one axis (FIB-SEM stacks): the hierarchy coarsens only
+    the strongly coupled axes until the couplings even out, so the iteration count stays far
+    from hypre.maxiter = 200 (full 2x2x2 coarsening needed 131 at 256^3) and tau still
+    matches the oracle."""
+    from oracle import oi_numpy as o
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    ph = _blobs((40, 44, 48), 33, 0.55, sigma=2.0)
+    ref = o.tortuosity(ph, 1, direction, -1.0, 1.0, eps=1e-12, dx=dx)
+    t = TortuosityHypre({"dx": dx}, None, None, ph, 0.55, 1, Direction(direction), SolverType.FlexGMRES, "", -1.0, 1.0)
+    tau = t.value()
+    assert t.getSolverConverged() and t.getSolverIterations() <= max_iters
+    assert abs(tau - ref.tau) <= TAU_RTOL * abs(ref.tau)
+    big = _blobs((128, 128, 128), 3, 0.5, sigma=2.0)
+    with capi.Solver(big.shape, direction, 1, -1.0, 1.0, dx=dx) as s:
+        s.set_phase(big)
+        s.build_mask()
+        info = s.solve()
+        assert info.converged and info.iterations <= max_iters
+
+
 # ------------------------------------------------------------------ the reference's sample image
 def test_sample_image_golden(capi, sample_phase):
     """BASELINE configs[0]/[1]: tau in X/Y/Z for both phases + VF; golden values
