@@ -1,4 +1,4 @@
-// VolumeFraction::value: integer count of fab == phase over the valid cells
+// VolumeFraction: integer count of cells == phase over the valid cells
 // (reference src/props/VolumeFraction.cpp:22-66), executed by the CUDA count
 // kernel behind oi_count_phase_i32.  No CPU path: a missing GPU aborts.
 #include "VolumeFraction.H"
@@ -8,18 +8,28 @@
 namespace OpenImpala {
 
 VolumeFraction::VolumeFraction(const amrex::iMultiFab& fm, const int phase, int comp)
-    : m_mf(fm), m_phase(phase), m_comp(comp) {
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_comp >= 0 && m_comp < m_mf.nComp(),
+    : m_field(&fm), m_phase_id(phase), m_component(comp) {
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_component >= 0 && m_component < m_field->nComp(),
                                      "VolumeFraction: Component index out of bounds.");
 }
 
-void VolumeFraction::value(long long& phase_count, long long& total_count, bool /*local*/) const {
-    const std::vector<int> cells = m_mf.validCopy(m_comp);
-    int64_t pc = 0, tc = 0;
-    const int rc = oi_count_phase_i32(cells.data(), (int64_t)cells.size(), m_phase, &pc, &tc);
-    if (rc != OI_OK) amrex::Abort(std::string("VolumeFraction: ") + oi_last_error());
-    phase_count = pc;
-    total_count = tc;
+VolumeFraction::Counts VolumeFraction::counts() const {
+    const std::vector<int> cells = m_field->validCopy(m_component);
+    int64_t n_phase = 0, n_total = 0;
+    if (oi_count_phase_i32(cells.data(), (int64_t)cells.size(), m_phase_id, &n_phase, &n_total) != OI_OK)
+        amrex::Abort(std::string("VolumeFraction: ") + oi_last_error());
+    Counts c;
+    c.phase = n_phase;
+    c.total = n_total;
+    return c;
 }
+
+void VolumeFraction::value(long long& phase_count, long long& total_count, bool /*local*/) const {
+    const Counts c = counts();
+    phase_count = c.phase;
+    total_count = c.total;
+}
+
+amrex::Real VolumeFraction::value_vf(bool /*local*/) const { return counts().fraction(); }
 
 }  // namespace OpenImpala
