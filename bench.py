@@ -240,13 +240,13 @@ def main():
     # stencil kernels (its loads are still staged), flags are always read.
     n_unk, pairs, quads = S.sparsity()
     fp, fq = 2.0 * pairs / local_cells, 4.0 * quads / local_cells     # fraction of cells in touched groups
-    bytes_dense = {"apply": 17.0, "smooth": 13.0, "residual_restrict": 9.5, "axpy2_dot": 57.0,
-                   "xpby": 20.0, "dot": 16.0}
+    bytes_dense = {"apply": 17.0, "smooth": 13.0, "residual_restrict": 9.5, "axpy2_dot": 33.0,
+                   "xpby": 37.0, "dot": 16.0}
     bytes_touched = {"apply": 9.0 + 8.0 * fp,              # p 8 + flags 1 staged for every cell; q stored per pair
                      "smooth": 9.0 + 4.0 * fq,             # z 4 + r 4 + flags 1 staged; z' stored per quad
                      "residual_restrict": 9.5,
-                     "axpy2_dot": 1.0 + 56.0 * fp,         # flags; x, r (r/w), p, q, r32, z1 per pair
-                     "xpby": 1.0 + 20.0 * fp,              # flags; p (r/w), z per pair
+                     "axpy2_dot": 1.0 + 32.0 * fp,         # flags; r (r/w), q, r32, z1 per pair (x += alpha p is deferred)
+                     "xpby": 1.0 + 36.0 * fp,              # flags; x (r/w), p (r/w), z per pair
                      "dot": 16.0}
     bytes_per_cell = bytes_touched
     for name, bpc in bytes_per_cell.items():

@@ -73,14 +73,19 @@ void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const dou
                    const double* num, const double* den, double* partials, unsigned int* counter,
                    double* out, int n_sm, cudaStream_t st);
 // same, plus what the next preconditioner application needs: r32 <- mg_t(r_new) and
-// z1 <- w0 * r_new / diag on unknowns (its first smoothing sweep from a zero guess)
+// z1 <- w0 * r_new / diag on unknowns (its first smoothing sweep from a zero guess).
+// x == nullptr: the solution update is deferred to vec_xpby / vec_axpy (x and p untouched)
 void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
                          const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
                          const double* den, double w0, double* partials, unsigned int* counter,
                          double* out, int n_sm, cudaStream_t st);
 // p = z + (num/den) p      (z is a multigrid-precision vector; both zero off the unknowns)
+// x != nullptr: first x += (anum/aden) p with the old p (deferred solution update)
 void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
-              const double* den, int n_sm, cudaStream_t st);
+              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st);
+// x += (num/den) p on the unknowns
+void vec_axpy(long long n, const uint8_t* flags, double* x, const double* p, const double* num, const double* den,
+              int n_sm, cudaStream_t st);
 // conversions between Krylov (fp64) and multigrid precision
 void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st);
 void vec_from_mg(long long n, double* dst, const mg_t* src, int n_sm, cudaStream_t st);

@@ -1105,8 +1105,10 @@ void run_solve(oi_solver* S) {
                 allreduce_sum_f64(S, d_pq, 1);
                 prof_mark(S, "axpy2+dot+first sweep");
                 const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
+                // MG path: x += alpha p is deferred to the xpby below (which reads p anyway);
+                // if the loop ends here instead, vec_axpy applies it
                 if (fuse_first)
-                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->r.p, S->p.p, S->q.p, S->r32.p,
+                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, nullptr, S->r.p, S->p.p, S->q.p, S->r32.p,
                                             S->za.p, d_rz, d_pq, first_smoothing_weight(S), S->d_partials,
                                             S->d_counter, d_rr, S->n_sm, S->st);
                 else
@@ -1117,10 +1119,16 @@ void run_solve(oi_solver* S) {
                 allreduce_sum_f64(S, d_rr, 1);
                 rr = read_scalar(S, d_rr);
                 if (!std::isfinite(rr)) { fail = true; break; }
-                if (std::sqrt(rr) <= tol) { converged = true; break; }
+                if (std::sqrt(rr) <= tol || it >= S->prm.maxiter) {
+                    if (fuse_first) { oi::vec_axpy(n, S->flags.p, S->x.p, S->p.p, d_rz, d_pq, S->n_sm, S->st); S->launches++; }
+                    converged = std::sqrt(rr) <= tol;
+                    break;
+                }
                 apply_precond(S, d_rzn, fuse_first);
                 prof_mark(S, "xpby");
-                oi::vec_xpby(n, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, S->n_sm, S->st); S->launches++;
+                oi::vec_xpby(n, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, fuse_first ? S->x.p : nullptr, d_rz, d_pq,
+                             S->n_sm, S->st);
+                S->launches++;
                 std::swap(d_rz, d_rzn);
             }
             if (fail || !converged) break;
@@ -1999,11 +2007,12 @@ int oi_time_kernel(oi_solver* S, const char* name, int32_t reps, double* avg_ms,
                 a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
                 oi::l0_residual_restrict(a, variant == 1 ? 0 : variant, S->st);
             } else if (k == "axpy2_dot") {
-                oi::vec_axpy2_dot_first(S->g, S->flags.p, n, S->x.p, S->q.p, S->p.p, S->r.p, S->r32.p, S->za.p,
+                oi::vec_axpy2_dot_first(S->g, S->flags.p, n, nullptr, S->q.p, S->p.p, S->r.p, S->r32.p, S->za.p,
                                         S->d_scal + 10, S->d_scal + 11, 0.5, S->d_partials, S->d_counter,
                                         S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "xpby") {
-                oi::vec_xpby(n, S->flags.p, S->q.p, S->za.p, S->d_scal + 10, S->d_scal + 11, S->n_sm, S->st);
+                oi::vec_xpby(n, S->flags.p, S->q.p, S->za.p, S->d_scal + 10, S->d_scal + 11, S->x.p, S->d_scal + 10,
+                             S->d_scal + 11, S->n_sm, S->st);
             } else if (k == "dot") {
                 oi::vec_dot(n, S->r.p, S->q.p, S->d_partials, S->d_counter, S->d_scal + 12, S->n_sm, S->st);
             } else if (k == "precond") {

@@ -45,6 +45,9 @@ axpy2_dot_kernel(long long n, double* __restrict__ x, double* __restrict__ r,
 // Same update, plus what the next preconditioner application needs: the residual in
 // multigrid precision (r32) and its first smoothing sweep from a zero guess,
 // z1 = w0 * r_new / diag.  Saves re-reading r and one launch per Krylov iteration.
+// UPDATE_X = false: x += alpha p is left to the next xpby (which has p in hand anyway), so this
+// kernel touches neither x nor p.
+template <bool UPDATE_X>
 __global__ void __launch_bounds__(VT)
 axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, double* __restrict__ x,
                        double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
@@ -91,9 +94,11 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
         for (int c = 0; c < NC; ++c) {
             if (f[c] & UNK2) {
                 const long long ii = i + c * stride;
-                xv[c] = *reinterpret_cast<const double2*>(x + ii);
+                if (UPDATE_X) {
+                    xv[c] = *reinterpret_cast<const double2*>(x + ii);
+                    pv[c] = *reinterpret_cast<const double2*>(p + ii);
+                }
                 rv[c] = *reinterpret_cast<const double2*>(r + ii);
-                pv[c] = *reinterpret_cast<const double2*>(p + ii);
                 qv[c] = *reinterpret_cast<const double2*>(q + ii);
             }
         }
@@ -101,9 +106,11 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
         for (int c = 0; c < NC; ++c) {
             if (f[c] & UNK2) {
                 const long long ii = i + c * stride;
-                xv[c].x += a * pv[c].x; xv[c].y += a * pv[c].y;
+                if (UPDATE_X) {
+                    xv[c].x += a * pv[c].x; xv[c].y += a * pv[c].y;
+                    *reinterpret_cast<double2*>(x + ii) = xv[c];
+                }
                 rv[c].x -= a * qv[c].x; rv[c].y -= a * qv[c].y;
-                *reinterpret_cast<double2*>(x + ii) = xv[c];
                 *reinterpret_cast<double2*>(r + ii) = rv[c];
                 acc += rv[c].x * rv[c].x + rv[c].y * rv[c].y;
                 const unsigned int f0 = f[c] & 0xffu, f1 = f[c] >> 8;
@@ -118,7 +125,7 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
         const long long i = n2;
-        x[i] += a * p[i];
+        if (UPDATE_X) x[i] += a * p[i];
         const double rv = r[i] - a * q[i];
         r[i] = rv;
         acc += rv * rv;
@@ -130,11 +137,16 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
     grid_reduce<1>(v, partials, counter, out);
 }
 
-// p = z + beta p, skipping 16-byte pairs without an unknown (z = p = 0 there)
+// p = z + beta p, skipping 16-byte pairs without an unknown (z = p = 0 there).
+// UPDATE_X: first x += alpha p with the OLD p (the solution update deferred from the
+// residual kernel: p is read once for both).
+template <bool UPDATE_X>
 __global__ void __launch_bounds__(VT)
 xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ p, const mg_t* __restrict__ z,
-            const double* __restrict__ num, const double* __restrict__ den) {
+            const double* __restrict__ num, const double* __restrict__ den, double* __restrict__ x,
+            const double* __restrict__ anum, const double* __restrict__ aden) {
     const double bta = num[0] / den[0];
+    const double alpha = UPDATE_X ? anum[0] / aden[0] : 0.0;
     const long long stride = (long long)gridDim.x * VT * 2;
     const long long n2 = n & ~1LL;
     typedef typename Vec2<mg_t>::type mg2;
@@ -149,7 +161,7 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
     }
     for (long long i = i0; i < n2; i += NC * stride) {
         unsigned int f[NC];
-        double2 pv[NC];
+        double2 pv[NC], xv[NC];
         mg2 zv[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -162,17 +174,35 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
             if (f[c] & UNK2) {
                 pv[c] = *reinterpret_cast<const double2*>(p + i + c * stride);
                 zv[c] = *reinterpret_cast<const mg2*>(z + i + c * stride);
+                if (UPDATE_X) xv[c] = *reinterpret_cast<const double2*>(x + i + c * stride);
             }
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (f[c] & UNK2) {
+                if (UPDATE_X) {
+                    xv[c].x += alpha * pv[c].x; xv[c].y += alpha * pv[c].y;
+                    *reinterpret_cast<double2*>(x + i + c * stride) = xv[c];
+                }
                 pv[c].x = (double)zv[c].x + bta * pv[c].x; pv[c].y = (double)zv[c].y + bta * pv[c].y;
                 *reinterpret_cast<double2*>(p + i + c * stride) = pv[c];
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) p[n2] = (double)z[n2] + bta * p[n2];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
+        if (UPDATE_X) x[n2] += alpha * p[n2];
+        p[n2] = (double)z[n2] + bta * p[n2];
+    }
+}
+
+// x += (num/den) p : the deferred solution update when the loop ends between two xpby
+__global__ void __launch_bounds__(VT)
+axpy_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ x, const double* __restrict__ p,
+            const double* __restrict__ num, const double* __restrict__ den) {
+    const double a = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride)
+        if (flags[i] & F_UNK) x[i] += a * p[i];
 }
 
 template <typename D, typename S>
@@ -239,12 +269,21 @@ void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, doubl
                          const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
                          const double* den, double w0, double* partials, unsigned int* counter,
                          double* out, int n_sm, cudaStream_t st) {
-    axpy2_dot_first_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den,
-                                                                      w0, partials, counter, out);
+    if (x)
+        axpy2_dot_first_kernel<true><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num,
+                                                                                den, w0, partials, counter, out);
+    else
+        axpy2_dot_first_kernel<false><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num,
+                                                                                 den, w0, partials, counter, out);
 }
 void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
-              const double* den, int n_sm, cudaStream_t st) {
-    xpby_kernel<<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den);
+              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st) {
+    if (x) xpby_kernel<true><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden);
+    else xpby_kernel<false><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr);
+}
+void vec_axpy(long long n, const uint8_t* flags, double* x, const double* p, const double* num, const double* den,
+              int n_sm, cudaStream_t st) {
+    axpy_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(n, flags, x, p, num, den);
 }
 void vec_to_mg(long long n, mg_t* dst, const double* src, int n_sm, cudaStream_t st) {
     convert_kernel<mg_t, double><<<nblocks(n, n_sm), VT, 0, st>>>(n, dst, src);
