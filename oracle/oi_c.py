@@ -120,3 +120,45 @@ def tortuosity(phase, phase_id, direction, vlo=-1.0, vhi=1.0, eps=1e-9, maxiter=
     d = dict(zip(keys, out.tolist()))
     d["iters"], d["n_active"] = int(d["iters"]), int(d["n_active"])
     return d
+
+
+# ---- homogenisation cell problem (second restatement, see oracle/oi_effdiff.py for the numpy one)
+def effdiff_fill_matrix(phase, phase_id, direction, dx=(1.0, 1.0, 1.0)):
+    lib = load()
+    p = _i32(phase)
+    nz, ny, nx = p.shape
+    n = p.size
+    a, rhs, xinit = np.empty((n, 7)), np.empty(n), np.empty(n)
+    d = np.array(dx, dtype=np.float64)
+    lib.oo_effdiff_fillmtx.restype = None
+    lib.oo_effdiff_fillmtx.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.oo_effdiff_fillmtx(a.ctypes.data, rhs.ctypes.data, xinit.ctypes.data, p.ctypes.data, phase_id, nx, ny, nz,
+                           d.ctypes.data, direction)
+    return a, rhs, xinit
+
+
+def effdiff_deff_tensor(phase, phase_id, dx=(1.0, 1.0, 1.0), eps=1e-12, maxiter=100000):
+    """D_eff / D by the C restatement: three Jacobi-PCG corrector solves + gradient sums."""
+    lib = load()
+    p = _i32(phase)
+    nz, ny, nx = p.shape
+    d = np.array(dx, dtype=np.float64)
+    lib.oo_effdiff_solve.restype = C.c_int
+    lib.oo_effdiff_solve.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_double, C.c_int, C.POINTER(C.c_double)]
+    lib.oo_effdiff_gradient_sums.restype = None
+    lib.oo_effdiff_gradient_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.POINTER(C.c_int64)]
+    D = np.zeros((3, 3))
+    iters = []
+    for k in range(3):
+        a, rhs, x = effdiff_fill_matrix(p, phase_id, k, dx)
+        rel = C.c_double(0)
+        iters.append(lib.oo_effdiff_solve(a.ctypes.data, rhs.ctypes.data, x.ctypes.data, nx, ny, nz, eps, maxiter,
+                                          C.byref(rel)))
+        sums = np.zeros(3)
+        na = C.c_int64(0)
+        lib.oo_effdiff_gradient_sums(x.ctypes.data, p.ctypes.data, phase_id, nx, ny, nz, d.ctypes.data,
+                                     sums.ctypes.data, C.byref(na))
+        for ax in range(3):
+            D[ax][k] = ((na.value if ax == k else 0.0) - sums[ax]) / p.size
+    return D, iters

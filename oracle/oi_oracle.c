@@ -361,3 +361,125 @@ int oo_tortuosity(const int32_t* phase, int nx, int ny, int nz, int32_t phase_id
     free(a); free(rhs); free(x); free(mask);
     return 0;
 }
+
+/* ===========================================================================
+ * Homogenisation cell problem (row f-1): second, independent restatement of
+ * effdiff_fillmtx + the periodic Krylov solve + the D_eff tensor sums.
+ * =========================================================================== */
+
+/* effdiff_fillmtx, src/props/EffDiffFillMtx.F90:109-258, on the whole periodic box
+ * (the mask ghosts are filled periodically, EffectiveDiffusivityHypre.cpp:478).
+ * a[7*m+s], slots C,-x,+x,-y,+y,-z,+z (F90:31-37); dx = cell sizes. */
+void oo_effdiff_fillmtx(double* a, double* rhs, double* xinit, const int32_t* phase, int32_t phase_id,
+                        int nx, int ny, int nz, const double* dx, int dir_k) {
+    const double inv2[3] = {1.0 / (dx[0] * dx[0]), 1.0 / (dx[1] * dx[1]), 1.0 / (dx[2] * dx[2])};
+    const double inv_2d[3] = {1.0 / (2.0 * dx[0]), 1.0 / (2.0 * dx[1]), 1.0 / (2.0 * dx[2])};
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t m = IDX(i, j, k);
+                double* row = a + 7 * m;
+                for (int s = 0; s < 7; ++s) row[s] = 0.0;
+                rhs[m] = 0.0;
+                xinit[m] = 0.0;
+                if (phase[m] != phase_id) { row[0] = 1.0; continue; }             /* F90:124-129 */
+                const int64_t nb[6] = {IDX((i + nx - 1) % nx, j, k), IDX((i + 1) % nx, j, k),
+                                       IDX(i, (j + ny - 1) % ny, k), IDX(i, (j + 1) % ny, k),
+                                       IDX(i, j, (k + nz - 1) % nz), IDX(i, j, (k + 1) % nz)};
+                double diag = 0.0, flux = 0.0;
+                int act[6];
+                for (int s = 0; s < 6; ++s) {
+                    const int axis = s / 2;
+                    act[s] = phase[nb[s]] == phase_id;
+                    if (act[s]) row[1 + s] = -inv2[axis];                           /* F90:152-154 */
+                    diag += inv2[axis];                                             /* both branches, F90:153,156 */
+                    if (!act[s] && axis == dir_k) flux += (s & 1) ? -(1.0 / dx[axis]) : (1.0 / dx[axis]);
+                }
+                row[0] = diag;
+                const double div = -((double)act[2 * dir_k + 1] - (double)act[2 * dir_k]) * inv_2d[dir_k];   /* F90:226-234 */
+                rhs[m] = div + flux;
+            }
+}
+
+static void matvec7_periodic(const double* a, const double* x, double* y, int nx, int ny, int nz) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t m = IDX(i, j, k);
+                const double* r = a + 7 * m;
+                double s = r[0] * x[m];
+                if (r[1] != 0.0) s += r[1] * x[IDX((i + nx - 1) % nx, j, k)];
+                if (r[2] != 0.0) s += r[2] * x[IDX((i + 1) % nx, j, k)];
+                if (r[3] != 0.0) s += r[3] * x[IDX(i, (j + ny - 1) % ny, k)];
+                if (r[4] != 0.0) s += r[4] * x[IDX(i, (j + 1) % ny, k)];
+                if (r[5] != 0.0) s += r[5] * x[IDX(i, j, (k + nz - 1) % nz)];
+                if (r[6] != 0.0) s += r[6] * x[IDX(i, j, (k + 1) % nz)];
+                y[m] = s;
+            }
+}
+
+/* EffectiveDiffusivityHypre::solve (src/props/EffectiveDiffusivityHypre.cpp:543-676) restated as
+ * Jacobi-PCG on the periodic struct matrix; stop ||b - A x|| <= eps ||b||.  Returns iterations. */
+int oo_effdiff_solve(const double* a, const double* rhs, double* x, int nx, int ny, int nz, double eps,
+                     int maxiter, double* relres) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    double* r = (double*)malloc(sizeof(double) * (size_t)n);
+    double* z = (double*)malloc(sizeof(double) * (size_t)n);
+    double* p = (double*)malloc(sizeof(double) * (size_t)n);
+    double* q = (double*)malloc(sizeof(double) * (size_t)n);
+    matvec7_periodic(a, x, q, nx, ny, nz);
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < n; ++m) r[m] = rhs[m] - q[m];
+    const double bnorm = sqrt(dot(rhs, rhs, n));
+    double rn = sqrt(dot(r, r, n));
+    const double tol = eps * bnorm;
+    int it = 0;
+    if (bnorm > 0.0 && rn > tol) {
+#pragma omp parallel for schedule(static)
+        for (int64_t m = 0; m < n; ++m) { z[m] = r[m] / a[7 * m]; p[m] = z[m]; }
+        double rz = dot(r, z, n);
+        while (it < maxiter) {
+            ++it;
+            matvec7_periodic(a, p, q, nx, ny, nz);
+            const double alpha = rz / dot(p, q, n);
+            double rr = 0.0;
+#pragma omp parallel for reduction(+ : rr) schedule(static)
+            for (int64_t m = 0; m < n; ++m) { x[m] += alpha * p[m]; r[m] -= alpha * q[m]; rr += r[m] * r[m]; }
+            rn = sqrt(rr);
+            if (!(rn > tol)) break;
+            double rzn = 0.0;
+#pragma omp parallel for reduction(+ : rzn) schedule(static)
+            for (int64_t m = 0; m < n; ++m) { z[m] = r[m] / a[7 * m]; rzn += r[m] * z[m]; }
+            const double beta = rzn / rz;
+            rz = rzn;
+#pragma omp parallel for schedule(static)
+            for (int64_t m = 0; m < n; ++m) p[m] = z[m] + beta * p[m];
+        }
+    }
+    if (relres) *relres = bnorm > 0.0 ? rn / bnorm : 0.0;
+    free(r); free(z); free(p); free(q);
+    return it;
+}
+
+/* One column of calculate_Deff_tensor_homogenization (src/props/Diffusion.cpp:97-141): sums over the
+ * active cells of the central differences of chi_k (periodic; chi = 0 in the solid). */
+void oo_effdiff_gradient_sums(const double* chi, const int32_t* phase, int32_t phase_id, int nx, int ny, int nz,
+                              const double* dx, double* sums3, int64_t* n_active) {
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    int64_t na = 0;
+#pragma omp parallel for reduction(+ : sx, sy, sz, na) schedule(static)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t m = IDX(i, j, k);
+                if (phase[m] != phase_id) continue;
+                ++na;
+                sx += (chi[IDX((i + 1) % nx, j, k)] - chi[IDX((i + nx - 1) % nx, j, k)]) * (1.0 / (2.0 * dx[0]));
+                sy += (chi[IDX(i, (j + 1) % ny, k)] - chi[IDX(i, (j + ny - 1) % ny, k)]) * (1.0 / (2.0 * dx[1]));
+                sz += (chi[IDX(i, j, (k + 1) % nz)] - chi[IDX(i, j, (k + nz - 1) % nz)]) * (1.0 / (2.0 * dx[2]));
+            }
+    sums3[0] = sx; sums3[1] = sy; sums3[2] = sz;
+    if (n_active) *n_active = na;
+}

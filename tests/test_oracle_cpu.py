@@ -211,3 +211,23 @@ def test_effdiff_golden_is_symmetric_and_near_porosity(sample_phase):
         assert g[f"phase{pid}"]["n_active"] == n == int((sample_phase == pid).sum())
         np.testing.assert_allclose(D, D.T, rtol=0, atol=1e-9)
         assert np.all(np.abs(np.diag(D) - n / 1e6) < 0.02)
+
+
+def test_effdiff_two_restatements_agree(oc, sample_phase):
+    """numpy/scipy (oracle/oi_effdiff.py) against plain C (oracle/oi_oracle.c): rows bit-exact,
+    tensors to 1e-9; the C one also reproduces the committed golden tensor of the sample image."""
+    import json
+    from oracle import oi_effdiff as oe
+    rng = np.random.default_rng(41)
+    ph = (rng.random((9, 12, 14)) < 0.55).astype(np.int32)
+    for dx in ((1.0, 1.0, 1.0), (0.5, 1.25, 2.0)):
+        for k in range(3):
+            a1, r1, x1 = oe.fill_matrix(ph, 1, k, dx)
+            a2, r2, x2 = oc.effdiff_fill_matrix(ph, 1, k, dx)
+            assert np.array_equal(a1, a2) and np.array_equal(r1, r2) and not x2.any()
+        D1 = oe.deff_tensor(ph, 1, dx)
+        D2, iters = oc.effdiff_deff_tensor(ph, 1, dx)
+        assert np.abs(D1 - D2).max() < 1e-9 and max(iters) > 0
+    gold = json.load(open(os.path.join(GOLDEN, "effdiff_golden.json")))
+    D, _ = oc.effdiff_deff_tensor(sample_phase, 1, eps=1e-11)
+    assert np.abs(D - np.array(gold["phase1"]["deff"])).max() < 1e-8
