@@ -954,11 +954,29 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         L0Args a = l0args(S, nullptr, rhs, cur, w[0], nullptr);
         oi::l0_jacobi_first(a, S->st); S->launches++;
     }
-    for (int s = 1; s < deg; ++s) {
-        halo0(S, cur);
+    // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout).
+    // Opt-in (OI_PAIR=1, read per call so that tests can compare both paths): at 1024^3 the pair
+    // kernel takes 6.1 ms against 4.9 ms for two single sweeps -- it halves the DRAM bytes but runs
+    // latency-bound (two barriers per plane, 16 warps per SM at 89 KB of shared memory per CTA).
+    const char* pair_env = getenv("OI_PAIR");
+    const bool no_pair = !(pair_env && pair_env[0] == '1');
+    bool use_pair = false;
+    {
+        L0Args a = l0args(S, cur, rhs, oth, 0.0, nullptr);
+        use_pair = !no_pair && variant == 0 && S->n_ranks == 1 && oi::pair_supported(a) && oi::ring_supported(a, 1);
+    }
+    for (int s = 1; s < deg;) {
         L0Args a = l0args(S, cur, rhs, oth, w[s], dot_out);
-        const bool dot = (!have_coarse && s == deg - 1 && dot_out);
-        oi::l0_smooth(a, false, dot, variant, S->st); S->launches++;
+        if (use_pair && s + 1 < deg) {
+            const bool dot = (!have_coarse && s + 1 == deg - 1 && dot_out);
+            oi::l0_smooth_pair(a, w[s], w[s + 1], dot, S->st); S->launches++;
+            s += 2;
+        } else {
+            halo0(S, cur);
+            const bool dot = (!have_coarse && s == deg - 1 && dot_out);
+            oi::l0_smooth(a, false, dot, variant, S->st); S->launches++;
+            s += 1;
+        }
         std::swap(cur, oth);
     }
     if (have_coarse) {
@@ -983,8 +1001,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         coarse_cycle(S, 0);
         prof_mark(S, "l0 prolong+post-smooth");
         haloL(S, h1.L, h1.L.x);
-        for (int s = 0; s < deg; ++s) {
-            const bool dot = (s == deg - 1) && dot_out;
+        for (int s = 0; s < deg;) {
             L0Args a = l0args(S, cur, rhs, oth, w[deg - 1 - s], dot_out);
             a.ec = h1.L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
             bool addc = (s == 0);
@@ -998,7 +1015,15 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             } else if (s > 0) {
                 halo0(S, cur);
             }
-            oi::l0_smooth(a, addc, dot, variant, S->st); S->launches++;
+            if (use_pair && !addc && s + 1 < deg) {
+                const bool dot = (s + 1 == deg - 1) && dot_out;
+                oi::l0_smooth_pair(a, w[deg - 1 - s], w[deg - 2 - s], dot, S->st); S->launches++;
+                s += 2;
+            } else {
+                const bool dot = (s == deg - 1) && dot_out;
+                oi::l0_smooth(a, addc, dot, variant, S->st); S->launches++;
+                s += 1;
+            }
             std::swap(cur, oth);
         }
     } else if (deg == 1 && dot_out) {

@@ -336,3 +336,34 @@ def test_streamed_upload_rejects_incomplete_slab(capi):
         assert lib.oi_phase_stream_submit(s._h, 0, 0, 4) != 0          # larger than the staging buffer
         assert lib.oi_phase_stream_end(s._h) != 0                      # 3 of 8 planes only
         assert b"every plane" in lib.oi_last_error()
+
+
+# ------------------------------------------------------------------ two sweeps per pass
+@pytest.mark.parametrize("shape,seed,por", [((40, 37, 100), 51, 0.5), ((70, 64, 64), 52, 0.45), ((33, 16, 8), 53, 0.6),
+                                            ((20, 130, 132), 54, 0.55)])
+@pytest.mark.parametrize("direction", [0, 2])
+def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, monkeypatch):
+    """The temporally blocked smoother (two sweeps per pass, oi_level0_pair.cu; opt-in with
+    OI_PAIR=1) against the single-sweep ring kernels: same V-cycle output (fp32 rounding only),
+    same iteration count, same tau.  Shapes cover partial tiles in x and y and z-chunk boundaries."""
+    ph = _blobs(shape, seed, por)
+    rng = np.random.default_rng(seed)
+    res = {}
+    for no_pair in ("1", "0"):
+        monkeypatch.setenv("OI_PAIR", "0" if no_pair == "1" else "1")
+        with capi.Solver(shape, direction, 1, -1.0, 1.0) as s:
+            s.set_phase(ph)
+            if s.build_mask() == 0:
+                pytest.skip("nothing percolates")
+            act = s.mask().astype(bool)
+            r = np.where(act, np.random.default_rng(seed).standard_normal(shape), 0.0)
+            z = s.apply_precond(r)
+            info = s.solve()
+            res[no_pair] = (z, info.iterations, s.fluxes()[:2], s.launch_count())
+    z1, it1, fl1, l1 = res["1"]
+    z0, it0, fl0, l0 = res["0"]
+    assert l0 < l1                                               # fewer launches: the pairs really ran
+    scale = float(np.abs(z1).max())
+    assert float(np.abs(z0 - z1).max()) <= 2e-5 * scale          # fp32 V-cycle, different summation order only
+    assert abs(it0 - it1) <= 1
+    assert abs(fl0[0] - fl1[0]) <= 1e-7 * abs(fl1[0]) and abs(fl0[1] - fl1[1]) <= 1e-7 * abs(fl1[1])
