@@ -9,7 +9,9 @@
 //   A) forms the intermediate v on the tile plus a one-cell rim (66 x 18 cells) from three
 //      input planes staged with a two-cell rim (68 x 20), and keeps the last three planes
 //      of v in shared memory;
-//   B) forms the final value of the plane below from those three planes of v.
+//   B) forms the final value of the plane two below from the last three planes of v (its own
+//      column travels in registers, only the x / y neighbours come from shared memory), so one
+//      CTA barrier per plane suffices.
 // Input, rhs and flag planes arrive through cp.async rings exactly as in the single-sweep
 // kernel.  Rim values are recomputed by the neighbouring CTAs (16 % more arithmetic), their
 // loads mostly hit L2.  Every field is zero off the unknowns and outside the box, so no
@@ -19,11 +21,11 @@
 // non-periodic box (ghost planes are one deep), nx % 4 == 0, fp32 multigrid vectors.
 //
 // STATUS (round 1): correct (tests/test_gpu_parity.py::test_pair_kernel_matches_single_sweeps) but
-// not yet faster -- 6.1 ms per pair at 1024^3 against 2 x 2.43 ms for two single sweeps.  It is
-// latency-bound, not bandwidth-bound: 89 KB of shared memory per CTA leaves 2 CTAs = 16 warps per
-// SM, there are two CTA barriers per plane, and all seven operands of both stages come from shared
-// memory.  Opt-in with OI_PAIR=1; next steps are register-carried z columns (as in the ring
-// kernel), 512-thread CTAs and a shallower rhs ring.
+// not yet faster -- 5.7 ms per pair at 1024^3 against 2 x 2.43 ms for two single sweeps (the first
+// version, with two barriers per plane and every operand from shared memory, took 6.3 ms).  It is
+// latency-bound, not bandwidth-bound: ~100 registers and 89 KB of shared memory per CTA leave
+// 2 CTAs = 16 warps per SM.  Opt-in with OI_PAIR=1; next steps: 512-thread CTAs (2 cells per
+// thread), a shallower rhs / flag ring, rim work spread over more threads.
 #include "oi_kernels.h"
 
 namespace oi {
@@ -34,8 +36,8 @@ constexpr int PTX = 64, PTY = 16;              // tile (cells)
 constexpr int PW = PTX + 8;                    // smem row pitch: [4 left | 64 | 4 right] cells
 constexpr int UH = PTY + 4;                    // rows of an input stage   (two-cell rim)
 constexpr int VH = PTY + 2;                    // rows of a v / rhs / flag stage (one-cell rim)
-constexpr int PP = 3;                          // planes in flight beyond the newest one needed
-constexpr int PR = PP + 3;                     // ring stages
+constexpr int PP = 2;                          // planes in flight beyond the newest one needed
+constexpr int PR = PP + 4;                     // ring stages (one spare: see the refill comment)
 constexpr int U_ST = UH * PW, V_ST = VH * PW;  // elements per stage
 
 __device__ __forceinline__ void cpa16(void* s, const void* g, bool ok) {
@@ -135,89 +137,115 @@ l0_pair_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restric
     const bool inb = u_ok1;
     float* out_own = out + u_col1;
     double dot_acc = 0.0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // kk = plane whose intermediate is formed this trip; the final value of plane kk-1 follows
+    // own-group values that travel in registers instead of through shared memory:
+    //   input column: planes kk-1, kk (the plane kk+1 is read once per trip)
+    //   intermediate: v(kk-3), v(kk-2), v(kk-1) as produced by stage A of the last three trips
+    //   rhs / flags of planes kk-2, kk-1 (read once, in stage A)
+    float4 u_m = zero4, u_c = zero4;
+    float4 v3 = zero4, v2 = zero4, v1 = zero4;
+    float4 b2 = zero4, b1 = zero4;
+    unsigned int f2 = 0u, f1 = 0u;
+    cpa_wait<PP + 1>();                    // planes k0-2, k0-1 have landed
+    __syncthreads();
+    if (k0 - 2 >= -1) u_m = *reinterpret_cast<const float4*>(us + stage_of(k0 - 2) * U_ST + u_off1);
+    u_c = *reinterpret_cast<const float4*>(us + stage_of(k0 - 1) * U_ST + u_off1);
+
+    // Trip kk: stage A forms v(kk) (tile + rim, written to the v ring), stage B the final value of
+    // plane kk-2 from v(kk-3 .. kk-1).  B only reads rim values that were written at least one trip
+    // (= one barrier) earlier, so one barrier per plane is enough and A and B overlap freely.
 #pragma unroll 1
-    for (int kk = k0 - 1; kk <= k1; ++kk) {
+    for (int kk = k0 - 1; kk <= k1 + 1; ++kk) {
         cpa_wait<PP>();                    // planes <= kk+1 have landed (this thread's copies)
-        __syncthreads();                   // ... everybody's; and the previous trip's reads are done
+        __syncthreads();                   // ... everybody's; v(kk-1) is complete; last trip's reads are done
 
         // ---- A: v(kk) on the tile + rim
         float* V = vs + (((kk % 3) + 3) % 3) * V_ST;
         const bool plane_in = (kk >= 0 && kk < g.nz);
-        {
+        float4 oA = zero4, bA = zero4;
+        unsigned int fA = 0u;
+        float4 u_p = zero4;
+        if (kk <= k1) {
             const float* Um = us + stage_of(kk - 1) * U_ST;
             const float* Uc = us + stage_of(kk) * U_ST;
             const float* Up = us + stage_of(kk + 1) * U_ST;
             const float* B = bs + stage_of(kk) * V_ST;
             const unsigned char* F = fs + stage_of(kk) * V_ST;
-            // a group at stage row r (0..17 in v coordinates), group gq (0..17); `only` < 0: all four
-            // cells, else just that cell of the group (the rim needs one column of a side group)
-            auto do_group = [&](int r, int gq, int only) {
-                const int vo = r * PW + 4 * gq;              // v / rhs / flag offset
-                const int uo = (r + 1) * PW + 4 * gq;        // same cell in an input stage
+            if (kk + 1 <= g.nz) u_p = *reinterpret_cast<const float4*>(Up + u_off1);
+            if (plane_in) {
+                // own group: z neighbours from registers
+                const int vo = v_off1, uo = u_off1;
+                fA = *reinterpret_cast<const unsigned int*>(F + vo);
+                bA = *reinterpret_cast<const float4*>(B + vo);
+                const float4 sS = *reinterpret_cast<const float4*>(Uc + uo - PW);
+                const float4 nN = *reinterpret_cast<const float4*>(Uc + uo + PW);
+                const float xw = Uc[uo - 1], xe = Uc[uo + 4];
+                oA.x = relax(fA & 0xffu, u_c.x, xw, u_c.y, sS.x, nN.x, u_m.x, u_p.x, bA.x, w1, cx, cy, cz, dtab);
+                oA.y = relax((fA >> 8) & 0xffu, u_c.y, u_c.x, u_c.z, sS.y, nN.y, u_m.y, u_p.y, bA.y, w1, cx, cy, cz, dtab);
+                oA.z = relax((fA >> 16) & 0xffu, u_c.z, u_c.y, u_c.w, sS.z, nN.z, u_m.z, u_p.z, bA.z, w1, cx, cy, cz, dtab);
+                oA.w = relax(fA >> 24, u_c.w, u_c.z, xe, sS.w, nN.w, u_m.w, u_p.w, bA.w, w1, cx, cy, cz, dtab);
+            }
+            *reinterpret_cast<float4*>(V + v_off1) = oA;
+            if (vr2 >= 0) {                // rim group (everything from shared memory)
+                const int only = vg2 == 0 ? 3 : (vg2 == 17 ? 0 : -1);
+                const int vo = vr2 * PW + 4 * vg2, uo = (vr2 + 1) * PW + 4 * vg2;
                 if (!plane_in) {
-                    if (only < 0) *reinterpret_cast<float4*>(V + vo) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (only < 0) *reinterpret_cast<float4*>(V + vo) = zero4;
                     else V[vo + only] = 0.f;
-                    return;
-                }
-                const unsigned int fw = *reinterpret_cast<const unsigned int*>(F + vo);
-                if (only < 0) {
-                    const float4 c = *reinterpret_cast<const float4*>(Uc + uo);
-                    const float4 s = *reinterpret_cast<const float4*>(Uc + uo - PW);
-                    const float4 n = *reinterpret_cast<const float4*>(Uc + uo + PW);
-                    const float4 d = *reinterpret_cast<const float4*>(Um + uo);
-                    const float4 p = *reinterpret_cast<const float4*>(Up + uo);
-                    const float4 bb = *reinterpret_cast<const float4*>(B + vo);
-                    const float xw = Uc[uo - 1], xe = Uc[uo + 4];
-                    float4 o;
-                    o.x = relax(fw & 0xffu, c.x, xw, c.y, s.x, n.x, d.x, p.x, bb.x, w1, cx, cy, cz, dtab);
-                    o.y = relax((fw >> 8) & 0xffu, c.y, c.x, c.z, s.y, n.y, d.y, p.y, bb.y, w1, cx, cy, cz, dtab);
-                    o.z = relax((fw >> 16) & 0xffu, c.z, c.y, c.w, s.z, n.z, d.z, p.z, bb.z, w1, cx, cy, cz, dtab);
-                    o.w = relax(fw >> 24, c.w, c.z, xe, s.w, n.w, d.w, p.w, bb.w, w1, cx, cy, cz, dtab);
-                    *reinterpret_cast<float4*>(V + vo) = o;
                 } else {
-                    const int a = uo + only;
-                    V[vo + only] = relax((fw >> (8 * only)) & 0xffu, Uc[a], Uc[a - 1], Uc[a + 1], Uc[a - PW], Uc[a + PW],
-                                         Um[a], Up[a], B[vo + only], w1, cx, cy, cz, dtab);
+                    const unsigned int fw = *reinterpret_cast<const unsigned int*>(F + vo);
+                    if (only < 0) {
+                        const float4 c = *reinterpret_cast<const float4*>(Uc + uo);
+                        const float4 sS = *reinterpret_cast<const float4*>(Uc + uo - PW);
+                        const float4 nN = *reinterpret_cast<const float4*>(Uc + uo + PW);
+                        const float4 d = *reinterpret_cast<const float4*>(Um + uo);
+                        const float4 pp = *reinterpret_cast<const float4*>(Up + uo);
+                        const float4 bb = *reinterpret_cast<const float4*>(B + vo);
+                        const float xw = Uc[uo - 1], xe = Uc[uo + 4];
+                        float4 o;
+                        o.x = relax(fw & 0xffu, c.x, xw, c.y, sS.x, nN.x, d.x, pp.x, bb.x, w1, cx, cy, cz, dtab);
+                        o.y = relax((fw >> 8) & 0xffu, c.y, c.x, c.z, sS.y, nN.y, d.y, pp.y, bb.y, w1, cx, cy, cz, dtab);
+                        o.z = relax((fw >> 16) & 0xffu, c.z, c.y, c.w, sS.z, nN.z, d.z, pp.z, bb.z, w1, cx, cy, cz, dtab);
+                        o.w = relax(fw >> 24, c.w, c.z, xe, sS.w, nN.w, d.w, pp.w, bb.w, w1, cx, cy, cz, dtab);
+                        *reinterpret_cast<float4*>(V + vo) = o;
+                    } else {
+                        const int a = uo + only;
+                        V[vo + only] = relax((fw >> (8 * only)) & 0xffu, Uc[a], Uc[a - 1], Uc[a + 1], Uc[a - PW],
+                                             Uc[a + PW], Um[a], Up[a], B[vo + only], w1, cx, cy, cz, dtab);
+                    }
                 }
-            };
-            do_group(ty + 1, 1 + tx, -1);
-            if (vr2 >= 0) do_group(vr2, vg2, vg2 == 0 ? 3 : (vg2 == 17 ? 0 : -1));
+            }
         }
-        __syncthreads();
 
-        // ---- B: final value of plane kk-1 on the tile
-        const int k = kk - 1;
+        // ---- B: final value of plane kk-2 on the tile: z neighbours and centre from registers,
+        // x / y neighbours from the v stage of plane kk-2 (written two trips ago)
+        const int k = kk - 2;
         if (k >= k0 && k < k1) {
-            const float* Vm = vs + ((((k - 1) % 3) + 3) % 3) * V_ST;
             const float* Vc = vs + (((k % 3) + 3) % 3) * V_ST;
-            const float* Vp = V;
-            const float* B = bs + stage_of(k) * V_ST;
-            const unsigned char* F = fs + stage_of(k) * V_ST;
             const int vo = v_off1;
-            const unsigned int fw = *reinterpret_cast<const unsigned int*>(F + vo);
-            const float4 c = *reinterpret_cast<const float4*>(Vc + vo);
-            const float4 s = *reinterpret_cast<const float4*>(Vc + vo - PW);
-            const float4 n = *reinterpret_cast<const float4*>(Vc + vo + PW);
-            const float4 d = *reinterpret_cast<const float4*>(Vm + vo);
-            const float4 p = *reinterpret_cast<const float4*>(Vp + vo);
-            const float4 bb = *reinterpret_cast<const float4*>(B + vo);
+            const float4 sS = *reinterpret_cast<const float4*>(Vc + vo - PW);
+            const float4 nN = *reinterpret_cast<const float4*>(Vc + vo + PW);
             const float xw = Vc[vo - 1], xe = Vc[vo + 4];
             float4 o;
-            o.x = relax(fw & 0xffu, c.x, xw, c.y, s.x, n.x, d.x, p.x, bb.x, w2, cx, cy, cz, dtab);
-            o.y = relax((fw >> 8) & 0xffu, c.y, c.x, c.z, s.y, n.y, d.y, p.y, bb.y, w2, cx, cy, cz, dtab);
-            o.z = relax((fw >> 16) & 0xffu, c.z, c.y, c.w, s.z, n.z, d.z, p.z, bb.z, w2, cx, cy, cz, dtab);
-            o.w = relax(fw >> 24, c.w, c.z, xe, s.w, n.w, d.w, p.w, bb.w, w2, cx, cy, cz, dtab);
-            if (DOT) dot_acc += (double)bb.x * (double)o.x + (double)bb.y * (double)o.y + (double)bb.z * (double)o.z +
-                                (double)bb.w * (double)o.w;
+            o.x = relax(f2 & 0xffu, v2.x, xw, v2.y, sS.x, nN.x, v3.x, v1.x, b2.x, w2, cx, cy, cz, dtab);
+            o.y = relax((f2 >> 8) & 0xffu, v2.y, v2.x, v2.z, sS.y, nN.y, v3.y, v1.y, b2.y, w2, cx, cy, cz, dtab);
+            o.z = relax((f2 >> 16) & 0xffu, v2.z, v2.y, v2.w, sS.z, nN.z, v3.z, v1.z, b2.z, w2, cx, cy, cz, dtab);
+            o.w = relax(f2 >> 24, v2.w, v2.z, xe, sS.w, nN.w, v3.w, v1.w, b2.w, w2, cx, cy, cz, dtab);
+            if (DOT) dot_acc += (double)b2.x * (double)o.x + (double)b2.y * (double)o.y + (double)b2.z * (double)o.z +
+                                (double)b2.w * (double)o.w;
             // a group without an unknown stays zero: its sector is never written
-            if (inb && (fw & 0x40404040u)) *reinterpret_cast<float4*>(out_own + (long long)k * g.plane) = o;
+            if (inb && (f2 & 0x40404040u)) *reinterpret_cast<float4*>(out_own + (long long)k * g.plane) = o;
         }
+        // rotate the register queues
+        u_m = u_c; u_c = u_p;
+        v3 = v2; v2 = v1; v1 = oA;
+        b2 = b1; b1 = bA;
+        f2 = f1; f1 = fA;
 
-        // refill: plane kk+2+PP takes the stage of plane kk-1, the oldest one.  Its input was last read
-        // in A above (before the barrier); of its rhs / flags B read only this thread's own group,
-        // and the other groups copied here are rim groups, which B never reads.
+        // refill: plane kk+2+PP takes the stage of plane kk-2 (PR = PP + 4 stages).  Nobody reads
+        // that plane any more: its input was last used by stage A of the previous trip, which every
+        // thread left before this trip's barrier; slower threads still in this trip need kk-1 .. kk+1.
         issue(kk + 2 + PP);
         cpa_commit();
     }

@@ -956,8 +956,8 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     }
     // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout).
     // Opt-in (OI_PAIR=1, read per call so that tests can compare both paths): at 1024^3 the pair
-    // kernel takes 6.1 ms against 4.9 ms for two single sweeps -- it halves the DRAM bytes but runs
-    // latency-bound (two barriers per plane, 16 warps per SM at 89 KB of shared memory per CTA).
+    // kernel takes 5.7 ms against 4.9 ms for two single sweeps -- it halves the DRAM bytes but runs
+    // latency-bound (16 warps per SM at ~100 registers / 89 KB of shared memory per CTA).
     const char* pair_env = getenv("OI_PAIR");
     const bool no_pair = !(pair_env && pair_env[0] == '1');
     bool use_pair = false;
