@@ -38,7 +38,7 @@ void l0_jacobi_first(const L0Args& a, cudaStream_t st);
 // two smoothing sweeps in one pass (oi_level0_pair.cu): out = S_w2(S_w1(u)); needs one z-slab,
 // a non-periodic box, nx % 4 == 0 and fp32 multigrid vectors
 bool pair_supported(const L0Args& a);
-void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, cudaStream_t st);
+void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant, cudaStream_t st);
 
 // ---------------------------------------------------------------- coarse levels
 // 7-point operator with stored face couplings (Galerkin sums of fine faces):

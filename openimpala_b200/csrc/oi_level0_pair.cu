@@ -21,11 +21,13 @@
 // non-periodic box (ghost planes are one deep), nx % 4 == 0, fp32 multigrid vectors.
 //
 // STATUS (round 1): correct (tests/test_gpu_parity.py::test_pair_kernel_matches_single_sweeps) but
-// not yet faster -- 5.7 ms per pair at 1024^3 against 2 x 2.43 ms for two single sweeps (the first
-// version, with two barriers per plane and every operand from shared memory, took 6.3 ms).  It is
-// latency-bound, not bandwidth-bound: ~100 registers and 89 KB of shared memory per CTA leave
-// 2 CTAs = 16 warps per SM.  Opt-in with OI_PAIR=1; next steps: 512-thread CTAs (2 cells per
-// thread), a shallower rhs / flag ring, rim work spread over more threads.
+// not yet faster than two single sweeps (2 x 2.43 ms at 1024^3):
+//   v1  256 threads, two barriers per plane, every operand from shared memory      6.3 ms
+//   v2  256 threads, one barrier per plane, own columns in registers (OI_PAIR=1)   5.7 ms
+//   v3  512 threads x 2 cells, 32 warps per SM (OI_PAIR=2)                          5.0 ms
+// It halves the DRAM bytes but is instruction / latency bound: two stencil evaluations plus the
+// rim (16 %) per cell per pass.  Opt-in; next steps: packed fp32 arithmetic (fma.rn.f32x2 on
+// sm_100), rim work spread over all warps, a shallower rhs / flag ring.
 #include "oi_kernels.h"
 
 namespace oi {
@@ -257,6 +259,157 @@ l0_pair_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Variant with 512 threads per CTA (2 cells per thread): same tile, rings and trip structure,
+// twice the warps per SM (2 CTAs x 16 warps) to hide the shared-memory and barrier latency
+// that bounds the 256-thread version.  Copy duties are one 16-byte group per thread.
+__device__ __forceinline__ float relax2(unsigned int f, float c, float w_, float e_, float s_, float n_, float d_,
+                                        float u_, float bb, float w, float cx, float cy, float cz,
+                                        const float2* dtab2) {
+    const float2 dd = dtab2[f & 63u];
+    const float au = dd.x * c - (cx * (w_ + e_) + cy * (s_ + n_) + cz * (d_ + u_));
+    return (f & F_UNK) ? c + w * (bb - au) * dd.y : 0.f;
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(512, 2)
+l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restrict__ u,
+                  const float* __restrict__ b, float* __restrict__ out, float w1, float w2, int zchunk,
+                  double* red_partials, unsigned int* red_counter, double* red_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* us = reinterpret_cast<float*>(smem_raw);            // [PR][UH][PW]
+    float* bs = us + PR * U_ST;                                // [PR][VH][PW]
+    float* vs = bs + PR * V_ST;                                // [3][VH][PW]
+    float2* dtab2 = reinterpret_cast<float2*>(vs + 3 * V_ST);  // [64] {diagonal, inverse}
+    unsigned char* fs = reinterpret_cast<unsigned char*>(dtab2 + 64);   // [PR][VH][PW] bytes
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;                    // 32 pairs x 16 rows
+    const int i0 = blockIdx.x * PTX, j0 = blockIdx.y * PTY;
+    const int k0 = blockIdx.z * zchunk, k1 = min(k0 + zchunk, g.nz);
+    const float cx = (float)g.cx, cy = (float)g.cy, cz = (float)g.cz;
+    if (tid < 64) {
+        const float d = row_diag<float>((unsigned int)tid, g);
+        dtab2[tid] = make_float2(d, d > 0.f ? 1.f / d : 0.f);
+    }
+    auto in_box = [&](int gi, int gj) { return gi >= 0 && gi < g.nx && gj >= 0 && gj < g.ny; };
+
+    // copy duties: input plane 20 rows x 18 groups (tid < 360), rhs / flag plane 18 x 18 (tid < 324)
+    const bool u_duty = tid < UH * 18, v_duty = tid < VH * 18;
+    const int ur = tid / 18, ug = tid % 18;
+    const int u_i = i0 + 4 * (ug - 1), u_j = j0 - 2 + ur;
+    const bool u_ok = u_duty && in_box(u_i, u_j);
+    const long long u_col = u_ok ? (long long)u_j * g.nx + u_i : 0;
+    const int u_dst = ur * PW + 4 * ug;
+    const int v_j = j0 - 1 + ur;                               // same (row, group) split, one row less rim
+    const bool v_ok = v_duty && in_box(u_i, v_j);
+    const long long v_col = v_ok ? (long long)v_j * g.nx + u_i : 0;
+    const int v_dst = ur * PW + 4 * ug;
+
+    // own pair
+    const int oi = i0 + 2 * tx, oj = j0 + ty;
+    const bool inb = in_box(oi, oj);
+    const long long o_col = inb ? (long long)oj * g.nx + oi : 0;
+    const int u_off = (ty + 2) * PW + 4 + 2 * tx;
+    const int v_off = (ty + 1) * PW + 4 + 2 * tx;
+    // rim duty: rows 0 and 17 as 64 pairs (tid < 64), the two side columns as 36 single cells (tid 64..99)
+    int rim_kind = 0, rim_vo = 0;                              // 1 = pair, 2 = single cell
+    if (tid < 64) { rim_kind = 1; rim_vo = ((tid >> 5) ? VH - 1 : 0) * PW + 4 + 2 * (tid & 31); }
+    else if (tid < 100) { const int t = tid - 64; rim_kind = 2; rim_vo = (t % VH) * PW + ((t / VH) ? 4 + PTX : 3); }
+
+    auto stage_of = [&](int q) { return ((q - (k0 - 2)) % PR + PR) % PR; };
+    auto issue = [&](int q) {
+        if (q < -1 || q > g.nz) return;
+        const int st = stage_of(q);
+        const long long poff = (long long)q * g.plane;
+        if (u_duty) cpa16(us + st * U_ST + u_dst, u + poff + u_col, u_ok);
+        if (v_duty) {
+            cpa16(bs + st * V_ST + v_dst, b + poff + v_col, v_ok);
+            cpa4(fs + st * V_ST + v_dst, flags + poff + v_col, v_ok);
+        }
+    };
+#pragma unroll 1
+    for (int q = k0 - 2; q <= k0 + PP; ++q) { issue(q); cpa_commit(); }
+
+    float* out_own = out + o_col;
+    double dot_acc = 0.0;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 u_m = zero2, u_c = zero2, v3 = zero2, v2 = zero2, v1 = zero2, b2 = zero2, b1 = zero2;
+    unsigned int f2 = 0u, f1 = 0u;
+    cpa_wait<PP + 1>();
+    __syncthreads();
+    if (k0 - 2 >= -1) u_m = *reinterpret_cast<const float2*>(us + stage_of(k0 - 2) * U_ST + u_off);
+    u_c = *reinterpret_cast<const float2*>(us + stage_of(k0 - 1) * U_ST + u_off);
+
+#pragma unroll 1
+    for (int kk = k0 - 1; kk <= k1 + 1; ++kk) {
+        cpa_wait<PP>();
+        __syncthreads();
+
+        float* V = vs + (((kk % 3) + 3) % 3) * V_ST;
+        const bool plane_in = (kk >= 0 && kk < g.nz);
+        float2 oA = zero2, bA = zero2, u_p = zero2;
+        unsigned int fA = 0u;
+        if (kk <= k1) {
+            const float* Um = us + stage_of(kk - 1) * U_ST;
+            const float* Uc = us + stage_of(kk) * U_ST;
+            const float* Up = us + stage_of(kk + 1) * U_ST;
+            const float* B = bs + stage_of(kk) * V_ST;
+            const unsigned char* F = fs + stage_of(kk) * V_ST;
+            if (kk + 1 <= g.nz) u_p = *reinterpret_cast<const float2*>(Up + u_off);
+            if (plane_in) {
+                fA = *reinterpret_cast<const unsigned short*>(F + v_off);
+                bA = *reinterpret_cast<const float2*>(B + v_off);
+                const float2 sS = *reinterpret_cast<const float2*>(Uc + u_off - PW);
+                const float2 nN = *reinterpret_cast<const float2*>(Uc + u_off + PW);
+                const float xw = Uc[u_off - 1], xe = Uc[u_off + 2];
+                oA.x = relax2(fA & 0xffu, u_c.x, xw, u_c.y, sS.x, nN.x, u_m.x, u_p.x, bA.x, w1, cx, cy, cz, dtab2);
+                oA.y = relax2(fA >> 8, u_c.y, u_c.x, xe, sS.y, nN.y, u_m.y, u_p.y, bA.y, w1, cx, cy, cz, dtab2);
+            }
+            *reinterpret_cast<float2*>(V + v_off) = oA;
+            if (rim_kind) {
+                const int vo = rim_vo, uo = rim_vo + PW;       // same cell one row further down in an input stage
+                if (!plane_in) {
+                    V[vo] = 0.f;
+                    if (rim_kind == 1) V[vo + 1] = 0.f;
+                } else {
+                    V[vo] = relax2(F[vo], Uc[uo], Uc[uo - 1], Uc[uo + 1], Uc[uo - PW], Uc[uo + PW], Um[uo], Up[uo],
+                                   B[vo], w1, cx, cy, cz, dtab2);
+                    if (rim_kind == 1)
+                        V[vo + 1] = relax2(F[vo + 1], Uc[uo + 1], Uc[uo], Uc[uo + 2], Uc[uo + 1 - PW], Uc[uo + 1 + PW],
+                                           Um[uo + 1], Up[uo + 1], B[vo + 1], w1, cx, cy, cz, dtab2);
+                }
+            }
+        }
+
+        const int k = kk - 2;
+        if (k >= k0 && k < k1) {
+            const float* Vc = vs + (((k % 3) + 3) % 3) * V_ST;
+            const float2 sS = *reinterpret_cast<const float2*>(Vc + v_off - PW);
+            const float2 nN = *reinterpret_cast<const float2*>(Vc + v_off + PW);
+            const float xw = Vc[v_off - 1], xe = Vc[v_off + 2];
+            float2 o;
+            o.x = relax2(f2 & 0xffu, v2.x, xw, v2.y, sS.x, nN.x, v3.x, v1.x, b2.x, w2, cx, cy, cz, dtab2);
+            o.y = relax2(f2 >> 8, v2.y, v2.x, xe, sS.y, nN.y, v3.y, v1.y, b2.y, w2, cx, cy, cz, dtab2);
+            if (DOT) dot_acc += (double)b2.x * (double)o.x + (double)b2.y * (double)o.y;
+            if (inb && (f2 & 0x4040u)) *reinterpret_cast<float2*>(out_own + (long long)k * g.plane) = o;
+        }
+        u_m = u_c; u_c = u_p;
+        v3 = v2; v2 = v1; v1 = oA;
+        b2 = b1; b1 = bA;
+        f2 = f1; f1 = fA;
+
+        issue(kk + 2 + PP);
+        cpa_commit();
+    }
+    cpa_wait<0>();
+
+    if (DOT) {
+        double v[1] = {dot_acc};
+        grid_reduce<1>(v, red_partials, red_counter, red_out);
+    }
+}
+
 size_t pair_smem_bytes() {
     return sizeof(float) * (size_t)(PR * U_ST + PR * V_ST + 3 * V_ST + 128) + (size_t)PR * V_ST;
 }
@@ -267,25 +420,33 @@ bool pair_supported(const L0Args& a) {
     return sizeof(mg_t) == 4 && (a.g.nx & 3) == 0 && a.g.periodic == 0 && a.g.nz == a.g.nzg;
 }
 
-// out = S_w2(S_w1(u)) ; dot: also red_out = b . out
-void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, cudaStream_t st) {
+// out = S_w2(S_w1(u)) ; dot: also red_out = b . out.  variant 1: 256 threads x 4 cells, 2: 512 x 2.
+void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant, cudaStream_t st) {
     static bool configured = false;
     const size_t smem = pair_smem_bytes();
     if (!configured) {
         cudaFuncSetAttribute(l0_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + PTX - 1) / PTX, (a.g.ny + PTY - 1) / PTY, (a.g.nz + zc - 1) / zc);
-    if (dot)
-        l0_pair_kernel<true><<<grid, 256, smem, st>>>(a.g, a.flags, static_cast<const float*>(a.u),
-            static_cast<const float*>(a.b), static_cast<float*>(a.out), (float)w1, (float)w2, zc, a.red_partials,
-            a.red_counter, a.red_out);
-    else
-        l0_pair_kernel<false><<<grid, 256, smem, st>>>(a.g, a.flags, static_cast<const float*>(a.u),
-            static_cast<const float*>(a.b), static_cast<float*>(a.out), (float)w1, (float)w2, zc, a.red_partials,
-            a.red_counter, a.red_out);
+    const float* u = static_cast<const float*>(a.u);
+    const float* b = static_cast<const float*>(a.b);
+    float* out = static_cast<float*>(a.out);
+    if (variant == 2) {
+        if (dot) l0_pair512_kernel<true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                  a.red_partials, a.red_counter, a.red_out);
+        else l0_pair512_kernel<false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                               a.red_partials, a.red_counter, a.red_out);
+    } else {
+        if (dot) l0_pair_kernel<true><<<grid, 256, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                               a.red_partials, a.red_counter, a.red_out);
+        else l0_pair_kernel<false><<<grid, 256, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                            a.red_partials, a.red_counter, a.red_out);
+    }
 }
 
 }  // namespace oi

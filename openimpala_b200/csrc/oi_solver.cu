@@ -955,11 +955,12 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         oi::l0_jacobi_first(a, S->st); S->launches++;
     }
     // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout).
-    // Opt-in (OI_PAIR=1, read per call so that tests can compare both paths): at 1024^3 the pair
-    // kernel takes 5.7 ms against 4.9 ms for two single sweeps -- it halves the DRAM bytes but runs
-    // latency-bound (16 warps per SM at ~100 registers / 89 KB of shared memory per CTA).
-    const char* pair_env = getenv("OI_PAIR");
-    const bool no_pair = !(pair_env && pair_env[0] == '1');
+    // Opt-in (OI_PAIR, read per call so that tests can compare the paths): at 1024^3 the pair kernel
+    // takes 5.0 ms (512-thread variant) against 4.9 ms for two single sweeps -- it halves the DRAM
+    // bytes but is instruction / latency bound; see the status note in oi_level0_pair.cu.
+    const char* pair_env = getenv("OI_PAIR");                // "1": 256 threads x 4 cells, "2": 512 threads x 2 cells
+    const int pair_variant = (pair_env && (pair_env[0] == '1' || pair_env[0] == '2')) ? pair_env[0] - '0' : 0;
+    const bool no_pair = pair_variant == 0;
     bool use_pair = false;
     {
         L0Args a = l0args(S, cur, rhs, oth, 0.0, nullptr);
@@ -969,7 +970,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         L0Args a = l0args(S, cur, rhs, oth, w[s], dot_out);
         if (use_pair && s + 1 < deg) {
             const bool dot = (!have_coarse && s + 1 == deg - 1 && dot_out);
-            oi::l0_smooth_pair(a, w[s], w[s + 1], dot, S->st); S->launches++;
+            oi::l0_smooth_pair(a, w[s], w[s + 1], dot, pair_variant, S->st); S->launches++;
             s += 2;
         } else {
             halo0(S, cur);
@@ -1017,7 +1018,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             }
             if (use_pair && !addc && s + 1 < deg) {
                 const bool dot = (s + 1 == deg - 1) && dot_out;
-                oi::l0_smooth_pair(a, w[deg - 1 - s], w[deg - 2 - s], dot, S->st); S->launches++;
+                oi::l0_smooth_pair(a, w[deg - 1 - s], w[deg - 2 - s], dot, pair_variant, S->st); S->launches++;
                 s += 2;
             } else {
                 const bool dot = (s == deg - 1) && dot_out;

@@ -342,7 +342,8 @@ def test_streamed_upload_rejects_incomplete_slab(capi):
 @pytest.mark.parametrize("shape,seed,por", [((40, 37, 100), 51, 0.5), ((70, 64, 64), 52, 0.45), ((33, 16, 8), 53, 0.6),
                                             ((20, 130, 132), 54, 0.55)])
 @pytest.mark.parametrize("direction", [0, 2])
-def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, monkeypatch):
+@pytest.mark.parametrize("pair_variant", ["1", "2"])
+def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, pair_variant, monkeypatch):
     """The temporally blocked smoother (two sweeps per pass, oi_level0_pair.cu; opt-in with
     OI_PAIR=1) against the single-sweep ring kernels: same V-cycle output (fp32 rounding only),
     same iteration count, same tau.  Shapes cover partial tiles in x and y and z-chunk boundaries."""
@@ -350,7 +351,7 @@ def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, mo
     rng = np.random.default_rng(seed)
     res = {}
     for no_pair in ("1", "0"):
-        monkeypatch.setenv("OI_PAIR", "0" if no_pair == "1" else "1")
+        monkeypatch.setenv("OI_PAIR", "0" if no_pair == "1" else pair_variant)
         with capi.Solver(shape, direction, 1, -1.0, 1.0) as s:
             s.set_phase(ph)
             if s.build_mask() == 0:
