@@ -20,14 +20,14 @@
 // Restrictions (the caller falls back to two single sweeps otherwise): one z-slab and a
 // non-periodic box (ghost planes are one deep), nx % 4 == 0, fp32 multigrid vectors.
 //
-// STATUS (round 1): correct (tests/test_gpu_parity.py::test_pair_kernel_matches_single_sweeps) but
-// not yet faster than two single sweeps (2 x 2.43 ms at 1024^3):
+// STATUS (round 1), time per pair at 1024^3 against 2 x 2.43 ms for two single sweeps:
 //   v1  256 threads, two barriers per plane, every operand from shared memory      6.3 ms
 //   v2  256 threads, one barrier per plane, own columns in registers (OI_PAIR=1)   5.7 ms
-//   v3  512 threads x 2 cells, 32 warps per SM (OI_PAIR=2)                          5.0 ms
-// It halves the DRAM bytes but is instruction / latency bound: two stencil evaluations plus the
-// rim (16 %) per cell per pass.  Opt-in; next steps: packed fp32 arithmetic (fma.rn.f32x2 on
-// sm_100), rim work spread over all warps, a shallower rhs / flag ring.
+//   v3  512 threads x 2 cells, 32 warps per SM                                      5.0 ms
+//   v4  v3 + packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2)  (default, OI_PAIR=2)  4.45 ms
+// The kernel halves the DRAM bytes but is instruction bound (two stencil evaluations plus the
+// 16 % rim per cell per pass), hence the packed arithmetic.  Next steps: rim work spread over
+// all warps, packed arithmetic for the rim, a shallower rhs / flag ring.
 #include "oi_kernels.h"
 
 namespace oi {
@@ -271,6 +271,49 @@ __device__ __forceinline__ float relax2(unsigned int f, float c, float w_, float
     return (f & F_UNK) ? c + w * (bb - au) * dd.y : 0.f;
 }
 
+// Packed fp32 arithmetic (sm_100: one FFMA2 / FADD2 / FMUL2 per two lanes): the two cells of a
+// thread's pair go through the stencil update together.
+__device__ __forceinline__ unsigned long long pk(float2 v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 upk(unsigned long long r) {
+    float2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
+    return upk(r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return upk(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return upk(r);
+}
+// weighted-Jacobi update of a pair of x-adjacent cells; nc* = (-c, -c) coefficient pairs
+__device__ __forceinline__ float2 relax_pair(unsigned int f0, unsigned int f1, float2 c, float xw, float xe, float2 s_,
+                                             float2 n_, float2 d_, float2 u_, float2 bb, float w, float2 ncx,
+                                             float2 ncy, float2 ncz, const float2* dtab2) {
+    const float2 dd0 = dtab2[f0 & 63u], dd1 = dtab2[f1 & 63u];
+    float2 t = mul2(ncz, add2(d_, u_));
+    t = fma2(ncy, add2(s_, n_), t);
+    t = fma2(ncx, add2(make_float2(xw, c.x), make_float2(c.y, xe)), t);       // -(off-diagonal part)
+    const float2 au = fma2(make_float2(dd0.x, dd1.x), c, t);
+    const float2 res = fma2(au, make_float2(-1.f, -1.f), bb);
+    float2 o = fma2(res, make_float2(w * dd0.y, w * dd1.y), c);
+    o.x = (f0 & F_UNK) ? o.x : 0.f;
+    o.y = (f1 & F_UNK) ? o.y : 0.f;
+    return o;
+}
+
 template <bool DOT>
 __global__ void __launch_bounds__(512, 2)
 l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restrict__ u,
@@ -288,6 +331,7 @@ l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __rest
     const int i0 = blockIdx.x * PTX, j0 = blockIdx.y * PTY;
     const int k0 = blockIdx.z * zchunk, k1 = min(k0 + zchunk, g.nz);
     const float cx = (float)g.cx, cy = (float)g.cy, cz = (float)g.cz;
+    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
     if (tid < 64) {
         const float d = row_diag<float>((unsigned int)tid, g);
         dtab2[tid] = make_float2(d, d > 0.f ? 1.f / d : 0.f);
@@ -363,8 +407,7 @@ l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __rest
                 const float2 sS = *reinterpret_cast<const float2*>(Uc + u_off - PW);
                 const float2 nN = *reinterpret_cast<const float2*>(Uc + u_off + PW);
                 const float xw = Uc[u_off - 1], xe = Uc[u_off + 2];
-                oA.x = relax2(fA & 0xffu, u_c.x, xw, u_c.y, sS.x, nN.x, u_m.x, u_p.x, bA.x, w1, cx, cy, cz, dtab2);
-                oA.y = relax2(fA >> 8, u_c.y, u_c.x, xe, sS.y, nN.y, u_m.y, u_p.y, bA.y, w1, cx, cy, cz, dtab2);
+                oA = relax_pair(fA & 0xffu, fA >> 8, u_c, xw, xe, sS, nN, u_m, u_p, bA, w1, ncx, ncy, ncz, dtab2);
             }
             *reinterpret_cast<float2*>(V + v_off) = oA;
             if (rim_kind) {
@@ -388,9 +431,7 @@ l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __rest
             const float2 sS = *reinterpret_cast<const float2*>(Vc + v_off - PW);
             const float2 nN = *reinterpret_cast<const float2*>(Vc + v_off + PW);
             const float xw = Vc[v_off - 1], xe = Vc[v_off + 2];
-            float2 o;
-            o.x = relax2(f2 & 0xffu, v2.x, xw, v2.y, sS.x, nN.x, v3.x, v1.x, b2.x, w2, cx, cy, cz, dtab2);
-            o.y = relax2(f2 >> 8, v2.y, v2.x, xe, sS.y, nN.y, v3.y, v1.y, b2.y, w2, cx, cy, cz, dtab2);
+            const float2 o = relax_pair(f2 & 0xffu, f2 >> 8, v2, xw, xe, sS, nN, v3, v1, b2, w2, ncx, ncy, ncz, dtab2);
             if (DOT) dot_acc += (double)b2.x * (double)o.x + (double)b2.y * (double)o.y;
             if (inb && (f2 & 0x4040u)) *reinterpret_cast<float2*>(out_own + (long long)k * g.plane) = o;
         }

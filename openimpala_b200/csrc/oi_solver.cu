@@ -954,12 +954,12 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         L0Args a = l0args(S, nullptr, rhs, cur, w[0], nullptr);
         oi::l0_jacobi_first(a, S->st); S->launches++;
     }
-    // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout).
-    // Opt-in (OI_PAIR, read per call so that tests can compare the paths): at 1024^3 the pair kernel
-    // takes 5.0 ms (512-thread variant) against 4.9 ms for two single sweeps -- it halves the DRAM
-    // bytes but is instruction / latency bound; see the status note in oi_level0_pair.cu.
-    const char* pair_env = getenv("OI_PAIR");                // "1": 256 threads x 4 cells, "2": 512 threads x 2 cells
-    const int pair_variant = (pair_env && (pair_env[0] == '1' || pair_env[0] == '2')) ? pair_env[0] - '0' : 0;
+    // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout): the
+    // 512-thread variant with packed fp32 arithmetic takes 4.45 ms at 1024^3 against 4.86 ms for two
+    // single sweeps.  OI_PAIR=0 turns it off, OI_PAIR=1 selects the 256-thread variant (read per
+    // call so that tests can compare the paths).
+    const char* pair_env = getenv("OI_PAIR");
+    const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '2') ? pair_env[0] - '0' : 2;
     const bool no_pair = pair_variant == 0;
     bool use_pair = false;
     {

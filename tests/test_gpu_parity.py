@@ -344,8 +344,8 @@ def test_streamed_upload_rejects_incomplete_slab(capi):
 @pytest.mark.parametrize("direction", [0, 2])
 @pytest.mark.parametrize("pair_variant", ["1", "2"])
 def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, pair_variant, monkeypatch):
-    """The temporally blocked smoother (two sweeps per pass, oi_level0_pair.cu; opt-in with
-    OI_PAIR=1) against the single-sweep ring kernels: same V-cycle output (fp32 rounding only),
+    """The temporally blocked smoother (two sweeps per pass, oi_level0_pair.cu; OI_PAIR selects
+    the variant, 0 = off) against the single-sweep ring kernels: same V-cycle output (fp32 rounding only),
     same iteration count, same tau.  Shapes cover partial tiles in x and y and z-chunk boundaries."""
     ph = _blobs(shape, seed, por)
     rng = np.random.default_rng(seed)
