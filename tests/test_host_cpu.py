@@ -189,3 +189,18 @@ def test_argument_validation_needs_no_gpu(built_lib):
     pc, tc = C.c_int64(0), C.c_int64(0)
     assert lib.oi_count_phase_u8(None, 5, 1, C.byref(pc), C.byref(tc)) == -1
     assert lib.oi_count_phase_u8(None, -1, 1, C.byref(pc), C.byref(tc)) == -1
+
+
+def test_sass_uses_blackwell_packed_fp32_and_async_copies(built_lib):
+    """The level-0 kernels stage planes with cp.async (LDGSTS) and the two-sweeps-per-pass smoother
+    does its stencil arithmetic with packed fp32 instructions (FFMA2 / FADD2 / FMUL2: sm_100 only)."""
+    import shutil
+    import subprocess
+    from openimpala_b200 import capi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("LDGSTS") > 50
+    assert sass.count("FFMA2") >= 10 and sass.count("FADD2") >= 6 and sass.count("FMUL2") >= 2
+    assert "HMMA" not in sass and "UTCHMMA" not in sass          # no tensor-core detour: the path is HBM-bound
