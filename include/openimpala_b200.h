@@ -214,6 +214,13 @@ int oi_sparsity(oi_solver* h, int64_t* stats3);
 /* Which halo path the handle uses (oi_halo_mode; AUTO for a single slab) and how
  * many ghost-plane exchanges went through peer memory so far. */
 int oi_halo_info(oi_solver* h, int32_t* mode, int64_t* peer_exchanges);
+/* Iterations replayed as a CUDA graph.  On a single slab of at most 2^25 cells (the
+ * launch-bound regime; OI_GRAPH=1 lifts the limit, OI_GRAPH=0 disables) every PCG
+ * iteration after the first is one graph launch: replays = how many so far on this
+ * handle, kernels_per_iteration = kernel nodes in one captured iteration (0 before the
+ * first capture).  Replaces nothing in the reference: HYPRE's Krylov loop
+ * (src/props/TortuosityHypre.cpp:683) is host driven. */
+int oi_graph_info(oi_solver* h, int64_t* replays, int64_t* kernels_per_iteration);
 /* Number of kernels this handle has launched since creation. */
 int oi_launch_count(oi_solver* h, int64_t* launches);
 

@@ -93,6 +93,7 @@ _SIGS = {
     "oi_release_cached_memory": (C.c_int, [C.POINTER(C.c_int64)]),
     "oi_sparsity": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "oi_halo_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "oi_graph_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -378,6 +379,12 @@ class Solver:
         m, n = C.c_int32(0), C.c_int64(0)
         _check(self._lib.oi_halo_info(self._h, C.byref(m), C.byref(n)))
         return m.value, n.value
+
+    def graph_info(self):
+        """(iterations replayed as a CUDA graph so far, kernel nodes per captured iteration)."""
+        r, k = C.c_int64(0), C.c_int64(0)
+        _check(self._lib.oi_graph_info(self._h, C.byref(r), C.byref(k)))
+        return r.value, k.value
 
     def launch_count(self) -> int:
         n = C.c_int64(0)

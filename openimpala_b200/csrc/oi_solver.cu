@@ -390,6 +390,13 @@ struct oi_solver {
     std::vector<HostLevel> levels;     // levels[0] is MG level 1
     std::vector<double> w_smooth, w_coarse;
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
+    // One PCG iteration captured as a CUDA graph (single slab): [0] with r.z in scalar slot 0,
+    // [1] with r.z in slot 3 (the two slots swap every iteration).  `launches` = kernel nodes.
+    struct IterGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    IterGraph iter_graph[2];
+    int graph_pair_sig = -1;           // OI_PAIR value baked into the captured graphs
+    bool graph_broken = false;         // a capture failed on this handle: stay on the stream path
+    long long graph_replays = 0;
     // results
     oi_solve_info info{};
     long long launches = 0;
@@ -1075,6 +1082,97 @@ double true_residual(oi_solver* S) {
     return read_scalar(S, d);
 }
 
+// ------------------------------------------------------------------ one PCG iteration
+// First half: q = A p, p.q, r -= alpha q (MG: also r32 and the first smoothing sweep), r.r.
+void iteration_front(oi_solver* S, double* d_rz, double* d_pq, double* d_rr, bool fuse_first) {
+    const long long n = S->n_local;
+    prof_mark(S, "apply q=Ap (+halo)");
+    halo0(S, S->p.p);
+    L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, d_pq);
+    oi::l0_apply(a, true, S->prm.stencil_variant, S->st); S->launches++;       // q = A p, pq = p.q
+    prof_mark(S, "allreduce p.q");
+    allreduce_sum_f64(S, d_pq, 1);
+    prof_mark(S, "axpy2+dot+first sweep");
+    // MG path: x += alpha p is deferred to the xpby of the second half (which reads p anyway);
+    // if the loop ends between the halves instead, vec_axpy applies it
+    if (fuse_first)
+        oi::vec_axpy2_dot_first(S->g, S->flags.p, n, nullptr, S->r.p, S->p.p, S->q.p, S->r32.p,
+                                S->za.p, d_rz, d_pq, first_smoothing_weight(S), S->d_partials,
+                                S->d_counter, d_rr, S->n_sm, S->st);
+    else
+        oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
+                          S->d_counter, d_rr, S->n_sm, S->st);
+    S->launches++;
+    prof_mark(S, "allreduce r.r + readback");
+    allreduce_sum_f64(S, d_rr, 1);
+}
+
+// Second half: z = M^-1 r with r.z -> d_rzn, then x += alpha p (MG path), p = z + beta p.
+void iteration_back(oi_solver* S, double* d_rz, double* d_rzn, double* d_pq, bool fuse_first) {
+    apply_precond(S, d_rzn, fuse_first);
+    prof_mark(S, "xpby");
+    oi::vec_xpby(S->n_local, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, fuse_first ? S->x.p : nullptr, d_rz, d_pq,
+                 S->n_sm, S->st);
+    S->launches++;
+}
+
+// ------------------------------------------------------------------ iteration graphs
+// Small boxes are launch bound (the sample image: ~65 launches of a few microseconds per
+// iteration), so a whole iteration -- both halves and the read-back of r.r between them --
+// is captured once per scalar-slot parity and replayed.  The host still tests r.r after
+// every iteration; when the test ends the loop the second half has already run, which
+// leaves x exactly where the stream path's closing vec_axpy would (x += alpha p rides in
+// xpby) and a search direction nobody uses.  Single slab only: the peer halo's stream
+// waits and the NCCL calls of a multi-rank iteration stay on the stream path.
+// OI_GRAPH=0 forces the stream path, OI_GRAPH=1 graphs for every size.
+void drop_iter_graphs(oi_solver* S) {
+    for (auto& g : S->iter_graph) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+        g.launches = 0;
+    }
+}
+
+bool iter_graph_wanted(const oi_solver* S) {
+    if (S->n_ranks != 1 || S->prof_on || S->graph_broken) return false;
+    const char* e = getenv("OI_GRAPH");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return S->n_local <= (1LL << 25);          // up to ~320^3: above that the launches hide behind the kernels
+}
+
+bool capture_iteration(oi_solver* S, int key, double* d_rz, double* d_rzn, double* d_pq, double* d_rr,
+                       bool fuse_first) {
+    const long long launches_before = S->launches;
+    if (cudaStreamBeginCapture(S->st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    bool ok = true;
+    try {
+        iteration_front(S, d_rz, d_pq, d_rr, fuse_first);
+        CUDA_CHECK(cudaMemcpyAsync(S->h_pinned, d_rr, sizeof(double), cudaMemcpyDeviceToHost, S->st));
+        iteration_back(S, d_rz, d_rzn, d_pq, fuse_first);
+    } catch (...) {
+        ok = false;                    // nothing has executed: the caller repeats the iteration on the stream
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamEndCapture(S->st, &graph) != cudaSuccess || !graph) ok = false;
+    const long long nodes = S->launches - launches_before;
+    S->launches = launches_before;
+    cudaGraphExec_t exec = nullptr;
+    if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        if (exec) cudaGraphExecDestroy(exec);
+        return false;
+    }
+    S->iter_graph[key].exec = exec;
+    S->iter_graph[key].launches = nodes;
+    return true;
+}
+
 void run_solve(oi_solver* S) {
     OI_REQUIRE(S->mask_built, "oi_solve: call oi_build_mask first");
     oi_solve_info& info = S->info;
@@ -1101,8 +1199,14 @@ void run_solve(oi_solver* S) {
     CUDA_CHECK(cudaEventRecord(e1, S->st));
 
     const long long n = S->n_local;
-    const int variant = S->prm.stencil_variant;
     double* sc = S->d_scal;   // [0]=rz [1]=pq [2]=rr [3]=rz_new
+    const bool use_graph = iter_graph_wanted(S);
+    {   // OI_PAIR is read per call and baked into a captured iteration
+        const char* pe = getenv("OI_PAIR");
+        const int sig = (pe && pe[0] >= '0' && pe[0] <= '2') ? pe[0] - '0' : 2;
+        if (sig != S->graph_pair_sig) drop_iter_graphs(S);
+        S->graph_pair_sig = sig;
+    }
     double* d_rz = sc + 0; double* d_pq = sc + 1; double* d_rr = sc + 2; double* d_rzn = sc + 3;
 
     prof_mark(S, "setup/restart/checks");
@@ -1121,28 +1225,32 @@ void run_solve(oi_solver* S) {
             // (re)start: z = M r, p = z
             apply_precond(S, d_rz);
             oi::vec_from_mg(n, S->p.p, S->zres, S->n_sm, S->st); S->launches++;
+            const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
             while (it < S->prm.maxiter) {
                 ++it;
-                prof_mark(S, "apply q=Ap (+halo)");
-                halo0(S, S->p.p);
-                L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, d_pq);
-                oi::l0_apply(a, true, variant, S->st); S->launches++;       // q = A p, pq = p.q
-                prof_mark(S, "allreduce p.q");
-                allreduce_sum_f64(S, d_pq, 1);
-                prof_mark(S, "axpy2+dot+first sweep");
-                const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
-                // MG path: x += alpha p is deferred to the xpby below (which reads p anyway);
-                // if the loop ends here instead, vec_axpy applies it
-                if (fuse_first)
-                    oi::vec_axpy2_dot_first(S->g, S->flags.p, n, nullptr, S->r.p, S->p.p, S->q.p, S->r32.p,
-                                            S->za.p, d_rz, d_pq, first_smoothing_weight(S), S->d_partials,
-                                            S->d_counter, d_rr, S->n_sm, S->st);
-                else
-                    oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
-                                      S->d_counter, d_rr, S->n_sm, S->st);
-                S->launches++;
-                prof_mark(S, "allreduce r.r + readback");
-                allreduce_sum_f64(S, d_rr, 1);
+                // the first iteration of a solve always runs on the stream (it also performs
+                // every kernel's one-time configuration); later ones replay a graph
+                if (use_graph && it >= 2 && !S->graph_broken) {
+                    const int key = (d_rz == sc + 0) ? 0 : 1;
+                    if (!S->iter_graph[key].exec &&
+                        !capture_iteration(S, key, d_rz, d_rzn, d_pq, d_rr, fuse_first))
+                        S->graph_broken = true;
+                    if (S->iter_graph[key].exec) {
+                        CUDA_CHECK(cudaGraphLaunch(S->iter_graph[key].exec, S->st));
+                        CUDA_CHECK(cudaStreamSynchronize(S->st));
+                        S->launches += S->iter_graph[key].launches;
+                        S->graph_replays++;
+                        rr = S->h_pinned[0];
+                        if (!std::isfinite(rr)) { fail = true; break; }
+                        if (std::sqrt(rr) <= tol || it >= S->prm.maxiter) {
+                            converged = std::sqrt(rr) <= tol;      // x += alpha p already applied by the graph's xpby
+                            break;
+                        }
+                        std::swap(d_rz, d_rzn);
+                        continue;
+                    }
+                }
+                iteration_front(S, d_rz, d_pq, d_rr, fuse_first);
                 rr = read_scalar(S, d_rr);
                 if (!std::isfinite(rr)) { fail = true; break; }
                 if (std::sqrt(rr) <= tol || it >= S->prm.maxiter) {
@@ -1150,11 +1258,7 @@ void run_solve(oi_solver* S) {
                     converged = std::sqrt(rr) <= tol;
                     break;
                 }
-                apply_precond(S, d_rzn, fuse_first);
-                prof_mark(S, "xpby");
-                oi::vec_xpby(n, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, fuse_first ? S->x.p : nullptr, d_rz, d_pq,
-                             S->n_sm, S->st);
-                S->launches++;
+                iteration_back(S, d_rz, d_rzn, d_pq, fuse_first);
                 std::swap(d_rz, d_rzn);
             }
             if (fail || !converged) break;
@@ -1252,6 +1356,7 @@ void build_mask(oi_solver* S) {
     const int dir = S->prm.direction;
     S->hierarchy_built = false;
     S->solved = false;
+    drop_iter_graphs(S);
     // Krylov vectors are allocated once per handle; while the mask is being built
     // they are dead, so the labelling scratch aliases them (no cudaMalloc/cudaFree
     // in the steady-state step): labels -> p, reach bytes -> q, plane bits -> z.
@@ -1379,6 +1484,7 @@ void require_gpu(int* count_out = nullptr) {
 
 // Everything a handle owns goes back to the caches (also used when oi_create fails half way).
 void release_resources(oi_solver* S) {
+    drop_iter_graphs(S);
     free_levels(S);
     free_vectors(S);
     S->active.release(); S->flags.release();
@@ -2116,6 +2222,15 @@ int oi_halo_info(oi_solver* S, int32_t* mode, int64_t* peer_exchanges) {
         OI_REQUIRE(S, "null handle");
         if (mode) *mode = S->n_ranks <= 1 ? OI_HALO_AUTO : (S->peer.on ? OI_HALO_PEER : OI_HALO_NCCL);
         if (peer_exchanges) *peer_exchanges = S->peer.exchanges;
+    });
+}
+
+int oi_graph_info(oi_solver* S, int64_t* replays, int64_t* kernels_per_iteration) {
+    return guarded([&] {
+        OI_REQUIRE(S, "null handle");
+        if (replays) *replays = S->graph_replays;
+        if (kernels_per_iteration)
+            *kernels_per_iteration = std::max(S->iter_graph[0].launches, S->iter_graph[1].launches);
     });
 }
 

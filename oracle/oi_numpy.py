@@ -428,6 +428,99 @@ def solve_full(phase, phase_id, direction, vlo, vhi, eps=1e-12, dx=(1.0, 1.0, 1.
     return x.reshape(phase.shape), mask, dict(iters=iters, relres=relres, bnorm=bnorm)
 
 
+def flexgmres(A, b, x0, precond, tol=1e-9, maxiter=200, k_dim=20, a_tol=0.0):
+    """Restatement of HYPRE's FlexGMRES (hypre v2.32.0 krylov/flexgmres.c, the
+    published right-preconditioned flexible GMRES(k) of Saad 1993) as the
+    reference drives it (TortuosityHypre.cpp:666-688): tolerance ``tol``
+    relative to ||b||_2 of the FULL rhs (||r0|| when b = 0), ``maxiter``
+    Krylov steps in total, restart length k_dim = 20 (the reference never calls
+    SetKDim, so HYPRE's default holds), modified Gram-Schmidt, Givens
+    rotations, preconditioned directions z_j kept so x += sum y_j z_j, and the
+    recurrence residual confirmed by a true residual b - A x before the solver
+    reports convergence.  ``precond(v)`` applies M^-1 (HYPRE: one SMG V-cycle;
+    any fixed or varying M is legal here).
+    Returns (x, iterations, final_relative_residual, converged)."""
+    x = np.array(x0, dtype=np.float64, copy=True)
+    b_norm = float(np.sqrt(b @ b))
+    r = b - A @ x
+    r_norm = float(np.sqrt(r @ r))
+    den = b_norm if b_norm > 0.0 else r_norm
+    epsilon = max(a_tol, tol * den)
+    it = 0
+    converged = r_norm <= epsilon
+    n = b.shape[0]
+    while it < maxiter and not converged and r_norm > 0.0:
+        P = np.empty((k_dim + 1, n))
+        Z = np.empty((k_dim, n))
+        hh = np.zeros((k_dim + 1, k_dim))
+        c = np.zeros(k_dim)
+        s = np.zeros(k_dim)
+        rs = np.zeros(k_dim + 1)
+        rs[0] = r_norm
+        P[0] = r / r_norm
+        i = 0
+        while i < k_dim and it < maxiter:
+            i += 1
+            it += 1
+            Z[i - 1] = precond(P[i - 1])
+            w = A @ Z[i - 1]
+            for j in range(i):                      # modified Gram-Schmidt
+                hh[j, i - 1] = P[j] @ w
+                w -= hh[j, i - 1] * P[j]
+            t = float(np.sqrt(w @ w))
+            hh[i, i - 1] = t
+            if t != 0.0:
+                w /= t
+            P[i] = w
+            for j in range(1, i):                   # earlier rotations on the new column
+                t = hh[j - 1, i - 1]
+                hh[j - 1, i - 1] = s[j - 1] * hh[j, i - 1] + c[j - 1] * t
+                hh[j, i - 1] = -s[j - 1] * t + c[j - 1] * hh[j, i - 1]
+            gamma = float(np.hypot(hh[i, i - 1], hh[i - 1, i - 1]))
+            if gamma == 0.0:
+                gamma = 1e-16
+            c[i - 1] = hh[i - 1, i - 1] / gamma
+            s[i - 1] = hh[i, i - 1] / gamma
+            rs[i] = -s[i - 1] * rs[i - 1]
+            rs[i - 1] = c[i - 1] * rs[i - 1]
+            hh[i - 1, i - 1] = s[i - 1] * hh[i, i - 1] + c[i - 1] * hh[i - 1, i - 1]
+            r_norm = abs(rs[i])
+            if r_norm <= epsilon:
+                break
+        y = rs[:i].copy()                           # back substitution
+        for k in range(i - 1, -1, -1):
+            y[k] -= hh[k, k + 1:i] @ y[k + 1:i]
+            y[k] /= hh[k, k]
+        x += y @ Z[:i]
+        r = b - A @ x                               # true residual at every restart
+        r_norm = float(np.sqrt(r @ r))
+        converged = r_norm <= epsilon
+    relres = r_norm / den if den > 0.0 else 0.0
+    return x, it, relres, bool(converged)
+
+
+def solve_full_flexgmres(phase, phase_id, direction, vlo, vhi, eps=1e-9, dx=(1.0, 1.0, 1.0),
+                         maxiter=200, mask=None, k_dim=20, drop_tol=1e-5, fill_factor=20.0):
+    """The reference's OWN formulation of a-7: the assembled NON-symmetric
+    system with its identity rows kept (no Dirichlet elimination), initial
+    guess = the ramp of tortuosity_fillmtx, FlexGMRES(20) with the reference's
+    tolerance / iteration cap (TortuosityHypre.cpp:142-143, 666-688) and
+    m_converged = finite and relres <= eps (:687-688).  HYPRE's SMG V-cycle
+    cannot be restated from this tree (un-vendored dependency); an incomplete
+    LU of the same matrix stands in as the right preconditioner -- FlexGMRES
+    accepts any M, and the converged x does not depend on it."""
+    import scipy.sparse.linalg as spla
+    if mask is None:
+        mask = activity_mask(phase, phase_id, direction)
+    a, rhs, x0 = fill_matrix(phase, mask, phase_id, direction, vlo, vhi, dx)
+    A = assemble_csr(a, phase.shape)
+    ilu = spla.spilu(A.tocsc(), drop_tol=drop_tol, fill_factor=fill_factor)
+    x, iters, relres, conv = flexgmres(A, rhs, x0, ilu.solve, tol=eps, maxiter=maxiter, k_dim=k_dim)
+    conv = bool(conv and np.isfinite(relres) and 0.0 <= relres <= eps)
+    return x.reshape(phase.shape), mask, dict(iters=iters, relres=relres, converged=conv,
+                                              bnorm=reference_stop_norm(rhs))
+
+
 # --------------------------------------------------------------------------
 # a-8 / a-9  global_fluxes + value  (TortuosityHypre.cpp:1000-1134, 761-891)
 # --------------------------------------------------------------------------
@@ -488,14 +581,21 @@ def tau_from_fluxes(fin, fout, active_vf, shape, direction, vlo, vhi, dx=(1.0, 1
 
 
 def tortuosity(phase, phase_id, direction, vlo=-1.0, vhi=1.0, eps=1e-12,
-               dx=(1.0, 1.0, 1.0)) -> TauResult:
-    """End-to-end oracle: mask -> solve -> flux -> tau."""
+               dx=(1.0, 1.0, 1.0), method="pcg", maxiter=None) -> TauResult:
+    """End-to-end oracle: mask -> solve -> flux -> tau.  method "pcg": the
+    eliminated SPD system by Jacobi-PCG; "flexgmres": the reference's own
+    non-symmetric system by FlexGMRES(20) (solve_full_flexgmres)."""
     mask = activity_mask(phase, phase_id, direction)
     n_active = int(mask.sum())
     active_vf = n_active / phase.size if phase.size else 0.0
     if active_vf <= np.finfo(np.float64).eps:
         return TauResult(float("nan"), 0.0, active_vf, 0.0, 0.0, n_active, False, 0, float("nan"))
-    x, mask, info = solve_full(phase, phase_id, direction, vlo, vhi, eps, dx, mask=mask)
+    if method == "flexgmres":
+        x, mask, info = solve_full_flexgmres(phase, phase_id, direction, vlo, vhi, eps, dx,
+                                             maxiter=200 if maxiter is None else maxiter, mask=mask)
+    else:
+        x, mask, info = solve_full(phase, phase_id, direction, vlo, vhi, eps, dx, mask=mask,
+                                   **({} if maxiter is None else {"maxiter": maxiter}))
     fin, fout, _, _ = global_fluxes(x, mask, direction, dx)
     conv = np.isfinite(info["relres"]) and info["relres"] <= eps
     tau, deff = tau_from_fluxes(fin, fout, active_vf, phase.shape, direction, vlo, vhi, dx, conv)

@@ -211,6 +211,10 @@ def test_sample_image_golden(capi, sample_phase):
     import hashlib
     from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
     gold = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    # the same image under the reference's own formulation and solver settings (FlexGMRES(20)
+    # on the un-eliminated system, eps 1e-9, maxiter 200): make_flexgmres_golden.py
+    fgm = {(c["phase"], c["direction"]): c
+           for c in json.load(open(os.path.join(GOLDEN, "sample_flexgmres_golden.json")))["cases"]}
     for case in gold["cases"]:
         t = TortuosityHypre(None, None, None, sample_phase, 0.4, case["phase"], Direction(case["direction"]),
                             SolverType.FlexGMRES, "", gold["vlo"], gold["vhi"])
@@ -220,6 +224,8 @@ def test_sample_image_golden(capi, sample_phase):
         tau = t.value()                        # default eps 1e-9, maxiter 200
         assert t.getSolverConverged() and t.getSolverIterations() <= 200
         assert abs(tau - case["tau"]) <= TAU_RTOL * case["tau"], (case, tau)
+        fg = fgm.get((case["phase"], case["direction"]))        # phase 1 only
+        assert fg is None or abs(tau - fg["tau"]) <= TAU_RTOL * fg["tau"], (fg, tau)
         fi, fo, ni, no = t.solver.fluxes()
         assert (ni, no) == (case["n_in"], case["n_out"])
         t.close()
@@ -368,3 +374,74 @@ def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, pa
     assert float(np.abs(z0 - z1).max()) <= 2e-5 * scale          # fp32 V-cycle, different summation order only
     assert abs(it0 - it1) <= 1
     assert abs(fl0[0] - fl1[0]) <= 1e-7 * abs(fl1[0]) and abs(fl0[1] - fl1[1]) <= 1e-7 * abs(fl1[1])
+
+
+# ------------------------------------------------------------------ iterations replayed as CUDA graphs
+@pytest.mark.parametrize("case", ["sample_x", "blobs_z", "blobs_jacobi", "odd_nx"])
+def test_iteration_graph_matches_stream_path(capi, sample_phase, case, monkeypatch):
+    """Small boxes are launch bound, so every PCG iteration after the first is one graph launch
+    (oi_graph_info; OI_GRAPH=0 keeps the stream path).  Same iteration count, same residual
+    history end point, same solution and fluxes; the graphs survive a second solve on the handle
+    and are re-captured after the mask is rebuilt."""
+    if case == "sample_x":
+        ph, direction, kw = sample_phase, 0, {}
+    elif case == "blobs_z":
+        ph, direction, kw = _blobs((48, 40, 64), 61, 0.55), 2, {}
+    elif case == "blobs_jacobi":
+        ph, direction, kw = _blobs((24, 20, 28), 62, 0.6), 1, {"precond": 1, "maxiter": 5000}
+    else:
+        ph, direction, kw = _blobs((30, 26, 37), 63, 0.6), 0, {}      # nx % 4 != 0: z-march kernels
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OI_GRAPH", mode)
+        with capi.Solver(ph.shape, direction, 1, -1.0, 1.0, **kw) as s:
+            s.set_phase(ph)
+            if s.build_mask() == 0:
+                pytest.skip("nothing percolates")
+            x_start = s.solution()
+            info = s.solve()
+            replays, nodes = s.graph_info()
+            first = (info.iterations, info.rel_residual, info.converged, s.solution(), s.fluxes()[:2], replays, nodes)
+            # again from the same start on the same handle: cached graphs, same answer
+            s.set_solution(x_start)
+            info2 = s.solve()
+            assert info2.iterations == info.iterations and info2.converged == info.converged
+            np.testing.assert_allclose(s.solution(), first[3], rtol=0, atol=1e-12)
+            # mask rebuilt: graphs dropped and captured afresh
+            s.build_mask()
+            info3 = s.solve()
+            assert info3.iterations == info.iterations
+            np.testing.assert_allclose(s.solution(), first[3], rtol=0, atol=1e-12)
+            out[mode] = first + (s.graph_info()[0],)
+    it0, rel0, conv0, x0, fl0, rep0, nodes0, rep0_all = out["0"]
+    it1, rel1, conv1, x1, fl1, rep1, nodes1, rep1_all = out["1"]
+    assert conv0 and conv1 and it0 == it1 and it1 >= 3
+    assert rep0 == 0 and nodes0 == 0 and rep0_all == 0                    # OI_GRAPH=0: stream path only
+    assert rep1 == it1 - 1 and nodes1 >= 4 and rep1_all == 3 * (it1 - 1)  # every iteration but the first (Jacobi-PCG: 4 kernels)
+    assert abs(rel0 - rel1) <= 1e-6 * rel0
+    np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-12)
+    assert abs(fl0[0] - fl1[0]) <= 1e-11 * abs(fl0[0]) and abs(fl0[1] - fl1[1]) <= 1e-11 * abs(fl0[1])
+
+
+def test_iteration_graph_default_and_cell_problem(capi, monkeypatch):
+    """Default gating: graphs on for a small single slab, for the periodic cell problem too
+    (its wrapped ghost planes are copy nodes of the graph)."""
+    from openimpala_b200.effdiff import EffectiveDiffusivityHypre
+    monkeypatch.delenv("OI_GRAPH", raising=False)
+    ph = _blobs((32, 28, 24), 64, 0.6)
+    with capi.Solver(ph.shape, 2, 1, -1.0, 1.0) as s:
+        s.set_phase(ph)
+        assert s.build_mask() > 0
+        info = s.solve()
+        assert info.converged and s.graph_info()[0] == info.iterations - 1
+    chi = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OI_GRAPH", mode)
+        with capi.Solver(ph.shape, 0, 1, problem=1, maxiter=1000) as s:
+            s.set_phase(ph)
+            s.build_mask()
+            info = s.solve()
+            assert info.converged
+            chi[mode] = (info.iterations, s.solution(), s.graph_info()[0])
+    assert chi["0"][0] == chi["1"][0] and chi["0"][2] == 0 and chi["1"][2] == chi["1"][0] - 1
+    np.testing.assert_allclose(chi["1"][1], chi["0"][1], rtol=0, atol=1e-12)
