@@ -13,6 +13,7 @@
 // couplings even out.  This replaces HYPRE SMG/PFMG's coarse
 // operator build (reference call site src/props/TortuosityHypre.cpp:671-681).
 #include "oi_kernels.h"
+#include "oi_coarse_tail.cuh"
 
 namespace oi {
 
@@ -252,6 +253,24 @@ coarse_restrict_kernel(CoarseLevel f, const mg_t* __restrict__ res, CoarseLevel 
     }
 }
 
+// ---------------------------------------------------------------- coarse tail
+// (the cycle itself is in oi_coarse_tail.cuh so that tests can run it on the host)
+constexpr int TAIL_NT = 1024;
+
+// one data-parallel step of the CTA: f(idx) for every idx in [0, n), then a barrier
+struct CtaStep {
+    template <class F>
+    __device__ __forceinline__ void operator()(int n, F f) const {
+        for (int idx = threadIdx.x; idx < n; idx += TAIL_NT) f(idx);
+        __syncthreads();
+    }
+};
+
+__global__ void __launch_bounds__(TAIL_NT, 1)
+coarse_tail_kernel(TailArgs a) {
+    tail_cycle(a, CtaStep());
+}
+
 inline int blocks_for(long long n) {
     long long b = (n + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
@@ -308,6 +327,10 @@ void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* o
             reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
     else
         coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
+}
+
+void coarse_tail_cycle(const TailArgs& a, cudaStream_t st) {
+    coarse_tail_kernel<<<1, TAIL_NT, 0, st>>>(a);
 }
 
 void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc, cudaStream_t st) {

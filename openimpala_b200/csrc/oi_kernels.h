@@ -71,6 +71,18 @@ void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, 
 void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc,
                      cudaStream_t st);
 
+// One-CTA V-cycle over the last levels of the hierarchy (each holding the whole box in z):
+// L[0] is the first tail level -- rhs in L[0].b, correction left in L[0].x -- L[n_levels-1]
+// the coarsest level of the hierarchy.  w/deg: smoothing weights of a level with a coarser
+// one below; wc/deg_c: the coarsest level's sweeps.
+constexpr int TAIL_MAX_LEVELS = 6;
+struct TailArgs {
+    int n_levels, deg, deg_c;
+    CoarseLevel L[TAIL_MAX_LEVELS];
+    mg_t w[16], wc[16];
+};
+void coarse_tail_cycle(const TailArgs& a, cudaStream_t st);
+
 // ---------------------------------------------------------------- vector ops (K4)
 // x += a p ; r -= a q ; out[0] = r.r      with a = num[0]/den[0] read on device
 void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,

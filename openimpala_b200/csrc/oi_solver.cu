@@ -390,6 +390,7 @@ struct oi_solver {
     std::vector<HostLevel> levels;     // levels[0] is MG level 1
     std::vector<double> w_smooth, w_coarse;
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
+    int tail_level = -1;               // levels[tail_level ..] are cycled by the one-CTA tail kernel (-1: none)
     // One PCG iteration captured as a CUDA graph (single slab): [0] with r.z in scalar slot 0,
     // [1] with r.z in slot 3 (the two slots swap every iteration).  `launches` = kernel nodes.
     struct IterGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
@@ -405,6 +406,12 @@ struct oi_solver {
 };
 
 namespace {
+
+// the one-CTA coarse tail: on by default on a single slab (OI_TAIL=0 turns it off); a multi-rank run
+// takes it for its replicated levels only when asked (OI_TAIL=1) until that path has run on >= 2 GPUs
+#ifndef OI_TAIL_DEFAULT
+#define OI_TAIL_DEFAULT true
+#endif
 
 using oi::CoarseLevel;
 using oi::Grid;
@@ -678,6 +685,28 @@ void plan_hierarchy(oi_solver* S) {
         }
     }
     S->fx0 = f0.fx; S->fy0 = f0.fy; S->fz0 = f0.fz;
+    // Coarse tail: the first level of at most OI_TAIL_CELLS cells that holds the whole box
+    // in z (single slab, or replicated) and everything below it run as ONE kernel
+    // (oi_coarse.cu: coarse_tail_kernel).  OI_TAIL=0|1.
+    S->tail_level = -1;
+    {
+        const char* e = getenv("OI_TAIL");
+        const bool on = e ? (e[0] == '1') : (OI_TAIL_DEFAULT && S->n_ranks == 1);
+        long long cells = 4096;
+        if (const char* c = getenv("OI_TAIL_CELLS")) cells = std::atoll(c);
+        if (on && cells > 0) {
+            const int nl = (int)lv.size();
+            for (int l = 0; l < nl; ++l) {
+                const HostLevel& h = lv[l];
+                const bool whole = (S->n_ranks == 1) || h.replicated;
+                if (!whole || h.gather_point) continue;
+                if ((long long)h.L.plane * h.L.nz > cells) continue;
+                if (nl - l > oi::TAIL_MAX_LEVELS) continue;
+                S->tail_level = l;
+                break;
+            }
+        }
+    }
     S->levels_planned = true;
 }
 
@@ -895,6 +924,19 @@ void coarse_cycle(oi_solver* S, size_t l) {
         wrap_ghosts_locally(S, w.L.x, plane * sizeof(mg_t), w.L.nz);
         CUDA_CHECK(cudaMemcpyAsync(L.x - plane, w.L.x + plane * (size_t)L.z0 - plane, plane * (size_t)(L.nz + 2) * sizeof(mg_t),
                                    cudaMemcpyDeviceToDevice, S->st));
+        return;
+    }
+    if ((int)l == S->tail_level) {
+        // this level and everything below it in one kernel
+        prof_mark(S, "mg tail");
+        oi::TailArgs ta{};
+        ta.n_levels = (int)(S->levels.size() - l);
+        ta.deg = (int)S->w_smooth.size();
+        ta.deg_c = (int)S->w_coarse.size();
+        for (int q = 0; q < ta.n_levels; ++q) ta.L[q] = S->levels[l + q].L;
+        for (int q = 0; q < ta.deg; ++q) ta.w[q] = (mg_t)S->w_smooth[q];
+        for (int q = 0; q < ta.deg_c; ++q) ta.wc[q] = (mg_t)S->w_coarse[q];
+        oi::coarse_tail_cycle(ta, S->st); S->launches++;
         return;
     }
     const bool last = (l + 1 == S->levels.size());

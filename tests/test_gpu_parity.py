@@ -445,3 +445,48 @@ def test_iteration_graph_default_and_cell_problem(capi, monkeypatch):
             chi[mode] = (info.iterations, s.solution(), s.graph_info()[0])
     assert chi["0"][0] == chi["1"][0] and chi["0"][2] == 0 and chi["1"][2] == chi["1"][0] - 1
     np.testing.assert_allclose(chi["1"][1], chi["0"][1], rtol=0, atol=1e-12)
+
+
+# ------------------------------------------------------------------ one-CTA coarse tail
+@pytest.mark.parametrize("case", ["sample_z", "blobs_x", "whole_hierarchy", "anisotropic", "cell_problem", "odd_nx"])
+def test_coarse_tail_matches_level_kernels(capi, sample_phase, case, monkeypatch):
+    """OI_TAIL=1: every level of at most 4096 cells and everything below it is cycled by ONE
+    kernel (oi_coarse_tail.cuh) instead of ~11 launches per level.  Same V-cycle up to fp32
+    summation order: preconditioner output, iteration count, result."""
+    kw, dx, problem = {}, (1.0, 1.0, 1.0), 0
+    if case == "sample_z":
+        ph, direction = sample_phase, 2                              # tail = 13^3, 7^3, 4^3
+    elif case == "blobs_x":
+        ph, direction = _blobs((48, 40, 64), 71, 0.55), 0            # tail = 12x10x16 and below
+    elif case == "whole_hierarchy":
+        ph, direction = _blobs((24, 20, 28), 72, 0.6), 1             # level 1 already fits: no level kernels at all
+    elif case == "anisotropic":
+        ph, direction, dx = _blobs((40, 36, 32), 73, 0.6), 2, (1.0, 1.0, 4.0)   # semicoarsened levels in the tail
+    elif case == "cell_problem":
+        ph, direction, problem = _blobs((32, 28, 24), 74, 0.6), 0, 1           # periodic: wrapped indices
+        kw = {"maxiter": 1000}
+    else:
+        ph, direction = _blobs((30, 26, 37), 75, 0.6), 0
+    out = {}
+    for tail in ("0", "1"):
+        monkeypatch.setenv("OI_TAIL", tail)
+        with capi.Solver(ph.shape, direction, 1, -1.0, 1.0, dx=dx, problem=problem, **kw) as s:
+            s.set_phase(ph)
+            if s.build_mask() == 0:
+                pytest.skip("nothing percolates")
+            act = s.mask().astype(bool)
+            r = np.where(act, np.random.default_rng(7).standard_normal(ph.shape), 0.0)
+            l0 = s.launch_count()
+            z = s.apply_precond(r)
+            per_cycle = s.launch_count() - l0
+            info = s.solve()
+            assert info.converged
+            out[tail] = (z, per_cycle, info.iterations, s.solution())
+    z0, n0, it0, x0 = out["0"]
+    z1, n1, it1, x1 = out["1"]
+    assert n1 <= n0 - 15                                             # at least two levels' worth of launches gone
+    scale = float(np.abs(z0).max())
+    assert float(np.abs(z1 - z0).max()) <= 2e-5 * scale
+    assert abs(it1 - it0) <= 1
+    # two converged solves (relative residual 1e-9) of the same system, not the same iterates
+    np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-5 * max(1.0, float(np.abs(x0).max())))

@@ -204,3 +204,124 @@ def test_sass_uses_blackwell_packed_fp32_and_async_copies(built_lib):
     assert sass.count("LDGSTS") > 50
     assert sass.count("FFMA2") >= 10 and sass.count("FADD2") >= 6 and sass.count("FMUL2") >= 2
     assert "HMMA" not in sass and "UTCHMMA" not in sass          # no tensor-core detour: the path is HBM-bound
+
+
+# ------------------------------------------------------------------ coarse tail on the host
+def _tail_levels(rng, dims0, factors, periodic, alive_frac=0.8):
+    """Random 7-point hierarchy: per level couplings to +x/+y/+z between live cells,
+    diagonal = adjacent couplings + a sink, 0 on dead cells."""
+    levels = []
+    nx, ny, nz = dims0
+    for (fx, fy, fz) in factors + [(1, 1, 1)]:
+        alive = rng.random((nz, ny, nx)) < alive_frac
+        c = []
+        for axis in (2, 1, 0):
+            nb = np.roll(alive, -1, axis)
+            cc = np.where(alive & nb, 0.25 + rng.random((nz, ny, nx)), 0.0)
+            if not periodic:
+                idx = [slice(None)] * 3
+                idx[axis] = -1
+                cc[tuple(idx)] = 0.0
+            c.append(cc.astype(np.float32))
+        cxp, cyp, czp = c
+        dg = np.zeros((nz, ny, nx))
+        for axis, cc in ((2, cxp), (1, cyp), (0, czp)):
+            dg += cc + np.roll(cc, 1, axis)
+        dg = np.where(alive, dg + 0.05 + 0.3 * rng.random((nz, ny, nx)), 0.0).astype(np.float32)
+        levels.append(dict(nx=nx, ny=ny, nz=nz, fx=fx, fy=fy, fz=fz, cxp=cxp, cyp=cyp, czp=czp, dg=dg))
+        nx, ny, nz = -(-nx // fx), -(-ny // fy), -(-nz // fz)
+    return levels
+
+
+def _tail_reference_cycle(levels, l, b, w, wc):
+    """The V-cycle of coarse_cycle() (oi_solver.cu) from its definition, in float64."""
+    L = levels[l]
+    dg = L["dg"].astype(np.float64)
+    live = dg > 0
+
+    def A(x):
+        acc = dg * x
+        for axis, key in ((2, "cxp"), (1, "cyp"), (0, "czp")):
+            cp = L[key].astype(np.float64)
+            acc = acc - cp * np.roll(x, -1, axis) - np.roll(cp, 1, axis) * np.roll(x, 1, axis)
+        return acc
+
+    def smooth(x, wt):
+        return np.where(live, x + wt * (b - A(x)) / np.where(live, dg, 1.0), 0.0)
+
+    last = (l + 1 == len(levels))
+    ws = wc if last else w
+    x = np.where(live, ws[0] * b / np.where(live, dg, 1.0), 0.0)
+    for s in range(1, len(ws)):
+        x = smooth(x, ws[s])
+    if last:
+        return x
+    r = np.where(live, b - A(x), 0.0)
+    C = levels[l + 1]
+    fx, fy, fz = L["fx"], L["fy"], L["fz"]
+    pad = np.zeros((C["nz"] * fz, C["ny"] * fy, C["nx"] * fx))
+    pad[:L["nz"], :L["ny"], :L["nx"]] = r
+    bc = pad.reshape(C["nz"], fz, C["ny"], fy, C["nx"], fx).sum(axis=(1, 3, 5))
+    ec = _tail_reference_cycle(levels, l + 1, bc, w, wc)
+    up = np.repeat(np.repeat(np.repeat(ec, fz, 0), fy, 1), fx, 2)[:L["nz"], :L["ny"], :L["nx"]]
+    x = np.where(live, x + up, x)
+    for s in range(len(w)):
+        x = smooth(x, w[len(w) - 1 - s])
+    return x
+
+
+@pytest.fixture(scope="module")
+def tail_emul(tmp_path_factory):
+    """tests/cpu_emul/tail_emul.cu: the CUDA kernel's own tail_cycle() compiled for the host."""
+    import ctypes
+    import subprocess
+    from openimpala_b200 import build
+    out = tmp_path_factory.mktemp("tail_emul") / "libtail_emul.so"
+    src = os.path.join(ROOT, "tests", "cpu_emul", "tail_emul.cu")
+    subprocess.run([build.NVCC, "-O2", "-std=c++17", "--expt-relaxed-constexpr"] + build.ARCH +
+                   ["-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", str(out), src], check=True)
+    return ctypes.CDLL(str(out))
+
+
+@pytest.mark.parametrize("dims0,factors,periodic,deg", [
+    ((16, 16, 16), [(2, 2, 2), (2, 2, 2)], 0, 4),              # 16^3 -> 8^3 -> 4^3 (the 1024^3 tail)
+    ((13, 13, 13), [(2, 2, 2), (2, 2, 2)], 0, 4),              # odd extents (the sample image's tail)
+    ((12, 10, 14), [(2, 2, 2), (2, 2, 2)], 7, 4),              # periodic box (cell problem)
+    ((9, 12, 20), [(1, 1, 2), (1, 2, 2), (2, 2, 2)], 0, 3),    # semicoarsened levels, odd degree
+    ((6, 5, 4), [], 0, 4),                                     # the coarsest level alone
+    ((7, 6, 5), [(2, 2, 1)], 7, 2),
+])
+def test_coarse_tail_cycle_on_the_host(tail_emul, dims0, factors, periodic, deg):
+    """The one-CTA coarse tail (oi_coarse_tail.cuh) executed on the host through the same
+    tail_cycle() template the kernel instantiates, against an independent numpy V-cycle:
+    sweep order, weights, residual, aggregation restriction, piecewise-constant
+    prolongation, periodic wrap, semicoarsening factors, result left in the first level's x."""
+    import ctypes
+    rng = np.random.default_rng(hash((dims0, periodic, deg)) % (2 ** 32))
+    levels = _tail_levels(rng, dims0, list(factors), bool(periodic))
+    w = [1.0 / (0.3 + 0.4 * k) for k in range(deg)]
+    wc = [1.0 / (0.2 + 0.22 * k) for k in range(8)]
+    b0 = np.where(levels[0]["dg"] > 0, rng.standard_normal(levels[0]["dg"].shape), 0.0).astype(np.float32)
+    ref = _tail_reference_cycle(levels, 0, b0.astype(np.float64), w, wc)
+    dims, fields, keep = [], [], []
+    for q, L in enumerate(levels):
+        dims += [L["nx"], L["ny"], L["nz"], L["fx"], L["fy"], L["fz"]]
+        n = L["nx"] * L["ny"] * L["nz"]
+        arrs = [np.ascontiguousarray(L[k]).reshape(n) for k in ("cxp", "cyp", "czp", "dg")]
+        x = rng.standard_normal(n).astype(np.float32)          # garbage: the cycle starts from zero itself
+        b = b0.reshape(n).copy() if q == 0 else rng.standard_normal(n).astype(np.float32)
+        t = rng.standard_normal(n).astype(np.float32)
+        arrs += [x, b, t]
+        keep.append(arrs)
+        fields += [a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for a in arrs]
+    c_dims = (ctypes.c_int * len(dims))(*dims)
+    c_fields = (ctypes.POINTER(ctypes.c_float) * len(fields))(*fields)
+    c_w = (ctypes.c_double * deg)(*w)
+    c_wc = (ctypes.c_double * 8)(*wc)
+    rc = tail_emul.oi_tail_emulate(len(levels), c_dims, int(periodic), c_fields, deg, c_w, 8, c_wc)
+    assert rc == 0
+    got = keep[0][4].reshape(ref.shape)
+    scale = float(np.abs(ref).max())
+    assert scale > 0
+    assert float(np.abs(got - ref).max()) <= 2e-5 * scale       # fp32 cycle against the float64 reference
+    assert not got[levels[0]["dg"] == 0].any()                  # empty aggregates stay zero

@@ -1,4 +1,5 @@
-"""Stream path against CUDA-graph replay of the PCG iterations (OI_GRAPH=0|1) on the
+"""Stream path against CUDA-graph replay of the PCG iterations (OI_GRAPH=0|1), without and
+with the one-CTA coarse tail (OI_TAIL=0|1), on the
 reference's sample image and on small sphere packings: solve milliseconds (CUDA events
 inside oi_solve) and wall-clock object-to-tau milliseconds, best of a few repetitions.
 Run on the GPU box:  python tools/graph_timing.py > gpurun_out/graph_timing.json"""
@@ -27,8 +28,9 @@ def read_sample_tiff():
 
 def run(ph, direction, reps=5):
     rows = {}
-    for mode in ("0", "1"):
+    for mode, tail in (("0", "0"), ("1", "0"), ("1", "1")):
         os.environ["OI_GRAPH"] = mode
+        os.environ["OI_TAIL"] = tail
         best_solve, best_wall, its, replays, nodes = 1e30, 1e30, 0, 0, 0
         for _ in range(reps):
             t0 = time.perf_counter()
@@ -42,9 +44,10 @@ def run(ph, direction, reps=5):
             best_solve = min(best_solve, info.solve_ms)
             best_wall = min(best_wall, wall)
             its = info.iterations
-        rows["graph" if mode == "1" else "stream"] = dict(solve_ms=best_solve, wall_ms=best_wall, iterations=its,
+        rows[("graph+tail" if tail == "1" else "graph") if mode == "1" else "stream"] = dict(solve_ms=best_solve, wall_ms=best_wall, iterations=its,
                                                           replays=replays, kernel_nodes=nodes)
     rows["solve_speedup"] = rows["stream"]["solve_ms"] / rows["graph"]["solve_ms"]
+    rows["solve_speedup_with_tail"] = rows["stream"]["solve_ms"] / rows["graph+tail"]["solve_ms"]
     return rows
 
 
@@ -53,6 +56,7 @@ if __name__ == "__main__":
     ph = read_sample_tiff()
     for d, name in enumerate("XYZ"):
         out[f"sample_100^3_{name}"] = run(ph, d)
-    for n in (64, 128, 192, 256, 320):
+    sizes = [int(v) for v in os.environ.get("OI_TIMING_SIZES", "64,128,192,256,320").split(",") if v]
+    for n in sizes:
         out[f"packing_{n}^3_Z"] = run(synth.sphere_packing(n, 12345, 12, 0.60), 2, reps=3)
     print(json.dumps(out, indent=1))
