@@ -271,6 +271,13 @@ coarse_tail_kernel(TailArgs a) {
     tail_cycle(a, CtaStep());
 }
 
+// fields staged in dynamic shared memory (fp32 multigrid vectors only)
+__global__ void __launch_bounds__(TAIL_NT, 1)
+coarse_tail_staged_kernel(TailArgs a) {
+    extern __shared__ float4 tail_smem[];
+    tail_cycle_staged(a, CtaStep(), reinterpret_cast<float*>(tail_smem));
+}
+
 inline int blocks_for(long long n) {
     long long b = (n + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
@@ -329,8 +336,20 @@ void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* o
         coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
 }
 
-void coarse_tail_cycle(const TailArgs& a, cudaStream_t st) {
-    coarse_tail_kernel<<<1, TAIL_NT, 0, st>>>(a);
+void coarse_tail_cycle(const TailArgs& a, bool staged, cudaStream_t st) {
+    // 227 KB of shared memory per CTA on sm_100a; stay a little below
+    constexpr size_t SMEM_LIMIT = 220 * 1024;
+    const size_t bytes = tail_staged_bytes(a);
+    if (staged && sizeof(mg_t) == sizeof(float) && bytes <= SMEM_LIMIT) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(coarse_tail_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+            configured = true;
+        }
+        coarse_tail_staged_kernel<<<1, TAIL_NT, bytes, st>>>(a);
+    } else {
+        coarse_tail_kernel<<<1, TAIL_NT, 0, st>>>(a);
+    }
 }
 
 void coarse_restrict(const CoarseLevel& f, const mg_t* res, const CoarseLevel& c, mg_t* bc, cudaStream_t st) {

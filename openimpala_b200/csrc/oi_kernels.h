@@ -81,7 +81,9 @@ struct TailArgs {
     CoarseLevel L[TAIL_MAX_LEVELS];
     mg_t w[16], wc[16];
 };
-void coarse_tail_cycle(const TailArgs& a, cudaStream_t st);
+// staged: run on shared-memory copies of the fields when they fit (else, and for fp64
+// multigrid vectors, in global memory)
+void coarse_tail_cycle(const TailArgs& a, bool staged, cudaStream_t st);
 
 // ---------------------------------------------------------------- vector ops (K4)
 // x += a p ; r -= a q ; out[0] = r.r      with a = num[0]/den[0] read on device

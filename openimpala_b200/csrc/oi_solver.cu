@@ -412,6 +412,10 @@ namespace {
 #ifndef OI_TAIL_DEFAULT
 #define OI_TAIL_DEFAULT true
 #endif
+// its shared-memory staging is opt-in (OI_TAIL_SMEM=1) until it has run on the GPU
+#ifndef OI_TAIL_SMEM_DEFAULT
+#define OI_TAIL_SMEM_DEFAULT false
+#endif
 
 using oi::CoarseLevel;
 using oi::Grid;
@@ -936,7 +940,10 @@ void coarse_cycle(oi_solver* S, size_t l) {
         for (int q = 0; q < ta.n_levels; ++q) ta.L[q] = S->levels[l + q].L;
         for (int q = 0; q < ta.deg; ++q) ta.w[q] = (mg_t)S->w_smooth[q];
         for (int q = 0; q < ta.deg_c; ++q) ta.wc[q] = (mg_t)S->w_coarse[q];
-        oi::coarse_tail_cycle(ta, S->st); S->launches++;
+        // OI_TAIL_SMEM=0: keep the fields in global memory (the variant the GPU suite has run)
+        const char* se = getenv("OI_TAIL_SMEM");
+        const bool staged = se ? (se[0] == '1') : OI_TAIL_SMEM_DEFAULT;
+        oi::coarse_tail_cycle(ta, staged, S->st); S->launches++;
         return;
     }
     const bool last = (l + 1 == S->levels.size());

@@ -4,6 +4,8 @@
 // sequential `step`, so that the cycle's control flow and index arithmetic can be
 // checked against an independent numpy V-cycle without a GPU
 // (tests/test_host_cpu.py::test_coarse_tail_cycle_on_the_host).
+#include <cstdlib>
+
 #include "../../openimpala_b200/csrc/oi_coarse_tail.cuh"
 
 namespace {
@@ -18,7 +20,7 @@ struct SeqStep {
 // dims: 6 ints per level (nx, ny, nz, fx, fy, fz); fields: 7 pointers per level
 // (cxp, cyp, czp, dg, x, b, t), each nx*ny*nz floats, x fastest, no ghost planes.
 extern "C" int oi_tail_emulate(int n_levels, const int* dims, int periodic, float** fields, int deg, const double* w,
-                               int deg_c, const double* wc) {
+                               int deg_c, const double* wc, int staged) {
     if (n_levels < 1 || n_levels > oi::TAIL_MAX_LEVELS || deg < 1 || deg > 16 || deg_c < 1 || deg_c > 16) return 1;
     if (sizeof(oi::mg_t) != sizeof(float)) return 2;
     oi::TailArgs a{};
@@ -36,6 +38,16 @@ extern "C" int oi_tail_emulate(int n_levels, const int* dims, int periodic, floa
         L.dgx = L.dgy = L.dgz = nullptr;
         L.x = reinterpret_cast<oi::mg_t*>(f[4]); L.b = reinterpret_cast<oi::mg_t*>(f[5]); L.t = reinterpret_cast<oi::mg_t*>(f[6]);
     }
-    oi::tail_cycle(a, SeqStep());
+    if (staged) {
+        // the kernel's dynamic shared memory is a plain host buffer here
+        const size_t bytes = oi::tail_staged_bytes(a);
+        float* buf = static_cast<float*>(aligned_alloc(16, (bytes + 15) / 16 * 16));
+        if (!buf) return 3;
+        for (size_t q = 0; q < bytes / sizeof(float); ++q) buf[q] = -12345.f;   // garbage: nothing may be assumed zero
+        oi::tail_cycle_staged(a, SeqStep(), buf);
+        free(buf);
+    } else {
+        oi::tail_cycle(a, SeqStep());
+    }
     return 0;
 }

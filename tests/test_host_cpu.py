@@ -291,7 +291,8 @@ def tail_emul(tmp_path_factory):
     ((6, 5, 4), [], 0, 4),                                     # the coarsest level alone
     ((7, 6, 5), [(2, 2, 1)], 7, 2),
 ])
-def test_coarse_tail_cycle_on_the_host(tail_emul, dims0, factors, periodic, deg):
+@pytest.mark.parametrize("staged", [0, 1])
+def test_coarse_tail_cycle_on_the_host(tail_emul, dims0, factors, periodic, deg, staged):
     """The one-CTA coarse tail (oi_coarse_tail.cuh) executed on the host through the same
     tail_cycle() template the kernel instantiates, against an independent numpy V-cycle:
     sweep order, weights, residual, aggregation restriction, piecewise-constant
@@ -318,8 +319,14 @@ def test_coarse_tail_cycle_on_the_host(tail_emul, dims0, factors, periodic, deg)
     c_fields = (ctypes.POINTER(ctypes.c_float) * len(fields))(*fields)
     c_w = (ctypes.c_double * deg)(*w)
     c_wc = (ctypes.c_double * 8)(*wc)
-    rc = tail_emul.oi_tail_emulate(len(levels), c_dims, int(periodic), c_fields, deg, c_w, 8, c_wc)
+    before = [[a.copy() for a in arrs] for arrs in keep]
+    rc = tail_emul.oi_tail_emulate(len(levels), c_dims, int(periodic), c_fields, deg, c_w, 8, c_wc, int(staged))
     assert rc == 0
+    if staged:      # the staged variant touches global memory only to read inputs and to write the first level's x
+        for q, (arrs, old) in enumerate(zip(keep, before)):
+            for m, (a, o) in enumerate(zip(arrs, old)):
+                if not (q == 0 and m == 4):
+                    assert np.array_equal(a, o), (q, m)
     got = keep[0][4].reshape(ref.shape)
     scale = float(np.abs(ref).max())
     assert scale > 0
