@@ -183,6 +183,18 @@ template <typename T>
 cudaError_t cmalloc(T** p, size_t bytes) { return dev_cache().alloc(reinterpret_cast<void**>(p), bytes); }
 inline void cfree(void* p) { dev_cache().free(p); }
 
+// A temporary device block that goes back to the cache on every exit path (a CUDA_CHECK
+// that throws included).
+template <typename T>
+struct TempBlock {
+    T* p = nullptr;
+    TempBlock() = default;
+    TempBlock(const TempBlock&) = delete;
+    TempBlock& operator=(const TempBlock&) = delete;
+    cudaError_t alloc(size_t bytes) { return cmalloc(&p, bytes); }
+    ~TempBlock() { if (p) cfree(p); }
+};
+
 // Small pinned host blocks (16 doubles per handle for scalar read-backs) are recycled
 // too: cudaFreeHost was measured at 2 - 640 ms per call on the B200 box.
 struct PinnedCache {
@@ -1569,22 +1581,23 @@ int count_host_field(const T* host, int64_t n, int32_t phase, int64_t* pc, int64
         OI_REQUIRE(host != nullptr || n == 0, "null field");
         OI_REQUIRE(n >= 0, "negative size");
         require_gpu();
-        unsigned long long* d_cnt = nullptr;
-        T* d = nullptr;
         unsigned long long h = 0;
         if (n > 0) {
             int dev = 0, n_sm = 148;
             CUDA_CHECK(cudaGetDevice(&dev));
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            CUDA_CHECK(cmalloc(&d, (size_t)n * sizeof(T)));
-            CUDA_CHECK(cmalloc(&d_cnt, sizeof(unsigned long long)));
+            TempBlock<T> field;
+            TempBlock<unsigned long long> cnt;
+            CUDA_CHECK(field.alloc((size_t)n * sizeof(T)));
+            CUDA_CHECK(cnt.alloc(sizeof(unsigned long long)));
+            T* d = field.p;
+            unsigned long long* d_cnt = cnt.p;
             CUDA_CHECK(cudaMemset(d_cnt, 0, sizeof(unsigned long long)));
             CUDA_CHECK(cudaMemcpy(d, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
             if (sizeof(T) == 1) oi::count_phase_u8(reinterpret_cast<const uint8_t*>(d), n, phase, d_cnt, n_sm, 0);
             else oi::count_phase_i32(reinterpret_cast<const int32_t*>(d), n, phase, d_cnt, n_sm, 0);
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaMemcpy(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
-            cfree(d); cfree(d_cnt);
         }
         if (pc) *pc = (int64_t)h;
         if (tc) *tc = n;
@@ -1595,12 +1608,12 @@ template <typename T>
 void set_phase_common(oi_solver* S, const T* src, bool src_on_device) {
     ensure_device(S);
     const long long n = S->n_local;
-    T* d_raw = nullptr;
+    TempBlock<T> raw;                 // released after the stream has been synchronised below (or on a throw)
     const T* d_in = src;
     if (!src_on_device) {
-        CUDA_CHECK(cmalloc(&d_raw, (size_t)n * sizeof(T)));
-        CUDA_CHECK(cudaMemcpyAsync(d_raw, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, S->st));
-        d_in = d_raw;
+        CUDA_CHECK(raw.alloc((size_t)n * sizeof(T)));
+        CUDA_CHECK(cudaMemcpyAsync(raw.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, S->st));
+        d_in = raw.p;
     }
     if (!S->d_isphase) CUDA_CHECK(cmalloc(&S->d_isphase, (size_t)n));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull + 4, 0, 2 * sizeof(unsigned long long), S->st));
@@ -1620,7 +1633,6 @@ void set_phase_common(oi_solver* S, const T* src, bool src_on_device) {
     CUDA_CHECK(cudaGetLastError());
     S->phase_count_local = (long long)h[0];
     S->nonbinary_local = (long long)h[1];
-    if (d_raw) cfree(d_raw);
     S->mask_built = false;
     S->solved = false;
 }
@@ -1972,9 +1984,10 @@ int oi_remspot(oi_solver* S, int32_t passes) {
         ensure_device(S);
         const Grid& g = S->g;
         const long long n = S->n_local;
-        uint8_t *fa = nullptr, *fb = nullptr;
-        CUDA_CHECK(cmalloc(&fa, (size_t)n));
-        CUDA_CHECK(cmalloc(&fb, (size_t)n));
+        TempBlock<uint8_t> flips_a, flips_b;
+        CUDA_CHECK(flips_a.alloc((size_t)n));
+        CUDA_CHECK(flips_b.alloc((size_t)n));
+        uint8_t *fa = flips_a.p, *fb = flips_b.p;      // swapped per round; the guards own the blocks
         for (int pass = 0; pass < passes; ++pass) {    // TortuosityHypre.cpp:269-287
             CUDA_CHECK(cudaMemsetAsync(fa, 0, (size_t)n, S->st));
             const int max_rounds = 4 * (g.nx + g.ny + g.nz) + 16;
@@ -1988,15 +2001,11 @@ int oi_remspot(oi_solver* S, int32_t passes) {
                 CUDA_CHECK(cudaStreamSynchronize(S->st));
                 std::swap(fa, fb);
             }
-            if (changed) {
-                cfree(fa); cfree(fb);
-                throw OiError(OI_ERR_INVALID, "oi_remspot: flip flags did not reach their fixed point");
-            }
+            if (changed) throw OiError(OI_ERR_INVALID, "oi_remspot: flip flags did not reach their fixed point");
             oi::remspot_apply(S->d_isphase, fa, n, S->d_ull + 7, S->n_sm, S->st);
             S->launches++;
         }
         CUDA_CHECK(cudaStreamSynchronize(S->st));
-        cfree(fa); cfree(fb);
         S->mask_built = false;
         S->solved = false;
     });
@@ -2117,12 +2126,11 @@ int oi_get_matrix_rows(oi_solver* S, double* host) {
     return guarded([&] {
         OI_REQUIRE(S && host && S->mask_built, "oi_get_matrix_rows: mask not built");
         ensure_device(S);
-        double* d = nullptr;
-        CUDA_CHECK(cmalloc(&d, (size_t)S->n_local * 7 * sizeof(double)));
-        oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, d, nullptr, S->st);
+        TempBlock<double> rows;
+        CUDA_CHECK(rows.alloc((size_t)S->n_local * 7 * sizeof(double)));
+        oi::export_rows(S->g, S->flags.p, S->active.p, S->prm.direction, S->n_dir, S->prm.vlo, S->prm.vhi, rows.p, nullptr, S->st);
         S->launches++;
-        copy_out(S, d, host, (size_t)S->n_local * 7);
-        cfree(d);
+        copy_out(S, rows.p, host, (size_t)S->n_local * 7);
     });
 }
 int oi_apply_operator(oi_solver* S, const double* hx, double* hy) {
