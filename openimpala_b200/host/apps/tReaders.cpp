@@ -6,7 +6,9 @@
 #include <string>
 
 #include <AMReX.H>
+#include <AMReX_MultiFab.H>
 #include <AMReX_ParmParse.H>
+#include <AMReX_PlotFileUtil.H>
 #include <AMReX_Print.H>
 
 #include "../io/DatReader.H"
@@ -89,6 +91,25 @@ int main(int argc, char* argv[]) {
             amrex::Print() << "ThresholdMinMax: " << mf.min(0) << " " << mf.max(0) << "\n";
             long long direct1 = mf.sum(0), total = domain.numPts();
             amrex::Print() << "DirectCount1: " << direct1 << " Total: " << total << "\n";
+            std::string plotfile;
+            if (pp.query("plotfile", plotfile)) {
+                // the thresholded field and an analytic ramp as an AMReX plotfile (the writer the
+                // TortuosityHypre / EffectiveDiffusivityHypre classes use for write_plotfile = 1)
+                amrex::RealBox rb({AMREX_D_DECL(0.0, 0.0, 0.0)},
+                                  {AMREX_D_DECL(amrex::Real(domain.length(0)), amrex::Real(domain.length(1)),
+                                                amrex::Real(domain.length(2)))});
+                const int is_per[3] = {0, 0, 0};
+                amrex::Geometry geom(domain, &rb, 0, is_per);
+                amrex::MultiFab plot(ba, dm, 2, 0);
+                for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
+                    for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
+                        for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i) {
+                            plot(i, j, k, 0) = amrex::Real(mf(i, j, k, 0));
+                            plot(i, j, k, 1) = i + 0.5 * j - 0.25 * k;
+                        }
+                amrex::WriteSingleLevelPlotfile(plotfile, plot, {"phase_id", "ramp"}, geom, 0.0, 0);
+                amrex::Print() << "Plotfile: " << plotfile << "\n";
+            }
             if (use_gpu_count) {
                 for (int phase = 0; phase <= 1; ++phase) {
                     OpenImpala::VolumeFraction vf(mf, phase);

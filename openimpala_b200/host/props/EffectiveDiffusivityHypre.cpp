@@ -12,6 +12,7 @@
 
 #include <AMReX_ParallelDescriptor.H>
 #include <AMReX_ParmParse.H>
+#include <AMReX_PlotFileUtil.H>
 #include <AMReX_Print.H>
 
 #include <openimpala_b200.h>
@@ -137,6 +138,28 @@ bool EffectiveDiffusivityHypre::solve() {
         amrex::Print() << "  HYPRE Final Relative Residual Norm: " << std::scientific << m_final_res_norm
                        << std::defaultfloat << std::endl;
         amrex::Print() << "  Solver Converged Status: " << (m_converged ? "Yes" : "No") << std::endl;
+    }
+    // <resultspath>/effdiff_chi_dir<k> with chi_k and the mask the solver used (:648-685)
+    if (m_write_plotfile && m_converged) {
+        if (m_verbose > 0 && io)
+            amrex::Print() << "  Writing solution plotfile for chi_k in direction " << static_cast<int>(m_dir_solve)
+                           << "..." << std::endl;
+        amrex::MultiFab mf_plot(m_ba, m_dm, 2, 0);
+        amrex::MultiFab chi(m_ba, m_dm, 1, 0);
+        getChiSolution(chi);
+        const amrex::Box& domain = m_geom.Domain();
+        for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
+            for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
+                for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i) {
+                    mf_plot(i, j, k, 0) = chi(i, j, k, 0);
+                    mf_plot(i, j, k, 1) = amrex::Real(m_mf_active_mask(i, j, k, 0));
+                }
+        const std::string full_plot_path = m_resultspath + "/effdiff_chi_dir" + std::to_string(static_cast<int>(m_dir_solve));
+        const amrex::Vector<std::string> varnames = {"chi_k", "active_mask_from_solver"};
+        amrex::WriteSingleLevelPlotfile(full_plot_path, mf_plot, varnames, m_geom, 0.0, 0);
+        if (m_verbose > 0 && io) amrex::Print() << "  Plotfile written to " << full_plot_path << std::endl;
+    } else if (m_write_plotfile && m_verbose >= 0 && io) {
+        amrex::Warning("Skipping plotfile write for chi_k because solver did not converge and had active cells.");
     }
     return m_converged;
 }

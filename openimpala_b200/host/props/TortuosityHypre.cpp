@@ -14,7 +14,9 @@
 #include <vector>
 
 #include <AMReX_ParallelDescriptor.H>
+#include <AMReX_MultiFab.H>
 #include <AMReX_ParmParse.H>
+#include <AMReX_PlotFileUtil.H>
 #include <AMReX_Print.H>
 
 #include <openimpala_b200.h>
@@ -52,6 +54,7 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
     initialize([&](oi_solver* h) {
         const std::vector<int> cells = mf_phase_input.validCopy(0);
         oi_check(oi_set_phase_i32(h, cells.data()), "oi_set_phase_i32");
+        if (m_write_plotfile) m_plot_phase = cells;
     });
 }
 
@@ -75,6 +78,9 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
             uint8_t* buf = nullptr;
             oi_check(oi_phase_stream_buffer(h, which, &buf), "oi_phase_stream_buffer");
             phase_stream(z0, n, buf);
+            if (m_write_plotfile)
+                m_plot_phase.insert(m_plot_phase.end(), buf,
+                                    buf + (size_t)n * (size_t)m_geom.Domain().length(0) * (size_t)m_geom.Domain().length(1));
             oi_check(oi_phase_stream_submit(h, which, z0, n), "oi_phase_stream_submit");
         }
         oi_check(oi_phase_stream_end(h), "oi_phase_stream_end");
@@ -174,8 +180,37 @@ bool TortuosityHypre::solve() {
         amrex::Print() << "  Solver Converged Status: " << (m_converged ? "Yes" : "No") << std::endl;
         amrex::Print() << "  Device time: solve " << info.solve_ms << " ms, multigrid setup " << info.setup_ms << " ms" << std::endl;
     }
-    if (m_write_plotfile && m_verbose >= 0) amrex::Warning("write_plotfile is not supported by the B200 path; skipped.");
+    if (m_write_plotfile && m_converged) writeSolutionPlotfile();                                  // :710-745
+    else if (m_write_plotfile && m_verbose >= 0 && io)
+        amrex::Warning("Skipping plotfile write because solver did not converge.");               // :746-750
     return m_converged;
+}
+
+// <resultspath>/tortuosity_solution_<dir> with solution_potential, phase_id and active_mask,
+// as the reference writes it (TortuosityHypre.cpp:710-745).  phase_id is the field handed to
+// the constructor (the reference plots it after the optional remspot filter).
+void TortuosityHypre::writeSolutionPlotfile() {
+    const bool io = amrex::ParallelDescriptor::IOProcessor();
+    if (m_verbose > 0 && io) amrex::Print() << "  Writing solution plotfile..." << std::endl;
+    const amrex::Box& domain = m_geom.Domain();
+    const size_t n = (size_t)domain.numPts();
+    std::vector<double> x(n);
+    std::vector<uint8_t> mask(n);
+    oi_check(oi_get_solution(m_solver, x.data()), "oi_get_solution");
+    oi_check(oi_get_mask_u8(m_solver, mask.data()), "oi_get_mask_u8");
+    amrex::MultiFab mf_plot(m_ba, m_dm, 3, 0);
+    size_t q = 0;
+    for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
+        for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
+            for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i, ++q) {
+                mf_plot(i, j, k, 0) = x[q];
+                mf_plot(i, j, k, 1) = q < m_plot_phase.size() ? amrex::Real(m_plot_phase[q]) : 0.0;
+                mf_plot(i, j, k, 2) = amrex::Real(mask[q]);
+            }
+    const std::string plotfilename = m_resultspath + "/tortuosity_solution_" + std::to_string(static_cast<int>(m_dir));
+    const amrex::Vector<std::string> varnames = {"solution_potential", "phase_id", "active_mask"};
+    amrex::WriteSingleLevelPlotfile(plotfilename, mf_plot, varnames, m_geom, 0.0, 0);
+    if (m_verbose > 0 && io) amrex::Print() << "  Plotfile written to " << plotfilename << std::endl;
 }
 
 void TortuosityHypre::global_fluxes() {

@@ -233,6 +233,87 @@ def test_dat_reader(host_bins, tmp_path):
     assert run("tReaders", "mode=dat", "gpu_count=0", f"datfile={tmp_path / 'bad.dat'}", check=False).returncode != 0
 
 
+def read_amrex_plotfile(path):
+    """Independent reader of a single-level, single-grid AMReX plotfile (layout of AMReX 25.03
+    WriteGenericPlotfileHeader + VisMF header version 1): returns (header dict, {name: array[z,y,x]})."""
+    import numpy as np
+    lines = open(os.path.join(path, "Header")).read().split("\n")
+    it = iter(lines)
+    h = {"version": next(it)}
+    ncomp = int(next(it))
+    h["names"] = [next(it) for _ in range(ncomp)]
+    h["dim"] = int(next(it))
+    h["time"] = float(next(it))
+    h["finest_level"] = int(next(it))
+    h["prob_lo"] = [float(v) for v in next(it).split()]
+    h["prob_hi"] = [float(v) for v in next(it).split()]
+    h["ref_ratio"] = next(it).split()
+    m = re.fullmatch(r"\(\((\d+),(\d+),(\d+)\) \((\d+),(\d+),(\d+)\) \(0,0,0\)\) ?", next(it))
+    assert m, "domain box line"
+    h["domain"] = [int(v) for v in m.groups()]
+    h["level_steps"] = [int(v) for v in next(it).split()]
+    h["dx"] = [float(v) for v in next(it).split()]
+    h["coord_sys"] = int(next(it))
+    h["bwidth"] = int(next(it))
+    lev, ngrids, t = next(it).split()
+    h["grids"] = int(ngrids)
+    assert int(lev) == 0 and float(t) == h["time"]
+    h["step"] = int(next(it))
+    h["grid_extent"] = [[float(v) for v in next(it).split()] for _ in range(3)]
+    h["mf_path"] = next(it)
+    # VisMF header
+    ch = open(os.path.join(path, h["mf_path"] + "_H")).read().split("\n")
+    it = iter(ch)
+    assert int(next(it)) == 1 and int(next(it)) == 1          # version 1, one file per process
+    assert int(next(it)) == ncomp
+    assert int(next(it)) == 0                                 # no ghost cells
+    assert next(it) == "(1 0"
+    box_line = next(it)
+    assert next(it) == ")"
+    assert int(next(it)) == 1
+    fod = next(it).split()
+    assert fod[0] == "FabOnDisk:" and int(fod[2]) == 0
+    assert next(it) == ""
+    assert next(it) == f"1,{ncomp}"
+    h["min"] = [float(v) for v in next(it).rstrip(",").split(",")]
+    assert next(it) == ""
+    assert next(it) == f"1,{ncomp}"
+    h["max"] = [float(v) for v in next(it).rstrip(",").split(",")]
+    raw = open(os.path.join(path, os.path.dirname(h["mf_path"]), fod[1]), "rb").read()
+    nl = raw.index(b"\n")
+    fab = raw[:nl].decode()
+    assert fab.startswith("FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))")   # native little-endian IEEE double
+    assert fab.endswith(box_line + f" {ncomp}")
+    lo_hi = h["domain"]
+    nx, ny, nz = (lo_hi[3 + d] - lo_hi[d] + 1 for d in range(3))
+    data = np.frombuffer(raw[nl + 1:], dtype="<f8")
+    assert data.size == ncomp * nx * ny * nz
+    data = data.reshape(ncomp, nz, ny, nx)
+    return h, {n: data[c] for c, n in enumerate(h["names"])}
+
+
+def test_plotfile_writer_round_trip(host_bins, tmp_path):
+    """amrex::WriteSingleLevelPlotfile of the stand-in (the writer behind write_plotfile = 1,
+    reference TortuosityHypre.cpp:710-745): Header / Cell_H / FAB parse back with an independent
+    reader and carry the fields bit for bit."""
+    import numpy as np
+    from oracle import oi_numpy as o
+    plt = str(tmp_path / "plt_check")
+    r = run("tReaders", "mode=tiff", "tifffile=tests/golden/SampleData_2Phase_squared.tif", "gpu_count=0",
+            f"plotfile={plt}")
+    assert "TEST PASSED" in r.stdout
+    h, f = read_amrex_plotfile(plt)
+    assert h["version"] == "HyperCLaw-V1.1" and h["names"] == ["phase_id", "ramp"] and h["dim"] == 3
+    assert h["domain"] == [0, 0, 0, 63, 63, 63] and h["finest_level"] == 0 and h["grids"] == 1
+    assert h["prob_lo"] == [0.0, 0.0, 0.0] and h["prob_hi"] == [64.0, 64.0, 64.0] and h["dx"] == [1.0, 1.0, 1.0]
+    assert h["grid_extent"] == [[0.0, 64.0]] * 3 and h["mf_path"] == "Level_0/Cell"
+    ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, "SampleData_2Phase_squared.tif")), 0.5)
+    assert np.array_equal(f["phase_id"], ph.astype(np.float64))
+    k, j, i = np.meshgrid(np.arange(64), np.arange(64), np.arange(64), indexing="ij")
+    assert np.array_equal(f["ramp"], i + 0.5 * j - 0.25 * k)
+    assert h["min"] == [0.0, f["ramp"].min()] and h["max"] == [1.0, f["ramp"].max()]
+
+
 def test_missing_required_key_aborts(host_bins):
     r = run("Diffusion", "calculation_method=flow_through", check=False)
     assert r.returncode != 0 and "filename" in r.stderr
@@ -284,6 +365,28 @@ def test_diffusion_app_results_txt(host_bins):
         ref = next(c for c in gold["cases"] if c["phase"] == 1 and c["direction"] == d)["tau"]
         assert abs(float(vals[key]) - ref) <= 1e-6 * ref
         assert re.fullmatch(r"\d+\.\d{9}", vals[key])
+
+
+@pytest.mark.gpu
+def test_diffusion_write_plotfile(host_bins):
+    """write_plotfile = 1 (Diffusion.cpp:211, 696 -> TortuosityHypre.cpp:710-745): the solution,
+    the phase ids and the percolation mask as <results_path>/tortuosity_solution_<dir>."""
+    import numpy as np
+    gold = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "direction=Z", "write_plotfile=1",
+        "results_path=gpurun_out/results_plot/", "verbose=0")
+    h, f = read_amrex_plotfile(os.path.join(ROOT, "gpurun_out", "results_plot", "tortuosity_solution_2"))
+    assert h["names"] == ["solution_potential", "phase_id", "active_mask"]
+    assert h["domain"] == [0, 0, 0, 99, 99, 99] and h["prob_hi"] == [100.0, 100.0, 100.0]
+    case = next(c for c in gold["cases"] if c["phase"] == 1 and c["direction"] == 2)
+    mask = f["active_mask"]
+    assert int(mask.sum()) == case["n_active"] and set(np.unique(mask)) <= {0.0, 1.0}
+    assert int((f["phase_id"] == 1).sum()) == gold["phase_count"]["1"]
+    x = f["solution_potential"]
+    act = mask.astype(bool)
+    assert not x[~act].any()                                          # zero off the percolating cells
+    assert np.all(x[0][act[0]] == -1.0) and np.all(x[-1][act[-1]] == 1.0)     # Dirichlet planes (app defaults vlo/vhi = -1/+1)
+    assert x[act].min() >= -1.0 - 1e-6 and x[act].max() <= 1.0 + 1e-6
 
 
 @pytest.mark.gpu
