@@ -341,11 +341,9 @@ void coarse_tail_cycle(const TailArgs& a, bool staged, cudaStream_t st) {
     constexpr size_t SMEM_LIMIT = 220 * 1024;
     const size_t bytes = tail_staged_bytes(a);
     if (staged && sizeof(mg_t) == sizeof(float) && bytes <= SMEM_LIMIT) {
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured = 0;
+        if (first_use_on_this_device(configured))
             cudaFuncSetAttribute(coarse_tail_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-            configured = true;
-        }
         coarse_tail_staged_kernel<<<1, TAIL_NT, bytes, st>>>(a);
     } else {
         coarse_tail_kernel<<<1, TAIL_NT, 0, st>>>(a);

@@ -124,4 +124,16 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials,
     }
 }
 
+// Function attributes (cudaFuncSetAttribute) belong to a device's context, so the one-time
+// configuration of a kernel has to happen once per device, not once per process: true the
+// first time a call site is reached with the current device.
+inline bool first_use_on_this_device(unsigned long long& seen_devices) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen_devices & bit) return false;
+    seen_devices |= bit;
+    return true;
+}
+
 }  // namespace oi

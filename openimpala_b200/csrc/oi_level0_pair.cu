@@ -463,14 +463,13 @@ bool pair_supported(const L0Args& a) {
 
 // out = S_w2(S_w1(u)) ; dot: also red_out = b . out.  variant 1: 256 threads x 4 cells, 2: 512 x 2.
 void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant, cudaStream_t st) {
-    static bool configured = false;
+    static unsigned long long configured = 0;
     const size_t smem = pair_smem_bytes();
-    if (!configured) {
+    if (first_use_on_this_device(configured)) {
         cudaFuncSetAttribute(l0_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
     }
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + PTX - 1) / PTX, (a.g.ny + PTY - 1) / PTY, (a.g.nz + zc - 1) / zc);

@@ -318,12 +318,10 @@ size_t ring_smem_bytes() {
 template <typename T, int MODE, bool DOT>
 void launch(const L0Args& a, cudaStream_t st) {
     typedef Cfg<T> C;
-    static bool configured = false;
+    static unsigned long long configured = 0;
     const size_t smem = ring_smem_bytes<T, MODE>();
-    if (!configured) {
+    if (first_use_on_this_device(configured))
         cudaFuncSetAttribute(l0_ring_kernel<T, MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + C::TX - 1) / C::TX, (a.g.ny + C::TY - 1) / C::TY, (a.g.nz + zc - 1) / zc);
     RingCoarse rc{a.cnx, a.cny, a.g.z0 >> 1};
