@@ -2,7 +2,9 @@
 // tRawReader.cpp, tHDF5Reader.cpp and src/props/tVolumeFraction.cpp:
 //   mode = tiff | tiffseq | raw | hdf5 | dat ; prints dims, sample metadata, thresholded min/max
 //   and the phase counts, compares the GPU count with a direct host loop.
+#include <functional>
 #include <iomanip>
+#include <vector>
 #include <string>
 
 #include <AMReX.H>
@@ -43,6 +45,29 @@ int main(int argc, char* argv[]) {
         auto prepare = [&](const amrex::Box& b) {
             domain = b; ba.define(b); ba.maxSize(box_size); dm.define(ba); mf.define(ba, dm, 1, 0);
         };
+        // u8_chunk = N: the streamed-upload entry point (thresholdPlanesU8, N planes at a time)
+        // must reproduce the iMultiFab path voxel for voxel
+        int u8_chunk = 0;
+        pp.query("u8_chunk", u8_chunk);
+        auto check_u8 = [&](const std::function<void(int, int, unsigned char*)>& planes) {
+            if (u8_chunk <= 0) return;
+            const size_t plane = (size_t)domain.length(0) * (size_t)domain.length(1);
+            std::vector<unsigned char> buf((size_t)u8_chunk * plane);
+            long long bad = 0;
+            for (int z0 = 0; z0 < domain.length(2); z0 += u8_chunk) {
+                const int nz = std::min(u8_chunk, domain.length(2) - z0);
+                std::fill(buf.begin(), buf.end(), (unsigned char)0xee);
+                planes(z0, nz, buf.data());
+                size_t q = 0;
+                for (int k = z0; k < z0 + nz; ++k)
+                    for (int j = 0; j < domain.length(1); ++j)
+                        for (int i = 0; i < domain.length(0); ++i, ++q)
+                            if ((int)buf[q] != mf(i, j, k, 0)) ++bad;
+            }
+            amrex::Print() << "U8ChunkMismatches: " << bad << "\n";
+            if (bad) fail("thresholdPlanesU8 differs from threshold()");
+        };
+        const double t_read0 = amrex::second();
         try {
             if (mode == "tiff") {
                 OpenImpala::TiffReader r(file);
@@ -50,6 +75,7 @@ int main(int argc, char* argv[]) {
                                << " SamplesPerPixel: " << r.samplesPerPixel() << "\n";
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
+                check_u8([&](int z0, int nz, unsigned char* out) { r.thresholdPlanesU8(threshold, 1, 0, z0, nz, out); });
             } else if (mode == "tiffseq") {
                 std::string suffix = ".tif";
                 int num_files = 0, start_index = 0, digits = 1;
@@ -60,6 +86,7 @@ int main(int argc, char* argv[]) {
                 OpenImpala::TiffReader r(file, num_files, start_index, digits, suffix);   // file = base pattern
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
+                check_u8([&](int z0, int nz, unsigned char* out) { r.thresholdPlanesU8(threshold, 1, 0, z0, nz, out); });
             } else if (mode == "raw") {
                 OpenImpala::RawDataType t = OpenImpala::RawDataType::UINT8;
                 if (datatype == "INT16_LE") t = OpenImpala::RawDataType::INT16_LE;
@@ -70,10 +97,12 @@ int main(int argc, char* argv[]) {
                 OpenImpala::RawReader r(file, width, height, depth, t);
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
+                check_u8([&](int z0, int nz, unsigned char* out) { r.thresholdPlanesU8(threshold, 1, 0, z0, nz, out); });
             } else if (mode == "hdf5") {
                 OpenImpala::HDF5Reader r(file, dataset);
                 prepare(r.box());
                 r.threshold(threshold, 1, 0, mf);
+                check_u8([&](int z0, int nz, unsigned char* out) { r.thresholdPlanesU8(threshold, 1, 0, z0, nz, out); });
             } else if (mode == "dat") {
                 OpenImpala::DatReader r(file);
                 prepare(r.box());
@@ -87,10 +116,21 @@ int main(int argc, char* argv[]) {
             fail(e.what());
         }
         if (passed) {
+            const double t_read = amrex::second() - t_read0;
+            amrex::Print() << "ReadThresholdSeconds: " << t_read << " (" << domain.numPts() / std::max(t_read, 1e-9) * 1e-6
+                           << " Mvoxel/s, open + decode + threshold into the int32 field)\n";
             amrex::Print() << "Dims: " << domain.length(0) << " " << domain.length(1) << " " << domain.length(2) << "\n";
             amrex::Print() << "ThresholdMinMax: " << mf.min(0) << " " << mf.max(0) << "\n";
             long long direct1 = mf.sum(0), total = domain.numPts();
             amrex::Print() << "DirectCount1: " << direct1 << " Total: " << total << "\n";
+            {   // position-weighted sum: catches a voxel that is right in value but wrong in place
+                unsigned long long chk = 0, idx = 0;
+                for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
+                    for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
+                        for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i, ++idx)
+                            chk += (idx % 65521ull + 1ull) * (unsigned long long)(mf(i, j, k, 0) & 0xff);
+                amrex::Print() << "WeightedChecksum: " << chk << "\n";
+            }
             std::string plotfile;
             if (pp.query("plotfile", plotfile)) {
                 // the thresholded field and an analytic ramp as an AMReX plotfile (the writer the

@@ -4,10 +4,13 @@
 // threshold rule double(v) > t ? a : b (:321-326).
 #include "HDF5Reader.H"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include <AMReX_Utility.H>
@@ -236,38 +239,92 @@ std::string HDF5Reader::getAttribute(const std::string& attr_name) const {
     return "<HDF5 Error reading attr '" + attr_name + "'>";   // attributes need libhdf5
 }
 
+// out[((k - z_begin) * H + j) * W + i] = (double(v) > t) ? vt : vf (reference rule,
+// src/io/HDF5Reader.cpp:321-326) for planes [z_begin, z_begin + nz) of the contiguous dataset:
+// whole planes are read at once, 8- and 16-bit integers go through a lookup table of the rule,
+// planes are spread over up to 16 threads (OI_IO_THREADS), each with its own file handle.
+template <class OutT>
+void HDF5Reader::thresholdInto(double t, OutT vt, OutT vf, int z_begin, int nz, OutT* out) const {
+    const size_t bps = (size_t)m_type_size;
+    const size_t plane = (size_t)m_width * (size_t)m_height;
+    std::vector<OutT> lut;
+    if (m_type_class != 1 && (bps == 1 || bps == 2)) {
+        lut.resize((size_t)1 << (8 * bps));
+        for (size_t v = 0; v < lut.size(); ++v) {
+            const double sv = !m_type_signed ? (double)v : (bps == 1 ? (double)(int8_t)(uint8_t)v : (double)(int16_t)(uint16_t)v);
+            lut[v] = (sv > t) ? vt : vf;
+        }
+    }
+    int T = (int)std::thread::hardware_concurrency();
+    if (T <= 0) T = 1;
+    T = std::min(T, 16);
+    if (const char* e = std::getenv("OI_IO_THREADS")) T = std::atoi(e);
+    T = std::max(1, std::min(T, nz));
+    std::vector<std::string> errors((size_t)T);
+    auto work = [&](int w) {
+        const int lo = z_begin + (int)((long long)nz * w / T), hi = z_begin + (int)((long long)nz * (w + 1) / T);
+        if (lo >= hi) return;
+        std::ifstream in(m_filename, std::ios::binary);
+        if (!in) { errors[(size_t)w] = "cannot reopen " + m_filename; return; }
+        std::vector<unsigned char> buf(plane * bps);
+        for (int k = lo; k < hi; ++k) {
+            in.clear();
+            in.seekg((std::streamoff)(m_data_offset + (uint64_t)k * plane * bps));
+            in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size());
+            if ((size_t)in.gcount() != buf.size()) std::memset(buf.data() + in.gcount(), 0, buf.size() - (size_t)in.gcount());
+            OutT* dst = out + (size_t)(k - z_begin) * plane;
+            const unsigned char* src = buf.data();
+            if (!lut.empty() && bps == 1) {
+                for (size_t q = 0; q < plane; ++q) dst[q] = lut[src[q]];
+            } else if (!lut.empty()) {
+                if (!m_type_big_endian) for (size_t q = 0; q < plane; ++q) dst[q] = lut[(size_t)src[2 * q] | ((size_t)src[2 * q + 1] << 8)];
+                else for (size_t q = 0; q < plane; ++q) dst[q] = lut[((size_t)src[2 * q] << 8) | (size_t)src[2 * q + 1]];
+            } else {
+                for (size_t i = 0; i < plane; ++i) {
+                    unsigned char b[8] = {0};
+                    const unsigned char* p = src + i * bps;
+                    for (size_t q = 0; q < bps && q < 8; ++q) b[q] = m_type_big_endian ? p[bps - 1 - q] : p[q];
+                    double v = 0.0;
+                    if (m_type_class == 1) {
+                        if (bps == 4) { float x; std::memcpy(&x, b, 4); v = (double)x; }
+                        else if (bps == 8) { std::memcpy(&v, b, 8); }
+                    } else if (m_type_signed) {
+                        if (bps == 4) { int32_t x; std::memcpy(&x, b, 4); v = (double)x; }
+                        else if (bps == 8) { int64_t x; std::memcpy(&x, b, 8); v = (double)x; }
+                    } else {
+                        uint64_t x = 0;
+                        std::memcpy(&x, b, bps > 8 ? 8 : bps);
+                        v = (double)x;
+                    }
+                    dst[i] = (v > t) ? vt : vf;
+                }
+            }
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < T; ++w) pool.emplace_back(work, w);
+        for (auto& th : pool) th.join();
+    }
+    for (const std::string& e : errors)
+        if (!e.empty()) amrex::Abort("[HDF5Reader::threshold] " + e);
+}
+
 void HDF5Reader::threshold(double t, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {
     if (!m_is_read) amrex::Abort("[HDF5Reader::threshold] metadata not read");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.boxArray().minimalBox() == this->box(), "HDF5Reader: iMultiFab domain mismatch");
-    std::ifstream in(m_filename, std::ios::binary);
-    if (!in) amrex::Abort("[HDF5Reader::threshold] cannot reopen " + m_filename);
-    const size_t bps = (size_t)m_type_size;
-    std::vector<unsigned char> row((size_t)m_width * bps);
-    for (int k = 0; k < m_depth; ++k)
-        for (int j = 0; j < m_height; ++j) {
-            in.seekg((std::streamoff)(m_data_offset + (((uint64_t)k * m_height + j) * (uint64_t)m_width) * bps));
-            in.read(reinterpret_cast<char*>(row.data()), (std::streamsize)row.size());
-            for (int i = 0; i < m_width; ++i) {
-                unsigned char b[8] = {0};
-                const unsigned char* p = row.data() + (size_t)i * bps;
-                for (size_t q = 0; q < bps && q < 8; ++q) b[q] = m_type_big_endian ? p[bps - 1 - q] : p[q];
-                double v = 0.0;
-                if (m_type_class == 1) {
-                    if (bps == 4) { float x; std::memcpy(&x, b, 4); v = (double)x; }
-                    else if (bps == 8) { std::memcpy(&v, b, 8); }
-                } else if (m_type_signed) {
-                    if (bps == 1) { int8_t x; std::memcpy(&x, b, 1); v = (double)x; }
-                    else if (bps == 2) { int16_t x; std::memcpy(&x, b, 2); v = (double)x; }
-                    else if (bps == 4) { int32_t x; std::memcpy(&x, b, 4); v = (double)x; }
-                    else if (bps == 8) { int64_t x; std::memcpy(&x, b, 8); v = (double)x; }
-                } else {
-                    uint64_t x = 0;
-                    std::memcpy(&x, b, bps > 8 ? 8 : bps);
-                    v = (double)x;
-                }
-                mf(i, j, k) = (v > t) ? value_if_true : value_if_false;
-            }
-        }
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.nGrow() == 0 && mf.validBox() == this->box(),
+                                     "HDF5Reader: the destination must be a ghost-free field over the dataset box");
+    thresholdInto<int>(t, value_if_true, value_if_false, 0, m_depth, &mf(0, 0, 0));
+}
+
+void HDF5Reader::thresholdPlanesU8(double t, unsigned char value_if_true, unsigned char value_if_false, int z_begin,
+                                   int nz, unsigned char* out) const {
+    if (!m_is_read) amrex::Abort("[HDF5Reader::thresholdPlanesU8] metadata not read");
+    if (z_begin < 0 || nz < 0 || z_begin + nz > m_depth) amrex::Abort("[HDF5Reader::thresholdPlanesU8] plane range outside the dataset");
+    thresholdInto<unsigned char>(t, value_if_true, value_if_false, z_begin, nz, out);
 }
 
 void HDF5Reader::threshold(double t, amrex::iMultiFab& mf) const { threshold(t, 1, 0, mf); }

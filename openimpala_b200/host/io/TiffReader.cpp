@@ -15,7 +15,9 @@
 #include <iomanip>
 #include <map>
 #include <sstream>
+#include <memory>
 #include <stdexcept>
+#include <thread>
 
 #include <zlib.h>
 
@@ -324,117 +326,192 @@ bool TiffReader::readFileSequence(const std::string& base_pattern, int num_files
     return true;
 }
 
+// ---- plane decode + threshold ------------------------------------------------------------
+// One directory (= one z-plane) is handed out as row spans of decoded sample bytes: row j,
+// columns [x0, x0 + n), `src` pointing at the first sample of the span (bit-packed data: at
+// the byte holding bit `bit0` of the span's bit string), `avail` bytes readable from `src`.
+// Samples past the decoded data read as 0.0, as in the reference's bounds-checked loops
+// (src/io/TiffReader.cpp:376-381, :419-432).
+namespace {
+
+struct RowSpan {
+    int j, x0, n;
+    const unsigned char* src;
+    size_t avail, bit0;
+};
+
+template <class RowFn>
+void decodeDirectoryRows(TiffFile& f, const Ifd& d, int W, int H, int bps, std::vector<unsigned char>& buf, RowFn&& row) {
+    const size_t bytes_per_sample = bps >= 8 ? (size_t)bps / 8 : 1;
+    const bool file_little = f.littleEndian();
+    const uint64_t comp = d.get(T_COMPRESSION, 1), pred = d.get(T_PREDICTOR, 1);
+    if (d.arr(T_TILEOFFSETS)) {                                   // tiled, reference :354-393
+        const int tw = (int)d.get(T_TILEWIDTH, 0), th = (int)d.get(T_TILELENGTH, 0);
+        const auto* offs = d.arr(T_TILEOFFSETS);
+        const auto* cnts = d.arr(T_TILEBYTECOUNTS);
+        if (tw <= 0 || th <= 0 || !cnts) amrex::Abort("Invalid tile params.");
+        const int tiles_x = (W + tw - 1) / tw;
+        for (size_t t = 0; t < offs->size(); ++t) {
+            buf.resize((size_t)(*cnts)[t]);
+            f.readAt((*offs)[t], buf.data(), buf.size());
+            if (comp != C_NONE || pred != 1)
+                decodeSegment(buf, comp, pred, bps == 1 ? ((size_t)tw * th + 7) / 8 : (size_t)tw * th * bytes_per_sample,
+                              (size_t)tw, bytes_per_sample, file_little);
+            const size_t nbytes = buf.size();
+            const int ox = (int)(t % tiles_x) * tw, oy = (int)(t / tiles_x) * th;
+            const int n = std::min(ox + tw, W) - ox;
+            if (n <= 0) continue;
+            for (int j = oy; j < std::min(oy + th, H); ++j) {
+                if (bps == 1) {                                   // bits run linearly through the tile (:376-381)
+                    row(RowSpan{j, ox, n, buf.data(), nbytes, (size_t)(j - oy) * (size_t)tw});
+                } else {
+                    const size_t off = (size_t)(j - oy) * (size_t)tw * bytes_per_sample;
+                    row(RowSpan{j, ox, n, buf.data() + std::min(off, nbytes), off < nbytes ? nbytes - off : 0, 0});
+                }
+            }
+        }
+    } else {                                                       // strips, reference :394-437
+        uint64_t rps = d.get(T_ROWSPERSTRIP, (uint64_t)H);
+        if (rps == 0 || rps > (uint64_t)H) rps = (uint64_t)H;
+        const auto* offs = d.arr(T_STRIPOFFSETS);
+        const auto* cnts = d.arr(T_STRIPBYTECOUNTS);
+        if (!offs) amrex::Abort("[TiffReader] TIFF directory without strip offsets.");
+        const size_t pitch1 = ((size_t)W + 7) / 8;                 // TIFFScanlineSize for 1-bit data
+        for (size_t s = 0; s < offs->size(); ++s) {
+            const int oy = (int)(s * rps);
+            if (oy >= H) break;
+            const int rows = (int)std::min<uint64_t>(rps, (uint64_t)(H - oy));
+            const size_t expect = bps == 1 ? pitch1 * rows : (size_t)W * rows * bytes_per_sample;
+            if (comp == C_NONE) {
+                buf.resize(cnts && s < cnts->size() ? std::min<size_t>((size_t)(*cnts)[s], expect) : expect);
+                f.readAt((*offs)[s], buf.data(), buf.size());
+            } else {
+                if (!cnts || s >= cnts->size()) amrex::Abort("[TiffReader] compressed TIFF without strip byte counts.");
+                buf.resize((size_t)(*cnts)[s]);
+                f.readAt((*offs)[s], buf.data(), buf.size());
+            }
+            if (comp != C_NONE || pred != 1) decodeSegment(buf, comp, pred, expect, (size_t)W, bytes_per_sample, file_little);
+            const size_t nbytes = buf.size();
+            const size_t row_bytes = bps == 1 ? pitch1 : (size_t)W * bytes_per_sample;
+            for (int j = oy; j < oy + rows; ++j) {
+                const size_t off = (size_t)(j - oy) * row_bytes;
+                row(RowSpan{j, 0, W, buf.data() + std::min(off, nbytes), off < nbytes ? nbytes - off : 0, 0});
+            }
+        }
+    }
+}
+
+int ioThreads(int planes) {
+    int t = (int)std::thread::hardware_concurrency();
+    if (t <= 0) t = 1;
+    t = std::min(t, 16);
+    if (const char* e = std::getenv("OI_IO_THREADS")) t = std::atoi(e);
+    return std::max(1, std::min(t, planes));
+}
+
+}  // namespace
+
+// out[((k - z_begin) * H + j) * W + i] = (double(sample) > thr) ? vt : vf for planes
+// [z_begin, z_begin + nz).  Planes are independent, so they are decoded by up to 16 threads
+// (OI_IO_THREADS), each with its own file handle; 1-, 8- and 16-bit integer samples go
+// through a lookup table of the rule instead of a per-sample conversion.
+template <class OutT>
+void TiffReader::thresholdInto(double thr, OutT vt, OutT vf, int z_begin, int nz, OutT* out) const {
+    const int W = m_width, H = m_height, bps = m_bits_per_sample, fmt = m_sample_format;
+    const size_t bytes_per_sample = bps >= 8 ? (size_t)bps / 8 : 1;
+    std::vector<OutT> lut;
+    if (bps == 1) {
+        lut = {(0.0 > thr) ? vt : vf, (1.0 > thr) ? vt : vf};
+    } else if ((bps == 8 || bps == 16) && (fmt == 1 || fmt == 2)) {
+        lut.resize((size_t)1 << bps);
+        for (size_t v = 0; v < lut.size(); ++v) {
+            const double sv = fmt == 1 ? (double)v : (bps == 8 ? (double)(int8_t)(uint8_t)v : (double)(int16_t)(uint16_t)v);
+            lut[v] = (sv > thr) ? vt : vf;
+        }
+    }
+    const OutT zero_value = (0.0 > thr) ? vt : vf;                 // samples past the decoded data
+    std::vector<Ifd> dirs;
+    if (!m_is_sequence) {
+        TiffFile f(m_filename);
+        dirs = f.directories();                                    // parsed once, shared read-only
+    }
+    const int T = ioThreads(nz);
+    std::vector<std::string> errors((size_t)T);
+    auto work = [&](int t) {
+        try {
+            const int lo = z_begin + (int)((long long)nz * t / T), hi = z_begin + (int)((long long)nz * (t + 1) / T);
+            std::vector<unsigned char> buf;
+            std::unique_ptr<TiffFile> stack;
+            if (!m_is_sequence && lo < hi) stack.reset(new TiffFile(m_filename));
+            for (int k = lo; k < hi; ++k) {
+                std::unique_ptr<TiffFile> single;
+                std::vector<Ifd> one;
+                const Ifd* d = nullptr;
+                TiffFile* f = stack.get();
+                if (m_is_sequence) {
+                    const std::string name = sequenceName(m_base_pattern, m_start_index + k, m_digits, m_suffix);
+                    single.reset(new TiffFile(name));
+                    one = single->directories();
+                    if (one.empty()) throw std::runtime_error("Seq: empty file " + name);
+                    d = &one[0];
+                    f = single.get();
+                } else {
+                    if (k >= (int)dirs.size()) break;
+                    d = &dirs[(size_t)k];
+                }
+                const bool file_little = f->littleEndian();
+                OutT* plane = out + (size_t)(k - z_begin) * (size_t)H * (size_t)W;
+                decodeDirectoryRows(*f, *d, W, H, bps, buf, [&](const RowSpan& r) {
+                    OutT* dst = plane + (size_t)r.j * (size_t)W + (size_t)r.x0;
+                    if (bps == 1) {
+                        for (int i = 0; i < r.n; ++i) {
+                            const size_t lin = r.bit0 + (size_t)i, byte_i = lin >> 3;
+                            dst[i] = byte_i < r.avail ? lut[(r.src[byte_i] >> (7 - (int)(lin & 7))) & 1] : zero_value;
+                        }
+                        return;
+                    }
+                    const int n_ok = (int)std::min<size_t>((size_t)r.n, r.avail / bytes_per_sample);
+                    if (!lut.empty() && bps == 8) {
+                        for (int i = 0; i < n_ok; ++i) dst[i] = lut[r.src[i]];
+                    } else if (!lut.empty()) {                     // 16 bits, file byte order
+                        if (file_little) for (int i = 0; i < n_ok; ++i) dst[i] = lut[(size_t)r.src[2 * i] | ((size_t)r.src[2 * i + 1] << 8)];
+                        else for (int i = 0; i < n_ok; ++i) dst[i] = lut[((size_t)r.src[2 * i] << 8) | (size_t)r.src[2 * i + 1]];
+                    } else {
+                        for (int i = 0; i < n_ok; ++i)
+                            dst[i] = (sampleAsDouble(r.src + (size_t)i * bytes_per_sample, bps, fmt, file_little) > thr) ? vt : vf;
+                    }
+                    for (int i = n_ok; i < r.n; ++i) dst[i] = zero_value;
+                });
+            }
+        } catch (const std::exception& e) {
+            errors[(size_t)t] = e.what();
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    for (const std::string& e : errors)
+        if (!e.empty()) amrex::Abort("[TiffReader] " + e);
+}
+
 void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int v_false, double thr) const {
     if (!m_is_read) amrex::Abort("[TiffReader::readDistributedIntoFab] Metadata not processed.");
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.boxArray().minimalBox() == this->box(), "Dest MF BoxArray domain mismatch.");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nComp() == 1, "Dest MF must have 1 component.");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nGrow() == 0, "Dest MF must have 0 ghost cells.");
-    decodePlanes(0, m_depth, [&](int i, int j, int k, double v) { dest(i, j, k) = (v > thr) ? v_true : v_false; });
+    // a ghost-free field over the image box is one dense x-fastest array
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.validBox() == box(), "Dest MF must cover the image box.");
+    thresholdInto<int>(thr, v_true, v_false, 0, m_depth, &dest(0, 0, 0));
 }
 
 void TiffReader::thresholdPlanesU8(double raw_threshold, unsigned char value_if_true, unsigned char value_if_false,
                                    int z_begin, int nz, unsigned char* out) const {
     if (!m_is_read) amrex::Abort("[TiffReader::thresholdPlanesU8] Metadata not processed.");
     if (z_begin < 0 || nz < 0 || z_begin + nz > m_depth) amrex::Abort("[TiffReader::thresholdPlanesU8] plane range outside the stack.");
-    const size_t W = (size_t)m_width, H = (size_t)m_height;
-    decodePlanes(z_begin, nz, [&](int i, int j, int k, double v) {
-        out[((size_t)(k - z_begin) * H + (size_t)j) * W + (size_t)i] = (v > raw_threshold) ? value_if_true : value_if_false;
-    });
-}
-
-// Decode planes [z_begin, z_begin + nz) and hand every sample to sink(i, j, k, value).
-void TiffReader::decodePlanes(int z_begin, int nz, const std::function<void(int, int, int, double)>& sink) const {
-    const int W = m_width, H = m_height, bps = m_bits_per_sample;
-    const size_t bytes_per_sample = bps >= 8 ? (size_t)bps / 8 : 1;
-    std::vector<unsigned char> buf;
-
-    auto decodeDirectory = [&](TiffFile& f, const Ifd& d, int k) {
-        const bool file_little = f.littleEndian();
-        const uint64_t comp = d.get(T_COMPRESSION, 1), pred = d.get(T_PREDICTOR, 1);
-        if (d.arr(T_TILEOFFSETS)) {                                   // tiled, reference :354-393
-            const int tw = (int)d.get(T_TILEWIDTH, 0), th = (int)d.get(T_TILELENGTH, 0);
-            const auto* offs = d.arr(T_TILEOFFSETS);
-            const auto* cnts = d.arr(T_TILEBYTECOUNTS);
-            if (tw <= 0 || th <= 0 || !cnts) amrex::Abort("Invalid tile params.");
-            const int tiles_x = (W + tw - 1) / tw;
-            for (size_t t = 0; t < offs->size(); ++t) {
-                buf.resize((size_t)(*cnts)[t]);
-                f.readAt((*offs)[t], buf.data(), buf.size());
-                if (comp != C_NONE || pred != 1)
-                    decodeSegment(buf, comp, pred, bps == 1 ? ((size_t)tw * th + 7) / 8 : (size_t)tw * th * bytes_per_sample,
-                                  (size_t)tw, bytes_per_sample, file_little);
-                const size_t nbytes = buf.size();
-                const int ox = (int)(t % tiles_x) * tw, oy = (int)(t / tiles_x) * th;
-                for (int j = oy; j < std::min(oy + th, H); ++j)
-                    for (int i = ox; i < std::min(ox + tw, W); ++i) {
-                        double v = 0.0;
-                        if (bps == 1) {
-                            const size_t lin = (size_t)(j - oy) * tw + (size_t)(i - ox);
-                            const size_t byte_i = lin / 8; const int bit_i = (int)(lin % 8);
-                            if (byte_i < nbytes) v = (double)((buf[byte_i] >> (7 - bit_i)) & 1);
-                        } else {
-                            const size_t off = ((size_t)(j - oy) * tw + (size_t)(i - ox)) * bytes_per_sample;
-                            if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
-                        }
-                        sink(i, j, k, v);
-                    }
-            }
-        } else {                                                       // strips, reference :394-437
-            uint64_t rps = d.get(T_ROWSPERSTRIP, (uint64_t)H);
-            if (rps == 0 || rps > (uint64_t)H) rps = (uint64_t)H;
-            const auto* offs = d.arr(T_STRIPOFFSETS);
-            const auto* cnts = d.arr(T_STRIPBYTECOUNTS);
-            if (!offs) amrex::Abort("[TiffReader] TIFF directory without strip offsets.");
-            const size_t pitch1 = ((size_t)W + 7) / 8;                 // TIFFScanlineSize for 1-bit data
-            for (size_t s = 0; s < offs->size(); ++s) {
-                const int oy = (int)(s * rps);
-                if (oy >= H) break;
-                const int rows = (int)std::min<uint64_t>(rps, (uint64_t)(H - oy));
-                const size_t expect = bps == 1 ? pitch1 * rows : (size_t)W * rows * bytes_per_sample;
-                if (comp == C_NONE) {
-                    buf.resize(cnts && s < cnts->size() ? std::min<size_t>((size_t)(*cnts)[s], expect) : expect);
-                    f.readAt((*offs)[s], buf.data(), buf.size());
-                } else {
-                    if (!cnts || s >= cnts->size()) amrex::Abort("[TiffReader] compressed TIFF without strip byte counts.");
-                    buf.resize((size_t)(*cnts)[s]);
-                    f.readAt((*offs)[s], buf.data(), buf.size());
-                }
-                if (comp != C_NONE || pred != 1) decodeSegment(buf, comp, pred, expect, (size_t)W, bytes_per_sample, file_little);
-                const size_t nbytes = buf.size();
-                for (int j = oy; j < oy + rows; ++j)
-                    for (int i = 0; i < W; ++i) {
-                        double v = 0.0;
-                        if (bps == 1) {
-                            const size_t byte_i = (size_t)(j - oy) * pitch1 + (size_t)i / 8;
-                            const int bit_i = i % 8;
-                            if (byte_i < nbytes) v = (double)((buf[byte_i] >> (7 - bit_i)) & 1);
-                        } else {
-                            const size_t off = ((size_t)(j - oy) * W + (size_t)i) * bytes_per_sample;
-                            if (off + bytes_per_sample <= nbytes) v = sampleAsDouble(buf.data() + off, bps, m_sample_format, file_little);
-                        }
-                        sink(i, j, k, v);
-                    }
-            }
-        }
-    };
-
-    try {
-        if (m_is_sequence) {
-            for (int k = z_begin; k < z_begin + nz; ++k) {
-                const std::string name = sequenceName(m_base_pattern, m_start_index + k, m_digits, m_suffix);
-                TiffFile f(name);
-                const std::vector<Ifd> dirs = f.directories();
-                if (dirs.empty()) amrex::Abort("[TiffReader] Seq: empty file " + name);
-                decodeDirectory(f, dirs[0], k);
-            }
-        } else {
-            TiffFile f(m_filename);                                    // opened once, not once per slice
-            const std::vector<Ifd> dirs = f.directories();
-            for (int k = z_begin; k < z_begin + nz && k < (int)dirs.size(); ++k) decodeDirectory(f, dirs[k], k);
-        }
-    } catch (const std::exception& e) {
-        amrex::Abort(std::string("[TiffReader] ") + e.what());
-    }
+    thresholdInto<unsigned char>(raw_threshold, value_if_true, value_if_false, z_begin, nz, out);
 }
 
 void TiffReader::threshold(double raw_threshold, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {

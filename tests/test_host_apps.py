@@ -31,6 +31,14 @@ def run(exe, *args, check=True):
     return r
 
 
+def weighted_checksum(vol01):
+    """tReaders' WeightedChecksum of a thresholded volume [z, y, x] (values 0/1)."""
+    import numpy as np
+    v = np.ascontiguousarray(vol01).reshape(-1).astype(np.uint64)
+    w = (np.arange(v.size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+    return int((w * v).sum(dtype=np.uint64))
+
+
 def field(out, key):
     m = re.search(rf"{key}:\s*(.+)", out)
     assert m, f"{key} not in output"
@@ -52,14 +60,24 @@ def test_readers_match_reference_fixtures(host_bins, mode, args, dims, count1):
     assert int(field(r.stdout, "DirectCount1")[0]) == count1
     if mode == "tiff" and "1bit" in args[0]:
         assert "BitsPerSample: 1 SampleFormat: 1 SamplesPerPixel: 1" in r.stdout   # tTiffReader.cpp
+    if mode in ("raw", "hdf5"):
+        # the HDF5 sample's payload is the RAW sample's bytes: same voxels in the same places,
+        # through threshold() and through the streamed-upload entry point (11 planes at a time)
+        import numpy as np
+        raw = np.fromfile(os.path.join(GOLDEN, "SampleData_2Phase_stack_3d_uint8.raw"), dtype=np.uint8).reshape(100, 100, 100)
+        assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(raw > 0.5)
+        r2 = run("tReaders", f"mode={mode}", "gpu_count=0", "u8_chunk=11", *args)
+        assert field(r2.stdout, "U8ChunkMismatches") == ["0"]
 
 
 def test_readers_agree_with_oracle_decoder(host_bins):
     from oracle import oi_numpy as o
     for name in ("SampleData_2Phase_stack_3d_1bit.tif", "spheres.tif", "SampleData_2Phase_squared.tif"):
         ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, name)))
-        r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile=tests/golden/{name}")
+        r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile=tests/golden/{name}", "u8_chunk=7")
+        assert field(r.stdout, "U8ChunkMismatches") == ["0"]         # streamed-upload entry point, 7 planes at a time
         assert int(field(r.stdout, "DirectCount1")[0]) == int(ph.sum())
+        assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(ph)
 
 
 @pytest.mark.parametrize("compression", ["tiff_lzw", "tiff_adobe_deflate", "packbits"])
@@ -91,9 +109,11 @@ def test_compressed_tiff_stacks(host_bins, tmp_path, compression, kind):
         pages = [Image.fromarray(p * 255).convert("1") for p in vol]
     f = tmp_path / f"stack_{kind}_{compression}.tif"
     pages[0].save(f, save_all=True, append_images=pages[1:], compression=compression, **extra)
-    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}")
+    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}", "u8_chunk=3")
     assert [int(v) for v in field(r.stdout, "Dims")] == [nx, ny, nz]
     assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > thr).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(vol > thr)
+    assert field(r.stdout, "U8ChunkMismatches") == ["0"]
 
 
 def _write_tiff(path, vol, *, big=False, little=True, tile=None, rows_per_strip=None):
@@ -194,9 +214,11 @@ def test_tiff_container_variants(host_bins, tmp_path, variant):
     _write_tiff(f, vol, big="bigtiff" in variant, little="_le_" in variant,
                 tile=(16, 16) if "tiles" in variant else None,
                 rows_per_strip=5 if "multi_strip" in variant else None)
-    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}")
+    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", f"threshold={thr}", "u8_chunk=3")
     assert [int(v) for v in field(r.stdout, "Dims")] == [nx, ny, nz]
     assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > thr).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(vol > thr)
+    assert field(r.stdout, "U8ChunkMismatches") == ["0"]
 
 
 def test_tiff_file_sequence(host_bins, tmp_path):
@@ -207,9 +229,40 @@ def test_tiff_file_sequence(host_bins, tmp_path):
     for k in range(6):
         _write_tiff(tmp_path / f"slice_{k + 3:04d}.tif", vol[k:k + 1])
     r = run("tReaders", "mode=tiffseq", "gpu_count=0", f"tifffile={tmp_path / 'slice_'}", "num_files=6",
-            "start_index=3", "digits=4", "threshold=99")
+            "start_index=3", "digits=4", "threshold=99", "u8_chunk=4")
+    assert field(r.stdout, "U8ChunkMismatches") == ["0"]
     assert [int(v) for v in field(r.stdout, "Dims")] == [18, 12, 6]
     assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > 99).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(vol > 99)
+
+
+@pytest.mark.parametrize("datatype,dtype,thr", [
+    ("UINT8", "u1", 100.5), ("INT16_LE", "<i2", -3.5), ("UINT16_LE", "<u2", 30000.0), ("UINT16_BE", ">u2", 30000.0),
+    ("FLOAT32_LE", "<f4", 0.25),
+])
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_raw_reader_types_and_threads(host_bins, tmp_path, datatype, dtype, thr, threads, monkeypatch):
+    """RawReader::threshold for the 8/16-bit lookup-table paths and the generic per-sample path,
+    single- and multi-threaded (OI_IO_THREADS), against numpy: (double(v) > thr) ? 1 : 0
+    (reference src/io/RawReader.cpp:379-491)."""
+    import numpy as np
+    rng = np.random.default_rng(17)
+    shape = (9, 11, 13)                                           # z, y, x
+    if dtype.endswith("f4"):
+        a = rng.standard_normal(shape).astype(dtype)
+    else:
+        info = np.iinfo(np.dtype(dtype))
+        a = rng.integers(info.min, info.max, size=shape, endpoint=True).astype(dtype)
+    path = tmp_path / "vol.raw"
+    a.tofile(path)
+    monkeypatch.setenv("OI_IO_THREADS", threads)
+    r = run("tReaders", "mode=raw", f"rawfile={path}", "width=13", "height=11", "depth=9", f"datatype={datatype}",
+            f"threshold={thr}", "gpu_count=0", "u8_chunk=4")
+    assert "TEST PASSED" in r.stdout
+    assert field(r.stdout, "U8ChunkMismatches") == ["0"]
+    assert field(r.stdout, "Dims") == ["13", "11", "9"]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((a.astype(np.float64) > thr).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(a.astype(np.float64) > thr)
 
 
 def test_dat_reader(host_bins, tmp_path):
@@ -225,6 +278,7 @@ def test_dat_reader(host_bins, tmp_path):
     r = run("tReaders", "mode=dat", "gpu_count=0", f"datfile={f}", "threshold=1999")
     assert [int(v) for v in field(r.stdout, "Dims")] == [9, 7, 5]
     assert int(field(r.stdout, "DirectCount1")[0]) == int((vol > 1999).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(vol > 1999)
     assert [int(v) for v in field(r.stdout, "RawCorner")] == [int(vol[0, 0, 0]), int(vol[-1, -1, -1])]
     # truncated payload and bad header are rejected
     (tmp_path / "short.dat").write_bytes(np.array([9, 7, 5], dtype="<i4").tobytes() + b"\0" * 10)
