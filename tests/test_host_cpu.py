@@ -332,3 +332,16 @@ def test_coarse_tail_cycle_on_the_host(tail_emul, dims0, factors, periodic, deg,
     assert scale > 0
     assert float(np.abs(got - ref).max()) <= 2e-5 * scale       # fp32 cycle against the float64 reference
     assert not got[levels[0]["dg"] == 0].any()                  # empty aggregates stay zero
+
+
+# ------------------------------------------------------------------ AMReX stand-in bulk routines
+def test_amrex_shim_bulk_routines(tmp_path):
+    """FillBoundary (ghost shell only), Copy (row copies) and min / max / sum of the AMReX
+    stand-in against naive per-cell loops: 72 cases over ghost widths, periodic flags, a
+    non-zero lower corner and degenerate extents (tests/cpu_emul/shim_check.cpp)."""
+    import subprocess
+    exe = tmp_path / "shim_check"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "openimpala_b200", "host", "amrex_shim"),
+                    os.path.join(ROOT, "tests", "cpu_emul", "shim_check.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
