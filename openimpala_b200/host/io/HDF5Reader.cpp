@@ -2,16 +2,24 @@
 // reference reader: dims (Z,Y,X) -> box (X,Y,Z) (src/io/HDF5Reader.cpp:136-153),
 // native-type dispatch u8/i8/u16/i16/u32/i32/u64/i64/f32/f64 (:359-383),
 // threshold rule double(v) > t ? a : b (:321-326).
+// Layouts: contiguous, and chunked through the version-1 B-tree chunk index with the
+// deflate (1), shuffle (2) and fletcher32 (3) filters -- what libhdf5 resolves behind
+// DataSet::read for the reference (:255-402).  Not handled: compact layout, new-style
+// groups / object headers (libver "latest"), szip / nbit / scale-offset filters, non-zero
+// fill values of unallocated chunks.
 #include "HDF5Reader.H"
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
 #include <vector>
+
+#include <zlib.h>
 
 #include <AMReX_Utility.H>
 
@@ -113,6 +121,29 @@ public:
         return walk(btree + base_addr, heap_data, name);
     }
     uint64_t baseAddr() const { return base_addr; }
+    // every chunk below a version-1 B-tree node of type 1 (raw data chunks); `ndims` is the
+    // dataset rank + 1 (the element-size dimension has an offset too)
+    template <class Sink>
+    void walkChunks(uint64_t node, int ndims, Sink&& sink, int depth = 0) {
+        char sig[4];
+        if (depth > 64 || !readAt(node, sig, 4) || std::memcmp(sig, "TREE", 4) != 0)
+            throw std::runtime_error("HDF5: bad chunk B-tree node");
+        unsigned char h[4];
+        readAt(node + 4, h, 4);
+        if (h[0] != 1) throw std::runtime_error("HDF5: chunk index is not a raw-data B-tree");
+        const int level = h[1], used = h[2] | (h[3] << 8);
+        const uint64_t key_bytes = 8 + 8 * (uint64_t)ndims;
+        uint64_t p = node + 8 + 2 * (uint64_t)so;
+        for (int e = 0; e < used; ++e) {
+            const uint32_t bytes = (uint32_t)rd(p, 4), mask = (uint32_t)rd(p + 4, 4);
+            uint64_t off[8] = {0};
+            for (int d = 0; d < ndims && d < 8; ++d) off[d] = rd(p + 8 + 8 * (uint64_t)d, 8);
+            const uint64_t child = rd(p + key_bytes, so) + base_addr;
+            if (level == 0) sink(child, bytes, mask, off);
+            else walkChunks(child, ndims, sink, depth + 1);
+            p += key_bytes + (uint64_t)so;
+        }
+    }
 private:
     uint64_t walk(uint64_t node, uint64_t heap_data, const std::string& name) {
         char sig[4];
@@ -184,6 +215,10 @@ bool HDF5Reader::readMetadataInternal() {
         }
         const int so = f.sizeOffsets(), sl = f.sizeLengths();
         bool have_space = false, have_type = false, have_layout = false;
+        uint64_t chunk_btree = UINT64_MAX;
+        m_chunked = false;
+        m_filters.clear();
+        m_chunks.clear();
         for (const auto& m : f.messages(obj)) {
             const unsigned char* d = m.data.data();
             if (m.type == 0x0001 && m.data.size() >= 8) {                 // dataspace
@@ -204,8 +239,21 @@ bool HDF5Reader::readMetadataInternal() {
                 have_type = true;
             } else if (m.type == 0x0008 && m.data.size() >= 2) {          // data layout
                 const int version = d[0];
-                if (version == 3) {
-                    if (d[1] != 1) throw std::runtime_error("only contiguous dataset layout is supported without libhdf5");
+                if (version == 3 && d[1] == 2) {                          // chunked: rank+1, B-tree address, chunk dims
+                    const int ndims = d[2];
+                    if (ndims != 4 || m.data.size() < (size_t)(3 + so + 4 * ndims))
+                        throw std::runtime_error("chunked layout of a dataset that is not rank 3");
+                    m_chunked = true;
+                    chunk_btree = 0;
+                    for (int q = 0; q < so; ++q) chunk_btree |= (uint64_t)d[3 + q] << (8 * q);
+                    for (int r = 0; r < 3; ++r) {
+                        const unsigned char* c = d + 3 + so + 4 * r;
+                        m_chunk_dims[r] = (uint64_t)c[0] | ((uint64_t)c[1] << 8) | ((uint64_t)c[2] << 16) | ((uint64_t)c[3] << 24);
+                        if (m_chunk_dims[r] == 0) throw std::runtime_error("zero chunk extent");
+                    }
+                    m_data_offset = 0;
+                } else if (version == 3) {
+                    if (d[1] != 1) throw std::runtime_error("compact dataset layout is not supported without libhdf5");
                     m_data_offset = 0;
                     for (int q = 0; q < so; ++q) m_data_offset |= (uint64_t)d[2 + q] << (8 * q);
                 } else if (version == 1 || version == 2) {
@@ -215,12 +263,40 @@ bool HDF5Reader::readMetadataInternal() {
                 } else throw std::runtime_error("unsupported layout message version");
                 m_data_offset += f.baseAddr();
                 have_layout = true;
-            } else if (m.type == 0x000B) {
-                if (m.data.size() >= 2 && d[1] > 0) throw std::runtime_error("filtered (compressed) datasets need libhdf5");
+            } else if (m.type == 0x000B && m.data.size() >= 2) {         // filter pipeline, versions 1 and 2
+                const int version = d[0], nf = d[1];
+                size_t p = version == 1 ? 8 : 2;
+                for (int q = 0; q < nf; ++q) {
+                    if (p + (version == 1 ? 8 : 6) > m.data.size()) throw std::runtime_error("truncated filter pipeline message");
+                    Filter flt;
+                    flt.id = d[p] | (d[p + 1] << 8);
+                    p += 2;
+                    size_t name_len = 0;
+                    if (version == 1 || flt.id >= 256) { name_len = d[p] | (d[p + 1] << 8); p += 2; }
+                    p += 2;                                               // flags
+                    const int ncl = d[p] | (d[p + 1] << 8);
+                    p += 2;
+                    p += version == 1 ? (name_len + 7) / 8 * 8 : name_len;
+                    if (p + 4 * (size_t)ncl > m.data.size()) throw std::runtime_error("truncated filter pipeline message");
+                    for (int c = 0; c < ncl; ++c, p += 4)
+                        flt.client.push_back((uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24));
+                    if (version == 1 && (ncl & 1)) p += 4;
+                    if (flt.id < 1 || flt.id > 3)
+                        throw std::runtime_error("HDF5 filter " + std::to_string(flt.id) + " (only deflate, shuffle and fletcher32 are built in)");
+                    m_filters.push_back(flt);
+                }
             }
         }
         if (!(have_space && have_type && have_layout)) throw std::runtime_error("incomplete dataset header");
         if (m_width <= 0 || m_height <= 0 || m_depth <= 0) throw std::runtime_error("bad dataset dimensions");
+        if (!m_chunked && !m_filters.empty()) throw std::runtime_error("filters on a dataset that is not chunked");
+        const uint64_t undef_addr = so >= 8 ? UINT64_MAX : ((1ull << (8 * so)) - 1);
+        if (m_chunked && chunk_btree != UINT64_MAX && chunk_btree != undef_addr) {   // undefined address: no chunk was ever written
+            f.walkChunks(chunk_btree + f.baseAddr(), 4, [&](uint64_t addr, uint32_t bytes, uint32_t mask, const uint64_t* off) {
+                if (off[0] >= (uint64_t)m_depth || off[1] >= (uint64_t)m_height || off[2] >= (uint64_t)m_width) return;
+                m_chunks.push_back(Chunk{addr, bytes, mask, {off[0], off[1], off[2]}});
+            });
+        }
     } catch (const std::exception& e) {
         amrex::Warning(std::string("[HDF5Reader] ") + e.what());
         return false;
@@ -255,13 +331,120 @@ void HDF5Reader::thresholdInto(double t, OutT vt, OutT vf, int z_begin, int nz, 
             lut[v] = (sv > t) ? vt : vf;
         }
     }
+    // n samples at src (file byte order) -> thresholded values
+    auto convert = [&](const unsigned char* src, size_t n, OutT* dst) {
+        if (!lut.empty() && bps == 1) {
+            for (size_t q = 0; q < n; ++q) dst[q] = lut[src[q]];
+        } else if (!lut.empty()) {
+            if (!m_type_big_endian) for (size_t q = 0; q < n; ++q) dst[q] = lut[(size_t)src[2 * q] | ((size_t)src[2 * q + 1] << 8)];
+            else for (size_t q = 0; q < n; ++q) dst[q] = lut[((size_t)src[2 * q] << 8) | (size_t)src[2 * q + 1]];
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                unsigned char b[8] = {0};
+                const unsigned char* p = src + i * bps;
+                for (size_t q = 0; q < bps && q < 8; ++q) b[q] = m_type_big_endian ? p[bps - 1 - q] : p[q];
+                double v = 0.0;
+                if (m_type_class == 1) {
+                    if (bps == 4) { float x; std::memcpy(&x, b, 4); v = (double)x; }
+                    else if (bps == 8) { std::memcpy(&v, b, 8); }
+                } else if (m_type_signed) {
+                    if (bps == 4) { int32_t x; std::memcpy(&x, b, 4); v = (double)x; }
+                    else if (bps == 8) { int64_t x; std::memcpy(&x, b, 8); v = (double)x; }
+                } else {
+                    uint64_t x = 0;
+                    std::memcpy(&x, b, bps > 8 ? 8 : bps);
+                    v = (double)x;
+                }
+                dst[i] = (v > t) ? vt : vf;
+            }
+        }
+    };
     int T = (int)std::thread::hardware_concurrency();
     if (T <= 0) T = 1;
     T = std::min(T, 16);
     if (const char* e = std::getenv("OI_IO_THREADS")) T = std::atoi(e);
+    auto run_threads = [&](int n_threads, const std::function<void(int)>& work) {
+        if (n_threads <= 1) { work(0); return; }
+        std::vector<std::thread> pool;
+        for (int w = 0; w < n_threads; ++w) pool.emplace_back(work, w);
+        for (auto& th : pool) th.join();
+    };
+
+    if (m_chunked) {
+        // unallocated chunks read as the fill value (0); allocated ones are read, run backwards
+        // through the filter pipeline and thresholded into their part of the output
+        const OutT fill = (0.0 > t) ? vt : vf;
+        std::fill(out, out + (size_t)nz * plane, fill);
+        std::vector<const Chunk*> todo;
+        for (const Chunk& c : m_chunks)
+            if (c.offset[0] < (uint64_t)(z_begin + nz) && c.offset[0] + m_chunk_dims[0] > (uint64_t)z_begin) todo.push_back(&c);
+        const size_t chunk_elems = (size_t)(m_chunk_dims[0] * m_chunk_dims[1] * m_chunk_dims[2]);
+        const size_t chunk_bytes = chunk_elems * bps;
+        const int TC = std::max(1, std::min<int>(T, (int)todo.size()));
+        std::vector<std::string> errors((size_t)TC);
+        run_threads(TC, [&](int w) {
+            try {
+                std::ifstream in(m_filename, std::ios::binary);
+                if (!in) throw std::runtime_error("cannot reopen " + m_filename);
+                std::vector<unsigned char> raw, data(chunk_bytes), tmp;
+                for (size_t ci = (size_t)w; ci < todo.size(); ci += (size_t)TC) {
+                    const Chunk& c = *todo[ci];
+                    raw.resize(c.bytes);
+                    in.clear();
+                    in.seekg((std::streamoff)c.address);
+                    in.read(reinterpret_cast<char*>(raw.data()), (std::streamsize)raw.size());
+                    if ((size_t)in.gcount() != raw.size()) throw std::runtime_error("chunk past the end of the file");
+                    // undo the pipeline, last filter first; bit q of the mask: filter q was skipped for this chunk
+                    for (int q = (int)m_filters.size() - 1; q >= 0; --q) {
+                        if (c.filter_mask & (1u << q)) continue;
+                        const Filter& flt = m_filters[(size_t)q];
+                        if (flt.id == 3) {                               // fletcher32: checksum appended
+                            if (raw.size() < 4) throw std::runtime_error("fletcher32 chunk shorter than its checksum");
+                            raw.resize(raw.size() - 4);
+                        } else if (flt.id == 1) {                        // deflate
+                            tmp.resize(chunk_bytes + 4);                 // (+4: a checksum filter may sit before deflate)
+                            uLongf len = (uLongf)tmp.size();
+                            if (uncompress(tmp.data(), &len, raw.data(), (uLong)raw.size()) != Z_OK)
+                                throw std::runtime_error("corrupt deflate stream in a chunk");
+                            tmp.resize((size_t)len);
+                            raw.swap(tmp);
+                        } else if (flt.id == 2) {                        // shuffle: byte planes of the elements
+                            const size_t es = flt.client.empty() ? bps : (size_t)flt.client[0];
+                            if (es > 1) {
+                                const size_t ne = raw.size() / es;
+                                tmp.resize(raw.size());
+                                for (size_t bq = 0; bq < es; ++bq)
+                                    for (size_t i = 0; i < ne; ++i) tmp[i * es + bq] = raw[bq * ne + i];
+                                for (size_t r = ne * es; r < raw.size(); ++r) tmp[r] = raw[r];
+                                raw.swap(tmp);
+                            }
+                        }
+                    }
+                    if (raw.size() < chunk_bytes) throw std::runtime_error("chunk holds fewer bytes than its extents");
+                    // the part of the chunk inside the dataset and inside [z_begin, z_begin + nz)
+                    const uint64_t z0 = std::max<uint64_t>(c.offset[0], (uint64_t)z_begin);
+                    const uint64_t z1 = std::min<uint64_t>({c.offset[0] + m_chunk_dims[0], (uint64_t)m_depth, (uint64_t)(z_begin + nz)});
+                    const uint64_t y1 = std::min<uint64_t>(c.offset[1] + m_chunk_dims[1], (uint64_t)m_height);
+                    const uint64_t x1 = std::min<uint64_t>(c.offset[2] + m_chunk_dims[2], (uint64_t)m_width);
+                    for (uint64_t z = z0; z < z1; ++z)
+                        for (uint64_t y = c.offset[1]; y < y1; ++y) {
+                            const size_t src_elem = (size_t)(((z - c.offset[0]) * m_chunk_dims[1] + (y - c.offset[1])) * m_chunk_dims[2]);
+                            OutT* dst = out + ((size_t)(z - (uint64_t)z_begin) * (size_t)m_height + (size_t)y) * (size_t)m_width + (size_t)c.offset[2];
+                            convert(raw.data() + src_elem * bps, (size_t)(x1 - c.offset[2]), dst);
+                        }
+                }
+            } catch (const std::exception& e) {
+                errors[(size_t)w] = e.what();
+            }
+        });
+        for (const std::string& e : errors)
+            if (!e.empty()) amrex::Abort("[HDF5Reader::threshold] " + e);
+        return;
+    }
+
     T = std::max(1, std::min(T, nz));
     std::vector<std::string> errors((size_t)T);
-    auto work = [&](int w) {
+    run_threads(T, [&](int w) {
         const int lo = z_begin + (int)((long long)nz * w / T), hi = z_begin + (int)((long long)nz * (w + 1) / T);
         if (lo >= hi) return;
         std::ifstream in(m_filename, std::ios::binary);
@@ -272,42 +455,9 @@ void HDF5Reader::thresholdInto(double t, OutT vt, OutT vf, int z_begin, int nz, 
             in.seekg((std::streamoff)(m_data_offset + (uint64_t)k * plane * bps));
             in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size());
             if ((size_t)in.gcount() != buf.size()) std::memset(buf.data() + in.gcount(), 0, buf.size() - (size_t)in.gcount());
-            OutT* dst = out + (size_t)(k - z_begin) * plane;
-            const unsigned char* src = buf.data();
-            if (!lut.empty() && bps == 1) {
-                for (size_t q = 0; q < plane; ++q) dst[q] = lut[src[q]];
-            } else if (!lut.empty()) {
-                if (!m_type_big_endian) for (size_t q = 0; q < plane; ++q) dst[q] = lut[(size_t)src[2 * q] | ((size_t)src[2 * q + 1] << 8)];
-                else for (size_t q = 0; q < plane; ++q) dst[q] = lut[((size_t)src[2 * q] << 8) | (size_t)src[2 * q + 1]];
-            } else {
-                for (size_t i = 0; i < plane; ++i) {
-                    unsigned char b[8] = {0};
-                    const unsigned char* p = src + i * bps;
-                    for (size_t q = 0; q < bps && q < 8; ++q) b[q] = m_type_big_endian ? p[bps - 1 - q] : p[q];
-                    double v = 0.0;
-                    if (m_type_class == 1) {
-                        if (bps == 4) { float x; std::memcpy(&x, b, 4); v = (double)x; }
-                        else if (bps == 8) { std::memcpy(&v, b, 8); }
-                    } else if (m_type_signed) {
-                        if (bps == 4) { int32_t x; std::memcpy(&x, b, 4); v = (double)x; }
-                        else if (bps == 8) { int64_t x; std::memcpy(&x, b, 8); v = (double)x; }
-                    } else {
-                        uint64_t x = 0;
-                        std::memcpy(&x, b, bps > 8 ? 8 : bps);
-                        v = (double)x;
-                    }
-                    dst[i] = (v > t) ? vt : vf;
-                }
-            }
+            convert(buf.data(), plane, out + (size_t)(k - z_begin) * plane);
         }
-    };
-    if (T == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int w = 0; w < T; ++w) pool.emplace_back(work, w);
-        for (auto& th : pool) th.join();
-    }
+    });
     for (const std::string& e : errors)
         if (!e.empty()) amrex::Abort("[HDF5Reader::threshold] " + e);
 }

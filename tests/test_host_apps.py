@@ -265,6 +265,201 @@ def test_raw_reader_types_and_threads(host_bins, tmp_path, datatype, dtype, thr,
     assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(a.astype(np.float64) > thr)
 
 
+def _write_hdf5(path, name, vol, chunks=None, shuffle=False, gzip=False, fletcher=False, skip_chunk=None,
+                unfiltered_chunk=None, leaf_fanout=5):
+    """A version-0-superblock HDF5 file with one old-style root group and one rank-3 dataset
+    `name`, written from the HDF5 file format specification (no h5py in this image):
+    contiguous, or chunked with a (two-level) version-1 B-tree chunk index and the shuffle /
+    deflate / fletcher32 filters.  skip_chunk: index of a chunk that is never allocated (reads
+    as the fill value 0); unfiltered_chunk: index of a chunk stored with its filter-mask bits
+    set (raw bytes)."""
+    import struct
+    import zlib
+    import numpy as np
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    dt = vol.dtype
+    es = dt.itemsize
+    big = dt.byteorder == ">"
+    buf = bytearray()
+
+    def pad8(b):
+        return b + b"\0" * (-len(b) % 8)
+
+    def msg(mtype, data):
+        data = pad8(data)
+        return struct.pack("<HHB3x", mtype, len(data), 0) + data
+
+    def obj_header(msgs):
+        body = b"".join(msgs)
+        return struct.pack("<BxHII4x", 1, len(msgs), 1, len(body)) + body
+
+    # ---- fixed front matter: superblock (96 bytes), root header, heap, group B-tree, SNOD
+    name_b = name.encode() + b"\0"
+    heap_data = pad8(b"\0") + pad8(name_b)
+    name_off = 8
+    heap_data += struct.pack("<QQ", 1, 16)                        # one free block (next = none, 16 bytes)
+    ROOT_HDR = 96
+    root_hdr_len = 16 + 8 + 16
+    HEAP = ROOT_HDR + root_hdr_len
+    HEAP_DATA = HEAP + 32
+    GTREE = HEAP_DATA + len(heap_data)
+    gtree_len = 8 + 16 + 8 + 8 + 8
+    SNOD = GTREE + gtree_len
+    snod_len = 8 + 40
+    DSET = SNOD + snod_len
+
+    # ---- dataset messages
+    nz, ny, nx = vol.shape
+    dataspace = struct.pack("<BBB5x", 1, 3, 0) + struct.pack("<QQQ", nz, ny, nx)
+    if dt.kind == "f":
+        bits0 = (1 if big else 0) | 0x20
+        dtype_msg = struct.pack("<BBBBI", 0x11, bits0, es * 8 - 1, 0, es)
+        dtype_msg += (struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127) if es == 4 else struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023))
+    else:
+        bits0 = (1 if big else 0) | (0x08 if dt.kind == "i" else 0)
+        dtype_msg = struct.pack("<BBBBI", 0x10, bits0, 0, 0, es) + struct.pack("<HH", 0, es * 8)
+    filters = []
+    if shuffle:
+        filters.append((2, [es]))
+    if gzip:
+        filters.append((1, [4]))
+    if fletcher:
+        filters.append((3, []))
+    msgs_wo_layout = [msg(0x0001, dataspace), msg(0x0003, dtype_msg)]
+    if filters:
+        fp = struct.pack("<BB6x", 1, len(filters))
+        for fid, client in filters:
+            fp += struct.pack("<HHHH", fid, 0, 0, len(client)) + b"".join(struct.pack("<I", c) for c in client)
+            if len(client) & 1:
+                fp += b"\0\0\0\0"
+        msgs_wo_layout.append(msg(0x000B, fp))
+    layout_len = len(msg(0x0008, b"\0" * (27 if chunks else 18)))
+    dset_len = 16 + sum(len(m) for m in msgs_wo_layout) + layout_len
+    DATA = DSET + dset_len                                        # first byte after the dataset header
+
+    tail = bytearray()                                            # everything from DATA on
+    if not chunks:
+        raw = np.ascontiguousarray(vol).tobytes()
+        layout = struct.pack("<BBQQ", 3, 1, DATA, len(raw))
+        tail += raw
+    else:
+        cz, cy, cx = chunks
+        entries = []                                              # (size, mask, (z, y, x), address)
+        idx = 0
+        for z0 in range(0, nz, cz):
+            for y0 in range(0, ny, cy):
+                for x0 in range(0, nx, cx):
+                    block = np.zeros((cz, cy, cx), dtype=dt)
+                    part = vol[z0:z0 + cz, y0:y0 + cy, x0:x0 + cx]
+                    block[:part.shape[0], :part.shape[1], :part.shape[2]] = part
+                    data = block.tobytes()
+                    mask = 0
+                    if idx == unfiltered_chunk:
+                        mask = (1 << len(filters)) - 1
+                    else:
+                        for fid, _ in filters:
+                            if fid == 2 and es > 1:
+                                a = np.frombuffer(data, dtype=np.uint8).reshape(-1, es)
+                                data = np.ascontiguousarray(a.T).tobytes()
+                            elif fid == 1:
+                                data = zlib.compress(data, 4)
+                            elif fid == 3:
+                                data = data + b"\0\0\0\0"
+                    if idx != skip_chunk:
+                        entries.append((len(data), mask, (z0, y0, x0), DATA + len(tail)))
+                        tail += data
+                        tail += b"\0" * (-len(tail) % 8)
+                    idx += 1
+
+        def key(size, mask, off):
+            return struct.pack("<IIQQQQ", size, mask, off[0], off[1], off[2], 0)
+
+        def node(level, ents):                                    # ents: (size, mask, off, child address)
+            b = b"TREE" + struct.pack("<BBHQQ", 1, level, len(ents), UNDEF, UNDEF)
+            for size, mask, off, child in ents:
+                b += key(size, mask, off) + struct.pack("<Q", child)
+            return b + key(0, 0, (nz, ny, nx))                    # closing key
+        leaves = [entries[i:i + leaf_fanout] for i in range(0, len(entries), leaf_fanout)]
+        uppers = []
+        for leaf in leaves:
+            addr = DATA + len(tail)
+            tail += node(0, leaf)
+            uppers.append((leaf[0][0], leaf[0][1], leaf[0][2], addr))
+        if len(uppers) == 1:
+            btree = uppers[0][3]
+        elif uppers:
+            btree = DATA + len(tail)
+            tail += node(1, uppers)
+        else:
+            btree = UNDEF
+        layout = struct.pack("<BBBQIIII", 3, 2, 4, btree, cz, cy, cx, es)
+    dset = obj_header(msgs_wo_layout + [msg(0x0008, layout)])
+    assert len(dset) == dset_len
+
+    eof = DATA + len(tail)
+    sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+    sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    sb += struct.pack("<QQII16x", 0, ROOT_HDR, 0, 0)             # root group symbol table entry
+    assert len(sb) == 96
+    root = obj_header([msg(0x0011, struct.pack("<QQ", GTREE, HEAP))])
+    assert len(root) == root_hdr_len
+    heap = b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), len(heap_data) - 16, HEAP_DATA)
+    gtree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, SNOD, name_off)
+    assert len(gtree) == gtree_len
+    snod = b"SNOD" + struct.pack("<BxH", 1, 1) + struct.pack("<QQII16x", name_off, DSET, 0, 0)
+    assert len(snod) == snod_len
+    buf += sb + root + heap + heap_data + gtree + snod + dset + tail
+    assert len(buf) == eof
+    with open(path, "wb") as fh:
+        fh.write(buf)
+
+
+@pytest.mark.parametrize("case", ["contiguous_u8", "chunked_u8", "chunked_u8_gzip", "chunked_u16_shuffle_gzip",
+                                  "chunked_i16be_gzip_fletcher", "chunked_f32_shuffle_gzip_partial", "chunked_sparse"])
+@pytest.mark.parametrize("threads", ["1", "6"])
+def test_hdf5_chunked_and_filtered(host_bins, tmp_path, case, threads, monkeypatch):
+    """Chunked HDF5 datasets through the version-1 B-tree chunk index with the deflate, shuffle
+    and fletcher32 filters (what libhdf5 resolves for the reference, src/io/HDF5Reader.cpp:255-402),
+    edge chunks that overhang the dataset, a chunk stored unfiltered (filter mask), a chunk that
+    was never allocated (fill value) and a two-level B-tree; files written from the format
+    specification by _write_hdf5 (its contiguous output goes through the code path the
+    reference's real sample file exercises)."""
+    import numpy as np
+    rng = np.random.default_rng(41)
+    shape = (11, 13, 17)                                          # z, y, x: no extent is a multiple of the chunk's
+    kw = {}
+    if case.endswith("_u8") or "u8_gzip" in case or case == "chunked_sparse":
+        vol, thr = rng.integers(0, 255, shape).astype("u1"), 120.5
+    elif "u16" in case:
+        vol, thr = rng.integers(0, 60000, shape).astype("<u2"), 30000.0
+    elif "i16be" in case:
+        vol, thr = rng.integers(-20000, 20000, shape).astype(">i2"), -100.5
+    else:
+        vol, thr = rng.standard_normal(shape).astype("<f4"), 0.1
+    if case != "contiguous_u8":
+        kw["chunks"] = (4, 5, 6)
+    kw["gzip"] = "gzip" in case
+    kw["shuffle"] = "shuffle" in case
+    kw["fletcher"] = "fletcher" in case
+    expect = vol.astype(np.float64)
+    if "partial" in case:
+        kw["unfiltered_chunk"] = 7
+    if case == "chunked_sparse":
+        kw["gzip"] = True
+        kw["skip_chunk"] = 10                                     # 3 x 3 x 3 chunks: index 10 = offsets (4, 0, 6)
+        expect = expect.copy()
+        expect[4:8, 0:5, 6:12] = 0.0
+    f = tmp_path / f"{case}.h5"
+    _write_hdf5(f, "image", vol, **kw)
+    monkeypatch.setenv("OI_IO_THREADS", threads)
+    r = run("tReaders", "mode=hdf5", f"hdf5file={f}", "hdf5dataset=image", f"threshold={thr}", "gpu_count=0", "u8_chunk=3")
+    assert "TEST PASSED" in r.stdout, r.stdout + r.stderr
+    assert [int(v) for v in field(r.stdout, "Dims")] == [17, 13, 11]
+    assert int(field(r.stdout, "DirectCount1")[0]) == int((expect > thr).sum())
+    assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(expect > thr)
+    assert field(r.stdout, "U8ChunkMismatches") == ["0"]
+
+
 def test_dat_reader(host_bins, tmp_path):
     # src/io/DatReader.cpp:60-248: int32 LE (W, H, D) header + uint16 LE voxels, x fastest
     import numpy as np
