@@ -402,7 +402,7 @@ int main(int argc, char* argv[]) {
                 amrex::Array<int, AMREX_SPACEDIM> np = {AMREX_D_DECL(0, 0, 0)};
                 geom_tort.define(geom_full.Domain(), &rb, 0, np.data());
             }
-            // b200.stream_upload = N (TIFF input): skip the int32 iMultiFab on the way to the GPU and
+            // b200.stream_upload = N (TIFF or HDF5 input): skip the int32 iMultiFab on the way to the GPU and
             // decode N planes at a time straight into the pinned staging buffers
             int stream_upload = 0;
             {
@@ -421,6 +421,15 @@ int main(int argc, char* argv[]) {
                     stream_upload, volume_fraction, phase_id, dir, stringToSolverType(solver_str), results_path, vlo, vhi,
                     verbose, write_plotfile != 0);
                 if (verbose >= 1) amrex::Print() << "  (phase field streamed from the TIFF in chunks of " << stream_upload << " planes)\n";
+            } else if (stream_upload > 0 && (ext_l == ".h5" || ext_l == ".hdf5")) {
+                OpenImpala::HDF5Reader reader(input.string(), hdf5_dataset);
+                const double thr = threshold_val;
+                solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
+                    geom_tort, ba, dm,
+                    [&](int z0, int nz, unsigned char* out) { reader.thresholdPlanesU8(thr, 1, 0, z0, nz, out); },
+                    stream_upload, volume_fraction, phase_id, dir, stringToSolverType(solver_str), results_path, vlo, vhi,
+                    verbose, write_plotfile != 0);
+                if (verbose >= 1) amrex::Print() << "  (phase field streamed from the HDF5 dataset in chunks of " << stream_upload << " planes)\n";
             } else {
                 solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
                     geom_tort, ba, dm, mf_phase, volume_fraction, phase_id, dir, stringToSolverType(solver_str),

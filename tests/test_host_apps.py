@@ -706,3 +706,20 @@ def test_diffusion_streamed_tiff_upload(host_bins):
     tau = float(re.search(r"Tortuosity_X: (\S+)", txt).group(1))
     ref = next(c for c in gold["cases"] if c["phase"] == 1 and c["direction"] == 0)["tau"]
     assert abs(tau - ref) <= 1e-6 * ref
+
+
+@pytest.mark.gpu
+def test_diffusion_streamed_hdf5_upload(host_bins):
+    # the same through HDF5Reader::thresholdPlanesU8 (the reference's HDF5 sample: 399 553 voxels of phase 1)
+    r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "filename=SampleData_2Phase_3d.hdf5",
+            "direction=Z", "b200.stream_upload=9", "results_path=gpurun_out/results_stream_h5/")
+    assert "streamed from the HDF5 dataset in chunks of 9 planes" in r.stdout
+    r2 = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "filename=SampleData_2Phase_3d.hdf5",
+             "direction=Z", "results_path=gpurun_out/results_plain_h5/")
+    taus = []
+    for d in ("results_stream_h5", "results_plain_h5"):
+        txt = open(os.path.join(ROOT, "gpurun_out", d, "results.txt")).read()
+        assert "VolumeFraction: 0.399553000" in txt
+        taus.append(float(re.search(r"Tortuosity_Z: (\S+)", txt).group(1)))
+    assert math.isfinite(taus[0]) and taus[0] > 1.0 and abs(taus[0] - taus[1]) <= 1e-9 * taus[1]
+
