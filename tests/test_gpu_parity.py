@@ -231,6 +231,30 @@ def test_sample_image_golden(capi, sample_phase):
         t.close()
 
 
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_sphere_packing_golden(capi, idx):
+    """The BASELINE workload generator at 96^3 ... 256^3 against the C restatement's answers
+    (tests/golden/packing_golden.json, made by make_packing_golden.py with Jacobi-PCG at 1e-11):
+    same packing (sha256), same phase and percolating counts, tau and both fluxes within 1e-6."""
+    import hashlib
+    from openimpala_b200 import synth
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre, VolumeFraction
+    gold = json.load(open(os.path.join(GOLDEN, "packing_golden.json")))
+    case = gold["cases"][idx]
+    ph = synth.sphere_packing(case["n"], 12345, 12, 0.60)
+    assert hashlib.sha256(ph.tobytes()).hexdigest() == case["sha256"]
+    pc, tc = VolumeFraction(ph, 1).value()
+    assert (pc, tc) == (case["phase_count"], case["n"] ** 3)
+    t = TortuosityHypre(None, None, None, ph, pc / tc, 1, Direction.Z, SolverType.FlexGMRES, "", gold["vlo"], gold["vhi"])
+    assert t._n_active == case["n_active"]
+    tau = t.value()                                # default eps 1e-9, maxiter 200
+    assert t.getSolverConverged()
+    assert abs(tau - case["tau"]) <= TAU_RTOL * case["tau"], (case, tau)
+    assert abs(t.getFluxIn() - case["flux_in"]) <= TAU_RTOL * abs(case["flux_in"])
+    assert abs(t.getFluxOut() - case["flux_out"]) <= TAU_RTOL * abs(case["flux_out"])
+    t.close()
+
+
 def test_preconditioner_is_symmetric(capi):
     """PCG needs M = M^T: <M a, b> == <a, M b> on random vectors."""
     ph = _blobs((24, 28, 32), 31, 0.6)

@@ -233,6 +233,28 @@ def test_sample_flexgmres_golden_vs_pcg_golden(gold):
         assert abs(abs(c["flux_in"]) - abs(c["flux_out"])) / avg <= 1e-6      # TortuosityHypre.cpp:794-803
 
 
+def test_packing_golden_fixture(o, oc):
+    """tests/golden/packing_golden.json (the BASELINE generator at 96^3 .. 256^3, C restatement):
+    the smallest case is re-derived here by BOTH restatements, and every case keeps the
+    reference's flux-conservation gate."""
+    import hashlib
+    from openimpala_b200 import synth
+    g = json.load(open(os.path.join(GOLDEN, "packing_golden.json")))
+    assert [c["n"] for c in g["cases"]] == [96, 128, 192, 256]
+    c0 = g["cases"][0]
+    ph = synth.sphere_packing(96, 12345, 12, 0.60)
+    assert hashlib.sha256(ph.tobytes()).hexdigest() == c0["sha256"]
+    assert int((ph == 1).sum()) == c0["phase_count"]
+    rn = o.tortuosity(ph.astype(np.int32), 1, 2, -1.0, 1.0, eps=1e-11)
+    rc = oc.tortuosity(ph.astype(np.int32), 1, 2, -1.0, 1.0, eps=1e-11)
+    assert rn.n_active == rc["n_active"] == c0["n_active"]
+    assert abs(rn.tau - c0["tau"]) <= 1e-9 * c0["tau"] and abs(rc["tau"] - c0["tau"]) <= 1e-9 * c0["tau"]
+    for c in g["cases"]:
+        avg = 0.5 * (abs(c["flux_in"]) + abs(c["flux_out"]))
+        assert abs(abs(c["flux_in"]) - abs(c["flux_out"])) / avg <= 1e-8
+        assert c["oracle_relres"] <= 1e-11 and 1.0 < c["tau"] < 3.0
+
+
 def test_vlo_vhi_independence(oc):
     ph = _blobs((12, 12, 12), 9, 0.65)
     a = oc.tortuosity(ph, 1, 0, -1.0, 1.0, eps=1e-12)["tau"]
