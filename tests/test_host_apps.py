@@ -24,8 +24,9 @@ def host_bins(built_lib):
     return BIN
 
 
-def run(exe, *args, check=True):
-    r = subprocess.run([os.path.join(BIN, exe), *args], cwd=ROOT, capture_output=True, text=True, timeout=600)
+def run(exe, *args, check=True, env=None):
+    r = subprocess.run([os.path.join(BIN, exe), *args], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                       env=None if env is None else {**os.environ, **env})
     if check:
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r
@@ -668,17 +669,16 @@ def test_diffusion_default_method_is_homogenization(host_bins):
     assert abs(float(re.search(r"Deff_xx: (\S+)", txt).group(1)) - ref[0][0]) <= 1e-6
 
 
-@pytest.mark.gpu
-def test_diffusion_rev_study_csv(host_bins):
+def _check_rev_study(results_path, env=None):
     # rev.do_study (Diffusion.cpp:317-504): random sub-volumes as periodic boxes -> one CSV row each;
     # every row must equal the oracle's tensor of that very sub-volume
     import numpy as np
     from oracle import oi_effdiff as oe
     from oracle import oi_numpy as o
     run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/",
-        "results_path=gpurun_out/results_rev/", "rev.do_study=1", "rev.num_samples=2", "rev.sizes=16 24 200",
-        "calculation_method=skip_if_rev", "rev.verbose=0", "verbose=0")
-    lines = open(os.path.join(ROOT, "gpurun_out", "results_rev", "rev_study_Deff.csv")).read().splitlines()
+        f"results_path={results_path}/", "rev.do_study=1", "rev.num_samples=2", "rev.sizes=16 24 200",
+        "calculation_method=skip_if_rev", "rev.verbose=0", "verbose=0", env=env)
+    lines = open(os.path.join(ROOT, results_path, "rev_study_Deff.csv")).read().splitlines()
     assert lines[0] == ("SampleNo,SeedX,SeedY,SeedZ,REV_Size_Target,ActualSizeX,ActualSizeY,ActualSizeZ,"
                         "D_xx,D_yy,D_zz,D_xy,D_xz,D_yz")
     rows = [l.split(",") for l in lines[1:]]
@@ -693,6 +693,16 @@ def test_diffusion_rev_study_csv(host_bins):
         got = [float(v) for v in r[8:14]]
         ref = [D[0][0], D[1][1], D[2][2], D[0][1], D[0][2], D[1][2]]
         assert max(abs(a - b) for a, b in zip(got, ref)) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_diffusion_rev_study_csv(host_bins):
+    _check_rev_study("gpurun_out/results_rev")
+
+
+def test_host_layer_on_the_mock_rev_study(mock_env, tmp_path):
+    # the same driver logic (mt19937 seeding, clipping, CSV) with the device replaced by the mock
+    _check_rev_study(str(tmp_path / "rev"), env=mock_env)
 
 
 @pytest.mark.gpu
@@ -722,4 +732,91 @@ def test_diffusion_streamed_hdf5_upload(host_bins):
         assert "VolumeFraction: 0.399553000" in txt
         taus.append(float(re.search(r"Tortuosity_Z: (\S+)", txt).group(1)))
     assert math.isfinite(taus[0]) and taus[0] > 1.0 and abs(taus[0] - taus[1]) <= 1e-9 * taus[1]
+
+
+# ------------------------------------------------------------------ host layer on a CPU mock of the C-ABI
+@pytest.fixture(scope="module")
+def mock_env(host_bins, tmp_path_factory):
+    """tests/cpu_emul/mock_capi.c: the C-ABI answered on the CPU by the oracle, LD_PRELOADed in
+    front of the real library.  Test infrastructure only -- it lets the readers -> apps -> host
+    classes -> results / plotfiles chain run in the GPU-less build container; the product library
+    itself has no CPU fallback (test_no_gpu_aborts_loudly)."""
+    from oracle import oi_c
+    oi_c.load()
+    out = tmp_path_factory.mktemp("mock_capi") / "libmock_capi.so"
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-o", str(out),
+                    os.path.join(ROOT, "tests", "cpu_emul", "mock_capi.c"), "-L", odir, "-l:liboi_oracle.so",
+                    "-Wl,-rpath," + odir, "-lm"], check=True)
+    return {"LD_PRELOAD": str(out)}
+
+
+def test_host_layer_on_the_mock_flow_through(mock_env, tmp_path):
+    """Diffusion (flow_through, write_plotfile = 1) on the 64^3 sample through readers, VolumeFraction,
+    TortuosityHypre::value() and its NaN/flux-gate tail, results.txt and the plotfile -- the device
+    replaced by the mock, so tau must be the oracle's."""
+    import numpy as np
+    from oracle import oi_c, oi_numpy as o
+    res = tmp_path / "res"
+    r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "filename=SampleData_2Phase_squared.tif",
+            "direction=X Z", "write_plotfile=1", f"results_path={res}/", env=mock_env)
+    ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, "SampleData_2Phase_squared.tif")), 0.5)
+    vals = dict(l.split(": ") for l in open(res / "results.txt").read().splitlines() if not l.startswith("#"))
+    assert list(vals) == ["VolumeFraction", "Tortuosity_X", "Tortuosity_Z"]
+    assert vals["VolumeFraction"] == f"{ph.mean():.9f}"
+    for d, key in ((0, "Tortuosity_X"), (2, "Tortuosity_Z")):
+        ref = oi_c.tortuosity(ph, 1, d, -1.0, 1.0, eps=1e-9)
+        assert abs(float(vals[key]) - ref["tau"]) <= 1e-6 * ref["tau"]
+        h, f = read_amrex_plotfile(str(res / f"tortuosity_solution_{d}"))
+        assert h["names"] == ["solution_potential", "phase_id", "active_mask"] and h["domain"] == [0, 0, 0, 63, 63, 63]
+        mask = f["active_mask"].astype(bool)
+        assert int(mask.sum()) == ref["n_active"]
+        assert np.array_equal(f["phase_id"], ph.astype(np.float64))
+        x = f["solution_potential"]
+        lo = (slice(None), slice(None), 0) if d == 0 else (0, slice(None), slice(None))
+        hi = (slice(None), slice(None), -1) if d == 0 else (-1, slice(None), slice(None))
+        assert np.all(x[lo][mask[lo]] == -1.0) and np.all(x[hi][mask[hi]] == 1.0) and not x[~mask].any()
+    assert "Conservation Check Status: PASS" in r.stdout
+
+
+@pytest.mark.parametrize("kind", ["tiff", "hdf5"])
+def test_host_layer_on_the_mock_streamed_upload(mock_env, tmp_path, kind):
+    """b200.stream_upload: chunks decoded straight into the staging buffers give the same tau as
+    the iMultiFab path, for TIFF and HDF5 input."""
+    name = "SampleData_2Phase_squared.tif" if kind == "tiff" else "SampleData_2Phase_3d.hdf5"
+    taus = []
+    for extra in (["b200.stream_upload=7"], []):
+        res = tmp_path / ("s" if extra else "p")
+        r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", f"filename={name}", "direction=Y",
+                f"results_path={res}/", *extra, env=mock_env)
+        if extra:
+            assert f"streamed from the {'TIFF' if kind == 'tiff' else 'HDF5 dataset'} in chunks of 7 planes" in r.stdout
+        taus.append(float(re.search(r"Tortuosity_Y: (\S+)", open(res / "results.txt").read()).group(1)))
+    assert math.isfinite(taus[0]) and taus[0] == taus[1]
+
+
+def test_host_layer_on_the_mock_homogenization_and_driver(mock_env, tmp_path):
+    """The app's default method (three corrector solves, D_eff tensor, chi plotfiles) and the
+    tTortuosity driver, on the mock."""
+    import numpy as np
+    from oracle import oi_c, oi_numpy as o
+    res = tmp_path / "homog"
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "filename=SampleData_2Phase_squared.tif",
+        "calculation_method=homogenization", "write_plotfile=1", f"results_path={res}/", env=mock_env)
+    txt = open(res / "results.txt").read()
+    ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, "SampleData_2Phase_squared.tif")), 0.5)
+    d = {k: float(v) for k, v in re.findall(r"(Deff_[xyz][xyz]): (\S+)", txt)}
+    assert len(d) == 9
+    ref = oi_c.effdiff_deff_tensor(ph, 1, eps=1e-10)
+    ref = np.asarray(ref[0] if isinstance(ref, tuple) else ref).reshape(3, 3)
+    for ia, a in enumerate("xyz"):
+        assert d[f"Deff_{a}{a}"] > 0.0
+        for ib, b in enumerate("xyz"):
+            assert abs(d[f"Deff_{a}{b}"] - d[f"Deff_{b}{a}"]) <= 1e-7          # tEffectiveDiffusivity.cpp:424-432
+            assert abs(d[f"Deff_{a}{b}"] - ref[ia, ib]) <= 1e-6
+    h, f = read_amrex_plotfile(str(res / "FullDomain_chi_X" / "effdiff_chi_dir0"))      # reference Diffusion.cpp:531-543
+    assert h["names"] == ["chi_k", "active_mask_from_solver"]
+    assert np.array_equal(f["active_mask_from_solver"], (ph == 1).astype(np.float64))
+    r = run("tTortuosity", "tests/inputs/tTortuosity.inputs", env=mock_env)
+    assert "TEST PASSED" in r.stdout or r.returncode == 0
 
