@@ -19,7 +19,7 @@ BIN = os.path.join(ROOT, "openimpala_b200", "bin")
 def host_bins(built_lib):
     from openimpala_b200 import build
     build.build_host()
-    for exe in ("Diffusion", "tTortuosity", "tReaders"):
+    for exe in ("Diffusion", "tTortuosity", "tReaders", "tEffectiveDiffusivity"):
         assert os.path.exists(os.path.join(BIN, exe))
     return BIN
 
@@ -696,6 +696,21 @@ def _check_rev_study(results_path, env=None):
 
 
 @pytest.mark.gpu
+def test_teffectivediffusivity_driver(host_bins):
+    # reference src/props/tEffectiveDiffusivity.cpp: solves converge, tensor symmetric to 1e-7, diagonals >= 0;
+    # plus the device gradient sums against the host's central differences of chi
+    import numpy as np
+    from oracle import oi_c, oi_numpy as o
+    r = run("tEffectiveDiffusivity", "tests/inputs/tEffectiveDiffusivity.inputs")
+    assert "TEST RESULT: PASS" in r.stdout and "D_eff tensor symmetry check: PASS" in r.stdout
+    ph = o.threshold(o.read_tiff_raw(os.path.join(GOLDEN, "SampleData_2Phase_squared.tif")), 0.5)
+    ref = np.asarray(oi_c.effdiff_deff_tensor(ph, 1, eps=1e-10)[0]).reshape(3, 3)
+    rows = re.findall(r"\[(\S+), (\S+), (\S+)\]", r.stdout)
+    got = np.array([[float(v) for v in row] for row in rows[-3:]])
+    assert np.abs(got - ref).max() <= 1e-6
+
+
+@pytest.mark.gpu
 def test_diffusion_rev_study_csv(host_bins):
     _check_rev_study("gpurun_out/results_rev")
 
@@ -819,4 +834,12 @@ def test_host_layer_on_the_mock_homogenization_and_driver(mock_env, tmp_path):
     assert np.array_equal(f["active_mask_from_solver"], (ph == 1).astype(np.float64))
     r = run("tTortuosity", "tests/inputs/tTortuosity.inputs", env=mock_env)
     assert "TEST PASSED" in r.stdout or r.returncode == 0
+    # the reference's tEffectiveDiffusivity checks: three converged solves, symmetric tensor, diagonals >= 0
+    r = run("tEffectiveDiffusivity", "tests/inputs/tEffectiveDiffusivity.inputs", f"resultsdir={tmp_path / 'teff'}",
+            "write_plotfile=1", env=mock_env)
+    assert "TEST RESULT: PASS" in r.stdout and "D_eff tensor symmetry check: PASS" in r.stdout
+    rows = re.findall(r"\[(\S+), (\S+), (\S+)\]", r.stdout)
+    got = np.array([[float(v) for v in row] for row in rows[-3:]])
+    assert np.abs(got - ref).max() <= 1e-6
+    assert sorted(os.listdir(tmp_path / "teff")) == ["effdiff_chi_dir0", "effdiff_chi_dir1", "effdiff_chi_dir2"]
 
