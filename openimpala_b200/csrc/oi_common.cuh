@@ -131,9 +131,9 @@ inline bool first_use_on_this_device(unsigned long long& seen_devices) {
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
-    if (seen_devices & bit) return false;
-    seen_devices |= bit;
-    return true;
+    // (host threads may drive different devices concurrently: atomic read-modify-write)
+    const unsigned long long before = __atomic_fetch_or(&seen_devices, bit, __ATOMIC_ACQ_REL);
+    return (before & bit) == 0;
 }
 
 }  // namespace oi

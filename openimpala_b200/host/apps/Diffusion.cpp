@@ -7,6 +7,9 @@
 //     results.txt.
 //   rev.do_study = 1 (:317-504): D_eff tensors of random sub-volumes -> rev_study_Deff.csv.
 #include <algorithm>
+#include <thread>
+#include <mutex>
+#include <atomic>
 #include <filesystem>
 #include <fstream>
 #include <iomanip>
@@ -21,6 +24,8 @@
 #include <AMReX.H>
 #include <AMReX_ParmParse.H>
 #include <AMReX_Print.H>
+
+#include <openimpala_b200.h>
 
 #include "../io/HDF5Reader.H"
 #include "../io/RawReader.H"
@@ -210,6 +215,9 @@ int main(int argc, char* argv[]) {
                     csv << "SampleNo,SeedX,SeedY,SeedZ,REV_Size_Target,ActualSizeX,ActualSizeY,ActualSizeZ,D_xx,D_yy,D_zz,D_xy,D_xz,D_yz\n";
                     std::mt19937 gen(amrex::ParallelDescriptor::MyProc() + 12345 + rev_num_samples);     // :341
                     const auto st_rev = static_cast<OpenImpala::EffectiveDiffusivityHypre::SolverType>(stringToSolverType(rev_solver_str));
+                    // (1) the sub-volumes, drawn in the reference's order from its generator
+                    struct RevJob { int sample; int target; amrex::IntVect seed_lo; amrex::Box bx; amrex::Real D[3][3]; };
+                    std::vector<RevJob> jobs;
                     for (int s_idx = 0; s_idx < rev_num_samples; ++s_idx) {
                         for (int target : sizes) {
                             amrex::IntVect seed_lo;
@@ -227,52 +235,89 @@ int main(int argc, char* argv[]) {
                                                    std::to_string(target) + " due to small/empty box after intersection");
                                 continue;
                             }
-                            if (rev_verbose >= 1)
-                                amrex::Print() << " REV Sample " << s_idx + 1 << ", Target Size " << target << ", Seed Lo (global): "
-                                               << seed_lo << ", Actual REV Box (global): " << bx << std::endl;
-                            // the sub-volume as its own periodic box with origin 0 (:377-420)
-                            const amrex::Box rel(amrex::IntVect(0, 0, 0), bx.bigEnd() - bx.smallEnd());
-                            amrex::Geometry geom_rev;
-                            amrex::RealBox rb_rev({AMREX_D_DECL(0.0, 0.0, 0.0)},
-                                                  {AMREX_D_DECL(amrex::Real(rel.length(0)), amrex::Real(rel.length(1)), amrex::Real(rel.length(2)))});
-                            amrex::Array<int, AMREX_SPACEDIM> per_rev = {AMREX_D_DECL(1, 1, 1)};
-                            geom_rev.define(rel, &rb_rev, 0, per_rev.data());
-                            amrex::BoxArray ba_rev(rel);
-                            ba_rev.maxSize(box_size);
-                            amrex::DistributionMapping dm_rev(ba_rev);
-                            amrex::iMultiFab mf_rev(ba_rev, dm_rev, 1, 1);
-                            mf_rev.setVal(0);
-                            for (int k = rel.smallEnd(2); k <= rel.bigEnd(2); ++k)
-                                for (int j = rel.smallEnd(1); j <= rel.bigEnd(1); ++j)
-                                    for (int i = rel.smallEnd(0); i <= rel.bigEnd(0); ++i)
-                                        mf_rev(i, j, k, 0) = mf_phase(i + bx.smallEnd(0), j + bx.smallEnd(1), k + bx.smallEnd(2), 0);
-                            mf_rev.FillBoundary(geom_rev.periodicity());
-                            amrex::Real D[3][3];
-                            for (auto& row : D) for (auto& v : row) v = std::numeric_limits<amrex::Real>::quiet_NaN();
-                            amrex::Real Dtmp[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-                            bool all_ok = true;
-                            const long long n_rev = rel.numPts();
-                            const OpenImpala::Direction dirs3[3] = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
-                            for (int c = 0; c < 3 && all_ok; ++c) {
-                                OpenImpala::EffectiveDiffusivityHypre solver(geom_rev, ba_rev, dm_rev, mf_rev, phase_id, dirs3[c], st_rev,
-                                                                             results_path, rev_verbose > 1 ? rev_verbose : 0, rev_write_plotfiles != 0);
-                                if (!solver.solve()) {
-                                    all_ok = false;
-                                    if (rev_verbose >= 1) amrex::Print() << "    REV Chi solve FAILED for dir " << c << std::endl;
-                                    break;
-                                }
-                                amrex::Real sums[3];
-                                long long n_active = 0;
-                                solver.gradientSums(sums, n_active);
-                                for (int r = 0; r < 3; ++r) Dtmp[r][c] = ((r == c ? (amrex::Real)n_active : 0.0) - sums[r]) / (amrex::Real)n_rev;
-                            }
-                            if (all_ok) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) D[r][c] = Dtmp[r][c];
-                            csv << s_idx + 1 << "," << seed_lo[0] << "," << seed_lo[1] << "," << seed_lo[2] << "," << target << ","
-                                << bx.length(0) << "," << bx.length(1) << "," << bx.length(2) << "," << std::fixed << std::setprecision(8)
-                                << D[0][0] << "," << D[1][1] << "," << D[2][2] << "," << D[0][1] << "," << D[0][2] << "," << D[1][2] << "\n";
-                            csv.flush();
+                            RevJob job{s_idx + 1, target, seed_lo, bx, {}};
+                            for (auto& row : job.D) for (auto& v : row) v = std::numeric_limits<amrex::Real>::quiet_NaN();
+                            jobs.push_back(job);
                         }
                     }
+                    // (2) the solves.  The sub-volumes are independent ("replicas"): b200.rev_workers = W runs them on
+                    // W host threads, worker w on device w % (number of GPUs) -- several GPUs share the study, and
+                    // several workers on one GPU overlap the launch-bound solves of small boxes (each solver object
+                    // has its own stream).  W = 1 (default) is the reference's serial loop.
+                    int rev_workers = 1;
+                    {
+                        amrex::ParmParse pp_b200("b200");
+                        pp_b200.query("rev_workers", rev_workers);
+                    }
+                    rev_workers = std::max(1, std::min<int>(rev_workers, (int)jobs.size()));
+                    int n_devices = 1;
+                    if (rev_workers > 1 && (oi_device_count(&n_devices) != 0 || n_devices < 1)) n_devices = 1;
+                    std::mutex print_mutex;
+                    auto run_job = [&](RevJob& job) {
+                        const amrex::Box& bx = job.bx;
+                        if (rev_verbose >= 1) {
+                            std::lock_guard<std::mutex> lk(print_mutex);
+                            amrex::Print() << " REV Sample " << job.sample << ", Target Size " << job.target << ", Seed Lo (global): "
+                                           << job.seed_lo << ", Actual REV Box (global): " << bx << std::endl;
+                        }
+                        // the sub-volume as its own periodic box with origin 0 (:377-420)
+                        const amrex::Box rel(amrex::IntVect(0, 0, 0), bx.bigEnd() - bx.smallEnd());
+                        amrex::Geometry geom_rev;
+                        amrex::RealBox rb_rev({AMREX_D_DECL(0.0, 0.0, 0.0)},
+                                              {AMREX_D_DECL(amrex::Real(rel.length(0)), amrex::Real(rel.length(1)), amrex::Real(rel.length(2)))});
+                        amrex::Array<int, AMREX_SPACEDIM> per_rev = {AMREX_D_DECL(1, 1, 1)};
+                        geom_rev.define(rel, &rb_rev, 0, per_rev.data());
+                        amrex::BoxArray ba_rev(rel);
+                        ba_rev.maxSize(box_size);
+                        amrex::DistributionMapping dm_rev(ba_rev);
+                        amrex::iMultiFab mf_rev(ba_rev, dm_rev, 1, 1);
+                        mf_rev.setVal(0);
+                        for (int k = rel.smallEnd(2); k <= rel.bigEnd(2); ++k)
+                            for (int j = rel.smallEnd(1); j <= rel.bigEnd(1); ++j)
+                                for (int i = rel.smallEnd(0); i <= rel.bigEnd(0); ++i)
+                                    mf_rev(i, j, k, 0) = mf_phase(i + bx.smallEnd(0), j + bx.smallEnd(1), k + bx.smallEnd(2), 0);
+                        mf_rev.FillBoundary(geom_rev.periodicity());
+                        amrex::Real Dtmp[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                        bool all_ok = true;
+                        const long long n_rev = rel.numPts();
+                        const OpenImpala::Direction dirs3[3] = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
+                        for (int c = 0; c < 3 && all_ok; ++c) {
+                            OpenImpala::EffectiveDiffusivityHypre solver(geom_rev, ba_rev, dm_rev, mf_rev, phase_id, dirs3[c], st_rev,
+                                                                         results_path, rev_verbose > 1 ? rev_verbose : 0, rev_write_plotfiles != 0);
+                            if (!solver.solve()) {
+                                all_ok = false;
+                                if (rev_verbose >= 1) amrex::Print() << "    REV Chi solve FAILED for dir " << c << std::endl;
+                                break;
+                            }
+                            amrex::Real sums[3];
+                            long long n_active = 0;
+                            solver.gradientSums(sums, n_active);
+                            for (int r = 0; r < 3; ++r) Dtmp[r][c] = ((r == c ? (amrex::Real)n_active : 0.0) - sums[r]) / (amrex::Real)n_rev;
+                        }
+                        if (all_ok) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) job.D[r][c] = Dtmp[r][c];
+                    };
+                    if (rev_workers == 1) {
+                        for (RevJob& job : jobs) run_job(job);
+                    } else {
+                        if (verbose >= 1)
+                            amrex::Print() << "  REV workers: " << rev_workers << " host threads over " << n_devices << " device(s)" << std::endl;
+                        std::atomic<size_t> next{0};
+                        std::vector<std::thread> pool;
+                        for (int w = 0; w < rev_workers; ++w)
+                            pool.emplace_back([&, w] {
+                                OpenImpala::EffectiveDiffusivityHypre::setThreadDevice(w % n_devices);
+                                for (size_t q = next++; q < jobs.size(); q = next++) run_job(jobs[q]);
+                            });
+                        for (auto& th : pool) th.join();
+                    }
+                    // (3) one CSV row per sub-volume, in the order they were drawn
+                    for (const RevJob& job : jobs) {
+                        const auto& D = job.D;
+                        csv << job.sample << "," << job.seed_lo[0] << "," << job.seed_lo[1] << "," << job.seed_lo[2] << "," << job.target << ","
+                            << job.bx.length(0) << "," << job.bx.length(1) << "," << job.bx.length(2) << "," << std::fixed << std::setprecision(8)
+                            << D[0][0] << "," << D[1][1] << "," << D[2][2] << "," << D[0][1] << "," << D[0][2] << "," << D[1][2] << "\n";
+                    }
+                    csv.flush();
                 }
             }
         }

@@ -34,6 +34,8 @@ amrex::Array<int, AMREX_SPACEDIM> EffectiveDiffusivityHypre::hiV(const amrex::Bo
     return {b.bigEnd(0), b.bigEnd(1), b.bigEnd(2)};
 }
 
+namespace { thread_local int t_thread_device = -1; }
+
 EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom, const amrex::BoxArray& ba,
                                                      const amrex::DistributionMapping& dm,
                                                      const amrex::iMultiFab& mf_phase_input, const int phase_id,
@@ -79,6 +81,7 @@ EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom
     p.eps = m_eps; p.maxiter = m_maxiter; p.verbose = m_verbose;
     amrex::ParmParse pp_b200("b200");
     pp_b200.query("device", p.device);
+    if (t_thread_device >= 0) p.device = t_thread_device;                 // setThreadDevice()
     pp_b200.query("mg_degree", p.mg_degree);
     pp_b200.query("stencil_variant", p.stencil_variant);
     pp_b200.query("precond", p.precond);
@@ -103,6 +106,8 @@ EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom
     }
     if (m_verbose > 0 && io) amrex::Print() << "EffectiveDiffusivityHypre: Initialization complete." << std::endl;
 }
+
+void EffectiveDiffusivityHypre::setThreadDevice(int device) { t_thread_device = device; }
 
 EffectiveDiffusivityHypre::~EffectiveDiffusivityHypre() {
     if (m_solver) oi_destroy(m_solver);

@@ -718,6 +718,16 @@ def test_diffusion_rev_study_csv(host_bins):
 def test_host_layer_on_the_mock_rev_study(mock_env, tmp_path):
     # the same driver logic (mt19937 seeding, clipping, CSV) with the device replaced by the mock
     _check_rev_study(str(tmp_path / "rev"), env=mock_env)
+    # b200.rev_workers: the sub-volumes on worker threads (replicas) -- same rows in the same order
+    outs = []
+    for w in (1, 3):
+        res = tmp_path / f"w{w}"
+        r = run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/", f"results_path={res}/",
+                "rev.do_study=1", "rev.num_samples=3", "rev.sizes=12 20 4", "calculation_method=skip_if_rev",
+                "rev.verbose=0", "verbose=1", f"b200.rev_workers={w}", env=mock_env)
+        assert ("REV workers: 3 host threads" in r.stdout) == (w == 3)
+        outs.append(open(res / "rev_study_Deff.csv").read())
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 1 + 6          # size 4 is skipped (< 8 cells)
 
 
 @pytest.mark.gpu
