@@ -438,7 +438,20 @@ int main(int argc, char* argv[]) {
         }
         if (dirs.empty()) amrex::Warning("No valid directions specified in 'direction' input. Skipping tortuosity calculation.");
 
-        for (const auto dir : dirs) {
+        // The directions are independent solves: b200.dir_workers = W runs them on W host threads, worker w
+        // on device w % (number of GPUs) (one solver object = one handle = one stream, so on a single GPU the
+        // launch-bound solves of a small image overlap).  W = 1 (default) is the reference's serial loop.
+        int dir_workers = 1;
+        {
+            amrex::ParmParse pp_b200("b200");
+            pp_b200.query("dir_workers", dir_workers);
+        }
+        dir_workers = std::max(1, std::min<int>(dir_workers, (int)dirs.size()));
+        int n_devices_dir = 1;
+        if (dir_workers > 1 && (oi_device_count(&n_devices_dir) != 0 || n_devices_dir < 1)) n_devices_dir = 1;
+        std::vector<amrex::Real> taus(dirs.size(), std::numeric_limits<amrex::Real>::quiet_NaN());
+        auto solve_direction = [&](size_t di) {
+            const auto dir = dirs[di];
             const std::string dc = dir == OpenImpala::Direction::X ? "X" : dir == OpenImpala::Direction::Y ? "Y" : "Z";
             if (verbose >= 1) amrex::Print() << "\n--- Solving for Tortuosity in Direction: " << dc << " ---\n";
             amrex::Geometry geom_tort;                 // same box, NON-periodic (reference :671-677)
@@ -482,8 +495,26 @@ int main(int argc, char* argv[]) {
             }
             OpenImpala::TortuosityHypre& solver = *solver_ptr;
             const amrex::Real tau = solver.value();
-            results["Tortuosity_" + dc] = tau;
+            taus[di] = tau;
             amrex::Print() << "  >>> Calculated Tortuosity (" << dc << "): " << std::fixed << std::setprecision(8) << tau << " <<<\n";
+        };
+        if (dir_workers == 1) {
+            for (size_t di = 0; di < dirs.size(); ++di) solve_direction(di);
+        } else {
+            if (verbose >= 1)
+                amrex::Print() << "  Direction workers: " << dir_workers << " host threads over " << n_devices_dir << " device(s)" << std::endl;
+            std::atomic<size_t> next_dir{0};
+            std::vector<std::thread> pool;
+            for (int w = 0; w < dir_workers; ++w)
+                pool.emplace_back([&, w] {
+                    OpenImpala::TortuosityHypre::setThreadDevice(w % n_devices_dir);
+                    for (size_t q = next_dir++; q < dirs.size(); q = next_dir++) solve_direction(q);
+                });
+            for (auto& th : pool) th.join();
+        }
+        for (size_t di = 0; di < dirs.size(); ++di) {
+            const auto dir = dirs[di];
+            results[std::string("Tortuosity_") + (dir == OpenImpala::Direction::X ? "X" : dir == OpenImpala::Direction::Y ? "Y" : "Z")] = taus[di];
         }
 
         const std::filesystem::path out_path = results_dir / output_filename;

@@ -40,6 +40,8 @@ amrex::Array<int, AMREX_SPACEDIM> TortuosityHypre::hiV(const amrex::Box& b) {
     return {b.bigEnd(0), b.bigEnd(1), b.bigEnd(2)};
 }
 
+namespace { thread_local int t_thread_device = -1; }
+
 TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxArray& ba,
                                  const amrex::DistributionMapping& dm,
                                  const amrex::iMultiFab& mf_phase_input, const amrex::Real vf,
@@ -123,6 +125,7 @@ void TortuosityHypre::initialize(const std::function<void(oi_solver*)>& upload_p
     p.eps = m_eps; p.maxiter = m_maxiter; p.verbose = m_verbose;
     amrex::ParmParse pp_b200("b200");            // extras of this implementation, all optional
     pp_b200.query("device", p.device);
+    if (t_thread_device >= 0) p.device = t_thread_device;             // setThreadDevice()
     pp_b200.query("mg_degree", p.mg_degree);
     pp_b200.query("flux_polish", p.flux_polish);
     pp_b200.query("stencil_variant", p.stencil_variant);
@@ -152,6 +155,8 @@ void TortuosityHypre::initialize(const std::function<void(oi_solver*)>& upload_p
     }
     if (m_verbose > 0 && io) amrex::Print() << "TortuosityHypre: Initialization complete." << std::endl;
 }
+
+void TortuosityHypre::setThreadDevice(int device) { t_thread_device = device; }
 
 TortuosityHypre::~TortuosityHypre() {
     if (m_solver) oi_destroy(m_solver);

@@ -804,6 +804,20 @@ def test_host_layer_on_the_mock_flow_through(mock_env, tmp_path):
     assert "Conservation Check Status: PASS" in r.stdout
 
 
+def test_host_layer_on_the_mock_direction_workers(mock_env, tmp_path):
+    """b200.dir_workers: the three directions as independent jobs on worker threads (one solver
+    object, handle and stream each) -- same results.txt, all three plotfiles."""
+    outs = []
+    for w in (1, 3):
+        res = tmp_path / f"w{w}"
+        r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", "filename=SampleData_2Phase_squared.tif",
+                f"results_path={res}/", f"b200.dir_workers={w}", "write_plotfile=1", env=mock_env)
+        assert ("Direction workers: 3 host threads" in r.stdout) == (w == 3)
+        outs.append(open(res / "results.txt").read())
+        assert sorted(os.listdir(res)) == ["results.txt", "tortuosity_solution_0", "tortuosity_solution_1", "tortuosity_solution_2"]
+    assert outs[0] == outs[1] and outs[0].count("Tortuosity_") == 3
+
+
 @pytest.mark.parametrize("kind", ["tiff", "hdf5"])
 def test_host_layer_on_the_mock_streamed_upload(mock_env, tmp_path, kind):
     """b200.stream_upload: chunks decoded straight into the staging buffers give the same tau as
