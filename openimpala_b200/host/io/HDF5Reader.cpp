@@ -121,6 +121,12 @@ public:
         return walk(btree + base_addr, heap_data, name);
     }
     uint64_t baseAddr() const { return base_addr; }
+    uint64_t fileSize() {
+        in.clear();
+        in.seekg(0, std::ios::end);
+        const std::streamoff e = in.tellg();
+        return e > 0 ? (uint64_t)e : 0;
+    }
     // every chunk below a version-1 B-tree node of type 1 (raw data chunks); `ndims` is the
     // dataset rank + 1 (the element-size dimension has an offset too)
     template <class Sink>
@@ -290,6 +296,14 @@ bool HDF5Reader::readMetadataInternal() {
         if (!(have_space && have_type && have_layout)) throw std::runtime_error("incomplete dataset header");
         if (m_width <= 0 || m_height <= 0 || m_depth <= 0) throw std::runtime_error("bad dataset dimensions");
         if (!m_chunked && !m_filters.empty()) throw std::runtime_error("filters on a dataset that is not chunked");
+        if (m_type_size <= 0 || m_type_size > 8) throw std::runtime_error("unsupported element size");
+        {   // a contiguous dataset lies inside the file; reject headers whose extents cannot be true
+            const uint64_t fsz = f.fileSize();
+            const long double bytes = (long double)m_width * (long double)m_height * (long double)m_depth * (long double)m_type_size;
+            if (!m_chunked && (m_data_offset > fsz || bytes > (long double)(fsz - m_data_offset)))
+                throw std::runtime_error("dataset extents exceed the file size");
+            if (bytes > 1.0e15L) throw std::runtime_error("implausible dataset extents");
+        }
         const uint64_t undef_addr = so >= 8 ? UINT64_MAX : ((1ull << (8 * so)) - 1);
         if (m_chunked && chunk_btree != UINT64_MAX && chunk_btree != undef_addr) {   // undefined address: no chunk was ever written
             f.walkChunks(chunk_btree + f.baseAddr(), 4, [&](uint64_t addr, uint32_t bytes, uint32_t mask, const uint64_t* off) {

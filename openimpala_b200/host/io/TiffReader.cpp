@@ -16,6 +16,7 @@
 #include <map>
 #include <sstream>
 #include <memory>
+#include <set>
 #include <stdexcept>
 #include <thread>
 
@@ -48,6 +49,8 @@ public:
         if (h[0] == 'I' && h[1] == 'I') little = true;
         else if (h[0] == 'M' && h[1] == 'M') little = false;
         else throw std::runtime_error("not a TIFF file: " + path);
+        in.seekg(0, std::ios::end);
+        file_size = (uint64_t)std::max<std::streamoff>(0, in.tellg());
         const uint64_t magic = rd(h + 2, 2);
         if (magic == 42) { big = false; first = rd(h + 4, 4); }
         else if (magic == 43) { big = true; first = rd(h + 8, 8); }
@@ -56,12 +59,16 @@ public:
     std::vector<Ifd> directories() {
         std::vector<Ifd> out;
         uint64_t off = first;
+        std::set<uint64_t> seen;                              // a corrupt next-IFD offset must not loop for ever
         while (off != 0) {
+            if (off >= file_size || !seen.insert(off).second)
+                throw std::runtime_error("corrupt TIFF directory chain");
             Ifd d;
             std::vector<unsigned char> cnt(big ? 8 : 2);
             readAt(off, cnt.data(), cnt.size());
             const uint64_t n = rd(cnt.data(), cnt.size());
             const size_t esz = big ? 20 : 12, vsz = big ? 8 : 4;
+            if (n > 65535 || off + cnt.size() + n * esz > file_size) throw std::runtime_error("corrupt TIFF directory");
             std::vector<unsigned char> ent(n * esz + vsz);
             readAt(off + cnt.size(), ent.data(), ent.size());
             for (uint64_t e = 0; e < n; ++e) {
@@ -70,6 +77,7 @@ public:
                 const uint64_t count = rd(p + 4, vsz);
                 const size_t tsz = typeSize(type);
                 if (tsz == 0 || count == 0) continue;
+                if (count > file_size) throw std::runtime_error("corrupt TIFF tag (count larger than the file)");
                 std::vector<unsigned char> raw(tsz * count);
                 if (raw.size() <= vsz) std::memcpy(raw.data(), p + 4 + vsz, raw.size());
                 else readAt(rd(p + 4 + vsz, vsz), raw.data(), raw.size());
@@ -109,7 +117,7 @@ private:
     }
     std::ifstream in;
     bool little = true, big = false;
-    uint64_t first = 0;
+    uint64_t first = 0, file_size = 0;
 };
 
 enum { T_WIDTH = 256, T_HEIGHT = 257, T_BPS = 258, T_COMPRESSION = 259, T_FILLORDER = 266,
@@ -432,8 +440,12 @@ void TiffReader::thresholdInto(double thr, OutT vt, OutT vf, int z_begin, int nz
     const OutT zero_value = (0.0 > thr) ? vt : vf;                 // samples past the decoded data
     std::vector<Ifd> dirs;
     if (!m_is_sequence) {
-        TiffFile f(m_filename);
-        dirs = f.directories();                                    // parsed once, shared read-only
+        try {
+            TiffFile f(m_filename);
+            dirs = f.directories();                                // parsed once, shared read-only
+        } catch (const std::exception& e) {
+            amrex::Abort(std::string("[TiffReader] ") + e.what());
+        }
     }
     const int T = ioThreads(nz);
     std::vector<std::string> errors((size_t)T);
