@@ -282,8 +282,11 @@ int main(int argc, char* argv[]) {
                         const long long n_rev = rel.numPts();
                         const OpenImpala::Direction dirs3[3] = {OpenImpala::Direction::X, OpenImpala::Direction::Y, OpenImpala::Direction::Z};
                         for (int c = 0; c < 3 && all_ok; ++c) {
+                            // plotfiles of a sub-volume go to their own directory (reference :434-441)
+                            const std::string rev_dir = (results_dir / ("REV_Sample" + std::to_string(job.sample) + "_Size" +
+                                                                        std::to_string(bx.length(0)) + "_Dir" + std::to_string(c))).string();
                             OpenImpala::EffectiveDiffusivityHypre solver(geom_rev, ba_rev, dm_rev, mf_rev, phase_id, dirs3[c], st_rev,
-                                                                         results_path, rev_verbose > 1 ? rev_verbose : 0, rev_write_plotfiles != 0);
+                                                                         rev_dir, rev_verbose > 1 ? rev_verbose : 0, rev_write_plotfiles != 0);
                             if (!solver.solve()) {
                                 all_ok = false;
                                 if (rev_verbose >= 1) amrex::Print() << "    REV Chi solve FAILED for dir " << c << std::endl;

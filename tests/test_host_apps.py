@@ -728,6 +728,15 @@ def test_host_layer_on_the_mock_rev_study(mock_env, tmp_path):
         assert ("REV workers: 3 host threads" in r.stdout) == (w == 3)
         outs.append(open(res / "rev_study_Deff.csv").read())
     assert outs[0] == outs[1] and len(outs[0].splitlines()) == 1 + 6          # size 4 is skipped (< 8 cells)
+    # rev.write_plotfiles: one directory per (sample, size, direction), reference Diffusion.cpp:434-441
+    res = tmp_path / "plots"
+    run("Diffusion", "filename=SampleData_2Phase_squared.tif", "data_path=tests/golden/", f"results_path={res}/",
+        "rev.do_study=1", "rev.num_samples=1", "rev.sizes=12 20", "calculation_method=skip_if_rev", "rev.verbose=0",
+        "verbose=0", "rev.write_plotfiles=1", "b200.rev_workers=2", env=mock_env)
+    dirs = sorted(d for d in os.listdir(res) if d.startswith("REV_"))
+    assert dirs == [f"REV_Sample1_Size{n}_Dir{c}" for n in (12, 20) for c in range(3)]
+    h, f = read_amrex_plotfile(str(res / "REV_Sample1_Size20_Dir2" / "effdiff_chi_dir2"))
+    assert h["domain"] == [0, 0, 0, 19, 19, 19] and h["names"] == ["chi_k", "active_mask_from_solver"]
 
 
 @pytest.mark.gpu
