@@ -79,6 +79,20 @@ void calculate_Deff_tensor_homogenization(amrex::Real Deff_tensor[AMREX_SPACEDIM
         for (int c = 0; c < 3; ++c) Deff_tensor[r][c] = n > 0 ? sum[r][c] / (amrex::Real)n : 0.0;
 }
 
+OpenImpala::RawDataType rawTypeFromString(const std::string& raw_type) {
+    static const std::map<std::string, OpenImpala::RawDataType> types = {
+        {"UINT8", OpenImpala::RawDataType::UINT8}, {"INT8", OpenImpala::RawDataType::INT8},
+        {"INT16_LE", OpenImpala::RawDataType::INT16_LE}, {"INT16_BE", OpenImpala::RawDataType::INT16_BE},
+        {"UINT16_LE", OpenImpala::RawDataType::UINT16_LE}, {"UINT16_BE", OpenImpala::RawDataType::UINT16_BE},
+        {"INT32_LE", OpenImpala::RawDataType::INT32_LE}, {"INT32_BE", OpenImpala::RawDataType::INT32_BE},
+        {"UINT32_LE", OpenImpala::RawDataType::UINT32_LE}, {"UINT32_BE", OpenImpala::RawDataType::UINT32_BE},
+        {"FLOAT32_LE", OpenImpala::RawDataType::FLOAT32_LE}, {"FLOAT32_BE", OpenImpala::RawDataType::FLOAT32_BE},
+        {"FLOAT64_LE", OpenImpala::RawDataType::FLOAT64_LE}, {"FLOAT64_BE", OpenImpala::RawDataType::FLOAT64_BE}};
+    auto it = types.find(raw_type);
+    if (it == types.end()) throw std::runtime_error("Unknown raw datatype: " + raw_type);
+    return it->second;
+}
+
 template <class Reader>
 void loadThresholded(Reader& reader, int box_size, double threshold, amrex::Box& domain, amrex::BoxArray& ba,
                      amrex::DistributionMapping& dm, amrex::iMultiFab& mf_phase) {
@@ -149,17 +163,7 @@ int main(int argc, char* argv[]) {
                 if (!reader.isRead()) throw std::runtime_error("HDF5Reader failed to read metadata.");
                 loadThresholded(reader, box_size, threshold_val, domain, ba, dm, mf_phase);
             } else if (ext == ".raw") {
-                static const std::map<std::string, OpenImpala::RawDataType> types = {
-                    {"UINT8", OpenImpala::RawDataType::UINT8}, {"INT8", OpenImpala::RawDataType::INT8},
-                    {"INT16_LE", OpenImpala::RawDataType::INT16_LE}, {"INT16_BE", OpenImpala::RawDataType::INT16_BE},
-                    {"UINT16_LE", OpenImpala::RawDataType::UINT16_LE}, {"UINT16_BE", OpenImpala::RawDataType::UINT16_BE},
-                    {"INT32_LE", OpenImpala::RawDataType::INT32_LE}, {"INT32_BE", OpenImpala::RawDataType::INT32_BE},
-                    {"UINT32_LE", OpenImpala::RawDataType::UINT32_LE}, {"UINT32_BE", OpenImpala::RawDataType::UINT32_BE},
-                    {"FLOAT32_LE", OpenImpala::RawDataType::FLOAT32_LE}, {"FLOAT32_BE", OpenImpala::RawDataType::FLOAT32_BE},
-                    {"FLOAT64_LE", OpenImpala::RawDataType::FLOAT64_LE}, {"FLOAT64_BE", OpenImpala::RawDataType::FLOAT64_BE}};
-                auto it = types.find(raw_type);
-                if (it == types.end()) throw std::runtime_error("Unknown raw datatype: " + raw_type);
-                OpenImpala::RawReader reader(input.string(), raw_w, raw_h, raw_d, it->second);
+                OpenImpala::RawReader reader(input.string(), raw_w, raw_h, raw_d, rawTypeFromString(raw_type));
                 loadThresholded(reader, box_size, threshold_val, domain, ba, dm, mf_phase);
             } else {
                 throw std::runtime_error("Unsupported file extension for full domain load: " + ext);
@@ -463,7 +467,7 @@ int main(int argc, char* argv[]) {
                 amrex::Array<int, AMREX_SPACEDIM> np = {AMREX_D_DECL(0, 0, 0)};
                 geom_tort.define(geom_full.Domain(), &rb, 0, np.data());
             }
-            // b200.stream_upload = N (TIFF or HDF5 input): skip the int32 iMultiFab on the way to the GPU and
+            // b200.stream_upload = N (TIFF, HDF5 or RAW input): skip the int32 iMultiFab on the way to the GPU and
             // decode N planes at a time straight into the pinned staging buffers
             int stream_upload = 0;
             {
@@ -491,6 +495,15 @@ int main(int argc, char* argv[]) {
                     stream_upload, volume_fraction, phase_id, dir, stringToSolverType(solver_str), results_path, vlo, vhi,
                     verbose, write_plotfile != 0);
                 if (verbose >= 1) amrex::Print() << "  (phase field streamed from the HDF5 dataset in chunks of " << stream_upload << " planes)\n";
+            } else if (stream_upload > 0 && ext_l == ".raw") {
+                OpenImpala::RawReader reader(input.string(), raw_w, raw_h, raw_d, rawTypeFromString(raw_type));
+                const double thr = threshold_val;
+                solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
+                    geom_tort, ba, dm,
+                    [&](int z0, int nz, unsigned char* out) { reader.thresholdPlanesU8(thr, 1, 0, z0, nz, out); },
+                    stream_upload, volume_fraction, phase_id, dir, stringToSolverType(solver_str), results_path, vlo, vhi,
+                    verbose, write_plotfile != 0);
+                if (verbose >= 1) amrex::Print() << "  (phase field streamed from the RAW volume in chunks of " << stream_upload << " planes)\n";
             } else {
                 solver_ptr = std::make_unique<OpenImpala::TortuosityHypre>(
                     geom_tort, ba, dm, mf_phase, volume_fraction, phase_id, dir, stringToSolverType(solver_str),

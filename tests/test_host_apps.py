@@ -827,18 +827,21 @@ def test_host_layer_on_the_mock_direction_workers(mock_env, tmp_path):
     assert outs[0] == outs[1] and outs[0].count("Tortuosity_") == 3
 
 
-@pytest.mark.parametrize("kind", ["tiff", "hdf5"])
+@pytest.mark.parametrize("kind", ["tiff", "hdf5", "raw"])
 def test_host_layer_on_the_mock_streamed_upload(mock_env, tmp_path, kind):
     """b200.stream_upload: chunks decoded straight into the staging buffers give the same tau as
-    the iMultiFab path, for TIFF and HDF5 input."""
-    name = "SampleData_2Phase_squared.tif" if kind == "tiff" else "SampleData_2Phase_3d.hdf5"
+    the iMultiFab path, for TIFF, HDF5 and RAW input."""
+    name = {"tiff": "SampleData_2Phase_squared.tif", "hdf5": "SampleData_2Phase_3d.hdf5",
+            "raw": "SampleData_2Phase_stack_3d_uint8.raw"}[kind]
+    what = {"tiff": "TIFF", "hdf5": "HDF5 dataset", "raw": "RAW volume"}[kind]
+    raw_keys = ["width=100", "height=100", "depth=100", "datatype=UINT8"] if kind == "raw" else []
     taus = []
     for extra in (["b200.stream_upload=7"], []):
         res = tmp_path / ("s" if extra else "p")
         r = run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", f"filename={name}", "direction=Y",
-                f"results_path={res}/", *extra, env=mock_env)
+                f"results_path={res}/", *raw_keys, *extra, env=mock_env)
         if extra:
-            assert f"streamed from the {'TIFF' if kind == 'tiff' else 'HDF5 dataset'} in chunks of 7 planes" in r.stdout
+            assert f"streamed from the {what} in chunks of 7 planes" in r.stdout
         taus.append(float(re.search(r"Tortuosity_Y: (\S+)", open(res / "results.txt").read()).group(1)))
     assert math.isfinite(taus[0]) and taus[0] == taus[1]
 
