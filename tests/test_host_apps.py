@@ -879,3 +879,29 @@ def test_host_layer_on_the_mock_homogenization_and_driver(mock_env, tmp_path):
     assert np.abs(got - ref).max() <= 1e-6
     assert sorted(os.listdir(tmp_path / "teff")) == ["effdiff_chi_dir0", "effdiff_chi_dir1", "effdiff_chi_dir2"]
 
+
+def test_host_layer_on_the_mock_nan_inf_conventions(mock_env, tmp_path):
+    """value()'s in-band failure conventions through the app (TortuosityHypre.cpp:764-877): a phase
+    that does not percolate in the flow direction -> NaN; equal Dirichlet values -> no potential
+    gradient -> +Inf; too few iterations -> not converged -> NaN."""
+    import numpy as np
+    from PIL import Image
+    vol = np.ones((12, 14, 16), dtype=np.uint8)           # z, y, x
+    vol[:, :, 7] = 0                                       # a solid wall across X
+    ims = [Image.fromarray(vol[k] * 255) for k in range(vol.shape[0])]
+    ims[0].save(tmp_path / "wall.tif", save_all=True, append_images=ims[1:])
+    base = ["tests/inputs/diffusion_flow_through.inputs", "filename=wall.tif", f"data_path={tmp_path}/", "threshold_val=127.5",
+            "verbose=0"]
+
+    def taus(*extra, name):
+        res = tmp_path / name
+        run("Diffusion", *base, f"results_path={res}/", *extra, env=mock_env)
+        return dict(re.findall(r"(Tortuosity_[XYZ]): (\S+)", open(res / "results.txt").read()))
+
+    t = taus("direction=X Y", name="blocked")
+    assert t["Tortuosity_X"].lower().lstrip("-") == "nan"                       # nothing percolates in X
+    assert abs(float(t["Tortuosity_Y"]) - (14 - 1) / 14 * 1.0) < 1e-6           # open slabs: tau = (N-1)/N
+    t = taus("direction=Y", "tortuosity.vlo=0.5", "tortuosity.vhi=0.5", name="flat")
+    assert t["Tortuosity_Y"].lower() in ("inf", "nan")                          # zero gradient / zero flux
+    assert t["Tortuosity_Y"].lower() == "inf"
+
