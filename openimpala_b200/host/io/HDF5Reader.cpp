@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -231,9 +232,13 @@ bool HDF5Reader::readMetadataInternal() {
                 const int version = d[0], rank = d[1];
                 if (rank != 3) throw std::runtime_error("dataset rank " + std::to_string(rank) + " != 3");
                 const size_t off = version == 1 ? 8 : 4;
+                if (m.data.size() < off + 3 * (size_t)sl) throw std::runtime_error("truncated dataspace message");
                 uint64_t dims[3] = {0, 0, 0};
                 for (int r = 0; r < 3; ++r)
                     for (int q = 0; q < sl; ++q) dims[r] |= (uint64_t)d[off + r * sl + q] << (8 * q);
+                // the reference rejects extents that do not fit an int (src/io/HDF5Reader.cpp:142)
+                for (int r = 0; r < 3; ++r)
+                    if (dims[r] == 0 || dims[r] > (uint64_t)INT_MAX) throw std::runtime_error("dataset extent outside (0, INT_MAX]");
                 m_depth = (int)dims[0]; m_height = (int)dims[1]; m_width = (int)dims[2];
                 have_space = true;
             } else if (m.type == 0x0003 && m.data.size() >= 8) {          // datatype
@@ -257,6 +262,11 @@ bool HDF5Reader::readMetadataInternal() {
                         m_chunk_dims[r] = (uint64_t)c[0] | ((uint64_t)c[1] << 8) | ((uint64_t)c[2] << 16) | ((uint64_t)c[3] << 24);
                         if (m_chunk_dims[r] == 0) throw std::runtime_error("zero chunk extent");
                     }
+                    // a chunk larger than 4 Gi elements is implausible (HDF5 itself caps a chunk at 4 GiB)
+                    // and would let the extent product wrap
+                    if (m_chunk_dims[0] * m_chunk_dims[1] > ((uint64_t)1 << 32) ||
+                        m_chunk_dims[0] * m_chunk_dims[1] * m_chunk_dims[2] > ((uint64_t)1 << 32))
+                        throw std::runtime_error("implausible chunk extents");
                     m_data_offset = 0;
                 } else if (version == 3) {
                     if (d[1] != 1) throw std::runtime_error("compact dataset layout is not supported without libhdf5");

@@ -277,6 +277,29 @@ void checkSupported(const Ifd& d, const std::string& name, int& w, int& h, uint1
         amrex::Abort("[TiffReader] unsupported TIFF predictor " + std::to_string(pred) + " in: " + name);
 }
 
+// Every directory of a stack (and every file of a sequence) is decoded with the metadata of the first
+// one, so each is checked against it before its bytes are thresholded: the reference re-queries libtiff
+// per directory (src/io/TiffReader.cpp:320-352) and a page of another size, bit depth or compression
+// scheme must not be read as raw samples.  Throws (worker threads collect the message).
+void verifyDirectory(const Ifd& d, const std::string& name, int W, int H, int bps, int fmt, int fill) {
+    const uint64_t comp = d.get(T_COMPRESSION, 1), pred = d.get(T_PREDICTOR, 1);
+    std::ostringstream why;
+    if ((int)d.get(T_WIDTH, 0) != W || (int)d.get(T_HEIGHT, 0) != H)
+        why << "size " << d.get(T_WIDTH, 0) << "x" << d.get(T_HEIGHT, 0) << " differs from the first page's " << W << "x" << H;
+    else if ((int)d.get(T_BPS, 1) != bps || (int)d.get(T_SAMPLEFORMAT, 1) != fmt)
+        why << "BitsPerSample/SampleFormat " << d.get(T_BPS, 1) << "/" << d.get(T_SAMPLEFORMAT, 1)
+            << " differ from the first page's " << bps << "/" << fmt;
+    else if ((int)d.get(T_FILLORDER, 1) != fill)
+        why << "FillOrder " << d.get(T_FILLORDER, 1) << " differs from the first page's " << fill;
+    else if (d.get(T_PLANAR, 1) != 1 || d.get(T_SPP, 1) != 1)
+        why << "Planar=" << d.get(T_PLANAR, 1) << ", SPP=" << d.get(T_SPP, 1) << " unsupported";
+    else if (comp != C_NONE && comp != C_LZW && comp != C_DEFLATE && comp != C_DEFLATE_OLD && comp != C_PACKBITS)
+        why << "unsupported compression scheme " << comp;
+    else if (pred != 1 && !(pred == 2 && bps >= 8 && fmt != 3))
+        why << "unsupported predictor " << pred;
+    if (!why.str().empty()) throw std::runtime_error("inconsistent TIFF directory in " + name + ": " + why.str());
+}
+
 }  // namespace
 
 TiffReader::TiffReader() = default;
@@ -358,6 +381,7 @@ void decodeDirectoryRows(TiffFile& f, const Ifd& d, int W, int H, int bps, std::
         const auto* offs = d.arr(T_TILEOFFSETS);
         const auto* cnts = d.arr(T_TILEBYTECOUNTS);
         if (tw <= 0 || th <= 0 || !cnts) amrex::Abort("Invalid tile params.");
+        if (cnts->size() < offs->size()) throw std::runtime_error("TIFF directory with fewer tile byte counts than tile offsets.");
         const int tiles_x = (W + tw - 1) / tw;
         for (size_t t = 0; t < offs->size(); ++t) {
             buf.resize((size_t)(*cnts)[t]);
@@ -467,9 +491,11 @@ void TiffReader::thresholdInto(double thr, OutT vt, OutT vf, int z_begin, int nz
                     if (one.empty()) throw std::runtime_error("Seq: empty file " + name);
                     d = &one[0];
                     f = single.get();
+                    verifyDirectory(*d, name, W, H, bps, fmt, m_fill_order);
                 } else {
                     if (k >= (int)dirs.size()) break;
                     d = &dirs[(size_t)k];
+                    verifyDirectory(*d, m_filename + " (directory " + std::to_string(k) + ")", W, H, bps, fmt, m_fill_order);
                 }
                 const bool file_little = f->littleEndian();
                 OutT* plane = out + (size_t)(k - z_begin) * (size_t)H * (size_t)W;

@@ -56,7 +56,7 @@ void oi_default_params(oi_params* p) {
     memset(p, 0, sizeof *p);
     p->direction = OI_DIR_X; p->phase_id = 1; p->vlo = 0.0; p->vhi = 1.0;
     p->dx[0] = p->dx[1] = p->dx[2] = 1.0;
-    p->eps = 1e-9; p->maxiter = 200; p->device = -1; p->flux_polish = 1;
+    p->eps = 1e-9; p->maxiter = 200; p->device = -1; p->flux_polish = 0;
 }
 
 int oi_count_phase_i32(const int32_t* f, int64_t n, int32_t phase, int64_t* pc, int64_t* tc) {

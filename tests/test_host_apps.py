@@ -237,6 +237,41 @@ def test_tiff_file_sequence(host_bins, tmp_path):
     assert int(field(r.stdout, "WeightedChecksum")[0]) == weighted_checksum(vol > 99)
 
 
+def test_tiff_inconsistent_pages_abort(host_bins, tmp_path):
+    """A later directory / sequence file that differs from the first one (size, bit depth, compression)
+    must abort instead of being thresholded with the first page's metadata (the reference re-queries
+    libtiff per directory, src/io/TiffReader.cpp:320-352)."""
+    import struct
+    import numpy as np
+    rng = np.random.default_rng(31)
+    a = rng.integers(0, 255, (1, 12, 18)).astype(np.uint8)
+    # sequence: second file has another size; third case: another bit depth
+    _write_tiff(tmp_path / "s_0000.tif", a)
+    _write_tiff(tmp_path / "s_0001.tif", rng.integers(0, 255, (1, 12, 20)).astype(np.uint8))
+    r = run("tReaders", "mode=tiffseq", "gpu_count=0", f"tifffile={tmp_path / 's_'}", "num_files=2", "start_index=0",
+            "digits=4", "threshold=99", check=False)
+    assert r.returncode != 0 and "inconsistent TIFF directory" in (r.stdout + r.stderr)
+    _write_tiff(tmp_path / "t_0000.tif", a)
+    _write_tiff(tmp_path / "t_0001.tif", rng.integers(0, 60000, (1, 12, 18)).astype(np.uint16))
+    r = run("tReaders", "mode=tiffseq", "gpu_count=0", f"tifffile={tmp_path / 't_'}", "num_files=2", "start_index=0",
+            "digits=4", "threshold=99", check=False)
+    assert r.returncode != 0 and "inconsistent TIFF directory" in (r.stdout + r.stderr)
+    # stack: patch the Compression tag (259) of the second directory to JPEG (7)
+    f = tmp_path / "stack.tif"
+    _write_tiff(f, rng.integers(0, 255, (3, 12, 18)).astype(np.uint8))
+    raw = bytearray(open(f, "rb").read())
+    off = struct.unpack_from("<I", raw, 4)[0]
+    nent = struct.unpack_from("<H", raw, off)[0]
+    off = struct.unpack_from("<I", raw, off + 2 + 12 * nent)[0]          # second IFD
+    nent = struct.unpack_from("<H", raw, off)[0]
+    for e in range(nent):
+        if struct.unpack_from("<H", raw, off + 2 + 12 * e)[0] == 259:
+            struct.pack_into("<I", raw, off + 2 + 12 * e + 8, 7)
+    open(f, "wb").write(bytes(raw))
+    r = run("tReaders", "mode=tiff", "gpu_count=0", f"tifffile={f}", "threshold=99", check=False)
+    assert r.returncode != 0 and "inconsistent TIFF directory" in (r.stdout + r.stderr)
+
+
 @pytest.mark.parametrize("datatype,dtype,thr", [
     ("UINT8", "u1", 100.5), ("INT16_LE", "<i2", -3.5), ("UINT16_LE", "<u2", 30000.0), ("UINT16_BE", ">u2", 30000.0),
     ("FLOAT32_LE", "<f4", 0.25),
