@@ -11,9 +11,16 @@ A "step" is one full pass of the hot path for one direction:
 `e2e`    : same metric through the public class (TortuosityHypre + value()) with
            the phase field in pinned HOST memory; H2D/D2H inside the timed region.
 Workload : synthetic overlapping-sphere packing S^3 (default 1024^3), tau in Z;
-           N GPUs split the SAME box into z-slabs (strong scaling).
+           N GPUs split the SAME box into z-slabs (strong scaling, the default).
+--scaling weak : the box grows with N at (about) 1024^3 cells per GPU -- 1024^3 @1,
+           1280^3 @2, 1536^3 @4, 2048^3 @8 (BASELINE configs[4]) -- and the line says
+           "scaling": "weak".  A default (strong) run on N > 1 GPUs also solves that
+           weak box once and reports it under "weak", so the driver's scaling run
+           carries the 2048^3 number without a second command.
 --impl reference : the CPU restatement (oracle/oi_oracle.c, OpenMP on all host
-           cores) on a bounded sample; rank 0 only.
+           cores, thread count set explicitly) on a bounded sample; rank 0 only.
+Every line carries "parity": exact integer facts and tau against the committed goldens
+(tests/golden/bench_golden.json) and the flux-conservation gate, at every N.
 """
 from __future__ import annotations
 
@@ -33,7 +40,9 @@ sys.path.insert(0, ROOT)
 METRIC = "tau_solve_dof_iter_per_s"
 UNIT = "DOF*iter/s"
 SEED, RADIUS, SOLID = 12345, 12, 0.60
-CPU_SAMPLE_N = 128          # bounded CPU sample: 128^3 packing with the same generator
+CPU_SAMPLE_N = int(os.environ.get("OI_BENCH_CPU_SAMPLE", "192"))   # bounded CPU sample of cpu_baseline / matched_size
+WEAK_SIZE = {1: 1024, 2: 1280, 4: 1536, 8: 2048}   # cubic boxes, slabs of equal 64-aligned height
+REF_ARM_BUDGET_S = 200.0    # --impl reference: whole run (warm-up + steps) sized to end within this
 
 
 def parse():
@@ -47,6 +56,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mg-degree", type=int, default=0)
+    ap.add_argument("--scaling", default=os.environ.get("OI_BENCH_SCALING", "strong"), choices=["strong", "weak"])
+    ap.add_argument("--no-weak-extra", action="store_true", help="strong run on N>1: skip the extra weak-box solve")
+    ap.add_argument("--no-matched", action="store_true", help="skip the GPU run at the CPU sample size")
     return ap.parse_args()
 
 
@@ -94,15 +106,30 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(steps: int, warmup: int, direction: int):
-    """The reference path restated on the host cores (oracle/oi_oracle.c)."""
+def cpu_reference_run(steps: int, warmup: int, direction: int, sample_n: int = 0, budget_s: float = 0.0):
+    """The reference path restated on the host cores (oracle/oi_oracle.c): mask by literal flood
+    sweeps, tortuosity_fillmtx into 7 stored coefficients, Jacobi-PCG, fluxes, tau.  The OpenMP thread
+    count is set explicitly to the cores this process may use (torchrun exports OMP_NUM_THREADS=1).
+    sample_n = 0: choose the largest sample of (256, 192, 128, 96, 64) whose warm-up + steps fit in
+    budget_s, from a timed 64^3 calibration solve (cost ~ n^4: cells x iterations)."""
     import numpy as np
     from openimpala_b200 import synth
     from oracle import oi_c
-    ph = synth.sphere_packing(CPU_SAMPLE_N, SEED, RADIUS, SOLID).astype(np.int32)
+    cores = oi_c.set_num_threads(oi_c.host_cores())
+    if sample_n <= 0:
+        ph = synth.sphere_packing(64, SEED, RADIUS, SOLID).astype(np.int32)
+        t0 = time.perf_counter()
+        oi_c.tortuosity(ph, 1, direction, -1.0, 1.0, eps=1e-9)
+        t64 = time.perf_counter() - t0
+        sample_n = 64
+        for cand in (256, 192, 128, 96):
+            if (steps + warmup) * t64 * (cand / 64.0) ** 4 <= budget_s:
+                sample_n = cand
+                break
+    ph = synth.sphere_packing(sample_n, SEED, RADIUS, SOLID).astype(np.int32)
     n = ph.size
     out = None
-    for _ in range(max(0, min(warmup, 1))):
+    for _ in range(warmup):
         out = oi_c.tortuosity(ph, 1, direction, -1.0, 1.0, eps=1e-9)
     t0 = time.perf_counter()
     its = 0
@@ -110,10 +137,38 @@ def cpu_reference_run(steps: int, warmup: int, direction: int):
         out = oi_c.tortuosity(ph, 1, direction, -1.0, 1.0, eps=1e-9)
         its += out["iters"]
     dt = time.perf_counter() - t0
-    return dict(value=n * its / dt, seconds=dt, iters=out["iters"], tau=out["tau"], n=n,
-                cores=oi_c.num_threads(),
-                sample=f"{CPU_SAMPLE_N}^3 sphere packing (seed {SEED}, R {RADIUS}), tau in "
-                       f"{'XYZ'[direction]}, full path mask+assemble+Jacobi-PCG to 1e-9, {steps} step(s)")
+    return dict(value=n * its / dt, seconds=dt, seconds_per_step=dt / steps, iters=out["iters"], tau=out["tau"],
+                n=n, sample_n=sample_n, cores=cores, n_active=out["n_active"],
+                sample=f"{sample_n}^3 sphere packing (seed {SEED}, R {RADIUS}), tau in "
+                       f"{'XYZ'[direction]}, full path mask+assemble+Jacobi-PCG to 1e-9, {steps} step(s), "
+                       f"{cores} OpenMP threads")
+
+
+def load_bench_golden():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "bench_golden.json")))
+    except Exception:
+        return {}
+
+
+def parity_block(n, direction, pc, n_active, n_in, n_out, tau, fin, fout, converged):
+    """Parity facts of this run against the committed goldens (integers exact, tau relative)."""
+    g = load_bench_golden().get(f"{n}:{direction}")
+    avg = 0.5 * (abs(fin) + abs(fout))
+    out = {"flux_rel": (abs(abs(fin) - abs(fout)) / avg) if avg > 0 else None, "flux_gate_1e-6": None,
+           "converged": bool(converged), "golden": None, "counts_exact": None, "tau_rel_vs_golden": None}
+    if out["flux_rel"] is not None:
+        out["flux_gate_1e-6"] = bool(out["flux_rel"] <= 1e-6)
+    if g:
+        out["golden"] = g.get("source")
+        checks = [("phase_cells", pc), ("active_cells", n_active), ("n_in", n_in), ("n_out", n_out)]
+        known = [(k, v) for k, v in checks if g.get(k) is not None]
+        out["counts_exact"] = bool(known) and all(int(g[k]) == int(v) for k, v in known)
+        out["counts_checked"] = [k for k, _ in known]
+        if g.get("tau") is not None and tau == tau:
+            out["tau_rel_vs_golden"] = abs(tau - g["tau"]) / abs(g["tau"])
+            out["tau_golden_kind"] = g.get("tau_kind")
+    return out
 
 
 def main():
@@ -126,20 +181,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 3))
-        r = cpu_reference_run(steps, args.warmup, direction)
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        r = cpu_reference_run(steps, warmup, direction, sample_n=0, budget_s=REF_ARM_BUDGET_S)
+        size = WEAK_SIZE.get(args.gpus, args.size) if args.scaling == "weak" else args.size
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "strong",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"sphere-packing {args.size}^3 tau in Z (bounded CPU sample: {r['sample']})"},
+            "config": {"workload": f"sphere-packing {size}^3 tau in {'XYZ'[direction]} "
+                                   f"(bounded CPU sample: {r['sample']})",
+                       "sample_rule": f"largest of 256/192/128/96/64 whose {warmup}+{steps} solves fit {REF_ARM_BUDGET_S:.0f} s "
+                                      "(64^3 calibration, cost ~ n^4)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "iterations": r["iters"], "tau": r["tau"],
+            "iterations": r["iters"], "tau": r["tau"], "time_to_solution_s": r["seconds_per_step"],
             "note": "reference (AMReX+HYPRE+MPI+gfortran) cannot be built in this image; this is the "
-                    "repo's C/OpenMP restatement with a Jacobi-PCG solver, not HYPRE FlexGMRES+SMG",
+                    "repo's C/OpenMP restatement with a Jacobi-PCG solver, not HYPRE FlexGMRES+SMG: its "
+                    "DOF*iter/s counts Jacobi-PCG iterations and is not comparable with the GPU arm's MG-PCG "
+                    "iterations -- compare time_to_solution_s at equal size (the GPU line's matched_size block)",
         }
         print(json.dumps(line))
         return 0
@@ -149,7 +210,7 @@ def main():
     import torch.distributed as dist
 
     from openimpala_b200 import capi, synth
-    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
+    from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre, tau_from_fluxes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback)")
@@ -164,65 +225,102 @@ def main():
         dist.broadcast(idt, 0)
         comm = capi.Comm(rank, world, bytes(idt.cpu().numpy().tobytes()), device=local_rank)
 
-    n = args.size
-    shape = (n, n, n)
-    z_begin, nz_local = capi.slab_partition(n, world)[rank]
-    t_gen = time.perf_counter()
-    slab = synth.sphere_packing_slab(shape, SEED, RADIUS, SOLID, z_begin, nz_local)
-    t_gen = time.perf_counter() - t_gen
-    host_pinned = torch.from_numpy(slab).pin_memory()
-    d_phase = host_pinned.to(dev, non_blocking=False)          # resident copy for `value`
-    ncells = n * n * n
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM ----------------
-    S = capi.Solver(shape, direction, 1, -1.0, 1.0, eps=1e-9, maxiter=200, device=local_rank,
-                    z_begin=z_begin, nz_local=nz_local, comm=comm, mg_degree=args.mg_degree)
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
 
-    def step_resident():
-        S.set_phase_device(d_phase.data_ptr())
-        pc, tc = S.volume_fraction()
-        n_active = S.build_mask()
-        info = S.solve()
-        fin, fout, ni, no = S.fluxes()
-        return pc, n_active, info, fin, fout
+    def run_resident(n, steps, warmup, slabs_over=None, keep=False, sample_clocks=False):
+        """`steps` timed passes of the hot path on the n^3 packing with the phase slab resident in HBM.
+        slabs_over: number of ranks the box is split over (default: all); ranks beyond it idle."""
+        nr = world if slabs_over is None else slabs_over
+        active_here = rank < nr
+        out = {}
+        if active_here:
+            z_begin, nz_local = capi.slab_partition(n, nr)[rank]
+            t_gen = time.perf_counter()
+            slab = synth.sphere_packing_slab((n, n, n), SEED, RADIUS, SOLID, z_begin, nz_local)
+            t_gen = time.perf_counter() - t_gen
+            host_pinned = torch.from_numpy(slab).pin_memory()
+            d_phase = host_pinned.to(dev, non_blocking=False)
+            S = capi.Solver((n, n, n), direction, 1, -1.0, 1.0, eps=1e-9, maxiter=200, device=local_rank,
+                            z_begin=z_begin, nz_local=nz_local, comm=comm if nr > 1 else None,
+                            mg_degree=args.mg_degree)
 
-    for _ in range(args.warmup):
-        res = step_resident()
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = S.launch_count()
-    S.timer_record(0)
-    t0 = time.perf_counter()
-    iters_total = 0
-    solve_ms = setup_ms = 0.0
-    for _ in range(args.steps):
-        res = step_resident()
-        iters_total += res[2].iterations
-        solve_ms += res[2].solve_ms
-        setup_ms += res[2].setup_ms
-    S.timer_record(1)
-    dev_ms = S.timer_elapsed_ms(0, 1)
-    sync_all()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clocks = sampler.stop()
-    launches = S.launch_count() - l0
-    halo_mode, halo_peer_exchanges = S.halo_info()
-    tmax = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = (float(v) for v in tmax.cpu())
-    pc, n_active, info, fin, fout = res
-    active_vf = n_active / ncells
-    from openimpala_b200.tortuosity import tau_from_fluxes
-    tau, deff, _ = tau_from_fluxes(fin, fout, active_vf, float(n), float(n) * n, -1.0, 1.0)
-    value = ncells * iters_total / (dev_ms * 1e-3)
+            def step():
+                S.set_phase_device(d_phase.data_ptr())
+                pc, tc = S.volume_fraction()
+                n_active = S.build_mask()
+                info = S.solve()
+                fin, fout, ni, no = S.fluxes()
+                return pc, n_active, info, fin, fout, ni, no
+            for _ in range(warmup):
+                res = step()
+        if nr == world:
+            sync_all()
+        else:
+            torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+        dev_ms = wall_ms = 0.0
+        if active_here:
+            l0 = S.launch_count()
+            S.timer_record(0)
+            t0 = time.perf_counter()
+            iters_total, solve_ms, setup_ms = 0, 0.0, 0.0
+            for _ in range(steps):
+                res = step()
+                iters_total += res[2].iterations
+                solve_ms += res[2].solve_ms
+                setup_ms += res[2].setup_ms
+            S.timer_record(1)
+            dev_ms = S.timer_elapsed_ms(0, 1)
+        if nr == world:
+            sync_all()
+        else:
+            torch.cuda.synchronize()
+        if active_here:
+            wall_ms = 1e3 * (time.perf_counter() - t0)
+        clocks = sampler.stop() if sampler else None
+        if nr == world:
+            dev_ms, wall_ms = max_over_ranks([dev_ms, wall_ms])
+        if active_here:
+            pc, n_active, info, fin, fout, ni, no = res
+            ncells = n * n * n
+            tau, deff, _ = tau_from_fluxes(fin, fout, n_active / ncells, float(n), float(n) * n, -1.0, 1.0)
+            out = dict(n=n, ncells=ncells, dev_ms=dev_ms, wall_ms=wall_ms, steps=steps, iters_total=iters_total,
+                       solve_ms=solve_ms, setup_ms=setup_ms, launches=S.launch_count() - l0, pc=pc, n_active=n_active,
+                       info=info, fin=fin, fout=fout, n_in=ni, n_out=no, tau=tau, deff=deff, clocks=clocks,
+                       z_begin=z_begin, nz_local=nz_local, t_gen=t_gen, halo=S.halo_info(),
+                       porosity=float(slab.mean()) if nr == 1 else None,
+                       value=ncells * iters_total / (dev_ms * 1e-3) if dev_ms > 0 else None,
+                       parity=parity_block(n, direction, pc, n_active, ni, no, tau, fin, fout, info.converged))
+            if keep:
+                out.update(S=S, slab=slab, host_pinned=host_pinned, d_phase=d_phase)
+            else:
+                S.close()
+                del d_phase, host_pinned, slab
+                capi.release_cached_memory()
+        return out
+
+    n = WEAK_SIZE.get(world, args.size) if args.scaling == "weak" else args.size
+    shape = (n, n, n)
+    ncells = n * n * n
+    main = run_resident(n, args.steps, args.warmup, keep=True, sample_clocks=True)
+    S, slab, host_pinned = main["S"], main["slab"], main["host_pinned"]
+    z_begin, nz_local = main["z_begin"], main["nz_local"]
+    dev_ms, wall_ms, iters_total = main["dev_ms"], main["wall_ms"], main["iters_total"]
+    info, value, clocks = main["info"], main["value"], main["clocks"]
+    halo_mode = main["halo"][0]
 
     # ---------------- roofline: dominant kernel timed live ----------------
     peaks = {}
@@ -248,29 +346,33 @@ def main():
                      "axpy2_dot": 1.0 + 32.0 * fp,         # flags; r (r/w), q, r32, z1 per pair (x += alpha p is deferred)
                      "xpby": 1.0 + 36.0 * fp,              # flags; x (r/w), p (r/w), z per pair
                      "dot": 16.0}
-    bytes_per_cell = bytes_touched
-    for name, bpc in bytes_per_cell.items():
+    for name, bpc in bytes_touched.items():
         ms, _ = S.time_kernel(name, 10)
         kern[name] = {"ms": ms, "gbs_dense": bytes_dense[name] * local_cells / (ms * 1e-3) / 1e9,
                       "bytes_per_cell_dense": bytes_dense[name],
                       "gbs_touched_16B_groups": bpc * local_cells / (ms * 1e-3) / 1e9, "bytes_per_cell_touched": bpc}
-    traffic = None
+    traffic = traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        # ncu dram bytes per launch of the APPLY kernel, captured at tj["apply_cells"] cells and
-        # scaled to this launch's cell count (traffic is proportional to cells for this kernel)
+        # ncu dram bytes per launch of the APPLY kernel, captured at tj["apply_cells"] cells; used as is when
+        # this launch has the same cell count, else scaled by the cell ratio (and said so)
         traffic = tj["apply_bytes_per_launch"] / tj["apply_cells"] * local_cells
+        traffic_src = tj.get("source", "profiles/roofline_traffic.json") + \
+            ("" if int(tj["apply_cells"]) == int(local_cells) else
+             f" (captured at {int(tj['apply_cells'])} cells, scaled to {int(local_cells)})")
     except Exception:
         pass
     # headline: SURVEY 8(d)'s algorithmic figure for K3 (17 B per cell of the dense box) x cells per launch
     roofline = {"bound": "hbm", "kernel": "l0_ring_kernel<double,APPLY,dot> (y = A p, p.Ap)",
                 "achieved": kern["apply"]["gbs_dense"], "peak": peak, "unit": "GB/s",
-                "frac": kern["apply"]["gbs_dense"] / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": 17.0,
+                "frac": kern["apply"]["gbs_dense"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "frac_of_actual_traffic": (traffic / (kern["apply"]["ms"] * 1e-3) / 1e9 / peak) if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": 17.0,
                 "touched_fraction": {"fp64_pairs": fp, "fp32_quads": fq, "unknown_cells": n_unk / local_cells},
                 "cells_per_launch": local_cells,
                 "kernels": kern}
     S.close()
+    del main["S"], main["d_phase"]
 
     # ---------------- e2e: public class, host buffers ----------------
     e2e = None
@@ -306,56 +408,84 @@ def main():
             tau_e2e, it = step_e2e()
             its += it
         sync_all()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.cpu())
+        dt = max_over_ranks([time.perf_counter() - t0])[0]
         per_step_iters = its / args.steps
         e2e = {"value": ncells * its / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(slab.nbytes),
                "d2h_bytes_per_step": int(8 * (per_step_iters + 4) + 16 + 24 + 8),
                "ms_per_step": 1e3 * dt / args.steps, "tau": tau_e2e,
                "rank0_breakdown_ms_per_step": {k_: v_ / args.steps for k_, v_ in e2e_parts.items()},
-               "timed": "wall clock around TortuosityHypre(...).value(), max over ranks; includes handle "
-                        "creation, cudaMalloc, H2D of the uint8 phase slab from pinned memory"}
+               "timed": "wall clock around TortuosityHypre(...).value() + close(), max over ranks; every step creates the "
+                        "handle, copies the uint8 phase slab from pinned host memory (H2D), builds the mask, solves, "
+                        "reads fluxes back (D2H).  Warm process: device blocks come from the library's cache after "
+                        "the first object (a cold first object additionally pays cudaMalloc, about 1 s at 1024^3)"}
+    del host_pinned, slab
+    capi.release_cached_memory()
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(1, 0, direction)
+    # ---------------- weak box beside a strong run on N > 1 GPUs ----------------
+    weak = None
+    if args.scaling == "strong" and world > 1 and world in WEAK_SIZE and not args.no_weak_extra and n == 1024:
+        wn = WEAK_SIZE[world]
+        w = run_resident(wn, min(args.steps, 3), 1)
+        weak = {"workload": f"sphere-packing {wn}^3, tau in {'XYZ'[direction]}, {world} z-slabs "
+                            f"({wn ** 3 / world / 1024 ** 3:.3f} x 1024^3 cells per GPU)",
+                "n": wn, "steps": w["steps"], "warmup": 1, "time_to_solution_s": w["dev_ms"] * 1e-3 / w["steps"],
+                "iterations": w["info"].iterations, "ms_per_iteration": w["solve_ms"] / max(1, w["iters_total"]),
+                "value": w["value"], "unit": UNIT, "tau": w["tau"], "active_cells": w["n_active"],
+                "rel_residual": w["info"].rel_residual, "parity": w["parity"],
+                "efficiency_note": "weak efficiency = value / (n_gpus x the 1-GPU line's value) for DOF*iter/s, or "
+                                   "the 1-GPU time_to_solution_s / this one for time-to-solution"}
+
+    # ---------------- CPU baseline + matched-size time-to-solution (rank 0 works, N=1 only for the CPU) ----------------
+    cpu = matched = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 0, direction, sample_n=CPU_SAMPLE_N)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "seconds": r["seconds"], "iterations": r["iters"],
+               "seconds": r["seconds"], "iterations": r["iters"], "tau": r["tau"],
                "note": "C/OpenMP restatement with Jacobi-PCG on the stored 7-coefficient matrix; the "
-                       "reference's HYPRE FlexGMRES+SMG stack is not buildable in this image"}
+                       "reference's HYPRE FlexGMRES+SMG stack is not buildable in this image.  Its DOF*iter/s counts "
+                       "Jacobi-PCG iterations: compare time-to-solution (matched_size), not this value"}
+        if not args.no_matched:
+            g = run_resident(r["sample_n"], 3, 2)
+            gpu_s = g["dev_ms"] * 1e-3 / g["steps"]
+            matched = {"n": r["sample_n"], "what": "time-to-solution of the same full step (mask, operator, solve to 1e-9, "
+                                                   "fluxes) on the same image", "gpu_s": gpu_s, "cpu_s": r["seconds_per_step"],
+                       "ratio": r["seconds_per_step"] / gpu_s, "gpu_iterations": g["info"].iterations,
+                       "cpu_iterations": r["iters"], "cpu_cores": r["cores"],
+                       "tau_rel_diff": abs(g["tau"] - r["tau"]) / abs(r["tau"]),
+                       "active_cells_equal": bool(g["n_active"] == r["n_active"])}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "precision_note": "operator apply, Krylov vectors, dots and fluxes in fp64; multigrid preconditioner vectors in fp32",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64 (fp32 V-cycle)", "data": "synthetic",
+            "precision_note": "operator apply, Krylov vectors, dots and fluxes in fp64; multigrid preconditioner vectors in fp32; "
+                              "the final residual is confirmed in fp64",
             "config": {"workload": f"sphere-packing {n}^3 uint8 (seed {SEED}, R {RADIUS}, solid {SOLID}), "
                                    f"tau in {'XYZ'[direction]}, phase 1, eps 1e-9, MG-PCG",
                        "parallelism": f"z-slabs x{world}",
                        "halo": {0: "none (single slab)", 1: "NCCL send/recv",
-                                2: "peer-memory stores over NVLink (CUDA IPC) + stream wait on flag words"}[halo_mode],
+                                2: "peer-memory stores over NVLink (CUDA IPC), boundary planes stored by the producing "
+                                   "kernels, consumers wait on flag words"}[halo_mode],
                        "l2_policy": "inputs larger than L2 (every fp64 vector >= 1 GiB at 512^3+)",
                        "sparsity_note": "16-byte groups without an unknown (solid) are skipped by the vector kernels and "
                                         "not stored by the stencil kernels: gbs_dense uses SURVEY 8(d)'s dense-box bytes "
                                         "(can exceed the copy peak where sectors are skipped), gbs_touched counts only "
                                         "occupied 16-byte groups (a lower bound on DRAM traffic, which moves whole sectors)",
-                       "porosity": float(slab.mean()) if world == 1 else None,
-                       "generate_s": t_gen},
+                       "porosity": main["porosity"],
+                       "generate_s": main["t_gen"]},
             "time_to_solution_s": dev_ms * 1e-3 / args.steps,
             "wall_ms_per_step": wall_ms / args.steps,
-            "solve_ms_per_step": solve_ms / args.steps, "mg_setup_ms_per_step": setup_ms / args.steps,
+            "solve_ms_per_step": main["solve_ms"] / args.steps, "mg_setup_ms_per_step": main["setup_ms"] / args.steps,
             "iterations": info.iterations, "rel_residual": info.rel_residual,
-            "converged": bool(info.converged), "tau": tau, "deff": deff, "active_cells": n_active,
-            "phase_cells": pc, "flux_in": fin, "flux_out": fout,
-            "dof_active_iter_per_s": n_active * iters_total / (dev_ms * 1e-3),
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e,
+            "converged": bool(info.converged), "tau": main["tau"], "deff": main["deff"], "active_cells": main["n_active"],
+            "phase_cells": main["pc"], "flux_in": main["fin"], "flux_out": main["fout"],
+            "n_in": main["n_in"], "n_out": main["n_out"],
+            "dof_active_iter_per_s": main["n_active"] * iters_total / (dev_ms * 1e-3),
+            "parity": main["parity"],
+            "gpu_launches": int(main["launches"]), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "matched_size": matched, "weak": weak, "e2e": e2e,
         }
         print(json.dumps(line))
     if comm is not None:

@@ -225,6 +225,22 @@ int oi_graph_info(oi_solver* h, int64_t* replays, int64_t* kernels_per_iteration
 /* Number of kernels this handle has launched since creation. */
 int oi_launch_count(oi_solver* h, int64_t* launches);
 
+/* ---- the reference's two existing C-ABI kernels, under their own names -----------------
+ * Fortran bind(c) convention: every scalar by reference, arrays with their own lo/hi
+ * bounds (x fastest), HOST pointers.  Drop-in replacements for the Fortran objects:
+ *   tortuosity_fillmtx  src/props/TortuosityHypreFill_F.H:47-68 (TortuosityHypreFill.F90:44-314)
+ *   tortuosity_remspot  src/props/Tortuosity_filcc_F.H:65-67    (Tortuosity_filcc.F90:88-177)
+ * The box is copied to the device, one kernel fills it, the result is copied back; rows,
+ * rhs and xinit are bit-identical to the Fortran's (openimpala_b200/csrc/oi_refabi.cu).
+ * They abort (like `error stop`) when no CUDA device is present. */
+void tortuosity_fillmtx(double* a, double* rhs, double* xinit, const int* nval, const int* p,
+                        const int* p_lo, const int* p_hi, const int* active_mask, const int* mask_lo,
+                        const int* mask_hi, const int* bxlo, const int* bxhi, const int* domlo,
+                        const int* domhi, const double* dxinv, const double* vlo, const double* vhi,
+                        const int* phase, const int* dir, const int* debug_print_level);
+void tortuosity_remspot(int* q, const int* q_lo, const int* q_hi, const int* ncomp, const int* bxlo,
+                        const int* bxhi, const int* domlo, const int* domhi);
+
 #ifdef __cplusplus
 }
 #endif

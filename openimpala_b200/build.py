@@ -28,7 +28,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"] + ARCH
 
-CU_SOURCES = ["oi_level0.cu", "oi_level0_ring.cu", "oi_level0_pair.cu", "oi_coarse.cu", "oi_vecops.cu", "oi_mask.cu", "oi_halo.cu", "oi_solver.cu"]
+CU_SOURCES = ["oi_level0.cu", "oi_level0_ring.cu", "oi_level0_tma.cu", "oi_level0_pair.cu", "oi_coarse.cu", "oi_vecops.cu", "oi_mask.cu", "oi_halo.cu", "oi_refabi.cu", "oi_solver.cu"]
 
 
 def _newer(target: str, deps) -> bool:

@@ -95,6 +95,9 @@ _SIGS = {
     "oi_halo_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "oi_graph_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    # the reference's own bind(c) entry points (Fortran convention: everything by reference)
+    "tortuosity_fillmtx": (None, [_P] * 20),
+    "tortuosity_remspot": (None, [_P] * 8),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -200,6 +203,43 @@ def slab_partition(nz: int, n_ranks: int, align: int = 0):
         out.append((z, n))
         z += n
     return out
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def ref_tortuosity_fillmtx(p, p_lo, active_mask, mask_lo, bxlo, bxhi, domlo, domhi, dxinv, vlo, vhi, phase, direction,
+                           xinit=None):
+    """tortuosity_fillmtx exactly as the reference's C++ calls it (TortuosityHypre.cpp:612-632): `p` and
+    `active_mask` are int32 arrays [z, y, x] whose element [0, 0, 0] has index p_lo / mask_lo (ghost cells
+    included); returns (a[n, 7], rhs[n], xinit[n]) for the cells of bxlo..bxhi, x fastest."""
+    lib = load()
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    m = np.ascontiguousarray(active_mask, dtype=np.int32)
+    p_hi = [p_lo[d] + p.shape[2 - d] - 1 for d in range(3)]
+    m_hi = [mask_lo[d] + m.shape[2 - d] - 1 for d in range(3)]
+    n = int(np.prod([bxhi[d] - bxlo[d] + 1 for d in range(3)]))
+    a = np.full((n, 7), np.nan)
+    rhs = np.full(n, np.nan)
+    x = np.zeros(n) if xinit is None else np.ascontiguousarray(xinit, dtype=np.float64).copy()
+    dxi = (C.c_double * 3)(*[float(v) for v in dxinv])
+    lib.tortuosity_fillmtx(a.ctypes.data, rhs.ctypes.data, x.ctypes.data, C.byref(C.c_int(n)), p.ctypes.data,
+                           _i3(p_lo), _i3(p_hi), m.ctypes.data, _i3(mask_lo), _i3(m_hi), _i3(bxlo), _i3(bxhi),
+                           _i3(domlo), _i3(domhi), dxi, C.byref(C.c_double(vlo)), C.byref(C.c_double(vhi)),
+                           C.byref(C.c_int(phase)), C.byref(C.c_int(direction)), C.byref(C.c_int(0)))
+    return a, rhs, x
+
+
+def ref_tortuosity_remspot(q, q_lo, bxlo, bxhi, domlo, domhi):
+    """tortuosity_remspot as the reference calls it (TortuosityHypre.cpp:270-290): one in-place pass over
+    bxlo..bxhi of the int32 array q [z, y, x] whose element [0, 0, 0] has index q_lo.  Returns the filtered copy."""
+    lib = load()
+    q = np.ascontiguousarray(q, dtype=np.int32).copy()
+    q_hi = [q_lo[d] + q.shape[2 - d] - 1 for d in range(3)]
+    lib.tortuosity_remspot(q.ctypes.data, _i3(q_lo), _i3(q_hi), C.byref(C.c_int(1)), _i3(bxlo), _i3(bxhi),
+                           _i3(domlo), _i3(domhi))
+    return q
 
 
 class Solver:

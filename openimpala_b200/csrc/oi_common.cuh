@@ -124,6 +124,54 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials,
     }
 }
 
+// ---- peer halo fused into the producing / consuming kernels (z-slabs, one process per GPU) ----
+// Replaces AMReX FillBoundary on the solve path (reference src/props/TortuosityHypre.cpp:339,
+// 584-585, 1033).  A kernel that WRITES a field with ghost planes stores its two boundary planes
+// straight into the z-neighbours' ghost planes (their arenas are mapped through CUDA IPC over
+// NVLink) and the last of its boundary CTAs publishes the exchange's sequence number in the
+// neighbour's flag word; a kernel that READS ghost planes lets only the CTAs that touch them spin
+// on the local flag word, and those CTAs are scheduled last, so the transfer and any skew between
+// the ranks hide behind the interior planes.  No push kernel, no stream wait, no host round trip.
+struct HaloOut {
+    void* dst_lo;                   // lower neighbour's ghost plane above its top plane   (nullptr: none)
+    void* dst_hi;                   // upper neighbour's ghost plane below its plane 0     (nullptr: none)
+    unsigned int* flag_lo;          // their flag words
+    unsigned int* flag_hi;
+    unsigned int* counter;          // local: [0] boundary CTAs done on the low side, [1] high side / all blocks
+    unsigned int seq;
+};
+struct HaloIn {
+    const unsigned int* flag_lo;    // local flag word written by the lower neighbour (nullptr: no wait)
+    const unsigned int* flag_hi;    // ... by the upper neighbour
+    unsigned int seq;
+};
+
+// one thread: spin until the flag word has reached seq (acquire at system scope)
+__device__ __forceinline__ void halo_spin(const unsigned int* flag, unsigned int seq) {
+    unsigned int v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - seq) >= 0) break;
+        __nanosleep(64);
+    }
+}
+// Every thread of the CTA, after its peer stores: the last of `expected` CTAs to arrive publishes seq
+// in the neighbours' flag words (either may be null).  Contains __syncthreads.
+__device__ __forceinline__ void halo_publish(unsigned int* counter, unsigned int expected, unsigned int* flag_a,
+                                             unsigned int* flag_b, unsigned int seq) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        if (ticket == expected - 1u) {
+            *counter = 0u;
+            __threadfence_system();
+            if (flag_a) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_a), "r"(seq) : "memory");
+            if (flag_b) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_b), "r"(seq) : "memory");
+        }
+    }
+}
+
 // Function attributes (cudaFuncSetAttribute) belong to a device's context, so the one-time
 // configuration of a kernel has to happen once per device, not once per process: true the
 // first time a call site is reached with the current device.

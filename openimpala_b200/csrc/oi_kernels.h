@@ -21,6 +21,11 @@ struct L0Args {
     unsigned int* red_counter;
     double* red_out;
     int n_sm;
+    // z-slabs: ghost planes of `u` arrive through the flag words of hin (the boundary CTAs wait inside
+    // the kernel), boundary planes of `out` are stored into the neighbours' ghost planes (hout).
+    // All-null (the default) = no halo work in the kernel.  Ring kernels, prolongation.
+    HaloIn hin;
+    HaloOut hout;
 };
 
 long long l0_max_blocks(const Grid& g, int n_sm);
@@ -28,8 +33,13 @@ int pick_zchunk(const Grid& g, int n_sm);
 // shared-memory ring kernels (oi_level0_ring.cu): mode 0 APPLY, 1 SMOOTH, 2 RESTRICT
 bool ring_supported(const L0Args& a, int mode);
 void ring_launch(const L0Args& a, int mode, bool dot, cudaStream_t st);
+// TMA variant of the ring (oi_level0_tma.cu): APPLY and SMOOTH through cp.async.bulk.tensor + mbarriers.
+// tma_launch returns false (nothing launched) when the tensor maps cannot be encoded.
+bool tma_supported(const L0Args& a, int mode);
+bool tma_launch(const L0Args& a, int mode, bool dot, cudaStream_t st);
 // z += P*ec on unknown cells (prolongation + correction)
 void l0_prolong_add(const L0Args& a, cudaStream_t st);
+bool prolong_halo_supported(const L0Args& a);
 void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st);
 void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st);
 void l0_residual_restrict(const L0Args& a, int variant, cudaStream_t st);
@@ -96,11 +106,14 @@ void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const dou
 void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
                          const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
                          const double* den, double w0, double* partials, unsigned int* counter,
-                         double* out, int n_sm, cudaStream_t st);
+                         double* out, int n_sm, cudaStream_t st, const HaloOut* ho = nullptr);
 // p = z + (num/den) p      (z is a multigrid-precision vector; both zero off the unknowns)
 // x != nullptr: first x += (anum/aden) p with the old p (deferred solution update)
+// ho (z-slabs): also store the new p's boundary planes into the neighbours' ghost planes
 void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
-              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st);
+              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st,
+              long long plane = 0, const HaloOut* ho = nullptr);
+bool vec_halo_supported(long long plane, long long n);
 // x += (num/den) p on the unknowns
 void vec_axpy(long long n, const uint8_t* flags, double* x, const double* p, const double* num, const double* den,
               int n_sm, cudaStream_t st);

@@ -15,6 +15,8 @@
 //   * gather: one thread per cell straight from global/L1/L2.
 // All kernels are templated on the element type: double for the Krylov operator
 // apply, mg_t for the multigrid sweeps.
+#include <cstdlib>
+
 #include "oi_kernels.h"
 
 namespace oi {
@@ -310,9 +312,16 @@ long long l0_max_blocks(const Grid& g, int n_sm) {
     return a > b ? a : b;
 }
 
+// OI_TMA=1: the ring kernels stage their planes with cp.async.bulk.tensor (oi_level0_tma.cu) where that applies
+static bool want_tma() {
+    const char* e = getenv("OI_TMA");
+    return e && e[0] == '1';
+}
+
 // variant: 0 = shared-memory ring (cp.async), 2 = register z-march, 1 = gather
 void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {           // fp64 fields
     if (variant == 0 && ring_supported(a, 0)) {
+        if (want_tma() && tma_supported(a, 0) && tma_launch(a, 0, dot, st)) return;
         ring_launch(a, 0, dot, st);
     } else if (variant == 0 || variant == 2) {
         if (dot) launch_zmarch<double, 0, false, true>(a, st); else launch_zmarch<double, 0, false, false>(a, st);
@@ -323,6 +332,7 @@ void l0_apply(const L0Args& a, bool dot, int variant, cudaStream_t st) {        
 
 void l0_smooth(const L0Args& a, bool addc, bool dot, int variant, cudaStream_t st) {   // mg_t fields
     if (variant == 0 && !addc && ring_supported(a, 1)) {
+        if (want_tma() && tma_supported(a, 1) && tma_launch(a, 1, dot, st)) return;
         ring_launch(a, 1, dot, st);
     } else if (variant == 0 || variant == 2) {
         if (addc) { if (dot) launch_zmarch<mg_t, 1, true, true>(a, st); else launch_zmarch<mg_t, 1, true, false>(a, st); }

@@ -451,6 +451,154 @@ l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Variant 3: the 512-thread kernel with the trip loop unrolled by the ring length, so that every
+// stage offset (input ring of PR = 6 stages, intermediate ring of 3) is a compile-time constant.
+// The SASS of variant 2 spends more than a third of its 309 instructions per trip on stage
+// arithmetic (IMAD / LEA / ISETP from the runtime modulo of stage_of()); the kernel is issue bound
+// (ncu: sm__inst_issued 77-80 %, DRAM 33 %), so those instructions are what it pays for.
+// Trip kk = kb + s with kb = k0 - 1 + 6 t:  plane kk+d of the input lives in stage (s + d + 1) % 6,
+// v(kk) in intermediate stage s % 3, v(kk-2) in (s + 1) % 3, the refill plane kk+4 goes to (s + 5) % 6.
+template <bool DOT>
+__global__ void __launch_bounds__(512, 2)
+l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restrict__ u,
+                   const float* __restrict__ b, float* __restrict__ out, float w1, float w2, int zchunk,
+                   double* red_partials, unsigned int* red_counter, double* red_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* us = reinterpret_cast<float*>(smem_raw);            // [PR][UH][PW]
+    float* bs = us + PR * U_ST;                                // [PR][VH][PW]
+    float* vs = bs + PR * V_ST;                                // [3][VH][PW]
+    float2* dtab2 = reinterpret_cast<float2*>(vs + 3 * V_ST);  // [64] {diagonal, inverse}
+    unsigned char* fs = reinterpret_cast<unsigned char*>(dtab2 + 64);   // [PR][VH][PW] bytes
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;                    // 32 pairs x 16 rows
+    const int i0 = blockIdx.x * PTX, j0 = blockIdx.y * PTY;
+    const int k0 = blockIdx.z * zchunk, k1 = min(k0 + zchunk, g.nz);
+    const float cx = (float)g.cx, cy = (float)g.cy, cz = (float)g.cz;
+    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+    if (tid < 64) {
+        const float d = row_diag<float>((unsigned int)tid, g);
+        dtab2[tid] = make_float2(d, d > 0.f ? 1.f / d : 0.f);
+    }
+    auto in_box = [&](int gi, int gj) { return gi >= 0 && gi < g.nx && gj >= 0 && gj < g.ny; };
+
+    const bool u_duty = tid < UH * 18, v_duty = tid < VH * 18;
+    const int ur = tid / 18, ug = tid % 18;
+    const int u_i = i0 + 4 * (ug - 1), u_j = j0 - 2 + ur;
+    const bool u_ok = u_duty && in_box(u_i, u_j);
+    const float* u_src = u + (u_ok ? (long long)u_j * g.nx + u_i : 0);
+    const int u_dst = ur * PW + 4 * ug;
+    const int v_j = j0 - 1 + ur;
+    const bool v_ok = v_duty && in_box(u_i, v_j);
+    const long long v_col = v_ok ? (long long)v_j * g.nx + u_i : 0;
+    const float* b_src = b + v_col;
+    const uint8_t* f_src = flags + v_col;
+    const int v_dst = ur * PW + 4 * ug;
+
+    const int oi = i0 + 2 * tx, oj = j0 + ty;
+    const bool inb = in_box(oi, oj);
+    const long long o_col = inb ? (long long)oj * g.nx + oi : 0;
+    const int u_off = (ty + 2) * PW + 4 + 2 * tx;
+    const int v_off = (ty + 1) * PW + 4 + 2 * tx;
+    int rim_kind = 0, rim_vo = 0;                              // 1 = pair, 2 = single cell
+    if (tid < 64) { rim_kind = 1; rim_vo = ((tid >> 5) ? VH - 1 : 0) * PW + 4 + 2 * (tid & 31); }
+    else if (tid < 100) { const int t = tid - 64; rim_kind = 2; rim_vo = (t % VH) * PW + ((t / VH) ? 4 + PTX : 3); }
+
+    // copies of plane q into stage st (a constant at every call site of the unrolled loop)
+    auto issue = [&](int q, int st) {
+        if (q < -1 || q > g.nz) return;
+        const long long poff = (long long)q * g.plane;
+        if (u_duty) cpa16(us + st * U_ST + u_dst, u_src + poff, u_ok);
+        if (v_duty) {
+            cpa16(bs + st * V_ST + v_dst, b_src + poff, v_ok);
+            cpa4(fs + st * V_ST + v_dst, f_src + poff, v_ok);
+        }
+    };
+    // prologue: planes k0-2 .. k0+PP into stages 0 .. PP+2, one commit group per plane
+#pragma unroll
+    for (int d = 0; d <= PP + 2; ++d) { issue(k0 - 2 + d, d); cpa_commit(); }
+
+    float* out_own = out + o_col;
+    double dot_acc = 0.0;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 u_m = zero2, u_c = zero2, v3 = zero2, v2 = zero2, v1 = zero2, b2 = zero2, b1 = zero2;
+    unsigned int f2 = 0u, f1 = 0u;
+    cpa_wait<PP + 1>();
+    __syncthreads();
+    if (k0 - 2 >= -1) u_m = *reinterpret_cast<const float2*>(us + 0 * U_ST + u_off);
+    u_c = *reinterpret_cast<const float2*>(us + 1 * U_ST + u_off);
+
+    for (int kb = k0 - 1; kb <= k1 + 1; kb += PR) {
+#pragma unroll
+        for (int s = 0; s < PR; ++s) {
+            const int kk = kb + s;
+            if (kk > k1 + 1) break;                            // CTA-uniform
+            cpa_wait<PP>();
+            __syncthreads();
+
+            float* V = vs + (s % 3) * V_ST;
+            const bool plane_in = (kk >= 0 && kk < g.nz);
+            float2 oA = zero2, bA = zero2, u_p = zero2;
+            unsigned int fA = 0u;
+            if (kk <= k1) {
+                const float* Um = us + (s % PR) * U_ST;
+                const float* Uc = us + ((s + 1) % PR) * U_ST;
+                const float* Up = us + ((s + 2) % PR) * U_ST;
+                const float* B = bs + ((s + 1) % PR) * V_ST;
+                const unsigned char* F = fs + ((s + 1) % PR) * V_ST;
+                if (kk + 1 <= g.nz) u_p = *reinterpret_cast<const float2*>(Up + u_off);
+                if (plane_in) {
+                    fA = *reinterpret_cast<const unsigned short*>(F + v_off);
+                    bA = *reinterpret_cast<const float2*>(B + v_off);
+                    const float2 sS = *reinterpret_cast<const float2*>(Uc + u_off - PW);
+                    const float2 nN = *reinterpret_cast<const float2*>(Uc + u_off + PW);
+                    const float xw = Uc[u_off - 1], xe = Uc[u_off + 2];
+                    oA = relax_pair(fA & 0xffu, fA >> 8, u_c, xw, xe, sS, nN, u_m, u_p, bA, w1, ncx, ncy, ncz, dtab2);
+                }
+                *reinterpret_cast<float2*>(V + v_off) = oA;
+                if (rim_kind) {
+                    const int vo = rim_vo, uo = rim_vo + PW;
+                    if (!plane_in) {
+                        V[vo] = 0.f;
+                        if (rim_kind == 1) V[vo + 1] = 0.f;
+                    } else {
+                        V[vo] = relax2(F[vo], Uc[uo], Uc[uo - 1], Uc[uo + 1], Uc[uo - PW], Uc[uo + PW], Um[uo], Up[uo],
+                                       B[vo], w1, cx, cy, cz, dtab2);
+                        if (rim_kind == 1)
+                            V[vo + 1] = relax2(F[vo + 1], Uc[uo + 1], Uc[uo], Uc[uo + 2], Uc[uo + 1 - PW], Uc[uo + 1 + PW],
+                                               Um[uo + 1], Up[uo + 1], B[vo + 1], w1, cx, cy, cz, dtab2);
+                    }
+                }
+            }
+
+            const int k = kk - 2;
+            if (k >= k0 && k < k1) {
+                const float* Vc = vs + ((s + 1) % 3) * V_ST;
+                const float2 sS = *reinterpret_cast<const float2*>(Vc + v_off - PW);
+                const float2 nN = *reinterpret_cast<const float2*>(Vc + v_off + PW);
+                const float xw = Vc[v_off - 1], xe = Vc[v_off + 2];
+                const float2 o = relax_pair(f2 & 0xffu, f2 >> 8, v2, xw, xe, sS, nN, v3, v1, b2, w2, ncx, ncy, ncz, dtab2);
+                if (DOT) dot_acc += (double)b2.x * (double)o.x + (double)b2.y * (double)o.y;
+                if (inb && (f2 & 0x4040u)) *reinterpret_cast<float2*>(out_own + (long long)k * g.plane) = o;
+            }
+            u_m = u_c; u_c = u_p;
+            v3 = v2; v2 = v1; v1 = oA;
+            b2 = b1; b1 = bA;
+            f2 = f1; f1 = fA;
+
+            issue(kk + 2 + PP, (s + 5) % PR);
+            cpa_commit();
+        }
+    }
+    cpa_wait<0>();
+
+    if (DOT) {
+        double v[1] = {dot_acc};
+        grid_reduce<1>(v, red_partials, red_counter, red_out);
+    }
+}
+
 size_t pair_smem_bytes() {
     return sizeof(float) * (size_t)(PR * U_ST + PR * V_ST + 3 * V_ST + 128) + (size_t)PR * V_ST;
 }
@@ -470,13 +618,20 @@ void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant
         cudaFuncSetAttribute(l0_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + PTX - 1) / PTX, (a.g.ny + PTY - 1) / PTY, (a.g.nz + zc - 1) / zc);
     const float* u = static_cast<const float*>(a.u);
     const float* b = static_cast<const float*>(a.b);
     float* out = static_cast<float*>(a.out);
-    if (variant == 2) {
+    if (variant == 3) {
+        if (dot) l0_pair512u_kernel<true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                   a.red_partials, a.red_counter, a.red_out);
+        else l0_pair512u_kernel<false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                a.red_partials, a.red_counter, a.red_out);
+    } else if (variant == 2) {
         if (dot) l0_pair512_kernel<true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
                                                                   a.red_partials, a.red_counter, a.red_out);
         else l0_pair512_kernel<false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,

@@ -70,11 +70,15 @@ struct RingCoarse { int cnx, cny, z0h; };   // RESTRICT target dims, (z0 >> 1)
 
 // MODE 0 APPLY: out = w * A u (+ dot u.out) ; 1 SMOOTH: out = u + w (b - A u)/d (+ dot b.out)
 // MODE 2 RESTRICT (2x2x2 or 2x2x1): out[coarse] = sum_children (b - A u)
-template <typename T, int MODE, bool DOT>
+// HALO (z-slabs): the CTAs of the first / last z-chunk wait for the neighbours' boundary planes on the
+// flag words of `hin` before they touch a ghost plane, store plane 0 / nz-1 of `out` into the
+// neighbours' ghost planes as they produce them (MODE 1) and publish `hout.seq`; those two chunks are
+// dispatched last (blockIdx.z is remapped), so transfer and rank skew hide behind the interior planes.
+template <typename T, int MODE, bool DOT, bool HALO>
 __global__ void __launch_bounds__(256)
 l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ u,
                const T* __restrict__ b, T* __restrict__ out, T w, RingCoarse rc, int fz, int zchunk,
-               double* red_partials, unsigned int* red_counter, double* red_out) {
+               double* red_partials, unsigned int* red_counter, double* red_out, HaloIn hin, HaloOut hout) {
     typedef Cfg<T> C;
     constexpr int CPT = C::CPT, TX = C::TX, TY = C::TY, PITCH = C::PITCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -91,9 +95,27 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
     const int i = blockIdx.x * TX + CPT * tx;                   // first of the CPT cells (multiple of CPT)
     const int j = blockIdx.y * TY + ty;
     const bool inb = (i < g.nx) && (j < g.ny);                  // nx % 4 == 0: all CPT cells in or out
-    const int k0 = blockIdx.z * zchunk;
+    int zc_idx = blockIdx.z;
+    if (HALO) {                                                 // interior chunks first, chunk 0 and the last one at the end
+        const int nzc = gridDim.z;
+        if (nzc > 2) zc_idx = ((int)blockIdx.z < nzc - 2) ? (int)blockIdx.z + 1 : ((int)blockIdx.z == nzc - 2 ? 0 : nzc - 1);
+    }
+    const int k0 = zc_idx * zchunk;
     const int k1 = min(k0 + zchunk, g.nz);
     const T cx = (T)g.cx, cy = (T)g.cy, cz = (T)g.cz;
+
+    if (HALO) {
+        const bool wlo = hin.flag_lo && k0 == 0, whi = hin.flag_hi && k1 == g.nz;
+        if (wlo || whi) {
+            if (tid == 0) {
+                if (wlo) halo_spin(hin.flag_lo, hin.seq);
+                if (whi) halo_spin(hin.flag_hi, hin.seq);
+            }
+            __syncthreads();
+        }
+    }
+    const bool push_lo = HALO && MODE == 1 && hout.dst_lo && k0 == 0;
+    const bool push_hi = HALO && MODE == 1 && hout.dst_hi && k1 == g.nz;
 
     if (tid < 64) {
         const T d = row_diag<T>((unsigned int)tid, g);
@@ -224,7 +246,13 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
                 // a 16-byte group without an unknown stays zero (every output field is
                 // zero off the unknowns from allocation on): its sector is never written
                 constexpr unsigned int UNKS = (CPT == 2) ? 0x4040u : 0x40404040u;
-                if (inb && (fword & UNKS)) *reinterpret_cast<Pack<T>*>(out_own) = o;
+                if (inb && (fword & UNKS)) {
+                    *reinterpret_cast<Pack<T>*>(out_own) = o;
+                    if (HALO) {
+                        if (push_lo && k == 0) *reinterpret_cast<Pack<T>*>(static_cast<T*>(hout.dst_lo) + col) = o;
+                        if (push_hi && k == g.nz - 1) *reinterpret_cast<Pack<T>*>(static_cast<T*>(hout.dst_hi) + col) = o;
+                    }
+                }
                 out_own += g.plane;
             } else {
                 // y pair = lane ^ 16; z pair carried across two planes
@@ -256,6 +284,12 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
     }
     cp_async_wait<0>();
 
+    if (HALO && MODE == 1) {
+        const unsigned int tiles = gridDim.x * gridDim.y;
+        if (hout.flag_lo && k0 == 0) halo_publish(hout.counter + 0, tiles, hout.flag_lo, nullptr, hout.seq);
+        if (hout.flag_hi && k1 == g.nz) halo_publish(hout.counter + 1, tiles, nullptr, hout.flag_hi, hout.seq);
+    }
+
     if (DOT) {
         double v[1] = {dot_acc};
         grid_reduce<1>(v, red_partials, red_counter, red_out);
@@ -282,30 +316,38 @@ prolong_add_kernel(Grid g, const uint8_t* __restrict__ flags, T* __restrict__ z,
     }
 }
 
-// 4 cells per thread (fp32, nx % 4 == 0): float4 z, 4 connectivity bytes, float2 coarse values
+// 4 cells per thread (fp32, nx % 4 == 0): float4 z, 4 connectivity bytes, float2 coarse values.
+// HALO (z-slabs): the corrected boundary planes also go into the neighbours' ghost planes.
+template <bool HALO>
 __global__ void __launch_bounds__(256)
 prolong_add_vec4_kernel(Grid g, const uint8_t* __restrict__ flags, float* __restrict__ z,
-                        const float* __restrict__ ec, int cnx, int cny, int fy, int fz) {
+                        const float* __restrict__ ec, int cnx, int cny, int fy, int fz, HaloOut ho) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 15) * 4;
     const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
-    if (i >= g.nx || j >= g.ny) return;
-    const int cj = (fy == 2) ? (j >> 1) : j;
-    const long long col = (long long)j * g.nx + i;
-    const long long ccol = (long long)cj * cnx + (i >> 1);      // fx == 2
-    const long long cplane = (long long)cnx * cny;
-    for (int k = blockIdx.z; k < g.nz; k += gridDim.z) {
-        const long long idx = (long long)k * g.plane + col;
-        const unsigned int f = *reinterpret_cast<const unsigned int*>(flags + idx);
-        if ((f & 0x40404040u) == 0u) continue;
-        const int ck = (fz == 2) ? (k >> 1) : k;
-        const float2 e = *reinterpret_cast<const float2*>(ec + (long long)ck * cplane + ccol);
-        float4 v = *reinterpret_cast<float4*>(z + idx);
-        if (f & 0x00000040u) v.x += e.x;
-        if (f & 0x00004000u) v.y += e.x;
-        if (f & 0x00400000u) v.z += e.y;
-        if (f & 0x40000000u) v.w += e.y;
-        *reinterpret_cast<float4*>(z + idx) = v;
+    if (i < g.nx && j < g.ny) {
+        const int cj = (fy == 2) ? (j >> 1) : j;
+        const long long col = (long long)j * g.nx + i;
+        const long long ccol = (long long)cj * cnx + (i >> 1);      // fx == 2
+        const long long cplane = (long long)cnx * cny;
+        for (int k = blockIdx.z; k < g.nz; k += gridDim.z) {
+            const long long idx = (long long)k * g.plane + col;
+            const unsigned int f = *reinterpret_cast<const unsigned int*>(flags + idx);
+            if ((f & 0x40404040u) == 0u) continue;
+            const int ck = (fz == 2) ? (k >> 1) : k;
+            const float2 e = *reinterpret_cast<const float2*>(ec + (long long)ck * cplane + ccol);
+            float4 v = *reinterpret_cast<float4*>(z + idx);
+            if (f & 0x00000040u) v.x += e.x;
+            if (f & 0x00004000u) v.y += e.x;
+            if (f & 0x00400000u) v.z += e.y;
+            if (f & 0x40000000u) v.w += e.y;
+            *reinterpret_cast<float4*>(z + idx) = v;
+            if (HALO) {
+                if (ho.dst_lo && k == 0) *reinterpret_cast<float4*>(static_cast<float*>(ho.dst_lo) + col) = v;
+                if (ho.dst_hi && k == g.nz - 1) *reinterpret_cast<float4*>(static_cast<float*>(ho.dst_hi) + col) = v;
+            }
+        }
     }
+    if (HALO) halo_publish(ho.counter, gridDim.x * gridDim.y * gridDim.z, ho.flag_lo, ho.flag_hi, ho.seq);
 }
 
 template <typename T, int MODE>
@@ -315,22 +357,32 @@ size_t ring_smem_bytes() {
            (size_t)RING_R * C::F_STAGE;
 }
 
-template <typename T, int MODE, bool DOT>
-void launch(const L0Args& a, cudaStream_t st) {
+template <typename T, int MODE, bool DOT, bool HALO>
+void launch_h(const L0Args& a, cudaStream_t st) {
     typedef Cfg<T> C;
     static unsigned long long configured = 0;
     const size_t smem = ring_smem_bytes<T, MODE>();
     if (first_use_on_this_device(configured))
-        cudaFuncSetAttribute(l0_ring_kernel<T, MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_ring_kernel<T, MODE, DOT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + C::TX - 1) / C::TX, (a.g.ny + C::TY - 1) / C::TY, (a.g.nz + zc - 1) / zc);
     RingCoarse rc{a.cnx, a.cny, a.g.z0 >> 1};
-    l0_ring_kernel<T, MODE, DOT><<<grid, C::NT, smem, st>>>(
+    l0_ring_kernel<T, MODE, DOT, HALO><<<grid, C::NT, smem, st>>>(
         a.g, a.flags, static_cast<const T*>(a.u), static_cast<const T*>(a.b), static_cast<T*>(a.out), (T)a.w, rc,
-        a.fz, zc, a.red_partials, a.red_counter, a.red_out);
+        a.fz, zc, a.red_partials, a.red_counter, a.red_out, a.hin, a.hout);
+}
+
+template <typename T, int MODE, bool DOT>
+void launch(const L0Args& a, cudaStream_t st) {
+    const bool halo = a.hin.flag_lo || a.hin.flag_hi || a.hout.flag_lo || a.hout.flag_hi;
+    if (halo) launch_h<T, MODE, DOT, true>(a, st);
+    else launch_h<T, MODE, DOT, false>(a, st);
 }
 
 }  // namespace
+
+// whether l0_prolong_add runs the kernel that can carry the boundary-plane push
+bool prolong_halo_supported(const L0Args& a) { return sizeof(mg_t) == 4 && (a.g.nx & 3) == 0 && a.fx == 2; }
 
 bool ring_supported(const L0Args& a, int mode) {
     // 16-byte vector accesses and the 4-byte copies of the connectivity bytes need
@@ -351,8 +403,12 @@ void l0_prolong_add(const L0Args& a, cudaStream_t st) {
     if (sizeof(mg_t) == 4 && (a.g.nx & 3) == 0 && a.fx == 2) {
         int gzv = a.g.nz < 128 ? a.g.nz : 128;
         dim3 gridv((a.g.nx + 63) / 64, (a.g.ny + 15) / 16, gzv);
-        prolong_add_vec4_kernel<<<gridv, 256, 0, st>>>(a.g, a.flags, reinterpret_cast<float*>(a.out),
-                                                       reinterpret_cast<const float*>(a.ec), a.cnx, a.cny, a.fy, a.fz);
+        if (a.hout.flag_lo || a.hout.flag_hi)
+            prolong_add_vec4_kernel<true><<<gridv, 256, 0, st>>>(a.g, a.flags, reinterpret_cast<float*>(a.out),
+                                                                 reinterpret_cast<const float*>(a.ec), a.cnx, a.cny, a.fy, a.fz, a.hout);
+        else
+            prolong_add_vec4_kernel<false><<<gridv, 256, 0, st>>>(a.g, a.flags, reinterpret_cast<float*>(a.out),
+                                                                  reinterpret_cast<const float*>(a.ec), a.cnx, a.cny, a.fy, a.fz, a.hout);
         return;
     }
     int gz = a.g.nz < 64 ? a.g.nz : 64;

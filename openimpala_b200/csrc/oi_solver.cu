@@ -312,9 +312,18 @@ struct PeerHalo {
     char* hi_base = nullptr;
     unsigned int* flags = nullptr;    // mine: [0] written by the lower neighbour, [1] by the upper
     unsigned int* counter = nullptr;  // push-kernel block counter
+    unsigned int* fused_counter = nullptr;   // two block counters of the kernels that push their own boundary planes
     unsigned int seq = 0;
     bool spin_wait = false;
     long long exchanges = 0;
+    // Boundary planes stored by the producing kernel itself (HaloOut): pending[id] = sequence number of
+    // a push nobody has waited for yet (0 = none).  The consumer of field id then only waits -- inside the
+    // kernel (HaloIn) when it can, else on the stream -- instead of launching the push kernel.
+    unsigned int pending[OI_MAX_HALO_FIELDS] = {};
+    int last_id = -1;                 // field of the most recent exchange (-1 after a collective)
+    bool fuse = true;                 // OI_HALO_FUSE=0: always the explicit push kernel + stream wait
+    bool inkernel_wait = true;        // OI_HALO_INKERNEL=0: fused pushes, but waits stay on the stream
+    long long fused_pushes = 0, inkernel_waits = 0, fences = 0;
 };
 
 typedef CUresult (*PFN_stream_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -401,6 +410,8 @@ struct oi_solver {
     // multigrid
     std::vector<HostLevel> levels;     // levels[0] is MG level 1
     std::vector<double> w_smooth, w_coarse;
+    std::vector<double> w_mid;         // smoothing weights of MG levels >= 1 that have a coarser level below (OI_MG_DEG_COARSE; default: w_smooth)
+    int w_from = 0;                    // OI_MG_W_FROM=L: MG levels >= L are visited twice per visit of their parent (W-cycle); 0 = V-cycle
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
     int tail_level = -1;               // levels[tail_level ..] are cycled by the one-CTA tail kernel (-1: none)
     // One PCG iteration captured as a CUDA graph (single slab): [0] with r.z in scalar slot 0,
@@ -446,12 +457,18 @@ std::vector<double> cheb_weights(int degree, double lo_frac, double lmax = 2.0) 
 }
 
 // ------------------------------------------------------------------ comm helpers
-// Peer path: boundary planes are stored straight into the neighbours' ghost planes
-// and the neighbours' flag words advance to this exchange's sequence number; the
-// local stream then waits on its own two flag words.  Ranks run the same sequence
-// of exchanges (SPMD), so one counter per handle orders them, and because every
-// stencil kernel is preceded by such a wait a neighbour can be at most one kernel
-// ahead: it never overwrites a ghost plane that is still being read.
+// Peer path, explicit form: one push kernel stores the two boundary planes straight into the
+// neighbours' ghost planes and advances their flag words to this exchange's sequence number; the
+// local stream then waits on its own two flag words.  Ranks run the same sequence of exchanges
+// (SPMD), so one counter per handle orders them.  Write-after-read safety of a ghost plane: a
+// neighbour's store for exchange s can only race with a local kernel still reading that plane from
+// an earlier exchange of the SAME field if nothing ordered the ranks in between; every other
+// exchange and every collective does, and peer_prepare_push / the bookkeeping of `last_id` fences
+// the one remaining case (the same field twice in a row).  The steady-state solve uses the fused
+// form below (HaloOut / HaloIn); this one serves setup, the closing residual and flux, and fields
+// whose producer cannot push.
+void peer_stream_wait(oi_solver* S, unsigned int seq);
+void peer_fence(oi_solver* S);
 bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz) {
     PeerHalo& P = S->peer;
     if (!P.on) return false;
@@ -460,6 +477,9 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
     for (size_t i = 0; i < P.mine.size(); ++i)
         if (P.mine[i].off0 == off0) { id = (int)i; break; }
     if (id < 0) return false;
+    if (P.last_id == id) peer_fence(S);                      // same field twice in a row: see above
+    P.pending[id] = 0;                                       // superseded by this explicit exchange
+    P.last_id = id;
     const int rk = S->rank, nr = S->n_ranks;
     const bool wrap = (S->g.periodic & oi::PER_Z) != 0;     // periodic box: rank 0 and rank nr-1 are neighbours
     const unsigned int seq = ++P.seq;
@@ -479,18 +499,7 @@ bool halo_exchange_peer(oi_solver* S, char* p0, size_t plane_bytes, long long nz
                   seq, P.counter, S->n_sm, S->st);
     S->launches++;
     P.exchanges++;
-    const unsigned int* wa = (rk > 0 || wrap) ? P.flags + 0 : nullptr;
-    const unsigned int* wb = (rk < nr - 1 || wrap) ? P.flags + 1 : nullptr;
-    PFN_stream_wait32 wait32 = P.spin_wait ? nullptr : driver_wait32();
-    if (wait32) {
-        if (wa && wait32(S->st, (CUdeviceptr)(uintptr_t)wa, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
-        if (wb && wait32(S->st, (CUdeviceptr)(uintptr_t)wb, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
-    } else {
-        oi::halo_wait_spin(wa, wb, seq, S->st);
-        S->launches++;
-    }
+    peer_stream_wait(S, seq);
     return true;
 }
 
@@ -527,10 +536,131 @@ void halo_exchange_bytes(oi_solver* S, void* plane0, size_t plane_bytes, long lo
 }
 
 using oi::mg_t;
+using oi::HaloIn;
+using oi::HaloOut;
+
+int peer_field_id(const oi_solver* S, const void* plane0) {
+    const PeerHalo& P = S->peer;
+    if (!P.on) return -1;
+    const unsigned long long off0 = (unsigned long long)(static_cast<const char*>(plane0) - P.arena.base);
+    for (size_t i = 0; i < P.mine.size(); ++i)
+        if (P.mine[i].off0 == off0) return (int)i;
+    return -1;
+}
+
+void peer_stream_wait(oi_solver* S, unsigned int seq) {
+    PeerHalo& P = S->peer;
+    const int rk = S->rank, nr = S->n_ranks;
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+    const unsigned int* wa = (rk > 0 || wrap) ? P.flags + 0 : nullptr;
+    const unsigned int* wb = (rk < nr - 1 || wrap) ? P.flags + 1 : nullptr;
+    PFN_stream_wait32 wait32 = P.spin_wait ? nullptr : driver_wait32();
+    if (wait32) {
+        if (wa && wait32(S->st, (CUdeviceptr)(uintptr_t)wa, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
+        if (wb && wait32(S->st, (CUdeviceptr)(uintptr_t)wb, seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            throw OiError(OI_ERR_CUDA, "cuStreamWaitValue32 failed");
+    } else {
+        oi::halo_wait_spin(wa, wb, seq, S->st);
+        S->launches++;
+    }
+}
+
+// A flag-only exchange: when it has passed on this stream, both neighbours have finished every kernel
+// they had queued before their side of it.
+void peer_fence(oi_solver* S) {
+    PeerHalo& P = S->peer;
+    const int rk = S->rank, nr = S->n_ranks;
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+    const unsigned int seq = ++P.seq;
+    unsigned int* flo = (rk > 0 || wrap) ? reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1 : nullptr;
+    unsigned int* fhi = (rk < nr - 1 || wrap) ? reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0 : nullptr;
+    oi::halo_push(nullptr, nullptr, nullptr, nullptr, 0, flo, fhi, seq, P.counter, S->n_sm, S->st);
+    S->launches++;
+    peer_stream_wait(S, seq);
+    P.last_id = -1;
+    P.fences++;
+}
+
+// The kernel about to be launched WRITES the field at plane0 and can store its boundary planes into the
+// neighbours' ghost planes itself: hand it the peer pointers and book the push.  False = not possible
+// here (single slab, NCCL halo, field outside the arena, fusion switched off): the consumer will then run
+// the explicit exchange.  A neighbour may still be reading the ghost plane this push overwrites only if
+// the very same field was exchanged last with nothing in between (every other exchange and every
+// collective orders the ranks); that case gets a fence first.
+bool peer_prepare_push(oi_solver* S, const void* plane0, size_t plane_bytes, long long nz, HaloOut* ho) {
+    PeerHalo& P = S->peer;
+    const int id = peer_field_id(S, plane0);
+    if (id < 0 || !P.fuse) return false;
+    if (P.last_id == id) peer_fence(S);
+    const int rk = S->rank, nr = S->n_ranks;
+    const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+    const unsigned int seq = ++P.seq;
+    *ho = HaloOut{};
+    if (rk > 0 || wrap) {
+        const HaloDesc& d = P.lo.f[id];
+        ho->dst_lo = P.lo_base + d.off0 + d.plane_bytes * (unsigned long long)d.nz;
+        ho->flag_lo = reinterpret_cast<unsigned int*>(P.lo_base + P.lo.flag_off) + 1;
+    }
+    if (rk < nr - 1 || wrap) {
+        const HaloDesc& d = P.hi.f[id];
+        ho->dst_hi = P.hi_base + d.off0 - d.plane_bytes;
+        ho->flag_hi = reinterpret_cast<unsigned int*>(P.hi_base + P.hi.flag_off) + 0;
+    }
+    (void)plane_bytes; (void)nz;
+    ho->counter = P.fused_counter;
+    ho->seq = seq;
+    P.pending[id] = seq;
+    P.last_id = id;
+    P.exchanges++;
+    P.fused_pushes++;
+    return true;
+}
+
+// the field at plane0 is about to be written by a kernel that does not push: forget a booked push
+void peer_invalidate(oi_solver* S, const void* plane0) {
+    const int id = peer_field_id(S, plane0);
+    if (id >= 0) S->peer.pending[id] = 0;
+}
+void peer_invalidate_all(oi_solver* S) {
+    for (auto& p : S->peer.pending) p = 0;
+}
+
+// Ghost planes of the field at plane0 are about to be read.  If its producer pushed them (pending), only
+// the wait is left: inside the consuming kernel when `in` is given (ring kernels), else on the stream.
+// Otherwise the explicit exchange runs (push kernel + wait, NCCL send/recv, or the periodic wrap on a
+// single slab).
+void halo_consume(oi_solver* S, void* plane0, size_t plane_bytes, long long nz, HaloIn* in) {
+    if (in) *in = HaloIn{};
+    if (S->n_ranks > 1) {
+        PeerHalo& P = S->peer;
+        const int id = peer_field_id(S, plane0);
+        if (id >= 0 && P.pending[id]) {
+            const unsigned int seq = P.pending[id];
+            P.pending[id] = 0;
+            if (in && P.inkernel_wait) {
+                const int rk = S->rank, nr = S->n_ranks;
+                const bool wrap = (S->g.periodic & oi::PER_Z) != 0;
+                in->flag_lo = (rk > 0 || wrap) ? P.flags + 0 : nullptr;
+                in->flag_hi = (rk < nr - 1 || wrap) ? P.flags + 1 : nullptr;
+                in->seq = seq;
+                P.inkernel_waits++;
+            } else {
+                peer_stream_wait(S, seq);
+            }
+            return;
+        }
+    }
+    halo_exchange_bytes(S, plane0, plane_bytes, nz);
+}
 
 template <typename T>
-inline void halo0(oi_solver* S, T* v) {
-    halo_exchange_bytes(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz);
+inline void halo0(oi_solver* S, T* v, HaloIn* in = nullptr) {
+    halo_consume(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz, in);
+}
+template <typename T>
+inline bool push0(oi_solver* S, T* v, HaloOut* ho) {
+    return S->n_ranks > 1 && peer_prepare_push(S, v, (size_t)S->g.plane * sizeof(T), S->g.nz, ho);
 }
 inline void haloL(oi_solver* S, const CoarseLevel& L, mg_t* v) {
     if (L.replicated) {                // whole level on every rank: ghost planes are the box faces
@@ -545,6 +675,7 @@ template <typename T>
 void gather_level(oi_solver* S, const HostLevel& dist, const T* src_plane0, T* dst_plane0) {
     NcclApi& N = nccl_api();
     const size_t plane = (size_t)dist.L.plane;
+    S->peer.last_id = -1;              // a collective orders the ranks
     NCCL_CHECK(N.GroupStart());
     for (int r = 0; r < S->n_ranks; ++r) {
         T* dst = dst_plane0 + plane * (size_t)dist.slab_z0[r];
@@ -556,14 +687,17 @@ void gather_level(oi_solver* S, const HostLevel& dist, const T* src_plane0, T* d
 
 void allreduce_sum_f64(oi_solver* S, double* d, int n) {
     if (S->n_ranks <= 1) return;
+    S->peer.last_id = -1;              // a collective orders the ranks
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclFloat64, ncclSum, S->comm, S->st));
 }
 void allreduce_sum_u64(oi_solver* S, unsigned long long* d, int n) {
     if (S->n_ranks <= 1) return;
+    S->peer.last_id = -1;
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclUint64, ncclSum, S->comm, S->st));
 }
 void allreduce_max_i32(oi_solver* S, int* d, int n) {
     if (S->n_ranks <= 1) return;
+    S->peer.last_id = -1;
     NCCL_CHECK(nccl_api().AllReduce(d, d, n, ncclInt32, ncclMax, S->comm, S->st));
 }
 
@@ -788,6 +922,11 @@ bool peer_setup(oi_solver* S) {
         CUDA_CHECK(cudaMemsetAsync(P.arena.base, 0, need, S->st));
         P.flags = static_cast<unsigned int*>(P.arena.take(256));
         P.counter = P.flags + 8;
+        P.fused_counter = P.flags + 16;
+        { const char* e = getenv("OI_HALO_FUSE"); P.fuse = !(e && e[0] == '0'); }
+        { const char* e = getenv("OI_HALO_INKERNEL"); P.inkernel_wait = !(e && e[0] == '0'); }
+        for (auto& q : P.pending) q = 0;
+        P.last_id = -1;
         auto reg = [&](char* plane0, size_t plane_bytes, long long nz) {
             HaloDesc d{(unsigned long long)(plane0 - P.arena.base), (unsigned long long)plane_bytes, nz};
             P.mine.push_back(d);
@@ -947,10 +1086,10 @@ void coarse_cycle(oi_solver* S, size_t l) {
         prof_mark(S, "mg tail");
         oi::TailArgs ta{};
         ta.n_levels = (int)(S->levels.size() - l);
-        ta.deg = (int)S->w_smooth.size();
+        ta.deg = (int)S->w_mid.size();
         ta.deg_c = (int)S->w_coarse.size();
         for (int q = 0; q < ta.n_levels; ++q) ta.L[q] = S->levels[l + q].L;
-        for (int q = 0; q < ta.deg; ++q) ta.w[q] = (mg_t)S->w_smooth[q];
+        for (int q = 0; q < ta.deg; ++q) ta.w[q] = (mg_t)S->w_mid[q];
         for (int q = 0; q < ta.deg_c; ++q) ta.wc[q] = (mg_t)S->w_coarse[q];
         // OI_TAIL_SMEM=0: keep the fields in global memory (the variant the GPU suite has run)
         const char* se = getenv("OI_TAIL_SMEM");
@@ -959,7 +1098,7 @@ void coarse_cycle(oi_solver* S, size_t l) {
         return;
     }
     const bool last = (l + 1 == S->levels.size());
-    const std::vector<double>& w = last ? S->w_coarse : S->w_smooth;
+    const std::vector<double>& w = last ? S->w_coarse : S->w_mid;
     const int deg = (int)w.size();
     mg_t* cur = L.t;
     mg_t* oth = L.x;
@@ -973,12 +1112,17 @@ void coarse_cycle(oi_solver* S, size_t l) {
     }
     if (!last) {
         HostLevel& hn = S->levels[l + 1];
-        haloL(S, L, cur);
-        oi::coarse_residual(L, cur, L.b, oth, S->st); S->launches++;
-        oi::coarse_restrict(L, oth, hn.L, hn.L.b, S->st); S->launches++;
-        coarse_cycle(S, l + 1);
-        prof_mark(S, lvl_names[l < 4 ? l : 4]);
-        oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
+        // W-cycle from MG level w_from on: the child (MG level l + 2) is visited twice, each visit
+        // on the residual of the correction so far (symmetric: 2B - BAB for a symmetric child cycle B)
+        const int visits = (S->w_from > 0 && (int)l + 2 >= S->w_from) ? 2 : 1;
+        for (int v = 0; v < visits; ++v) {
+            haloL(S, L, cur);
+            oi::coarse_residual(L, cur, L.b, oth, S->st); S->launches++;
+            oi::coarse_restrict(L, oth, hn.L, hn.L.b, S->st); S->launches++;
+            coarse_cycle(S, l + 1);
+            prof_mark(S, lvl_names[l < 4 ? l : 4]);
+            oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
+        }
         for (int s = 0; s < deg; ++s) {
             haloL(S, L, cur);
             oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], S->st);
@@ -1004,6 +1148,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         oi::l0_jacobi_precond_dot(S->g, S->flags.p, S->r.p, S->za.p, S->d_partials, S->d_counter,
                                   dot_out ? dot_out : S->d_scal + 15, S->n_sm, S->st);
         S->launches++;
+        peer_invalidate(S, S->za.p);
         S->zres = S->za.p;
         if (dot_out) allreduce_sum_f64(S, dot_out, 1);
         return;
@@ -1021,19 +1166,30 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     if (!first_done) {
         L0Args a = l0args(S, nullptr, rhs, cur, w[0], nullptr);
         oi::l0_jacobi_first(a, S->st); S->launches++;
+        peer_invalidate(S, cur);
     }
     // Two sweeps per pass where the pair kernel applies (one slab, non-periodic, ring layout): the
     // 512-thread variant with packed fp32 arithmetic takes 4.45 ms at 1024^3 against 4.86 ms for two
     // single sweeps.  OI_PAIR=0 turns it off, OI_PAIR=1 selects the 256-thread variant (read per
     // call so that tests can compare the paths).
     const char* pair_env = getenv("OI_PAIR");
-    const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '2') ? pair_env[0] - '0' : 2;
+    const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '3') ? pair_env[0] - '0' : 2;
     const bool no_pair = pair_variant == 0;
-    bool use_pair = false;
+    bool use_pair = false, ring1 = false;
     {
         L0Args a = l0args(S, cur, rhs, oth, 0.0, nullptr);
-        use_pair = !no_pair && variant == 0 && S->n_ranks == 1 && oi::pair_supported(a) && oi::ring_supported(a, 1);
+        ring1 = variant == 0 && oi::ring_supported(a, 1);
+        use_pair = !no_pair && variant == 0 && S->n_ranks == 1 && oi::pair_supported(a) && ring1;
     }
+    // One single sweep cur -> oth.  z-slabs: the ghost planes of cur come from its producer's push (the
+    // boundary CTAs wait inside the kernel) and, when somebody will read oth's ghost planes (`consumed`),
+    // this kernel stores oth's boundary planes into the neighbours itself.
+    auto single_sweep = [&](L0Args& a, bool addc, bool dot, bool consumed) {
+        const bool ring = ring1 && !addc;
+        halo0(S, cur, ring ? &a.hin : nullptr);
+        if (!(ring && consumed && push0(S, oth, &a.hout))) peer_invalidate(S, oth);
+        oi::l0_smooth(a, addc, dot, variant, S->st); S->launches++;
+    };
     for (int s = 1; s < deg;) {
         L0Args a = l0args(S, cur, rhs, oth, w[s], dot_out);
         if (use_pair && s + 1 < deg) {
@@ -1041,9 +1197,8 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             oi::l0_smooth_pair(a, w[s], w[s + 1], dot, pair_variant, S->st); S->launches++;
             s += 2;
         } else {
-            halo0(S, cur);
             const bool dot = (!have_coarse && s == deg - 1 && dot_out);
-            oi::l0_smooth(a, false, dot, variant, S->st); S->launches++;
+            single_sweep(a, false, dot, have_coarse || s + 1 < deg);
             s += 1;
         }
         std::swap(cur, oth);
@@ -1051,16 +1206,18 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     if (have_coarse) {
         HostLevel& h1 = S->levels[0];
         prof_mark(S, "l0 residual+restrict");
-        halo0(S, cur);
         {
             L0Args a = l0args(S, cur, rhs, h1.L.b, 0.0, nullptr);
             a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
+            const bool ring2 = variant == 0 && oi::ring_supported(a, 2);
+            halo0(S, cur, ring2 ? &a.hin : nullptr);
             if (variant != 1) {
                 oi::l0_residual_restrict(a, variant, S->st); S->launches++;
             } else {
                 // unfused cross-check path: residual to scratch, gather-restrict
                 a.out = oth;
                 oi::l0_residual(a, S->st); S->launches++;
+                peer_invalidate(S, oth);
                 CoarseLevel fine{};
                 fine.nx = S->g.nx; fine.ny = S->g.ny; fine.nz = S->g.nz; fine.plane = S->g.plane;
                 fine.fx = f0.fx; fine.fy = f0.fy; fine.fz = f0.fz;
@@ -1074,15 +1231,14 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             L0Args a = l0args(S, cur, rhs, oth, w[deg - 1 - s], dot_out);
             a.ec = h1.L.x; a.fx = f0.fx; a.fy = f0.fy; a.fz = f0.fz;
             bool addc = (s == 0);
-            if (addc && ((variant == 0 && oi::ring_supported(a, 1)) || S->g.periodic)) {
-                // ring kernels take the field as is: apply the correction first
+            if (addc && (ring1 || S->g.periodic)) {
+                // ring kernels take the field as is: apply the correction first (in place; the corrected
+                // boundary planes go to the neighbours from the prolongation kernel)
                 L0Args pa = a;
                 pa.out = cur;
+                if (!(oi::prolong_halo_supported(pa) && push0(S, cur, &pa.hout))) peer_invalidate(S, cur);
                 oi::l0_prolong_add(pa, S->st); S->launches++;
                 addc = false;
-                halo0(S, cur);
-            } else if (s > 0) {
-                halo0(S, cur);
             }
             if (use_pair && !addc && s + 1 < deg) {
                 const bool dot = (s + 1 == deg - 1) && dot_out;
@@ -1090,7 +1246,13 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
                 s += 2;
             } else {
                 const bool dot = (s == deg - 1) && dot_out;
-                oi::l0_smooth(a, addc, dot, variant, S->st); S->launches++;
+                if (addc) {
+                    // fused-correction sweep of the z-march / gather variants: reads cur as stored plus P e_c
+                    peer_invalidate(S, oth);
+                    oi::l0_smooth(a, true, dot, variant, S->st); S->launches++;
+                } else {
+                    single_sweep(a, false, dot, s + 1 < deg);
+                }
                 s += 1;
             }
             std::swap(cur, oth);
@@ -1148,19 +1310,26 @@ double true_residual(oi_solver* S) {
 void iteration_front(oi_solver* S, double* d_rz, double* d_pq, double* d_rr, bool fuse_first) {
     const long long n = S->n_local;
     prof_mark(S, "apply q=Ap (+halo)");
-    halo0(S, S->p.p);
     L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, d_pq);
+    // ghost planes of p: pushed by the xpby that made p (the boundary CTAs of the apply wait for them
+    // inside the kernel), else the explicit exchange
+    const bool ring0 = S->prm.stencil_variant == 0 && oi::ring_supported(a, 0);
+    halo0(S, S->p.p, ring0 ? &a.hin : nullptr);
     oi::l0_apply(a, true, S->prm.stencil_variant, S->st); S->launches++;       // q = A p, pq = p.q
     prof_mark(S, "allreduce p.q");
     allreduce_sum_f64(S, d_pq, 1);
     prof_mark(S, "axpy2+dot+first sweep");
     // MG path: x += alpha p is deferred to the xpby of the second half (which reads p anyway);
     // if the loop ends between the halves instead, vec_axpy applies it
-    if (fuse_first)
+    if (fuse_first) {
+        // the first sweep z1 lands in za: its boundary planes go to the neighbours from this kernel
+        HaloOut ho{};
+        const bool pushed = oi::vec_halo_supported(S->g.plane, S->n_local) && push0(S, S->za.p, &ho);
+        if (!pushed) peer_invalidate(S, S->za.p);
         oi::vec_axpy2_dot_first(S->g, S->flags.p, n, nullptr, S->r.p, S->p.p, S->q.p, S->r32.p,
                                 S->za.p, d_rz, d_pq, first_smoothing_weight(S), S->d_partials,
-                                S->d_counter, d_rr, S->n_sm, S->st);
-    else
+                                S->d_counter, d_rr, S->n_sm, S->st, pushed ? &ho : nullptr);
+    } else
         oi::vec_axpy2_dot(n, S->x.p, S->r.p, S->p.p, S->q.p, d_rz, d_pq, S->d_partials,
                           S->d_counter, d_rr, S->n_sm, S->st);
     S->launches++;
@@ -1172,8 +1341,11 @@ void iteration_front(oi_solver* S, double* d_rz, double* d_pq, double* d_rr, boo
 void iteration_back(oi_solver* S, double* d_rz, double* d_rzn, double* d_pq, bool fuse_first) {
     apply_precond(S, d_rzn, fuse_first);
     prof_mark(S, "xpby");
+    HaloOut ho{};
+    const bool pushed = oi::vec_halo_supported(S->g.plane, S->n_local) && push0(S, S->p.p, &ho);   // new p -> neighbours' ghost planes
+    if (!pushed) peer_invalidate(S, S->p.p);
     oi::vec_xpby(S->n_local, S->flags.p, S->p.p, S->zres, d_rzn, d_rz, fuse_first ? S->x.p : nullptr, d_rz, d_pq,
-                 S->n_sm, S->st);
+                 S->n_sm, S->st, S->g.plane, pushed ? &ho : nullptr);
     S->launches++;
 }
 
@@ -1264,13 +1436,14 @@ void run_solve(oi_solver* S) {
     const bool use_graph = iter_graph_wanted(S);
     {   // OI_PAIR is read per call and baked into a captured iteration
         const char* pe = getenv("OI_PAIR");
-        const int sig = (pe && pe[0] >= '0' && pe[0] <= '2') ? pe[0] - '0' : 2;
+        const int sig = (pe && pe[0] >= '0' && pe[0] <= '3') ? pe[0] - '0' : 2;
         if (sig != S->graph_pair_sig) drop_iter_graphs(S);
         S->graph_pair_sig = sig;
     }
     double* d_rz = sc + 0; double* d_pq = sc + 1; double* d_rr = sc + 2; double* d_rzn = sc + 3;
 
     prof_mark(S, "setup/restart/checks");
+    peer_invalidate_all(S);
     double rr = true_residual(S);
     const double r0 = std::sqrt(rr);
     // HYPRE: ||r|| <= max(atol, eps*||b||), ||b|| = 0 -> relative to ||r0||
@@ -1292,6 +1465,7 @@ void run_solve(oi_solver* S) {
             // (re)start: z = M r, p = z
             apply_precond(S, d_rz);
             oi::vec_from_mg(n, S->p.p, S->zres, S->n_sm, S->st); S->launches++;
+            peer_invalidate(S, S->p.p);
             const bool fuse_first = (S->prm.precond == OI_PRECOND_MG);
             while (it < S->prm.maxiter) {
                 ++it;
@@ -1795,6 +1969,12 @@ int oi_create(oi_solver** out, const oi_params* p) {
         static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
         S->w_smooth = cheb_weights(deg, deg <= 8 ? lo_tab[deg] : 0.07);
         S->w_coarse = cheb_weights(8, 0.05);
+        S->w_mid = S->w_smooth;
+        if (const char* e = getenv("OI_MG_DEG_COARSE")) {
+            const int dc = std::atoi(e);
+            if (dc >= 1 && dc <= 16) S->w_mid = cheb_weights(dc, dc <= 8 ? lo_tab[dc] : 0.07);
+        }
+        if (const char* e = getenv("OI_MG_W_FROM")) S->w_from = std::max(0, std::atoi(e));
         CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
         CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));
         long long nb = std::max<long long>(oi::l0_max_blocks(g, S->n_sm), oi::vec_max_blocks(S->n_sm));
@@ -2153,6 +2333,7 @@ int oi_apply_operator(oi_solver* S, const double* hx, double* hy) {
         ensure_device(S);
         CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
         CUDA_CHECK(cudaMemcpyAsync(S->p.p, hx, (size_t)S->n_local * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        peer_invalidate_all(S);
         halo0(S, S->p.p);
         L0Args a = l0args(S, S->p.p, nullptr, S->q.p, 1.0, S->d_scal + 14);
         oi::l0_apply(a, true, S->prm.stencil_variant, S->st); S->launches++;
@@ -2169,6 +2350,7 @@ int oi_apply_precond(oi_solver* S, const double* hr, double* hz) {
         ensure_device(S);
         if (!S->hierarchy_built) build_hierarchy(S);
         CUDA_CHECK(cudaMemcpyAsync(S->r.p, hr, (size_t)S->n_local * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        peer_invalidate_all(S);
         apply_precond(S, S->d_scal + 13);
         oi::vec_from_mg(S->n_local, S->q.p, S->zres, S->n_sm, S->st); S->launches++;
         copy_out(S, S->q.p, hz, (size_t)S->n_local);

@@ -3,6 +3,8 @@
 // struct axpy / inner-product calls inside the Krylov loop (reference call site
 // src/props/TortuosityHypre.cpp:681-683).  Scalars (alpha, beta) are read from
 // device memory so the loop needs no host round trip to form them.
+#include <cstdlib>
+
 #include "oi_kernels.h"
 
 namespace oi {
@@ -47,48 +49,41 @@ axpy2_dot_kernel(long long n, double* __restrict__ x, double* __restrict__ r,
 // z1 = w0 * r_new / diag.  Saves re-reading r and one launch per Krylov iteration.
 // UPDATE_X = false: x += alpha p is left to the next xpby (which has p in hand anyway), so this
 // kernel touches neither x nor p.
-template <bool UPDATE_X>
-__global__ void __launch_bounds__(VT)
-axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, double* __restrict__ x,
-                       double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
-                       mg_t* __restrict__ r32, mg_t* __restrict__ z1, const double* __restrict__ num,
-                       const double* __restrict__ den, double w0, double* partials, unsigned int* counter,
-                       double* out) {
-    __shared__ double winv[64];
-    if (threadIdx.x < 64) {
-        const int t = threadIdx.x;
-        const double d = row_diag<double>((unsigned int)t, g);
-        winv[t] = d > 0.0 ? w0 / d : 0.0;
-    }
-    __syncthreads();
-    const double a = num[0] / den[0];
-    const long long stride = (long long)gridDim.x * VT * 2;
+// Every vector here is zero on cells that are not unknowns (solid, non-percolating,
+// Dirichlet planes: p = q = r = 0 there and x keeps its value), so a 16-byte pair
+// without an unknown is skipped: its sectors are never fetched or written.  NC pairs
+// per trip, all their loads issued before the first store (the compiler cannot
+// reorder a load of x[i2] over a store to x[i]), and the flags of the next trip are
+// fetched a trip ahead, so the flag -> data dependency is off the critical path.
+// Works on the pairs [lo, hi) with `nthr` threads striding together, this one being thread `t`;
+// PUSH: the range is a boundary plane and z1 also goes to dst (a neighbour's ghost plane).
+// Returns this thread's share of r.r.
+template <bool UPDATE_X, bool PUSH, int NC>
+__device__ __forceinline__ double axpy2_first_range(long long lo, long long hi, long long t, long long nthr,
+                                                    const uint8_t* __restrict__ flags, double* __restrict__ x,
+                                                    double* __restrict__ r, const double* __restrict__ p,
+                                                    const double* __restrict__ q, mg_t* __restrict__ r32,
+                                                    mg_t* __restrict__ z1, double a, const double* winv,
+                                                    mg_t* __restrict__ dst) {
+    const long long stride = nthr * 2;
     double acc = 0.0;
-    const long long n2 = n & ~1LL;
     typedef typename Vec2<mg_t>::type mg2;
-    // Every vector here is zero on cells that are not unknowns (solid, non-percolating,
-    // Dirichlet planes: p = q = r = 0 there and x keeps its value), so a 16-byte pair
-    // without an unknown is skipped: its sectors are never fetched or written.  NC pairs
-    // per trip, all their loads issued before the first store (the compiler cannot
-    // reorder a load of x[i2] over a store to x[i]), and the flags of the next trip are
-    // fetched a trip ahead, so the flag -> data dependency is off the critical path.
-    constexpr int NC = 4;
     constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
-    const long long i0 = ((long long)blockIdx.x * VT + threadIdx.x) * 2;
+    const long long i0 = lo + t * 2;
     unsigned int fnext[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const long long ii = i0 + c * stride;
-        fnext[c] = (ii < n2) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
+        fnext[c] = (ii < hi) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
     }
-    for (long long i = i0; i < n2; i += NC * stride) {
+    for (long long i = i0; i < hi; i += NC * stride) {
         unsigned int f[NC];
         double2 xv[NC], rv[NC], pv[NC], qv[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             f[c] = fnext[c];
             const long long in = i + (NC + c) * stride;
-            fnext[c] = (in < n2) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
+            fnext[c] = (in < hi) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -120,18 +115,60 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
                 zv.y = (f1 & F_UNK) ? (mg_t)(rv[c].y * winv[f1 & 63u]) : (mg_t)0;
                 *reinterpret_cast<mg2*>(r32 + ii) = rr;
                 *reinterpret_cast<mg2*>(z1 + ii) = zv;
+                if (PUSH) *reinterpret_cast<mg2*>(dst + (ii - lo)) = zv;
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
-        const long long i = n2;
-        if (UPDATE_X) x[i] += a * p[i];
-        const double rv = r[i] - a * q[i];
-        r[i] = rv;
-        acc += rv * rv;
-        const unsigned int f = flags[i];
-        r32[i] = (mg_t)rv;
-        z1[i] = (f & F_UNK) ? (mg_t)(rv * winv[f & 63u]) : (mg_t)0;
+    return acc;
+}
+
+// HALO (z-slabs): the first `halo_blocks` blocks own the two boundary planes and store z1 into the
+// neighbours' ghost planes as well; the last block to finish publishes the exchange (needs an even
+// plane size and at least two planes).
+template <bool UPDATE_X, bool HALO, int NCI>
+__global__ void __launch_bounds__(VT, NCI == 4 ? 0 : 4)
+axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, double* __restrict__ x,
+                       double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
+                       mg_t* __restrict__ r32, mg_t* __restrict__ z1, const double* __restrict__ num,
+                       const double* __restrict__ den, double w0, double* partials, unsigned int* counter,
+                       double* out, int halo_blocks, HaloOut ho) {
+    __shared__ double winv[64];
+    if (threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        const double d = row_diag<double>((unsigned int)t, g);
+        winv[t] = d > 0.0 ? w0 / d : 0.0;
+    }
+    __syncthreads();
+    const double a = num[0] / den[0];
+    const long long n2 = n & ~1LL;
+    double acc = 0.0;
+    if (!HALO) {
+        acc = axpy2_first_range<UPDATE_X, false, NCI>(0, n2, (long long)blockIdx.x * VT + threadIdx.x,
+                                                    (long long)gridDim.x * VT, flags, x, r, p, q, r32, z1, a, winv, nullptr);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
+            const long long i = n2;
+            if (UPDATE_X) x[i] += a * p[i];
+            const double rv = r[i] - a * q[i];
+            r[i] = rv;
+            acc += rv * rv;
+            const unsigned int f = flags[i];
+            r32[i] = (mg_t)rv;
+            z1[i] = (f & F_UNK) ? (mg_t)(rv * winv[f & 63u]) : (mg_t)0;
+        }
+    } else {
+        const long long plane = g.plane, top = n - plane;
+        if ((int)blockIdx.x < halo_blocks) {
+            const long long t = (long long)blockIdx.x * VT + threadIdx.x, nthr = (long long)halo_blocks * VT;
+            if (ho.dst_lo) acc += axpy2_first_range<UPDATE_X, true, 2>(0, plane, t, nthr, flags, x, r, p, q, r32, z1, a, winv, static_cast<mg_t*>(ho.dst_lo));
+            else acc += axpy2_first_range<UPDATE_X, false, 2>(0, plane, t, nthr, flags, x, r, p, q, r32, z1, a, winv, nullptr);
+            if (ho.dst_hi) acc += axpy2_first_range<UPDATE_X, true, 2>(top, n, t, nthr, flags, x, r, p, q, r32, z1, a, winv, static_cast<mg_t*>(ho.dst_hi));
+            else acc += axpy2_first_range<UPDATE_X, false, 2>(top, n, t, nthr, flags, x, r, p, q, r32, z1, a, winv, nullptr);
+        } else if (top > plane) {
+            acc = axpy2_first_range<UPDATE_X, false, NCI>(plane, top, (long long)(blockIdx.x - halo_blocks) * VT + threadIdx.x,
+                                                        (long long)(gridDim.x - halo_blocks) * VT, flags, x, r, p, q, r32, z1, a,
+                                                        winv, nullptr);
+        }
+        halo_publish(ho.counter, gridDim.x, ho.flag_lo, ho.flag_hi, ho.seq);
     }
     double v[1] = {acc};
     grid_reduce<1>(v, partials, counter, out);
@@ -140,26 +177,25 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
 // p = z + beta p, skipping 16-byte pairs without an unknown (z = p = 0 there).
 // UPDATE_X: first x += alpha p with the OLD p (the solution update deferred from the
 // residual kernel: p is read once for both).
-template <bool UPDATE_X>
-__global__ void __launch_bounds__(VT)
-xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ p, const mg_t* __restrict__ z,
-            const double* __restrict__ num, const double* __restrict__ den, double* __restrict__ x,
-            const double* __restrict__ anum, const double* __restrict__ aden) {
-    const double bta = num[0] / den[0];
-    const double alpha = UPDATE_X ? anum[0] / aden[0] : 0.0;
-    const long long stride = (long long)gridDim.x * VT * 2;
-    const long long n2 = n & ~1LL;
+// Works on the pairs [lo, hi) with `nthr` threads striding together, this one being thread `t`.
+// PUSH: the range is a boundary plane; the new values also go to dst (a neighbour's ghost plane, whose
+// element 0 corresponds to element lo).  NC pairs per trip: loads first, then stores.
+template <bool UPDATE_X, bool PUSH, int NC>
+__device__ __forceinline__ void xpby_range(long long lo, long long hi, long long t, long long nthr,
+                                           const uint8_t* __restrict__ flags, double* __restrict__ p,
+                                           const mg_t* __restrict__ z, double* __restrict__ x, double bta,
+                                           double alpha, double* __restrict__ dst) {
+    const long long stride = nthr * 2;
     typedef typename Vec2<mg_t>::type mg2;
     constexpr unsigned int UNK2 = (unsigned int)F_UNK | ((unsigned int)F_UNK << 8);
-    constexpr int NC = 4;            // pairs per trip: loads first, then stores (see axpy2_dot_first_kernel)
-    const long long i0 = ((long long)blockIdx.x * VT + threadIdx.x) * 2;
+    const long long i0 = lo + t * 2;
     unsigned int fnext[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const long long ii = i0 + c * stride;
-        fnext[c] = (ii < n2) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
+        fnext[c] = (ii < hi) ? *reinterpret_cast<const unsigned short*>(flags + ii) : 0u;
     }
-    for (long long i = i0; i < n2; i += NC * stride) {
+    for (long long i = i0; i < hi; i += NC * stride) {
         unsigned int f[NC];
         double2 pv[NC], xv[NC];
         mg2 zv[NC];
@@ -167,7 +203,7 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
         for (int c = 0; c < NC; ++c) {
             f[c] = fnext[c];
             const long long in = i + (NC + c) * stride;
-            fnext[c] = (in < n2) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
+            fnext[c] = (in < hi) ? *reinterpret_cast<const unsigned short*>(flags + in) : 0u;
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -186,12 +222,46 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
                 }
                 pv[c].x = (double)zv[c].x + bta * pv[c].x; pv[c].y = (double)zv[c].y + bta * pv[c].y;
                 *reinterpret_cast<double2*>(p + i + c * stride) = pv[c];
+                if (PUSH) *reinterpret_cast<double2*>(dst + (i + c * stride - lo)) = pv[c];
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
-        if (UPDATE_X) x[n2] += alpha * p[n2];
-        p[n2] = (double)z[n2] + bta * p[n2];
+}
+
+// HALO (z-slabs): the first blocks of the grid own the two boundary planes and store the new p into the
+// neighbours' ghost planes as well, the rest of the grid runs the plain loop over the interior planes;
+// the last block to finish publishes the exchange.
+template <bool UPDATE_X, bool HALO, int NCI>
+__global__ void __launch_bounds__(VT, HALO ? 3 : (NCI == 4 ? 0 : 4))      // (HALO: keep the three blocks per SM of the plain kernel)
+xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ p, const mg_t* __restrict__ z,
+            const double* __restrict__ num, const double* __restrict__ den, double* __restrict__ x,
+            const double* __restrict__ anum, const double* __restrict__ aden, long long plane, int halo_blocks,
+            HaloOut ho) {
+    const double bta = num[0] / den[0];
+    const double alpha = UPDATE_X ? anum[0] / aden[0] : 0.0;
+    const long long n2 = n & ~1LL;
+    if (!HALO) {
+        xpby_range<UPDATE_X, false, NCI>(0, n2, (long long)blockIdx.x * VT + threadIdx.x, (long long)gridDim.x * VT,
+                                       flags, p, z, x, bta, alpha, nullptr);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < n) {
+            if (UPDATE_X) x[n2] += alpha * p[n2];
+            p[n2] = (double)z[n2] + bta * p[n2];
+        }
+    } else {
+        // plane and n are even here (checked by the launcher)
+        const long long top = n - plane;
+        if ((int)blockIdx.x < halo_blocks) {
+            const long long t = (long long)blockIdx.x * VT + threadIdx.x, nthr = (long long)halo_blocks * VT;
+            if (ho.dst_lo) xpby_range<UPDATE_X, true, 1>(0, plane, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_lo));
+            else xpby_range<UPDATE_X, false, 1>(0, plane, t, nthr, flags, p, z, x, bta, alpha, nullptr);
+            // (at least two planes, checked by the launcher: the two boundary planes are distinct)
+            if (ho.dst_hi) xpby_range<UPDATE_X, true, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_hi));
+            else xpby_range<UPDATE_X, false, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, nullptr);
+        } else if (top > plane) {
+            xpby_range<UPDATE_X, false, 4>(plane, top, (long long)(blockIdx.x - halo_blocks) * VT + threadIdx.x,
+                                           (long long)(gridDim.x - halo_blocks) * VT, flags, p, z, x, bta, alpha, nullptr);
+        }
+        halo_publish(ho.counter, gridDim.x, ho.flag_lo, ho.flag_hi, ho.seq);
     }
 }
 
@@ -260,6 +330,12 @@ inline int nblocks(long long work_items, int n_sm) {
 
 int vec_max_blocks(int n_sm) { return n_sm * 8; }
 
+// OI_VEC_NC=2|4: pairs per trip of the residual-update and xpby kernels (4 = default)
+static int vec_nc() {
+    const char* e = getenv("OI_VEC_NC");
+    return (e && e[0] == '2') ? 2 : 4;
+}
+
 void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
                    const double* num, const double* den, double* partials, unsigned int* counter,
                    double* out, int n_sm, cudaStream_t st) {
@@ -268,19 +344,49 @@ void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const dou
 void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, double* x, double* r,
                          const double* p, const double* q, mg_t* r32, mg_t* z1, const double* num,
                          const double* den, double w0, double* partials, unsigned int* counter,
-                         double* out, int n_sm, cudaStream_t st) {
-    if (x)
-        axpy2_dot_first_kernel<true><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num,
-                                                                                den, w0, partials, counter, out);
+                         double* out, int n_sm, cudaStream_t st, const HaloOut* ho) {
+    const int nb = nblocks((n + 1) / 2, n_sm);
+    const HaloOut none{};
+    if (ho && x == nullptr && vec_halo_supported(g.plane, n)) {
+        int hb = (int)((2 * g.plane * (long long)nb + n - 1) / n);
+        hb = hb < 1 ? 1 : hb;
+        // (the grid reduction's scratch holds vec_max_blocks + a margin of blocks: stay within nb)
+        const int nbt = nb;
+        hb = hb >= nbt ? nbt - 1 : hb;
+        if (hb < 1) hb = 1;
+        axpy2_dot_first_kernel<false, true, 4><<<nbt, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
+                                                                   counter, out, hb, *ho);
+    } else if (x)
+        axpy2_dot_first_kernel<true, false, 4><<<nb, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
+                                                                  counter, out, 0, none);
+    else if (vec_nc() == 2)       // OI_VEC_NC=2: two pairs per trip, four blocks per SM (A/B knob)
+        axpy2_dot_first_kernel<false, false, 2><<<nb, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
+                                                                   counter, out, 0, none);
     else
-        axpy2_dot_first_kernel<false><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num,
-                                                                                 den, w0, partials, counter, out);
+        axpy2_dot_first_kernel<false, false, 4><<<nb, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
+                                                                   counter, out, 0, none);
 }
 void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const double* num,
-              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st) {
-    if (x) xpby_kernel<true><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden);
-    else xpby_kernel<false><<<nblocks((n + 1) / 2, n_sm), VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr);
+              const double* den, double* x, const double* anum, const double* aden, int n_sm, cudaStream_t st,
+              long long plane, const HaloOut* ho) {
+    const int nb = nblocks((n + 1) / 2, n_sm);
+    const HaloOut none{};
+    if (ho && vec_halo_supported(plane, n)) {
+        // enough blocks for the two boundary planes to finish with the interior
+        int hb = (int)((2 * plane * (long long)nb + n - 1) / n);
+        hb = hb < 1 ? 1 : hb;
+        const int nbt = nb + hb;
+        if (x) xpby_kernel<true, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, plane, hb, *ho);
+        else xpby_kernel<false, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr, plane, hb, *ho);
+    } else {
+        if (x && vec_nc() == 2) xpby_kernel<true, false, 2><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
+        else if (x) xpby_kernel<true, false, 4><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
+        else xpby_kernel<false, false, 4><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr, 0, 0, none);
+    }
 }
+// whether the two kernels above can carry the boundary-plane push for this plane size
+// (even plane: a pair never straddles two planes; at least two planes: the boundary planes are distinct)
+bool vec_halo_supported(long long plane, long long n) { return plane > 0 && (plane & 1) == 0 && n >= 2 * plane; }
 void vec_axpy(long long n, const uint8_t* flags, double* x, const double* p, const double* num, const double* den,
               int n_sm, cudaStream_t st) {
     axpy_kernel<<<nblocks(n, n_sm), VT, 0, st>>>(n, flags, x, p, num, den);

@@ -20,6 +20,8 @@ def load():
             subprocess.check_call(["make", "-s", "-C", _HERE])
         lib = C.CDLL(_LIB)
         lib.oo_num_threads.restype = C.c_int
+        lib.oo_set_num_threads.restype = C.c_int
+        lib.oo_set_num_threads.argtypes = [C.c_int]
         lib.oo_count_phase_i32.restype = C.c_int64
         lib.oo_count_phase_i32.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         lib.oo_remspot.restype = None
@@ -51,6 +53,19 @@ def load():
 
 def num_threads() -> int:
     return load().oo_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of every later call (overrides OMP_NUM_THREADS); returns the count in force."""
+    return load().oo_set_num_threads(int(n))
+
+
+def host_cores() -> int:
+    """Cores this process may run on (the affinity mask, not the machine total)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def _i32(a):

@@ -40,6 +40,18 @@ int oo_num_threads(void) {
 #endif
 }
 
+/* Explicit thread count for the timed CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers,
+ * which would silently turn the baseline into a one-core run.  Returns the count now in force. */
+int oo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* VolumeFraction::value, src/props/VolumeFraction.cpp:22-66 */
 int64_t oo_count_phase_i32(const int32_t* f, int64_t n, int32_t phase) {
     int64_t c = 0;

@@ -76,6 +76,30 @@ def main():
         else:
             full_mask_ok = True   # each rank checks its own slab against the oracle-free single-GPU answer on rank 0 only
             ok = ok and chk and full_mask_ok
+    # Repeated solves must be bit-identical: every reduction is ordered (block partials summed in block order,
+    # one all-reduce per scalar), so any ghost plane read before its neighbour stored it -- or overwritten while
+    # still being read -- shows up as a changed bit.  mg_degree = 1 exchanges the same level-0 field in
+    # consecutive sweeps (the schedule the peer halo's write-after-read argument is weakest for).
+    import hashlib
+    for shape, direction, radius, deg, reps in [((128, 128, 128), 2, 8, 0, 10), ((128, 96, 64), 2, 6, 1, 6),
+                                                ((256, 192, 128), 2, 8, 2, 4)]:
+        full = synth.sphere_packing_slab(shape, seed=17, radius=radius, solid_target=0.5)
+        z0, nzl = capi.slab_partition(shape[0], world)[rank]
+        s = capi.Solver(shape, direction, 1, -1.0, 1.0, device=local, z_begin=z0, nz_local=nzl, comm=comm,
+                        mg_degree=deg)
+        s.set_phase(np.ascontiguousarray(full[z0:z0 + nzl]))
+        sigs = []
+        for rep in range(reps):
+            s.build_mask()
+            info = s.solve()
+            fin, fout, _, _ = s.fluxes()
+            sigs.append((info.iterations, info.rel_residual, fin, fout, hashlib.sha256(s.solution().tobytes()).hexdigest()))
+        s.close()
+        same = all(sg == sigs[0] for sg in sigs) and bool(info.converged)
+        if rank == 0:
+            print(f"repeat {shape} mg_degree={deg or 4}: {reps} solves, iters={sigs[0][0]} relres={sigs[0][1]:.3e} "
+                  f"{'BIT-IDENTICAL' if same else 'DIFFER: ' + str([sg[:4] for sg in sigs])}", flush=True)
+        ok = ok and same
     # homogenisation cell problem on z-slabs of a periodic box: same tensor as one GPU
     from openimpala_b200.effdiff import calculate_Deff_tensor_homogenization
     for shape, radius, halo_mode in [((96, 64, 80), 6, capi.OI_HALO_AUTO), ((64, 48, 36), 5, capi.OI_HALO_NCCL),

@@ -83,3 +83,49 @@ def test_stencil_variants_agree_256(capi):
     ph = synth.sphere_packing(256, SEED, RADIUS, SOLID)
     taus = [_tau(capi, ph, -1.0, 1.0, variant=v)["tau"] for v in (0, 2, 1)]
     assert max(taus) - min(taus) <= 1e-7 * taus[0]
+
+
+def test_default_large_box_path_against_independent_kernels_384(capi):
+    """Above 2^25 cells the default path changes (iterations on the stream instead of CUDA graphs, the
+    two-sweeps-per-pass smoother, 64-bit offsets): pin it at 384^3 against a path that shares none of its solve
+    kernels -- Jacobi-preconditioned CG on the gather stencil (precond=JACOBI, stencil_variant=1) -- to 1e-7."""
+    from openimpala_b200 import synth
+    from openimpala_b200.tortuosity import tau_from_fluxes
+    ph = synth.sphere_packing(384, SEED, RADIUS, SOLID)
+    out = []
+    for kw in (dict(), dict(precond=capi.OI_PRECOND_JACOBI, stencil_variant=1, maxiter=20000)):
+        with capi.Solver(ph.shape, 2, 1, -1.0, 1.0, eps=1e-10, **kw) as s:
+            s.set_phase(ph)
+            n_active = s.build_mask()
+            info = s.solve()
+            fin, fout, ni, no = s.fluxes()
+            tau, _, conserved = tau_from_fluxes(fin, fout, n_active / ph.size, 384.0, 384.0 * 384.0, -1.0, 1.0)
+            replays, _ = s.graph_info()
+            out.append(dict(tau=tau, n_active=n_active, ni=ni, no=no, info=info, replays=replays, conserved=conserved))
+    a, b = out
+    assert a["replays"] == 0                                   # the default path at this size is the stream path
+    assert a["info"].converged and b["info"].converged and a["conserved"] and b["conserved"]
+    assert (a["n_active"], a["ni"], a["no"]) == (b["n_active"], b["ni"], b["no"])
+    assert a["info"].iterations <= 40 and b["info"].iterations > 10 * a["info"].iterations
+    assert abs(a["tau"] - b["tau"]) <= 1e-7 * b["tau"], (a["tau"], b["tau"])
+
+
+def test_sphere_packing_golden_512(capi, packing):
+    """BASELINE configs[2] against the C oracle's solve of the same 512^3 image (tests/golden/packing_golden_512.json,
+    Jacobi-PCG on the stored matrix to 1e-11, made by make_packing_golden_512.py): integers exact, tau / fluxes to 1e-6."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "packing_golden_512.json")
+    if not os.path.exists(path):
+        pytest.skip("packing_golden_512.json not generated yet")
+    g = json.load(open(path))["cases"][0]
+    ph = packing
+    assert hashlib.sha256(ph.tobytes()).hexdigest() == g["sha256"]
+    r = _tau(capi, ph, -1.0, 1.0)
+    assert r["pc"] == g["phase_count"] and r["n_active"] == g["n_active"]
+    assert r["info"].converged
+    assert abs(r["tau"] - g["tau"]) <= 1e-6 * g["tau"], (r["tau"], g["tau"])
+    assert abs(r["fin"] - g["flux_in"]) <= 1e-6 * abs(g["flux_in"])
+    assert abs(r["fout"] - g["flux_out"]) <= 1e-6 * abs(g["flux_out"])

@@ -170,6 +170,43 @@ def test_equal_potentials_gives_inf(capi):
     assert math.isinf(t.value())               # avg flux ~ 0 -> +Inf (TortuosityHypre.cpp:846-851)
 
 
+def test_flux_gate_returns_nan_like_the_reference(capi, sample_phase):
+    """Default (flux_polish = 0) is the reference's behaviour: the solve stops on the residual rule alone and value()
+    returns NaN when the boundary fluxes disagree by more than 1e-6 (TortuosityHypre.cpp:794-823).  A loose
+    hypre.eps makes the gate fire; the opt-in polish keeps iterating and returns a finite tau."""
+    from openimpala_b200.tortuosity import Direction, ParmParse, SolverType, TortuosityHypre
+    ParmParse.table["hypre.eps"] = 1e-4
+    try:
+        t = TortuosityHypre(None, None, None, sample_phase, 0.4, 1, Direction.X, SolverType.FlexGMRES, "", -1.0, 1.0)
+        tau = t.value()
+        assert t.getSolverConverged() and t.getFinalRelativeResidualNorm() <= 1e-4
+        fin, fout = abs(t.getFluxIn()), abs(t.getFluxOut())
+        mismatch = abs(fin - fout) / (0.5 * (fin + fout))
+        assert mismatch > 1e-6, "pick a looser eps: the gate has to fire for this test to mean anything"
+        assert math.isnan(tau)                                               # the reference's NaN
+        t.close()
+        t = TortuosityHypre(None, None, None, sample_phase, 0.4, 1, Direction.X, SolverType.FlexGMRES, "", -1.0, 1.0,
+                            flux_polish=1)
+        tau = t.value()
+        fin, fout = abs(t.getFluxIn()), abs(t.getFluxOut())
+        assert t.getSolverConverged() and math.isfinite(tau)
+        assert abs(fin - fout) / (0.5 * (fin + fout)) <= 1e-6
+        assert abs(tau - 3.1330740847) <= 1e-4 * 3.1330740847               # SURVEY 8c-3 (sample, phase 1, X)
+        t.close()
+        # a polish round that runs into hypre.maxiter must not downgrade a solve confirmed at eps
+        ParmParse.table["hypre.maxiter"] = 6
+        ParmParse.table["hypre.eps"] = 1e-2
+        t = TortuosityHypre(None, None, None, sample_phase, 0.4, 1, Direction.X, SolverType.FlexGMRES, "", -1.0, 1.0,
+                            flux_polish=1)
+        t.value()
+        if t.getSolverIterations() >= 6 and t.getFinalRelativeResidualNorm() <= 1e-2:
+            assert t.getSolverConverged()
+        t.close()
+    finally:
+        ParmParse.table.pop("hypre.eps", None)
+        ParmParse.table.pop("hypre.maxiter", None)
+
+
 def test_anisotropic_cell_size(capi):
     from oracle import oi_numpy as o
     from openimpala_b200.tortuosity import Direction, SolverType, TortuosityHypre
@@ -372,7 +409,7 @@ def test_streamed_upload_rejects_incomplete_slab(capi):
 @pytest.mark.parametrize("shape,seed,por", [((40, 37, 100), 51, 0.5), ((70, 64, 64), 52, 0.45), ((33, 16, 8), 53, 0.6),
                                             ((20, 130, 132), 54, 0.55)])
 @pytest.mark.parametrize("direction", [0, 2])
-@pytest.mark.parametrize("pair_variant", ["1", "2"])
+@pytest.mark.parametrize("pair_variant", ["1", "2", "3"])
 def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, pair_variant, monkeypatch):
     """The temporally blocked smoother (two sweeps per pass, oi_level0_pair.cu; OI_PAIR selects
     the variant, 0 = off) against the single-sweep ring kernels: same V-cycle output (fp32 rounding only),
@@ -398,6 +435,37 @@ def test_pair_kernel_matches_single_sweeps(capi, shape, seed, por, direction, pa
     assert float(np.abs(z0 - z1).max()) <= 2e-5 * scale          # fp32 V-cycle, different summation order only
     assert abs(it0 - it1) <= 1
     assert abs(fl0[0] - fl1[0]) <= 1e-7 * abs(fl1[0]) and abs(fl0[1] - fl1[1]) <= 1e-7 * abs(fl1[1])
+
+
+@pytest.mark.parametrize("shape,seed,por", [((40, 37, 96), 61, 0.5), ((70, 50, 80), 62, 0.45), ((130, 24, 16), 63, 0.6),
+                                            ((20, 130, 144), 64, 0.55)])
+@pytest.mark.parametrize("direction", [0, 2])
+def test_tma_ring_matches_cp_async_ring(capi, shape, seed, por, direction, monkeypatch):
+    """OI_TMA=1 stages the z-planes of the level-0 operator apply and smoother with cp.async.bulk.tensor + mbarriers
+    (oi_level0_tma.cu) instead of per-thread cp.async.  Same tile, same arithmetic in the same order: A p bit-identical,
+    the V-cycle to fp32 rounding of the parts that still differ (none expected), same iterations and fluxes.  Shapes
+    have nx % 16 == 0 and cover partial tiles in x and y, z-chunk boundaries and boxes thinner than the ring."""
+    ph = _blobs(shape, seed, por)
+    res = {}
+    for tma in ("0", "1"):
+        monkeypatch.setenv("OI_TMA", tma)
+        monkeypatch.setenv("OI_PAIR", "0")                       # single sweeps: the kernels under test
+        with capi.Solver(shape, direction, 1, -1.0, 1.0) as s:
+            s.set_phase(ph)
+            if s.build_mask() == 0:
+                pytest.skip("nothing percolates")
+            act = s.mask().astype(bool)
+            x = np.where(act, np.random.default_rng(seed).standard_normal(shape), 0.0)
+            y = s.apply_operator(x)
+            z = s.apply_precond(x)
+            info = s.solve()
+            res[tma] = (y, z, info.iterations, info.rel_residual, s.fluxes()[:2])
+    y0, z0, it0, rr0, fl0 = res["0"]
+    y1, z1, it1, rr1, fl1 = res["1"]
+    assert np.array_equal(y0, y1)
+    assert float(np.abs(z0 - z1).max()) <= 1e-6 * float(np.abs(z0).max())
+    assert it0 == it1
+    assert abs(fl0[0] - fl1[0]) <= 1e-9 * abs(fl0[0]) and abs(fl0[1] - fl1[1]) <= 1e-9 * abs(fl0[1])
 
 
 # ------------------------------------------------------------------ iterations replayed as CUDA graphs

@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     txt = open(os.path.join(ROOT, "include", "openimpala_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(oi_[a-z0-9_]+)\s*\(", txt)))
+    # oi_* plus the reference's own bind(c) names (tortuosity_fillmtx, tortuosity_remspot)
+    return sorted(set(re.findall(r"\b((?:oi|tortuosity)_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol(built_lib):

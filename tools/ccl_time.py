@@ -1,5 +1,7 @@
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys, time, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 import numpy as np
 from openimpala_b200 import capi, synth
 n = int(sys.argv[1])

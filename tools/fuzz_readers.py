@@ -6,8 +6,10 @@ issue.  Round-1 record: FUZZ_SEED=5 (300 inputs) and FUZZ_SEED=11 FUZZ_TRIALS=24
 no memory error and no hang after the directory-cycle / extent checks went in; the only
 non-clean exits left are out-of-memory aborts on headers that claim absurd extents.
     sh tools/sanitize_readers.sh && FUZZ_SEED=11 FUZZ_TRIALS=240 python tools/fuzz_readers.py"""
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import os, random, subprocess, sys, shutil
-sys.path.insert(0, '/root/repo/tests'); sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.join(_ROOT, 'tests')); sys.path.insert(0, _ROOT)
 import numpy as np
 import test_host_apps as t
 random.seed(int(os.environ.get("FUZZ_SEED", "5")))
@@ -18,8 +20,8 @@ t._write_hdf5('/tmp/fuzz/base.h5', 'image', vol, chunks=(4, 5, 6), gzip=True, sh
 vol16 = rng.integers(0, 60000, (11, 13, 17)).astype('<u2')
 t._write_hdf5('/tmp/fuzz/base16.h5', 'image', vol16, chunks=(4, 5, 6), gzip=True, shuffle=True, fletcher=True)
 bases = [('/tmp/fuzz/base.h5', ['mode=hdf5', 'hdf5dataset=image']), ('/tmp/fuzz/base16.h5', ['mode=hdf5', 'hdf5dataset=image']),
-         ('/root/repo/tests/golden/SampleData_2Phase_3d.hdf5', ['mode=hdf5', 'hdf5dataset=image']),
-         ('/root/repo/tests/golden/SampleData_2Phase_squared.tif', ['mode=tiff']),
+         (os.path.join(_ROOT, 'tests/golden/SampleData_2Phase_3d.hdf5'), ['mode=hdf5', 'hdf5dataset=image']),
+         (os.path.join(_ROOT, 'tests/golden/SampleData_2Phase_squared.tif'), ['mode=tiff']),
          ('/tmp/pack64_lzw.tif', ['mode=tiff'])]
 from PIL import Image
 ims=[Image.fromarray(rng.integers(0,255,(64,64)).astype(np.uint8)) for _ in range(8)]

@@ -1,5 +1,7 @@
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 import numpy as np
 from tools.robustness_sweep import blobs, run
 for n in (128, 256, 384, 512):

@@ -1,9 +1,11 @@
 """Scratch study: V-cycle carried out in fp32 (operators + vectors) inside an fp64 PCG."""
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys, time
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 import importlib.util
-spec = importlib.util.spec_from_file_location("mgp", "/root/repo/tools/mg_prototype.py")
+spec = importlib.util.spec_from_file_location("mgp", os.path.join(_ROOT, "tools/mg_prototype.py"))
 m = importlib.util.module_from_spec(spec)
 _argv = sys.argv; sys.argv = ["x"]; spec.loader.exec_module(m); sys.argv = _argv
 o = m.o
@@ -41,7 +43,7 @@ def run(ph, pid, d, label):
 
 which = sys.argv[1]
 if which == "sample":
-    ph = o.threshold(o.read_tiff_raw("/root/repo/tests/golden/SampleData_2Phase_stack_3d_1bit.tif"))
+    ph = o.threshold(o.read_tiff_raw(os.path.join(_ROOT, "tests/golden/SampleData_2Phase_stack_3d_1bit.tif")))
     run(ph, 1, 0, "sample p1 X")
 else:
     ph = o.sphere_packing(int(which), radius=12).astype(np.int32)

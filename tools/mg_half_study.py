@@ -7,13 +7,15 @@ Question: does the rounding of the stored iterates cost PCG iterations?
 
     python tools/mg_half_study.py 128        # sphere packing n (radius 12), or `sample`
 """
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import importlib.util
 import sys
 
 import numpy as np
 
-sys.path.insert(0, "/root/repo")
-spec = importlib.util.spec_from_file_location("mgp", "/root/repo/tools/mg_prototype.py")
+sys.path.insert(0, _ROOT)
+spec = importlib.util.spec_from_file_location("mgp", os.path.join(_ROOT, "tools/mg_prototype.py"))
 m = importlib.util.module_from_spec(spec)
 _argv = sys.argv; sys.argv = ["x"]; spec.loader.exec_module(m); sys.argv = _argv
 o = m.o
@@ -79,7 +81,7 @@ def run(ph, pid, d, label):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "96"
 if which == "sample":
-    ph = o.threshold(o.read_tiff_raw("/root/repo/tests/golden/SampleData_2Phase_stack_3d_1bit.tif"))
+    ph = o.threshold(o.read_tiff_raw(os.path.join(_ROOT, "tests/golden/SampleData_2Phase_stack_3d_1bit.tif")))
     run(ph, 1, 0, "sample p1 X")
 else:
     ph = o.sphere_packing(int(which), radius=12).astype(np.int32)

@@ -6,13 +6,15 @@ aggregation-Galerkin sums scaled by 1/2 (what the CUDA path stores).
     python tools/mg_interp_study.py 128 [radius]
     python tools/mg_interp_study.py sample
 """
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 import time
 
 import numpy as np
 import scipy.sparse as sp
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 from oracle import oi_numpy as o  # noqa: E402
 from tools.mg_prototype import cheb_weights, pcg, smooth_wjac  # noqa: E402
 

@@ -10,12 +10,14 @@ stopping rule and the visits per level, from which DESIGN.md's cost estimate is 
 
     python tools/mg_kcycle_study.py 128 12        # sphere packing n, radius
 """
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 sys.argv, _argv = sys.argv[:1], sys.argv          # keep mg_prototype's __main__ blocks quiet
 from tools.mg_prototype import build_hierarchy, cheb_weights, smooth_wjac  # noqa: E402
 from oracle import oi_numpy as o  # noqa: E402

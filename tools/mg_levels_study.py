@@ -1,10 +1,12 @@
 """Scratch study: smoother degree per level (fine vs coarse) on a sphere packing."""
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys, time
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 sys.argv = [sys.argv[0]] + sys.argv[1:]
 import importlib.util
-spec = importlib.util.spec_from_file_location("mgp", "/root/repo/tools/mg_prototype.py")
+spec = importlib.util.spec_from_file_location("mgp", os.path.join(_ROOT, "tools/mg_prototype.py"))
 m = importlib.util.module_from_spec(spec)
 _argv = sys.argv; sys.argv = ["x"]; spec.loader.exec_module(m); sys.argv = _argv
 o = m.o

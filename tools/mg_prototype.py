@@ -1,13 +1,15 @@
 """Scratch study (CPU, scipy): how many PCG iterations does a cell-centred
 aggregation-Galerkin V-cycle need on binary porous geometry?  Drives the
 design choices in DESIGN.md (smoother, sweeps, coarse scaling)."""
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 import time
 
 import numpy as np
 import scipy.sparse as sp
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 from oracle import oi_numpy as o  # noqa: E402
 
 

@@ -4,13 +4,15 @@ with per-axis scaling 1/f_a of the aggregated couplings.
 
     python tools/mg_semicoarsen_study.py 64 1 1 5
 """
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 import time
 
 import numpy as np
 import scipy.sparse as sp
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 from oracle import oi_numpy as o  # noqa: E402
 from tools.mg_prototype import cheb_weights, pcg, smooth_wjac  # noqa: E402
 

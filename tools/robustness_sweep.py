@@ -1,12 +1,14 @@
 """GPU sweep over geometries: iteration counts / convergence of the MG-PCG solve away from the
 benchmark packing (low porosity near the percolation threshold, blobby random fields, thin
 channels, anisotropic cells, non-cubic boxes)."""
+import os
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, _ROOT)
 from openimpala_b200 import capi, synth  # noqa: E402
 from openimpala_b200.tortuosity import tau_from_fluxes  # noqa: E402
 
