@@ -114,6 +114,10 @@ void        oi_default_params(oi_params* p);
 int oi_comm_unique_id(void* id128_out);
 int oi_comm_create(oi_comm** out, int32_t rank, int32_t n_ranks, const void* id128, int32_t device);
 int oi_comm_destroy(oi_comm* c);
+/* Sum of n int64 values over the ranks of the communicator, in place (host pointer).  Stands in for
+ * amrex::ParallelDescriptor::ReduceLongSum of the reference's callers (VolumeFraction.cpp:58-60).
+ * A NULL communicator is one rank: the values stay as they are. */
+int oi_comm_allreduce_sum_i64(oi_comm* c, int64_t* values, int32_t n);
 
 /* ---- VolumeFraction::value, src/props/VolumeFraction.cpp:22-66 ---------- */
 /* Count cells == phase in a host field (copied to the device, counted there).

@@ -60,6 +60,7 @@ _SIGS = {
     "oi_comm_unique_id": (C.c_int, [_P]),
     "oi_comm_create": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P, C.c_int32]),
     "oi_comm_destroy": (C.c_int, [_P]),
+    "oi_comm_allreduce_sum_i64": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
     "oi_count_phase_i32": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_count_phase_u8": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "oi_create": (C.c_int, [C.POINTER(_P), C.POINTER(oi_params)]),

@@ -12,6 +12,8 @@
 // anisotropic cells are semicoarsened (only the strongly coupled axes) until the
 // couplings even out.  This replaces HYPRE SMG/PFMG's coarse
 // operator build (reference call site src/props/TortuosityHypre.cpp:671-681).
+#include <cuda_fp16.h>
+
 #include "oi_kernels.h"
 #include "oi_coarse_tail.cuh"
 
@@ -152,9 +154,19 @@ coarse_stencil_kernel(CoarseLevel L, const mg_t* __restrict__ x, const mg_t* __r
 // Vectorised variant for fp32 levels whose nx is a multiple of 4: each thread owns
 // four x-adjacent cells (16-byte loads of x, b and of every coefficient array), a
 // CTA covers 64 x 16 cells of one plane.  Same arithmetic as the scalar kernel.
+// HALF: the four coefficient arrays are read from their exact half-precision copies (8-byte loads).
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4h(const unsigned short* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ld1h(const unsigned short* p) {
+    return __half2float(*reinterpret_cast<const __half*>(p));
+}
 
-template <int MODE>
+template <int MODE, bool HALF>
 __global__ void __launch_bounds__(256)
 coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const float* __restrict__ b,
                            float* __restrict__ out, float w) {
@@ -165,22 +177,24 @@ coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const flo
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
         const long long idx = (long long)k * L.plane + col;
-        const float4 d = ld4(L.dg + idx);
+        const float4 d = HALF ? ld4h(L.hd + idx) : ld4(L.dg + idx);
         float4 o = zero4;
         if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
             const float4 c = ld4(x + idx);
-            const float4 cxp = ld4(L.cxp + idx), cyp = ld4(L.cyp + idx), czp = ld4(L.czp + idx);
+            const float4 cxp = HALF ? ld4h(L.hx + idx) : ld4(L.cxp + idx);
+            const float4 cyp = HALF ? ld4h(L.hy + idx) : ld4(L.cyp + idx);
+            const float4 czp = HALF ? ld4h(L.hz + idx) : ld4(L.czp + idx);
             const bool px = (L.periodic & PER_X) != 0, py = (L.periodic & PER_Y) != 0;
             const long long iw = (i > 0) ? idx - 1 : idx + (L.nx - 1);
             const long long js = (j > 0) ? idx - L.nx : idx + (long long)(L.ny - 1) * L.nx;
             const long long jn = (j + 1 < L.ny) ? idx + L.nx : idx - (long long)j * L.nx;
-            const float cxw = (i > 0 || px) ? L.cxp[iw] : 0.f;
+            const float cxw = (i > 0 || px) ? (HALF ? ld1h(L.hx + iw) : L.cxp[iw]) : 0.f;
             const float xw = (i > 0 || px) ? x[iw] : 0.f;
             const float xe = (i + 4 < L.nx) ? x[idx + 4] : (px ? x[idx - i] : 0.f);
-            const float4 cym = (j > 0 || py) ? ld4(L.cyp + js) : zero4;
+            const float4 cym = (j > 0 || py) ? (HALF ? ld4h(L.hy + js) : ld4(L.cyp + js)) : zero4;
             const float4 ys = (j > 0 || py) ? ld4(x + js) : zero4;
             const float4 yn = (j + 1 < L.ny || py) ? ld4(x + jn) : zero4;
-            const float4 czm = ld4(L.czp + idx - L.plane);          // k-1 may be the ghost plane
+            const float4 czm = HALF ? ld4h(L.hz + idx - L.plane) : ld4(L.czp + idx - L.plane);   // k-1 may be the ghost plane
             const float4 zd = ld4(x + idx - L.plane);
             const float4 zu = ld4(x + idx + L.plane);
             float4 acc;
@@ -203,6 +217,20 @@ coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const flo
         }
         *reinterpret_cast<float4*>(out + idx) = o;
     }
+}
+
+__global__ void __launch_bounds__(256)
+to_half_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, long long n, unsigned long long* mismatch) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = src[i];
+        const __half h = __float2half_rn(v);
+        if (__half2float(h) != v) ++bad;
+        dst[i] = *reinterpret_cast<const unsigned short*>(&h);
+    }
+    bad = warp_sum_ll(bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatch, (unsigned long long)bad);
 }
 
 // x += P * ec on non-empty cells (prolongation + correction between coarse levels)
@@ -278,6 +306,11 @@ coarse_tail_staged_kernel(TailArgs a) {
     tail_cycle_staged(a, CtaStep(), reinterpret_cast<float*>(tail_smem));
 }
 
+// the 16-byte path needs fp32 vectors and every row / plane start 16-byte aligned
+static bool vec4_ok(const CoarseLevel& L) {
+    return sizeof(mg_t) == 4 && (L.nx & 3) == 0 && L.nx >= 16;
+}
+
 inline int blocks_for(long long n) {
     long long b = (n + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
@@ -298,6 +331,12 @@ void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, cudaSt
                                                                                    1.0 / f.fz);
 }
 
+void coarse_to_half(const float* src, unsigned short* dst, long long n, unsigned long long* mismatch, cudaStream_t st) {
+    to_half_kernel<<<blocks_for(n), 256, 0, st>>>(src, dst, n, mismatch);
+}
+
+bool coarse_half_applicable(const CoarseLevel& L) { return vec4_ok(L); }
+
 void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
     coarse_jacobi_first_kernel<<<blocks_for((long long)L.nz * L.plane), 256, 0, st>>>(L, b, out, (mg_t)w);
 }
@@ -307,18 +346,17 @@ static dim3 grid3(const CoarseLevel& L) {
     return dim3((L.nx + 63) / 64, (L.ny + 3) / 4, gz > 0 ? gz : 1);
 }
 
-// the 16-byte path needs fp32 vectors and every row / plane start 16-byte aligned
-static bool vec4_ok(const CoarseLevel& L) {
-    return sizeof(mg_t) == 4 && (L.nx & 3) == 0 && L.nx >= 16;
-}
 static dim3 grid_vec4(const CoarseLevel& L) {
     int gz = L.nz < 128 ? L.nz : 128;
     return dim3((L.nx + 63) / 64, (L.ny + 15) / 16, gz > 0 ? gz : 1);
 }
 
 void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
-    if (vec4_ok(L))
-        coarse_stencil_vec4_kernel<1><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+    if (vec4_ok(L) && L.hd)
+        coarse_stencil_vec4_kernel<1, true><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), (float)w);
+    else if (vec4_ok(L))
+        coarse_stencil_vec4_kernel<1, false><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
             reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), (float)w);
     else
         coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
@@ -329,8 +367,11 @@ void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, 
 }
 
 void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st) {
-    if (vec4_ok(L))
-        coarse_stencil_vec4_kernel<2><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+    if (vec4_ok(L) && L.hd)
+        coarse_stencil_vec4_kernel<2, true><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
+            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
+    else if (vec4_ok(L))
+        coarse_stencil_vec4_kernel<2, false><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
             reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
     else
         coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);

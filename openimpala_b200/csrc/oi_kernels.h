@@ -61,6 +61,11 @@ struct CoarseLevel {
     int fx, fy, fz;            // coarsening factors from this level to the next
     int periodic;              // PER_X | PER_Y | PER_Z of the box (cell problem), else 0
     int replicated;            // multi-rank: this level holds the whole box on every rank (no halo)
+    // Half-precision copies of cxp, cyp, czp, dg for the bandwidth-bound smoothing / residual kernel (20 instead
+    // of 28 bytes per cell and sweep).  Only set on levels where every coefficient survives the conversion
+    // exactly (small-integer multiples of 2^-level: levels 1-3 for unit cells), so both sets describe the
+    // SAME operator; nullptr otherwise.  Same layout and ghost planes as the float arrays.
+    const unsigned short *hx, *hy, *hz, *hd;
     float *cxp, *cyp, *czp;    // coupling to +x,+y,+z neighbour (>= 0), ghost planes
     float* dg;                 // diagonal (0 = empty aggregate)
     float *dgx, *dgy, *dgz;    // its shares by axis (build time only: each is scaled by 1/f_axis)
@@ -70,6 +75,9 @@ struct CoarseLevel {
 void coarse_build_from_flags(const Grid& g, const uint8_t* flags, int dir_axis, int n_dir_global,
                              const CoarseLevel& c, int fx, int fy, int fz, cudaStream_t st);
 void coarse_build_from_coarse(const CoarseLevel& f, const CoarseLevel& c, cudaStream_t st);
+// dst[i] = half(src[i]) for i in [0, n); *mismatch += number of values the conversion changed
+bool coarse_half_applicable(const CoarseLevel& L);       // this level runs the kernel that can read them
+void coarse_to_half(const float* src, unsigned short* dst, long long n, unsigned long long* mismatch, cudaStream_t st);
 void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st);
 // out = x + w (b - A x) / dg
 void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w,

@@ -347,6 +347,7 @@ struct HostLevel {
     oi::CoarseLevel L{};
     Field<float> cxp, cyp, czp, dg;
     Field<float> dgx, dgy, dgz;             // diagonal by axis, read only by the next level's build
+    Field<unsigned short> hx, hy, hz, hd;   // exact half copies of cxp, cyp, czp, dg (first levels only; oi_kernels.h)
     Field<oi::mg_t> x, b, t;
     // Agglomeration (n_ranks > 1): the first level small enough is kept twice -- once
     // distributed (`gather_point`: it only receives the restricted residual and hands back
@@ -758,6 +759,7 @@ void free_levels(oi_solver* S) {
     for (auto& h : S->levels) {
         h.cxp.release(); h.cyp.release(); h.czp.release(); h.dg.release();
         h.dgx.release(); h.dgy.release(); h.dgz.release();
+        h.hx.release(); h.hy.release(); h.hz.release(); h.hd.release();
         h.x.release(); h.b.release(); h.t.release();
     }
     S->levels.clear();
@@ -875,6 +877,18 @@ void allocate_hierarchy(oi_solver* S) {
         h.L.cxp = h.cxp.p; h.L.cyp = h.cyp.p; h.L.czp = h.czp.p; h.L.dg = h.dg.p;
         h.L.dgx = h.dgx.p; h.L.dgy = h.dgy.p; h.L.dgz = h.dgz.p;
         h.L.x = h.x.p; h.L.b = h.b.p; h.L.t = h.t.p;
+        h.L.hx = h.L.hy = h.L.hz = h.L.hd = nullptr;
+    }
+    // half copies of the coefficients for the first (large, bandwidth-bound) levels; OI_COARSE_HALF=0 turns them off
+    {
+        const char* e = getenv("OI_COARSE_HALF");
+        const bool on = !(e && e[0] == '0');
+        for (size_t l = 0; on && l < S->levels.size() && l < 3; ++l) {
+            HostLevel& h = S->levels[l];
+            if (!oi::coarse_half_applicable(h.L)) continue;
+            h.hx.alloc(h.L.plane, h.L.nz, S->st); h.hy.alloc(h.L.plane, h.L.nz, S->st);
+            h.hz.alloc(h.L.plane, h.L.nz, S->st); h.hd.alloc(h.L.plane, h.L.nz, S->st);
+        }
     }
     S->levels_allocated = true;
 }
@@ -1059,6 +1073,35 @@ void build_hierarchy(oi_solver* S) {
         halo_exchange_bytes(S, lv[l].czp.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
         halo_exchange_bytes(S, lv[l].dg.p, (size_t)lv[l].L.plane * sizeof(float), lv[l].L.nz);
     }
+    // half copies (ghost planes included) where the conversion is exact on the whole level, on every rank
+    {
+        int n_half = 0;
+        CUDA_CHECK(cudaMemsetAsync(S->d_ull + 8, 0, 3 * sizeof(unsigned long long), S->st));
+        for (size_t l = 0; l < lv.size() && l < 3; ++l) {
+            HostLevel& h = lv[l];
+            h.L.hx = h.L.hy = h.L.hz = h.L.hd = nullptr;
+            if (!h.hd.base) continue;
+            const long long cnt = h.L.plane * (long long)(h.L.nz + 2);
+            unsigned long long* bad = S->d_ull + 8 + l;
+            oi::coarse_to_half(h.cxp.p - h.L.plane, h.hx.p - h.L.plane, cnt, bad, S->st);
+            oi::coarse_to_half(h.cyp.p - h.L.plane, h.hy.p - h.L.plane, cnt, bad, S->st);
+            oi::coarse_to_half(h.czp.p - h.L.plane, h.hz.p - h.L.plane, cnt, bad, S->st);
+            oi::coarse_to_half(h.dg.p - h.L.plane, h.hd.p - h.L.plane, cnt, bad, S->st);
+            S->launches += 4;
+            ++n_half;
+        }
+        if (n_half) {
+            allreduce_sum_u64(S, S->d_ull + 8, 3);
+            unsigned long long bad[3] = {0, 0, 0};
+            CUDA_CHECK(cudaMemcpyAsync(bad, S->d_ull + 8, sizeof(bad), cudaMemcpyDeviceToHost, S->st));
+            CUDA_CHECK(cudaStreamSynchronize(S->st));
+            for (size_t l = 0; l < lv.size() && l < 3; ++l) {
+                HostLevel& h = lv[l];
+                if (!h.hd.base || bad[l] != 0) continue;
+                h.L.hx = h.hx.p; h.L.hy = h.hy.p; h.L.hz = h.hz.p; h.L.hd = h.hd.p;
+            }
+        }
+    }
     S->hierarchy_built = true;
 }
 
@@ -1173,7 +1216,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     // single sweeps.  OI_PAIR=0 turns it off, OI_PAIR=1 selects the 256-thread variant (read per
     // call so that tests can compare the paths).
     const char* pair_env = getenv("OI_PAIR");
-    const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '3') ? pair_env[0] - '0' : 2;
+    const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '3') ? pair_env[0] - '0' : 3;
     const bool no_pair = pair_variant == 0;
     bool use_pair = false, ring1 = false;
     {
@@ -1436,7 +1479,7 @@ void run_solve(oi_solver* S) {
     const bool use_graph = iter_graph_wanted(S);
     {   // OI_PAIR is read per call and baked into a captured iteration
         const char* pe = getenv("OI_PAIR");
-        const int sig = (pe && pe[0] >= '0' && pe[0] <= '3') ? pe[0] - '0' : 2;
+        const int sig = (pe && pe[0] >= '0' && pe[0] <= '3') ? pe[0] - '0' : 3;
         if (sig != S->graph_pair_sig) drop_iter_graphs(S);
         S->graph_pair_sig = sig;
     }
@@ -1904,6 +1947,20 @@ int oi_comm_destroy(oi_comm* c) {
     });
 }
 
+int oi_comm_allreduce_sum_i64(oi_comm* c, int64_t* values, int32_t n) {
+    if (!c || c->n_ranks <= 1 || n <= 0) return OI_OK;
+    return guarded([&] {
+        OI_REQUIRE(values != nullptr, "oi_comm_allreduce_sum_i64: null buffer");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        TempBlock<long long> d;
+        CUDA_CHECK(d.alloc(sizeof(long long) * (size_t)n));
+        CUDA_CHECK(cudaMemcpy(d.p, values, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice));
+        NCCL_CHECK(nccl_api().AllReduce(d.p, d.p, (size_t)n, ncclInt64, ncclSum, c->comm, (cudaStream_t)0));
+        CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
+        CUDA_CHECK(cudaMemcpy(values, d.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost));
+    });
+}
+
 int oi_count_phase_i32(const int32_t* f, int64_t n, int32_t phase, int64_t* pc, int64_t* tc) {
     return count_host_field<int32_t>(f, n, phase, pc, tc);
 }
@@ -1969,11 +2026,13 @@ int oi_create(oi_solver** out, const oi_params* p) {
         static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
         S->w_smooth = cheb_weights(deg, deg <= 8 ? lo_tab[deg] : 0.07);
         S->w_coarse = cheb_weights(8, 0.05);
-        S->w_mid = S->w_smooth;
-        if (const char* e = getenv("OI_MG_DEG_COARSE")) {
-            const int dc = std::atoi(e);
-            if (dc >= 1 && dc <= 16) S->w_mid = cheb_weights(dc, dc <= 8 ? lo_tab[dc] : 0.07);
-        }
+        // Levels >= 1 smooth with degree 8 per leg whatever the level-0 degree: a sweep there costs 1/8 (and
+        // less) of a level-0 sweep, and the stronger coarse solves take the 1024^3 packing from 26 to 20 PCG
+        // iterations (profiles/r2_degree_sweep.md); beyond 8 the count no longer moves.  OI_MG_DEG_COARSE=n.
+        int dc = 8;
+        if (const char* e = getenv("OI_MG_DEG_COARSE")) dc = std::atoi(e);
+        if (dc < 1 || dc > 16) dc = 8;
+        S->w_mid = cheb_weights(dc, dc <= 8 ? lo_tab[dc] : 0.07);
         if (const char* e = getenv("OI_MG_W_FROM")) S->w_from = std::max(0, std::atoi(e));
         CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
         CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));
@@ -1982,7 +2041,7 @@ int oi_create(oi_solver** out, const oi_params* p) {
         CUDA_CHECK(cmalloc(&S->d_partials, (size_t)nb * 2 * sizeof(double)));
         CUDA_CHECK(cmalloc(&S->d_counter, sizeof(unsigned int)));
         CUDA_CHECK(cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int), S->st));
-        CUDA_CHECK(cmalloc(&S->d_ull, 8 * sizeof(unsigned long long)));
+        CUDA_CHECK(cmalloc(&S->d_ull, 16 * sizeof(unsigned long long)));
         CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
         CUDA_CHECK(cmalloc(&S->d_changed, sizeof(int)));
         S->h_pinned = pinned_cache().get();

@@ -330,10 +330,12 @@ inline int nblocks(long long work_items, int n_sm) {
 
 int vec_max_blocks(int n_sm) { return n_sm * 8; }
 
-// OI_VEC_NC=2|4: pairs per trip of the residual-update and xpby kernels (4 = default)
-static int vec_nc() {
+// OI_VEC_NC=2|4: pairs per trip of the residual-update and xpby kernels.  Measured at 1024^3
+// (profiles/r2_variants_ab.md): xpby 4.77 ms with 2 pairs and four blocks per SM against 4.91 ms with 4,
+// the residual update 6.19 against 6.13 -- so xpby defaults to 2, the residual update to 4.
+static int vec_nc(int dflt) {
     const char* e = getenv("OI_VEC_NC");
-    return (e && e[0] == '2') ? 2 : 4;
+    return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : dflt;
 }
 
 void vec_axpy2_dot(long long n, double* x, double* r, const double* p, const double* q,
@@ -359,7 +361,7 @@ void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, doubl
     } else if (x)
         axpy2_dot_first_kernel<true, false, 4><<<nb, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
                                                                   counter, out, 0, none);
-    else if (vec_nc() == 2)       // OI_VEC_NC=2: two pairs per trip, four blocks per SM (A/B knob)
+    else if (vec_nc(4) == 2)       // OI_VEC_NC=2: two pairs per trip, four blocks per SM (A/B knob)
         axpy2_dot_first_kernel<false, false, 2><<<nb, VT, 0, st>>>(g, flags, n, x, r, p, q, r32, z1, num, den, w0, partials,
                                                                    counter, out, 0, none);
     else
@@ -379,7 +381,7 @@ void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const
         if (x) xpby_kernel<true, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, plane, hb, *ho);
         else xpby_kernel<false, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr, plane, hb, *ho);
     } else {
-        if (x && vec_nc() == 2) xpby_kernel<true, false, 2><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
+        if (x && vec_nc(2) == 2) xpby_kernel<true, false, 2><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
         else if (x) xpby_kernel<true, false, 4><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
         else xpby_kernel<false, false, 4><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr, 0, 0, none);
     }

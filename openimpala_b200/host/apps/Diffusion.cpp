@@ -21,6 +21,9 @@
 #include <string>
 #include <vector>
 
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <AMReX.H>
 #include <AMReX_ParmParse.H>
 #include <AMReX_Print.H>
@@ -108,7 +111,62 @@ void loadThresholded(Reader& reader, int box_size, double threshold, amrex::Box&
 
 }  // namespace
 
+// `Diffusion inputs b200.ranks=N`: the reference is started as N MPI ranks by mpirun; without MPI this
+// process starts the N ranks itself (one per GPU): N copies of the same command line with OI_RANK,
+// OI_WORLD_SIZE and OI_COMM_FILE in their environment, each owning one z-slab of the image.  Returns -1
+// when this process should carry on (a single rank, or already one of the ranks).
+int launchRanks(int argc, char* argv[]) {
+    if (std::getenv("OI_RANK") || std::getenv("RANK")) return -1;
+    int ranks = 1;
+    for (int a = 1; a < argc; ++a) {
+        const std::string arg = argv[a];
+        if (arg.rfind("b200.ranks=", 0) == 0) ranks = std::atoi(arg.c_str() + 11);
+    }
+    if (ranks <= 1 && argc > 1) {                     // the key may also sit in the inputs file
+        std::ifstream in(argv[1]);
+        std::string line;
+        while (std::getline(in, line)) {
+            const size_t h = line.find('#');
+            if (h != std::string::npos) line.erase(h);
+            std::string key, eq;
+            int v = 0;
+            std::stringstream ss(line);
+            if ((ss >> key >> eq >> v) && key == "b200.ranks" && eq == "=") ranks = v;
+        }
+    }
+    if (ranks <= 1) return -1;
+    const std::string comm_file = (std::filesystem::temp_directory_path() / ("oi_comm_" + std::to_string((long)getpid()))).string();
+    std::filesystem::remove(comm_file);
+    std::vector<pid_t> kids;
+    for (int r = 0; r < ranks; ++r) {
+        const pid_t pid = fork();
+        if (pid < 0) { std::perror("fork"); return 1; }
+        if (pid == 0) {
+            setenv("OI_RANK", std::to_string(r).c_str(), 1);
+            setenv("OI_WORLD_SIZE", std::to_string(ranks).c_str(), 1);
+            setenv("OI_COMM_FILE", comm_file.c_str(), 1);
+            execv("/proc/self/exe", argv);
+            std::perror("execv");
+            _exit(127);
+        }
+        kids.push_back(pid);
+    }
+    int rc = 0;
+    for (pid_t k : kids) {
+        int st = 0;
+        waitpid(k, &st, 0);
+        const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
+        if (code != 0) rc = code;
+    }
+    std::filesystem::remove(comm_file);
+    return rc;
+}
+
 int main(int argc, char* argv[]) {
+    {
+        const int launched = launchRanks(argc, argv);
+        if (launched >= 0) return launched;
+    }
     amrex::Initialize(argc, argv);
     {
         const amrex::Real t_start = amrex::second();
@@ -199,6 +257,8 @@ int main(int argc, char* argv[]) {
             ppr.query("results_file", rev_results_filename);
             ppr.query("write_plotfiles", rev_write_plotfiles);
             ppr.query("verbose", rev_verbose);
+            if (rev_do_study && amrex::ParallelDescriptor::NProcs() > 1)
+                amrex::Abort("rev.do_study runs on one rank (use b200.rev_workers to spread the sub-volumes over the GPUs).");
             if (rev_do_study) {
                 if (verbose >= 1) {
                     amrex::Print() << "\n--- Starting REV Study (Homogenization Method) for Phase ID " << phase_id << " ---\n";
@@ -330,6 +390,8 @@ int main(int argc, char* argv[]) {
         }
         if (method != "flow_through" && method != "homogenization" && method != "skip_if_rev")
             amrex::Abort("Invalid calculation_method: '" + method + "'. Use homogenization, flow_through or skip_if_rev.");
+        if (amrex::ParallelDescriptor::NProcs() > 1 && method != "flow_through")
+            amrex::Abort("More than one rank (z-slabs over several GPUs) runs calculation_method = flow_through in this build.");
         if (method == "skip_if_rev") {                      // reference :507: no full-domain calculation
             amrex::Print() << std::endl << "Total run time (seconds) = " << (amrex::second() - t_start) << std::endl;
             amrex::Finalize();
@@ -454,6 +516,7 @@ int main(int argc, char* argv[]) {
             pp_b200.query("dir_workers", dir_workers);
         }
         dir_workers = std::max(1, std::min<int>(dir_workers, (int)dirs.size()));
+        if (amrex::ParallelDescriptor::NProcs() > 1) dir_workers = 1;       // the ranks already share every solve
         int n_devices_dir = 1;
         if (dir_workers > 1 && (oi_device_count(&n_devices_dir) != 0 || n_devices_dir < 1)) n_devices_dir = 1;
         std::vector<amrex::Real> taus(dirs.size(), std::numeric_limits<amrex::Real>::quiet_NaN());
@@ -535,8 +598,11 @@ int main(int argc, char* argv[]) {
 
         const std::filesystem::path out_path = results_dir / output_filename;
         amrex::Print() << "\nWriting final results to: " << out_path << "\n";
-        std::ofstream out(out_path);
-        if (out.is_open()) {
+        std::ofstream out;
+        if (amrex::ParallelDescriptor::IOProcessor()) out.open(out_path);
+        if (!amrex::ParallelDescriptor::IOProcessor()) {
+            // (only the IO processor writes, as with the reference's ParallelDescriptor::IOProcessor() guard)
+        } else if (out.is_open()) {
             out << "# Tortuosity Calculation Results (Flow-Through Method)\n";
             out << "# Input File: " << filename << "\n";
             out << "# Analysis Phase ID: " << phase_id << "\n";

@@ -489,9 +489,13 @@ void HDF5Reader::thresholdInto(double t, OutT vt, OutT vf, int z_begin, int nz, 
 void HDF5Reader::threshold(double t, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {
     if (!m_is_read) amrex::Abort("[HDF5Reader::threshold] metadata not read");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.boxArray().minimalBox() == this->box(), "HDF5Reader: iMultiFab domain mismatch");
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.nGrow() == 0 && mf.validBox() == this->box(),
-                                     "HDF5Reader: the destination must be a ghost-free field over the dataset box");
-    thresholdInto<int>(t, value_if_true, value_if_false, 0, m_depth, &mf(0, 0, 0));
+    // one rank: the whole dataset; z-slabs: this rank's planes (full rows and columns)
+    const amrex::Box vb = mf.validBox(), full = this->box();
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.nGrow() == 0 && vb.smallEnd(0) == full.smallEnd(0) && vb.bigEnd(0) == full.bigEnd(0) &&
+                                     vb.smallEnd(1) == full.smallEnd(1) && vb.bigEnd(1) == full.bigEnd(1) &&
+                                     vb.smallEnd(2) >= full.smallEnd(2) && vb.bigEnd(2) <= full.bigEnd(2),
+                                     "HDF5Reader: the destination must be a ghost-free field over the dataset box (or a z-slab of it)");
+    thresholdInto<int>(t, value_if_true, value_if_false, vb.smallEnd(2), vb.length(2), &mf(vb.smallEnd(0), vb.smallEnd(1), vb.smallEnd(2)));
 }
 
 void HDF5Reader::thresholdPlanesU8(double t, unsigned char value_if_true, unsigned char value_if_false, int z_begin,

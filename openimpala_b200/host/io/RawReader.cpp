@@ -155,9 +155,15 @@ void RawReader::thresholdInto(double t, OutT vt, OutT vf, int z_begin, int nz, O
 void RawReader::threshold(double t, int value_if_true, int value_if_false, amrex::iMultiFab& mf) const {
     if (!m_is_read) amrex::Abort("RawReader::threshold: no data has been read");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(mf.boxArray().minimalBox() == this->box(), "RawReader: iMultiFab domain mismatch");
-    if (mf.nGrow() == 0 && mf.validBox() == this->box()) {             // ghost-free field: one dense x-fastest array
-        thresholdInto<int>(t, value_if_true, value_if_false, 0, m_depth, &mf(0, 0, 0));
-        return;
+    {   // ghost-free field over the whole volume or over a z-slab of it: one dense x-fastest array
+        const amrex::Box vb = mf.validBox(), full = this->box();
+        if (mf.nGrow() == 0 && vb.smallEnd(0) == full.smallEnd(0) && vb.bigEnd(0) == full.bigEnd(0) &&
+            vb.smallEnd(1) == full.smallEnd(1) && vb.bigEnd(1) == full.bigEnd(1) && vb.smallEnd(2) >= full.smallEnd(2) &&
+            vb.bigEnd(2) <= full.bigEnd(2)) {
+            thresholdInto<int>(t, value_if_true, value_if_false, vb.smallEnd(2), vb.length(2),
+                               &mf(vb.smallEnd(0), vb.smallEnd(1), vb.smallEnd(2)));
+            return;
+        }
     }
     const amrex::Box& b = mf.validBox();
     for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)

@@ -541,8 +541,13 @@ void TiffReader::readDistributedIntoFab(amrex::iMultiFab& dest, int v_true, int 
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nComp() == 1, "Dest MF must have 1 component.");
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.nGrow() == 0, "Dest MF must have 0 ghost cells.");
     // a ghost-free field over the image box is one dense x-fastest array
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(dest.validBox() == box(), "Dest MF must cover the image box.");
-    thresholdInto<int>(thr, v_true, v_false, 0, m_depth, &dest(0, 0, 0));
+    // one rank: the whole image; z-slabs: this rank's planes (full rows and columns)
+    const amrex::Box vb = dest.validBox(), full = box();
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(vb.smallEnd(0) == full.smallEnd(0) && vb.bigEnd(0) == full.bigEnd(0) &&
+                                     vb.smallEnd(1) == full.smallEnd(1) && vb.bigEnd(1) == full.bigEnd(1) &&
+                                     vb.smallEnd(2) >= full.smallEnd(2) && vb.bigEnd(2) <= full.bigEnd(2),
+                                     "Dest MF must cover the image box (or a z-slab of it).");
+    thresholdInto<int>(thr, v_true, v_false, vb.smallEnd(2), vb.length(2), &dest(vb.smallEnd(0), vb.smallEnd(1), vb.smallEnd(2)));
 }
 
 void TiffReader::thresholdPlanesU8(double raw_threshold, unsigned char value_if_true, unsigned char value_if_false,

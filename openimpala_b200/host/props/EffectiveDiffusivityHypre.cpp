@@ -61,6 +61,9 @@ EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom
             amrex::Abort("EffectiveDiffusivityHypre: this build solves the cell problem on a fully periodic "
                          "geometry (Diffusion.cpp:306-308); a non-periodic direction was requested.");
 
+    if (amrex::ParallelDescriptor::NProcs() > 1)
+        amrex::Abort("EffectiveDiffusivityHypre: the C++ class runs the cell problem on one rank in this build "
+                     "(the library solves it on z-slabs: openimpala_b200.effdiff, oi_params.comm)");
     // generateActiveMask (:213-330): phase == phase_id, ghosts by periodicity
     const amrex::Box& domain = m_geom.Domain();
     m_mf_active_mask.setVal(0);

@@ -71,7 +71,8 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
     // the phase field arrives in z-chunks decoded straight into pinned staging buffers;
     // decoding of chunk k+1 overlaps the upload of chunk k
     initialize([&](oi_solver* h) {
-        const int nz = m_geom.Domain().length(2);
+        const amrex::Box lb = m_ba.localBox();                         // planes of this rank's slab
+        const int nz = lb.length(2), zb = lb.smallEnd(2) - m_geom.Domain().smallEnd(2);
         const int chunk = std::max(1, std::min(planes_per_chunk, nz));
         oi_check(oi_phase_stream_begin(h, chunk), "oi_phase_stream_begin");
         int which = 0;
@@ -79,7 +80,7 @@ TortuosityHypre::TortuosityHypre(const amrex::Geometry& geom, const amrex::BoxAr
             const int n = std::min(chunk, nz - z0);
             uint8_t* buf = nullptr;
             oi_check(oi_phase_stream_buffer(h, which, &buf), "oi_phase_stream_buffer");
-            phase_stream(z0, n, buf);
+            phase_stream(zb + z0, n, buf);
             if (m_write_plotfile)
                 m_plot_phase.insert(m_plot_phase.end(), buf,
                                     buf + (size_t)n * (size_t)m_geom.Domain().length(0) * (size_t)m_geom.Domain().length(1));
@@ -117,14 +118,22 @@ void TortuosityHypre::initialize(const std::function<void(oi_solver*)>& upload_p
     oi_params p;
     oi_default_params(&p);
     p.nx = domain.length(0); p.ny = domain.length(1); p.nz = domain.length(2);
-    p.z_begin = 0; p.nz_local = p.nz;
+    // this rank's z-slab of the BoxArray (reference: every rank owns the boxes its DistributionMapping
+    // assigns to it, TortuosityHypre.H:68-80); one rank = the whole box
+    const amrex::Box local = m_ba.localBox();
+    p.z_begin = local.smallEnd(2) - domain.smallEnd(2); p.nz_local = local.length(2);
+    p.comm = amrex::ParallelDescriptor::Communicator();
+    if (amrex::ParallelDescriptor::NProcs() > 1) {
+        p.device = amrex::ParallelDescriptor::LocalDevice();
+        if (m_write_plotfile) amrex::Abort("TortuosityHypre: write_plotfile is not supported on more than one rank in this build");
+    }
     p.direction = static_cast<int>(m_dir);
     p.phase_id = m_phase;
     p.vlo = m_vlo; p.vhi = m_vhi;
     for (int d = 0; d < 3; ++d) p.dx[d] = m_geom.CellSize(d);
     p.eps = m_eps; p.maxiter = m_maxiter; p.verbose = m_verbose;
     amrex::ParmParse pp_b200("b200");            // extras of this implementation, all optional
-    pp_b200.query("device", p.device);
+    if (amrex::ParallelDescriptor::NProcs() <= 1) pp_b200.query("device", p.device);
     if (t_thread_device >= 0) p.device = t_thread_device;             // setThreadDevice()
     pp_b200.query("mg_degree", p.mg_degree);
     pp_b200.query("flux_polish", p.flux_polish);

@@ -13,7 +13,8 @@ VolumeFraction::VolumeFraction(const amrex::iMultiFab& fm, const int phase, int 
                                      "VolumeFraction: Component index out of bounds.");
 }
 
-VolumeFraction::Counts VolumeFraction::counts() const {
+// local = false: summed over the ranks (reference VolumeFraction.cpp:58-60, ReduceLongSum)
+VolumeFraction::Counts VolumeFraction::counts(bool local) const {
     const std::vector<int> cells = m_field->validCopy(m_component);
     int64_t n_phase = 0, n_total = 0;
     if (oi_count_phase_i32(cells.data(), (int64_t)cells.size(), m_phase_id, &n_phase, &n_total) != OI_OK)
@@ -21,15 +22,20 @@ VolumeFraction::Counts VolumeFraction::counts() const {
     Counts c;
     c.phase = n_phase;
     c.total = n_total;
+    if (!local && amrex::ParallelDescriptor::NProcs() > 1) {
+        long long v[2] = {c.phase, c.total};
+        amrex::ParallelDescriptor::ReduceLongSum(v, 2);
+        c.phase = v[0]; c.total = v[1];
+    }
     return c;
 }
 
-void VolumeFraction::value(long long& phase_count, long long& total_count, bool /*local*/) const {
-    const Counts c = counts();
+void VolumeFraction::value(long long& phase_count, long long& total_count, bool local) const {
+    const Counts c = counts(local);
     phase_count = c.phase;
     total_count = c.total;
 }
 
-amrex::Real VolumeFraction::value_vf(bool /*local*/) const { return counts().fraction(); }
+amrex::Real VolumeFraction::value_vf(bool local) const { return counts(local).fraction(); }
 
 }  // namespace OpenImpala

@@ -653,6 +653,30 @@ def test_diffusion_app_results_txt(host_bins):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_diffusion_app_on_several_ranks(host_bins, ranks, tmp_path):
+    """`Diffusion inputs b200.ranks=N`: the app starts N ranks (one per GPU), every rank reads its own z-slab of the
+    TIFF, the C++ classes take the slab from BoxArray / DistributionMapping and the rank's communicator
+    (reference: SPMD over MPI ranks, TortuosityHypre.H:68-80, Diffusion.cpp:266-268).  results.txt must equal the
+    one-rank file: VolumeFraction identical, tau to 1e-8."""
+    from openimpala_b200 import capi
+    if capi.device_count() < ranks:
+        pytest.skip(f"needs >= {ranks} GPUs")
+    out1, outn = tmp_path / "one", tmp_path / "many"
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", f"results_path={out1}")
+    run("Diffusion", "tests/inputs/diffusion_flow_through.inputs", f"results_path={outn}", f"b200.ranks={ranks}")
+
+    def parse(path):
+        lines = [l for l in open(os.path.join(path, "results.txt")).read().splitlines() if not l.startswith("#")]
+        return dict(l.split(": ") for l in lines)
+    a, b = parse(out1), parse(outn)
+    assert list(a) == list(b) == ["VolumeFraction", "Tortuosity_X", "Tortuosity_Y", "Tortuosity_Z"]
+    assert a["VolumeFraction"] == b["VolumeFraction"] == "0.398309000"
+    for k in ("Tortuosity_X", "Tortuosity_Y", "Tortuosity_Z"):
+        assert abs(float(a[k]) - float(b[k])) <= 1e-8 * float(a[k]), (k, a[k], b[k])
+
+
+@pytest.mark.gpu
 def test_diffusion_write_plotfile(host_bins):
     """write_plotfile = 1 (Diffusion.cpp:211, 696 -> TortuosityHypre.cpp:710-745): the solution,
     the phase ids and the percolation mask as <results_path>/tortuosity_solution_<dir>."""

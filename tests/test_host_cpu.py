@@ -343,6 +343,7 @@ def test_amrex_shim_bulk_routines(tmp_path):
     import subprocess
     exe = tmp_path / "shim_check"
     subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "openimpala_b200", "host", "amrex_shim"),
+                    "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "cpu_emul", "shim_check.cpp"), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr

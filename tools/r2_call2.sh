@@ -2,10 +2,11 @@
 # Round-2 GPU call 2 (one B200): new kernel variants (TMA ring, unrolled pair, NC=2 vector kernels) against the
 # defaults, and the (level-0 degree, coarse degree) sweep at 1024^3.
 O=gpurun_out/r2c2; mkdir -p $O
-python -m pytest tests/test_gpu_parity.py -q -k "tma_ring or pair_kernel_matches or flux_gate" > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
+python -m pytest tests/test_gpu_parity.py -q -k "tma_ring or pair_kernel_matches or flux_gate or tau_matches or sphere_packing_golden or coarse_tail or symmetric" > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
 tail -3 $O/tests.log
 B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 $B > $O/base.json 2> $O/base.err
+OI_COARSE_HALF=0 $B > $O/nohalf.json 2> $O/nohalf.err
 OI_TMA=1 $B > $O/tma.json 2> $O/tma.err
 OI_TMA=1 OI_PAIR=0 $B > $O/tma_nopair.json 2> $O/tma_nopair.err
 OI_PAIR=0 $B > $O/nopair.json 2> $O/nopair.err
