@@ -166,56 +166,84 @@ __device__ __forceinline__ float ld1h(const unsigned short* p) {
     return __half2float(*reinterpret_cast<const __half*>(p));
 }
 
-template <int MODE, bool HALF>
+// HALO (z-slabs): the boundary planes are visited last; the blocks that own plane 0 / nz-1 wait for the
+// neighbour's plane on the flag words of `hin` before they read the ghost plane, store their part of the
+// new plane into the neighbour's ghost plane (MODE 1) and publish `hout.seq` -- no push kernel and no
+// stream wait between two sweeps of a distributed level.
+template <int MODE, bool HALF, bool HALO>
 __global__ void __launch_bounds__(256)
 coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const float* __restrict__ b,
-                           float* __restrict__ out, float w) {
+                           float* __restrict__ out, float w, HaloIn hin, HaloOut hout) {
     const int i = blockIdx.x * 64 + (threadIdx.x & 15) * 4;
     const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
-    if (i >= L.nx || j >= L.ny) return;
+    const bool valid = i < L.nx && j < L.ny;
+    if (!HALO && !valid) return;
     const long long col = (long long)j * L.nx + i;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = blockIdx.z; k < L.nz; k += gridDim.z) {
-        const long long idx = (long long)k * L.plane + col;
-        const float4 d = HALF ? ld4h(L.hd + idx) : ld4(L.dg + idx);
-        float4 o = zero4;
-        if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
-            const float4 c = ld4(x + idx);
-            const float4 cxp = HALF ? ld4h(L.hx + idx) : ld4(L.cxp + idx);
-            const float4 cyp = HALF ? ld4h(L.hy + idx) : ld4(L.cyp + idx);
-            const float4 czp = HALF ? ld4h(L.hz + idx) : ld4(L.czp + idx);
-            const bool px = (L.periodic & PER_X) != 0, py = (L.periodic & PER_Y) != 0;
-            const long long iw = (i > 0) ? idx - 1 : idx + (L.nx - 1);
-            const long long js = (j > 0) ? idx - L.nx : idx + (long long)(L.ny - 1) * L.nx;
-            const long long jn = (j + 1 < L.ny) ? idx + L.nx : idx - (long long)j * L.nx;
-            const float cxw = (i > 0 || px) ? (HALF ? ld1h(L.hx + iw) : L.cxp[iw]) : 0.f;
-            const float xw = (i > 0 || px) ? x[iw] : 0.f;
-            const float xe = (i + 4 < L.nx) ? x[idx + 4] : (px ? x[idx - i] : 0.f);
-            const float4 cym = (j > 0 || py) ? (HALF ? ld4h(L.hy + js) : ld4(L.cyp + js)) : zero4;
-            const float4 ys = (j > 0 || py) ? ld4(x + js) : zero4;
-            const float4 yn = (j + 1 < L.ny || py) ? ld4(x + jn) : zero4;
-            const float4 czm = HALF ? ld4h(L.hz + idx - L.plane) : ld4(L.czp + idx - L.plane);   // k-1 may be the ghost plane
-            const float4 zd = ld4(x + idx - L.plane);
-            const float4 zu = ld4(x + idx + L.plane);
-            float4 acc;
-            acc.x = d.x * c.x - cxp.x * c.y - cxw * xw - cyp.x * yn.x - cym.x * ys.x - czp.x * zu.x - czm.x * zd.x;
-            acc.y = d.y * c.y - cxp.y * c.z - cxp.x * c.x - cyp.y * yn.y - cym.y * ys.y - czp.y * zu.y - czm.y * zd.y;
-            acc.z = d.z * c.z - cxp.z * c.w - cxp.y * c.y - cyp.z * yn.z - cym.z * ys.z - czp.z * zu.z - czm.z * zd.z;
-            acc.w = d.w * c.w - cxp.w * xe - cxp.z * c.z - cyp.w * yn.w - cym.w * ys.w - czp.w * zu.w - czm.w * zd.w;
-            const float4 bb = ld4(b + idx);
-            if (MODE == 1) {
-                o.x = d.x > 0.f ? c.x + w * (bb.x - acc.x) / d.x : 0.f;
-                o.y = d.y > 0.f ? c.y + w * (bb.y - acc.y) / d.y : 0.f;
-                o.z = d.z > 0.f ? c.z + w * (bb.z - acc.z) / d.z : 0.f;
-                o.w = d.w > 0.f ? c.w + w * (bb.w - acc.w) / d.w : 0.f;
-            } else {
-                o.x = d.x > 0.f ? bb.x - acc.x : 0.f;
-                o.y = d.y > 0.f ? bb.y - acc.y : 0.f;
-                o.z = d.z > 0.f ? bb.z - acc.z : 0.f;
-                o.w = d.w > 0.f ? bb.w - acc.w : 0.f;
+    for (int kk = blockIdx.z; kk < L.nz; kk += gridDim.z) {
+        int k = kk;
+        if (HALO) {
+            if (L.nz >= 2) k = (kk < L.nz - 2) ? kk + 1 : (kk == L.nz - 2 ? 0 : L.nz - 1);
+            const bool wlo = hin.flag_lo && k == 0, whi = hin.flag_hi && k == L.nz - 1;
+            if (wlo || whi) {
+                if (threadIdx.x == 0) {
+                    if (wlo) halo_spin(hin.flag_lo, hin.seq);
+                    if (whi) halo_spin(hin.flag_hi, hin.seq);
+                }
+                __syncthreads();
             }
         }
-        *reinterpret_cast<float4*>(out + idx) = o;
+        if (valid) {
+            const long long idx = (long long)k * L.plane + col;
+            const float4 d = HALF ? ld4h(L.hd + idx) : ld4(L.dg + idx);
+            float4 o = zero4;
+            if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
+                const float4 c = ld4(x + idx);
+                const float4 cxp = HALF ? ld4h(L.hx + idx) : ld4(L.cxp + idx);
+                const float4 cyp = HALF ? ld4h(L.hy + idx) : ld4(L.cyp + idx);
+                const float4 czp = HALF ? ld4h(L.hz + idx) : ld4(L.czp + idx);
+                const bool px = (L.periodic & PER_X) != 0, py = (L.periodic & PER_Y) != 0;
+                const long long iw = (i > 0) ? idx - 1 : idx + (L.nx - 1);
+                const long long js = (j > 0) ? idx - L.nx : idx + (long long)(L.ny - 1) * L.nx;
+                const long long jn = (j + 1 < L.ny) ? idx + L.nx : idx - (long long)j * L.nx;
+                const float cxw = (i > 0 || px) ? (HALF ? ld1h(L.hx + iw) : L.cxp[iw]) : 0.f;
+                const float xw = (i > 0 || px) ? x[iw] : 0.f;
+                const float xe = (i + 4 < L.nx) ? x[idx + 4] : (px ? x[idx - i] : 0.f);
+                const float4 cym = (j > 0 || py) ? (HALF ? ld4h(L.hy + js) : ld4(L.cyp + js)) : zero4;
+                const float4 ys = (j > 0 || py) ? ld4(x + js) : zero4;
+                const float4 yn = (j + 1 < L.ny || py) ? ld4(x + jn) : zero4;
+                const float4 czm = HALF ? ld4h(L.hz + idx - L.plane) : ld4(L.czp + idx - L.plane);   // k-1 may be the ghost plane
+                const float4 zd = ld4(x + idx - L.plane);
+                const float4 zu = ld4(x + idx + L.plane);
+                float4 acc;
+                acc.x = d.x * c.x - cxp.x * c.y - cxw * xw - cyp.x * yn.x - cym.x * ys.x - czp.x * zu.x - czm.x * zd.x;
+                acc.y = d.y * c.y - cxp.y * c.z - cxp.x * c.x - cyp.y * yn.y - cym.y * ys.y - czp.y * zu.y - czm.y * zd.y;
+                acc.z = d.z * c.z - cxp.z * c.w - cxp.y * c.y - cyp.z * yn.z - cym.z * ys.z - czp.z * zu.z - czm.z * zd.z;
+                acc.w = d.w * c.w - cxp.w * xe - cxp.z * c.z - cyp.w * yn.w - cym.w * ys.w - czp.w * zu.w - czm.w * zd.w;
+                const float4 bb = ld4(b + idx);
+                if (MODE == 1) {
+                    o.x = d.x > 0.f ? c.x + w * (bb.x - acc.x) / d.x : 0.f;
+                    o.y = d.y > 0.f ? c.y + w * (bb.y - acc.y) / d.y : 0.f;
+                    o.z = d.z > 0.f ? c.z + w * (bb.z - acc.z) / d.z : 0.f;
+                    o.w = d.w > 0.f ? c.w + w * (bb.w - acc.w) / d.w : 0.f;
+                } else {
+                    o.x = d.x > 0.f ? bb.x - acc.x : 0.f;
+                    o.y = d.y > 0.f ? bb.y - acc.y : 0.f;
+                    o.z = d.z > 0.f ? bb.z - acc.z : 0.f;
+                    o.w = d.w > 0.f ? bb.w - acc.w : 0.f;
+                }
+            }
+            *reinterpret_cast<float4*>(out + idx) = o;
+            if (HALO && MODE == 1) {
+                if (hout.dst_lo && k == 0) *reinterpret_cast<float4*>(static_cast<float*>(hout.dst_lo) + col) = o;
+                if (hout.dst_hi && k == L.nz - 1) *reinterpret_cast<float4*>(static_cast<float*>(hout.dst_hi) + col) = o;
+            }
+        }
+        if (HALO && MODE == 1) {
+            const unsigned int tiles = gridDim.x * gridDim.y;
+            if (hout.flag_lo && k == 0) halo_publish(hout.counter + 0, tiles, hout.flag_lo, nullptr, hout.seq);
+            if (hout.flag_hi && k == L.nz - 1) halo_publish(hout.counter + 1, tiles, nullptr, hout.flag_hi, hout.seq);
+        }
     }
 }
 
@@ -351,30 +379,41 @@ static dim3 grid_vec4(const CoarseLevel& L) {
     return dim3((L.nx + 63) / 64, (L.ny + 15) / 16, gz > 0 ? gz : 1);
 }
 
-void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w, cudaStream_t st) {
-    if (vec4_ok(L) && L.hd)
-        coarse_stencil_vec4_kernel<1, true><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
-            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), (float)w);
-    else if (vec4_ok(L))
-        coarse_stencil_vec4_kernel<1, false><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
-            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), (float)w);
-    else
-        coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
+template <int MODE>
+static void launch_vec4(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, float w, const HaloIn* hin,
+                        const HaloOut* hout, cudaStream_t st) {
+    const float* xf = reinterpret_cast<const float*>(x);
+    const float* bf = reinterpret_cast<const float*>(b);
+    float* of = reinterpret_cast<float*>(out);
+    const HaloIn hi = hin ? *hin : HaloIn{};
+    const HaloOut ho = hout ? *hout : HaloOut{};
+    const bool halo = hi.flag_lo || hi.flag_hi || ho.flag_lo || ho.flag_hi;
+    const dim3 g = grid_vec4(L);
+    if (L.hd) {
+        if (halo) coarse_stencil_vec4_kernel<MODE, true, true><<<g, 256, 0, st>>>(L, xf, bf, of, w, hi, ho);
+        else coarse_stencil_vec4_kernel<MODE, true, false><<<g, 256, 0, st>>>(L, xf, bf, of, w, hi, ho);
+    } else {
+        if (halo) coarse_stencil_vec4_kernel<MODE, false, true><<<g, 256, 0, st>>>(L, xf, bf, of, w, hi, ho);
+        else coarse_stencil_vec4_kernel<MODE, false, false><<<g, 256, 0, st>>>(L, xf, bf, of, w, hi, ho);
+    }
+}
+
+// whether coarse_smooth / coarse_residual run the kernel that can wait for / push the ghost planes itself
+bool coarse_halo_supported(const CoarseLevel& L) { return vec4_ok(L); }
+
+void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w, cudaStream_t st,
+                   const HaloIn* hin, const HaloOut* hout) {
+    if (vec4_ok(L)) launch_vec4<1>(L, x, b, out, (float)w, hin, hout, st);
+    else coarse_stencil_kernel<1><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)w);
 }
 
 void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec, cudaStream_t st) {
     coarse_prolong_add_kernel<<<grid3(L), 256, 0, st>>>(L, x, ec, next.nx, next.ny);
 }
 
-void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st) {
-    if (vec4_ok(L) && L.hd)
-        coarse_stencil_vec4_kernel<2, true><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
-            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
-    else if (vec4_ok(L))
-        coarse_stencil_vec4_kernel<2, false><<<grid_vec4(L), 256, 0, st>>>(L, reinterpret_cast<const float*>(x),
-            reinterpret_cast<const float*>(b), reinterpret_cast<float*>(out), 0.f);
-    else
-        coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
+void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st, const HaloIn* hin) {
+    if (vec4_ok(L)) launch_vec4<2>(L, x, b, out, 0.f, hin, nullptr, st);
+    else coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
 }
 
 void coarse_tail_cycle(const TailArgs& a, bool staged, cudaStream_t st) {

@@ -80,9 +80,13 @@ bool coarse_half_applicable(const CoarseLevel& L);       // this level runs the 
 void coarse_to_half(const float* src, unsigned short* dst, long long n, unsigned long long* mismatch, cudaStream_t st);
 void coarse_jacobi_first(const CoarseLevel& L, const mg_t* b, mg_t* out, double w, cudaStream_t st);
 // out = x + w (b - A x) / dg
+// hin / hout (z-slabs, optional): wait for the ghost planes of x inside the kernel / store the boundary planes of
+// out into the neighbours' ghost planes (only where coarse_halo_supported(L))
 void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w,
-                   cudaStream_t st);
-void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st);
+                   cudaStream_t st, const HaloIn* hin = nullptr, const HaloOut* hout = nullptr);
+void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st,
+                     const HaloIn* hin = nullptr);
+bool coarse_halo_supported(const CoarseLevel& L);
 // x += P * ec  (ec lives on level `next`)
 void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec,
                         cudaStream_t st);

@@ -347,7 +347,12 @@ prolong_add_vec4_kernel(Grid g, const uint8_t* __restrict__ flags, float* __rest
             }
         }
     }
-    if (HALO) halo_publish(ho.counter, gridDim.x * gridDim.y * gridDim.z, ho.flag_lo, ho.flag_hi, ho.seq);
+    if (HALO) {
+        // only the blocks that own a boundary plane stored into a neighbour: they alone fence and count in
+        const unsigned int tiles = gridDim.x * gridDim.y;
+        if (ho.flag_lo && blockIdx.z == 0) halo_publish(ho.counter + 0, tiles, ho.flag_lo, nullptr, ho.seq);
+        if (ho.flag_hi && (int)blockIdx.z == (g.nz - 1) % (int)gridDim.z) halo_publish(ho.counter + 1, tiles, nullptr, ho.flag_hi, ho.seq);
+    }
 }
 
 template <typename T, int MODE>

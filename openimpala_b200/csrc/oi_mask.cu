@@ -158,6 +158,19 @@ ccl_merge_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, int nz)
     }
 }
 
+// merge plane k with plane k-1 (one union per start of an overlap segment along x)
+__global__ void __launch_bounds__(BT)
+ccl_merge_zplane_kernel(const uint8_t* __restrict__ ph, int* L, int nx, long long plane, int k) {
+    const long long stride = (long long)gridDim.x * BT;
+    const long long base = (long long)k * plane;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < plane; t += stride) {
+        const long long idx = base + t;
+        if (!ph[idx] || !ph[idx - plane]) continue;
+        const bool left = (t % nx) > 0 && ph[idx - 1];
+        if (!(left && ph[idx - plane - 1])) uf_union(L, (int)idx, (int)(idx - plane));
+    }
+}
+
 __global__ void __launch_bounds__(BT)
 ccl_flatten_kernel(const uint8_t* __restrict__ ph, int* L, long long n) {
     const long long stride = (long long)gridDim.x * BT;
@@ -580,10 +593,25 @@ int ccl_label(const uint8_t* ph, int* L, int nx, int ny, int nz, int n_sm, cudaS
     const long long n = (long long)nx * ny * nz;
     const long long nrows = (long long)ny * nz;
     ccl_rows_kernel<<<nblocks(nrows * 32, n_sm), BT, 0, st>>>(ph, L, nx, nrows);
-    // (merging within planes first, flattening, then merging across planes was measured: no faster)
-    ccl_merge_kernel<3><<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
+    // OI_CCL=0: every union (across y and across z) in one pass over the box.  At 1024^3 that pass costs
+    // ~80 ms (ncu: profiles/r2_launches_1024.csv) although it moves little data: every plane hooks onto
+    // every other at once, and finds walk parent chains that cross many planes before path halving has
+    // shortened them.  Default: merge inside the planes first (trees stay inside one plane), flatten, then
+    // merge plane k onto plane k-1 for k = 1, 2, ... in stream order -- when plane k is merged everything
+    // below is already resolved, so a find is two or three hops.  nz - 1 small launches instead of one big one.
+    const char* e = getenv("OI_CCL");
+    if (e && e[0] == '0') {
+        ccl_merge_kernel<3><<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
+        ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
+        return 3;
+    }
+    const long long plane = (long long)nx * ny;
+    ccl_merge_kernel<1><<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
     ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
-    return 3;
+    for (int k = 1; k < nz; ++k)
+        ccl_merge_zplane_kernel<<<nblocks(plane, n_sm), BT, 0, st>>>(ph, L, nx, plane, k);
+    ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
+    return 3 + nz;
 }
 void ccl_mark_planes(const uint8_t* ph, const int* L, unsigned int* reach, int nx, int ny, int nz,
                      int dir, int lo_local, int hi_local, int n_sm, cudaStream_t st) {

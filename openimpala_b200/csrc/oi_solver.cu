@@ -1147,31 +1147,45 @@ void coarse_cycle(oi_solver* S, size_t l) {
     mg_t* oth = L.x;
     static const char* lvl_names[] = {"mg level 1", "mg level 2", "mg level 3", "mg level 4", "mg levels 5+"};
     prof_mark(S, lvl_names[l < 4 ? l : 4]);
-    oi::coarse_jacobi_first(L, L.b, cur, w[0], S->st); S->launches++;
-    for (int s = 1; s < deg; ++s) {
-        haloL(S, L, cur);
-        oi::coarse_smooth(L, cur, L.b, oth, w[s], S->st); S->launches++;
+    // z-slabs: on a distributed level the sweep kernel waits for the ghost planes of its input itself and
+    // stores the boundary planes of its output into the neighbours (HaloIn / HaloOut); the first sweep after
+    // jacobi_first / the prolongation still sees the explicit exchange (those kernels do not push)
+    const size_t pbytes = (size_t)L.plane * sizeof(mg_t);
+    const bool fuse_c = S->n_ranks > 1 && !L.replicated && oi::coarse_halo_supported(L);
+    auto sweep = [&](double wt, bool consumed) {
+        HaloIn hin{};
+        HaloOut hout{};
+        if (fuse_c) {
+            halo_consume(S, cur, pbytes, L.nz, &hin);
+            if (!(consumed && peer_prepare_push(S, oth, pbytes, L.nz, &hout))) peer_invalidate(S, oth);
+        } else {
+            haloL(S, L, cur);
+            if (S->n_ranks > 1) peer_invalidate(S, oth);
+        }
+        oi::coarse_smooth(L, cur, L.b, oth, wt, S->st, &hin, &hout); S->launches++;
         std::swap(cur, oth);
-    }
+    };
+    oi::coarse_jacobi_first(L, L.b, cur, w[0], S->st); S->launches++;
+    if (S->n_ranks > 1) peer_invalidate(S, cur);
+    for (int s = 1; s < deg; ++s) sweep(w[s], !last || s + 1 < deg);
     if (!last) {
         HostLevel& hn = S->levels[l + 1];
         // W-cycle from MG level w_from on: the child (MG level l + 2) is visited twice, each visit
         // on the residual of the correction so far (symmetric: 2B - BAB for a symmetric child cycle B)
         const int visits = (S->w_from > 0 && (int)l + 2 >= S->w_from) ? 2 : 1;
         for (int v = 0; v < visits; ++v) {
-            haloL(S, L, cur);
-            oi::coarse_residual(L, cur, L.b, oth, S->st); S->launches++;
+            HaloIn hin{};
+            if (fuse_c) halo_consume(S, cur, pbytes, L.nz, &hin);
+            else haloL(S, L, cur);
+            if (S->n_ranks > 1) peer_invalidate(S, oth);
+            oi::coarse_residual(L, cur, L.b, oth, S->st, &hin); S->launches++;
             oi::coarse_restrict(L, oth, hn.L, hn.L.b, S->st); S->launches++;
             coarse_cycle(S, l + 1);
             prof_mark(S, lvl_names[l < 4 ? l : 4]);
             oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
+            if (S->n_ranks > 1) peer_invalidate(S, cur);
         }
-        for (int s = 0; s < deg; ++s) {
-            haloL(S, L, cur);
-            oi::coarse_smooth(L, cur, L.b, oth, w[deg - 1 - s], S->st);
-            S->launches++;
-            std::swap(cur, oth);
-        }
+        for (int s = 0; s < deg; ++s) sweep(w[deg - 1 - s], s + 1 < deg);
     }
     if (cur != L.x) { L.t = L.x; L.x = cur; }
 }
@@ -1501,7 +1515,6 @@ void run_solve(oi_solver* S) {
     // polish round cut short by maxiter must not downgrade it (x only ever moved along A-norm
     // descent directions since the confirmation); the residual reported is the true one.
     bool confirmed_at_eps = false;
-    double rr_confirmed = 0.0;
 
     while (!fail) {
         if (!converged) {
@@ -1555,9 +1568,9 @@ void run_solve(oi_solver* S) {
                 continue;
             }
         }
-        if (polish_rounds == 0) { confirmed_at_eps = true; rr_confirmed = rr; }
+        if (polish_rounds == 0) confirmed_at_eps = true;
         // optional flux polish: stay well inside the reference's 1e-6 conservation gate
-        if (S->prm.flux_polish && !cellp && polish_rounds < 4 && it < S->prm.maxiter && rr > 0.0) {
+        if (S->prm.flux_polish && !cellp && polish_rounds < 8 && it < S->prm.maxiter && rr > 0.0) {
             double fin, fout;
             compute_fluxes(S, &fin, &fout);
             const double avg = 0.5 * (std::fabs(fin) + std::fabs(fout));
@@ -1592,7 +1605,6 @@ void run_solve(oi_solver* S) {
     // m_converged = finite && 0 <= relres <= eps  (TortuosityHypre.cpp:687-688)
     info.converged = (!fail && std::isfinite(info.rel_residual) && info.rel_residual >= 0.0 &&
                       (info.rel_residual <= S->prm.eps * 1.0000001 || (confirmed_at_eps && polish_rounds > 0))) ? 1 : 0;
-    (void)rr_confirmed;
     S->solved = true;
 }
 
@@ -2021,7 +2033,9 @@ int oi_create(oi_solver** out, const oi_params* p) {
         { const char* e = getenv("OI_PROFILE"); S->prof_on = (e && e[0] == '1'); }
         S->n_local = g.plane * nzl;
         S->n_dir = p->direction == 0 ? p->nx : (p->direction == 1 ? p->ny : p->nz);
-        const int deg = p->mg_degree > 0 ? p->mg_degree : 4;
+        // level-0 degree 5 with degree 8 below: 18 PCG iterations at 1024^3 (round 1: degree 4 everywhere, 26);
+        // profiles/r2_degree_sweep.md
+        const int deg = p->mg_degree > 0 ? p->mg_degree : 5;
         OI_REQUIRE(deg <= 16, "mg_degree too large");
         static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
         S->w_smooth = cheb_weights(deg, deg <= 8 ? lo_tab[deg] : 0.07);

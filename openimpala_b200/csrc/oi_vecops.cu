@@ -163,12 +163,13 @@ axpy2_dot_first_kernel(Grid g, const uint8_t* __restrict__ flags, long long n, d
             else acc += axpy2_first_range<UPDATE_X, false, 2>(0, plane, t, nthr, flags, x, r, p, q, r32, z1, a, winv, nullptr);
             if (ho.dst_hi) acc += axpy2_first_range<UPDATE_X, true, 2>(top, n, t, nthr, flags, x, r, p, q, r32, z1, a, winv, static_cast<mg_t*>(ho.dst_hi));
             else acc += axpy2_first_range<UPDATE_X, false, 2>(top, n, t, nthr, flags, x, r, p, q, r32, z1, a, winv, nullptr);
+            // only the blocks that stored into the neighbours fence at system scope and count in
+            halo_publish(ho.counter, (unsigned int)halo_blocks, ho.flag_lo, ho.flag_hi, ho.seq);
         } else if (top > plane) {
             acc = axpy2_first_range<UPDATE_X, false, NCI>(plane, top, (long long)(blockIdx.x - halo_blocks) * VT + threadIdx.x,
                                                         (long long)(gridDim.x - halo_blocks) * VT, flags, x, r, p, q, r32, z1, a,
                                                         winv, nullptr);
         }
-        halo_publish(ho.counter, gridDim.x, ho.flag_lo, ho.flag_hi, ho.seq);
     }
     double v[1] = {acc};
     grid_reduce<1>(v, partials, counter, out);
@@ -232,7 +233,7 @@ __device__ __forceinline__ void xpby_range(long long lo, long long hi, long long
 // neighbours' ghost planes as well, the rest of the grid runs the plain loop over the interior planes;
 // the last block to finish publishes the exchange.
 template <bool UPDATE_X, bool HALO, int NCI>
-__global__ void __launch_bounds__(VT, HALO ? 3 : (NCI == 4 ? 0 : 4))      // (HALO: keep the three blocks per SM of the plain kernel)
+__global__ void __launch_bounds__(VT, NCI == 4 ? 0 : 4)
 xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__ p, const mg_t* __restrict__ z,
             const double* __restrict__ num, const double* __restrict__ den, double* __restrict__ x,
             const double* __restrict__ anum, const double* __restrict__ aden, long long plane, int halo_blocks,
@@ -257,11 +258,12 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
             // (at least two planes, checked by the launcher: the two boundary planes are distinct)
             if (ho.dst_hi) xpby_range<UPDATE_X, true, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_hi));
             else xpby_range<UPDATE_X, false, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, nullptr);
+            // only the blocks that stored into the neighbours fence at system scope and count in
+            halo_publish(ho.counter, (unsigned int)halo_blocks, ho.flag_lo, ho.flag_hi, ho.seq);
         } else if (top > plane) {
-            xpby_range<UPDATE_X, false, 4>(plane, top, (long long)(blockIdx.x - halo_blocks) * VT + threadIdx.x,
-                                           (long long)(gridDim.x - halo_blocks) * VT, flags, p, z, x, bta, alpha, nullptr);
+            xpby_range<UPDATE_X, false, NCI>(plane, top, (long long)(blockIdx.x - halo_blocks) * VT + threadIdx.x,
+                                             (long long)(gridDim.x - halo_blocks) * VT, flags, p, z, x, bta, alpha, nullptr);
         }
-        halo_publish(ho.counter, gridDim.x, ho.flag_lo, ho.flag_hi, ho.seq);
     }
 }
 
@@ -378,7 +380,7 @@ void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const
         int hb = (int)((2 * plane * (long long)nb + n - 1) / n);
         hb = hb < 1 ? 1 : hb;
         const int nbt = nb + hb;
-        if (x) xpby_kernel<true, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, plane, hb, *ho);
+        if (x) xpby_kernel<true, true, 2><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, plane, hb, *ho);
         else xpby_kernel<false, true, 4><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, nullptr, nullptr, nullptr, plane, hb, *ho);
     } else {
         if (x && vec_nc(2) == 2) xpby_kernel<true, false, 2><<<nb, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, 0, 0, none);
