@@ -1681,7 +1681,9 @@ void build_mask(oi_solver* S) {
     CUDA_CHECK(cudaMemsetAsync(d_reach, 0, reach_words * sizeof(unsigned int), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->d_ull, 0, 8 * sizeof(unsigned long long), S->st));
 
+    prof_mark(S, "mask: labelling (CCL)");
     S->launches += oi::ccl_label(S->d_isphase, d_labels, g.nx, g.ny, g.nz, S->n_sm, S->st);
+    prof_mark(S, "mask: plane marks + slab fixed point");
     int lo_local = 0, hi_local = S->n_dir - 1;
     if (dir == 2) {
         lo_local = (g.z0 == 0) ? 0 : -1;
@@ -1723,6 +1725,7 @@ void build_mask(oi_solver* S) {
 
     if (!S->active.base) S->active.alloc(g.plane, g.nz, S->st);
     if (!S->flags.base) S->flags.alloc(g.plane, g.nz, S->st);
+    prof_mark(S, "mask: active + connectivity bytes");
     oi::build_active(S->d_isphase, d_labels, d_reach, S->active.p, g.nx, g.ny, g.nz, S->d_ull + 0,
                      S->n_sm, S->st); S->launches++;
     halo_exchange_bytes(S, S->active.p, (size_t)g.plane, g.nz);
@@ -1737,6 +1740,7 @@ void build_mask(oi_solver* S) {
     S->n_out = (long long)h[2];
     // the scratch aliases held integers: restore the vectors' invariant (zero
     // everywhere, ghost planes included) before they are used as fp64 fields
+    prof_mark(S, "mask: re-zero vectors + initial guess");
     CUDA_CHECK(cudaMemsetAsync(S->p.base, 0, S->p.count * sizeof(double), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->q.base, 0, S->q.count * sizeof(double), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->r.base, 0, S->r.count * sizeof(double), S->st));
@@ -1752,6 +1756,8 @@ void build_mask(oi_solver* S) {
         CUDA_CHECK(cudaMemsetAsync(S->x.base, 0, S->x.count * sizeof(double), S->st));
         CUDA_CHECK(cudaStreamSynchronize(S->st));
     }
+    prof_mark(S, "end");
+    prof_report(S, 1);
     S->mask_built = true;
 }
 
@@ -2038,7 +2044,9 @@ int oi_create(oi_solver** out, const oi_params* p) {
         const int deg = p->mg_degree > 0 ? p->mg_degree : 5;
         OI_REQUIRE(deg <= 16, "mg_degree too large");
         static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
-        S->w_smooth = cheb_weights(deg, deg <= 8 ? lo_tab[deg] : 0.07);
+        double lo0 = deg <= 8 ? lo_tab[deg] : 0.07;
+        if (const char* e = getenv("OI_MG_LO0")) { const double v = std::atof(e); if (v > 0.0 && v < 1.0) lo0 = v; }   // experiments
+        S->w_smooth = cheb_weights(deg, lo0);
         S->w_coarse = cheb_weights(8, 0.05);
         // Levels >= 1 smooth with degree 8 per leg whatever the level-0 degree: a sweep there costs 1/8 (and
         // less) of a level-0 sweep, and the stronger coarse solves take the 1024^3 packing from 26 to 20 PCG
@@ -2046,7 +2054,9 @@ int oi_create(oi_solver** out, const oi_params* p) {
         int dc = 8;
         if (const char* e = getenv("OI_MG_DEG_COARSE")) dc = std::atoi(e);
         if (dc < 1 || dc > 16) dc = 8;
-        S->w_mid = cheb_weights(dc, dc <= 8 ? lo_tab[dc] : 0.07);
+        double loc = dc <= 8 ? lo_tab[dc] : 0.07;
+        if (const char* e = getenv("OI_MG_LOC")) { const double v = std::atof(e); if (v > 0.0 && v < 1.0) loc = v; }   // experiments
+        S->w_mid = cheb_weights(dc, loc);
         if (const char* e = getenv("OI_MG_W_FROM")) S->w_from = std::max(0, std::atoi(e));
         CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
         CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));

@@ -253,11 +253,11 @@ xpby_kernel(long long n, const uint8_t* __restrict__ flags, double* __restrict__
         const long long top = n - plane;
         if ((int)blockIdx.x < halo_blocks) {
             const long long t = (long long)blockIdx.x * VT + threadIdx.x, nthr = (long long)halo_blocks * VT;
-            if (ho.dst_lo) xpby_range<UPDATE_X, true, 1>(0, plane, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_lo));
-            else xpby_range<UPDATE_X, false, 1>(0, plane, t, nthr, flags, p, z, x, bta, alpha, nullptr);
+            if (ho.dst_lo) xpby_range<UPDATE_X, true, 2>(0, plane, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_lo));
+            else xpby_range<UPDATE_X, false, 2>(0, plane, t, nthr, flags, p, z, x, bta, alpha, nullptr);
             // (at least two planes, checked by the launcher: the two boundary planes are distinct)
-            if (ho.dst_hi) xpby_range<UPDATE_X, true, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_hi));
-            else xpby_range<UPDATE_X, false, 1>(top, n, t, nthr, flags, p, z, x, bta, alpha, nullptr);
+            if (ho.dst_hi) xpby_range<UPDATE_X, true, 2>(top, n, t, nthr, flags, p, z, x, bta, alpha, static_cast<double*>(ho.dst_hi));
+            else xpby_range<UPDATE_X, false, 2>(top, n, t, nthr, flags, p, z, x, bta, alpha, nullptr);
             // only the blocks that stored into the neighbours fence at system scope and count in
             halo_publish(ho.counter, (unsigned int)halo_blocks, ho.flag_lo, ho.flag_hi, ho.seq);
         } else if (top > plane) {
@@ -352,8 +352,8 @@ void vec_axpy2_dot_first(const Grid& g, const uint8_t* flags, long long n, doubl
     const int nb = nblocks((n + 1) / 2, n_sm);
     const HaloOut none{};
     if (ho && x == nullptr && vec_halo_supported(g.plane, n)) {
-        int hb = (int)((2 * g.plane * (long long)nb + n - 1) / n);
-        hb = hb < 1 ? 1 : hb;
+        int hb = (int)((8 * g.plane * (long long)nb + n - 1) / n);        // four times the fair share (see vec_xpby)
+        hb = hb < 8 ? 8 : hb;
         // (the grid reduction's scratch holds vec_max_blocks + a margin of blocks: stay within nb)
         const int nbt = nb;
         hb = hb >= nbt ? nbt - 1 : hb;
@@ -376,8 +376,10 @@ void vec_xpby(long long n, const uint8_t* flags, double* p, const mg_t* z, const
     const int nb = nblocks((n + 1) / 2, n_sm);
     const HaloOut none{};
     if (ho && vec_halo_supported(plane, n)) {
-        // enough blocks for the two boundary planes to finish with the interior
-        int hb = (int)((2 * plane * (long long)nb + n - 1) / n);
+        // blocks for the two boundary planes: four times their fair share (their loop carries fewer loads in
+        // flight and stores across NVLink), so that they are never the tail of the kernel
+        int hb = (int)((8 * plane * (long long)nb + n - 1) / n);
+        hb = hb < 8 ? 8 : (hb > nb / 4 ? nb / 4 : hb);
         hb = hb < 1 ? 1 : hb;
         const int nbt = nb + hb;
         if (x) xpby_kernel<true, true, 2><<<nbt, VT, 0, st>>>(n, flags, p, z, num, den, x, anum, aden, plane, hb, *ho);

@@ -47,6 +47,9 @@ def load():
         lib.oo_tortuosity.restype = C.c_int
         lib.oo_tortuosity.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_double,
                                       C.c_double, C.c_double, C.c_int, C.c_void_p]
+        lib.oo_tortuosity_mg.restype = C.c_int
+        lib.oo_tortuosity_mg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_double,
+                                         C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -132,6 +135,19 @@ def tortuosity(phase, phase_id, direction, vlo=-1.0, vhi=1.0, eps=1e-9, maxiter=
     out = np.zeros(9)
     load().oo_tortuosity(p.ctypes.data, nx, ny, nz, phase_id, direction, vlo, vhi, eps, maxiter, out.ctypes.data)
     keys = ("tau", "deff", "active_vf", "flux_in", "flux_out", "iters", "relres", "n_active", "solve_s")
+    d = dict(zip(keys, out.tolist()))
+    d["iters"], d["n_active"] = int(d["iters"]), int(d["n_active"])
+    return d
+
+
+def tortuosity_mg(phase, phase_id, direction, vlo=-1.0, vhi=1.0, eps=1e-9, maxiter=200, d0=0, dc=0):
+    """The same path with the CPU port of the GPU arm's MG-PCG solver (oo_solve_mgpcg) instead of Jacobi-PCG.
+    -> dict(tau, deff, active_vf, flux_in, flux_out, iters, relres, n_active, solve_s, mask_s)"""
+    p = _i32(phase)
+    nz, ny, nx = p.shape
+    out = np.zeros(10)
+    load().oo_tortuosity_mg(p.ctypes.data, nx, ny, nz, phase_id, direction, vlo, vhi, eps, maxiter, d0, dc, out.ctypes.data)
+    keys = ("tau", "deff", "active_vf", "flux_in", "flux_out", "iters", "relres", "n_active", "solve_s", "mask_s")
     d = dict(zip(keys, out.tolist()))
     d["iters"], d["n_active"] = int(d["iters"]), int(d["n_active"])
     return d

@@ -495,3 +495,260 @@ void oo_effdiff_gradient_sums(const double* chi, const int32_t* phase, int32_t p
     sums3[0] = sx; sums3[1] = sy; sums3[2] = sz;
     if (n_active) *n_active = na;
 }
+
+/* ===========================================================================
+ * CPU port of the GPU arm's solver (benchmark baseline, and a third independent
+ * solve for the parity tests): PCG preconditioned by one geometric V-cycle on the
+ * system with its identity rows eliminated -- the algorithm of
+ * openimpala_b200/csrc/oi_solver.cu restated for host cores in plain C + OpenMP,
+ * all in fp64.  It stands where HYPRE's FlexGMRES + SMG V-cycle stands in the
+ * reference (src/props/TortuosityHypre.cpp:666-691): a multigrid-preconditioned
+ * Krylov solve with the reference's stopping rule, so its time is a far fairer CPU
+ * baseline than Jacobi-PCG.  Coarse operators: 2x2x2 aggregation, couplings summed
+ * over coarse faces and scaled by 1/2 (the rediscretisation-equivalent operator),
+ * diagonal = outward couplings + sink terms; smoother: Jacobi with the reciprocals
+ * of the Chebyshev roots as weights (degree d0 on level 0, dc below), mirrored
+ * before / after the coarse correction; coarsest level: 8 sweeps.
+ * =========================================================================== */
+typedef struct {
+    int nx, ny, nz;
+    double *cx, *cy, *cz, *dg;      /* coupling to the +x,+y,+z neighbour; diagonal (0 = no unknown) */
+    double *x, *b, *t;
+} mg_level;
+
+static void mg_free(mg_level* L) { free(L->cx); free(L->cy); free(L->cz); free(L->dg); free(L->x); free(L->b); free(L->t); }
+
+static void mg_cheb(int deg, double lo_frac, double* w) {
+    const double a = lo_frac * 2.0, b = 2.0;
+    for (int k = 1; k <= deg; ++k)
+        w[k - 1] = 1.0 / (0.5 * (a + b) + 0.5 * (b - a) * cos(3.14159265358979323846 * (2.0 * k - 1.0) / (2.0 * deg)));
+}
+
+/* out = x + w (b - A x) / dg  (res == 1: out = b - A x; res == 2: out = A x);  x == NULL means a zero guess */
+static void mg_sweep(const mg_level* L, const double* x, const double* b, double* out, double w, int res) {
+    const int nx = L->nx, ny = L->ny, nz = L->nz;
+    const int64_t sy = nx, sz = (int64_t)nx * ny;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t m = ((int64_t)k * ny + j) * nx + i;
+                const double d = L->dg[m];
+                if (!(d > 0.0)) { out[m] = 0.0; continue; }
+                if (!x) { out[m] = res ? b[m] : w * b[m] / d; continue; }
+                double ax = d * x[m];
+                if (i + 1 < nx) ax -= L->cx[m] * x[m + 1];
+                if (i > 0) ax -= L->cx[m - 1] * x[m - 1];
+                if (j + 1 < ny) ax -= L->cy[m] * x[m + sy];
+                if (j > 0) ax -= L->cy[m - sy] * x[m - sy];
+                if (k + 1 < nz) ax -= L->cz[m] * x[m + sz];
+                if (k > 0) ax -= L->cz[m - sz] * x[m - sz];
+                out[m] = res == 2 ? ax : (res ? b[m] - ax : x[m] + w * (b[m] - ax) / d);
+            }
+}
+
+static void mg_coarsen(const mg_level* F, mg_level* C) {
+    const int nx = (F->nx + 1) / 2, ny = (F->ny + 1) / 2, nz = (F->nz + 1) / 2;
+    const size_t n = (size_t)nx * ny * nz;
+    C->nx = nx; C->ny = ny; C->nz = nz;
+    C->cx = (double*)calloc(n, sizeof(double)); C->cy = (double*)calloc(n, sizeof(double));
+    C->cz = (double*)calloc(n, sizeof(double)); C->dg = (double*)calloc(n, sizeof(double));
+    C->x = (double*)calloc(n, sizeof(double)); C->b = (double*)calloc(n, sizeof(double)); C->t = (double*)calloc(n, sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int K = 0; K < nz; ++K)
+        for (int J = 0; J < ny; ++J)
+            for (int I = 0; I < nx; ++I) {
+                double sx = 0, sy = 0, sz = 0, sd = 0, in = 0;
+                for (int k = 2 * K; k < 2 * K + 2 && k < F->nz; ++k)
+                    for (int j = 2 * J; j < 2 * J + 2 && j < F->ny; ++j)
+                        for (int i = 2 * I; i < 2 * I + 2 && i < F->nx; ++i) {
+                            const int64_t m = ((int64_t)k * F->ny + j) * F->nx + i;
+                            sd += F->dg[m];
+                            if (i + 1 < F->nx) { if (i + 1 < 2 * I + 2) in += F->cx[m]; else sx += F->cx[m]; }
+                            if (j + 1 < F->ny) { if (j + 1 < 2 * J + 2) in += F->cy[m]; else sy += F->cy[m]; }
+                            if (k + 1 < F->nz) { if (k + 1 < 2 * K + 2) in += F->cz[m]; else sz += F->cz[m]; }
+                        }
+                const int64_t M = ((int64_t)K * ny + J) * nx + I;
+                C->cx[M] = 0.5 * sx; C->cy[M] = 0.5 * sy; C->cz[M] = 0.5 * sz;
+                C->dg[M] = 0.5 * (sd - 2.0 * in);
+            }
+}
+
+static void mg_restrict(const mg_level* F, const double* res, mg_level* C) {
+#pragma omp parallel for schedule(static)
+    for (int K = 0; K < C->nz; ++K)
+        for (int J = 0; J < C->ny; ++J)
+            for (int I = 0; I < C->nx; ++I) {
+                double s = 0.0;
+                for (int k = 2 * K; k < 2 * K + 2 && k < F->nz; ++k)
+                    for (int j = 2 * J; j < 2 * J + 2 && j < F->ny; ++j)
+                        for (int i = 2 * I; i < 2 * I + 2 && i < F->nx; ++i)
+                            s += res[((int64_t)k * F->ny + j) * F->nx + i];
+                C->b[((int64_t)K * C->ny + J) * C->nx + I] = s;
+            }
+}
+
+static void mg_prolong_add(const mg_level* F, double* x, const mg_level* C) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < F->nz; ++k)
+        for (int j = 0; j < F->ny; ++j)
+            for (int i = 0; i < F->nx; ++i) {
+                const int64_t m = ((int64_t)k * F->ny + j) * F->nx + i;
+                if (F->dg[m] > 0.0) x[m] += C->x[((int64_t)(k >> 1) * C->ny + (j >> 1)) * C->nx + (i >> 1)];
+            }
+}
+
+/* L[l].x = M^-1 L[l].b by one V-cycle (zero initial guess); w0: level-0 weights, wm: levels below, wc: coarsest */
+static void mg_vcycle(mg_level* L, int l, int nl, const double* w0, int d0, const double* wm, int dm, const double* wc, int dc) {
+    mg_level* A = &L[l];
+    const int last = (l + 1 == nl);
+    const double* w = last ? wc : (l == 0 ? w0 : wm);
+    const int deg = last ? dc : (l == 0 ? d0 : dm);
+    double *cur = A->x, *oth = A->t, *tmp;
+    mg_sweep(A, NULL, A->b, cur, w[0], 0);
+    for (int s = 1; s < deg; ++s) { mg_sweep(A, cur, A->b, oth, w[s], 0); tmp = cur; cur = oth; oth = tmp; }
+    if (!last) {
+        mg_sweep(A, cur, A->b, oth, 0.0, 1);
+        mg_restrict(A, oth, &L[l + 1]);
+        mg_vcycle(L, l + 1, nl, w0, d0, wm, dm, wc, dc);
+        mg_prolong_add(A, cur, &L[l + 1]);
+        for (int s = 0; s < deg; ++s) { mg_sweep(A, cur, A->b, oth, w[deg - 1 - s], 0); tmp = cur; cur = oth; oth = tmp; }
+    }
+    if (cur != A->x) { A->t = A->x; A->x = cur; }
+}
+
+/* Solve the eliminated system of the tortuosity problem by MG-PCG.  mask: activity mask (oo_activity_mask);
+ * x: out, the full potential field (Dirichlet values on the active plane cells, 0 on inactive cells).
+ * Stop rule and return values as oo_solve_pcg.  d0 / dc: smoothing degree on level 0 / below (0 = 5 / 8). */
+int oo_solve_mgpcg(const uint8_t* mask, int nx, int ny, int nz, int dir, double vlo, double vhi, double eps,
+                   int maxiter, int d0, int dc, double* x, double* relres) {
+    const int64_t n = (int64_t)nx * ny * nz, sy = nx, sz = (int64_t)nx * ny;
+    const int nd = dir == 0 ? nx : (dir == 1 ? ny : nz);
+    if (d0 <= 0) d0 = 5;
+    if (dc <= 0) dc = 8;
+    if (d0 > 16) d0 = 16;
+    if (dc > 16) dc = 16;
+    static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
+    double w0[16], wm[16], wc[8];
+    mg_cheb(d0, d0 <= 8 ? lo_tab[d0] : 0.07, w0);
+    mg_cheb(dc, dc <= 8 ? lo_tab[dc] : 0.07, wm);
+    mg_cheb(8, 0.05, wc);
+    mg_level L[20];
+    int nl = 1;
+    mg_level* F = &L[0];
+    F->nx = nx; F->ny = ny; F->nz = nz;
+    F->cx = (double*)calloc((size_t)n, sizeof(double)); F->cy = (double*)calloc((size_t)n, sizeof(double));
+    F->cz = (double*)calloc((size_t)n, sizeof(double)); F->dg = (double*)calloc((size_t)n, sizeof(double));
+    F->x = (double*)calloc((size_t)n, sizeof(double)); F->b = (double*)calloc((size_t)n, sizeof(double)); F->t = (double*)calloc((size_t)n, sizeof(double));
+    double* bvec = (double*)calloc((size_t)n, sizeof(double));       /* rhs of the eliminated system */
+    int64_t n_in = 0, n_out = 0;
+    /* level 0 from the mask (tortuosity_fillmtx with its identity rows eliminated, F90:111-228) */
+#pragma omp parallel for schedule(static) reduction(+ : n_in, n_out)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int64_t m = ((int64_t)k * ny + j) * nx + i;
+                x[m] = 0.0;
+                if (!mask[m]) continue;
+                const int d = dir == 0 ? i : (dir == 1 ? j : k);
+                if (d == 0) { x[m] = vlo; ++n_in; continue; }
+                if (d == nd - 1) { x[m] = vhi; ++n_out; continue; }
+                x[m] = vlo + (vhi - vlo) * (double)d * (nd > 1 ? 1.0 / (double)(nd - 1) : 0.0);   /* ramp, F90:233-262 */
+                double diag = 0.0, rhs = 0.0;
+                const int64_t nb[6] = {m - 1, m + 1, m - sy, m + sy, m - sz, m + sz};
+                const int ok[6] = {i > 0, i + 1 < nx, j > 0, j + 1 < ny, k > 0, k + 1 < nz};
+                const int dn[6] = {dir == 0 ? d - 1 : d, dir == 0 ? d + 1 : d, dir == 1 ? d - 1 : d, dir == 1 ? d + 1 : d,
+                                   dir == 2 ? d - 1 : d, dir == 2 ? d + 1 : d};
+                for (int s = 0; s < 6; ++s) {
+                    if (!ok[s] || !mask[nb[s]]) continue;
+                    diag += 1.0;
+                    if (dn[s] == 0) rhs += vlo;                        /* Dirichlet neighbour: to the rhs */
+                    else if (dn[s] == nd - 1) rhs += vhi;
+                    else if (s == 1) F->cx[m] = 1.0;
+                    else if (s == 3) F->cy[m] = 1.0;
+                    else if (s == 5) F->cz[m] = 1.0;
+                }
+                F->dg[m] = diag;
+                bvec[m] = rhs;
+            }
+    while (nl < 20 && (L[nl - 1].nx >= 3 || L[nl - 1].ny >= 3 || L[nl - 1].nz >= 3) &&
+           (int64_t)L[nl - 1].nx * L[nl - 1].ny * L[nl - 1].nz > 64) {
+        mg_coarsen(&L[nl - 1], &L[nl]);
+        ++nl;
+    }
+    double* r = (double*)calloc((size_t)n, sizeof(double));
+    double* p = (double*)calloc((size_t)n, sizeof(double));
+    double* q = (double*)calloc((size_t)n, sizeof(double));
+    double* u = (double*)calloc((size_t)n, sizeof(double));            /* unknown part of x */
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < n; ++m) u[m] = F->dg[m] > 0.0 ? x[m] : 0.0;
+    mg_sweep(F, u, bvec, r, 0.0, 1);                                  /* r = b - A u */
+    const double bnorm = sqrt((double)n_in * vlo * vlo + (double)n_out * vhi * vhi);
+    double rn = sqrt(dot(r, r, n));
+    const double den = bnorm > 0.0 ? bnorm : rn;
+    const double tol = eps * den;
+    int it = 0;
+    if (rn > tol) {
+        memcpy(F->b, r, sizeof(double) * (size_t)n);
+        mg_vcycle(L, 0, nl, w0, d0, wm, dc, wc, 8);
+        memcpy(p, F->x, sizeof(double) * (size_t)n);
+        double rz = dot(r, p, n);
+        while (it < maxiter) {
+            ++it;
+            mg_sweep(F, p, NULL, q, 0.0, 2);
+            const double alpha = rz / dot(p, q, n);
+            double rr = 0.0;
+#pragma omp parallel for reduction(+ : rr) schedule(static)
+            for (int64_t m = 0; m < n; ++m) { u[m] += alpha * p[m]; r[m] -= alpha * q[m]; rr += r[m] * r[m]; }
+            rn = sqrt(rr);
+            if (!(rn > tol)) break;
+            memcpy(F->b, r, sizeof(double) * (size_t)n);
+            mg_vcycle(L, 0, nl, w0, d0, wm, dc, wc, 8);
+            const double rzn = dot(r, F->x, n);
+            const double beta = rzn / rz;
+            rz = rzn;
+            const double* z = F->x;
+#pragma omp parallel for schedule(static)
+            for (int64_t m = 0; m < n; ++m) p[m] = z[m] + beta * p[m];
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < n; ++m) if (F->dg[m] > 0.0) x[m] = u[m];
+    if (relres) *relres = den > 0.0 ? rn / den : 0.0;
+    for (int l = 0; l < nl; ++l) mg_free(&L[l]);
+    free(bvec); free(r); free(p); free(q); free(u);
+    return it;
+}
+
+/* oo_tortuosity with the MG-PCG solve (same mask, flux and tau tail) */
+int oo_tortuosity_mg(const int32_t* phase, int nx, int ny, int nz, int32_t phase_id, int dir,
+                     double vlo, double vhi, double eps, int maxiter, int d0, int dc, double* out) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    const double dx[3] = {1.0, 1.0, 1.0};
+    uint8_t* mask = (uint8_t*)malloc((size_t)n);
+#ifdef _OPENMP
+    const double tm = omp_get_wtime();
+#endif
+    const int64_t na = oo_activity_mask(phase, phase_id, nx, ny, nz, dir, mask, 0);
+    const double avf = n > 0 ? (double)na / (double)n : 0.0;
+    for (int q = 0; q < 10; ++q) out[q] = 0.0;
+    out[2] = avf; out[7] = (double)na;
+    if (na == 0) { out[0] = NAN; free(mask); return 0; }
+    double* x = (double*)calloc((size_t)n, sizeof(double));
+    double relres = 0.0;
+#ifdef _OPENMP
+    const double t0 = omp_get_wtime();
+    out[9] = t0 - tm;                                                   /* mask seconds */
+#endif
+    const int it = oo_solve_mgpcg(mask, nx, ny, nz, dir, vlo, vhi, eps, maxiter, d0, dc, x, &relres);
+#ifdef _OPENMP
+    out[8] = omp_get_wtime() - t0;
+#endif
+    double fin, fout, deff;
+    oo_fluxes(x, mask, nx, ny, nz, dir, dx, &fin, &fout, NULL, NULL);
+    const int conv = isfinite(relres) && relres >= 0.0 && relres <= eps;
+    out[0] = oo_tau(fin, fout, avf, nx, ny, nz, dir, dx, vlo, vhi, conv, &deff);
+    out[1] = deff; out[3] = fin; out[4] = fout; out[5] = (double)it; out[6] = relres;
+    free(x); free(mask);
+    return 0;
+}

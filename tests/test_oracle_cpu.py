@@ -323,3 +323,23 @@ def test_effdiff_two_restatements_agree(oc, sample_phase):
     gold = json.load(open(os.path.join(GOLDEN, "effdiff_golden.json")))
     D, _ = oc.effdiff_deff_tensor(sample_phase, 1, eps=1e-11)
     assert np.abs(D - np.array(gold["phase1"]["deff"])).max() < 1e-8
+
+
+def test_mgpcg_port_agrees_with_jacobi_pcg_goldens():
+    """Third independent solve of the same systems: the CPU port of the GPU arm's MG-PCG (oracle/oi_oracle.c
+    oo_solve_mgpcg; also bench.py's CPU baseline) against the Jacobi-PCG goldens of the sphere packings
+    (tests/golden/packing_golden.json) -- integers exact, tau to 1e-7 (the goldens are converged to 1e-11, the
+    port stops at the reference's 1e-9)."""
+    import json
+    from oracle import oi_c
+    from openimpala_b200 import synth
+    gold = json.load(open(os.path.join(GOLDEN, "packing_golden.json")))
+    for case in gold["cases"][:2]:                       # 96^3, 128^3
+        ph = synth.sphere_packing(case["n"], 12345, 12, 0.60).astype(np.int32)
+        r = oi_c.tortuosity_mg(ph, 1, 2, -1.0, 1.0, eps=1e-9)
+        assert r["n_active"] == case["n_active"]
+        assert r["relres"] <= 1e-9 and r["iters"] <= 30
+        assert abs(r["tau"] - case["tau"]) <= 1e-7 * case["tau"], (r["tau"], case["tau"])
+    # analytic: open column, tau = (N - 1) / N
+    r = oi_c.tortuosity_mg(np.ones((16, 16, 16), dtype=np.int32), 1, 0, 0.0, 1.0, eps=1e-12)
+    assert abs(r["tau"] - 15.0 / 16.0) <= 1e-10
