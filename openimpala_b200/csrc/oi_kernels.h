@@ -26,6 +26,12 @@ struct L0Args {
     // All-null (the default) = no halo work in the kernel.  Ring kernels, prolongation.
     HaloIn hin;
     HaloOut hout;
+    // z-slabs, two sweeps per pass: the ring SMOOTH kernel run on the two boundary planes only (bnd_only: nothing
+    // is stored locally, the planes go to the neighbours through hout), and the planes received from them, which
+    // the pair kernel takes as the intermediate iterate at k = -1 / k = nz (nullptr: outside the box, zero)
+    int bnd_only;
+    const void* vb_lo;
+    const void* vb_hi;
 };
 
 long long l0_max_blocks(const Grid& g, int n_sm);
@@ -48,6 +54,8 @@ void l0_jacobi_first(const L0Args& a, cudaStream_t st);
 // two smoothing sweeps in one pass (oi_level0_pair.cu): out = S_w2(S_w1(u)); needs one z-slab,
 // a non-periodic box, nx % 4 == 0 and fp32 multigrid vectors
 bool pair_supported(const L0Args& a);
+// the same kernel on one z-slab of several (needs the neighbours' intermediate boundary planes, vb_lo / vb_hi)
+bool pair_supported_slab(const L0Args& a);
 void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant, cudaStream_t st);
 
 // ---------------------------------------------------------------- coarse levels

@@ -459,11 +459,17 @@ l0_pair512_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __rest
 // (ncu: sm__inst_issued 77-80 %, DRAM 33 %), so those instructions are what it pays for.
 // Trip kk = kb + s with kb = k0 - 1 + 6 t:  plane kk+d of the input lives in stage (s + d + 1) % 6,
 // v(kk) in intermediate stage s % 3, v(kk-2) in (s + 1) % 3, the refill plane kk+4 goes to (s + 5) % 6.
-template <bool DOT>
+// HALO (one z-slab of several): u carries the neighbours' boundary planes in its ghost planes, and the
+// intermediate iterate at k = -1 / k = nz -- the neighbours' own v(nz-1) / v(0), made by the boundary-plane
+// run of the ring kernel and stored into vb_lo / vb_hi -- is read instead of taken as zero.  The first and
+// last z-chunk are dispatched last, wait for those planes on the flag words of `hin`, store plane 0 / nz-1
+// of the result into the neighbours' ghost planes and publish `hout.seq`.
+template <bool DOT, bool HALO>
 __global__ void __launch_bounds__(512, 2)
 l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __restrict__ u,
                    const float* __restrict__ b, float* __restrict__ out, float w1, float w2, int zchunk,
-                   double* red_partials, unsigned int* red_counter, double* red_out) {
+                   double* red_partials, unsigned int* red_counter, double* red_out, HaloIn hin, HaloOut hout,
+                   const float* __restrict__ vb_lo, const float* __restrict__ vb_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* us = reinterpret_cast<float*>(smem_raw);            // [PR][UH][PW]
     float* bs = us + PR * U_ST;                                // [PR][VH][PW]
@@ -474,7 +480,22 @@ l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __res
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;                    // 32 pairs x 16 rows
     const int i0 = blockIdx.x * PTX, j0 = blockIdx.y * PTY;
-    const int k0 = blockIdx.z * zchunk, k1 = min(k0 + zchunk, g.nz);
+    int zc_idx = blockIdx.z;
+    if (HALO) {                                                 // interior chunks first, chunk 0 and the last one at the end
+        const int nzc = gridDim.z;
+        if (nzc > 2) zc_idx = ((int)blockIdx.z < nzc - 2) ? (int)blockIdx.z + 1 : ((int)blockIdx.z == nzc - 2 ? 0 : nzc - 1);
+    }
+    const int k0 = zc_idx * zchunk, k1 = min(k0 + zchunk, g.nz);
+    if (HALO) {
+        const bool wlo = hin.flag_lo && k0 == 0, whi = hin.flag_hi && k1 == g.nz;
+        if (wlo || whi) {
+            if (tid == 0) {
+                if (wlo) halo_spin(hin.flag_lo, hin.seq);
+                if (whi) halo_spin(hin.flag_hi, hin.seq);
+            }
+            __syncthreads();
+        }
+    }
     const float cx = (float)g.cx, cy = (float)g.cy, cz = (float)g.cz;
     const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
     if (tid < 64) {
@@ -556,12 +577,25 @@ l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __res
                     const float xw = Uc[u_off - 1], xe = Uc[u_off + 2];
                     oA = relax_pair(fA & 0xffu, fA >> 8, u_c, xw, xe, sS, nN, u_m, u_p, bA, w1, ncx, ncy, ncz, dtab2);
                 }
+                // the neighbours' intermediate plane stands in at k = -1 / k = nz (HALO); own values are loaded
+                // here, rim values below
+                const float* vbp = nullptr;
+                if (HALO && !plane_in) vbp = (kk < 0) ? vb_lo : vb_hi;
+                if (vbp && inb) oA = *reinterpret_cast<const float2*>(vbp + o_col);
                 *reinterpret_cast<float2*>(V + v_off) = oA;
                 if (rim_kind) {
                     const int vo = rim_vo, uo = rim_vo + PW;
                     if (!plane_in) {
-                        V[vo] = 0.f;
-                        if (rim_kind == 1) V[vo + 1] = 0.f;
+                        float r0 = 0.f, r1 = 0.f;
+                        if (vbp) {
+                            // stage position vo -> cell (i0 - 4 + column, j0 - 1 + row) of the plane
+                            const int rr = vo / PW, cc = vo - rr * PW;
+                            const int gi = i0 - 4 + cc, gj = j0 - 1 + rr;
+                            if (in_box(gi, gj)) r0 = vbp[(long long)gj * g.nx + gi];
+                            if (rim_kind == 1 && in_box(gi + 1, gj)) r1 = vbp[(long long)gj * g.nx + gi + 1];
+                        }
+                        V[vo] = r0;
+                        if (rim_kind == 1) V[vo + 1] = r1;
                     } else {
                         V[vo] = relax2(F[vo], Uc[uo], Uc[uo - 1], Uc[uo + 1], Uc[uo - PW], Uc[uo + PW], Um[uo], Up[uo],
                                        B[vo], w1, cx, cy, cz, dtab2);
@@ -580,7 +614,13 @@ l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __res
                 const float xw = Vc[v_off - 1], xe = Vc[v_off + 2];
                 const float2 o = relax_pair(f2 & 0xffu, f2 >> 8, v2, xw, xe, sS, nN, v3, v1, b2, w2, ncx, ncy, ncz, dtab2);
                 if (DOT) dot_acc += (double)b2.x * (double)o.x + (double)b2.y * (double)o.y;
-                if (inb && (f2 & 0x4040u)) *reinterpret_cast<float2*>(out_own + (long long)k * g.plane) = o;
+                if (inb && (f2 & 0x4040u)) {
+                    *reinterpret_cast<float2*>(out_own + (long long)k * g.plane) = o;
+                    if (HALO) {
+                        if (hout.dst_lo && k == 0) *reinterpret_cast<float2*>(static_cast<float*>(hout.dst_lo) + o_col) = o;
+                        if (hout.dst_hi && k == g.nz - 1) *reinterpret_cast<float2*>(static_cast<float*>(hout.dst_hi) + o_col) = o;
+                    }
+                }
             }
             u_m = u_c; u_c = u_p;
             v3 = v2; v2 = v1; v1 = oA;
@@ -592,6 +632,12 @@ l0_pair512u_kernel(Grid g, const uint8_t* __restrict__ flags, const float* __res
         }
     }
     cpa_wait<0>();
+
+    if (HALO) {
+        const unsigned int tiles = gridDim.x * gridDim.y;
+        if (hout.flag_lo && k0 == 0) halo_publish(hout.counter + 0, tiles, hout.flag_lo, nullptr, hout.seq);
+        if (hout.flag_hi && k1 == g.nz) halo_publish(hout.counter + 1, tiles, nullptr, hout.flag_hi, hout.seq);
+    }
 
     if (DOT) {
         double v[1] = {dot_acc};
@@ -608,6 +654,9 @@ size_t pair_smem_bytes() {
 bool pair_supported(const L0Args& a) {
     return sizeof(mg_t) == 4 && (a.g.nx & 3) == 0 && a.g.periodic == 0 && a.g.nz == a.g.nzg;
 }
+bool pair_supported_slab(const L0Args& a) {
+    return sizeof(mg_t) == 4 && (a.g.nx & 3) == 0 && a.g.periodic == 0 && a.g.nz >= 2;
+}
 
 // out = S_w2(S_w1(u)) ; dot: also red_out = b . out.  variant 1: 256 threads x 4 cells, 2: 512 x 2.
 void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant, cudaStream_t st) {
@@ -618,19 +667,29 @@ void l0_smooth_pair(const L0Args& a, double w1, double w2, bool dot, int variant
         cudaFuncSetAttribute(l0_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(l0_pair512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(l0_pair512u_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(l0_pair512u_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(l0_pair512u_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + PTX - 1) / PTX, (a.g.ny + PTY - 1) / PTY, (a.g.nz + zc - 1) / zc);
     const float* u = static_cast<const float*>(a.u);
     const float* b = static_cast<const float*>(a.b);
     float* out = static_cast<float*>(a.out);
-    if (variant == 3) {
-        if (dot) l0_pair512u_kernel<true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
-                                                                   a.red_partials, a.red_counter, a.red_out);
-        else l0_pair512u_kernel<false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
-                                                                a.red_partials, a.red_counter, a.red_out);
+    const bool halo = a.hin.flag_lo || a.hin.flag_hi || a.hout.flag_lo || a.hout.flag_hi || a.vb_lo || a.vb_hi;
+    const float* vlo = static_cast<const float*>(a.vb_lo);
+    const float* vhi = static_cast<const float*>(a.vb_hi);
+    if (halo) {          // one z-slab of several: always the unrolled 512-thread kernel
+        if (dot) l0_pair512u_kernel<true, true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                         a.red_partials, a.red_counter, a.red_out, a.hin, a.hout, vlo, vhi);
+        else l0_pair512u_kernel<false, true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                      a.red_partials, a.red_counter, a.red_out, a.hin, a.hout, vlo, vhi);
+    } else if (variant == 3) {
+        if (dot) l0_pair512u_kernel<true, false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                          a.red_partials, a.red_counter, a.red_out, a.hin, a.hout, nullptr, nullptr);
+        else l0_pair512u_kernel<false, false><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
+                                                                       a.red_partials, a.red_counter, a.red_out, a.hin, a.hout, nullptr, nullptr);
     } else if (variant == 2) {
         if (dot) l0_pair512_kernel<true><<<grid, 512, smem, st>>>(a.g, a.flags, u, b, out, (float)w1, (float)w2, zc,
                                                                   a.red_partials, a.red_counter, a.red_out);

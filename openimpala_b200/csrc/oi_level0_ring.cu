@@ -78,7 +78,7 @@ template <typename T, int MODE, bool DOT, bool HALO>
 __global__ void __launch_bounds__(256)
 l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ u,
                const T* __restrict__ b, T* __restrict__ out, T w, RingCoarse rc, int fz, int zchunk,
-               double* red_partials, unsigned int* red_counter, double* red_out, HaloIn hin, HaloOut hout) {
+               double* red_partials, unsigned int* red_counter, double* red_out, HaloIn hin, HaloOut hout, int bnd_only) {
     typedef Cfg<T> C;
     constexpr int CPT = C::CPT, TX = C::TX, TY = C::TY, PITCH = C::PITCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,8 +100,10 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
         const int nzc = gridDim.z;
         if (nzc > 2) zc_idx = ((int)blockIdx.z < nzc - 2) ? (int)blockIdx.z + 1 : ((int)blockIdx.z == nzc - 2 ? 0 : nzc - 1);
     }
-    const int k0 = zc_idx * zchunk;
-    const int k1 = min(k0 + zchunk, g.nz);
+    // bnd_only (HALO, MODE 1): two one-plane chunks, plane 0 and plane nz-1; nothing is stored locally
+    const bool bnd = HALO && MODE == 1 && bnd_only != 0;
+    const int k0 = bnd ? (blockIdx.z == 0 ? 0 : g.nz - 1) : zc_idx * zchunk;
+    const int k1 = bnd ? k0 + 1 : min(k0 + zchunk, g.nz);
     const T cx = (T)g.cx, cy = (T)g.cy, cz = (T)g.cz;
 
     if (HALO) {
@@ -247,7 +249,7 @@ l0_ring_kernel(Grid g, const uint8_t* __restrict__ flags, const T* __restrict__ 
                 // zero off the unknowns from allocation on): its sector is never written
                 constexpr unsigned int UNKS = (CPT == 2) ? 0x4040u : 0x40404040u;
                 if (inb && (fword & UNKS)) {
-                    *reinterpret_cast<Pack<T>*>(out_own) = o;
+                    if (!bnd) *reinterpret_cast<Pack<T>*>(out_own) = o;
                     if (HALO) {
                         if (push_lo && k == 0) *reinterpret_cast<Pack<T>*>(static_cast<T*>(hout.dst_lo) + col) = o;
                         if (push_hi && k == g.nz - 1) *reinterpret_cast<Pack<T>*>(static_cast<T*>(hout.dst_hi) + col) = o;
@@ -371,10 +373,12 @@ void launch_h(const L0Args& a, cudaStream_t st) {
         cudaFuncSetAttribute(l0_ring_kernel<T, MODE, DOT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int zc = pick_zchunk(a.g, a.n_sm);
     dim3 grid((a.g.nx + C::TX - 1) / C::TX, (a.g.ny + C::TY - 1) / C::TY, (a.g.nz + zc - 1) / zc);
+    const int bnd = (HALO && MODE == 1 && a.bnd_only && a.g.nz >= 2) ? 1 : 0;
+    if (bnd) grid.z = 2;
     RingCoarse rc{a.cnx, a.cny, a.g.z0 >> 1};
     l0_ring_kernel<T, MODE, DOT, HALO><<<grid, C::NT, smem, st>>>(
         a.g, a.flags, static_cast<const T*>(a.u), static_cast<const T*>(a.b), static_cast<T*>(a.out), (T)a.w, rc,
-        a.fz, zc, a.red_partials, a.red_counter, a.red_out, a.hin, a.hout);
+        a.fz, zc, a.red_partials, a.red_counter, a.red_out, a.hin, a.hout, bnd);
 }
 
 template <typename T, int MODE, bool DOT>

@@ -158,17 +158,20 @@ ccl_merge_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, int nz)
     }
 }
 
-// merge plane k with plane k-1 (one union per start of an overlap segment along x)
+// Merge one slice of the box with the slice before it along AXIS (1: row j of every plane with row j-1,
+// 2: plane k with plane k-1); one union per start of an overlap segment along x, one thread per cell.
+template <int AXIS>
 __global__ void __launch_bounds__(BT)
-ccl_merge_zplane_kernel(const uint8_t* __restrict__ ph, int* L, int nx, long long plane, int k) {
-    const long long stride = (long long)gridDim.x * BT;
-    const long long base = (long long)k * plane;
-    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < plane; t += stride) {
-        const long long idx = base + t;
-        if (!ph[idx] || !ph[idx - plane]) continue;
-        const bool left = (t % nx) > 0 && ph[idx - 1];
-        if (!(left && ph[idx - plane - 1])) uf_union(L, (int)idx, (int)(idx - plane));
-    }
+ccl_merge_slice_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, long long plane, long long count, int s) {
+    const long long t = (long long)blockIdx.x * BT + threadIdx.x;
+    if (t >= count) return;
+    const int i = (int)(t % nx);
+    long long idx, back;
+    if (AXIS == 2) { idx = (long long)s * plane + t; back = plane; }
+    else { idx = (t / nx) * plane + (long long)s * nx + i; back = nx; }
+    if (!ph[idx] || !ph[idx - back]) return;
+    if (i > 0 && ph[idx - 1] && ph[idx - back - 1]) return;          // not the start of the overlap segment
+    uf_union(L, (int)idx, (int)(idx - back));
 }
 
 __global__ void __launch_bounds__(BT)
@@ -289,6 +292,66 @@ build_flags_kernel(Grid g, const uint8_t* __restrict__ active, uint8_t* __restri
             }
         }
         flags[idx] = f;
+    }
+    c_in = warp_sum_ll(c_in);
+    c_out = warp_sum_ll(c_out);
+    if ((threadIdx.x & 31) == 0) {
+        if (c_in) atomicAdd(&counts[0], (unsigned long long)c_in);
+        if (c_out) atomicAdd(&counts[1], (unsigned long long)c_out);
+    }
+}
+
+// Same, four x-adjacent cells per thread (nx % 4 == 0): the active bytes of the own quad and of its four y / z
+// neighbour quads come as one 32-bit load each, the index split happens once per quad.
+__global__ void __launch_bounds__(BT)
+build_flags_vec4_kernel(Grid g, const uint8_t* __restrict__ active, uint8_t* __restrict__ flags, int dir,
+                        int n_dir, unsigned long long* counts) {
+    const long long nq = ((long long)g.nz * g.plane) >> 2;
+    const long long stride = (long long)gridDim.x * BT;
+    const int qx = g.nx >> 2;                          // quads per row
+    const bool cellp = g.diag_full > 0.0;
+    long long c_in = 0, c_out = 0;
+    for (long long q = (long long)blockIdx.x * BT + threadIdx.x; q < nq; q += stride) {
+        const long long idx = q << 2;
+        const unsigned int a = *reinterpret_cast<const unsigned int*>(active + idx);
+        unsigned int out = 0u;
+        if (a) {
+            const int i = (int)(q % qx) << 2;
+            const long long rowq = q / qx;
+            const int j = (int)(rowq % g.ny);
+            const int k = (int)(rowq / g.ny);
+            const long long row = idx - i, colk = idx - (long long)j * g.nx;
+            const int jm = wrap_lo(j, g.ny, g.periodic & PER_Y), jp = wrap_hi(j, g.ny, g.periodic & PER_Y);
+            const unsigned int ym = jm >= 0 ? *reinterpret_cast<const unsigned int*>(active + colk + (long long)jm * g.nx) : 0u;
+            const unsigned int yp = jp >= 0 ? *reinterpret_cast<const unsigned int*>(active + colk + (long long)jp * g.nx) : 0u;
+            const unsigned int zm = *reinterpret_cast<const unsigned int*>(active + idx - g.plane);   // ghost planes are valid
+            const unsigned int zp = *reinterpret_cast<const unsigned int*>(active + idx + g.plane);
+            const int iw = wrap_lo(i, g.nx, g.periodic & PER_X);
+            const int ie = (i + 4 < g.nx) ? i + 4 : ((g.periodic & PER_X) ? 0 : -1);
+            const unsigned int west = iw >= 0 ? active[row + iw] : 0u;
+            const unsigned int east = ie >= 0 ? active[row + ie] : 0u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (!((a >> (8 * c)) & 0xffu)) continue;
+                const int d = dir == 0 ? i + c : (dir == 1 ? j : g.z0 + k);
+                unsigned int f;
+                if (!cellp && d == 0) { f = F_DIR; ++c_in; }
+                else if (!cellp && d == n_dir - 1) { f = F_DIR; ++c_out; }
+                else {
+                    f = F_UNK;
+                    const unsigned int xm = c > 0 ? (a >> (8 * (c - 1))) & 0xffu : west;
+                    const unsigned int xp = c < 3 ? (a >> (8 * (c + 1))) & 0xffu : east;
+                    if (xm) f |= F_XM;
+                    if (xp) f |= F_XP;
+                    if ((ym >> (8 * c)) & 0xffu) f |= F_YM;
+                    if ((yp >> (8 * c)) & 0xffu) f |= F_YP;
+                    if ((zm >> (8 * c)) & 0xffu) f |= F_ZM;
+                    if ((zp >> (8 * c)) & 0xffu) f |= F_ZP;
+                }
+                out |= f << (8 * c);
+            }
+        }
+        *reinterpret_cast<unsigned int*>(flags + idx) = out;
     }
     c_in = warp_sum_ll(c_in);
     c_out = warp_sum_ll(c_out);
@@ -596,22 +659,29 @@ int ccl_label(const uint8_t* ph, int* L, int nx, int ny, int nz, int n_sm, cudaS
     // OI_CCL=0: every union (across y and across z) in one pass over the box.  At 1024^3 that pass costs
     // ~80 ms (ncu: profiles/r2_launches_1024.csv) although it moves little data: every plane hooks onto
     // every other at once, and finds walk parent chains that cross many planes before path halving has
-    // shortened them.  Default: merge inside the planes first (trees stay inside one plane), flatten, then
-    // merge plane k onto plane k-1 for k = 1, 2, ... in stream order -- when plane k is merged everything
-    // below is already resolved, so a find is two or three hops.  nz - 1 small launches instead of one big one.
+    // shortened them (the same happens inside a plane: one pass over all rows of all planes took 52 ms).
+    // Default: slice by slice in stream order -- row j of every plane onto row j-1 for j = 1, 2, ..., then plane
+    // k onto plane k-1 for k = 1, 2, ... -- so that when a slice is merged everything before it is already
+    // resolved and a find is two or three hops.  ny + nz - 2 small launches (one thread per cell of the slice)
+    // instead of one big one.
+    // Small boxes keep the single pass (its chains are short there, and a few hundred launches would cost more
+    // than they save); OI_CCL=1 forces the slices, OI_CCL=0 the single pass.
     const char* e = getenv("OI_CCL");
-    if (e && e[0] == '0') {
+    const bool slices = e ? (e[0] != '0') : (n >= (1LL << 25));
+    if (!slices) {
         ccl_merge_kernel<3><<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
         ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
         return 3;
     }
     const long long plane = (long long)nx * ny;
-    ccl_merge_kernel<1><<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, nx, ny, nz);
-    ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
+    // rows first: row j of every plane onto row j-1 (trees stay inside one plane and two rows deep), then planes
+    const long long rowcells = (long long)nx * nz;
+    for (int j = 1; j < ny; ++j)
+        ccl_merge_slice_kernel<1><<<(unsigned)((rowcells + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, rowcells, j);
     for (int k = 1; k < nz; ++k)
-        ccl_merge_zplane_kernel<<<nblocks(plane, n_sm), BT, 0, st>>>(ph, L, nx, plane, k);
+        ccl_merge_slice_kernel<2><<<(unsigned)((plane + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, plane, k);
     ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
-    return 3 + nz;
+    return 1 + ny + nz;
 }
 void ccl_mark_planes(const uint8_t* ph, const int* L, unsigned int* reach, int nx, int ny, int nz,
                      int dir, int lo_local, int hi_local, int n_sm, cudaStream_t st) {
@@ -637,7 +707,11 @@ void build_flags(const Grid& g, const uint8_t* active, uint8_t* flags, int dir,
                  unsigned long long* counts, cudaStream_t st) {
     const long long n = (long long)g.nz * g.plane;
     const int n_dir = (dir == 0) ? g.nx : (dir == 1 ? g.ny : g.nzg);
-    build_flags_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, active, flags, dir, n_dir, counts);
+    // (plane 0 of every field is 256-byte aligned, so with nx % 4 == 0 every quad is 4-byte aligned)
+    if ((g.nx & 3) == 0 && (reinterpret_cast<uintptr_t>(active) & 3) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0)
+        build_flags_vec4_kernel<<<nblocks(n >> 2, 148), BT, 0, st>>>(g, active, flags, dir, n_dir, counts);
+    else
+        build_flags_kernel<<<nblocks(n, 148), BT, 0, st>>>(g, active, flags, dir, n_dir, counts);
 }
 void fill_initial_guess(const Grid& g, const uint8_t* flags, double* x, int dir, int n_dir,
                         double vlo, double vhi, int mirror_quirk, cudaStream_t st) {

@@ -323,7 +323,12 @@ struct PeerHalo {
     int last_id = -1;                 // field of the most recent exchange (-1 after a collective)
     bool fuse = true;                 // OI_HALO_FUSE=0: always the explicit push kernel + stream wait
     bool inkernel_wait = true;        // OI_HALO_INKERNEL=0: fused pushes, but waits stay on the stream
-    long long fused_pushes = 0, inkernel_waits = 0, fences = 0;
+    long long fused_pushes = 0, inkernel_waits = 0, fences = 0, pair_passes = 0;
+    // two planes of multigrid vectors written by the neighbours: the intermediate iterate of a two-sweep pass at
+    // the plane below plane 0 (vb_lo) and above plane nz-1 (vb_hi); registered as a halo field of zero planes
+    // whose "plane 0" is vb_hi, so the generic ghost-plane addressing lands on them
+    oi::mg_t* vb_lo = nullptr;
+    oi::mg_t* vb_hi = nullptr;
 };
 
 typedef CUresult (*PFN_stream_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -745,6 +750,10 @@ void prof_report(oi_solver* S, int iterations) {
         if (!found) acc.emplace_back(S->prof_marks[i].first, (double)ms);
     }
     std::fprintf(stderr, "[oi profile] rank %d: %d iterations, %.3f ms marked\n", S->rank, iterations, total);
+    if (S->n_ranks > 1)
+        std::fprintf(stderr, "[oi profile] rank %d   halo so far: %lld exchanges, %lld fused pushes, %lld in-kernel waits, "
+                             "%lld fences, %lld two-sweep passes on slabs\n", S->rank, S->peer.exchanges, S->peer.fused_pushes,
+                     S->peer.inkernel_waits, S->peer.fences, S->peer.pair_passes);
     for (auto& a : acc)
         std::fprintf(stderr, "[oi profile] rank %d   %-22s %9.3f ms  %5.1f%%  %8.3f ms/iter\n", S->rank,
                      a.first.c_str(), a.second, 100.0 * a.second / total, a.second / std::max(1, iterations));
@@ -924,6 +933,7 @@ bool peer_setup(oi_solver* S) {
     auto add = [&](size_t b) { need += b + 256; };
     add(Field<double>::bytes_needed(g.plane, g.nz)); add(Field<double>::bytes_needed(g.plane, g.nz));
     add(Field<mg_t>::bytes_needed(g.plane, g.nz)); add(Field<mg_t>::bytes_needed(g.plane, g.nz));
+    add(2 * (size_t)g.plane * sizeof(mg_t));
     if (mg) for (HostLevel& h : S->levels) {
         if (h.replicated) continue;        // no halo traffic on a level every rank holds whole
         add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz)); add(Field<mg_t>::bytes_needed(h.L.plane, h.L.nz));
@@ -949,6 +959,9 @@ bool peer_setup(oi_solver* S) {
         S->p.alloc(g.plane, g.nz, S->st, &P.arena);  reg((char*)S->p.p, g.plane * sizeof(double), g.nz);
         S->za.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->za.p, g.plane * sizeof(mg_t), g.nz);
         S->zb.alloc(g.plane, g.nz, S->st, &P.arena); reg((char*)S->zb.p, g.plane * sizeof(mg_t), g.nz);
+        P.vb_lo = static_cast<mg_t*>(P.arena.take(2 * (size_t)g.plane * sizeof(mg_t)));
+        P.vb_hi = P.vb_lo + g.plane;
+        reg((char*)P.vb_hi, g.plane * sizeof(mg_t), 0);
         if (mg) for (HostLevel& h : S->levels) {
             if (h.replicated) continue;
             h.x.alloc(h.L.plane, h.L.nz, S->st, &P.arena); reg((char*)h.x.p, h.L.plane * sizeof(mg_t), h.L.nz);
@@ -1232,12 +1245,38 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
     const char* pair_env = getenv("OI_PAIR");
     const int pair_variant = (pair_env && pair_env[0] >= '0' && pair_env[0] <= '3') ? pair_env[0] - '0' : 3;
     const bool no_pair = pair_variant == 0;
-    bool use_pair = false, ring1 = false;
+    bool use_pair = false, ring1 = false, pair_slab = false;
     {
         L0Args a = l0args(S, cur, rhs, oth, 0.0, nullptr);
         ring1 = variant == 0 && oi::ring_supported(a, 1);
         use_pair = !no_pair && variant == 0 && S->n_ranks == 1 && oi::pair_supported(a) && ring1;
+        // z-slabs: the same kernel, fed with the neighbours' intermediate boundary planes (peer halo only;
+        // OI_PAIR_SLAB=0 turns it off)
+        const char* ps = getenv("OI_PAIR_SLAB");
+        pair_slab = !no_pair && variant == 0 && S->n_ranks > 1 && S->peer.on && S->peer.fuse && S->peer.vb_lo &&
+                    !(ps && ps[0] == '0') && oi::pair_supported_slab(a) && ring1;
+        if (pair_slab) use_pair = true;
     }
+    // Two sweeps cur -> oth in one pass.  One slab: the pair kernel as is.  z-slabs: first the ring kernel runs the
+    // first sweep on the two boundary planes only and stores them into the neighbours' vb planes, then the pair
+    // kernel takes those planes as the intermediate iterate outside its slab.
+    auto pair_pass = [&](L0Args& a, double wa, double wb, bool dot, bool consumed) {
+        if (pair_slab) {
+            const mg_t* vlo = (S->rank > 0) ? S->peer.vb_lo : nullptr;
+            const mg_t* vhi = (S->rank < S->n_ranks - 1) ? S->peer.vb_hi : nullptr;
+            L0Args e = l0args(S, cur, rhs, oth, wa, nullptr);
+            e.bnd_only = 1;
+            halo0(S, cur, &e.hin);
+            const bool ok = peer_prepare_push(S, S->peer.vb_hi, (size_t)S->g.plane * sizeof(mg_t), 0, &e.hout);
+            if (!ok) throw OiError(OI_ERR_INVALID, "pair pass on z-slabs: the vb planes are not registered");
+            oi::l0_smooth(e, false, false, variant, S->st); S->launches++;
+            halo_consume(S, S->peer.vb_hi, (size_t)S->g.plane * sizeof(mg_t), 0, &a.hin);
+            a.vb_lo = vlo; a.vb_hi = vhi;
+            if (!(consumed && push0(S, oth, &a.hout))) peer_invalidate(S, oth);
+            S->peer.pair_passes++;
+        }
+        oi::l0_smooth_pair(a, wa, wb, dot, pair_variant, S->st); S->launches++;
+    };
     // One single sweep cur -> oth.  z-slabs: the ghost planes of cur come from its producer's push (the
     // boundary CTAs wait inside the kernel) and, when somebody will read oth's ghost planes (`consumed`),
     // this kernel stores oth's boundary planes into the neighbours itself.
@@ -1251,7 +1290,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         L0Args a = l0args(S, cur, rhs, oth, w[s], dot_out);
         if (use_pair && s + 1 < deg) {
             const bool dot = (!have_coarse && s + 1 == deg - 1 && dot_out);
-            oi::l0_smooth_pair(a, w[s], w[s + 1], dot, pair_variant, S->st); S->launches++;
+            pair_pass(a, w[s], w[s + 1], dot, have_coarse || s + 2 < deg);
             s += 2;
         } else {
             const bool dot = (!have_coarse && s == deg - 1 && dot_out);
@@ -1299,7 +1338,7 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
             }
             if (use_pair && !addc && s + 1 < deg) {
                 const bool dot = (s + 1 == deg - 1) && dot_out;
-                oi::l0_smooth_pair(a, w[deg - 1 - s], w[deg - 2 - s], dot, pair_variant, S->st); S->launches++;
+                pair_pass(a, w[deg - 1 - s], w[deg - 2 - s], dot, s + 2 < deg);
                 s += 2;
             } else {
                 const bool dot = (s == deg - 1) && dot_out;
@@ -1614,6 +1653,8 @@ void zero_mg_vectors(oi_solver* S) {
     CUDA_CHECK(cudaMemsetAsync(S->r32.base, 0, S->r32.count * sizeof(mg_t), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->za.base, 0, S->za.count * sizeof(mg_t), S->st));
     CUDA_CHECK(cudaMemsetAsync(S->zb.base, 0, S->zb.count * sizeof(mg_t), S->st));
+    if (S->peer.on && S->peer.vb_lo)
+        CUDA_CHECK(cudaMemsetAsync(S->peer.vb_lo, 0, 2 * (size_t)S->g.plane * sizeof(mg_t), S->st));
 }
 
 // ------------------------------------------------------------------ mask
@@ -2043,7 +2084,11 @@ int oi_create(oi_solver** out, const oi_params* p) {
         // profiles/r2_degree_sweep.md
         const int deg = p->mg_degree > 0 ? p->mg_degree : 5;
         OI_REQUIRE(deg <= 16, "mg_degree too large");
-        static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
+        // lower end of the Chebyshev interval as a fraction of the upper end, by degree.  Round 2 re-tuned the
+        // entries for degree >= 4 on the GPU (profiles/r2_degree_sweep.md): 0.12 -> 0.05 at degree 5 and 0.08 -> 0.05
+        // at degree 8 take the 1024^3 packing from 18 to 17 and the 512^3 one from 17 to 15 iterations; 0.03 - 0.10
+        // all give the same count at 1024^3.
+        static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.10, 0.05, 0.05, 0.05, 0.05};
         double lo0 = deg <= 8 ? lo_tab[deg] : 0.07;
         if (const char* e = getenv("OI_MG_LO0")) { const double v = std::atof(e); if (v > 0.0 && v < 1.0) lo0 = v; }   // experiments
         S->w_smooth = cheb_weights(deg, lo0);

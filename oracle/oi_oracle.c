@@ -628,7 +628,7 @@ int oo_solve_mgpcg(const uint8_t* mask, int nx, int ny, int nz, int dir, double 
     if (dc <= 0) dc = 8;
     if (d0 > 16) d0 = 16;
     if (dc > 16) dc = 16;
-    static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.15, 0.12, 0.1, 0.09, 0.08};
+    static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.10, 0.05, 0.05, 0.05, 0.05};     /* as oi_solver.cu */
     double w0[16], wm[16], wc[8];
     mg_cheb(d0, d0 <= 8 ? lo_tab[d0] : 0.07, w0);
     mg_cheb(dc, dc <= 8 ? lo_tab[dc] : 0.07, wm);

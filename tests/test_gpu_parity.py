@@ -95,6 +95,26 @@ def test_mask_rows_and_operator(capi, shape, seed, por, direction):
             np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("shape,seed,por", [((13, 17, 20), 3, 0.55), ((40, 40, 40), 7, 0.45), ((7, 130, 70), 8, 0.5),
+                                            ((64, 48, 96), 9, 0.42)])
+@pytest.mark.parametrize("direction", [0, 1, 2])
+@pytest.mark.parametrize("ccl", ["0", "1"])
+def test_mask_both_labelling_schedules(capi, shape, seed, por, direction, ccl, monkeypatch):
+    """The percolation labelling merges either in one pass over the box (OI_CCL=0, the default below 2^25 cells)
+    or slice by slice (OI_CCL=1, the default above): union-find results do not depend on the order of the
+    unions, so both must give the oracle's mask bit for bit (near-threshold porosities: many components)."""
+    from oracle import oi_numpy as o
+    monkeypatch.setenv("OI_CCL", ccl)
+    ph = _blobs(shape, seed, por)
+    for phase_id in (1, 0):
+        mask = o.activity_mask(ph, phase_id, direction)
+        with capi.Solver(shape, direction, phase_id, vlo=-1.0, vhi=1.0) as s:
+            s.set_phase(ph)
+            assert s.build_mask() == int(mask.sum())
+            if mask.any():
+                assert np.array_equal(s.mask().astype(bool), mask)
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("shape,seed,por", CASES[:5])
 def test_tau_matches_oracle(capi, shape, seed, por, variant):
