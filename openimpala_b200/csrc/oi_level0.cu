@@ -280,8 +280,10 @@ int pick_zchunk(const Grid& g, int n_sm) {
     long long chunks = (target + tiles - 1) / tiles;
     if (chunks < 1) chunks = 1;
     int zc = (int)((g.nz + chunks - 1) / chunks);
+    int cap = 64;
+    if (const char* e = getenv("OI_ZCHUNK")) { const int v = atoi(e); if (v >= 8 && v <= 1024) cap = v; }   // experiments
     if (zc < 16) zc = 16;
-    if (zc > 64) zc = 64;
+    if (zc > cap) zc = cap;
     zc = (zc + 1) & ~1;                            // even: restriction pairs stay in one chunk
     return zc;
 }

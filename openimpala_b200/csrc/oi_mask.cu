@@ -158,17 +158,22 @@ ccl_merge_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, int nz)
     }
 }
 
-// Merge one slice of the box with the slice before it along AXIS (1: row j of every plane with row j-1,
-// 2: plane k with plane k-1); one union per start of an overlap segment along x, one thread per cell.
+// Merge slices of the box with the slice before them along AXIS (1: row j of every plane with row j-1,
+// 2: plane k with plane k-1) for every slice s = span, 3 span, 5 span, ... (< extent): the boundaries between
+// groups of `span` slices that earlier launches have already merged internally.  One union per start of an
+// overlap segment along x, one thread per cell.
 template <int AXIS>
 __global__ void __launch_bounds__(BT)
-ccl_merge_slice_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, long long plane, long long count, int s) {
+ccl_merge_slices_kernel(const uint8_t* __restrict__ ph, int* L, int nx, int ny, long long plane, long long slice_cells,
+                        long long total, int span) {
     const long long t = (long long)blockIdx.x * BT + threadIdx.x;
-    if (t >= count) return;
-    const int i = (int)(t % nx);
+    if (t >= total) return;
+    const long long w = t % slice_cells;
+    const int s = span + (int)(t / slice_cells) * 2 * span;
+    const int i = (int)(w % nx);
     long long idx, back;
-    if (AXIS == 2) { idx = (long long)s * plane + t; back = plane; }
-    else { idx = (t / nx) * plane + (long long)s * nx + i; back = nx; }
+    if (AXIS == 2) { idx = (long long)s * plane + w; back = plane; }
+    else { idx = (w / nx) * plane + (long long)s * nx + i; back = nx; }
     if (!ph[idx] || !ph[idx - back]) return;
     if (i > 0 && ph[idx - 1] && ph[idx - back - 1]) return;          // not the start of the overlap segment
     uf_union(L, (int)idx, (int)(idx - back));
@@ -660,10 +665,11 @@ int ccl_label(const uint8_t* ph, int* L, int nx, int ny, int nz, int n_sm, cudaS
     // ~80 ms (ncu: profiles/r2_launches_1024.csv) although it moves little data: every plane hooks onto
     // every other at once, and finds walk parent chains that cross many planes before path halving has
     // shortened them (the same happens inside a plane: one pass over all rows of all planes took 52 ms).
-    // Default: slice by slice in stream order -- row j of every plane onto row j-1 for j = 1, 2, ..., then plane
-    // k onto plane k-1 for k = 1, 2, ... -- so that when a slice is merged everything before it is already
-    // resolved and a find is two or three hops.  ny + nz - 2 small launches (one thread per cell of the slice)
-    // instead of one big one.
+    // Default: divide and conquer -- first the boundaries between single rows (rows 1, 3, 5, ... of every plane
+    // onto the row before), then between pairs of rows (2, 6, 10, ...), then groups of four, ... and the same along
+    // z -- so that both sides of a boundary are already resolved when it is merged and a find is two or three
+    // hops.  log2(ny) + log2(nz) launches, one thread per cell of the merged slices.  (Round 2 first tried one
+    // launch per slice in stream order: 46 ms at 1024^3, launch bound at 20 us per slice.)
     // Small boxes keep the single pass (its chains are short there, and a few hundred launches would cost more
     // than they save); OI_CCL=1 forces the slices, OI_CCL=0 the single pass.
     const char* e = getenv("OI_CCL");
@@ -674,14 +680,23 @@ int ccl_label(const uint8_t* ph, int* L, int nx, int ny, int nz, int n_sm, cudaS
         return 3;
     }
     const long long plane = (long long)nx * ny;
-    // rows first: row j of every plane onto row j-1 (trees stay inside one plane and two rows deep), then planes
+    int launches = 2;
+    // rows first (trees stay inside one plane), then planes; span = 1, 2, 4, ...: at every launch the groups of
+    // `span` slices on either side of a merged boundary are already resolved, so parent chains grow by one hop per
+    // launch at most and path halving keeps a find at two or three hops
     const long long rowcells = (long long)nx * nz;
-    for (int j = 1; j < ny; ++j)
-        ccl_merge_slice_kernel<1><<<(unsigned)((rowcells + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, rowcells, j);
-    for (int k = 1; k < nz; ++k)
-        ccl_merge_slice_kernel<2><<<(unsigned)((plane + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, plane, k);
+    for (int span = 1; span < ny; span *= 2, ++launches) {
+        const long long nb = (ny - span + 2 * span - 1) / (2 * span);           // slices span, 3 span, ... < ny
+        const long long total = nb * rowcells;
+        ccl_merge_slices_kernel<1><<<(unsigned)((total + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, rowcells, total, span);
+    }
+    for (int span = 1; span < nz; span *= 2, ++launches) {
+        const long long nb = (nz - span + 2 * span - 1) / (2 * span);
+        const long long total = nb * plane;
+        ccl_merge_slices_kernel<2><<<(unsigned)((total + BT - 1) / BT), BT, 0, st>>>(ph, L, nx, ny, plane, plane, total, span);
+    }
     ccl_flatten_kernel<<<nblocks(n, n_sm), BT, 0, st>>>(ph, L, n);
-    return 1 + ny + nz;
+    return launches;
 }
 void ccl_mark_planes(const uint8_t* ph, const int* L, unsigned int* reach, int nx, int ny, int nz,
                      int dir, int lo_local, int hi_local, int n_sm, cudaStream_t st) {

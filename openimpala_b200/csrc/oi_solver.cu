@@ -416,6 +416,7 @@ struct oi_solver {
     // multigrid
     std::vector<HostLevel> levels;     // levels[0] is MG level 1
     std::vector<double> w_smooth, w_coarse;
+    std::vector<double> w_l1;          // MG level 1 only, when OI_MG_DEG_L1 is set (experiments); else empty
     std::vector<double> w_mid;         // smoothing weights of MG levels >= 1 that have a coarser level below (OI_MG_DEG_COARSE; default: w_smooth)
     int w_from = 0;                    // OI_MG_W_FROM=L: MG levels >= L are visited twice per visit of their parent (W-cycle); 0 = V-cycle
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
@@ -1154,7 +1155,7 @@ void coarse_cycle(oi_solver* S, size_t l) {
         return;
     }
     const bool last = (l + 1 == S->levels.size());
-    const std::vector<double>& w = last ? S->w_coarse : S->w_mid;
+    const std::vector<double>& w = last ? S->w_coarse : ((l == 0 && !S->w_l1.empty()) ? S->w_l1 : S->w_mid);
     const int deg = (int)w.size();
     mg_t* cur = L.t;
     mg_t* oth = L.x;
@@ -1250,11 +1251,13 @@ void apply_precond(oi_solver* S, double* dot_out, bool first_done = false) {
         L0Args a = l0args(S, cur, rhs, oth, 0.0, nullptr);
         ring1 = variant == 0 && oi::ring_supported(a, 1);
         use_pair = !no_pair && variant == 0 && S->n_ranks == 1 && oi::pair_supported(a) && ring1;
-        // z-slabs: the same kernel, fed with the neighbours' intermediate boundary planes (peer halo only;
-        // OI_PAIR_SLAB=0 turns it off)
+        // z-slabs: the same kernel, fed with the neighbours' intermediate boundary planes (peer halo only).
+        // Opt-in (OI_PAIR_SLAB=1): measured at 1024^3 it is no faster than single sweeps on slabs -- 28.42 vs 28.49
+        // ms per iteration on 2 GPUs, 8.79 vs 8.67 on 8 (profiles/r2_multi_gpu.md): the boundary pre-sweep and
+        // its extra exchange per pass cost what the saved bytes give on slabs this thin.
         const char* ps = getenv("OI_PAIR_SLAB");
         pair_slab = !no_pair && variant == 0 && S->n_ranks > 1 && S->peer.on && S->peer.fuse && S->peer.vb_lo &&
-                    !(ps && ps[0] == '0') && oi::pair_supported_slab(a) && ring1;
+                    (ps && ps[0] == '1') && oi::pair_supported_slab(a) && ring1;
         if (pair_slab) use_pair = true;
     }
     // Two sweeps cur -> oth in one pass.  One slab: the pair kernel as is.  z-slabs: first the ring kernel runs the
@@ -2103,6 +2106,10 @@ int oi_create(oi_solver** out, const oi_params* p) {
         if (const char* e = getenv("OI_MG_LOC")) { const double v = std::atof(e); if (v > 0.0 && v < 1.0) loc = v; }   // experiments
         S->w_mid = cheb_weights(dc, loc);
         if (const char* e = getenv("OI_MG_W_FROM")) S->w_from = std::max(0, std::atoi(e));
+        if (const char* e = getenv("OI_MG_DEG_L1")) {
+            const int d1 = std::atoi(e);
+            if (d1 >= 1 && d1 <= 16) S->w_l1 = cheb_weights(d1, d1 <= 8 ? lo_tab[d1] : 0.05);
+        }
         CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
         CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));
         long long nb = std::max<long long>(oi::l0_max_blocks(g, S->n_sm), oi::vec_max_blocks(S->n_sm));

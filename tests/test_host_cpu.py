@@ -347,3 +347,22 @@ def test_amrex_shim_bulk_routines(tmp_path):
                     os.path.join(ROOT, "tests", "cpu_emul", "shim_check.cpp"), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_slab_rule_equals_python_slab_partition(tmp_path):
+    """The C++ stand-in's ParallelDescriptor::slab (which z-slab a rank of `Diffusion b200.ranks=N` owns) and
+    capi.slab_partition (bench.py, the Python classes) must cut the box the same way: multigrid aggregates never
+    straddle ranks only if both sides align the slab boundaries identically."""
+    import subprocess
+    from openimpala_b200 import capi
+    src = tmp_path / "slab.cpp"
+    src.write_text('#include <AMReX.H>\n#include <cstdio>\n#include <cstdlib>\n'
+                   'int main(int c, char** v) { int nz = atoi(v[1]), n = atoi(v[2]);\n'
+                   '  for (int r = 0; r < n; ++r) { int z0, nzl; amrex::ParallelDescriptor::slab(nz, n, r, z0, nzl); printf("%d %d\\n", z0, nzl); } }\n')
+    exe = tmp_path / "slab"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "openimpala_b200", "host", "amrex_shim"),
+                    "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    for nz, n in [(100, 2), (100, 4), (1024, 8), (1024, 2), (1280, 2), (1536, 4), (2048, 8), (64, 8), (97, 3), (512, 4), (130, 5)]:
+        out = subprocess.run([str(exe), str(nz), str(n)], capture_output=True, text=True, check=True).stdout.split()
+        got = [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(n)]
+        assert got == capi.slab_partition(nz, n), (nz, n, got)

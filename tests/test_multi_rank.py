@@ -54,6 +54,20 @@ def test_slab_logic_world2_gloo():
 
 
 @pytest.mark.gpu
+def test_two_sweep_passes_on_slabs():
+    """OI_PAIR_SLAB=1: the pair kernel on z-slabs, fed by the boundary pre-sweep through the neighbours' vb planes
+    (opt-in: no faster than single sweeps on thin slabs) -- the same parity worker must pass on 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(ROOT, "tests", "multi_gpu_worker.py")],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500, env={**os.environ, "OI_PAIR_SLAB": "1"})
+    assert r.returncode == 0 and "MULTI_GPU_PARITY PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_parity(world):
     """Distributed result == single-GPU result (integers exact, tau 1e-8), peer halo and NCCL halo, the cell
