@@ -247,6 +247,135 @@ coarse_stencil_vec4_kernel(CoarseLevel L, const float* __restrict__ x, const flo
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Two smoothing sweeps of a stored-coefficient level in one pass (the level-1 counterpart of
+// oi_level0_pair.cu):  v = x + w1 (b - A x)/d ,  out = v + w2 (b - A v)/d.
+// Level 1 is 1/8 of the cells but, with degree 8 per leg, a fifth of a PCG iteration; a sweep moves
+// x 4 + b 4 + four half coefficients 8 + out 4 = 20 B per cell, so two sweeps per pass halve that.
+// A CTA owns a 64 x 16 tile and marches along z.  Per plane kk it
+//   A) forms v(kk) on its tile (4 cells per thread, operands straight from global memory / L1 as in the
+//      single-sweep kernel, own z column in registers) and on the one-cell rim around it (164 cells, one per
+//      thread of the first 164), and keeps the last three planes of v in shared memory;
+//   B) forms out(kk-1) from v(kk-2 .. kk): own column from registers, x / y neighbours from shared memory,
+//      coefficients of plane kk-1 re-read (L1 hits: the same thread loaded them one trip earlier).
+// One CTA barrier per plane.  Single z-slab (or a level every rank holds whole), non-periodic box,
+// nx % 4 == 0, fp32 vectors, half coefficient copies present.
+constexpr int CPX = 64, CPY = 16, CPW = CPX + 8, CVH = CPY + 2;     // tile, smem pitch [4 | 64 | 4], rows with rim
+
+// A x at one cell from its seven values and the couplings (same expression order as coarse_stencil_kernel)
+__device__ __forceinline__ float coarse_ax(float d, float c, float cxp, float xe, float cxw, float xw, float cyp, float yn,
+                                           float cym, float ys, float czp, float zu, float czm, float zd) {
+    return d * c - cxp * xe - cxw * xw - cyp * yn - cym * ys - czp * zu - czm * zd;
+}
+
+__global__ void __launch_bounds__(256)
+coarse_pair_kernel(CoarseLevel L, const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ out,
+                   float w1, float w2, int zchunk) {
+    __shared__ __align__(16) float vs[3][CVH][CPW];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * CPX, j0 = blockIdx.y * CPY;
+    const int i = i0 + (tid & 15) * 4, j = j0 + (tid >> 4);
+    const int k0 = blockIdx.z * zchunk, k1 = min(k0 + zchunk, L.nz);
+    const bool inb = i < L.nx && j < L.ny;
+    const long long col = inb ? (long long)j * L.nx + i : 0;
+    const int vrow = (tid >> 4) + 1, vcol = 4 + (tid & 15) * 4;
+    // rim duty: rows j0-1 and j0+16 (2 x 64 cells), then columns i0-1 and i0+64 (2 x 18 cells)
+    int ri = 0, rj = 0, rrow = 0, rcol = 0;
+    const bool rim = tid < 2 * CPX + 2 * CVH;
+    if (tid < 2 * CPX) { rrow = (tid >= CPX) ? CVH - 1 : 0; rcol = 4 + (tid % CPX); }
+    else if (rim) { const int t = tid - 2 * CPX; rrow = t % CVH; rcol = (t >= CVH) ? 4 + CPX : 3; }
+    ri = i0 - 4 + rcol; rj = j0 - 1 + rrow;
+    const bool rin = rim && ri >= 0 && ri < L.nx && rj >= 0 && rj < L.ny;
+    const long long rcolg = rin ? (long long)rj * L.nx + ri : 0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // v at one cell of plane k from global memory (scalar path, for the rim)
+    auto v_cell = [&](long long idx, int ci, int cj) -> float {
+        const float d = ld1h(L.hd + idx);
+        if (!(d > 0.f)) return 0.f;
+        const float c = x[idx];
+        const float xe = (ci + 1 < L.nx) ? x[idx + 1] : 0.f, xw = (ci > 0) ? x[idx - 1] : 0.f;
+        const float yn = (cj + 1 < L.ny) ? x[idx + L.nx] : 0.f, ys = (cj > 0) ? x[idx - L.nx] : 0.f;
+        const float cxw = (ci > 0) ? ld1h(L.hx + idx - 1) : 0.f, cym = (cj > 0) ? ld1h(L.hy + idx - L.nx) : 0.f;
+        const float ax = coarse_ax(d, c, ld1h(L.hx + idx), xe, cxw, xw, ld1h(L.hy + idx), yn, cym, ys, ld1h(L.hz + idx),
+                                   x[idx + L.plane], ld1h(L.hz + idx - L.plane), x[idx - L.plane]);
+        return c + w1 * (b[idx] - ax) / d;
+    };
+
+    float4 x_m = zero4, x_c = zero4, v3 = zero4, v2 = zero4;
+    if (inb) {
+        x_m = ld4(x + (long long)(k0 - 2) * L.plane + col + (k0 - 2 < -1 ? L.plane : 0));   // plane k0-2 (or the ghost plane again: unused)
+        x_c = ld4(x + (long long)(k0 - 1) * L.plane + col);
+    }
+    for (int kk = k0 - 1; kk <= k1; ++kk) {
+        __syncthreads();                       // v(kk-1) complete; the slot of v(kk-3) is free
+        float (*V)[CPW] = vs[((kk % 3) + 3) % 3];
+        const bool plane_in = kk >= 0 && kk < L.nz;
+        float4 x_p = zero4, vA = zero4;
+        if (inb && kk + 1 <= L.nz) x_p = ld4(x + (long long)(kk + 1) * L.plane + col);
+        // ---- A: v(kk) on the tile (own four cells) ...
+        if (plane_in && inb) {
+            const long long idx = (long long)kk * L.plane + col;
+            const float4 d = ld4h(L.hd + idx);
+            if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
+                const float4 cxp = ld4h(L.hx + idx), cyp = ld4h(L.hy + idx), czp = ld4h(L.hz + idx);
+                const float4 czm = ld4h(L.hz + idx - L.plane);
+                const float cxw = (i > 0) ? ld1h(L.hx + idx - 1) : 0.f;
+                const float xw = (i > 0) ? x[idx - 1] : 0.f;
+                const float xe = (i + 4 < L.nx) ? x[idx + 4] : 0.f;
+                const float4 cym = (j > 0) ? ld4h(L.hy + idx - L.nx) : zero4;
+                const float4 ys = (j > 0) ? ld4(x + idx - L.nx) : zero4;
+                const float4 yn = (j + 1 < L.ny) ? ld4(x + idx + L.nx) : zero4;
+                const float4 bb = ld4(b + idx);
+                const float4 c = x_c;
+                const float ax0 = coarse_ax(d.x, c.x, cxp.x, c.y, cxw, xw, cyp.x, yn.x, cym.x, ys.x, czp.x, x_p.x, czm.x, x_m.x);
+                const float ax1 = coarse_ax(d.y, c.y, cxp.y, c.z, cxp.x, c.x, cyp.y, yn.y, cym.y, ys.y, czp.y, x_p.y, czm.y, x_m.y);
+                const float ax2 = coarse_ax(d.z, c.z, cxp.z, c.w, cxp.y, c.y, cyp.z, yn.z, cym.z, ys.z, czp.z, x_p.z, czm.z, x_m.z);
+                const float ax3 = coarse_ax(d.w, c.w, cxp.w, xe, cxp.z, c.z, cyp.w, yn.w, cym.w, ys.w, czp.w, x_p.w, czm.w, x_m.w);
+                vA.x = d.x > 0.f ? c.x + w1 * (bb.x - ax0) / d.x : 0.f;
+                vA.y = d.y > 0.f ? c.y + w1 * (bb.y - ax1) / d.y : 0.f;
+                vA.z = d.z > 0.f ? c.z + w1 * (bb.z - ax2) / d.z : 0.f;
+                vA.w = d.w > 0.f ? c.w + w1 * (bb.w - ax3) / d.w : 0.f;
+            }
+        }
+        *reinterpret_cast<float4*>(&V[vrow][vcol]) = vA;
+        // ... and on the rim
+        if (rim) V[rrow][rcol] = (plane_in && rin) ? v_cell((long long)kk * L.plane + rcolg, ri, rj) : 0.f;
+
+        // ---- B: out(kk-1) from v(kk-2), v(kk-1) (shared memory: written one trip ago), v(kk) = vA
+        const int k = kk - 1;
+        if (k >= k0 && k < k1 && inb) {
+            const float (*Vc)[CPW] = vs[((k % 3) + 3) % 3];
+            const long long idx = (long long)k * L.plane + col;
+            const float4 d = ld4h(L.hd + idx);
+            float4 o = zero4;
+            if (d.x > 0.f || d.y > 0.f || d.z > 0.f || d.w > 0.f) {
+                const float4 cxp = ld4h(L.hx + idx), cyp = ld4h(L.hy + idx), czp = ld4h(L.hz + idx);
+                const float4 czm = ld4h(L.hz + idx - L.plane);
+                const float cxw = (i > 0) ? ld1h(L.hx + idx - 1) : 0.f;
+                const float4 cym = (j > 0) ? ld4h(L.hy + idx - L.nx) : zero4;
+                const float4 bb = ld4(b + idx);
+                const float4 c = v2;
+                const float xw = Vc[vrow][vcol - 1], xe = Vc[vrow][vcol + 4];
+                const float4 ys = *reinterpret_cast<const float4*>(&Vc[vrow - 1][vcol]);
+                const float4 yn = *reinterpret_cast<const float4*>(&Vc[vrow + 1][vcol]);
+                const float ax0 = coarse_ax(d.x, c.x, cxp.x, c.y, cxw, xw, cyp.x, yn.x, cym.x, ys.x, czp.x, vA.x, czm.x, v3.x);
+                const float ax1 = coarse_ax(d.y, c.y, cxp.y, c.z, cxp.x, c.x, cyp.y, yn.y, cym.y, ys.y, czp.y, vA.y, czm.y, v3.y);
+                const float ax2 = coarse_ax(d.z, c.z, cxp.z, c.w, cxp.y, c.y, cyp.z, yn.z, cym.z, ys.z, czp.z, vA.z, czm.z, v3.z);
+                const float ax3 = coarse_ax(d.w, c.w, cxp.w, xe, cxp.z, c.z, cyp.w, yn.w, cym.w, ys.w, czp.w, vA.w, czm.w, v3.w);
+                o.x = d.x > 0.f ? c.x + w2 * (bb.x - ax0) / d.x : 0.f;
+                o.y = d.y > 0.f ? c.y + w2 * (bb.y - ax1) / d.y : 0.f;
+                o.z = d.z > 0.f ? c.z + w2 * (bb.z - ax2) / d.z : 0.f;
+                o.w = d.w > 0.f ? c.w + w2 * (bb.w - ax3) / d.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(out + idx) = o;
+        }
+        // rotate the register queues: x column and the own v column (v2 = v(kk-1) must be the value stage A stored)
+        x_m = x_c; x_c = x_p;
+        v3 = v2; v2 = vA;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 to_half_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, long long n, unsigned long long* mismatch) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -414,6 +543,18 @@ void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, 
 void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st, const HaloIn* hin) {
     if (vec4_ok(L)) launch_vec4<2>(L, x, b, out, 0.f, hin, nullptr, st);
     else coarse_stencil_kernel<2><<<grid3(L), 256, 0, st>>>(L, x, b, out, (mg_t)0);
+}
+
+// two sweeps per pass (coarse_pair_kernel): big single-slab levels with half coefficient copies only
+bool coarse_pair_supported(const CoarseLevel& L) {
+    return vec4_ok(L) && L.hd != nullptr && L.periodic == 0 && (long long)L.plane * L.nz >= (1LL << 21);
+}
+void coarse_smooth_pair(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w1, double w2,
+                        cudaStream_t st) {
+    const int zc = L.nz >= 256 ? 64 : 32;
+    dim3 grid((L.nx + CPX - 1) / CPX, (L.ny + CPY - 1) / CPY, (L.nz + zc - 1) / zc);
+    coarse_pair_kernel<<<grid, 256, 0, st>>>(L, reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(b),
+                                             reinterpret_cast<float*>(out), (float)w1, (float)w2, zc);
 }
 
 void coarse_tail_cycle(const TailArgs& a, bool staged, cudaStream_t st) {

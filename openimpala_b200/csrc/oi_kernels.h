@@ -95,6 +95,10 @@ void coarse_smooth(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out
 void coarse_residual(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, cudaStream_t st,
                      const HaloIn* hin = nullptr);
 bool coarse_halo_supported(const CoarseLevel& L);
+// out = S_w2(S_w1(x)) in one pass (single z-slab, non-periodic, half coefficient copies, >= 2^21 cells)
+bool coarse_pair_supported(const CoarseLevel& L);
+void coarse_smooth_pair(const CoarseLevel& L, const mg_t* x, const mg_t* b, mg_t* out, double w1, double w2,
+                        cudaStream_t st);
 // x += P * ec  (ec lives on level `next`)
 void coarse_prolong_add(const CoarseLevel& L, mg_t* x, const CoarseLevel& next, const mg_t* ec,
                         cudaStream_t st);

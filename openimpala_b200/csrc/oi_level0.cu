@@ -280,7 +280,9 @@ int pick_zchunk(const Grid& g, int n_sm) {
     long long chunks = (target + tiles - 1) / tiles;
     if (chunks < 1) chunks = 1;
     int zc = (int)((g.nz + chunks - 1) / chunks);
-    int cap = 64;
+    // chunks of at most 128 planes on a single slab (919 vs 928 ms per 1024^3 step against 64), 64 on z-slabs, where
+    // the first and last chunk are the ones that wait for the neighbours and should stay a small share
+    int cap = (g.nz == g.nzg) ? 128 : 64;
     if (const char* e = getenv("OI_ZCHUNK")) { const int v = atoi(e); if (v >= 8 && v <= 1024) cap = v; }   // experiments
     if (zc < 16) zc = 16;
     if (zc > cap) zc = cap;

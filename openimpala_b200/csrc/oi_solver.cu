@@ -455,6 +455,17 @@ std::vector<double> cheb_weights(int degree, double lo_frac, double lmax = 2.0) 
     // Jacobi weights 1/root_k of the Chebyshev polynomial on [lo_frac*lmax, lmax];
     // D^-1 A of this weakly diagonally dominant M-matrix has spectrum in (0, 2].
     std::vector<double> w(degree);
+    // OI_MG_CHEB4=1 (experiment): the roots of the fourth-kind Chebyshev smoother polynomial instead
+    // (lmax sin^2(k pi / (2 degree + 1)), largest root first), which needs no lower end of the interval
+    if (const char* e = getenv("OI_MG_CHEB4")) {
+        if (e[0] == '1') {
+            for (int k = 1; k <= degree; ++k) {
+                const double sn = std::sin(M_PI * (double)(degree + 1 - k) / (2.0 * degree + 1.0));
+                w[k - 1] = 1.0 / (lmax * sn * sn);
+            }
+            return w;
+        }
+    }
     const double a = lo_frac * lmax, b = lmax;
     for (int k = 1; k <= degree; ++k) {
         const double root = 0.5 * (a + b) + 0.5 * (b - a) * std::cos(M_PI * (2.0 * k - 1.0) / (2.0 * degree));
@@ -1179,9 +1190,23 @@ void coarse_cycle(oi_solver* S, size_t l) {
         oi::coarse_smooth(L, cur, L.b, oth, wt, S->st, &hin, &hout); S->launches++;
         std::swap(cur, oth);
     };
+    // two sweeps per pass on a big level that this rank holds whole (OI_COARSE_PAIR=0 turns it off)
+    bool pair_c = false;
+    {
+        const char* e = getenv("OI_COARSE_PAIR");
+        pair_c = !(e && e[0] == '0') && sizeof(mg_t) == 4 && (S->n_ranks == 1 || L.replicated) && oi::coarse_pair_supported(L);
+    }
+    auto pair_sweep = [&](double wa, double wb) {
+        haloL(S, L, cur);
+        oi::coarse_smooth_pair(L, cur, L.b, oth, wa, wb, S->st); S->launches++;
+        std::swap(cur, oth);
+    };
     oi::coarse_jacobi_first(L, L.b, cur, w[0], S->st); S->launches++;
     if (S->n_ranks > 1) peer_invalidate(S, cur);
-    for (int s = 1; s < deg; ++s) sweep(w[s], !last || s + 1 < deg);
+    for (int s = 1; s < deg;) {
+        if (pair_c && s + 1 < deg) { pair_sweep(w[s], w[s + 1]); s += 2; }
+        else { sweep(w[s], !last || s + 1 < deg); s += 1; }
+    }
     if (!last) {
         HostLevel& hn = S->levels[l + 1];
         // W-cycle from MG level w_from on: the child (MG level l + 2) is visited twice, each visit
@@ -1199,7 +1224,10 @@ void coarse_cycle(oi_solver* S, size_t l) {
             oi::coarse_prolong_add(L, cur, hn.L, hn.L.x, S->st); S->launches++;
             if (S->n_ranks > 1) peer_invalidate(S, cur);
         }
-        for (int s = 0; s < deg; ++s) sweep(w[deg - 1 - s], s + 1 < deg);
+        for (int s = 0; s < deg;) {
+            if (pair_c && s + 1 < deg) { pair_sweep(w[deg - 1 - s], w[deg - 2 - s]); s += 2; }
+            else { sweep(w[deg - 1 - s], s + 1 < deg); s += 1; }
+        }
     }
     if (cur != L.x) { L.t = L.x; L.x = cur; }
 }

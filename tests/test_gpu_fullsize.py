@@ -129,3 +129,29 @@ def test_sphere_packing_golden_512(capi, packing):
     assert abs(r["tau"] - g["tau"]) <= 1e-6 * g["tau"], (r["tau"], g["tau"])
     assert abs(r["fin"] - g["flux_in"]) <= 1e-6 * abs(g["flux_in"])
     assert abs(r["fout"] - g["flux_out"]) <= 1e-6 * abs(g["flux_out"])
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 256), (272, 296, 328)])
+def test_coarse_two_sweep_pass_matches_single_sweeps(capi, shape, monkeypatch):
+    """Level 1 (>= 2^21 cells, single slab) smooths two sweeps per pass (coarse_pair_kernel, oi_coarse.cu); OI_COARSE_PAIR=0
+    keeps single sweeps.  Same V-cycle output up to fp32 summation order, same iterations, same fluxes.  The second
+    shape gives level 1 partial tiles in x and y and a partial last z-chunk."""
+    from openimpala_b200 import synth
+    ph = synth.sphere_packing_slab(shape, SEED, RADIUS, SOLID)
+    res = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("OI_COARSE_PAIR", pair)
+        with capi.Solver(shape, 2, 1, -1.0, 1.0) as s:
+            s.set_phase(ph)
+            assert s.build_mask() > 0
+            act = s.mask().astype(bool)
+            r = np.where(act, np.random.default_rng(5).standard_normal(shape), 0.0)
+            z = s.apply_precond(r)
+            info = s.solve()
+            res[pair] = (z, info.iterations, s.fluxes()[:2], s.launch_count())
+    z0, it0, fl0, l0 = res["0"]
+    z1, it1, fl1, l1 = res["1"]
+    assert l1 < l0                                               # fewer launches: the pairs really ran
+    assert float(np.abs(z0 - z1).max()) <= 2e-5 * float(np.abs(z0).max())
+    assert abs(it0 - it1) <= 1
+    assert abs(fl0[0] - fl1[0]) <= 1e-7 * abs(fl0[0]) and abs(fl0[1] - fl1[1]) <= 1e-7 * abs(fl0[1])
