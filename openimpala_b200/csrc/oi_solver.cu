@@ -421,6 +421,7 @@ struct oi_solver {
     int w_from = 0;                    // OI_MG_W_FROM=L: MG levels >= L are visited twice per visit of their parent (W-cycle); 0 = V-cycle
     int fx0 = 1, fy0 = 1, fz0 = 1;     // coarsening factors level 0 -> MG level 1
     int tail_level = -1;               // levels[tail_level ..] are cycled by the one-CTA tail kernel (-1: none)
+    long long tail_cells = 4096;       // size limit of the tail's first level (OI_TAIL_CELLS)
     // One PCG iteration captured as a CUDA graph (single slab): [0] with r.z in scalar slot 0,
     // [1] with r.z in slot 3 (the two slots swap every iteration).  `launches` = kernel nodes.
     struct IterGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
@@ -455,16 +456,18 @@ std::vector<double> cheb_weights(int degree, double lo_frac, double lmax = 2.0) 
     // Jacobi weights 1/root_k of the Chebyshev polynomial on [lo_frac*lmax, lmax];
     // D^-1 A of this weakly diagonally dominant M-matrix has spectrum in (0, 2].
     std::vector<double> w(degree);
-    // OI_MG_CHEB4=1 (experiment): the roots of the fourth-kind Chebyshev smoother polynomial instead
-    // (lmax sin^2(k pi / (2 degree + 1)), largest root first), which needs no lower end of the interval
-    if (const char* e = getenv("OI_MG_CHEB4")) {
-        if (e[0] == '1') {
-            for (int k = 1; k <= degree; ++k) {
-                const double sn = std::sin(M_PI * (double)(degree + 1 - k) / (2.0 * degree + 1.0));
-                w[k - 1] = 1.0 / (lmax * sn * sn);
-            }
-            return w;
+    // Default since round 2: the roots of the FOURTH-kind Chebyshev smoother polynomial, lmax sin^2(k pi / (2 degree +
+    // 1)) (largest root first) -- the polynomial that minimises the multigrid smoothing bound rather than the maximum
+    // over an interval whose lower end has to be guessed (Lottes, "Optimal polynomial smoothers for multigrid V-cycles",
+    // 2022).  1024^3: 17 -> 16 iterations at equal cost per iteration (profiles/r2_degree_sweep.md).  OI_MG_CHEB4=0:
+    // first-kind roots on [lo_frac lmax, lmax] as in round 1.
+    const char* c4 = getenv("OI_MG_CHEB4");
+    if (!(c4 && c4[0] == '0')) {
+        for (int k = 1; k <= degree; ++k) {
+            const double sn = std::sin(M_PI * (double)(degree + 1 - k) / (2.0 * degree + 1.0));
+            w[k - 1] = 1.0 / (lmax * sn * sn);
         }
+        return w;
     }
     const double a = lo_frac * lmax, b = lmax;
     for (int k = 1; k <= degree; ++k) {
@@ -867,6 +870,7 @@ void plan_hierarchy(oi_solver* S) {
         const bool on = e ? (e[0] == '1') : (OI_TAIL_DEFAULT && S->n_ranks == 1);
         long long cells = 4096;
         if (const char* c = getenv("OI_TAIL_CELLS")) cells = std::atoll(c);
+        S->tail_cells = cells;
         if (on && cells > 0) {
             const int nl = (int)lv.size();
             for (int l = 0; l < nl; ++l) {
@@ -1166,7 +1170,10 @@ void coarse_cycle(oi_solver* S, size_t l) {
         return;
     }
     const bool last = (l + 1 == S->levels.size());
-    const std::vector<double>& w = last ? S->w_coarse : ((l == 0 && !S->w_l1.empty()) ? S->w_l1 : S->w_mid);
+    // MG level 1 has its own (lower) degree when it is a big level; a level 1 small enough for the one-CTA tail
+    // smooths like the levels below it, whether the tail is in use or not
+    const bool own_l1 = l == 0 && !S->w_l1.empty() && (long long)L.plane * L.nzg > S->tail_cells;
+    const std::vector<double>& w = last ? S->w_coarse : (own_l1 ? S->w_l1 : S->w_mid);
     const int deg = (int)w.size();
     mg_t* cur = L.t;
     mg_t* oth = L.x;
@@ -1190,11 +1197,14 @@ void coarse_cycle(oi_solver* S, size_t l) {
         oi::coarse_smooth(L, cur, L.b, oth, wt, S->st, &hin, &hout); S->launches++;
         std::swap(cur, oth);
     };
-    // two sweeps per pass on a big level that this rank holds whole (OI_COARSE_PAIR=0 turns it off)
+    // Two sweeps per pass on a big level that this rank holds whole: opt-in (OI_COARSE_PAIR=1).  Parity-tested
+    // (test_coarse_two_sweep_pass_matches_single_sweeps) but measured SLOWER than single sweeps at 1024^3 (51.36 vs
+    // 50.43 ms per iteration): with its rim recomputed from global memory and 76 registers the kernel is latency
+    // bound, and the single sweep already runs at three quarters of the bandwidth roofline on 20 B per cell.
     bool pair_c = false;
     {
         const char* e = getenv("OI_COARSE_PAIR");
-        pair_c = !(e && e[0] == '0') && sizeof(mg_t) == 4 && (S->n_ranks == 1 || L.replicated) && oi::coarse_pair_supported(L);
+        pair_c = (e && e[0] == '1') && sizeof(mg_t) == 4 && (S->n_ranks == 1 || L.replicated) && oi::coarse_pair_supported(L);
     }
     auto pair_sweep = [&](double wa, double wb) {
         haloL(S, L, cur);
@@ -2134,9 +2144,13 @@ int oi_create(oi_solver** out, const oi_params* p) {
         if (const char* e = getenv("OI_MG_LOC")) { const double v = std::atof(e); if (v > 0.0 && v < 1.0) loc = v; }   // experiments
         S->w_mid = cheb_weights(dc, loc);
         if (const char* e = getenv("OI_MG_W_FROM")) S->w_from = std::max(0, std::atoi(e));
-        if (const char* e = getenv("OI_MG_DEG_L1")) {
-            const int d1 = std::atoi(e);
-            if (d1 >= 1 && d1 <= 16) S->w_l1 = cheb_weights(d1, d1 <= 8 ? lo_tab[d1] : 0.05);
+        // MG level 1 (1/8 of the cells, but bandwidth bound like level 0) smooths with degree 4, the small levels
+        // below it with degree 8: 17 iterations at 1024^3 for level-1 degree 4, 5 or 6 (16 at 8), 45.7 vs 50.5 ms per
+        // iteration -> 840 vs 871 ms per step (profiles/r2_degree_sweep.md).  OI_MG_DEG_L1=n.
+        {
+            int d1 = 4;
+            if (const char* e = getenv("OI_MG_DEG_L1")) d1 = std::atoi(e);
+            if (d1 >= 1 && d1 <= 16 && d1 != dc) S->w_l1 = cheb_weights(d1, d1 <= 8 ? lo_tab[d1] : 0.05);
         }
         CUDA_CHECK(cmalloc(&S->d_scal, 16 * sizeof(double)));
         CUDA_CHECK(cudaMemsetAsync(S->d_scal, 0, 16 * sizeof(double), S->st));

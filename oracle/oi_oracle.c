@@ -507,7 +507,7 @@ void oo_effdiff_gradient_sums(const double* chi, const int32_t* phase, int32_t p
  * baseline than Jacobi-PCG.  Coarse operators: 2x2x2 aggregation, couplings summed
  * over coarse faces and scaled by 1/2 (the rediscretisation-equivalent operator),
  * diagonal = outward couplings + sink terms; smoother: Jacobi with the reciprocals
- * of the Chebyshev roots as weights (degree d0 on level 0, dc below), mirrored
+ * of the fourth-kind Chebyshev roots as weights (degree d0 on level 0, 4 on level 1, dc below), mirrored
  * before / after the coarse correction; coarsest level: 8 sweeps.
  * =========================================================================== */
 typedef struct {
@@ -518,10 +518,14 @@ typedef struct {
 
 static void mg_free(mg_level* L) { free(L->cx); free(L->cy); free(L->cz); free(L->dg); free(L->x); free(L->b); free(L->t); }
 
+/* Jacobi weights = reciprocals of the roots of the fourth-kind Chebyshev smoother polynomial on (0, 2]
+ * (oi_solver.cu cheb_weights, the GPU arm's default), largest root first */
 static void mg_cheb(int deg, double lo_frac, double* w) {
-    const double a = lo_frac * 2.0, b = 2.0;
-    for (int k = 1; k <= deg; ++k)
-        w[k - 1] = 1.0 / (0.5 * (a + b) + 0.5 * (b - a) * cos(3.14159265358979323846 * (2.0 * k - 1.0) / (2.0 * deg)));
+    (void)lo_frac;
+    for (int k = 1; k <= deg; ++k) {
+        const double sn = sin(3.14159265358979323846 * (double)(deg + 1 - k) / (2.0 * deg + 1.0));
+        w[k - 1] = 1.0 / (2.0 * sn * sn);
+    }
 }
 
 /* out = x + w (b - A x) / dg  (res == 1: out = b - A x; res == 2: out = A x);  x == NULL means a zero guess */
@@ -599,11 +603,13 @@ static void mg_prolong_add(const mg_level* F, double* x, const mg_level* C) {
 }
 
 /* L[l].x = M^-1 L[l].b by one V-cycle (zero initial guess); w0: level-0 weights, wm: levels below, wc: coarsest */
+static const double* g_w1 = NULL;   /* level-1 weights (degree g_d1), set by oo_solve_mgpcg */
+static int g_d1 = 0;
 static void mg_vcycle(mg_level* L, int l, int nl, const double* w0, int d0, const double* wm, int dm, const double* wc, int dc) {
     mg_level* A = &L[l];
     const int last = (l + 1 == nl);
-    const double* w = last ? wc : (l == 0 ? w0 : wm);
-    const int deg = last ? dc : (l == 0 ? d0 : dm);
+    const double* w = last ? wc : (l == 0 ? w0 : (l == 1 && g_w1 ? g_w1 : wm));
+    const int deg = last ? dc : (l == 0 ? d0 : (l == 1 && g_w1 ? g_d1 : dm));
     double *cur = A->x, *oth = A->t, *tmp;
     mg_sweep(A, NULL, A->b, cur, w[0], 0);
     for (int s = 1; s < deg; ++s) { mg_sweep(A, cur, A->b, oth, w[s], 0); tmp = cur; cur = oth; oth = tmp; }
@@ -630,6 +636,9 @@ int oo_solve_mgpcg(const uint8_t* mask, int nx, int ny, int nz, int dir, double 
     if (dc > 16) dc = 16;
     static const double lo_tab[] = {0.4, 0.4, 0.25, 0.2, 0.10, 0.05, 0.05, 0.05, 0.05};     /* as oi_solver.cu */
     double w0[16], wm[16], wc[8];
+    static double w1[16];
+    mg_cheb(4, 0.1, w1);                 /* MG level 1: degree 4, as the GPU arm's default */
+    g_w1 = w1; g_d1 = 4;
     mg_cheb(d0, d0 <= 8 ? lo_tab[d0] : 0.07, w0);
     mg_cheb(dc, dc <= 8 ? lo_tab[dc] : 0.07, wm);
     mg_cheb(8, 0.05, wc);

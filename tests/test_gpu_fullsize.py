@@ -133,8 +133,8 @@ def test_sphere_packing_golden_512(capi, packing):
 
 @pytest.mark.parametrize("shape", [(256, 256, 256), (272, 296, 328)])
 def test_coarse_two_sweep_pass_matches_single_sweeps(capi, shape, monkeypatch):
-    """Level 1 (>= 2^21 cells, single slab) smooths two sweeps per pass (coarse_pair_kernel, oi_coarse.cu); OI_COARSE_PAIR=0
-    keeps single sweeps.  Same V-cycle output up to fp32 summation order, same iterations, same fluxes.  The second
+    """Level 1 (>= 2^21 cells, single slab) can smooth two sweeps per pass (coarse_pair_kernel, oi_coarse.cu;
+    OI_COARSE_PAIR=1, opt-in because it measured slower than the single sweeps it replaces).  Same V-cycle output up to fp32 summation order, same iterations, same fluxes.  The second
     shape gives level 1 partial tiles in x and y and a partial last z-chunk."""
     from openimpala_b200 import synth
     ph = synth.sphere_packing_slab(shape, SEED, RADIUS, SOLID)
