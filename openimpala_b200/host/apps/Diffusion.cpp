@@ -390,8 +390,6 @@ int main(int argc, char* argv[]) {
         }
         if (method != "flow_through" && method != "homogenization" && method != "skip_if_rev")
             amrex::Abort("Invalid calculation_method: '" + method + "'. Use homogenization, flow_through or skip_if_rev.");
-        if (amrex::ParallelDescriptor::NProcs() > 1 && method != "flow_through")
-            amrex::Abort("More than one rank (z-slabs over several GPUs) runs calculation_method = flow_through in this build.");
         if (method == "skip_if_rev") {                      // reference :507: no full-domain calculation
             amrex::Print() << std::endl << "Total run time (seconds) = " << (amrex::second() - t_start) << std::endl;
             amrex::Finalize();
@@ -405,6 +403,8 @@ int main(int argc, char* argv[]) {
             int check_host_tensor = 0;
             amrex::ParmParse pp_b200("b200");
             pp_b200.query("check_host_tensor", check_host_tensor);
+            if (check_host_tensor && amrex::ParallelDescriptor::NProcs() > 1)
+                amrex::Abort("b200.check_host_tensor needs the whole corrector fields on one rank");
             const auto st_eff = static_cast<OpenImpala::EffectiveDiffusivityHypre::SolverType>(stringToSolverType(solver_str));
             amrex::Real Deff[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
             const long long n_total = domain.numPts();
@@ -448,7 +448,8 @@ int main(int argc, char* argv[]) {
                 }
                 // (the reference prints the tensor only; the file is an addition of this build)
                 const std::filesystem::path out_path = results_dir / output_filename;
-                std::ofstream out(out_path);
+                std::ofstream out;
+                if (amrex::ParallelDescriptor::IOProcessor()) out.open(out_path);
                 if (out.is_open()) {
                     out << "# Effective Diffusivity Results (Homogenization Method)\n";
                     out << "# Input File: " << filename << "\n";

@@ -61,15 +61,18 @@ EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom
             amrex::Abort("EffectiveDiffusivityHypre: this build solves the cell problem on a fully periodic "
                          "geometry (Diffusion.cpp:306-308); a non-periodic direction was requested.");
 
-    if (amrex::ParallelDescriptor::NProcs() > 1)
-        amrex::Abort("EffectiveDiffusivityHypre: the C++ class runs the cell problem on one rank in this build "
-                     "(the library solves it on z-slabs: openimpala_b200.effdiff, oi_params.comm)");
+    // this rank's z-slab of the BoxArray (reference: SPMD over MPI ranks, EffectiveDiffusivityHypre.H:55-63); one rank =
+    // the whole box.  The periodic wrap in z between the first and the last slab is the library's (peer / NCCL halo).
+    const int n_ranks = amrex::ParallelDescriptor::NProcs();
+    if (n_ranks > 1 && m_write_plotfile)
+        amrex::Abort("EffectiveDiffusivityHypre: write_plotfile is not supported on more than one rank in this build");
     // generateActiveMask (:213-330): phase == phase_id, ghosts by periodicity
     const amrex::Box& domain = m_geom.Domain();
+    const amrex::Box local = m_ba.localBox();
     m_mf_active_mask.setVal(0);
-    for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
-        for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
-            for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i)
+    for (int k = local.smallEnd(2); k <= local.bigEnd(2); ++k)
+        for (int j = local.smallEnd(1); j <= local.bigEnd(1); ++j)
+            for (int i = local.smallEnd(0); i <= local.bigEnd(0); ++i)
                 m_mf_active_mask(i, j, k, 0) = (mf_phase_input(i, j, k, 0) == m_phase_id) ? 1 : 0;
     m_mf_active_mask.FillBoundary(m_geom.periodicity());
 
@@ -77,13 +80,15 @@ EffectiveDiffusivityHypre::EffectiveDiffusivityHypre(const amrex::Geometry& geom
     oi_default_params(&p);
     p.problem = OI_PROBLEM_CELL;
     p.nx = domain.length(0); p.ny = domain.length(1); p.nz = domain.length(2);
-    p.z_begin = 0; p.nz_local = p.nz;
+    p.z_begin = local.smallEnd(2) - domain.smallEnd(2); p.nz_local = local.length(2);
+    p.comm = amrex::ParallelDescriptor::Communicator();
+    if (n_ranks > 1) p.device = amrex::ParallelDescriptor::LocalDevice();
     p.direction = static_cast<int>(m_dir_solve);
     p.phase_id = m_phase_id;
     for (int d = 0; d < 3; ++d) p.dx[d] = m_geom.CellSize(d);
     p.eps = m_eps; p.maxiter = m_maxiter; p.verbose = m_verbose;
     amrex::ParmParse pp_b200("b200");
-    pp_b200.query("device", p.device);
+    if (n_ranks <= 1) pp_b200.query("device", p.device);
     if (t_thread_device >= 0) p.device = t_thread_device;                 // setThreadDevice()
     pp_b200.query("mg_degree", p.mg_degree);
     pp_b200.query("stencil_variant", p.stencil_variant);
@@ -175,13 +180,14 @@ bool EffectiveDiffusivityHypre::solve() {
 void EffectiveDiffusivityHypre::getChiSolution(amrex::MultiFab& chi_field) {
     chi_field.setVal(0.0);
     if (m_solver && m_converged && m_num_active > 0) {                    // :631-637: zero if not converged
-        const amrex::Box& domain = m_geom.Domain();
-        std::vector<double> x((size_t)domain.numPts());
+        // this rank's slab of the corrector field (the whole box on one rank)
+        const amrex::Box local = m_ba.localBox();
+        std::vector<double> x((size_t)local.numPts());
         oi_check(oi_get_solution(m_solver, x.data()), "oi_get_solution");
         size_t n = 0;
-        for (int k = domain.smallEnd(2); k <= domain.bigEnd(2); ++k)
-            for (int j = domain.smallEnd(1); j <= domain.bigEnd(1); ++j)
-                for (int i = domain.smallEnd(0); i <= domain.bigEnd(0); ++i) chi_field(i, j, k, 0) = x[n++];
+        for (int k = local.smallEnd(2); k <= local.bigEnd(2); ++k)
+            for (int j = local.smallEnd(1); j <= local.bigEnd(1); ++j)
+                for (int i = local.smallEnd(0); i <= local.bigEnd(0); ++i) chi_field(i, j, k, 0) = x[n++];
     }
     if (chi_field.nGrow() > 0) chi_field.FillBoundary(m_geom.periodicity());           // :742-744
 }

@@ -677,6 +677,31 @@ def test_diffusion_app_on_several_ranks(host_bins, ranks, tmp_path):
 
 
 @pytest.mark.gpu
+def test_diffusion_homogenization_on_two_ranks(host_bins, tmp_path):
+    """The app's default method on z-slabs: `EffectiveDiffusivityHypre` takes this rank's slab from the BoxArray
+    and the rank's communicator (reference: SPMD over MPI ranks, EffectiveDiffusivityHypre.H:55-63); the periodic wrap
+    in z between the last and the first slab and the reduction of the gradient sums are the library's.  The D_eff
+    tensor of two ranks (ragged slabs of 64 + 36 planes) must equal the one-rank tensor."""
+    from openimpala_b200 import capi
+    if capi.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    common = ("filename=SampleData_2Phase_stack_3d_1bit.tif", "data_path=tests/golden/", "phase_id=1", "verbose=0")
+    out1, out2 = tmp_path / "one", tmp_path / "two"
+    run("Diffusion", *common, f"results_path={out1}")
+    run("Diffusion", *common, f"results_path={out2}", "b200.ranks=2")
+
+    def parse(path):
+        txt = open(os.path.join(path, "results.txt")).read()
+        return {k: float(v) for k, v in re.findall(r"^(Deff_[xyz][xyz]): (\S+)$", txt, flags=re.M)}
+    a, b = parse(out1), parse(out2)
+    assert len(a) == 9 and list(a) == list(b)
+    gold = json.load(open(os.path.join(GOLDEN, "effdiff_golden.json")))["phase1"]["deff"]
+    assert abs(a["Deff_xx"] - gold[0][0]) <= 1e-6
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-8, (k, a[k], b[k])
+
+
+@pytest.mark.gpu
 def test_diffusion_write_plotfile(host_bins):
     """write_plotfile = 1 (Diffusion.cpp:211, 696 -> TortuosityHypre.cpp:710-745): the solution,
     the phase ids and the percolation mask as <results_path>/tortuosity_solution_<dir>."""
