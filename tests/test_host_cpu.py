@@ -366,3 +366,61 @@ def test_cpp_slab_rule_equals_python_slab_partition(tmp_path):
         out = subprocess.run([str(exe), str(nz), str(n)], capture_output=True, text=True, check=True).stdout.split()
         got = [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(n)]
         assert got == capi.slab_partition(nz, n), (nz, n, got)
+
+
+def test_cpp_fields_hold_the_rank_slab_and_leave_z_ghosts_to_the_neighbours(tmp_path):
+    """SPMD stand-in (`OI_RANK` / `OI_WORLD_SIZE`): a field of a 2-rank run holds this rank's z-slab of the BoxArray,
+    `validCopy` is that slab, and FillBoundary wraps the periodic x / y ghosts inside the slab but leaves the z ghost
+    planes alone -- they belong to the neighbour ranks and are the library's to exchange (the homogenisation method
+    of `Diffusion b200.ranks=N` relies on exactly this)."""
+    import subprocess
+    from openimpala_b200 import capi
+    src = tmp_path / "slabfab.cpp"
+    src.write_text(r"""
+#include <AMReX.H>
+#include <cstdio>
+int main() {
+    using namespace amrex;
+    Box dom(IntVect(0, 0, 0), IntVect(7, 5, 99));
+    BoxArray ba(dom);
+    DistributionMapping dm(ba);
+    iMultiFab f(ba, dm, 1, 1);
+    const Box loc = ba.localBox();
+    f.setVal(-7);
+    for (int k = loc.smallEnd(2); k <= loc.bigEnd(2); ++k)
+        for (int j = 0; j <= 5; ++j)
+            for (int i = 0; i <= 7; ++i) f(i, j, k, 0) = i + 10 * j + 100 * k;
+    Periodicity per; per.p = {1, 1, 1};
+    f.FillBoundary(per);
+    int bad = 0;
+    const int k0 = loc.smallEnd(2), k1 = loc.bigEnd(2);
+    for (int k = k0; k <= k1; ++k)
+        for (int j = -1; j <= 6; ++j)
+            for (int i = -1; i <= 8; ++i) {
+                const int want = (i + 8) % 8 + 10 * ((j + 6) % 6) + 100 * k;
+                if (f(i, j, k, 0) != want) ++bad;
+            }
+    for (int j = -1; j <= 6; ++j)
+        for (int i = -1; i <= 8; ++i) {
+            if (f(i, j, k0 - 1, 0) != -7) ++bad;            // z ghosts untouched
+            if (f(i, j, k1 + 1, 0) != -7) ++bad;
+        }
+    const std::vector<int> v = f.validCopy(0);
+    if ((long long)v.size() != loc.numPts() || v.front() != 100 * k0 || v.back() != 7 + 50 + 100 * k1) ++bad;
+    std::printf("%d %d %d\n", k0, loc.length(2), bad);
+    return 0;
+}
+""")
+    exe = tmp_path / "slabfab"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "openimpala_b200", "host", "amrex_shim"),
+                    "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    parts = capi.slab_partition(100, 2)
+    for rank in (0, 1):
+        out = subprocess.run([str(exe)], capture_output=True, text=True, check=True,
+                             env={**os.environ, "OI_RANK": str(rank), "OI_WORLD_SIZE": "2"}).stdout.split()
+        assert (int(out[0]), int(out[1])) == parts[rank] and int(out[2]) == 0, (rank, out)
+    # one rank: the whole box, z ghosts wrapped as well
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True,
+                         env={k: v for k, v in os.environ.items() if k not in ("OI_RANK", "OI_WORLD_SIZE", "RANK", "WORLD_SIZE")}
+                         ).stdout.split()
+    assert (int(out[0]), int(out[1])) == (0, 100) and int(out[2]) == 2 * 8 * 10, out     # the two wrapped z ghost planes
